@@ -1,0 +1,246 @@
+/*
+ * panfeed_b200.h — C-ABI of the B200-native k-mer streaming hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json's north_star names:
+ * the two Python callables of the reference that are bound with
+ * functools.partial in /root/reference/panfeed/__main__.py:277-297 and invoked
+ * per cluster at __main__.py:351-356 (single process) or inside worker()/
+ * writer() at __main__.py:39-81:
+ *
+ *     cluster_cutter   /root/reference/panfeed/panfeed.py:23-113
+ *     pattern_hasher   /root/reference/panfeed/panfeed.py:132-235
+ *     init_presabs_vector              panfeed.py:16-20
+ *
+ * The reference has no FFI; every entry point below states which reference
+ * lines it replaces.  Plain pointers and sizes only: no torch, no CUDA types.
+ * One pf_ctx per GPU, driven by one host thread.  Every call returns PF_OK (0)
+ * or a negative pf_status; pf_last_error() gives the message.  The library
+ * never frees caller memory; result pointers are owned by the context and stay
+ * valid until the next pf_collect()/pf_destroy() on it.
+ *
+ * There is no CPU fallback: without a CUDA device pf_create() fails.
+ */
+#ifndef PANFEED_B200_H
+#define PANFEED_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_ABI_VERSION 1
+
+typedef enum pf_status {
+  PF_OK = 0,
+  PF_ERR_INVALID = -1,      /* bad argument / malformed batch              */
+  PF_ERR_CUDA = -2,         /* CUDA runtime error (no device, launch, ...) */
+  PF_ERR_NOMEM = -3,        /* host or device allocation failed            */
+  PF_ERR_UNSUPPORTED = -4,  /* e.g. k > 32                                 */
+  PF_ERR_STATE = -5,        /* call order violated                         */
+  PF_ERR_INTERNAL = -6      /* device-side watchdog / invariant violated   */
+} pf_status;
+
+typedef struct pf_ctx pf_ctx;
+
+/* Options bound into the two reference callables at __main__.py:277-297. */
+typedef struct pf_params {
+  uint32_t abi_version;          /* PF_ABI_VERSION                                  */
+  uint32_t k;                    /* -k/--kmer-length, 1..32 (64-bit 2-bit path)      */
+  uint32_t n_samples;            /* S = number of strain columns of the panaroo CSV */
+  uint32_t canonical;            /* 1 unless --non-canonical (panfeed.py:69-88)     */
+  uint32_t consider_missing;     /* --consider-missing (panfeed.py:16-20,192-196)   */
+  uint32_t cluster_equal_filter; /* 1 iff --no-filter GIVEN: the reference runs the
+                                    "same as cluster" filter only when patfilt is
+                                    False (panfeed.py:202-204, __main__.py:292)     */
+  uint32_t emit_positions;       /* 1 if any --targets strain exists (panfeed.py:90)*/
+  uint32_t sort_bits;            /* 0 = auto; else number of leading bits of the
+                                    mixed key the radix sort orders (multiple of 8,
+                                    8..64); the rest is resolved exactly in K3     */
+  double   maf;                  /* --maf, compared in float64 exactly as
+                                    panfeed.py:190-200 (see pf_maf_window)          */
+} pf_params;
+
+/* One cut, gene-oriented sequence = one reference Seqinfo (classes.py:11-18,
+ * built at input.py:455-459).  Bases live in the packed plane. */
+typedef struct pf_seq_desc {
+  uint64_t base_off;  /* index of the first base in the packed plane; multiple of 64 */
+  uint32_t len;       /* number of bases                                              */
+  uint32_t cluster;   /* batch-local cluster index; non-decreasing over the array     */
+  uint32_t sample;    /* rank of the strain in sorted(strains) (panfeed.py:47-48);
+                         non-decreasing inside a cluster                              */
+  uint32_t flags;     /* PF_SEQ_* */
+  int32_t  start;     /* Seqinfo.start (1-based contig coordinate of the cut window)  */
+  int32_t  end;       /* Seqinfo.end                                                  */
+  int32_t  offset;    /* Seqinfo.offset (upstream bases actually included)            */
+  int32_t  strand;    /* +1 / -1                                                      */
+  uint64_t amb_off;   /* if PF_SEQ_AMBIGUOUS: index of this sequence's first base in
+                         the 4-bit plane (multiple of 32)                              */
+} pf_seq_desc;        /* 48 bytes */
+
+#define PF_SEQ_TARGET    1u  /* strain in --targets: emit positional records (panfeed.py:90-107) */
+#define PF_SEQ_AMBIGUOUS 2u  /* sequence holds non-ACGT symbols (N / IUPAC)                       */
+
+/* 4-bit symbol codes of the ambiguous plane: rank in ASCII order, so that the
+ * unsigned comparison of packed k-mers equals the reference's string "<=". */
+#define PF_AMB_ALPHABET "ABCDGHKMNRSTVWXY"
+
+typedef struct pf_cluster_desc {
+  uint32_t id;        /* caller's cluster number, echoed in result rows */
+  uint32_t reserved;
+} pf_cluster_desc;
+
+/* One batch of whole gene clusters = the items iter_gene_clusters yields
+ * (input.py:468) for those clusters. */
+typedef struct pf_batch {
+  const uint64_t*        packed_bases;   /* 2-bit plane: base i in word i>>5 at bits
+                                            [63-2*(i&31)-1, 63-2*(i&31)], A=0 C=1 G=2 T=3 */
+  uint64_t               n_words;        /* length of packed_bases                         */
+  const pf_seq_desc*     seqs;
+  uint32_t               n_seqs;
+  const pf_cluster_desc* clusters;
+  uint32_t               n_clusters;
+  const uint32_t*        cluster_presence; /* n_clusters x pf_pattern_words(S) words: bit
+                                              (s&31) of word (s>>5) = clusterpresab[s]
+                                              (input.py:371-377)                          */
+  const uint64_t*        amb_codes;      /* 4-bit plane (16 symbols per word, first symbol
+                                            in the top nibble) for PF_SEQ_AMBIGUOUS
+                                            sequences; NULL if none                        */
+  uint64_t               n_amb_words;
+} pf_batch;
+
+/* Result of one batch.  Rows are the lines pattern_hasher writes to
+ * kmers_to_hashes (panfeed.py:177,208); patterns the lines it writes to
+ * hashes_to_patterns (panfeed.py:187,223); positional records the lines
+ * cluster_cutter formats for kmers.tsv (panfeed.py:104-107). */
+typedef struct pf_batch_result {
+  /* k-mer rows that survived the MAF / same-as-cluster filters (U') */
+  uint64_t        n_rows;
+  const uint32_t* row_cluster;     /* pf_cluster_desc.id                                   */
+  const uint64_t* row_kmer;        /* 2-bit k-mer, first base in the top used bits          */
+  const uint32_t* row_count;       /* number of samples carrying it                         */
+  const uint32_t* row_pattern;     /* index into the context's k-mer pattern pool           */
+  /* rows whose k-mer holds N/IUPAC symbols (128-bit keys, 4 bits per symbol) */
+  uint64_t        n_wide_rows;
+  const uint32_t* wide_row_cluster;
+  const uint64_t* wide_row_kmer;   /* 2 words per row: [hi, lo]                             */
+  const uint32_t* wide_row_count;
+  const uint32_t* wide_row_pattern;
+  /* the cluster's own row ("idx\t\tid", panfeed.py:175-187) */
+  uint32_t        n_clusters;
+  const uint32_t* cluster_pattern; /* index into the cluster pattern pool (int64 namespace) */
+  /* patterns first seen in this batch, appended to the pools in this order */
+  uint64_t        kmer_pattern_base;    /* pool index of the first new k-mer pattern        */
+  uint64_t        n_new_kmer_patterns;
+  const uint32_t* new_kmer_patterns;    /* n x pf_kmer_pattern_words(): presence words,
+                                           then (consider_missing only) one word = index of
+                                           the cluster pattern giving the NaN plane          */
+  uint64_t        cluster_pattern_base;
+  uint64_t        n_new_cluster_patterns;
+  const uint32_t* new_cluster_patterns; /* n x pf_pattern_words(S)                           */
+  /* positional records, one per k-mer instance of PF_SEQ_TARGET sequences */
+  uint64_t        n_pos;
+  const uint64_t* pos_kmer;        /* canonical mode: the canonical k-mer; else the forward one */
+  const uint32_t* pos_seq;         /* index into pf_batch.seqs                                   */
+  const int32_t*  pos_contig_start;/* contig_end  = contig_start + k (panfeed.py:91-99)          */
+  const int32_t*  pos_gene_start;  /* gene_end    = gene_start + k   (panfeed.py:101-102)        */
+  const uint8_t*  pos_flags;       /* bit0: reverse complement was the canonical one
+                                      (used_strand = -1); bit1: k-mer is ambiguous, then
+                                      pos_kmer holds an index into pos_wide_kmer              */
+  const uint64_t* pos_wide_kmer;   /* 2 words per ambiguous positional k-mer                  */
+  uint64_t        n_pos_wide;
+} pf_batch_result;
+
+typedef struct pf_stats {
+  uint64_t batches;
+  uint64_t bases;            /* N: sum of pf_seq_desc.len                           */
+  uint64_t instances;        /* M: k-mer records extracted                          */
+  uint64_t unique_kmers;     /* U: distinct (cluster, k-mer)                        */
+  uint64_t rows;             /* U'                                                  */
+  uint64_t kmer_patterns;    /* P (k-mer namespace)                                 */
+  uint64_t cluster_patterns; /* P (cluster namespace)                               */
+  uint32_t sort_passes;      /* radix passes used by the last batch                  */
+  uint32_t launches;         /* kernels launched by the last batch                   */
+  /* device time of the last batch, CUDA events on the context stream */
+  float ms_h2d, ms_extract, ms_sort, ms_reduce, ms_dedup, ms_d2h, ms_total;
+  uint64_t total_launches;   /* kernels launched since pf_create                     */
+} pf_stats;
+
+/* ---- lifetime ---- */
+int  pf_create(pf_ctx** out, int device, const pf_params* params);
+void pf_destroy(pf_ctx* ctx);
+const char* pf_last_error(const pf_ctx* ctx);   /* ctx may be NULL: create errors */
+int  pf_abi_version(void);
+
+/* ---- the hot path ---- */
+/* pf_submit = pf_upload + pf_execute.  Host buffers of the batch must stay
+ * valid until pf_upload returns (they are staged through pinned memory). */
+int pf_upload(pf_ctx* ctx, const pf_batch* batch);   /* validate, H2D, plan tiles   */
+int pf_execute(pf_ctx* ctx);                         /* K1..K4 on the resident batch */
+int pf_submit(pf_ctx* ctx, const pf_batch* batch);
+int pf_collect(pf_ctx* ctx, pf_batch_result* out);   /* sync + D2H                  */
+
+/* Forget all patterns (the `patterns = set()` reset of --multiple-files,
+ * panfeed.py:165; also used between benchmark repetitions). */
+int pf_reset_patterns(pf_ctx* ctx);
+
+/* ---- helpers that are part of the contract ---- */
+uint32_t pf_pattern_words(uint32_t n_samples);            /* ceil(S/32)               */
+uint32_t pf_kmer_pattern_words(const pf_ctx* ctx);        /* + 1 if consider_missing   */
+/* Integer window [lo, hi] of sample counts c that survive
+ *   af = c / n; if af >= 0.5: af = 1 - af; drop if af < maf
+ * evaluated in IEEE double exactly as panfeed.py:190-200.  Returns 0 and
+ * lo > hi if nothing survives. */
+int pf_maf_window(double maf, uint32_t n, uint32_t* lo, uint32_t* hi);
+/* Device-side pool access (full bitsets of every pattern seen so far). */
+int pf_patterns_export(pf_ctx* ctx, int cluster_namespace, uint64_t first,
+                       uint64_t count, uint32_t* host_out);
+int pf_stats_get(pf_ctx* ctx, pf_stats* out);
+/* CUDA stream the context launches on, as an opaque handle (cudaStream_t). */
+void* pf_stream(pf_ctx* ctx);
+
+/* ---- synthetic pangenome, generated on the device ---- */
+typedef struct pf_synth_params {
+  uint64_t seed;
+  uint32_t n_samples;
+  uint32_t n_clusters;       /* clusters in this batch                              */
+  uint32_t first_cluster;    /* global index of the first (for the RNG stream)      */
+  uint32_t gene_len;         /* ancestral length incl. flanks (e.g. 1200)           */
+  uint32_t n_founders;       /* 8                                                   */
+  float    founder_div;      /* 0.01                                                */
+  float    private_div;      /* 0.001                                               */
+  float    core_fraction;    /* 0.6: first fraction of clusters present w.p. 0.99   */
+  float    paralog_rate;     /* 0.01                                                */
+  uint32_t total_clusters;   /* C of the whole pangenome (core/accessory split)     */
+  uint32_t all_targets;      /* 1: flag every sequence PF_SEQ_TARGET                */
+} pf_synth_params;
+/* Sizes of the batch pf_synth_fill will write. */
+int pf_synth_plan(const pf_synth_params* p, uint32_t* n_seqs, uint64_t* n_words);
+/* Fill caller-provided HOST buffers (seqs, clusters, presence, packed bases)
+ * with a deterministic synthetic batch; bases are generated on `device`. */
+int pf_synth_fill(int device, const pf_synth_params* p, pf_seq_desc* seqs,
+                  pf_cluster_desc* clusters, uint32_t* presence,
+                  uint64_t* packed_bases);
+
+/* ---- multi-GPU global pattern dedup ----
+ * Clusters are sharded over ranks; the only global state is the reference's
+ * `patterns` set (__main__.py:70).  Owner of a pattern = hash(bitset) % world.
+ * The caller moves the buffers between ranks (NCCL all-to-all); all pointers
+ * in this group are DEVICE pointers owned by the caller. */
+int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t world,
+                     const uint32_t* mask_remap_dev, /* local->global cluster-pattern ids, or NULL */
+                     uint32_t* send_words_dev, uint64_t capacity_patterns,
+                     uint64_t* counts_host /* [world] */);
+int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace,
+                      const uint32_t* recv_words_dev, uint64_t n_recv,
+                      uint32_t* recv_unique_index_dev, uint64_t* n_unique_host);
+int pf_exchange_unique_export(pf_ctx* ctx, int cluster_namespace,
+                              uint32_t* host_out /* n_unique x words */);
+int pf_exchange_unpack(pf_ctx* ctx, int cluster_namespace,
+                       const uint32_t* returned_ids_dev, /* in send order */
+                       uint32_t* local_to_global_dev /* [n local patterns] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANFEED_B200_H */
