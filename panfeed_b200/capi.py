@@ -1,0 +1,323 @@
+"""ctypes binding of libpanfeed_b200.so (include/panfeed_b200.h).
+
+This is the binding a maintainer of the reference would add next to
+`/root/reference/panfeed/panfeed.py`.  There is no
+fallback: if the shared library is missing or no CUDA device exists the calls
+raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libpanfeed_b200.so")
+
+PF_ABI_VERSION = 1
+PF_SEQ_TARGET = 1
+PF_SEQ_AMBIGUOUS = 2
+AMB_ALPHABET = "ABCDGHKMNRSTVWXY"
+
+
+class PfError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"panfeed_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("k", C.c_uint32),
+                ("n_samples", C.c_uint32), ("canonical", C.c_uint32),
+                ("consider_missing", C.c_uint32),
+                ("cluster_equal_filter", C.c_uint32),
+                ("emit_positions", C.c_uint32), ("sort_bits", C.c_uint32),
+                ("maf", C.c_double)]
+
+
+SEQ_DTYPE = np.dtype([("base_off", "<u8"), ("len", "<u4"), ("cluster", "<u4"),
+                      ("sample", "<u4"), ("flags", "<u4"), ("start", "<i4"),
+                      ("end", "<i4"), ("offset", "<i4"), ("strand", "<i4"),
+                      ("amb_off", "<u8")])
+assert SEQ_DTYPE.itemsize == 48
+CLUSTER_DTYPE = np.dtype([("id", "<u4"), ("reserved", "<u4")])
+
+
+class Batch(C.Structure):
+    _fields_ = [("packed_bases", C.c_void_p), ("n_words", C.c_uint64),
+                ("seqs", C.c_void_p), ("n_seqs", C.c_uint32),
+                ("clusters", C.c_void_p), ("n_clusters", C.c_uint32),
+                ("cluster_presence", C.c_void_p),
+                ("amb_codes", C.c_void_p), ("n_amb_words", C.c_uint64)]
+
+
+class BatchResult(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64),
+                ("row_cluster", C.POINTER(C.c_uint32)),
+                ("row_kmer", C.POINTER(C.c_uint64)),
+                ("row_count", C.POINTER(C.c_uint32)),
+                ("row_pattern", C.POINTER(C.c_uint32)),
+                ("n_wide_rows", C.c_uint64),
+                ("wide_row_cluster", C.POINTER(C.c_uint32)),
+                ("wide_row_kmer", C.POINTER(C.c_uint64)),
+                ("wide_row_count", C.POINTER(C.c_uint32)),
+                ("wide_row_pattern", C.POINTER(C.c_uint32)),
+                ("n_clusters", C.c_uint32),
+                ("cluster_pattern", C.POINTER(C.c_uint32)),
+                ("kmer_pattern_base", C.c_uint64),
+                ("n_new_kmer_patterns", C.c_uint64),
+                ("new_kmer_patterns", C.POINTER(C.c_uint32)),
+                ("cluster_pattern_base", C.c_uint64),
+                ("n_new_cluster_patterns", C.c_uint64),
+                ("new_cluster_patterns", C.POINTER(C.c_uint32)),
+                ("n_pos", C.c_uint64),
+                ("pos_kmer", C.POINTER(C.c_uint64)),
+                ("pos_seq", C.POINTER(C.c_uint32)),
+                ("pos_contig_start", C.POINTER(C.c_int32)),
+                ("pos_gene_start", C.POINTER(C.c_int32)),
+                ("pos_flags", C.POINTER(C.c_uint8)),
+                ("pos_wide_kmer", C.POINTER(C.c_uint64)),
+                ("n_pos_wide", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("batches", C.c_uint64), ("bases", C.c_uint64),
+                ("instances", C.c_uint64), ("unique_kmers", C.c_uint64),
+                ("rows", C.c_uint64), ("kmer_patterns", C.c_uint64),
+                ("cluster_patterns", C.c_uint64), ("sort_passes", C.c_uint32),
+                ("launches", C.c_uint32), ("ms_h2d", C.c_float),
+                ("ms_extract", C.c_float), ("ms_sort", C.c_float),
+                ("ms_reduce", C.c_float), ("ms_dedup", C.c_float),
+                ("ms_d2h", C.c_float), ("ms_total", C.c_float),
+                ("total_launches", C.c_uint64)]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("n_samples", C.c_uint32),
+                ("n_clusters", C.c_uint32), ("first_cluster", C.c_uint32),
+                ("gene_len", C.c_uint32), ("n_founders", C.c_uint32),
+                ("founder_div", C.c_float), ("private_div", C.c_float),
+                ("core_fraction", C.c_float), ("paralog_rate", C.c_float),
+                ("total_clusters", C.c_uint32), ("all_targets", C.c_uint32)]
+
+
+EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
+           "pf_upload", "pf_execute", "pf_submit", "pf_collect",
+           "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
+           "pf_maf_window", "pf_patterns_export", "pf_stats_get", "pf_stream",
+           "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
+           "pf_exchange_dedup", "pf_exchange_unique_export",
+           "pf_exchange_unpack"]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PfError(-2, f"{LIB_PATH} is missing: build it with "
+                          "`make -C panfeed_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+    lib.pf_create.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(Params)]
+    lib.pf_destroy.argtypes = [vp]
+    lib.pf_destroy.restype = None
+    lib.pf_last_error.argtypes = [vp]
+    lib.pf_last_error.restype = C.c_char_p
+    lib.pf_upload.argtypes = [vp, C.POINTER(Batch)]
+    lib.pf_execute.argtypes = [vp]
+    lib.pf_submit.argtypes = [vp, C.POINTER(Batch)]
+    lib.pf_collect.argtypes = [vp, C.POINTER(BatchResult)]
+    lib.pf_reset_patterns.argtypes = [vp]
+    lib.pf_pattern_words.argtypes = [u32]
+    lib.pf_pattern_words.restype = u32
+    lib.pf_kmer_pattern_words.argtypes = [vp]
+    lib.pf_kmer_pattern_words.restype = u32
+    lib.pf_maf_window.argtypes = [C.c_double, u32, C.POINTER(u32), C.POINTER(u32)]
+    lib.pf_patterns_export.argtypes = [vp, C.c_int, u64, u64, vp]
+    lib.pf_stats_get.argtypes = [vp, C.POINTER(Stats)]
+    lib.pf_stream.argtypes = [vp]
+    lib.pf_stream.restype = vp
+    lib.pf_synth_plan.argtypes = [C.POINTER(SynthParams), C.POINTER(u32), C.POINTER(u64)]
+    lib.pf_synth_fill.argtypes = [C.c_int, C.POINTER(SynthParams), vp, vp, vp, vp]
+    lib.pf_exchange_pack.argtypes = [vp, C.c_int, u32, vp, vp, u64, C.POINTER(u64)]
+    lib.pf_exchange_dedup.argtypes = [vp, C.c_int, vp, u64, vp, C.POINTER(u64)]
+    lib.pf_exchange_unique_export.argtypes = [vp, C.c_int, vp]
+    lib.pf_exchange_unpack.argtypes = [vp, C.c_int, vp, vp]
+    if lib.pf_abi_version() != PF_ABI_VERSION:
+        raise PfError(-1, "ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def maf_window(maf, n):
+    lo, hi = C.c_uint32(), C.c_uint32()
+    ok = load().pf_maf_window(maf, n, C.byref(lo), C.byref(hi))
+    return (lo.value, hi.value) if ok else None
+
+
+def _np(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
+
+
+class HostBatch:
+    """Numpy-side image of a pf_batch (arrays must stay alive during upload)."""
+
+    def __init__(self, packed, seqs, clusters, presence, amb=None):
+        self.packed = np.ascontiguousarray(packed, dtype=np.uint64)
+        self.seqs = np.ascontiguousarray(seqs, dtype=SEQ_DTYPE)
+        self.clusters = np.ascontiguousarray(clusters, dtype=CLUSTER_DTYPE)
+        self.presence = np.ascontiguousarray(presence, dtype=np.uint32)
+        self.amb = None if amb is None else np.ascontiguousarray(amb, dtype=np.uint64)
+
+    def struct(self):
+        b = Batch()
+        b.packed_bases = self.packed.ctypes.data if self.packed.size else None
+        b.n_words = self.packed.size
+        b.seqs = self.seqs.ctypes.data if self.seqs.size else None
+        b.n_seqs = self.seqs.size
+        b.clusters = self.clusters.ctypes.data if self.clusters.size else None
+        b.n_clusters = self.clusters.size
+        b.cluster_presence = self.presence.ctypes.data if self.presence.size else None
+        if self.amb is not None and self.amb.size:
+            b.amb_codes = self.amb.ctypes.data
+            b.n_amb_words = self.amb.size
+        return b
+
+    @property
+    def n_bases(self):
+        return int(self.seqs["len"].sum())
+
+
+class Context:
+    """One pf_ctx: the reference's bound `iter_o` / `func_w` pair for one GPU."""
+
+    def __init__(self, k, n_samples, canonical=True, consider_missing=False,
+                 cluster_equal_filter=False, emit_positions=False, maf=0.01,
+                 sort_bits=0, device=0):
+        self.lib = load()
+        self.params = Params(PF_ABI_VERSION, k, n_samples, int(canonical),
+                             int(consider_missing), int(cluster_equal_filter),
+                             int(emit_positions), sort_bits, maf)
+        self.h = C.c_void_p()
+        rc = self.lib.pf_create(C.byref(self.h), device, C.byref(self.params))
+        if rc != 0:
+            raise PfError(rc, self.lib.pf_last_error(None).decode())
+        self.k, self.S = k, n_samples
+        self.W = self.lib.pf_pattern_words(n_samples)
+        self.Wk = self.lib.pf_kmer_pattern_words(self.h)
+        self.consider_missing = bool(consider_missing)
+        self.canonical = bool(canonical)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PfError(rc, self.lib.pf_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.pf_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, hb):
+        s = hb.struct()
+        self._check(self.lib.pf_upload(self.h, C.byref(s)))
+
+    def execute(self):
+        self._check(self.lib.pf_execute(self.h))
+
+    def submit(self, hb):
+        s = hb.struct()
+        self._check(self.lib.pf_submit(self.h, C.byref(s)))
+
+    def collect(self, copy=True):
+        r = BatchResult()
+        self._check(self.lib.pf_collect(self.h, C.byref(r)))
+        nr, nw = int(r.n_rows), int(r.n_wide_rows)
+        out = {
+            "row_cluster": _np(r.row_cluster, nr, np.uint32),
+            "row_kmer": _np(r.row_kmer, nr, np.uint64),
+            "row_count": _np(r.row_count, nr, np.uint32),
+            "row_pattern": _np(r.row_pattern, nr, np.uint32),
+            "wide_row_cluster": _np(r.wide_row_cluster, nw, np.uint32),
+            "wide_row_kmer": _np(r.wide_row_kmer, 2 * nw, np.uint64).reshape(-1, 2),
+            "wide_row_count": _np(r.wide_row_count, nw, np.uint32),
+            "wide_row_pattern": _np(r.wide_row_pattern, nw, np.uint32),
+            "cluster_pattern": _np(r.cluster_pattern, r.n_clusters, np.uint32),
+            "kmer_pattern_base": int(r.kmer_pattern_base),
+            "new_kmer_patterns": _np(r.new_kmer_patterns,
+                                     r.n_new_kmer_patterns * self.Wk,
+                                     np.uint32).reshape(-1, self.Wk),
+            "cluster_pattern_base": int(r.cluster_pattern_base),
+            "new_cluster_patterns": _np(r.new_cluster_patterns,
+                                        r.n_new_cluster_patterns * self.W,
+                                        np.uint32).reshape(-1, self.W),
+            "pos_kmer": _np(r.pos_kmer, r.n_pos, np.uint64),
+            "pos_seq": _np(r.pos_seq, r.n_pos, np.uint32),
+            "pos_contig_start": _np(r.pos_contig_start, r.n_pos, np.int32),
+            "pos_gene_start": _np(r.pos_gene_start, r.n_pos, np.int32),
+            "pos_flags": _np(r.pos_flags, r.n_pos, np.uint8),
+            "pos_wide_kmer": _np(r.pos_wide_kmer, 2 * r.n_pos_wide,
+                                 np.uint64).reshape(-1, 2),
+        }
+        return out
+
+    def reset_patterns(self):
+        self._check(self.lib.pf_reset_patterns(self.h))
+
+    def stats(self):
+        s = Stats()
+        self._check(self.lib.pf_stats_get(self.h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in Stats._fields_}
+
+    def export_patterns(self, cluster_namespace, first, count):
+        w = self.W if cluster_namespace else self.Wk
+        out = np.zeros((count, w), np.uint32)
+        self._check(self.lib.pf_patterns_export(self.h, int(cluster_namespace),
+                                                first, count, out.ctypes.data))
+        return out
+
+    def stream_handle(self):
+        return self.lib.pf_stream(self.h)
+
+
+def synth_batch(device, seed, n_samples, n_clusters, first_cluster=0,
+                total_clusters=None, gene_len=1200, n_founders=8,
+                founder_div=0.01, private_div=0.001, core_fraction=0.6,
+                paralog_rate=0.01, all_targets=False, pinned=False):
+    """Deterministic synthetic batch, bases generated on the
+    device and returned in host arrays."""
+    lib = load()
+    p = SynthParams(seed, n_samples, n_clusters, first_cluster, gene_len,
+                    n_founders, founder_div, private_div, core_fraction,
+                    paralog_rate, total_clusters or n_clusters,
+                    int(all_targets))
+    n_seqs, n_words = C.c_uint32(), C.c_uint64()
+    rc = lib.pf_synth_plan(C.byref(p), C.byref(n_seqs), C.byref(n_words))
+    if rc != 0:
+        raise PfError(rc, "pf_synth_plan failed")
+    W = lib.pf_pattern_words(n_samples)
+    seqs = np.zeros(n_seqs.value, SEQ_DTYPE)
+    clusters = np.zeros(n_clusters, CLUSTER_DTYPE)
+    presence = np.zeros((n_clusters, W), np.uint32)
+    if pinned:
+        import torch
+        packed = torch.empty(max(1, n_words.value), dtype=torch.int64,
+                             pin_memory=True).numpy().view(np.uint64)[:n_words.value]
+    else:
+        packed = np.zeros(n_words.value, np.uint64)
+    rc = lib.pf_synth_fill(device, C.byref(p), seqs.ctypes.data,
+                           clusters.ctypes.data, presence.ctypes.data,
+                           packed.ctypes.data)
+    if rc != 0:
+        raise PfError(rc, lib.pf_last_error(None).decode())
+    return HostBatch(packed, seqs, clusters, presence)

@@ -1,0 +1,1166 @@
+// libpanfeed_b200.so — C-ABI entry points (include/panfeed_b200.h) and the host
+// side of the pipeline: batch validation and planning, buffer management,
+// kernel sequencing on one CUDA stream, result staging.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/panfeed_b200.h"
+#include "k1_extract.cuh"
+#include "k2_onesweep.cuh"
+#include "k3_reduce.cuh"
+#include "k4_dedup.cuh"
+#include "synth.cuh"
+
+using namespace pf;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PatternSpace {
+  uint32_t key_words = 0;
+  DevBuf pool;            // n x key_words
+  uint64_t n = 0;         // committed patterns
+  DevBuf table;           // table_size x u32
+  uint32_t table_size = 0;
+  // exchange state
+  DevBuf x_owner, x_pos, x_perm, x_counts, x_unique;
+  uint64_t x_n_unique = 0;
+};
+
+struct WidthState {       // per key width (narrow u64 / wide Key128)
+  DevBuf keys[2], vals[2];
+  DevBuf tiles, seg_start, seg_hist, lookback;
+  PinBuf h_tiles, h_seg_start;
+  uint32_t n_tiles = 0;
+  uint32_t n_records = 0;
+  uint32_t n_runs = 0;
+  uint32_t n_rows = 0;
+  int sort_bits = 0, passes = 0;
+  int final_buf = 0;      // which of keys[]/vals[] holds the sorted records
+};
+
+enum Ev { EV_START, EV_EXTRACT, EV_SORT, EV_REDUCE, EV_DEDUP, EV_END, EV_COUNT };
+
+}  // namespace
+
+struct pf_ctx {
+  pf_params prm{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint32_t W = 0, Wk = 0;
+  std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> maf_cache;
+
+  // resident batch
+  bool have_batch = false, executed = false;
+  uint32_t n_seqs = 0, n_clusters = 0, n_wide_seqs = 0;
+  uint64_t n_words = 0, n_amb_words = 0, n_bases = 0;
+  uint32_t n_pos = 0, n_pos_wide = 0;
+  PinBuf h_seqs, h_clusters, h_wide_seqs;
+  DevBuf d_bases, d_amb, d_ambbits, d_seqs, d_clusters, d_wide_seqs, d_presence;
+  WidthState nar, wid;
+  DevBuf d_counters;       // u32[16]: tickets, n_runs, errors, totals
+  PinBuf h_counters;
+  DevBuf d_bsum;
+  // rows (narrow first, then wide)
+  DevBuf d_row_cluster, d_row_kmer, d_wrow_kmer, d_row_count, d_row_pattern, d_cand;
+  DevBuf d_rep, d_slot_of, d_winner;
+  DevBuf d_cl_pattern, d_cl_rep, d_cl_slot, d_cl_winner;
+  DevBuf d_pos_kmer, d_pos_seq, d_pos_cstart, d_pos_gstart, d_pos_flags, d_pos_wide;
+  PatternSpace kp, cp;     // k-mer patterns, cluster patterns
+  uint64_t kp_base = 0, cp_base = 0;   // pool sizes before the resident batch
+  // pinned results
+  PinBuf r_row_cluster, r_row_kmer, r_wrow_kmer, r_row_count, r_row_pattern, r_cl_pattern;
+  PinBuf r_new_kp, r_new_cp, r_pos_kmer, r_pos_seq, r_pos_cstart, r_pos_gstart, r_pos_flags,
+      r_pos_wide;
+  cudaEvent_t ev[EV_COUNT]{};
+  cudaEvent_t ev_h2d[2]{}, ev_d2h[2]{};
+  pf_stats stats{};
+  uint32_t launches = 0;
+};
+
+namespace {
+
+int fail(pf_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(ctx, PF_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                  __FILE__, __LINE__);                                                 \
+  } while (0)
+
+int dev_ensure(pf_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false) {
+  if (bytes <= b.cap) return PF_OK;
+  size_t want = std::max(bytes, b.cap + b.cap / 2);
+  want = (want + 255) & ~size_t(255);
+  void* np = nullptr;
+  CU(cudaMalloc(&np, want));
+  if (keep && b.p && b.cap) {
+    CU(cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  if (b.p) CU(cudaFree(b.p));
+  b.p = np;
+  b.cap = want;
+  return PF_OK;
+}
+int pin_ensure(pf_ctx* ctx, PinBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return PF_OK;
+  size_t want = std::max(bytes, b.cap + b.cap / 2);
+  want = (want + 4095) & ~size_t(4095);
+  if (b.p) CU(cudaFreeHost(b.p));
+  b.p = nullptr; b.cap = 0;
+  CU(cudaMallocHost(&b.p, want));
+  b.cap = want;
+  return PF_OK;
+}
+#define TRY(x) do { int r_ = (x); if (r_ != PF_OK) return r_; } while (0)
+
+inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+constexpr int kGridPersist = 148 * 4;
+
+// counters layout in d_counters
+enum { C_TICKET_N = 0, C_TICKET_W = 1, C_RUNS_N = 2, C_RUNS_W = 3, C_ERR = 4, C_ROWS_N = 5,
+       C_ROWS_W = 6, C_NEW_KP = 7, C_NEW_CP = 8, C_TICKET_MARK_N = 9, C_TICKET_MARK_W = 10,
+       C_COUNT = 16 };
+
+bool keep_count(double maf, uint32_t c, uint32_t n) {
+  double af = (double)c / (double)n;      // numpy: vec.sum() / vec.shape[0]
+  if (af >= 0.5) af = 1 - af;
+  return !(af < maf);
+}
+
+}  // namespace
+
+extern "C" int pf_maf_window(double maf, uint32_t n, uint32_t* lo, uint32_t* hi) {
+  if (!lo || !hi) return PF_ERR_INVALID;
+  if (n == 0) { *lo = 0; *hi = 0; return 1; }   // 0/0 = NaN: neither comparison fires
+  const uint32_t mid = (uint32_t)(((uint64_t)n + 1) / 2);   // first c with c/n >= 0.5
+  // rising part [0, mid): kept counts form a suffix
+  uint32_t a = 0, b = mid;                 // first kept in [a, b) or b
+  while (a < b) { uint32_t m = a + (b - a) / 2; if (keep_count(maf, m, n)) b = m; else a = m + 1; }
+  const uint32_t rise_lo = a;              // == mid if none
+  // falling part [mid, n]: kept counts form a prefix
+  uint32_t x = mid, y = n + 1;             // first dropped in [x, y) or y
+  while (x < y) { uint32_t m = x + (y - x) / 2; if (!keep_count(maf, m, n)) y = m; else x = m + 1; }
+  const uint32_t fall_end = x;             // kept: [mid, fall_end)
+  const bool rise = rise_lo < mid, fall = fall_end > mid;
+  if (!rise && !fall) { *lo = 1; *hi = 0; return 0; }
+  *lo = rise ? rise_lo : mid;
+  *hi = fall ? fall_end - 1 : mid - 1;
+  return 1;
+}
+
+extern "C" uint32_t pf_pattern_words(uint32_t n_samples) { return (n_samples + 31u) / 32u; }
+extern "C" int pf_abi_version(void) { return PF_ABI_VERSION; }
+extern "C" const char* pf_last_error(const pf_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+extern "C" uint32_t pf_kmer_pattern_words(const pf_ctx* ctx) { return ctx ? ctx->Wk : 0; }
+extern "C" void* pf_stream(pf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
+  pf_ctx* ctx = nullptr;
+  if (!out || !p) return fail(nullptr, PF_ERR_INVALID, "pf_create: null argument");
+  *out = nullptr;
+  if (p->abi_version != PF_ABI_VERSION)
+    return fail(nullptr, PF_ERR_INVALID, "pf_create: ABI version %u != %u", p->abi_version, PF_ABI_VERSION);
+  if (p->k < 1 || p->k > 32)
+    return fail(nullptr, PF_ERR_UNSUPPORTED, "k=%u unsupported: the 64-bit 2-bit path covers 1..32", p->k);
+  if (p->n_samples < 1) return fail(nullptr, PF_ERR_INVALID, "n_samples must be >= 1");
+  if (p->sort_bits != 0 && (p->sort_bits % 8 != 0 || p->sort_bits < 8 || p->sort_bits > 64))
+    return fail(nullptr, PF_ERR_INVALID, "sort_bits must be 0 or a multiple of 8 in 8..64");
+  if (!(p->maf <= 0.5) || p->maf < 0)
+    return fail(nullptr, PF_ERR_INVALID, "--maf should be in [0, 0.5]");
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    return fail(nullptr, PF_ERR_CUDA, "no CUDA device: %s (this library has no CPU fallback)",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n_dev) return fail(nullptr, PF_ERR_INVALID, "device %d out of range", device);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, PF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major < 10)
+    return fail(nullptr, PF_ERR_UNSUPPORTED, "device is sm_%d%d; this library is built for sm_100a only",
+                prop.major, prop.minor);
+  ctx = new pf_ctx();
+  ctx->prm = *p;
+  ctx->device = device;
+  ctx->W = pf_pattern_words(p->n_samples);
+  ctx->Wk = ctx->W + (p->consider_missing ? 1u : 0u);
+  ctx->kp.key_words = ctx->Wk;
+  ctx->cp.key_words = ctx->W;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, PF_ERR_CUDA, "cudaStreamCreate failed");
+  }
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  for (auto& ev : ctx->ev_h2d) cudaEventCreate(&ev);
+  for (auto& ev : ctx->ev_d2h) cudaEventCreate(&ev);
+  // opt in to > 48 KB dynamic shared memory for the sort passes
+  cudaFuncSetAttribute(k2_onesweep_pass<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(SortSmem<uint64_t>));
+  cudaFuncSetAttribute(k2_onesweep_pass<Key128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(SortSmem<Key128>));
+  const int k3_smem = (int)(8 * ctx->W * sizeof(uint32_t));
+  if (k3_smem > 48 * 1024) {
+    cudaFuncSetAttribute(k3_runs<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3_smem);
+    cudaFuncSetAttribute(k3_runs<uint64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3_smem);
+    cudaFuncSetAttribute(k3_runs<Key128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3_smem);
+    cudaFuncSetAttribute(k3_runs<Key128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3_smem);
+  }
+  if (k3_smem > 200 * 1024) {
+    pf_destroy(ctx);
+    return fail(nullptr, PF_ERR_UNSUPPORTED, "n_samples=%u needs %d B of shared memory per CTA", p->n_samples, k3_smem);
+  }
+  *out = ctx;
+  return PF_OK;
+}
+
+extern "C" void pf_destroy(pf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  auto fd = [](DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
+  auto fp = [](PinBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; };
+  for (DevBuf* b : {&ctx->d_bases, &ctx->d_amb, &ctx->d_ambbits, &ctx->d_seqs, &ctx->d_clusters,
+                    &ctx->d_wide_seqs, &ctx->d_presence, &ctx->d_counters, &ctx->d_bsum,
+                    &ctx->d_row_cluster, &ctx->d_row_kmer, &ctx->d_wrow_kmer, &ctx->d_row_count,
+                    &ctx->d_row_pattern, &ctx->d_cand, &ctx->d_rep, &ctx->d_slot_of, &ctx->d_winner,
+                    &ctx->d_cl_pattern, &ctx->d_cl_rep, &ctx->d_cl_slot, &ctx->d_cl_winner,
+                    &ctx->d_pos_kmer, &ctx->d_pos_seq, &ctx->d_pos_cstart, &ctx->d_pos_gstart,
+                    &ctx->d_pos_flags, &ctx->d_pos_wide})
+    fd(*b);
+  for (WidthState* w : {&ctx->nar, &ctx->wid}) {
+    for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
+                      &w->seg_hist, &w->lookback})
+      fd(*b);
+    fp(w->h_tiles); fp(w->h_seg_start);
+  }
+  for (PatternSpace* s : {&ctx->kp, &ctx->cp})
+    for (DevBuf* b : {&s->pool, &s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique})
+      fd(*b);
+  for (PinBuf* b : {&ctx->h_seqs, &ctx->h_clusters, &ctx->h_wide_seqs, &ctx->h_counters,
+                    &ctx->r_row_cluster, &ctx->r_row_kmer, &ctx->r_wrow_kmer, &ctx->r_row_count,
+                    &ctx->r_row_pattern, &ctx->r_cl_pattern, &ctx->r_new_kp, &ctx->r_new_cp,
+                    &ctx->r_pos_kmer, &ctx->r_pos_seq, &ctx->r_pos_cstart, &ctx->r_pos_gstart,
+                    &ctx->r_pos_flags, &ctx->r_pos_wide})
+    fp(*b);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_h2d) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_d2h) if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+namespace {
+
+int auto_sort_bits(const pf_ctx* ctx, uint32_t max_seg_records) {
+  if (ctx->prm.sort_bits) return (int)ctx->prm.sort_bits;
+  int lg = 0;
+  while ((1ull << lg) < (uint64_t)std::max<uint32_t>(max_seg_records, 1)) ++lg;
+  int bits = ((lg + 12 + 7) / 8) * 8;      // expected shared prefixes per segment <= n / 8192
+  return std::min(64, std::max(16, bits));
+}
+
+// Build the tile list of one key width from the per-cluster record ranges.
+int plan_tiles(pf_ctx* ctx, WidthState& w, const std::vector<std::pair<uint32_t, uint32_t>>& ranges) {
+  uint64_t n_tiles = 0;
+  uint32_t max_seg = 0;
+  for (auto& r : ranges) {
+    n_tiles += cdiv(r.second - r.first, kSortTile);
+    max_seg = std::max(max_seg, r.second - r.first);
+  }
+  if (max_seg >= (1u << 30))
+    return fail(ctx, PF_ERR_INVALID, "a cluster has %u k-mer records; the limit per cluster is 2^30", max_seg);
+  w.n_tiles = (uint32_t)n_tiles;
+  w.sort_bits = auto_sort_bits(ctx, max_seg);
+  w.passes = w.sort_bits / 8;
+  TRY(pin_ensure(ctx, w.h_tiles, std::max<size_t>(1, n_tiles) * sizeof(TileDev)));
+  TRY(pin_ensure(ctx, w.h_seg_start, std::max<size_t>(1, ranges.size()) * sizeof(uint32_t)));
+  TileDev* t = w.h_tiles.as<TileDev>();
+  uint32_t* ss = w.h_seg_start.as<uint32_t>();
+  uint32_t ti = 0;
+  for (uint32_t c = 0; c < ranges.size(); ++c) {
+    ss[c] = ranges[c].first;
+    const uint32_t first = ti;
+    for (uint32_t s = ranges[c].first; s < ranges[c].second; s += kSortTile) {
+      t[ti].start = s;
+      t[ti].count = std::min<uint32_t>(kSortTile, ranges[c].second - s);
+      t[ti].seg = c;
+      t[ti].first_tile = first;
+      ++ti;
+    }
+  }
+  return PF_OK;
+}
+
+}  // namespace
+
+extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
+  if (!ctx) return PF_ERR_INVALID;
+  if (!b) return fail(ctx, PF_ERR_INVALID, "pf_upload: null batch");
+  CU(cudaSetDevice(ctx->device));
+  ctx->have_batch = false;
+  ctx->executed = false;
+  const pf_params& P = ctx->prm;
+  const uint32_t k = P.k, S = P.n_samples, W = ctx->W;
+  if (b->n_seqs && (!b->seqs || !b->packed_bases)) return fail(ctx, PF_ERR_INVALID, "null seqs/packed_bases");
+  if (b->n_clusters && (!b->clusters || !b->cluster_presence))
+    return fail(ctx, PF_ERR_INVALID, "null clusters/cluster_presence");
+  if (b->n_clusters == 0 && b->n_seqs) return fail(ctx, PF_ERR_INVALID, "sequences without clusters");
+
+  TRY(pin_ensure(ctx, ctx->h_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(SeqDev)));
+  TRY(pin_ensure(ctx, ctx->h_clusters, std::max<size_t>(1, b->n_clusters) * sizeof(ClusterDev)));
+  TRY(pin_ensure(ctx, ctx->h_wide_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(uint32_t)));
+  SeqDev* hs = ctx->h_seqs.as<SeqDev>();
+  ClusterDev* hc = ctx->h_clusters.as<ClusterDev>();
+  uint32_t* hw = ctx->h_wide_seqs.as<uint32_t>();
+
+  const uint32_t mult = P.canonical ? 1u : 2u;
+  uint64_t rec = 0, wrec = 0, pos = 0, pwide = 0, bases = 0;
+  uint32_t n_wide = 0;
+  std::vector<std::pair<uint32_t, uint32_t>> nr(b->n_clusters), wr(b->n_clusters);
+  for (uint32_t c = 0; c < b->n_clusters; ++c) { nr[c] = {0u, 0u}; wr[c] = {0u, 0u}; }
+  uint32_t cur = 0;
+  bool opened = false;
+  uint32_t prev_sample = 0;
+  auto open_cluster = [&](uint32_t c) { nr[c].first = (uint32_t)rec; wr[c].first = (uint32_t)wrec; };
+  auto close_cluster = [&](uint32_t c) { nr[c].second = (uint32_t)rec; wr[c].second = (uint32_t)wrec; };
+  if (b->n_clusters) { open_cluster(0); opened = true; }
+  for (uint32_t i = 0; i < b->n_seqs; ++i) {
+    const pf_seq_desc& q = b->seqs[i];
+    if (q.cluster >= b->n_clusters) return fail(ctx, PF_ERR_INVALID, "seq %u: cluster %u out of range", i, q.cluster);
+    if (q.cluster < cur) return fail(ctx, PF_ERR_INVALID, "seq %u: clusters must be non-decreasing", i);
+    while (cur < q.cluster) { close_cluster(cur); ++cur; open_cluster(cur); prev_sample = 0; }
+    if (q.sample >= S) return fail(ctx, PF_ERR_INVALID, "seq %u: sample rank %u >= n_samples %u", i, q.sample, S);
+    if (q.sample < prev_sample)
+      return fail(ctx, PF_ERR_INVALID, "seq %u: sample ranks must be non-decreasing inside a cluster", i);
+    prev_sample = q.sample;
+    if (!((b->cluster_presence[(size_t)q.cluster * W + (q.sample >> 5)] >> (q.sample & 31)) & 1u))
+      return fail(ctx, PF_ERR_INVALID, "seq %u: sample %u is not marked present in cluster %u", i, q.sample, q.cluster);
+    if (q.base_off & 63u) return fail(ctx, PF_ERR_INVALID, "seq %u: base_off must be a multiple of 64", i);
+    if (q.base_off + q.len > b->n_words * 32ull)
+      return fail(ctx, PF_ERR_INVALID, "seq %u: bases run past the packed plane", i);
+    if (q.strand != 1 && q.strand != -1) return fail(ctx, PF_ERR_INVALID, "seq %u: strand must be +1/-1", i);
+    const bool amb = (q.flags & PF_SEQ_AMBIGUOUS) != 0;
+    if (amb) {
+      if (!b->amb_codes) return fail(ctx, PF_ERR_INVALID, "seq %u is ambiguous but amb_codes is NULL", i);
+      if (q.amb_off & 31u) return fail(ctx, PF_ERR_INVALID, "seq %u: amb_off must be a multiple of 32", i);
+      if (q.amb_off + q.len > b->n_amb_words * 16ull)
+        return fail(ctx, PF_ERR_INVALID, "seq %u: symbols run past the 4-bit plane", i);
+    }
+    const bool target = P.emit_positions && (q.flags & PF_SEQ_TARGET);
+    const uint32_t nwin = q.len >= k ? q.len - k + 1 : 0;
+    SeqDev& d = hs[i];
+    d.base_off = q.base_off; d.amb_off = amb ? q.amb_off : 0; d.len = q.len; d.sample = q.sample;
+    d.cluster = q.cluster; d.flags = (target ? 1u : 0u) | (amb ? 2u : 0u);
+    d.start = q.start; d.end = q.end; d.offset = q.offset; d.strand = q.strand;
+    d.rec_off = (uint32_t)rec; d.pos_off = (uint32_t)pos; d.wrec_off = (uint32_t)wrec;
+    d.pwide_off = (uint32_t)pwide;
+    rec += (uint64_t)nwin * mult;
+    if (target) pos += nwin;
+    if (amb) { wrec += (uint64_t)nwin * mult; hw[n_wide++] = i; if (target) pwide += nwin; }
+    bases += q.len;
+    if (rec >= (1ull << 32) - kSortTile || wrec >= (1ull << 32) - kSortTile)
+      return fail(ctx, PF_ERR_INVALID, "batch holds more than 2^32 k-mer records; split it");
+  }
+  if (opened) {
+    while (cur + 1 < b->n_clusters) { close_cluster(cur); ++cur; open_cluster(cur); }
+    close_cluster(cur);
+  }
+  for (uint32_t c = 0; c < b->n_clusters; ++c) {
+    uint32_t np = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+      uint32_t word = b->cluster_presence[(size_t)c * W + w];
+      if (w == W - 1 && (S & 31u)) {
+        if (word >> (S & 31u)) return fail(ctx, PF_ERR_INVALID, "cluster %u: presence bits beyond n_samples", c);
+      }
+      np += (uint32_t)__builtin_popcount(word);
+    }
+    ClusterDev& d = hc[c];
+    d.rec_start = nr[c].first; d.rec_end = nr[c].second;
+    d.wrec_start = wr[c].first; d.wrec_end = wr[c].second;
+    d.id = b->clusters[c].id; d.n_present = np;
+    const uint32_t n = P.consider_missing ? np : S;
+    auto it = ctx->maf_cache.find(n);
+    if (it == ctx->maf_cache.end()) {
+      uint32_t lo, hi;
+      pf_maf_window(P.maf, n, &lo, &hi);
+      it = ctx->maf_cache.emplace(n, std::make_pair(lo, hi)).first;
+    }
+    uint32_t lo = it->second.first, hi = it->second.second;
+    // "same as cluster" (panfeed.py:202-204): k-mer bits are a subset of the
+    // cluster's, so equality <=> count == n_present; NaN entries never compare equal.
+    if (P.cluster_equal_filter && (!P.consider_missing || np == S)) {
+      if (np == 0) { lo = 1; hi = 0; }
+      else hi = std::min(hi, np - 1);
+    }
+    if (lo == 0) lo = 1;                    // a k-mer row always has >= 1 sample
+    d.lo = lo; d.hi = hi;
+  }
+
+  ctx->n_seqs = b->n_seqs; ctx->n_clusters = b->n_clusters; ctx->n_wide_seqs = n_wide;
+  ctx->n_words = b->n_words; ctx->n_amb_words = n_wide ? b->n_amb_words : 0; ctx->n_bases = bases;
+  ctx->n_pos = (uint32_t)pos; ctx->n_pos_wide = (uint32_t)pwide;
+  ctx->nar.n_records = (uint32_t)rec; ctx->wid.n_records = (uint32_t)wrec;
+  if (pos >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "more than 2^32 positional records; split the batch");
+  TRY(plan_tiles(ctx, ctx->nar, nr));
+  TRY(plan_tiles(ctx, ctx->wid, wr));
+
+  // ---- device buffers + H2D ------------------------------------------------
+  const size_t slack_words = 80;
+  TRY(dev_ensure(ctx, ctx->d_bases, (b->n_words + slack_words) * 8));
+  TRY(dev_ensure(ctx, ctx->d_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(SeqDev)));
+  TRY(dev_ensure(ctx, ctx->d_clusters, std::max<size_t>(1, b->n_clusters) * sizeof(ClusterDev)));
+  TRY(dev_ensure(ctx, ctx->d_presence, std::max<size_t>(1, (size_t)b->n_clusters * W) * 4));
+  TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4));
+  TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4));
+  for (WidthState* w : {&ctx->nar, &ctx->wid}) {
+    TRY(dev_ensure(ctx, w->tiles, std::max<size_t>(1, w->n_tiles) * sizeof(TileDev)));
+    TRY(dev_ensure(ctx, w->seg_start, std::max<size_t>(1, b->n_clusters) * 4));
+    TRY(dev_ensure(ctx, w->seg_hist, std::max<size_t>(1, (size_t)b->n_clusters * w->passes * kRadix) * 4));
+    TRY(dev_ensure(ctx, w->lookback, std::max<size_t>(1, (size_t)w->n_tiles * kRadix) * 4));
+  }
+  cudaStream_t st = ctx->stream;
+  CU(cudaEventRecord(ctx->ev_h2d[0], st));
+  if (b->n_words) CU(cudaMemcpyAsync(ctx->d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync((char*)ctx->d_bases.p + b->n_words * 8, 0, slack_words * 8, st));
+  if (b->n_seqs) CU(cudaMemcpyAsync(ctx->d_seqs.p, hs, b->n_seqs * sizeof(SeqDev), cudaMemcpyHostToDevice, st));
+  if (b->n_clusters) {
+    CU(cudaMemcpyAsync(ctx->d_clusters.p, hc, b->n_clusters * sizeof(ClusterDev), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->d_presence.p, b->cluster_presence, (size_t)b->n_clusters * W * 4, cudaMemcpyHostToDevice, st));
+  }
+  for (WidthState* w : {&ctx->nar, &ctx->wid}) {
+    if (w->n_tiles) CU(cudaMemcpyAsync(w->tiles.p, w->h_tiles.p, w->n_tiles * sizeof(TileDev), cudaMemcpyHostToDevice, st));
+    if (b->n_clusters) CU(cudaMemcpyAsync(w->seg_start.p, w->h_seg_start.p, b->n_clusters * 4, cudaMemcpyHostToDevice, st));
+  }
+  if (n_wide) {
+    const size_t bit_words = (b->n_amb_words + 1) / 2 + 4;
+    TRY(dev_ensure(ctx, ctx->d_amb, (b->n_amb_words + 8) * 8));
+    TRY(dev_ensure(ctx, ctx->d_ambbits, bit_words * 4));
+    TRY(dev_ensure(ctx, ctx->d_wide_seqs, n_wide * 4));
+    CU(cudaMemcpyAsync(ctx->d_amb.p, b->amb_codes, b->n_amb_words * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync((char*)ctx->d_amb.p + b->n_amb_words * 8, 0, 8 * 8, st));
+    CU(cudaMemcpyAsync(ctx->d_wide_seqs.p, hw, n_wide * 4, cudaMemcpyHostToDevice, st));
+    k1_amb_bits<<<cdiv(bit_words, 256), 256, 0, st>>>(ctx->d_amb.as<uint64_t>(), b->n_amb_words,
+                                                       ctx->d_ambbits.as<uint32_t>(), bit_words);
+    ctx->launches++;
+  }
+  CU(cudaEventRecord(ctx->ev_h2d[1], st));
+  // caller buffers may be pageable: make sure the copies have consumed them
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  ctx->have_batch = true;
+  return PF_OK;
+}
+
+namespace {
+
+template <typename KeyT>
+int sort_width(pf_ctx* ctx, WidthState& w, int ticket_idx) {
+  if (w.n_records == 0) { w.final_buf = 0; return PF_OK; }
+  cudaStream_t st = ctx->stream;
+  const int key_bits = KeyTraits<KeyT>::kBits;
+  const int shift0 = key_bits - w.sort_bits;
+  const uint32_t n_seg = ctx->n_clusters;
+  CU(cudaMemsetAsync(w.seg_hist.p, 0, (size_t)n_seg * w.passes * kRadix * 4, st));
+  const uint32_t hist_ctas = std::min<uint32_t>(w.n_tiles, 148 * 8);
+  const uint32_t per = cdiv(w.n_tiles, hist_ctas);
+  k2_histogram<KeyT><<<cdiv(w.n_tiles, per), 256, 0, st>>>(w.keys[0].as<KeyT>(), w.tiles.as<TileDev>(),
+                                                           w.n_tiles, per, w.passes, shift0,
+                                                           w.seg_hist.as<uint32_t>());
+  const uint32_t rows = n_seg * w.passes;
+  k2_scan_histogram<<<cdiv(rows, 8), 256, 0, st>>>(w.seg_hist.as<uint32_t>(), w.seg_start.as<uint32_t>(), rows, w.passes);
+  ctx->launches += 2;
+  uint32_t* counters = ctx->d_counters.as<uint32_t>();
+  int src = 0;
+  for (int p = 0; p < w.passes; ++p) {
+    CU(cudaMemsetAsync(w.lookback.p, 0, (size_t)w.n_tiles * kRadix * 4, st));
+    CU(cudaMemsetAsync(counters + ticket_idx, 0, 4, st));
+    k2_onesweep_pass<KeyT><<<w.n_tiles, kSortThreads, sizeof(SortSmem<KeyT>), st>>>(
+        w.keys[src].as<KeyT>(), w.vals[src].as<uint32_t>(), w.keys[src ^ 1].as<KeyT>(),
+        w.vals[src ^ 1].as<uint32_t>(), w.tiles.as<TileDev>(), w.n_tiles, w.seg_hist.as<uint32_t>(), p,
+        w.passes, shift0 + 8 * p, w.lookback.as<uint32_t>(), counters + ticket_idx, counters + C_ERR);
+    ctx->launches++;
+    src ^= 1;
+  }
+  w.final_buf = src;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
+template <typename KeyT>
+int mark_width(pf_ctx* ctx, WidthState& w, int ticket_idx, int runs_idx) {
+  if (w.n_records == 0) return PF_OK;
+  cudaStream_t st = ctx->stream;
+  uint32_t* counters = ctx->d_counters.as<uint32_t>();
+  const int other = w.final_buf ^ 1;
+  // the idle ping-pong buffers hold the run lists: keys[other] = run_start | run_seg, vals[other] = nrows
+  uint32_t* run_start = w.keys[other].as<uint32_t>();
+  uint32_t* run_seg = run_start + ((size_t)w.n_records + 1);
+  CU(cudaMemsetAsync(w.lookback.p, 0, (size_t)w.n_tiles * 8, st));
+  CU(cudaMemsetAsync(counters + ticket_idx, 0, 4, st));
+  k3_mark_runs<KeyT><<<w.n_tiles, kSortThreads, 0, st>>>(
+      w.keys[w.final_buf].as<KeyT>(), w.tiles.as<TileDev>(), w.n_tiles, w.sort_bits, run_start, run_seg,
+      w.lookback.as<uint64_t>(), counters + ticket_idx, counters + runs_idx, counters + C_ERR);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
+int scan_inplace(pf_ctx* ctx, uint32_t* data, uint32_t n, uint32_t* total_dev) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t nb = std::max(1u, cdiv(n, kScanBlock));
+  TRY(dev_ensure(ctx, ctx->d_bsum, ((size_t)nb + 1) * 4));
+  scan_block_sums<<<nb, 256, 0, st>>>(data, n, ctx->d_bsum.as<uint32_t>());
+  scan_of_sums<<<1, 1024, 0, st>>>(ctx->d_bsum.as<uint32_t>(), nb, total_dev);
+  scan_apply<<<nb, 256, 0, st>>>(data, n, ctx->d_bsum.as<uint32_t>(), nb);
+  ctx->launches += 3;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
+template <typename KeyT, bool EMIT>
+int runs_width(pf_ctx* ctx, WidthState& w, RowOut out) {
+  if (w.n_runs == 0) return PF_OK;
+  cudaStream_t st = ctx->stream;
+  const int other = w.final_buf ^ 1;
+  uint32_t* run_start = w.keys[other].as<uint32_t>();
+  uint32_t* run_seg = run_start + ((size_t)w.n_records + 1);
+  uint32_t* nrows = w.vals[other].as<uint32_t>();
+  const size_t smem = (size_t)8 * ctx->W * 4;
+  const uint32_t grid = std::min<uint32_t>(cdiv(w.n_runs, 8), kGridPersist * 2);
+  k3_runs<KeyT, EMIT><<<grid, 256, smem, st>>>(w.keys[w.final_buf].as<KeyT>(), w.vals[w.final_buf].as<uint32_t>(),
+                                               run_start, run_seg, w.n_runs, w.n_records,
+                                               ctx->d_clusters.as<ClusterDev>(), nrows, out);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
+// Ensure the table of a pattern space can take `extra` more patterns at <= 50 % load.
+int table_reserve(pf_ctx* ctx, PatternSpace& s, uint64_t extra) {
+  cudaStream_t st = ctx->stream;
+  const uint64_t need = (s.n + extra) * 2 + 16;
+  if (need >= (1ull << 31)) return fail(ctx, PF_ERR_NOMEM, "pattern table would exceed 2^31 slots");
+  TRY(dev_ensure(ctx, s.pool, std::max<size_t>(1, (s.n + extra)) * s.key_words * 4, true));
+  if (need <= s.table_size) return PF_OK;
+  uint32_t size = std::max<uint32_t>(1024, s.table_size);
+  while (size < need) size *= 2;
+  DevBuf nt;
+  TRY(dev_ensure(ctx, nt, (size_t)size * 4));
+  CU(cudaMemsetAsync(nt.p, 0xff, (size_t)size * 4, st));
+  if (s.n) {
+    k4_rehash<<<std::min<uint32_t>(cdiv(s.n, 8), kGridPersist), 256, 0, st>>>(
+        s.pool.as<uint32_t>(), (uint32_t)s.n, s.key_words, nt.as<uint32_t>(), size - 1);
+    ctx->launches++;
+  }
+  CU(cudaStreamSynchronize(st));
+  if (s.table.p) CU(cudaFree(s.table.p));
+  s.table = nt;
+  s.table_size = size;
+  return PF_OK;
+}
+
+// Dedup n candidate keys against a pattern space; ids to `ids_out`, number of
+// new patterns to counters[new_idx] (device).
+int dedup(pf_ctx* ctx, PatternSpace& s, const uint32_t* cand, uint32_t n, DevBuf& rep, DevBuf& slot_of,
+          DevBuf& winner, uint32_t* ids_out, int new_idx) {
+  cudaStream_t st = ctx->stream;
+  uint32_t* counters = ctx->d_counters.as<uint32_t>();
+  if (n == 0) { CU(cudaMemsetAsync(counters + new_idx, 0, 4, st)); return PF_OK; }
+  TRY(table_reserve(ctx, s, n));
+  TRY(dev_ensure(ctx, rep, (size_t)n * 4));
+  TRY(dev_ensure(ctx, slot_of, (size_t)n * 4));
+  TRY(dev_ensure(ctx, winner, ((size_t)n + 1) * 4));
+  const uint32_t grid = std::min<uint32_t>(cdiv(n, 8), kGridPersist * 2);
+  k4_probe<<<grid, 256, 0, st>>>(cand, n, s.key_words, s.pool.as<uint32_t>(), s.table.as<uint32_t>(),
+                                 s.table_size - 1, rep.as<uint32_t>(), slot_of.as<uint32_t>(),
+                                 winner.as<uint32_t>());
+  ctx->launches++;
+  TRY(scan_inplace(ctx, winner.as<uint32_t>(), n, counters + new_idx));
+  k4_commit<<<grid, 256, 0, st>>>(cand, n, s.key_words, s.pool.as<uint32_t>(), (uint32_t)s.n,
+                                  s.table.as<uint32_t>(), rep.as<uint32_t>(), slot_of.as<uint32_t>(),
+                                  winner.as<uint32_t>(), ids_out);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
+int check_device_error(pf_ctx* ctx) {
+  const uint32_t e = ctx->h_counters.as<uint32_t>()[C_ERR];
+  if (e) return fail(ctx, PF_ERR_INTERNAL, "device watchdog: look-back chain stalled (code %u)", e);
+  return PF_OK;
+}
+
+}  // namespace
+
+extern "C" int pf_execute(pf_ctx* ctx) {
+  if (!ctx) return PF_ERR_INVALID;
+  if (!ctx->have_batch) return fail(ctx, PF_ERR_STATE, "pf_execute: no batch uploaded");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const pf_params& P = ctx->prm;
+  const uint32_t launches0 = ctx->launches;
+  WidthState& N = ctx->nar;
+  WidthState& Wd = ctx->wid;
+  uint32_t* counters = ctx->d_counters.as<uint32_t>();
+  uint32_t* hcnt = ctx->h_counters.as<uint32_t>();
+  if (ctx->executed) {      // a previous execution was never collected: fold its pattern count in
+    CU(cudaStreamSynchronize(st));
+    ctx->kp.n = ctx->kp_base + hcnt[C_NEW_KP];
+    ctx->executed = false;
+  }
+  ctx->kp_base = ctx->kp.n;
+  ctx->cp_base = ctx->cp.n;
+
+  // record buffers (ping-pong); the idle one later holds the run lists, so give
+  // it room for n+1 run starts + n run segments (8n+4 bytes <= 8n+8)
+  for (int i = 0; i < 2; ++i) {
+    TRY(dev_ensure(ctx, N.keys[i], ((size_t)N.n_records + 2) * 8));
+    TRY(dev_ensure(ctx, N.vals[i], ((size_t)N.n_records + 2) * 4));
+    TRY(dev_ensure(ctx, Wd.keys[i], ((size_t)Wd.n_records + 2) * 16));
+    TRY(dev_ensure(ctx, Wd.vals[i], ((size_t)Wd.n_records + 2) * 4));
+  }
+  if (ctx->n_pos) {
+    TRY(dev_ensure(ctx, ctx->d_pos_kmer, (size_t)ctx->n_pos * 8));
+    TRY(dev_ensure(ctx, ctx->d_pos_seq, (size_t)ctx->n_pos * 4));
+    TRY(dev_ensure(ctx, ctx->d_pos_cstart, (size_t)ctx->n_pos * 4));
+    TRY(dev_ensure(ctx, ctx->d_pos_gstart, (size_t)ctx->n_pos * 4));
+    TRY(dev_ensure(ctx, ctx->d_pos_flags, (size_t)ctx->n_pos));
+  }
+  if (ctx->n_pos_wide) TRY(dev_ensure(ctx, ctx->d_pos_wide, (size_t)ctx->n_pos_wide * 16));
+
+  CU(cudaMemsetAsync(counters, 0, C_COUNT * 4, st));
+  CU(cudaEventRecord(ctx->ev[EV_START], st));
+
+  // ---- K1 ---------------------------------------------------------------
+  PosOut po{ctx->d_pos_kmer.as<uint64_t>(), ctx->d_pos_seq.as<uint32_t>(), ctx->d_pos_cstart.as<int32_t>(),
+            ctx->d_pos_gstart.as<int32_t>(), ctx->d_pos_flags.as<uint8_t>()};
+  if (ctx->n_seqs && N.n_records) {
+    const uint32_t grid = std::min<uint32_t>(cdiv(ctx->n_seqs, kK1Warps), 148 * 8);
+    if (P.canonical)
+      k1_extract<true><<<grid, kK1Warps * 32, 0, st>>>(ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(),
+                                                      ctx->d_seqs.as<SeqDev>(), ctx->n_seqs, (int)P.k,
+                                                      N.keys[0].as<uint64_t>(), N.vals[0].as<uint32_t>(), po);
+    else
+      k1_extract<false><<<grid, kK1Warps * 32, 0, st>>>(ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(),
+                                                       ctx->d_seqs.as<SeqDev>(), ctx->n_seqs, (int)P.k,
+                                                       N.keys[0].as<uint64_t>(), N.vals[0].as<uint32_t>(), po);
+    ctx->launches++;
+  }
+  if (ctx->n_wide_seqs && Wd.n_records) {
+    const uint32_t grid = std::min<uint32_t>(cdiv(ctx->n_wide_seqs, 8), 148 * 8);
+    if (P.canonical)
+      k1_extract_wide<true><<<grid, 256, 0, st>>>(ctx->d_amb.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(),
+                                                 ctx->d_wide_seqs.as<uint32_t>(), ctx->n_wide_seqs, (int)P.k,
+                                                 Wd.keys[0].as<Key128>(), Wd.vals[0].as<uint32_t>(),
+                                                 ctx->d_pos_wide.as<uint64_t>());
+    else
+      k1_extract_wide<false><<<grid, 256, 0, st>>>(ctx->d_amb.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(),
+                                                  ctx->d_wide_seqs.as<uint32_t>(), ctx->n_wide_seqs, (int)P.k,
+                                                  Wd.keys[0].as<Key128>(), Wd.vals[0].as<uint32_t>(),
+                                                  ctx->d_pos_wide.as<uint64_t>());
+    ctx->launches++;
+  }
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev[EV_EXTRACT], st));
+
+  // ---- K2 ---------------------------------------------------------------
+  TRY(sort_width<uint64_t>(ctx, N, C_TICKET_N));
+  TRY(sort_width<Key128>(ctx, Wd, C_TICKET_W));
+  CU(cudaEventRecord(ctx->ev[EV_SORT], st));
+
+  // ---- K3: runs ------------------------------------------------------------
+  TRY(mark_width<uint64_t>(ctx, N, C_TICKET_MARK_N, C_RUNS_N));
+  TRY(mark_width<Key128>(ctx, Wd, C_TICKET_MARK_W, C_RUNS_W));
+  CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  TRY(check_device_error(ctx));
+  N.n_runs = N.n_records ? hcnt[C_RUNS_N] : 0;
+  Wd.n_runs = Wd.n_records ? hcnt[C_RUNS_W] : 0;
+
+  RowOut ro{};
+  ro.key_words = ctx->Wk; ro.pattern_words = ctx->W;
+  TRY((runs_width<uint64_t, false>(ctx, N, ro)));
+  TRY((runs_width<Key128, false>(ctx, Wd, ro)));
+  if (N.n_runs) TRY(scan_inplace(ctx, N.vals[N.final_buf ^ 1].as<uint32_t>(), N.n_runs, counters + C_ROWS_N));
+  if (Wd.n_runs) TRY(scan_inplace(ctx, Wd.vals[Wd.final_buf ^ 1].as<uint32_t>(), Wd.n_runs, counters + C_ROWS_W));
+
+  // ---- cluster rows (int64 namespace), needed for the NaN-plane word ---------
+  TRY(dev_ensure(ctx, ctx->d_cl_pattern, std::max<size_t>(1, ctx->n_clusters) * 4));
+  TRY(dedup(ctx, ctx->cp, ctx->d_presence.as<uint32_t>(), ctx->n_clusters, ctx->d_cl_rep, ctx->d_cl_slot,
+            ctx->d_cl_winner, ctx->d_cl_pattern.as<uint32_t>(), C_NEW_CP));
+
+  CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  N.n_rows = N.n_runs ? hcnt[C_ROWS_N] : 0;
+  Wd.n_rows = Wd.n_runs ? hcnt[C_ROWS_W] : 0;
+  ctx->cp.n = ctx->cp_base + hcnt[C_NEW_CP];
+  const uint64_t rows = (uint64_t)N.n_rows + Wd.n_rows;
+  if (rows >= (1ull << 31)) return fail(ctx, PF_ERR_INVALID, "batch yields 2^31 rows or more; split it");
+
+  TRY(dev_ensure(ctx, ctx->d_row_cluster, std::max<size_t>(1, rows) * 4));
+  TRY(dev_ensure(ctx, ctx->d_row_count, std::max<size_t>(1, rows) * 4));
+  TRY(dev_ensure(ctx, ctx->d_row_pattern, std::max<size_t>(1, rows) * 4));
+  TRY(dev_ensure(ctx, ctx->d_row_kmer, std::max<size_t>(1, N.n_rows) * 8));
+  TRY(dev_ensure(ctx, ctx->d_wrow_kmer, std::max<size_t>(1, Wd.n_rows) * 16));
+  TRY(dev_ensure(ctx, ctx->d_cand, std::max<size_t>(1, rows) * ctx->Wk * 4));
+  ro.cluster = ctx->d_row_cluster.as<uint32_t>();
+  ro.count = ctx->d_row_count.as<uint32_t>();
+  ro.cand = ctx->d_cand.as<uint32_t>();
+  ro.cluster_pattern = ctx->d_cl_pattern.as<uint32_t>();
+  ro.kmer = ctx->d_row_kmer.as<uint64_t>();
+  ro.row_base = 0;
+  if (N.n_rows) TRY((runs_width<uint64_t, true>(ctx, N, ro)));
+  ro.kmer = ctx->d_wrow_kmer.as<uint64_t>();
+  ro.row_base = N.n_rows;
+  if (Wd.n_rows) TRY((runs_width<Key128, true>(ctx, Wd, ro)));
+  CU(cudaEventRecord(ctx->ev[EV_REDUCE], st));
+
+  // ---- K4 ---------------------------------------------------------------
+  TRY(dedup(ctx, ctx->kp, ctx->d_cand.as<uint32_t>(), (uint32_t)rows, ctx->d_rep, ctx->d_slot_of,
+            ctx->d_winner, ctx->d_row_pattern.as<uint32_t>(), C_NEW_KP));
+  CU(cudaEventRecord(ctx->ev[EV_DEDUP], st));
+  CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(ctx->ev[EV_END], st));
+  ctx->executed = true;
+  ctx->stats.launches = ctx->launches - launches0;
+  return PF_OK;
+}
+
+extern "C" int pf_submit(pf_ctx* ctx, const pf_batch* batch) {
+  int r = pf_upload(ctx, batch);
+  if (r != PF_OK) return r;
+  return pf_execute(ctx);
+}
+
+extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
+  if (!ctx) return PF_ERR_INVALID;
+  if (!ctx->executed) return fail(ctx, PF_ERR_STATE, "pf_collect: nothing executed");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CU(cudaStreamSynchronize(st));
+  uint32_t* hcnt = ctx->h_counters.as<uint32_t>();
+  TRY(check_device_error(ctx));
+  WidthState& N = ctx->nar;
+  WidthState& Wd = ctx->wid;
+  const uint64_t rows = (uint64_t)N.n_rows + Wd.n_rows;
+  const uint64_t new_kp = hcnt[C_NEW_KP];
+  const uint64_t new_cp = ctx->cp.n - ctx->cp_base;
+  ctx->kp.n = ctx->kp_base + new_kp;
+  ctx->executed = false;      // results are handed out once
+
+  CU(cudaEventRecord(ctx->ev_d2h[0], st));
+  auto d2h = [&](PinBuf& dst, const void* src, size_t bytes) -> int {
+    TRY(pin_ensure(ctx, dst, std::max<size_t>(bytes, 8)));
+    if (bytes) CU(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyDeviceToHost, st));
+    return PF_OK;
+  };
+  TRY(d2h(ctx->r_row_cluster, ctx->d_row_cluster.p, rows * 4));
+  TRY(d2h(ctx->r_row_count, ctx->d_row_count.p, rows * 4));
+  TRY(d2h(ctx->r_row_pattern, ctx->d_row_pattern.p, rows * 4));
+  TRY(d2h(ctx->r_row_kmer, ctx->d_row_kmer.p, (size_t)N.n_rows * 8));
+  TRY(d2h(ctx->r_wrow_kmer, ctx->d_wrow_kmer.p, (size_t)Wd.n_rows * 16));
+  TRY(d2h(ctx->r_cl_pattern, ctx->d_cl_pattern.p, (size_t)ctx->n_clusters * 4));
+  TRY(d2h(ctx->r_new_kp, ctx->kp.pool.as<uint32_t>() + ctx->kp_base * ctx->Wk, new_kp * ctx->Wk * 4));
+  TRY(d2h(ctx->r_new_cp, ctx->cp.pool.as<uint32_t>() + ctx->cp_base * ctx->W, new_cp * ctx->W * 4));
+  if (ctx->n_pos) {
+    TRY(d2h(ctx->r_pos_kmer, ctx->d_pos_kmer.p, (size_t)ctx->n_pos * 8));
+    TRY(d2h(ctx->r_pos_seq, ctx->d_pos_seq.p, (size_t)ctx->n_pos * 4));
+    TRY(d2h(ctx->r_pos_cstart, ctx->d_pos_cstart.p, (size_t)ctx->n_pos * 4));
+    TRY(d2h(ctx->r_pos_gstart, ctx->d_pos_gstart.p, (size_t)ctx->n_pos * 4));
+    TRY(d2h(ctx->r_pos_flags, ctx->d_pos_flags.p, (size_t)ctx->n_pos));
+  }
+  if (ctx->n_pos_wide) TRY(d2h(ctx->r_pos_wide, ctx->d_pos_wide.p, (size_t)ctx->n_pos_wide * 16));
+  CU(cudaEventRecord(ctx->ev_d2h[1], st));
+  CU(cudaStreamSynchronize(st));
+
+  if (out) {
+    memset(out, 0, sizeof *out);
+    out->n_rows = N.n_rows;
+    out->row_cluster = ctx->r_row_cluster.as<uint32_t>();
+    out->row_kmer = ctx->r_row_kmer.as<uint64_t>();
+    out->row_count = ctx->r_row_count.as<uint32_t>();
+    out->row_pattern = ctx->r_row_pattern.as<uint32_t>();
+    out->n_wide_rows = Wd.n_rows;
+    out->wide_row_cluster = out->row_cluster + N.n_rows;
+    out->wide_row_kmer = ctx->r_wrow_kmer.as<uint64_t>();
+    out->wide_row_count = out->row_count + N.n_rows;
+    out->wide_row_pattern = out->row_pattern + N.n_rows;
+    out->n_clusters = ctx->n_clusters;
+    out->cluster_pattern = ctx->r_cl_pattern.as<uint32_t>();
+    out->kmer_pattern_base = ctx->kp_base;
+    out->n_new_kmer_patterns = new_kp;
+    out->new_kmer_patterns = ctx->r_new_kp.as<uint32_t>();
+    out->cluster_pattern_base = ctx->cp_base;
+    out->n_new_cluster_patterns = new_cp;
+    out->new_cluster_patterns = ctx->r_new_cp.as<uint32_t>();
+    out->n_pos = ctx->n_pos;
+    out->pos_kmer = ctx->r_pos_kmer.as<uint64_t>();
+    out->pos_seq = ctx->r_pos_seq.as<uint32_t>();
+    out->pos_contig_start = ctx->r_pos_cstart.as<int32_t>();
+    out->pos_gene_start = ctx->r_pos_gstart.as<int32_t>();
+    out->pos_flags = ctx->r_pos_flags.as<uint8_t>();
+    out->pos_wide_kmer = ctx->r_pos_wide.as<uint64_t>();
+    out->n_pos_wide = ctx->n_pos_wide;
+  }
+  // ---- stats ---------------------------------------------------------------
+  pf_stats& s = ctx->stats;
+  s.batches++;
+  s.bases += ctx->n_bases;
+  s.instances += (uint64_t)N.n_records + Wd.n_records;
+  s.unique_kmers += (uint64_t)N.n_runs + Wd.n_runs;
+  s.rows += rows;
+  s.kmer_patterns = ctx->kp.n;
+  s.cluster_patterns = ctx->cp.n;
+  s.sort_passes = (uint32_t)N.passes;
+  s.total_launches = ctx->launches;
+  auto ms = [](cudaEvent_t a, cudaEvent_t b) { float m = 0; cudaEventElapsedTime(&m, a, b); return m; };
+  s.ms_h2d = ms(ctx->ev_h2d[0], ctx->ev_h2d[1]);
+  s.ms_extract = ms(ctx->ev[EV_START], ctx->ev[EV_EXTRACT]);
+  s.ms_sort = ms(ctx->ev[EV_EXTRACT], ctx->ev[EV_SORT]);
+  s.ms_reduce = ms(ctx->ev[EV_SORT], ctx->ev[EV_REDUCE]);
+  s.ms_dedup = ms(ctx->ev[EV_REDUCE], ctx->ev[EV_DEDUP]);
+  s.ms_d2h = ms(ctx->ev_d2h[0], ctx->ev_d2h[1]);
+  s.ms_total = ms(ctx->ev[EV_START], ctx->ev[EV_END]);
+  return PF_OK;
+}
+
+extern "C" int pf_reset_patterns(pf_ctx* ctx) {
+  if (!ctx) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (PatternSpace* s : {&ctx->kp, &ctx->cp}) {
+    s->n = 0;
+    s->x_n_unique = 0;
+    if (s->table.p) CU(cudaMemsetAsync(s->table.p, 0xff, (size_t)s->table_size * 4, ctx->stream));
+  }
+  ctx->kp_base = ctx->cp_base = 0;
+  ctx->stats.kmer_patterns = ctx->stats.cluster_patterns = 0;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return PF_OK;
+}
+
+extern "C" int pf_patterns_export(pf_ctx* ctx, int cluster_namespace, uint64_t first, uint64_t count,
+                                  uint32_t* host_out) {
+  if (!ctx || !host_out) return PF_ERR_INVALID;
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  if (first + count > s.n) return fail(ctx, PF_ERR_INVALID, "pattern range [%llu,%llu) beyond %llu",
+                                       (unsigned long long)first, (unsigned long long)(first + count),
+                                       (unsigned long long)s.n);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (count)
+    CU(cudaMemcpy(host_out, s.pool.as<uint32_t>() + first * s.key_words, count * s.key_words * 4,
+                  cudaMemcpyDeviceToHost));
+  return PF_OK;
+}
+
+extern "C" int pf_stats_get(pf_ctx* ctx, pf_stats* out) {
+  if (!ctx || !out) return PF_ERR_INVALID;
+  *out = ctx->stats;
+  out->total_launches = ctx->launches;
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// synthetic pangenome
+// ---------------------------------------------------------------------------
+namespace {
+struct SynthCell { bool present; uint32_t copies; };
+inline uint64_t thr64(double p) {
+  if (p <= 0) return 0;
+  if (p >= 1) return ~0ull;
+  return (uint64_t)(p * 18446744073709551616.0);
+}
+inline SynthCell synth_cell(const pf_synth_params* p, uint32_t gc, uint32_t s) {
+  const uint32_t n_core = (uint32_t)((double)p->total_clusters * p->core_fraction);
+  double pc = 0.99;
+  if (gc >= n_core) {
+    const uint64_t h = synth_hash(p->seed, gc, 0, 0, kTagAccessoryP);
+    pc = 0.05 + 0.90 * ((double)(h >> 11) / 9007199254740992.0);
+  }
+  SynthCell c;
+  c.present = synth_hash(p->seed, gc, s, 0, kTagPresence) < thr64(pc);
+  c.copies = c.present ? (synth_hash(p->seed, gc, s, 0, kTagParalog) < thr64(p->paralog_rate) ? 2u : 1u) : 0u;
+  return c;
+}
+}  // namespace
+
+extern "C" int pf_synth_plan(const pf_synth_params* p, uint32_t* n_seqs, uint64_t* n_words) {
+  if (!p || !n_seqs || !n_words || p->gene_len == 0 || p->n_founders == 0) return PF_ERR_INVALID;
+  const uint64_t wps = ((uint64_t)p->gene_len + 63) / 64 * 2;   // words per sequence, 64-base aligned
+  uint64_t n = 0;
+  for (uint32_t c = 0; c < p->n_clusters; ++c)
+    for (uint32_t s = 0; s < p->n_samples; ++s) n += synth_cell(p, p->first_cluster + c, s).copies;
+  if (n >= (1ull << 32)) return PF_ERR_INVALID;
+  *n_seqs = (uint32_t)n;
+  *n_words = n * wps;
+  return PF_OK;
+}
+
+extern "C" int pf_synth_fill(int device, const pf_synth_params* p, pf_seq_desc* seqs,
+                             pf_cluster_desc* clusters, uint32_t* presence, uint64_t* packed_bases) {
+  pf_ctx* ctx = nullptr;
+  if (!p || !seqs || !clusters || !presence || !packed_bases) return fail(nullptr, PF_ERR_INVALID, "pf_synth_fill: null argument");
+  const uint32_t W = pf_pattern_words(p->n_samples);
+  const uint64_t wps = ((uint64_t)p->gene_len + 63) / 64 * 2;
+  std::vector<SynthSeq> ss;
+  memset(presence, 0, (size_t)p->n_clusters * W * 4);
+  uint64_t n = 0;
+  for (uint32_t c = 0; c < p->n_clusters; ++c) {
+    const uint32_t gc = p->first_cluster + c;
+    clusters[c].id = gc;
+    clusters[c].reserved = 0;
+    for (uint32_t s = 0; s < p->n_samples; ++s) {
+      const SynthCell cell = synth_cell(p, gc, s);
+      if (!cell.present) continue;
+      presence[(size_t)c * W + (s >> 5)] |= 1u << (s & 31);
+      for (uint32_t cp = 0; cp < cell.copies; ++cp) {
+        pf_seq_desc& q = seqs[n];
+        q.base_off = n * wps * 32;
+        q.len = p->gene_len;
+        q.cluster = c;
+        q.sample = s;
+        q.flags = p->all_targets ? PF_SEQ_TARGET : 0u;
+        const uint64_t inst = ((uint64_t)s << 8) | cp;
+        q.strand = (synth_hash(p->seed, gc, inst, 0, kTagStrand) & 1u) ? 1 : -1;
+        q.start = 1 + (int32_t)(synth_hash(p->seed, gc, inst, 0, kTagStart) % 1000000u);
+        q.end = q.start + (int32_t)p->gene_len - 1;
+        q.offset = 100;
+        q.amb_off = 0;
+        ss.push_back(SynthSeq{n * wps, gc, s, cp, p->gene_len});
+        ++n;
+      }
+    }
+  }
+  if (n == 0) return PF_OK;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, PF_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  SynthSeq* d_ss = nullptr;
+  uint64_t* d_out = nullptr;
+  CU(cudaMalloc(&d_ss, ss.size() * sizeof(SynthSeq)));
+  CU(cudaMalloc(&d_out, n * wps * 8));
+  CU(cudaMemcpy(d_ss, ss.data(), ss.size() * sizeof(SynthSeq), cudaMemcpyHostToDevice));
+  const uint64_t threads = n * wps;
+  synth_bases<<<cdiv(threads, 256), 256>>>(d_ss, (uint32_t)n, (uint32_t)wps, p->seed, p->n_founders,
+                                           thr64(p->founder_div), thr64(p->private_div), d_out);
+  CU(cudaGetLastError());
+  CU(cudaMemcpy(packed_bases, d_out, n * wps * 8, cudaMemcpyDeviceToHost));
+  cudaFree(d_ss);
+  cudaFree(d_out);
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// multi-GPU exchange
+// ---------------------------------------------------------------------------
+namespace pf {
+
+// owner of every local pattern + its position inside the owner's bucket
+__global__ void __launch_bounds__(256)
+x_classify(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
+           const uint32_t* __restrict__ mask_remap, uint32_t world, uint32_t* __restrict__ owner,
+           uint32_t* __restrict__ pos, uint32_t* __restrict__ counts) {
+  const uint32_t lane = lane_id();
+  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += total_warps) {
+    const uint32_t* key = pool + (size_t)e * key_words;
+    uint64_t h = 0;
+    for (uint32_t w = lane; w < key_words; w += 32) {
+      uint32_t v = key[w];
+      if (mask_remap && w == key_words - 1) v = mask_remap[v];
+      h += word_hash(v, w);
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) h += __shfl_xor_sync(kFull, h, m);
+    h = mix64(h);
+    if (lane == 0) {
+      const uint32_t o = (uint32_t)((h >> 32) % world);
+      owner[e] = o;
+      pos[e] = atomicAdd(&counts[o], 1u);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+x_pack(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
+       const uint32_t* __restrict__ mask_remap, const uint32_t* __restrict__ owner,
+       const uint32_t* __restrict__ pos, const uint32_t* __restrict__ offsets,
+       uint32_t* __restrict__ send, uint32_t* __restrict__ perm) {
+  const uint32_t lane = lane_id();
+  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += total_warps) {
+    const uint32_t dst = offsets[owner[e]] + pos[e];
+    const uint32_t* key = pool + (size_t)e * key_words;
+    uint32_t* out = send + (size_t)dst * key_words;
+    for (uint32_t w = lane; w < key_words; w += 32) {
+      uint32_t v = key[w];
+      if (mask_remap && w == key_words - 1) v = mask_remap[v];
+      out[w] = v;
+    }
+    if (lane == 0) perm[e] = dst;
+  }
+}
+
+// unique index of every received key + compacted unique keys
+__global__ void __launch_bounds__(256)
+x_finish(const uint32_t* __restrict__ recv, uint32_t n, uint32_t key_words,
+         const uint32_t* __restrict__ rep, const uint32_t* __restrict__ winner_rank,
+         uint32_t* __restrict__ unique_index, uint32_t* __restrict__ unique_keys) {
+  const uint32_t lane = lane_id();
+  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += total_warps) {
+    const uint32_t q = rep[e] & ~kTentative;         // every rep is tentative here (empty pool)
+    const uint32_t u = winner_rank[q];
+    if (lane == 0) unique_index[e] = u;
+    if (q == e) {
+      const uint32_t* src = recv + (size_t)e * key_words;
+      uint32_t* dst = unique_keys + (size_t)u * key_words;
+      for (uint32_t w = lane; w < key_words; w += 32) dst[w] = src[w];
+    }
+  }
+}
+
+__global__ void x_unpack(const uint32_t* __restrict__ returned, const uint32_t* __restrict__ perm,
+                         uint32_t n, uint32_t* __restrict__ local_to_global) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) local_to_global[i] = returned[perm[i]];
+}
+
+}  // namespace pf
+
+extern "C" int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t world,
+                                const uint32_t* mask_remap_dev, uint32_t* send_words_dev,
+                                uint64_t capacity_patterns, uint64_t* counts_host) {
+  if (!ctx || !counts_host || world == 0) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  cudaStream_t st = ctx->stream;
+  const uint32_t n = (uint32_t)s.n;
+  if (n > capacity_patterns) return fail(ctx, PF_ERR_INVALID, "send buffer too small: %u patterns", n);
+  if (mask_remap_dev && (cluster_namespace || !ctx->prm.consider_missing))
+    return fail(ctx, PF_ERR_INVALID, "mask_remap only applies to k-mer patterns with consider_missing");
+  TRY(dev_ensure(ctx, s.x_owner, std::max<size_t>(1, n) * 4));
+  TRY(dev_ensure(ctx, s.x_pos, std::max<size_t>(1, n) * 4));
+  TRY(dev_ensure(ctx, s.x_perm, std::max<size_t>(1, n) * 4));
+  TRY(dev_ensure(ctx, s.x_counts, (size_t)world * 2 * 4));
+  CU(cudaMemsetAsync(s.x_counts.p, 0, (size_t)world * 2 * 4, st));
+  std::vector<uint32_t> counts(world, 0), offsets(world, 0);
+  if (n) {
+    if (!send_words_dev) return fail(ctx, PF_ERR_INVALID, "null send buffer");
+    const uint32_t grid = std::min<uint32_t>(cdiv(n, 8), kGridPersist);
+    x_classify<<<grid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev, world,
+                                     s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(), s.x_counts.as<uint32_t>());
+    CU(cudaMemcpyAsync(counts.data(), s.x_counts.p, world * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (uint32_t r = 1; r < world; ++r) offsets[r] = offsets[r - 1] + counts[r - 1];
+    CU(cudaMemcpyAsync(s.x_counts.as<uint32_t>() + world, offsets.data(), world * 4, cudaMemcpyHostToDevice, st));
+    x_pack<<<grid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev, s.x_owner.as<uint32_t>(),
+                                 s.x_pos.as<uint32_t>(), s.x_counts.as<uint32_t>() + world, send_words_dev,
+                                 s.x_perm.as<uint32_t>());
+    ctx->launches += 2;
+    CU(cudaStreamSynchronize(st));
+    CU(cudaGetLastError());
+  }
+  for (uint32_t r = 0; r < world; ++r) counts_host[r] = counts[r];
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint32_t* recv_words_dev,
+                                 uint64_t n_recv, uint32_t* recv_unique_index_dev, uint64_t* n_unique_host) {
+  if (!ctx || !n_unique_host) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  cudaStream_t st = ctx->stream;
+  *n_unique_host = 0;
+  s.x_n_unique = 0;
+  if (n_recv == 0) return PF_OK;
+  if (n_recv >= (1ull << 30)) return fail(ctx, PF_ERR_INVALID, "too many received patterns");
+  if (!recv_words_dev || !recv_unique_index_dev) return fail(ctx, PF_ERR_INVALID, "null exchange buffer");
+  const uint32_t n = (uint32_t)n_recv;
+  uint32_t size = 1024;
+  while (size < 2ull * n + 16) size *= 2;
+  DevBuf table, rep, slot_of, winner;
+  TRY(dev_ensure(ctx, table, (size_t)size * 4));
+  TRY(dev_ensure(ctx, rep, (size_t)n * 4));
+  TRY(dev_ensure(ctx, slot_of, (size_t)n * 4));
+  TRY(dev_ensure(ctx, winner, ((size_t)n + 1) * 4));
+  TRY(dev_ensure(ctx, s.x_unique, (size_t)n * s.key_words * 4));
+  CU(cudaMemsetAsync(table.p, 0xff, (size_t)size * 4, st));
+  uint32_t* counters = ctx->d_counters.p ? ctx->d_counters.as<uint32_t>() : nullptr;
+  if (!counters) { TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4)); TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4)); counters = ctx->d_counters.as<uint32_t>(); }
+  const uint32_t grid = std::min<uint32_t>(cdiv(n, 8), kGridPersist * 2);
+  k4_probe<<<grid, 256, 0, st>>>(recv_words_dev, n, s.key_words, nullptr, table.as<uint32_t>(), size - 1,
+                                 rep.as<uint32_t>(), slot_of.as<uint32_t>(), winner.as<uint32_t>());
+  TRY(scan_inplace(ctx, winner.as<uint32_t>(), n, counters + C_NEW_KP));
+  x_finish<<<grid, 256, 0, st>>>(recv_words_dev, n, s.key_words, rep.as<uint32_t>(), winner.as<uint32_t>(),
+                                 recv_unique_index_dev, s.x_unique.as<uint32_t>());
+  ctx->launches += 2;
+  uint32_t total = 0;
+  CU(cudaMemcpyAsync(&total, counters + C_NEW_KP, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  for (DevBuf* b : {&table, &rep, &slot_of, &winner}) cudaFree(b->p);
+  s.x_n_unique = total;
+  *n_unique_host = total;
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_unique_export(pf_ctx* ctx, int cluster_namespace, uint32_t* host_out) {
+  if (!ctx) return PF_ERR_INVALID;
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  if (s.x_n_unique == 0) return PF_OK;
+  if (!host_out) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpy(host_out, s.x_unique.p, s.x_n_unique * s.key_words * 4, cudaMemcpyDeviceToHost));
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_unpack(pf_ctx* ctx, int cluster_namespace, const uint32_t* returned_ids_dev,
+                                  uint32_t* local_to_global_dev) {
+  if (!ctx) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  const uint32_t n = (uint32_t)s.n;
+  if (n == 0) return PF_OK;
+  if (!returned_ids_dev || !local_to_global_dev) return fail(ctx, PF_ERR_INVALID, "null exchange buffer");
+  x_unpack<<<cdiv(n, 256), 256, 0, ctx->stream>>>(returned_ids_dev, s.x_perm.as<uint32_t>(), n, local_to_global_dev);
+  ctx->launches++;
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  return PF_OK;
+}

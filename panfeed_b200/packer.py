@@ -1,0 +1,158 @@
+"""Host packer: cluster items -> 2-bit / 4-bit planes + descriptors.
+
+Re-expresses what the reference hands from `iter_gene_clusters` to
+`cluster_cutter` (`/root/reference/panfeed/input.py:455-468`,
+`panfeed/panfeed.py:31,47-49`): per cluster a dict strain -> [Seqinfo] and the
+int presence vector.  Only `Seqinfo.sequence` is packed; the complement string
+the reference carries (`input.py:448-452`) is implied (the kernel derives the
+reverse complement from the 2-bit codes, with pyfaidx's table for IUPAC codes).
+"""
+import numpy as np
+
+from . import capi
+
+_LUT2 = np.full(256, 255, np.uint8)
+for _i, _c in enumerate("ACGT"):
+    _LUT2[ord(_c)] = _i
+_LUT4 = np.full(256, 255, np.uint8)
+for _i, _c in enumerate(capi.AMB_ALPHABET):
+    _LUT4[ord(_c)] = _i
+_SHIFT2 = (62 - 2 * np.arange(32)).astype(np.uint64)
+_SHIFT4 = (60 - 4 * np.arange(16)).astype(np.uint64)
+
+
+class PackedCluster:
+    """One cluster, packed and ordered by sample rank (what `cluster_cutter`
+    returns in place of its k-mer dict)."""
+    __slots__ = ("idx", "clusterpresab", "seq_bytes", "sample", "target",
+                 "start", "end", "offset", "strand", "meta", "k", "canonical",
+                 "consider_missing")
+
+    def __init__(self, cluster, idx, clusterpresab, stroi):
+        self.idx = idx
+        self.clusterpresab = np.asarray(clusterpresab)
+        rank = {s: i for i, s in enumerate(sorted(cluster.keys()))}
+        rows = []
+        for strain in cluster.keys():
+            for q in cluster[strain]:
+                rows.append((rank[strain], strain, q))
+        rows.sort(key=lambda r: r[0])      # stable: paralog order is kept
+        self.seq_bytes = [r[2].sequence.encode("ascii") for r in rows]
+        self.sample = np.array([r[0] for r in rows], np.uint32)
+        self.target = np.array([r[1] in stroi for r in rows], bool)
+        self.start = np.array([r[2].start for r in rows], np.int32)
+        self.end = np.array([r[2].end for r in rows], np.int32)
+        self.offset = np.array([r[2].offset for r in rows], np.int32)
+        self.strand = np.array([r[2].strand for r in rows], np.int32)
+        self.meta = [(r[1], r[2].id, r[2].chromosome) for r in rows]
+
+    def n_records(self, k, canonical):
+        n = sum(max(0, len(b) - k + 1) for b in self.seq_bytes)
+        return n if canonical else 2 * n
+
+
+def presence_words(presab):
+    """int vector [S] -> uint32 words, bit (s & 31) of word (s >> 5)."""
+    presab = np.asarray(presab)
+    S = presab.shape[0]
+    W = (S + 31) // 32
+    bits = np.zeros(W * 32, np.uint8)
+    bits[:S] = presab != 0
+    return (bits.reshape(W, 32).astype(np.uint32) <<
+            np.arange(32, dtype=np.uint32)).sum(axis=1, dtype=np.uint64).astype(np.uint32)
+
+
+def pack_batch(packed_clusters, cluster_ids=None):
+    """-> (capi.HostBatch, seq_meta list, cluster idx list)."""
+    seq_bytes, lens = [], []
+    for pc in packed_clusters:
+        seq_bytes.extend(pc.seq_bytes)
+    n_seqs = len(seq_bytes)
+    lens = np.array([len(b) for b in seq_bytes], np.int64)
+    padded = (lens + 63) // 64 * 64
+    offs = np.zeros(n_seqs + 1, np.int64)
+    np.cumsum(padded, out=offs[1:])
+    total = int(offs[-1])
+    ascii_plane = np.full(total, ord("A"), np.uint8)
+    for b, o in zip(seq_bytes, offs[:-1]):
+        ascii_plane[o:o + len(b)] = np.frombuffer(b, np.uint8)
+    code2 = _LUT2[ascii_plane]
+    bad = code2 == 255
+    amb_seq = np.zeros(n_seqs, bool)
+    amb_plane = None
+    amb_off = np.zeros(n_seqs, np.uint64)
+    if bad.any():
+        which = np.searchsorted(offs, np.nonzero(bad)[0], side="right") - 1
+        amb_seq[np.unique(which)] = True
+        chunks, cur = [], 0
+        for i in np.nonzero(amb_seq)[0]:
+            seg = ascii_plane[offs[i]:offs[i] + padded[i]]
+            c4 = _LUT4[seg]
+            if (c4 == 255).any():
+                sym = chr(int(seg[np.nonzero(c4 == 255)[0][0]]))
+                raise ValueError(f"unsupported sequence symbol {sym!r}: only "
+                                 f"{capi.AMB_ALPHABET} (IUPAC, upper case) are accepted")
+            amb_off[i] = cur
+            chunks.append(c4)
+            cur += len(c4)
+        c4 = np.concatenate(chunks)
+        amb_plane = (c4.reshape(-1, 16).astype(np.uint64) << _SHIFT4).sum(
+            axis=1, dtype=np.uint64)
+        code2[bad] = 0
+    packed = (code2.reshape(-1, 32).astype(np.uint64) << _SHIFT2).sum(
+        axis=1, dtype=np.uint64)
+
+    seqs = np.zeros(n_seqs, capi.SEQ_DTYPE)
+    clusters = np.zeros(len(packed_clusters), capi.CLUSTER_DTYPE)
+    S = len(packed_clusters[0].clusterpresab) if packed_clusters else 0
+    W = (S + 31) // 32
+    presence = np.zeros((len(packed_clusters), W), np.uint32)
+    meta, ids = [], []
+    i = 0
+    for ci, pc in enumerate(packed_clusters):
+        n = len(pc.seq_bytes)
+        sl = slice(i, i + n)
+        seqs["cluster"][sl] = ci
+        seqs["sample"][sl] = pc.sample
+        seqs["flags"][sl] = pc.target.astype(np.uint32) * capi.PF_SEQ_TARGET
+        seqs["start"][sl] = pc.start
+        seqs["end"][sl] = pc.end
+        seqs["offset"][sl] = pc.offset
+        seqs["strand"][sl] = pc.strand
+        clusters["id"][ci] = ci if cluster_ids is None else cluster_ids[ci]
+        presence[ci] = presence_words(pc.clusterpresab)
+        meta.extend(pc.meta)
+        ids.append(pc.idx)
+        i += n
+    seqs["base_off"] = offs[:-1].astype(np.uint64)
+    seqs["len"] = lens.astype(np.uint32)
+    seqs["flags"] |= amb_seq.astype(np.uint32) * capi.PF_SEQ_AMBIGUOUS
+    seqs["amb_off"] = amb_off
+    return capi.HostBatch(packed, seqs, clusters, presence, amb_plane), meta, ids
+
+
+_ACGT = np.frombuffer(b"ACGT", np.uint8)
+_AMB = np.frombuffer(capi.AMB_ALPHABET.encode(), np.uint8)
+
+
+def kmers_to_str(kmers, k):
+    """uint64 2-bit k-mers -> numpy bytes array S{k}."""
+    kmers = np.asarray(kmers, np.uint64)
+    if kmers.size == 0:
+        return np.zeros(0, f"S{k}")
+    sh = (2 * (k - 1 - np.arange(k))).astype(np.uint64)
+    codes = ((kmers[:, None] >> sh[None, :]) & np.uint64(3)).astype(np.uint8)
+    return np.ascontiguousarray(_ACGT[codes]).view(f"S{k}").ravel()
+
+
+def wide_kmers_to_str(kmers, k):
+    """[n,2] uint64 (hi, lo) 4-bit k-mers -> numpy bytes array S{k}."""
+    kmers = np.asarray(kmers, np.uint64).reshape(-1, 2)
+    if kmers.shape[0] == 0:
+        return np.zeros(0, f"S{k}")
+    out = np.zeros((kmers.shape[0], k), np.uint8)
+    for i in range(k):
+        nib = k - 1 - i                    # nibble index from the bottom
+        word = kmers[:, 1] if nib < 16 else kmers[:, 0]
+        out[:, i] = _AMB[((word >> np.uint64(4 * (nib % 16))) & np.uint64(15)).astype(np.uint8)]
+    return np.ascontiguousarray(out).view(f"S{k}").ravel()

@@ -1,0 +1,178 @@
+"""Parity of the CUDA path (through the C-ABI) against the reference goldens
+and the C oracle.  Bit-exact after canonical sorting; pattern ids are compared
+through their full vectors (rendered to the reference's MD5 ids)."""
+import os
+
+import numpy as np
+import pytest
+
+import gpu_util
+import helpers
+import render
+from oracle import oracle_c, ref_port
+from test_oracle_c import _items
+
+pytestmark = pytest.mark.gpu
+
+
+def _render_gpu(out, S, k, consider_missing, canonical):
+    res = dict(out)
+    res["row_kmer"] = [x.decode() for x in out["row_kmer"]]
+    res["pos_seq"] = res["pos_pos"] = res["pos_used_strand"] = res["pos_kmer"] = []
+    got = render.render(res, out["ids"], out["seq_meta"], out["seqs"], S, k,
+                        consider_missing, canonical)
+    got["kmers.tsv"] = gpu_util.kmers_tsv_lines(out, k, canonical)
+    return got
+
+
+@pytest.mark.parametrize("mode", sorted(helpers.modes()))
+def test_fixture_modes_match_reference_goldens(mode):
+    kw = helpers.cli_kwargs(helpers.modes()[mode])
+    cwd = os.getcwd()
+    os.chdir(helpers.GOLDEN)
+    try:
+        items, stroi, S = _items(kw)
+    finally:
+        os.chdir(cwd)
+    out = gpu_util.run_gpu(items, stroi, S, kw["k"], not kw["non_canonical"],
+                           kw["consider_missing"], kw["no_filter"], kw["maf"],
+                           batch_clusters=3)
+    got = _render_gpu(out, S, kw["k"], kw["consider_missing"],
+                      not kw["non_canonical"])
+    for name in helpers.FILES:
+        assert sorted(got[name]) == render.golden_body(
+            helpers.golden(mode, name)), (mode, name)
+
+
+def _random_items(rng, S, k, n_clusters, L, amb_rate=0.0, div=0.03):
+    comp = str.maketrans("ACGTN", "TGCAN")
+    names = [f"g{i:04d}" for i in range(S)]
+    order = list(rng.permutation(names))
+    items = []
+    for c in range(n_clusters):
+        Lc = int(rng.integers(max(1, L // 2), L + 1))
+        anc = rng.choice(list("ACGT"), Lc)
+        founders = []
+        for _ in range(3):
+            f = anc.copy()
+            m = rng.random(Lc) < div
+            f[m] = rng.choice(list("ACGT"), int(m.sum()))
+            founders.append(f)
+        presab = np.zeros(S, dtype=int)
+        cluster, absent = {}, []
+        p_present = rng.uniform(0.2, 1.0)
+        for s in order:
+            if rng.random() > p_present:
+                absent.append(s)
+                continue
+            presab[names.index(s)] = 1
+            lst = []
+            for _ in range(2 if rng.random() < 0.1 else 1):
+                q = founders[int(rng.integers(3))].copy()
+                m = rng.random(Lc) < 0.004
+                q[m] = rng.choice(list("ACGT"), int(m.sum()))
+                if amb_rate:
+                    m = rng.random(Lc) < amb_rate
+                    q[m] = rng.choice(list("NRYK"), int(m.sum()))
+                q = "".join(q)
+                lst.append(ref_port.CutSeq(q, q.translate(comp), s + "_f", "ctg",
+                                           101, 100 + Lc,
+                                           int(rng.choice([1, -1])),
+                                           int(rng.choice([0, 5]))))
+            cluster[s] = lst
+        for s in absent:
+            cluster[s] = []
+        items.append((cluster, f"cl{c}", presab))
+    return items, set(order[:max(1, S // 10)])
+
+
+def _compare_with_oracle(items, stroi, S, k, canon, cm, nf, maf, **gpu_kw):
+    want = oracle_c.run(items, stroi, k, canon, cm, nf, maf, n_threads=4)
+    w = dict(want)
+    w["row_kmer"] = [x.decode() for x in want["row_kmer"]]
+    w["pos_kmer"] = [x.decode() for x in want["pos_kmer"]]
+    want_lines = render.render(w, want["ids"], want["seq_meta"], want["seqs"],
+                               S, k, cm, canon)
+    out = gpu_util.run_gpu(items, stroi, S, k, canon, cm, nf, maf, **gpu_kw)
+    got = _render_gpu(out, S, k, cm, canon)
+    for name in helpers.FILES:
+        assert sorted(got[name]) == sorted(want_lines[name]), name
+    return out, want
+
+
+CASES = [
+    # S,   k, clusters, L,  canon, cm,    nf,    maf,  amb,  sort_bits, batch
+    (40,  31, 5, 300, True,  False, False, 0.01, 0.0,  0, 2),
+    (40,  31, 5, 300, True,  False, False, 0.01, 0.0,  8, 5),    # heavy prefix sharing
+    (70,  15, 4, 200, False, False, True,  0.05, 0.0,  16, 4),
+    (33,  32, 4, 250, True,  True,  False, 0.10, 0.0,  0, 1),
+    (33,  32, 4, 250, False, True,  True,  0.02, 0.002, 8, 2),   # k=32 non-canonical + IUPAC
+    (129, 21, 3, 400, True,  True,  True,  0.01, 0.001, 0, 3),
+    (5,   4,  3, 60,  True,  False, False, 0.0,  0.0,  8, 3),    # tiny even k: palindromes
+    (1,   31, 2, 100, True,  False, False, 0.01, 0.0,  0, 2),    # single sample
+    (600, 31, 2, 700, True,  False, False, 0.01, 0.0,  0, 1),    # multi-tile segments
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
+def test_random_clusters_match_oracle(case):
+    S, k, nc, L, canon, cm, nf, maf, amb, sb, bc = case
+    rng = np.random.default_rng(1000 + S * 7 + k)
+    items, stroi = _random_items(rng, S, k, nc, L, amb)
+    _compare_with_oracle(items, stroi, S, k, canon, cm, nf, maf,
+                         batch_clusters=bc, sort_bits=sb)
+
+
+def test_empty_and_ragged_batches():
+    rng = np.random.default_rng(3)
+    items, stroi = _random_items(rng, 12, 31, 3, 120)
+    # a cluster with no sequences at all, one whose sequences are all shorter than k
+    names = sorted(items[0][0].keys())
+    empty = ({s: [] for s in names}, "cl_empty", np.zeros(12, dtype=int))
+    short_seq = ref_port.CutSeq("ACGTACGTAC", "TGCATGCATG", "x", "c", 1, 10, 1, 0)
+    presab = np.zeros(12, dtype=int)
+    presab[0] = 1
+    short = ({s: ([short_seq] if s == names[0] else []) for s in names},
+             "cl_short", presab)
+    items = [empty] + items[:1] + [short] + items[1:] + [empty]
+    _compare_with_oracle(items, stroi, 12, 31, True, False, False, 0.01,
+                         batch_clusters=2)
+
+
+def test_synthetic_device_batch_matches_oracle():
+    """pf_synth_fill batch: CUDA path vs C oracle on the unpacked bases."""
+    from panfeed_b200 import capi, packer
+    S, C, L, k = 96, 6, 420, 31
+    hb = capi.synth_batch(0, 20261018, S, C, total_clusters=C, gene_len=L,
+                          all_targets=False)
+    # unpack to ASCII for the oracle
+    sh = (62 - 2 * np.arange(32)).astype(np.uint64)
+    codes = ((hb.packed[:, None] >> sh[None, :]) & np.uint64(3)).astype(np.uint8).ravel()
+    ascii_plane = np.frombuffer(b"ACGT", np.uint8)[codes]
+    seqs = np.zeros(len(hb.seqs), oracle_c.SEQ_DTYPE)
+    for f in ("len", "cluster", "sample", "start", "end", "offset", "strand"):
+        seqs[f] = hb.seqs[f]
+    seqs["off"] = hb.seqs["base_off"]
+    idx = np.arange(S)
+    presab = ((hb.presence[:, idx >> 5] >> (idx & 31)) & 1).astype(np.uint8)
+    want = oracle_c.run_arrays(ascii_plane, seqs, presab, k, True, False, False,
+                               0.01, n_threads=4)
+    ctx = capi.Context(k, S, maf=0.01)
+    try:
+        ctx.submit(hb)
+        r = ctx.collect()
+        st = ctx.stats()
+    finally:
+        ctx.close()
+    assert st["instances"] == want["n_instances"]
+    got_rows = sorted(zip(r["row_cluster"].tolist(),
+                          packer.kmers_to_str(r["row_kmer"], k).tolist(),
+                          r["row_count"].tolist(),
+                          [r["new_kmer_patterns"][p].tobytes() for p in r["row_pattern"]]))
+    want_rows = sorted(zip(want["row_cluster"].tolist(), want["row_kmer"].tolist(),
+                           want["row_count"].tolist(),
+                           [want["kmer_pattern_bits"][p].tobytes() for p in want["row_pattern"]]))
+    assert len(got_rows) > 100
+    assert got_rows == want_rows
+    assert len(r["new_kmer_patterns"]) == len(want["kmer_pattern_bits"])
+    assert st["unique_kmers"] == want["n_unique"]
