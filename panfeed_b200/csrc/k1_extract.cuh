@@ -155,7 +155,7 @@ __global__ void k1_extract_wide(const uint64_t* __restrict__ amb_codes,
                                 const SeqDev* __restrict__ seqs,
                                 const uint32_t* __restrict__ wide_seqs, uint32_t n_wide_seqs,
                                 int k, Key128* __restrict__ keys, uint32_t* __restrict__ vals,
-                                uint64_t* __restrict__ pos_wide) {
+                                uint64_t* __restrict__ pos_wide, uint8_t* __restrict__ pos_flags) {
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t stride = gridDim.x * (blockDim.x >> 5);
@@ -190,6 +190,9 @@ __global__ void k1_extract_wide(const uint64_t* __restrict__ amb_codes,
         if (target && is_amb) {
           pos_wide[2 * ((size_t)d.pwide_off + p)] = canon.hi;
           pos_wide[2 * ((size_t)d.pwide_off + p) + 1] = canon.lo;
+          // runs after the narrow kernel on the same stream: the strand choice of an
+          // ambiguous window must come from the 4-bit comparison
+          pos_flags[(size_t)d.pos_off + p] = (uint8_t)((use_rc ? 1u : 0u) | 2u);
         }
       } else {
         const size_t rec = (size_t)d.wrec_off + 2 * (size_t)p;

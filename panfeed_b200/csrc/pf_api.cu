@@ -687,12 +687,12 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       k1_extract_wide<true><<<grid, 256, 0, st>>>(ctx->d_amb.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(),
                                                  ctx->d_wide_seqs.as<uint32_t>(), ctx->n_wide_seqs, (int)P.k,
                                                  Wd.keys[0].as<Key128>(), Wd.vals[0].as<uint32_t>(),
-                                                 ctx->d_pos_wide.as<uint64_t>());
+                                                 ctx->d_pos_wide.as<uint64_t>(), ctx->d_pos_flags.as<uint8_t>());
     else
       k1_extract_wide<false><<<grid, 256, 0, st>>>(ctx->d_amb.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(),
                                                   ctx->d_wide_seqs.as<uint32_t>(), ctx->n_wide_seqs, (int)P.k,
                                                   Wd.keys[0].as<Key128>(), Wd.vals[0].as<uint32_t>(),
-                                                  ctx->d_pos_wide.as<uint64_t>());
+                                                  ctx->d_pos_wide.as<uint64_t>(), ctx->d_pos_flags.as<uint8_t>());
     ctx->launches++;
   }
   CU(cudaGetLastError());
