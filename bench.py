@@ -1,0 +1,429 @@
+#!/usr/bin/env python
+"""Benchmark of the per-gene-cluster k-mer streaming hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step = one pass of K1..K4 over the whole synthetic pangenome of BASELINE.json
+config #2 (500 genomes x 4,000 gene clusters, 1.2 kb cut sequences, k=31,
+first pass).  `value` = input bases/s with the batch already resident in HBM;
+`e2e` = the same through pf_submit/pf_collect from pinned host buffers
+(H2D + kernels + D2H).  N > 1: every rank runs its own 4,000 clusters of a
+4,000*N-cluster pangenome (weak scaling) and a step ends with the global
+pattern dedup exchange (NCCL all-to-all).
+
+`--impl reference` times the CPU restatement of the reference's own code path
+(oracle/ref_port.py, pure Python + numpy like the reference, one process per
+host core) on a bounded sample of the same workload; the reference package
+itself cannot travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20261018 + 2          # seed = 20261018 + config_id
+R_BYTES = 12                 # record: 8-byte key + 4-byte sample rank
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--samples", type=int, default=500)
+    p.add_argument("--clusters", type=int, default=4000)
+    p.add_argument("--gene-len", type=int, default=1200)
+    p.add_argument("-k", type=int, default=31)
+    p.add_argument("--maf", type=float, default=0.01)
+    p.add_argument("--consider-missing", action="store_true")
+    p.add_argument("--sort-bits", type=int, default=0)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=15.0)
+    return p.parse_args()
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.device)], stdout=self.f,
+                stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().split("\n") if r]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# CPU legs (oracle = test infrastructure; allowed here as the measured baseline)
+# --------------------------------------------------------------------------
+def unpack_ascii(hb, seq_slice):
+    """ASCII bases + oracle seq array for a slice of a HostBatch's sequences."""
+    from oracle import oracle_c
+    seqs = hb.seqs[seq_slice]
+    w0 = int(seqs["base_off"][0]) // 32
+    w1 = int(seqs["base_off"][-1] + (seqs["len"][-1] + 63) // 64 * 64) // 32
+    sh = (62 - 2 * np.arange(32)).astype(np.uint64)
+    codes = ((hb.packed[w0:w1, None] >> sh[None, :]) & np.uint64(3)).astype(np.uint8).ravel()
+    ascii_plane = np.frombuffer(b"ACGT", np.uint8)[codes]
+    out = np.zeros(len(seqs), oracle_c.SEQ_DTYPE)
+    for f in ("len", "sample", "start", "end", "offset", "strand"):
+        out[f] = seqs[f]
+    out["cluster"] = seqs["cluster"] - seqs["cluster"][0]
+    out["off"] = seqs["base_off"] - np.uint64(w0 * 32)
+    return ascii_plane, out
+
+
+def cpu_baseline_c(hb, S, k, maf, consider_missing, budget_s):
+    """C oracle, all host cores, on the first n clusters of the workload."""
+    from oracle import oracle_c
+    oracle_c.build()
+    cores = os.cpu_count() or 1
+    first = np.searchsorted(hb.seqs["cluster"], np.arange(len(hb.clusters) + 1))
+    idx = np.arange(S)
+    n = min(len(hb.clusters), max(cores, 8))
+    best = None
+    while True:
+        sl = slice(int(first[0]), int(first[n]))
+        ascii_plane, seqs = unpack_ascii(hb, sl)
+        presab = ((hb.presence[:n, idx >> 5] >> (idx & 31)) & 1).astype(np.uint8)
+        t0 = time.perf_counter()
+        res = oracle_c.run_arrays(ascii_plane, seqs, presab, k, True, consider_missing,
+                                  False, maf, n_threads=cores)
+        dt = time.perf_counter() - t0
+        bases = int(seqs["len"].sum())
+        best = {"value": bases / dt, "unit": "bases/s", "cores": cores, "kind": "port",
+                "sample": f"oracle/oracle.c (C restatement, {cores} threads) on the first {n} "
+                          f"clusters of the workload: {bases} bases in {dt:.2f} s",
+                "unique_kmers_per_s": res["n_unique"] / dt}
+        if dt >= budget_s / 3 or n >= len(hb.clusters):
+            return best
+        n = min(len(hb.clusters), max(n + 1, int(n * min(8.0, budget_s / max(dt, 1e-3)) * 0.7)))
+
+
+def numpy_cluster(rng, S, L, cluster_index, total_clusters):
+    """One synthetic cluster as reference-style Seqinfo lists (model of SURVEY §8(d))."""
+    from oracle.ref_port import CutSeq
+    comp = str.maketrans("ACGT", "TGCA")
+    anc = rng.integers(0, 4, L)
+    founders = []
+    for _ in range(8):
+        f = anc.copy()
+        m = rng.random(L) < 0.01
+        f[m] = (f[m] + rng.integers(1, 4, int(m.sum()))) & 3
+        founders.append(f)
+    core = cluster_index < int(0.6 * total_clusters)
+    p = 0.99 if core else rng.uniform(0.05, 0.95)
+    names = [f"g{i:05d}" for i in range(S)]
+    cluster, presab, absent = {}, np.zeros(S, dtype=int), []
+    lut = np.frombuffer(b"ACGT", np.uint8)
+    for i, s in enumerate(names):
+        if rng.random() >= p:
+            absent.append(s)
+            continue
+        presab[i] = 1
+        lst = []
+        for _ in range(2 if rng.random() < 0.01 else 1):
+            q = founders[int(rng.integers(8))].copy()
+            m = rng.random(L) < 0.001
+            q[m] = (q[m] + rng.integers(1, 4, int(m.sum()))) & 3
+            seq = lut[q].tobytes().decode()
+            lst.append(CutSeq(seq, seq.translate(comp), s + "_1", "ctg", 1001, 1000 + L,
+                              int(rng.choice([1, -1])), 100))
+        cluster[s] = lst
+    for s in absent:
+        cluster[s] = []
+    return cluster, f"group_{cluster_index}", presab
+
+
+def _ref_worker(job):
+    from oracle import ref_port
+    item, k, maf, cm = job
+    res = ref_port.kmer_stage(item, k, "", True, cm)
+    pats = set()
+    a, b, c = ref_port.pattern_stage((res,), True, maf, cm, pats)
+    bases = sum(len(q.sequence) for v in item[0].values() for q in v)
+    return bases, len(res[1]), len(b) + len(c)
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's algorithm as restated in oracle/ref_port.py
+    (pure Python + numpy, like the reference), one worker process per host core, on a
+    bounded sample of the same workload per step."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(SEED)
+    per_step = cores                      # one cluster per core per step
+    ctx = mp.get_context("fork")
+    steps = args.warmup + args.steps
+    items = [[numpy_cluster(rng, args.samples, args.gene_len, (s * per_step + i) % args.clusters,
+                            args.clusters) for i in range(per_step)] for s in range(min(steps, 2))]
+    times, bases_l, uniq_l = [], [], []
+    with ctx.Pool(cores) as pool:
+        for s in range(steps):
+            jobs = [(it, args.k, args.maf, args.consider_missing) for it in items[s % len(items)]]
+            t0 = time.perf_counter()
+            out = pool.map(_ref_worker, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+                bases_l.append(sum(o[0] for o in out))
+                uniq_l.append(sum(o[1] for o in out))
+    total_t = sum(times)
+    value = sum(bases_l) / total_t
+    line = {
+        "impl": "reference", "metric": "input_bases_per_s", "value": value, "unit": "bases/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_t / max(1, len(times)), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(args),
+        "unique_kmers_per_s": sum(uniq_l) / total_t,
+        "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "port",
+                         "sample": f"oracle/ref_port.py (Python restatement of panfeed.py:23-235; the "
+                                   f"reference package cannot travel to the GPU box), {cores} worker "
+                                   f"processes, {per_step} clusters of the workload per step"},
+        "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE.json configs[1]: synthetic {args.samples} genomes x {args.clusters} "
+                        f"gene clusters (~1 kb + 100 bp flanks = {args.gene_len} bp), first pass, k={args.k}",
+            "samples": args.samples, "clusters_per_gpu": args.clusters, "gene_len": args.gene_len,
+            "k": args.k, "maf": args.maf, "consider_missing": bool(args.consider_missing),
+            "l2": "inputs (>= 0.6 GB packed bases, >= 28 GB of records per step) far exceed the 126 MB L2"}
+
+
+# --------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from panfeed_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    S, C, L, k = args.samples, args.clusters, args.gene_len, args.k
+    total_clusters = C * world
+    hb = capi.synth_batch(local, SEED, S, C, first_cluster=rank * C, total_clusters=total_clusters,
+                          gene_len=L, pinned=True)
+    n_bases = hb.n_bases
+    ctx = capi.Context(k, S, canonical=True, consider_missing=args.consider_missing,
+                       cluster_equal_filter=False, emit_positions=False, maf=args.maf,
+                       sort_bits=args.sort_bits, device=local)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+    exch = None
+    if world > 1:
+        from panfeed_b200 import dist as pfdist
+        exch = pfdist.PatternExchange(ctx, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        ctx.reset_patterns()
+        ctx.execute()
+        if exch is not None:
+            exch.run()
+
+    # ---- value: batch resident in HBM -------------------------------------
+    ctx.upload(hb)
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    launches0 = ctx.stats()["total_launches"]
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    stage_ms = {}
+    for _ in range(args.steps):
+        step_resident()
+        st = ctx.stats()
+        for key in ("ms_extract", "ms_hist", "ms_sort", "ms_mark", "ms_count", "ms_reduce",
+                    "ms_dedup", "ms_total"):
+            stage_ms[key] = stage_ms.get(key, 0.0) + st[key]
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    st = ctx.stats()
+    launches = st["total_launches"] - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * n_bases / (ms_step * 1e-3)
+    # sizes of one step: read from a collect of the last execution
+    ctx.collect(copy=False)
+    st = ctx.stats()
+    M = st["instances"]             # exactly one collected batch so far
+    U = st["unique_kmers"]
+    rows = st["rows"]
+    passes = st["sort_passes"]
+    for key in stage_ms:
+        stage_ms[key] /= args.steps
+
+    # ---- e2e: pinned host buffers -> pf_submit -> pf_collect -----------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            ctx.reset_patterns()
+            ctx.submit(hb)
+            ctx.collect(copy=False)
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(args.steps):
+            ctx.reset_patterns()
+            ctx.submit(hb)
+            r = ctx.collect(copy=False)
+            if exch is not None:
+                exch.run()
+            d2h = r["d2h_bytes"]
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = (hb.packed.nbytes + len(hb.seqs) * 64 + len(hb.clusters) * 32 + hb.presence.nbytes
+               + (M // 4096 + len(hb.clusters)) * 16)
+        e2e = {"value": world * n_bases * args.steps / dt, "unit": "bases/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * dt / args.steps}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        pass_ms = stage_ms["ms_sort"] / max(1, passes)
+        pass_bytes = 2 * R_BYTES * M
+        achieved = pass_bytes / (pass_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                "k2_onesweep_pass_bytes_per_launch")
+        except Exception:
+            pass
+        # whole-path algorithmic bytes per SURVEY.md §8(d), declared 8-pass model
+        alg = {
+            "k1_extract": n_bases / 4 + 32 * len(hb.seqs) + R_BYTES * M,
+            "k2_sort_declared_8_passes": 8 * M + 8 * 2 * R_BYTES * M,
+            "k3_reduce": R_BYTES * M + 12 * U + rows * 4 * ((S + 31) // 32),
+        }
+        stages = {
+            "k1_extract": {"ms": stage_ms["ms_extract"], "alg_GBps": alg["k1_extract"] / stage_ms["ms_extract"] / 1e6},
+            "k2_histogram": {"ms": stage_ms["ms_hist"], "alg_GBps": 8 * M / max(stage_ms["ms_hist"], 1e-6) / 1e6},
+            "k2_onesweep_passes": {"ms": stage_ms["ms_sort"], "passes": passes,
+                                   "alg_GBps": passes * pass_bytes / stage_ms["ms_sort"] / 1e6,
+                                   "declared_model_GBps": alg["k2_sort_declared_8_passes"] /
+                                   (stage_ms["ms_sort"] + stage_ms["ms_hist"]) / 1e6},
+            "k3_mark_count_emit": {"ms": stage_ms["ms_mark"] + stage_ms["ms_count"] + stage_ms["ms_reduce"],
+                                   "alg_GBps": alg["k3_reduce"] / (stage_ms["ms_mark"] + stage_ms["ms_count"]
+                                                                   + stage_ms["ms_reduce"]) / 1e6},
+            "k4_dedup": {"ms": stage_ms["ms_dedup"]},
+        }
+        line = {
+            "metric": "input_bases_per_s", "value": value, "unit": "bases/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": workload_config(args),
+            "unique_kmers_per_s": world * U / (ms_step * 1e-3),
+            "bases_per_step_per_gpu": n_bases, "kmer_instances_per_step_per_gpu": M,
+            "unique_kmers_per_step_per_gpu": U, "rows_per_step_per_gpu": rows,
+            "patterns_per_gpu": st["kmer_patterns"],
+            "roofline": {"bound": "hbm", "kernel": "k2_onesweep_pass<u64>",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": pass_bytes,
+                         "launch_ms": pass_ms, "launches_per_step": passes,
+                         "note": "one radix pass reads and writes every 12-byte record once (2*R*M)"},
+            "stages": stages,
+            "end_to_end_alg_bytes_per_base_declared": sum(alg.values()) / n_bases,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_c(hb, S, k, args.maf, args.consider_missing,
+                                                  args.cpu_seconds)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

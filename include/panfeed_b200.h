@@ -161,8 +161,11 @@ typedef struct pf_stats {
   uint64_t cluster_patterns; /* P (cluster namespace)                               */
   uint32_t sort_passes;      /* radix passes used by the last batch                  */
   uint32_t launches;         /* kernels launched by the last batch                   */
-  /* device time of the last batch, CUDA events on the context stream */
-  float ms_h2d, ms_extract, ms_sort, ms_reduce, ms_dedup, ms_d2h, ms_total;
+  /* device time of the last batch, CUDA events on the context stream:
+     h2d | K1 extract | K2 histogram | K2 onesweep passes | K3 mark runs |
+     K3 count (incl. the host sync for the run count) | K3 emit + cluster-row
+     dedup (incl. the host sync for the row count) | K4 dedup | d2h | K1..K4 */
+  float ms_h2d, ms_extract, ms_hist, ms_sort, ms_mark, ms_count, ms_reduce, ms_dedup, ms_d2h, ms_total;
   uint64_t total_launches;   /* kernels launched since pf_create                     */
 } pf_stats;
 

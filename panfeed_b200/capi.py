@@ -85,8 +85,10 @@ class Stats(C.Structure):
                 ("rows", C.c_uint64), ("kmer_patterns", C.c_uint64),
                 ("cluster_patterns", C.c_uint64), ("sort_passes", C.c_uint32),
                 ("launches", C.c_uint32), ("ms_h2d", C.c_float),
-                ("ms_extract", C.c_float), ("ms_sort", C.c_float),
-                ("ms_reduce", C.c_float), ("ms_dedup", C.c_float),
+                ("ms_extract", C.c_float), ("ms_hist", C.c_float),
+                ("ms_sort", C.c_float), ("ms_mark", C.c_float),
+                ("ms_count", C.c_float), ("ms_reduce", C.c_float),
+                ("ms_dedup", C.c_float),
                 ("ms_d2h", C.c_float), ("ms_total", C.c_float),
                 ("total_launches", C.c_uint64)]
 
@@ -158,10 +160,11 @@ def maf_window(maf, n):
     return (lo.value, hi.value) if ok else None
 
 
-def _np(ptr, n, dtype):
+def _np(ptr, n, dtype, copy=True):
     if n == 0:
         return np.zeros(0, dtype)
-    return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
+    a = np.ctypeslib.as_array(ptr, shape=(int(n),))
+    return a.astype(dtype, copy=True) if copy else a
 
 
 class HostBatch:
@@ -240,9 +243,12 @@ class Context:
         self._check(self.lib.pf_submit(self.h, C.byref(s)))
 
     def collect(self, copy=True):
+        """Results of the last execution.  copy=False returns views into the
+        context's pinned buffers, valid until the next collect()."""
         r = BatchResult()
         self._check(self.lib.pf_collect(self.h, C.byref(r)))
         nr, nw = int(r.n_rows), int(r.n_wide_rows)
+        _np = lambda p, n, d: globals()["_np"](p, n, d, copy)  # noqa: E731
         out = {
             "row_cluster": _np(r.row_cluster, nr, np.uint32),
             "row_kmer": _np(r.row_kmer, nr, np.uint64),
@@ -269,6 +275,8 @@ class Context:
             "pos_wide_kmer": _np(r.pos_wide_kmer, 2 * r.n_pos_wide,
                                  np.uint64).reshape(-1, 2),
         }
+        out["d2h_bytes"] = int(sum(v.nbytes for v in out.values()
+                                   if isinstance(v, np.ndarray)))
         return out
 
     def reset_patterns(self):

@@ -58,7 +58,7 @@ struct WidthState {       // per key width (narrow u64 / wide Key128)
   int final_buf = 0;      // which of keys[]/vals[] holds the sorted records
 };
 
-enum Ev { EV_START, EV_EXTRACT, EV_SORT, EV_REDUCE, EV_DEDUP, EV_END, EV_COUNT };
+enum Ev { EV_START, EV_EXTRACT, EV_HIST, EV_SORT, EV_MARK, EV_COUNTED, EV_REDUCE, EV_DEDUP, EV_END, EV_COUNT };
 
 }  // namespace
 
@@ -489,11 +489,10 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
 namespace {
 
 template <typename KeyT>
-int sort_width(pf_ctx* ctx, WidthState& w, int ticket_idx) {
-  if (w.n_records == 0) { w.final_buf = 0; return PF_OK; }
+int hist_width(pf_ctx* ctx, WidthState& w) {
+  if (w.n_records == 0) return PF_OK;
   cudaStream_t st = ctx->stream;
-  const int key_bits = KeyTraits<KeyT>::kBits;
-  const int shift0 = key_bits - w.sort_bits;
+  const int shift0 = KeyTraits<KeyT>::kBits - w.sort_bits;
   const uint32_t n_seg = ctx->n_clusters;
   CU(cudaMemsetAsync(w.seg_hist.p, 0, (size_t)n_seg * w.passes * kRadix * 4, st));
   const uint32_t hist_ctas = std::min<uint32_t>(w.n_tiles, 148 * 8);
@@ -504,6 +503,15 @@ int sort_width(pf_ctx* ctx, WidthState& w, int ticket_idx) {
   const uint32_t rows = n_seg * w.passes;
   k2_scan_histogram<<<cdiv(rows, 8), 256, 0, st>>>(w.seg_hist.as<uint32_t>(), w.seg_start.as<uint32_t>(), rows, w.passes);
   ctx->launches += 2;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
+template <typename KeyT>
+int passes_width(pf_ctx* ctx, WidthState& w, int ticket_idx) {
+  if (w.n_records == 0) { w.final_buf = 0; return PF_OK; }
+  cudaStream_t st = ctx->stream;
+  const int shift0 = KeyTraits<KeyT>::kBits - w.sort_bits;
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
   int src = 0;
   for (int p = 0; p < w.passes; ++p) {
@@ -619,6 +627,29 @@ int dedup(pf_ctx* ctx, PatternSpace& s, const uint32_t* cand, uint32_t n, DevBuf
   return PF_OK;
 }
 
+// A previous pf_execute that was never collected: fold its new-pattern count in.
+int finalize_pending(pf_ctx* ctx) {
+  if (!ctx->executed) return PF_OK;
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->kp.n = ctx->kp_base + ctx->h_counters.as<uint32_t>()[C_NEW_KP];
+  return PF_OK;
+}
+
+void fill_timings(pf_ctx* ctx) {
+  pf_stats& s = ctx->stats;
+  auto ms = [](cudaEvent_t a, cudaEvent_t b) { float m = 0; if (cudaEventElapsedTime(&m, a, b) != cudaSuccess) { cudaGetLastError(); m = 0; } return m; };
+  s.ms_h2d = ms(ctx->ev_h2d[0], ctx->ev_h2d[1]);
+  s.ms_extract = ms(ctx->ev[EV_START], ctx->ev[EV_EXTRACT]);
+  s.ms_hist = ms(ctx->ev[EV_EXTRACT], ctx->ev[EV_HIST]);
+  s.ms_sort = ms(ctx->ev[EV_HIST], ctx->ev[EV_SORT]);
+  s.ms_mark = ms(ctx->ev[EV_SORT], ctx->ev[EV_MARK]);
+  s.ms_count = ms(ctx->ev[EV_MARK], ctx->ev[EV_COUNTED]);
+  s.ms_reduce = ms(ctx->ev[EV_COUNTED], ctx->ev[EV_REDUCE]);
+  s.ms_dedup = ms(ctx->ev[EV_REDUCE], ctx->ev[EV_DEDUP]);
+  s.ms_total = ms(ctx->ev[EV_START], ctx->ev[EV_END]);
+  s.sort_passes = (uint32_t)ctx->nar.passes;
+}
+
 int check_device_error(pf_ctx* ctx) {
   const uint32_t e = ctx->h_counters.as<uint32_t>()[C_ERR];
   if (e) return fail(ctx, PF_ERR_INTERNAL, "device watchdog: look-back chain stalled (code %u)", e);
@@ -638,11 +669,8 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   WidthState& Wd = ctx->wid;
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
   uint32_t* hcnt = ctx->h_counters.as<uint32_t>();
-  if (ctx->executed) {      // a previous execution was never collected: fold its pattern count in
-    CU(cudaStreamSynchronize(st));
-    ctx->kp.n = ctx->kp_base + hcnt[C_NEW_KP];
-    ctx->executed = false;
-  }
+  TRY(finalize_pending(ctx));
+  ctx->executed = false;
   ctx->kp_base = ctx->kp.n;
   ctx->cp_base = ctx->cp.n;
 
@@ -699,13 +727,17 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   CU(cudaEventRecord(ctx->ev[EV_EXTRACT], st));
 
   // ---- K2 ---------------------------------------------------------------
-  TRY(sort_width<uint64_t>(ctx, N, C_TICKET_N));
-  TRY(sort_width<Key128>(ctx, Wd, C_TICKET_W));
+  TRY(hist_width<uint64_t>(ctx, N));
+  TRY(hist_width<Key128>(ctx, Wd));
+  CU(cudaEventRecord(ctx->ev[EV_HIST], st));
+  TRY(passes_width<uint64_t>(ctx, N, C_TICKET_N));
+  TRY(passes_width<Key128>(ctx, Wd, C_TICKET_W));
   CU(cudaEventRecord(ctx->ev[EV_SORT], st));
 
   // ---- K3: runs ------------------------------------------------------------
   TRY(mark_width<uint64_t>(ctx, N, C_TICKET_MARK_N, C_RUNS_N));
   TRY(mark_width<Key128>(ctx, Wd, C_TICKET_MARK_W, C_RUNS_W));
+  CU(cudaEventRecord(ctx->ev[EV_MARK], st));
   CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   TRY(check_device_error(ctx));
@@ -716,6 +748,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   ro.key_words = ctx->Wk; ro.pattern_words = ctx->W;
   TRY((runs_width<uint64_t, false>(ctx, N, ro)));
   TRY((runs_width<Key128, false>(ctx, Wd, ro)));
+  CU(cudaEventRecord(ctx->ev[EV_COUNTED], st));
   if (N.n_runs) TRY(scan_inplace(ctx, N.vals[N.final_buf ^ 1].as<uint32_t>(), N.n_runs, counters + C_ROWS_N));
   if (Wd.n_runs) TRY(scan_inplace(ctx, Wd.vals[Wd.final_buf ^ 1].as<uint32_t>(), Wd.n_runs, counters + C_ROWS_W));
 
@@ -848,14 +881,11 @@ extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
   s.cluster_patterns = ctx->cp.n;
   s.sort_passes = (uint32_t)N.passes;
   s.total_launches = ctx->launches;
-  auto ms = [](cudaEvent_t a, cudaEvent_t b) { float m = 0; cudaEventElapsedTime(&m, a, b); return m; };
-  s.ms_h2d = ms(ctx->ev_h2d[0], ctx->ev_h2d[1]);
-  s.ms_extract = ms(ctx->ev[EV_START], ctx->ev[EV_EXTRACT]);
-  s.ms_sort = ms(ctx->ev[EV_EXTRACT], ctx->ev[EV_SORT]);
-  s.ms_reduce = ms(ctx->ev[EV_SORT], ctx->ev[EV_REDUCE]);
-  s.ms_dedup = ms(ctx->ev[EV_REDUCE], ctx->ev[EV_DEDUP]);
-  s.ms_d2h = ms(ctx->ev_d2h[0], ctx->ev_d2h[1]);
-  s.ms_total = ms(ctx->ev[EV_START], ctx->ev[EV_END]);
+  fill_timings(ctx);
+  {
+    float m = 0;
+    if (cudaEventElapsedTime(&m, ctx->ev_d2h[0], ctx->ev_d2h[1]) == cudaSuccess) s.ms_d2h = m;
+  }
   return PF_OK;
 }
 
@@ -863,6 +893,7 @@ extern "C" int pf_reset_patterns(pf_ctx* ctx) {
   if (!ctx) return PF_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->executed = false;
   for (PatternSpace* s : {&ctx->kp, &ctx->cp}) {
     s->n = 0;
     s->x_n_unique = 0;
@@ -877,6 +908,7 @@ extern "C" int pf_reset_patterns(pf_ctx* ctx) {
 extern "C" int pf_patterns_export(pf_ctx* ctx, int cluster_namespace, uint64_t first, uint64_t count,
                                   uint32_t* host_out) {
   if (!ctx || !host_out) return PF_ERR_INVALID;
+  TRY(finalize_pending(ctx));
   PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
   if (first + count > s.n) return fail(ctx, PF_ERR_INVALID, "pattern range [%llu,%llu) beyond %llu",
                                        (unsigned long long)first, (unsigned long long)(first + count),
@@ -891,6 +923,10 @@ extern "C" int pf_patterns_export(pf_ctx* ctx, int cluster_namespace, uint64_t f
 
 extern "C" int pf_stats_get(pf_ctx* ctx, pf_stats* out) {
   if (!ctx || !out) return PF_ERR_INVALID;
+  if (ctx->executed) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    fill_timings(ctx);
+  }
   *out = ctx->stats;
   out->total_launches = ctx->launches;
   return PF_OK;
@@ -1068,6 +1104,7 @@ extern "C" int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t wor
                                 uint64_t capacity_patterns, uint64_t* counts_host) {
   if (!ctx || !counts_host || world == 0) return PF_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
+  TRY(finalize_pending(ctx));
   PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
   cudaStream_t st = ctx->stream;
   const uint32_t n = (uint32_t)s.n;
