@@ -372,10 +372,11 @@ def main():
         pass_ms = stage_ms["ms_sort"] / max(1, passes)
         pass_bytes = 2 * R_BYTES * M
         achieved = pass_bytes / (pass_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = None       # dram read+write bytes per launch, scaled from the ncu capture
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-                "k2_onesweep_pass_bytes_per_launch")
+            per_rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+                "k2_onesweep_pass_dram_bytes_per_record")
+            traffic = per_rec * M if per_rec else None
         except Exception:
             pass
         # whole-path algorithmic bytes per SURVEY.md §8(d), declared 8-pass model

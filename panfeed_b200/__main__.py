@@ -1,0 +1,116 @@
+"""`panfeed` command line of the B200 build: the reference's options
+(`/root/reference/panfeed/__main__.py:84-223`) and wiring (`:226-369`), with the
+two hot callables running on the GPU.  `--cores` and `-ql` are accepted for
+compatibility; clusters are batched to the device instead of forked workers, so
+row order is deterministic and `--compress` output is always valid gzip."""
+import argparse
+import logging
+import sys
+from functools import partial
+
+from . import __version__
+from .input import (clean_up_fasta, iter_gene_clusters, prep_data_n_fasta, set_input_output,
+                    what_are_my_inputfiles)
+from .panfeed import PatternStore, cluster_cutter, pattern_hasher, write_headers
+
+logger = logging.getLogger("panfeed")
+
+
+def set_logging(v):
+    logger.propagate = True
+    logger.setLevel(logging.DEBUG)
+    ch = logging.StreamHandler()
+    ch.setLevel(logging.DEBUG if v >= 1 else logging.INFO)
+    ch.setFormatter(logging.Formatter("%(asctime)s - %(name)s - %(message)s", "%H:%M:%S"))
+    logger.addHandler(ch)
+
+
+def get_options(argv=None):
+    p = argparse.ArgumentParser(
+        prog="panfeed",
+        description="Get gene cluster specific k-mers from a set of bacterial genomes "
+                    "(B200-native build)")
+    p.add_argument("-g", "--gff", required=True,
+                   help="Directory with all samples' GFF files, or a file listing them")
+    p.add_argument("-p", "--presence-absence", required=True,
+                   help="Gene clusters presence absence table as output by panaroo")
+    p.add_argument("--targets", default=None,
+                   help="File with the samples whose k-mer positions are logged")
+    p.add_argument("--genes", default=None,
+                   help="File with the gene clusters to process (default: all)")
+    p.add_argument("-o", "--output", default="panfeed",
+                   help="Output directory (must not exist)")
+    p.add_argument("-f", "--fasta", help="Directory or file of files with nucleotide fastas")
+    p.add_argument("-k", "--kmer-length", type=int, default=31, help="K-mer length (1..32)")
+    p.add_argument("--maf", type=float, default=0.01, help="Minor allele frequency threshold")
+    p.add_argument("--upstream", type=int, default=0)
+    p.add_argument("--downstream", type=int, default=0)
+    p.add_argument("--downstream-start-codon", action="store_true", default=False)
+    p.add_argument("--non-canonical", action="store_true", default=False)
+    p.add_argument("--no-filter", action="store_true", default=False)
+    p.add_argument("--consider-missing", action="store_true", default=False)
+    p.add_argument("--multiple-files", action="store_true", default=False)
+    p.add_argument("--compress", action="store_true", default=False)
+    p.add_argument("--cores", type=int, default=1, help="accepted for compatibility (GPU build)")
+    p.add_argument("-ql", "--queue-limit", type=int, default=3,
+                   help="accepted for compatibility (GPU build)")
+    p.add_argument("--stop-on-missing", action="store_true", default=False)
+    p.add_argument("--device", type=int, default=0, help="CUDA device")
+    p.add_argument("-v", action="count", default=0)
+    p.add_argument("--version", action="version", version="%(prog)s " + __version__)
+    return p.parse_args(argv)
+
+
+def main(argv=None):
+    args = get_options(argv)
+    set_logging(args.v)
+    klength = args.kmer_length
+    if args.downstream_start_codon and args.upstream + args.downstream < klength:
+        logger.warning("Query sequence is shorter than k-mer length"
+                       "Decrease k-mer size or increase query sequence length")
+        sys.exit(1)
+    if args.maf > 0.5:
+        logger.warning("--maf should be below 0.5")
+        sys.exit(1)
+    if klength < 1 or klength > 32:
+        logger.error("this build supports k-mer lengths 1..32 (64-bit 2-bit encoding)")
+        sys.exit(1)
+
+    logger.info("Looking at input GFF files")
+    filelist, fastalist = what_are_my_inputfiles(args.gff, args.fasta)
+    logger.info(f"Found {len(filelist)} input genomes")
+    logger.info("Preparing output files")
+    (stroi, genes, kmer_stroi, hash_pat, kmer_hash, genepres) = set_input_output(
+        args.targets, args.genes, args.presence_absence, args.output,
+        not args.multiple_files, args.compress)
+    logger.info("Preparing inputs")
+    data = prep_data_n_fasta(filelist, fastalist, args.gff, args.fasta, args.output)
+    if not args.multiple_files:
+        write_headers(hash_pat, kmer_hash, genepres)
+
+    logger.info("Extracting k-mers")
+    iter_i = iter_gene_clusters(genepres, data, args.upstream, args.downstream,
+                                args.downstream_start_codon, not args.no_filter, genes,
+                                args.stop_on_missing)
+    iter_o = partial(cluster_cutter, klength=klength, stroi=stroi,
+                     multiple_files=args.multiple_files, canon=not args.non_canonical,
+                     consider_missing_cluster=args.consider_missing, output=args.output,
+                     compress=args.compress)
+    patterns = PatternStore()
+    func_w = partial(pattern_hasher, kmer_stroi=kmer_stroi, hash_pat=hash_pat,
+                     kmer_hash=kmer_hash, genepres=genepres, patfilt=not args.no_filter,
+                     maf=args.maf, consider_missing_cluster=args.consider_missing,
+                     output=args.output, compress=args.compress, device=args.device)
+    # one streaming call: the generator packs clusters while the GPU batches them
+    patterns = func_w((iter_o(x) for x in iter_i), patterns=patterns)
+    patterns.close()
+
+    for handle in (kmer_stroi, hash_pat, kmer_hash):
+        if handle is not None:
+            handle.close()
+    logger.info("Removing temporary fasta files and faidx indices")
+    clean_up_fasta(filelist, fastalist, args.output, args.fasta)
+
+
+if __name__ == "__main__":
+    main()

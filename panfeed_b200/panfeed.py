@@ -1,0 +1,297 @@
+"""The reference's hot-path callables, re-hosted on the CUDA library.
+
+Same names, argument meaning and output files as
+`/root/reference/panfeed/panfeed.py`:
+
+    cluster_cutter(cluster_gen, klength, stroi, multiple_files, canon,
+                   consider_missing_cluster, output, compress)     panfeed.py:23
+    pattern_hasher(cluster_dict_iter, kmer_stroi, hash_pat, kmer_hash, genepres,
+                   patfilt, maf, output, patterns, consider_missing_cluster,
+                   compress)                                        panfeed.py:132
+    write_headers(hash_pat, kmer_hash, genepres)                    panfeed.py:116
+
+What changes is where the work happens.  `cluster_cutter` only packs the
+cluster (host); the k-mer extraction, sorting, presence-bitset reduction, MAF /
+same-as-cluster filters and the global pattern dedup all run on the GPU inside
+`pattern_hasher`, many clusters per launch.  The second element of the tuple
+`cluster_cutter` returns is therefore a `PackedCluster`, not a dict, and
+`patterns` is a `PatternStore` (the device-resident pattern table plus the id
+strings handed out so far) instead of a Python set.  There is no CPU path.
+"""
+import binascii
+import hashlib
+import logging
+import os
+
+import numpy as np
+
+from . import capi, packer
+from .input import create_hash_files, create_kmer_stroi
+
+logger = logging.getLogger("panfeed.panfeed")
+
+# k-mer records per GPU batch (whole clusters are never split)
+BATCH_RECORDS = 192 * 1024 * 1024
+
+_COMP = bytes.maketrans(b"ACTGNYRWSKMDVHBX", b"TGACNRYWSMKHBDVX")
+
+
+def pattern_id(vec):
+    """base64(md5(raw little-endian bytes of the vector))[:24] (panfeed.py:175-176,
+    206-207): int64 bytes for cluster rows, float64 bytes for k-mer rows."""
+    return binascii.b2a_base64(hashlib.md5(np.ascontiguousarray(vec).view(np.uint8)).digest()
+                               ).decode()[:24]
+
+
+def cluster_cutter(cluster_gen, klength, stroi, multiple_files, canon,
+                   consider_missing_cluster, output, compress=False):
+    """Pack one cluster for the GPU.  Returns the reference's 4-tuple shape
+    (idx, <payload>, clusterpresab, memchunk); the positional rows the reference
+    formats here (panfeed.py:90-107) come back from the device in
+    `pattern_hasher`, so memchunk is always None."""
+    cluster, idx, clusterpresab = cluster_gen
+    logger.debug(f"Packing sequences of {idx}")
+    pc = packer.PackedCluster(cluster, idx, clusterpresab, stroi)
+    pc.k, pc.canonical, pc.consider_missing = klength, bool(canon), bool(consider_missing_cluster)
+    return idx, pc, clusterpresab, None
+
+
+def write_headers(hash_pat, kmer_hash, genepres):
+    hash_pat.write("hashed_pattern" + "".join(f"\t{s}" for s in sorted(genepres.columns)) + "\n")
+    hash_pat.flush()
+    kmer_hash.write("cluster\tk-mer\thashed_pattern\n")
+    kmer_hash.flush()
+
+
+class PatternStore:
+    """What `patterns` is in this build: the GPU context (pattern tables and
+    pools live in HBM) and the ids of every pattern written so far."""
+
+    def __init__(self):
+        self.ctx = None
+        self.key = None
+        self.kmer_ids = []        # pool index -> id string (float64 namespace)
+        self.cluster_ids = []     # pool index -> id string (int64 namespace)
+        self.cluster_bits = []    # pool index -> presence words (for the NaN plane)
+        self.seen = set()         # the reference's `patterns` set of id strings
+
+    def __len__(self):
+        return len(self.seen)
+
+    def context(self, k, S, canonical, consider_missing, cluster_equal_filter, maf,
+                device=0, sort_bits=0):
+        key = (k, S, canonical, consider_missing, cluster_equal_filter, maf, device)
+        if self.ctx is None:
+            self.ctx = capi.Context(k, S, canonical, consider_missing, cluster_equal_filter,
+                                    emit_positions=True, maf=maf, sort_bits=sort_bits,
+                                    device=device)
+            self.key = key
+        elif key != self.key:
+            raise ValueError("pattern_hasher was called with options that differ from the ones "
+                             "its PatternStore was created with")
+        return self.ctx
+
+    def reset(self):
+        """`patterns = set()` of --multiple-files (panfeed.py:165)."""
+        if self.ctx is not None:
+            self.ctx.reset_patterns()
+        self.kmer_ids, self.cluster_ids, self.cluster_bits = [], [], []
+        self.seen = set()
+
+    def close(self):
+        if self.ctx is not None:
+            self.ctx.close()
+            self.ctx = None
+
+
+def _expand_bits(words, S):
+    """uint32 [n, W] -> uint8 [n, S] of 0/1."""
+    b = np.unpackbits(np.ascontiguousarray(words).view(np.uint8), axis=1, bitorder="little")
+    return b[:, :S]
+
+
+def _pattern_lines(ids, cells, nan_mask):
+    """hashes_to_patterns rows: id + one '0'/'1' (or empty for NaN) per sample."""
+    n, S = cells.shape
+    if n == 0:
+        return ""
+    if nan_mask is None:
+        # fixed layout: id(24) \t c0 \t c1 ... \t c(S-1) \n
+        fixed = np.empty((n, 24 + 2 * S + 1), np.uint8)
+        fixed[:, :24] = np.frombuffer("".join(ids).encode(), np.uint8).reshape(n, 24)
+        fixed[:, 24:24 + 2 * S:2] = ord("\t")
+        fixed[:, 25:25 + 2 * S:2] = cells + ord("0")
+        fixed[:, -1] = ord("\n")
+        return fixed.tobytes().decode()
+    lines = []
+    for pid, c, m in zip(ids, cells, nan_mask):
+        lines.append(pid + "\t" + "\t".join("" if isnan else str(v)
+                                            for v, isnan in zip(c.tolist(), m.tolist())) + "\n")
+    return "".join(lines)
+
+
+def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
+    """One GPU batch -> (kmers.tsv text, hashes_to_patterns text, per-cluster
+    kmers_to_hashes texts)."""
+    hb, meta, ids = packer.pack_batch(pcs, list(range(len(pcs))))
+    ctx.submit(hb)
+    r = ctx.collect()
+
+    # ---- new patterns -> ids + hashes_to_patterns rows ------------------------
+    pat_text = []
+    new_cp = r["new_cluster_patterns"]
+    if len(new_cp):
+        cells = _expand_bits(new_cp, S)
+        ints = cells.astype(np.int64)
+        new_ids, fresh = [], []
+        for row in ints:
+            pid = pattern_id(row)
+            new_ids.append(pid)
+            fresh.append(pid not in store.seen)
+            store.seen.add(pid)
+        store.cluster_ids += new_ids
+        store.cluster_bits += [w for w in new_cp]
+        sel = np.array(fresh, bool)
+        pat_text.append(_pattern_lines([p for p, f in zip(new_ids, fresh) if f], cells[sel], None))
+    new_kp = r["new_kmer_patterns"]
+    if len(new_kp):
+        W = (S + 31) // 32
+        cells = _expand_bits(new_kp[:, :W], S)
+        vecs = cells.astype(np.float64)
+        nan_mask = None
+        if consider_missing:
+            present = _expand_bits(np.stack([store.cluster_bits[c] for c in new_kp[:, W]]), S)
+            nan_mask = present == 0
+            vecs[nan_mask] = np.nan
+        new_ids, fresh = [], []
+        for row in vecs:
+            pid = pattern_id(row)
+            new_ids.append(pid)
+            fresh.append(pid not in store.seen)
+            store.seen.add(pid)
+        store.kmer_ids += new_ids
+        sel = np.array(fresh, bool)
+        pat_text.append(_pattern_lines([p for p, f in zip(new_ids, fresh) if f], cells[sel],
+                                       None if nan_mask is None else nan_mask[sel]))
+
+    # ---- kmers_to_hashes rows, cluster by cluster ------------------------------
+    kmer_ids = np.array(store.kmer_ids, dtype="S24") if store.kmer_ids else np.zeros(0, "S24")
+    row_cluster = np.concatenate([r["row_cluster"], r["wide_row_cluster"]])
+    row_kmer = np.concatenate([packer.kmers_to_str(r["row_kmer"], k),
+                               packer.wide_kmers_to_str(r["wide_row_kmer"], k)])
+    row_pid = kmer_ids[np.concatenate([r["row_pattern"], r["wide_row_pattern"]]).astype(np.int64)] \
+        if len(row_cluster) else np.zeros(0, "S24")
+    order = np.lexsort((row_kmer, row_cluster))
+    row_cluster, row_kmer, row_pid = row_cluster[order], row_kmer[order], row_pid[order]
+    bounds = np.searchsorted(row_cluster, np.arange(len(pcs) + 1))
+    hash_texts = []
+    for c, idx in enumerate(idxs):
+        head = f"{idx}\t\t{store.cluster_ids[r['cluster_pattern'][c]]}\n"
+        lo, hi = bounds[c], bounds[c + 1]
+        n = hi - lo
+        if n == 0:
+            hash_texts.append(head)
+            continue
+        tag = (str(idx) + "\t").encode()
+        width = len(tag) + k + 1 + 24 + 1
+        buf = np.empty((n, width), np.uint8)
+        buf[:, :len(tag)] = np.frombuffer(tag, np.uint8)
+        buf[:, len(tag):len(tag) + k] = row_kmer[lo:hi].view(np.uint8).reshape(n, k)
+        buf[:, len(tag) + k] = ord("\t")
+        buf[:, len(tag) + k + 1:width - 1] = row_pid[lo:hi].view(np.uint8).reshape(n, 24)
+        buf[:, -1] = ord("\n")
+        hash_texts.append(head + buf.tobytes().decode())
+
+    # ---- kmers.tsv rows from the positional records -----------------------------
+    pos_text = ""
+    if len(r["pos_seq"]):
+        kmer_s = packer.kmers_to_str(r["pos_kmer"], k)
+        amb = (r["pos_flags"] & 2) != 0
+        if amb.any():
+            wide_s = packer.wide_kmers_to_str(r["pos_wide_kmer"], k)
+            kmer_s = kmer_s.copy()
+            kmer_s[amb] = wide_s[r["pos_kmer"][amb].astype(np.int64)]
+        seq = r["pos_seq"].astype(np.int64)
+        strand = hb.seqs["strand"][seq]
+        lead = np.array([f"{idxs[hb.seqs['cluster'][i]]}\t{meta[i][0]}\t{meta[i][1]}\t{meta[i][2]}\t"
+                         f"{hb.seqs['strand'][i]}\t" for i in range(len(hb.seqs))], dtype=object)
+        c0 = r["pos_contig_start"].astype(np.int64)
+        g0 = r["pos_gene_start"].astype(np.int64)
+        coords = (np.char.add(np.char.add(np.char.add(c0.astype(str), "\t"),
+                                          np.char.add((c0 + k).astype(str), "\t")),
+                              np.char.add(np.char.add(g0.astype(str), "\t"),
+                                          np.char.add((g0 + k).astype(str), "\t"))))
+        kmer_u = kmer_s.astype(str)
+        if canonical:
+            used = np.where((r["pos_flags"] & 1) != 0, "-1", "1")
+            rows = [a + b + u + "\t" + km + "\n"
+                    for a, b, u, km in zip(lead[seq], coords, used, kmer_u)]
+        else:
+            rows = []
+            for a, b, st, km in zip(lead[seq], coords, strand, kmer_s):
+                rc = km.translate(_COMP)[::-1].decode()
+                rows.append(f"{a}{b}{st}\t{km.decode()}\n{a}{b}{-st}\t{rc}\n")
+        pos_text = "".join(rows)
+    return pos_text, "".join(pat_text), hash_texts
+
+
+def pattern_hasher(cluster_dict_iter, kmer_stroi, hash_pat, kmer_hash, genepres, patfilt, maf,
+                   output, patterns=None, consider_missing_cluster=False, compress=False,
+                   device=0, sort_bits=0):
+    """Consumes `cluster_cutter` results, runs K1..K4 on the GPU in batches of
+    whole clusters and writes the three files exactly as the reference does
+    (panfeed.py:152-233).  Returns the updated `patterns` (a PatternStore)."""
+    multiple_files = hash_pat is None or kmer_hash is None
+    if patterns is None or isinstance(patterns, set):
+        patterns = PatternStore()
+    S = len(genepres.columns)
+
+    pending, pending_records = [], 0
+
+    def flush():
+        nonlocal pending, pending_records, hash_pat, kmer_hash
+        if not pending:
+            return
+        pcs = [p[1] for p in pending]
+        idxs = [p[0] for p in pending]
+        first = pcs[0]
+        ctx = patterns.context(first.k, S, first.canonical, bool(consider_missing_cluster),
+                               patfilt == False, maf, device, sort_bits)  # noqa: E712
+        pos_text, pat_text, hash_texts = _run_batch(patterns, ctx, pcs, idxs, S, first.k,
+                                                    first.canonical, bool(consider_missing_cluster))
+        if multiple_files:
+            path = os.path.join(output, idxs[0])
+            if not os.path.exists(path):
+                os.mkdir(path)
+            ks = create_kmer_stroi(path, compress)
+            ks.write(pos_text)
+            ks.close()
+            hp, kh = create_hash_files(path, compress)
+            write_headers(hp, kh, genepres)
+            hp.write(pat_text)
+            kh.write("".join(hash_texts))
+            hp.close()
+            kh.close()
+        else:
+            if kmer_stroi is not None:
+                kmer_stroi.write(pos_text)
+            hash_pat.write(pat_text)
+            kmer_hash.write("".join(hash_texts))
+        pending, pending_records = [], 0
+
+    for idx, pc, clusterpresab, memchunk in cluster_dict_iter:
+        if multiple_files:
+            flush()
+            patterns.reset()
+        n = pc.n_records(pc.k, pc.canonical)
+        if pending and pending_records + n > BATCH_RECORDS:
+            flush()
+        pending.append((idx, pc))
+        pending_records += n
+        if multiple_files:
+            flush()
+    flush()
+    if not multiple_files:
+        hash_pat.flush()
+        kmer_hash.flush()
+    return patterns
