@@ -924,9 +924,11 @@ extern "C" int pf_patterns_export(pf_ctx* ctx, int cluster_namespace, uint64_t f
 extern "C" int pf_stats_get(pf_ctx* ctx, pf_stats* out) {
   if (!ctx || !out) return PF_ERR_INVALID;
   if (ctx->executed) {
-    CU(cudaStreamSynchronize(ctx->stream));
+    TRY(finalize_pending(ctx));
     fill_timings(ctx);
   }
+  ctx->stats.kmer_patterns = ctx->kp.n;
+  ctx->stats.cluster_patterns = ctx->cp.n;
   *out = ctx->stats;
   out->total_launches = ctx->launches;
   return PF_OK;
