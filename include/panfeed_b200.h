@@ -57,6 +57,11 @@ typedef struct pf_params {
   uint32_t sort_bits;            /* 0 = auto; else number of leading bits of the
                                     mixed key the radix sort orders (multiple of 8,
                                     8..64); the rest is resolved exactly in K3     */
+  uint32_t mode;                 /* 0 = partition: few radix passes, then per-tile grouping
+                                    in a shared-memory hash table (default);
+                                    1 = full sort: LSD passes over sort_bits, then a
+                                    segmented run reduction                          */
+  uint32_t reserved;
   double   maf;                  /* --maf, compared in float64 exactly as
                                     panfeed.py:190-200 (see pf_maf_window)          */
 } pf_params;

@@ -30,15 +30,16 @@ constexpr uint64_t kFlag64Agg = 1ull << 62;
 constexpr uint64_t kFlag64Incl = 2ull << 62;
 constexpr uint64_t kFlag64Mask = 3ull << 62;
 
-template <typename KeyT>
+template <typename KeyT, int ITEMS>
 __global__ void __launch_bounds__(kSortThreads)
 k3_mark_runs(const KeyT* __restrict__ keys, const TileDev* __restrict__ tiles, uint32_t n_tiles,
              int sort_bits, uint32_t* __restrict__ run_start, uint32_t* __restrict__ run_seg,
+             uint32_t* __restrict__ tile_first_run /* [n_tiles + 1] or null */,
              uint64_t* __restrict__ lookback /* [n_tiles], zeroed */,
              uint32_t* __restrict__ ticket, uint32_t* __restrict__ n_runs_out,
              uint32_t* __restrict__ err) {
   constexpr int kWarps = kSortThreads / 32;
-  constexpr int kGroups = kSortItems * kWarps;         // 32-record groups per tile
+  constexpr int kGroups = ITEMS * kWarps;              // 32-record groups per tile
   __shared__ uint32_t group_count[kGroups];
   __shared__ uint32_t group_off[kGroups];
   __shared__ uint32_t s_tile;
@@ -50,9 +51,9 @@ k3_mark_runs(const KeyT* __restrict__ keys, const TileDev* __restrict__ tiles, u
   if (tile >= n_tiles) return;
   const TileDev td = tiles[tile];
 
-  uint32_t heads[kSortItems];
+  uint32_t heads[ITEMS];
 #pragma unroll
-  for (int j = 0; j < kSortItems; ++j) {
+  for (int j = 0; j < ITEMS; ++j) {
     const uint32_t idx = j * kSortThreads + tid;       // group g = j*kWarps + warp, tile order
     bool head = false;
     if (idx < td.count) {
@@ -99,13 +100,17 @@ k3_mark_runs(const KeyT* __restrict__ keys, const TileDev* __restrict__ tiles, u
       }
       st_relaxed(&lookback[tile], kFlag64Incl | (prev + total));
       s_base = prev;
-      if (tile == n_tiles - 1) *n_runs_out = (uint32_t)(prev + total);
+      if (tile_first_run) tile_first_run[tile] = (uint32_t)prev;
+      if (tile == n_tiles - 1) {
+        *n_runs_out = (uint32_t)(prev + total);
+        if (tile_first_run) tile_first_run[n_tiles] = (uint32_t)(prev + total);
+      }
     }
   }
   __syncthreads();
   const uint32_t base = (uint32_t)s_base;
 #pragma unroll
-  for (int j = 0; j < kSortItems; ++j) {
+  for (int j = 0; j < ITEMS; ++j) {
     if (heads[j] >> lane & 1u) {
       const uint32_t slot = base + group_off[j * kWarps + warp] + __popc(heads[j] & lanemask_lt());
       run_start[slot] = td.start + j * kSortThreads + tid;

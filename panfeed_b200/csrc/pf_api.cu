@@ -15,6 +15,7 @@
 #include "k1_extract.cuh"
 #include "k2_onesweep.cuh"
 #include "k3_reduce.cuh"
+#include "k3_local.cuh"
 #include "k4_dedup.cuh"
 #include "synth.cuh"
 
@@ -49,8 +50,9 @@ struct PatternSpace {
 struct WidthState {       // per key width (narrow u64 / wide Key128)
   DevBuf keys[2], vals[2];
   DevBuf tiles, seg_start, seg_hist, lookback;
-  PinBuf h_tiles, h_seg_start;
-  uint32_t n_tiles = 0;
+  DevBuf ltiles, tile_first_run;     // partition mode: 2048-record tiles of the local reduce
+  PinBuf h_tiles, h_seg_start, h_ltiles;
+  uint32_t n_tiles = 0, n_ltiles = 0, max_seg = 0;
   uint32_t n_records = 0;
   uint32_t n_runs = 0;
   uint32_t n_rows = 0;
@@ -86,6 +88,11 @@ struct pf_ctx {
   DevBuf d_rep, d_slot_of, d_winner;
   DevBuf d_cl_pattern, d_cl_rep, d_cl_slot, d_cl_winner;
   DevBuf d_pos_kmer, d_pos_seq, d_pos_cstart, d_pos_gstart, d_pos_flags, d_pos_wide;
+  bool partition = true;   // mode 0: few radix passes + shared-memory hash grouping (k3_local)
+  int extra_bits = 0;      // sort bits added after a table overflow (sticky)
+  double row_ratio = 1.0 / 48;   // surviving rows per record, learned from earlier batches
+  uint64_t row_cap = 0;
+  uint64_t unique_last = 0;
   PatternSpace kp, cp;     // k-mer patterns, cluster patterns
   uint64_t kp_base = 0, cp_base = 0;   // pool sizes before the resident batch
   // pinned results
@@ -151,7 +158,7 @@ constexpr int kGridPersist = 148 * 4;
 // counters layout in d_counters
 enum { C_TICKET_N = 0, C_TICKET_W = 1, C_RUNS_N = 2, C_RUNS_W = 3, C_ERR = 4, C_ROWS_N = 5,
        C_ROWS_W = 6, C_NEW_KP = 7, C_NEW_CP = 8, C_TICKET_MARK_N = 9, C_TICKET_MARK_W = 10,
-       C_COUNT = 16 };
+       C_LOCAL = 11 /* 4 words: rows, unique, table overflow, row overflow */, C_COUNT = 16 };
 
 bool keep_count(double maf, uint32_t c, uint32_t n) {
   double af = (double)c / (double)n;      // numpy: vec.sum() / vec.shape[0]
@@ -199,6 +206,7 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
   if (p->n_samples < 1) return fail(nullptr, PF_ERR_INVALID, "n_samples must be >= 1");
   if (p->sort_bits != 0 && (p->sort_bits % 8 != 0 || p->sort_bits < 8 || p->sort_bits > 64))
     return fail(nullptr, PF_ERR_INVALID, "sort_bits must be 0 or a multiple of 8 in 8..64");
+  if (p->mode > 1) return fail(nullptr, PF_ERR_INVALID, "mode must be 0 (partition) or 1 (full sort)");
   if (!(p->maf <= 0.5) || p->maf < 0)
     return fail(nullptr, PF_ERR_INVALID, "--maf should be in [0, 0.5]");
   int n_dev = 0;
@@ -221,6 +229,8 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
   ctx->Wk = ctx->W + (p->consider_missing ? 1u : 0u);
   ctx->kp.key_words = ctx->Wk;
   ctx->cp.key_words = ctx->W;
+  // partition mode needs (slot:13 | sample:19) pair words and a bitset row that fits the pool
+  ctx->partition = (p->mode == 0) && p->n_samples < kLocalMaxSamples && ctx->W <= (uint32_t)kLocalPoolWords;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete ctx;
     return fail(nullptr, PF_ERR_CUDA, "cudaStreamCreate failed");
@@ -233,6 +243,7 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
                        (int)sizeof(SortSmem<uint64_t>));
   cudaFuncSetAttribute(k2_onesweep_pass<Key128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)sizeof(SortSmem<Key128>));
+  cudaFuncSetAttribute(k3_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LocalSmem));
   const int k3_smem = (int)(8 * ctx->W * sizeof(uint32_t));
   if (k3_smem > 48 * 1024) {
     cudaFuncSetAttribute(k3_runs<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3_smem);
@@ -264,9 +275,9 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
     fd(*b);
   for (WidthState* w : {&ctx->nar, &ctx->wid}) {
     for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
-                      &w->seg_hist, &w->lookback})
+                      &w->seg_hist, &w->lookback, &w->ltiles, &w->tile_first_run})
       fd(*b);
-    fp(w->h_tiles); fp(w->h_seg_start);
+    fp(w->h_tiles); fp(w->h_seg_start); fp(w->h_ltiles);
   }
   for (PatternSpace* s : {&ctx->kp, &ctx->cp})
     for (DevBuf* b : {&s->pool, &s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique})
@@ -286,8 +297,15 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
 
 namespace {
 
-int auto_sort_bits(const pf_ctx* ctx, uint32_t max_seg_records) {
-  if (ctx->prm.sort_bits) return (int)ctx->prm.sort_bits;
+int auto_sort_bits(const pf_ctx* ctx, uint32_t max_seg_records, bool narrow) {
+  if (ctx->prm.sort_bits) return std::min(64, (int)ctx->prm.sort_bits + (narrow ? ctx->extra_bits : 0));
+  if (narrow && ctx->partition) {
+    // enough 8-bit passes that a prefix bucket of the largest cluster averages <= 4096 records
+    int passes = 1;
+    uint64_t buckets = 256;
+    while ((uint64_t)max_seg_records / buckets > 4096 && passes < 8) { ++passes; buckets <<= 8; }
+    return std::min(64, 8 * passes + ctx->extra_bits);
+  }
   int lg = 0;
   while ((1ull << lg) < (uint64_t)std::max<uint32_t>(max_seg_records, 1)) ++lg;
   int bits = ((lg + 12 + 7) / 8) * 8;      // expected shared prefixes per segment <= n / 8192
@@ -295,7 +313,7 @@ int auto_sort_bits(const pf_ctx* ctx, uint32_t max_seg_records) {
 }
 
 // Build the tile list of one key width from the per-cluster record ranges.
-int plan_tiles(pf_ctx* ctx, WidthState& w, const std::vector<std::pair<uint32_t, uint32_t>>& ranges) {
+int plan_tiles(pf_ctx* ctx, WidthState& w, const std::vector<std::pair<uint32_t, uint32_t>>& ranges, bool narrow) {
   uint64_t n_tiles = 0;
   uint32_t max_seg = 0;
   for (auto& r : ranges) {
@@ -305,8 +323,29 @@ int plan_tiles(pf_ctx* ctx, WidthState& w, const std::vector<std::pair<uint32_t,
   if (max_seg >= (1u << 30))
     return fail(ctx, PF_ERR_INVALID, "a cluster has %u k-mer records; the limit per cluster is 2^30", max_seg);
   w.n_tiles = (uint32_t)n_tiles;
-  w.sort_bits = auto_sort_bits(ctx, max_seg);
+  w.max_seg = max_seg;
+  w.sort_bits = auto_sort_bits(ctx, max_seg, narrow);
   w.passes = w.sort_bits / 8;
+  if (narrow && ctx->partition) {      // second tile list: 2048-record tiles for mark + local reduce
+    uint64_t nl = 0;
+    for (auto& r : ranges) nl += cdiv(r.second - r.first, kLocalTile);
+    w.n_ltiles = (uint32_t)nl;
+    TRY(pin_ensure(ctx, w.h_ltiles, std::max<size_t>(1, nl) * sizeof(TileDev)));
+    TileDev* lt = w.h_ltiles.as<TileDev>();
+    uint32_t li = 0;
+    for (uint32_t c = 0; c < ranges.size(); ++c) {
+      const uint32_t first = li;
+      for (uint32_t s = ranges[c].first; s < ranges[c].second; s += kLocalTile) {
+        lt[li].start = s;
+        lt[li].count = std::min<uint32_t>(kLocalTile, ranges[c].second - s);
+        lt[li].seg = c;
+        lt[li].first_tile = first;
+        ++li;
+      }
+    }
+  } else {
+    w.n_ltiles = 0;
+  }
   TRY(pin_ensure(ctx, w.h_tiles, std::max<size_t>(1, n_tiles) * sizeof(TileDev)));
   TRY(pin_ensure(ctx, w.h_seg_start, std::max<size_t>(1, ranges.size()) * sizeof(uint32_t)));
   TileDev* t = w.h_tiles.as<TileDev>();
@@ -436,8 +475,8 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
   ctx->n_pos = (uint32_t)pos; ctx->n_pos_wide = (uint32_t)pwide;
   ctx->nar.n_records = (uint32_t)rec; ctx->wid.n_records = (uint32_t)wrec;
   if (pos >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "more than 2^32 positional records; split the batch");
-  TRY(plan_tiles(ctx, ctx->nar, nr));
-  TRY(plan_tiles(ctx, ctx->wid, wr));
+  TRY(plan_tiles(ctx, ctx->nar, nr, true));
+  TRY(plan_tiles(ctx, ctx->wid, wr, false));
 
   // ---- device buffers + H2D ------------------------------------------------
   const size_t slack_words = 80;
@@ -452,6 +491,11 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
     TRY(dev_ensure(ctx, w->seg_start, std::max<size_t>(1, b->n_clusters) * 4));
     TRY(dev_ensure(ctx, w->seg_hist, std::max<size_t>(1, (size_t)b->n_clusters * w->passes * kRadix) * 4));
     TRY(dev_ensure(ctx, w->lookback, std::max<size_t>(1, (size_t)w->n_tiles * kRadix) * 4));
+    if (w->n_ltiles) {
+      TRY(dev_ensure(ctx, w->ltiles, (size_t)w->n_ltiles * sizeof(TileDev)));
+      TRY(dev_ensure(ctx, w->tile_first_run, ((size_t)w->n_ltiles + 1) * 4));
+      TRY(dev_ensure(ctx, w->lookback, std::max<size_t>((size_t)w->n_tiles * kRadix * 4, (size_t)w->n_ltiles * 8)));
+    }
   }
   cudaStream_t st = ctx->stream;
   CU(cudaEventRecord(ctx->ev_h2d[0], st));
@@ -464,6 +508,7 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
   }
   for (WidthState* w : {&ctx->nar, &ctx->wid}) {
     if (w->n_tiles) CU(cudaMemcpyAsync(w->tiles.p, w->h_tiles.p, w->n_tiles * sizeof(TileDev), cudaMemcpyHostToDevice, st));
+    if (w->n_ltiles) CU(cudaMemcpyAsync(w->ltiles.p, w->h_ltiles.p, w->n_ltiles * sizeof(TileDev), cudaMemcpyHostToDevice, st));
     if (b->n_clusters) CU(cudaMemcpyAsync(w->seg_start.p, w->h_seg_start.p, b->n_clusters * 4, cudaMemcpyHostToDevice, st));
   }
   if (n_wide) {
@@ -530,7 +575,7 @@ int passes_width(pf_ctx* ctx, WidthState& w, int ticket_idx) {
 }
 
 template <typename KeyT>
-int mark_width(pf_ctx* ctx, WidthState& w, int ticket_idx, int runs_idx) {
+int mark_width(pf_ctx* ctx, WidthState& w, int ticket_idx, int runs_idx, bool local_tiles) {
   if (w.n_records == 0) return PF_OK;
   cudaStream_t st = ctx->stream;
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
@@ -538,11 +583,18 @@ int mark_width(pf_ctx* ctx, WidthState& w, int ticket_idx, int runs_idx) {
   // the idle ping-pong buffers hold the run lists: keys[other] = run_start | run_seg, vals[other] = nrows
   uint32_t* run_start = w.keys[other].as<uint32_t>();
   uint32_t* run_seg = run_start + ((size_t)w.n_records + 1);
-  CU(cudaMemsetAsync(w.lookback.p, 0, (size_t)w.n_tiles * 8, st));
+  const uint32_t nt = local_tiles ? w.n_ltiles : w.n_tiles;
+  CU(cudaMemsetAsync(w.lookback.p, 0, (size_t)nt * 8, st));
   CU(cudaMemsetAsync(counters + ticket_idx, 0, 4, st));
-  k3_mark_runs<KeyT><<<w.n_tiles, kSortThreads, 0, st>>>(
-      w.keys[w.final_buf].as<KeyT>(), w.tiles.as<TileDev>(), w.n_tiles, w.sort_bits, run_start, run_seg,
-      w.lookback.as<uint64_t>(), counters + ticket_idx, counters + runs_idx, counters + C_ERR);
+  if (local_tiles)
+    k3_mark_runs<KeyT, kLocalItems><<<nt, kSortThreads, 0, st>>>(
+        w.keys[w.final_buf].as<KeyT>(), w.ltiles.as<TileDev>(), nt, w.sort_bits, run_start, run_seg,
+        w.tile_first_run.as<uint32_t>(), w.lookback.as<uint64_t>(), counters + ticket_idx,
+        counters + runs_idx, counters + C_ERR);
+  else
+    k3_mark_runs<KeyT, kSortItems><<<nt, kSortThreads, 0, st>>>(
+        w.keys[w.final_buf].as<KeyT>(), w.tiles.as<TileDev>(), nt, w.sort_bits, run_start, run_seg,
+        nullptr, w.lookback.as<uint64_t>(), counters + ticket_idx, counters + runs_idx, counters + C_ERR);
   ctx->launches++;
   CU(cudaGetLastError());
   return PF_OK;
@@ -658,43 +710,22 @@ int check_device_error(pf_ctx* ctx) {
 
 }  // namespace
 
-extern "C" int pf_execute(pf_ctx* ctx) {
-  if (!ctx) return PF_ERR_INVALID;
-  if (!ctx->have_batch) return fail(ctx, PF_ERR_STATE, "pf_execute: no batch uploaded");
-  CU(cudaSetDevice(ctx->device));
+namespace {
+
+int ensure_rows(pf_ctx* ctx, uint64_t rows, uint64_t narrow_rows, bool keep) {
+  TRY(dev_ensure(ctx, ctx->d_row_cluster, std::max<size_t>(1, rows) * 4, keep));
+  TRY(dev_ensure(ctx, ctx->d_row_count, std::max<size_t>(1, rows) * 4, keep));
+  TRY(dev_ensure(ctx, ctx->d_row_pattern, std::max<size_t>(1, rows) * 4, keep));
+  TRY(dev_ensure(ctx, ctx->d_row_kmer, std::max<size_t>(1, narrow_rows) * 8, keep));
+  TRY(dev_ensure(ctx, ctx->d_cand, std::max<size_t>(1, rows) * ctx->Wk * 4, keep));
+  return PF_OK;
+}
+
+int launch_k1(pf_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   const pf_params& P = ctx->prm;
-  const uint32_t launches0 = ctx->launches;
   WidthState& N = ctx->nar;
   WidthState& Wd = ctx->wid;
-  uint32_t* counters = ctx->d_counters.as<uint32_t>();
-  uint32_t* hcnt = ctx->h_counters.as<uint32_t>();
-  TRY(finalize_pending(ctx));
-  ctx->executed = false;
-  ctx->kp_base = ctx->kp.n;
-  ctx->cp_base = ctx->cp.n;
-
-  // record buffers (ping-pong); the idle one later holds the run lists, so give
-  // it room for n+1 run starts + n run segments (8n+4 bytes <= 8n+8)
-  for (int i = 0; i < 2; ++i) {
-    TRY(dev_ensure(ctx, N.keys[i], ((size_t)N.n_records + 2) * 8));
-    TRY(dev_ensure(ctx, N.vals[i], ((size_t)N.n_records + 2) * 4));
-    TRY(dev_ensure(ctx, Wd.keys[i], ((size_t)Wd.n_records + 2) * 16));
-    TRY(dev_ensure(ctx, Wd.vals[i], ((size_t)Wd.n_records + 2) * 4));
-  }
-  if (ctx->n_pos) {
-    TRY(dev_ensure(ctx, ctx->d_pos_kmer, (size_t)ctx->n_pos * 8));
-    TRY(dev_ensure(ctx, ctx->d_pos_seq, (size_t)ctx->n_pos * 4));
-    TRY(dev_ensure(ctx, ctx->d_pos_cstart, (size_t)ctx->n_pos * 4));
-    TRY(dev_ensure(ctx, ctx->d_pos_gstart, (size_t)ctx->n_pos * 4));
-    TRY(dev_ensure(ctx, ctx->d_pos_flags, (size_t)ctx->n_pos));
-  }
-  if (ctx->n_pos_wide) TRY(dev_ensure(ctx, ctx->d_pos_wide, (size_t)ctx->n_pos_wide * 16));
-
-  CU(cudaMemsetAsync(counters, 0, C_COUNT * 4, st));
-  CU(cudaEventRecord(ctx->ev[EV_START], st));
-
-  // ---- K1 ---------------------------------------------------------------
   PosOut po{ctx->d_pos_kmer.as<uint64_t>(), ctx->d_pos_seq.as<uint32_t>(), ctx->d_pos_cstart.as<int32_t>(),
             ctx->d_pos_gstart.as<int32_t>(), ctx->d_pos_flags.as<uint8_t>()};
   if (ctx->n_seqs && N.n_records) {
@@ -724,63 +755,179 @@ extern "C" int pf_execute(pf_ctx* ctx) {
     ctx->launches++;
   }
   CU(cudaGetLastError());
-  CU(cudaEventRecord(ctx->ev[EV_EXTRACT], st));
+  return PF_OK;
+}
 
-  // ---- K2 ---------------------------------------------------------------
-  TRY(hist_width<uint64_t>(ctx, N));
-  TRY(hist_width<Key128>(ctx, Wd));
-  CU(cudaEventRecord(ctx->ev[EV_HIST], st));
-  TRY(passes_width<uint64_t>(ctx, N, C_TICKET_N));
-  TRY(passes_width<Key128>(ctx, Wd, C_TICKET_W));
-  CU(cudaEventRecord(ctx->ev[EV_SORT], st));
+int launch_local(pf_ctx* ctx, RowOut ro) {
+  WidthState& N = ctx->nar;
+  if (N.n_records == 0) return PF_OK;
+  cudaStream_t st = ctx->stream;
+  uint32_t* counters = ctx->d_counters.as<uint32_t>();
+  const int other = N.final_buf ^ 1;
+  CU(cudaMemsetAsync(counters + C_LOCAL, 0, 4 * 4, st));
+  k3_local<<<N.n_ltiles, kLocalThreads, sizeof(LocalSmem), st>>>(
+      N.keys[N.final_buf].as<uint64_t>(), N.vals[N.final_buf].as<uint32_t>(), N.ltiles.as<TileDev>(),
+      N.n_ltiles, N.tile_first_run.as<uint32_t>(), N.keys[other].as<uint32_t>(), N.n_records,
+      ctx->d_clusters.as<ClusterDev>(), ro, (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu),
+      counters + C_LOCAL);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
 
-  // ---- K3: runs ------------------------------------------------------------
-  TRY(mark_width<uint64_t>(ctx, N, C_TICKET_MARK_N, C_RUNS_N));
-  TRY(mark_width<Key128>(ctx, Wd, C_TICKET_MARK_W, C_RUNS_W));
-  CU(cudaEventRecord(ctx->ev[EV_MARK], st));
-  CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  TRY(check_device_error(ctx));
-  N.n_runs = N.n_records ? hcnt[C_RUNS_N] : 0;
-  Wd.n_runs = Wd.n_records ? hcnt[C_RUNS_W] : 0;
+}  // namespace
 
-  RowOut ro{};
-  ro.key_words = ctx->Wk; ro.pattern_words = ctx->W;
-  TRY((runs_width<uint64_t, false>(ctx, N, ro)));
-  TRY((runs_width<Key128, false>(ctx, Wd, ro)));
-  CU(cudaEventRecord(ctx->ev[EV_COUNTED], st));
-  if (N.n_runs) TRY(scan_inplace(ctx, N.vals[N.final_buf ^ 1].as<uint32_t>(), N.n_runs, counters + C_ROWS_N));
-  if (Wd.n_runs) TRY(scan_inplace(ctx, Wd.vals[Wd.final_buf ^ 1].as<uint32_t>(), Wd.n_runs, counters + C_ROWS_W));
+extern "C" int pf_execute(pf_ctx* ctx) {
+  if (!ctx) return PF_ERR_INVALID;
+  if (!ctx->have_batch) return fail(ctx, PF_ERR_STATE, "pf_execute: no batch uploaded");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint32_t launches0 = ctx->launches;
+  WidthState& N = ctx->nar;
+  WidthState& Wd = ctx->wid;
+  uint32_t* counters = ctx->d_counters.as<uint32_t>();
+  uint32_t* hcnt = ctx->h_counters.as<uint32_t>();
+  TRY(finalize_pending(ctx));
+  ctx->executed = false;
+  ctx->kp_base = ctx->kp.n;
+  ctx->cp_base = ctx->cp.n;
+  const bool part = ctx->partition;
 
-  // ---- cluster rows (int64 namespace), needed for the NaN-plane word ---------
+  // record buffers (ping-pong); the idle one later holds the run lists, so give
+  // it room for n+1 run starts + n run segments (8n+4 bytes <= 8n+16)
+  for (int i = 0; i < 2; ++i) {
+    TRY(dev_ensure(ctx, N.keys[i], ((size_t)N.n_records + 2) * 8));
+    TRY(dev_ensure(ctx, N.vals[i], ((size_t)N.n_records + 2) * 4));
+    TRY(dev_ensure(ctx, Wd.keys[i], ((size_t)Wd.n_records + 2) * 16));
+    TRY(dev_ensure(ctx, Wd.vals[i], ((size_t)Wd.n_records + 2) * 4));
+  }
+  if (ctx->n_pos) {
+    TRY(dev_ensure(ctx, ctx->d_pos_kmer, (size_t)ctx->n_pos * 8));
+    TRY(dev_ensure(ctx, ctx->d_pos_seq, (size_t)ctx->n_pos * 4));
+    TRY(dev_ensure(ctx, ctx->d_pos_cstart, (size_t)ctx->n_pos * 4));
+    TRY(dev_ensure(ctx, ctx->d_pos_gstart, (size_t)ctx->n_pos * 4));
+    TRY(dev_ensure(ctx, ctx->d_pos_flags, (size_t)ctx->n_pos));
+  }
+  if (ctx->n_pos_wide) TRY(dev_ensure(ctx, ctx->d_pos_wide, (size_t)ctx->n_pos_wide * 16));
   TRY(dev_ensure(ctx, ctx->d_cl_pattern, std::max<size_t>(1, ctx->n_clusters) * 4));
+  if (part) {
+    ctx->row_cap = std::max<uint64_t>(ctx->row_cap, std::max<uint64_t>(
+        65536, (uint64_t)(ctx->row_ratio * 1.3 * (double)N.n_records) + 4096));
+    TRY(ensure_rows(ctx, ctx->row_cap, ctx->row_cap, false));
+  }
+
+  CU(cudaMemsetAsync(counters, 0, C_COUNT * 4, st));
+  CU(cudaEventRecord(ctx->ev[EV_START], st));
+
+  // ---- cluster rows (int64 namespace) first: their ids are the NaN-plane word
+  //      of k-mer pattern keys in cluster-absent mode ------------------------------
   TRY(dedup(ctx, ctx->cp, ctx->d_presence.as<uint32_t>(), ctx->n_clusters, ctx->d_cl_rep, ctx->d_cl_slot,
             ctx->d_cl_winner, ctx->d_cl_pattern.as<uint32_t>(), C_NEW_CP));
 
-  CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
-  CU(cudaStreamSynchronize(st));
-  N.n_rows = N.n_runs ? hcnt[C_ROWS_N] : 0;
-  Wd.n_rows = Wd.n_runs ? hcnt[C_ROWS_W] : 0;
-  ctx->cp.n = ctx->cp_base + hcnt[C_NEW_CP];
+  RowOut ro{};
+  ro.key_words = ctx->Wk; ro.pattern_words = ctx->W;
+  ro.cluster_pattern = ctx->d_cl_pattern.as<uint32_t>();
+
+  for (int attempt = 0;; ++attempt) {
+    // ---- K1 -------------------------------------------------------------------
+    TRY(launch_k1(ctx));
+    CU(cudaEventRecord(ctx->ev[EV_EXTRACT], st));
+    // ---- K2 -------------------------------------------------------------------
+    TRY(hist_width<uint64_t>(ctx, N));
+    TRY(hist_width<Key128>(ctx, Wd));
+    CU(cudaEventRecord(ctx->ev[EV_HIST], st));
+    TRY(passes_width<uint64_t>(ctx, N, C_TICKET_N));
+    TRY(passes_width<Key128>(ctx, Wd, C_TICKET_W));
+    CU(cudaEventRecord(ctx->ev[EV_SORT], st));
+    // ---- K3: runs -----------------------------------------------------------------
+    TRY(mark_width<uint64_t>(ctx, N, C_TICKET_MARK_N, C_RUNS_N, part));
+    TRY(mark_width<Key128>(ctx, Wd, C_TICKET_MARK_W, C_RUNS_W, false));
+    CU(cudaEventRecord(ctx->ev[EV_MARK], st));
+    if (part) {
+      ro.cluster = ctx->d_row_cluster.as<uint32_t>();
+      ro.count = ctx->d_row_count.as<uint32_t>();
+      ro.cand = ctx->d_cand.as<uint32_t>();
+      ro.kmer = ctx->d_row_kmer.as<uint64_t>();
+      ro.row_base = 0;
+      TRY(launch_local(ctx, ro));
+    }
+    CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    TRY(check_device_error(ctx));
+    ctx->cp.n = ctx->cp_base + hcnt[C_NEW_CP];
+    N.n_runs = N.n_records ? hcnt[C_RUNS_N] : 0;
+    Wd.n_runs = Wd.n_records ? hcnt[C_RUNS_W] : 0;
+    if (!part || N.n_records == 0) break;
+    if (hcnt[C_LOCAL + LC_TABLE_OVERFLOW]) {
+      // more distinct k-mers under one sorted prefix than a CTA's table holds:
+      // sort 8 more bits and start over (at 64 bits this cannot happen)
+      if (N.sort_bits >= 64) return fail(ctx, PF_ERR_INTERNAL, "local table overflow at 64 sorted bits");
+      ctx->extra_bits += 8;
+      N.sort_bits = auto_sort_bits(ctx, N.max_seg, true);
+      N.passes = N.sort_bits / 8;
+      TRY(dev_ensure(ctx, N.seg_hist, std::max<size_t>(1, (size_t)ctx->n_clusters * N.passes * kRadix) * 4));
+      continue;
+    }
+    if (hcnt[C_LOCAL + LC_ROW_OVERFLOW]) {
+      ctx->row_cap = (uint64_t)hcnt[C_LOCAL + LC_ROWS] + 1024;
+      TRY(ensure_rows(ctx, ctx->row_cap, ctx->row_cap, false));
+      ro.cluster = ctx->d_row_cluster.as<uint32_t>();
+      ro.count = ctx->d_row_count.as<uint32_t>();
+      ro.cand = ctx->d_cand.as<uint32_t>();
+      ro.kmer = ctx->d_row_kmer.as<uint64_t>();
+      TRY(launch_local(ctx, ro));
+      CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      if (hcnt[C_LOCAL + LC_ROW_OVERFLOW] || hcnt[C_LOCAL + LC_TABLE_OVERFLOW])
+        return fail(ctx, PF_ERR_INTERNAL, "local reduce overflowed twice");
+    }
+    if (attempt > 8) return fail(ctx, PF_ERR_INTERNAL, "partition mode did not converge");
+    break;
+  }
+
+  if (part) {
+    N.n_rows = N.n_records ? hcnt[C_LOCAL + LC_ROWS] : 0;
+    ctx->unique_last = N.n_records ? hcnt[C_LOCAL + LC_UNIQUE] : 0;
+    if (N.n_records) ctx->row_ratio = std::max(1e-4, (double)N.n_rows / (double)N.n_records);
+  } else {
+    TRY((runs_width<uint64_t, false>(ctx, N, ro)));
+  }
+  TRY((runs_width<Key128, false>(ctx, Wd, ro)));
+  CU(cudaEventRecord(ctx->ev[EV_COUNTED], st));
+  const bool need_scan = (!part && N.n_runs) || Wd.n_runs;
+  if (need_scan) {
+    if (!part && N.n_runs)
+      TRY(scan_inplace(ctx, N.vals[N.final_buf ^ 1].as<uint32_t>(), N.n_runs, counters + C_ROWS_N));
+    if (Wd.n_runs) TRY(scan_inplace(ctx, Wd.vals[Wd.final_buf ^ 1].as<uint32_t>(), Wd.n_runs, counters + C_ROWS_W));
+    CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (!part) N.n_rows = N.n_runs ? hcnt[C_ROWS_N] : 0;
+    Wd.n_rows = Wd.n_runs ? hcnt[C_ROWS_W] : 0;
+  } else {
+    if (!part) N.n_rows = 0;
+    Wd.n_rows = 0;
+  }
+  if (!part) ctx->unique_last = N.n_runs;
+  ctx->unique_last += Wd.n_runs;
   const uint64_t rows = (uint64_t)N.n_rows + Wd.n_rows;
   if (rows >= (1ull << 31)) return fail(ctx, PF_ERR_INVALID, "batch yields 2^31 rows or more; split it");
 
-  TRY(dev_ensure(ctx, ctx->d_row_cluster, std::max<size_t>(1, rows) * 4));
-  TRY(dev_ensure(ctx, ctx->d_row_count, std::max<size_t>(1, rows) * 4));
-  TRY(dev_ensure(ctx, ctx->d_row_pattern, std::max<size_t>(1, rows) * 4));
-  TRY(dev_ensure(ctx, ctx->d_row_kmer, std::max<size_t>(1, N.n_rows) * 8));
+  if (!part || Wd.n_rows) TRY(ensure_rows(ctx, std::max<uint64_t>(rows, part ? ctx->row_cap : 0),
+                                          std::max<uint64_t>(N.n_rows, part ? ctx->row_cap : 0), part));
   TRY(dev_ensure(ctx, ctx->d_wrow_kmer, std::max<size_t>(1, Wd.n_rows) * 16));
-  TRY(dev_ensure(ctx, ctx->d_cand, std::max<size_t>(1, rows) * ctx->Wk * 4));
   ro.cluster = ctx->d_row_cluster.as<uint32_t>();
   ro.count = ctx->d_row_count.as<uint32_t>();
   ro.cand = ctx->d_cand.as<uint32_t>();
-  ro.cluster_pattern = ctx->d_cl_pattern.as<uint32_t>();
-  ro.kmer = ctx->d_row_kmer.as<uint64_t>();
-  ro.row_base = 0;
-  if (N.n_rows) TRY((runs_width<uint64_t, true>(ctx, N, ro)));
-  ro.kmer = ctx->d_wrow_kmer.as<uint64_t>();
-  ro.row_base = N.n_rows;
-  if (Wd.n_rows) TRY((runs_width<Key128, true>(ctx, Wd, ro)));
+  if (!part && N.n_rows) {
+    ro.kmer = ctx->d_row_kmer.as<uint64_t>();
+    ro.row_base = 0;
+    TRY((runs_width<uint64_t, true>(ctx, N, ro)));
+  }
+  if (Wd.n_rows) {
+    ro.kmer = ctx->d_wrow_kmer.as<uint64_t>();
+    ro.row_base = N.n_rows;
+    TRY((runs_width<Key128, true>(ctx, Wd, ro)));
+  }
   CU(cudaEventRecord(ctx->ev[EV_REDUCE], st));
 
   // ---- K4 ---------------------------------------------------------------
@@ -875,7 +1022,7 @@ extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
   s.batches++;
   s.bases += ctx->n_bases;
   s.instances += (uint64_t)N.n_records + Wd.n_records;
-  s.unique_kmers += (uint64_t)N.n_runs + Wd.n_runs;
+  s.unique_kmers += ctx->unique_last;
   s.rows += rows;
   s.kmer_patterns = ctx->kp.n;
   s.cluster_patterns = ctx->cp.n;

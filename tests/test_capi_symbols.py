@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header():
     assert capi.SEQ_DTYPE.itemsize == 48
-    assert ctypes.sizeof(capi.Params) == 40
+    assert ctypes.sizeof(capi.Params) == 48
     assert ctypes.sizeof(capi.Batch) == 72
 
 

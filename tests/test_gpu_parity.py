@@ -25,8 +25,9 @@ def _render_gpu(out, S, k, consider_missing, canonical):
     return got
 
 
+@pytest.mark.parametrize("engine", [0, 1], ids=["partition", "fullsort"])
 @pytest.mark.parametrize("mode", sorted(helpers.modes()))
-def test_fixture_modes_match_reference_goldens(mode):
+def test_fixture_modes_match_reference_goldens(mode, engine):
     kw = helpers.cli_kwargs(helpers.modes()[mode])
     cwd = os.getcwd()
     os.chdir(helpers.GOLDEN)
@@ -36,7 +37,7 @@ def test_fixture_modes_match_reference_goldens(mode):
         os.chdir(cwd)
     out = gpu_util.run_gpu(items, stroi, S, kw["k"], not kw["non_canonical"],
                            kw["consider_missing"], kw["no_filter"], kw["maf"],
-                           batch_clusters=3)
+                           batch_clusters=3, mode=engine)
     got = _render_gpu(out, S, kw["k"], kw["consider_missing"],
                       not kw["non_canonical"])
     for name in helpers.FILES:
@@ -114,13 +115,31 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("engine", [0, 1], ids=["partition", "fullsort"])
 @pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
-def test_random_clusters_match_oracle(case):
+def test_random_clusters_match_oracle(case, engine):
     S, k, nc, L, canon, cm, nf, maf, amb, sb, bc = case
     rng = np.random.default_rng(1000 + S * 7 + k)
     items, stroi = _random_items(rng, S, k, nc, L, amb)
     _compare_with_oracle(items, stroi, S, k, canon, cm, nf, maf,
-                         batch_clusters=bc, sort_bits=sb)
+                         batch_clusters=bc, sort_bits=sb, mode=engine)
+
+
+def test_partition_mode_escalates_on_table_overflow():
+    """One sorted byte, > 3072 distinct k-mers under a prefix: the CTA table
+    overflows, the library must add sorted bits and still be exact."""
+    rng = np.random.default_rng(77)
+    comp = str.maketrans("ACGT", "TGCA")
+    S = 4
+    names = [f"g{i}" for i in range(S)]
+    cluster = {}
+    for s in names:   # unrelated random sequences: every k-mer is unique
+        q = "".join(rng.choice(list("ACGT"), 300000))
+        cluster[s] = [ref_port.CutSeq(q, q.translate(comp), s + "_f", "c", 1, 300000, 1, 0)]
+    items = [(cluster, "big", np.ones(S, dtype=int))]
+    out, want = _compare_with_oracle(items, set(), S, 31, True, False, False, 0.0,
+                                     batch_clusters=1, sort_bits=8, mode=0)
+    assert out["stats"]["sort_passes"] >= 2
 
 
 def test_empty_and_ragged_batches():
