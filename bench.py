@@ -396,6 +396,7 @@ def main():
                                    "alg_GBps": alg["k3_reduce"] / (stage_ms["ms_mark"] + stage_ms["ms_count"]
                                                                    + stage_ms["ms_reduce"]) / 1e6},
             "k4_dedup": {"ms": stage_ms["ms_dedup"]},
+            "raw_ms": {k_: round(v_, 3) for k_, v_ in stage_ms.items()},
         }
         line = {
             "metric": "input_bases_per_s", "value": value, "unit": "bases/s", "n_gpus": world,

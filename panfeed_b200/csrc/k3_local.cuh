@@ -4,26 +4,31 @@
 // 8p bits of the mixed key only.  Instead of spending more global passes, one
 // CTA takes all prefix-runs that START inside its 2048-record tile (a handful
 // of buckets, typically a few thousand records and ~100 distinct k-mers),
-// streams their records once through a shared-memory open-addressing table
-// keyed on the FULL 64-bit key, and does the whole reduction on chip:
+// streams their records through a shared-memory open-addressing table keyed on
+// the FULL 64-bit key, and does the whole reduction on chip.  Two variants:
 //
-//   phase 1  find-or-insert the key (64-bit CAS in shared memory), count its
-//            distinct samples.  Records of one key arrive in ascending sample
-//            order (stable passes, sample-ordered packing), so across 2048-record
-//            chunks only "equal to the last sample seen" can repeat; inside a
-//            chunk a small (slot, sample) pair set removes duplicates exactly.
-//   phase 2  keys whose count lies in the cluster's integer MAF window get a row
-//            (one atomicAdd per CTA on the global row counter).
-//   phase 3  the records are streamed again (L2-resident) and the surviving
-//            keys' sample bits are OR-ed into shared-memory bitsets, as many rows
-//            per round as fit, then written out coalesced with the row's
-//            (cluster, un-mixed k-mer, count).
+// k3_local_direct (S <= 1024): every distinct key gets a dense id and a W-word
+//   bitset in shared memory; each record is one table probe + one atomicOr.  The
+//   sample count is the popcount, so record order is irrelevant.  One pass over
+//   the records.
+//
+// k3_local (any S): bitsets for every key would not fit, so
+//   phase 1  find-or-insert the key, count its distinct samples.  Records of one
+//            key arrive in ascending sample order (stable passes, sample-ordered
+//            packing): across 2048-record chunks only "equal to the last sample
+//            seen" can repeat; inside a chunk a (slot, sample) pair set removes
+//            duplicates exactly.
+//   phase 2  keys whose count lies in the cluster's integer MAF window get a row.
+//   phase 3  the records are streamed again (L2-resident) and the surviving keys'
+//            sample bits are OR-ed into shared-memory bitsets, as many rows per
+//            round as fit, then written out coalesced.
 //
 // Replaces `cluster_dict[kmer][sortstrain[strain]] = 1` and the filters of
-// /root/reference/panfeed/panfeed.py:77-88,190-204.  Exact for any input: if a
-// CTA meets more distinct keys than its table holds it raises a flag and the
-// host re-runs the batch with 8 more sorted bits (at 64 bits a tile can hold
-// at most 2048 + 1 distinct keys, which always fits).
+// /root/reference/panfeed/panfeed.py:77-88,190-204.  Exact for any input: a CTA
+// that meets more distinct keys than it can hold raises a flag; the host falls
+// back from the direct to the general variant, and from there re-runs the batch
+// with 8 more sorted bits (at 64 bits a tile holds at most 2048 + 1 distinct
+// keys, which always fits the general table).
 #pragma once
 #include "pf_common.cuh"
 #include "k3_reduce.cuh"
@@ -33,24 +38,194 @@ namespace pf {
 constexpr int kLocalThreads = 256;
 constexpr int kLocalItems = 8;
 constexpr int kLocalTile = kLocalThreads * kLocalItems;   // 2048 records
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr uint32_t kNoRow = 0xffffffffu;
+enum { LC_ROWS = 0, LC_UNIQUE = 1, LC_TABLE_OVERFLOW = 2, LC_ROW_OVERFLOW = 3 };
+
+// prefix-runs of one radix pass are the digit buckets: their starts are the
+// scanned histogram itself.  first_run[t] = first bucket starting at or after tile t.
+__global__ void k3_tiles_from_hist(const TileDev* __restrict__ ltiles, uint32_t n_ltiles,
+                                   const uint32_t* __restrict__ digit_start /* [seg][256] */,
+                                   uint32_t n_seg, uint32_t* __restrict__ tile_first_run) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_ltiles) return;
+  if (t == n_ltiles) { tile_first_run[t] = n_seg * kRadix; return; }
+  const TileDev td = ltiles[t];
+  const uint32_t* s = digit_start + (size_t)td.seg * kRadix;
+  uint32_t lo = 0, hi = kRadix;                 // first d with s[d] >= td.start
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (s[mid] < td.start) lo = mid + 1; else hi = mid;
+  }
+  tile_first_run[t] = td.seg * kRadix + lo;
+}
+
+// ---------------------------------------------------------------------------
+// direct variant
+// ---------------------------------------------------------------------------
+constexpr int kDirectSlots = 2048;
+constexpr int kDirectPoolWords = 12288;          // 48 KB of bitsets
+constexpr uint32_t kDirectMaxUnique = 768;
+constexpr uint32_t kDirectMaxWords = 32;         // S <= 1024
+
+struct DirectSmem {
+  uint64_t keys[kDirectSlots + 1];     // slot kDirectSlots: home of the key equal to kEmptyKey
+  alignas(16) uint32_t pool[kDirectPoolWords];   // dense id x W words
+  uint16_t id[kDirectSlots + 2];       // slot -> dense id
+  uint16_t row_slot[kDirectMaxUnique]; // surviving row -> slot
+  uint32_t n_unique, n_pass, row_base, special_used, overflow, ok;
+};
+
+__global__ void __launch_bounds__(kLocalThreads, 3)
+k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                const TileDev* __restrict__ ltiles, uint32_t n_ltiles,
+                const uint32_t* __restrict__ tile_first_run /* [n_ltiles + 1] */,
+                const uint32_t* __restrict__ run_start, uint32_t n_records,
+                const ClusterDev* __restrict__ clusters, RowOut out, uint32_t row_capacity,
+                uint32_t* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char local_raw[];
+  DirectSmem& sm = *reinterpret_cast<DirectSmem*>(local_raw);
+  const uint32_t tid = threadIdx.x;
+  const uint32_t t = blockIdx.x;
+  const uint32_t r0 = tile_first_run[t], r1 = tile_first_run[t + 1];
+  if (r0 == r1) return;
+  const uint32_t n_runs = tile_first_run[n_ltiles];
+  const uint32_t a = run_start[r0];
+  const uint32_t b = (r1 < n_runs) ? run_start[r1] : n_records;
+  if (a >= b) return;
+  const uint32_t seg = ltiles[t].seg;
+  const ClusterDev cl = clusters[seg];
+  const uint32_t W = out.pattern_words;
+  const uint32_t max_unique = min(kDirectMaxUnique, (uint32_t)kDirectPoolWords / W);
+
+  for (uint32_t i = tid; i <= kDirectSlots; i += kLocalThreads) sm.keys[i] = kEmptyKey;
+  {
+    uint4* p4 = reinterpret_cast<uint4*>(sm.pool);
+    for (uint32_t i = tid; i < kDirectPoolWords / 4; i += kLocalThreads) p4[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (tid == 0) { sm.n_unique = 0; sm.n_pass = 0; sm.special_used = 0; sm.overflow = 0; sm.ok = 1; }
+  __syncthreads();
+
+  for (uint32_t c0 = a; c0 < b; c0 += kLocalTile) {
+    uint64_t key[kLocalItems];
+    uint32_t val[kLocalItems];
+    uint16_t slot[kLocalItems];
+    uint32_t inserted = 0;
+#pragma unroll
+    for (int j = 0; j < kLocalItems; ++j) {
+      const uint32_t i = c0 + j * kLocalThreads + tid;
+      val[j] = kInvalidSample;
+      key[j] = 0;
+      if (i < b) { key[j] = keys[i]; val[j] = vals[i]; }
+    }
+    // (i) find or insert
+#pragma unroll
+    for (int j = 0; j < kLocalItems; ++j) {
+      slot[j] = 0xffff;
+      if (val[j] == kInvalidSample) continue;
+      const uint64_t k = key[j];
+      if (k == kEmptyKey) {
+        if (atomicExch(&sm.special_used, 1u) == 0u) inserted |= 1u << j;
+        slot[j] = kDirectSlots;
+        continue;
+      }
+      uint32_t h = (uint32_t)k & (kDirectSlots - 1);
+      for (int probes = 0; probes < kDirectSlots; ++probes) {
+        const uint64_t cur = sm.keys[h];
+        if (cur == k) { slot[j] = (uint16_t)h; break; }
+        if (cur == kEmptyKey) {
+          const uint64_t old = atomicCAS(reinterpret_cast<unsigned long long*>(&sm.keys[h]),
+                                         (unsigned long long)kEmptyKey, (unsigned long long)k);
+          if (old == kEmptyKey) { slot[j] = (uint16_t)h; inserted |= 1u << j; break; }
+          if (old == k) { slot[j] = (uint16_t)h; break; }
+        }
+        h = (h + 1) & (kDirectSlots - 1);
+      }
+      if (slot[j] == 0xffff) sm.overflow = 1;
+    }
+    __syncthreads();
+    // (ii) dense ids for the keys this thread inserted
+#pragma unroll
+    for (int j = 0; j < kLocalItems; ++j) {
+      if (inserted >> j & 1u) {
+        const uint32_t id = atomicAdd(&sm.n_unique, 1u);
+        if (id < max_unique) sm.id[slot[j]] = (uint16_t)id; else sm.overflow = 1;
+      }
+    }
+    __syncthreads();
+    if (sm.overflow) {
+      if (tid == 0) atomicExch(&counters[LC_TABLE_OVERFLOW], 1u);
+      return;
+    }
+    // (iii) one OR per record
+#pragma unroll
+    for (int j = 0; j < kLocalItems; ++j) {
+      if (slot[j] == 0xffff) continue;
+      const uint32_t v = val[j];
+      atomicOr(&sm.pool[(uint32_t)sm.id[slot[j]] * W + (v >> 5)], 1u << (v & 31u));
+    }
+  }
+  __syncthreads();
+
+  // ---- counts, filter, rows ---------------------------------------------------------
+  for (uint32_t i = tid; i <= kDirectSlots; i += kLocalThreads) {
+    const bool used = (i < kDirectSlots) ? (sm.keys[i] != kEmptyKey) : (sm.special_used != 0u);
+    if (!used) continue;
+    const uint32_t* bits = sm.pool + (uint32_t)sm.id[i] * W;
+    uint32_t c = 0;
+    for (uint32_t w = 0; w < W; ++w) c += __popc(bits[w]);
+    if (c >= cl.lo && c <= cl.hi) sm.row_slot[atomicAdd(&sm.n_pass, 1u)] = (uint16_t)i;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    atomicAdd(&counters[LC_UNIQUE], sm.n_unique);
+    if (sm.n_pass) {
+      const uint32_t base = atomicAdd(&counters[LC_ROWS], sm.n_pass);
+      sm.row_base = base;
+      if ((uint64_t)base + sm.n_pass > row_capacity) {
+        sm.ok = 0;
+        atomicExch(&counters[LC_ROW_OVERFLOW], 1u);
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t n_pass = sm.n_pass;
+  if (n_pass == 0 || !sm.ok) return;
+  const uint32_t base = sm.row_base;
+  for (uint32_t r = tid; r < n_pass; r += kLocalThreads) {
+    const uint32_t s = sm.row_slot[r];
+    const uint32_t* bits = sm.pool + (uint32_t)sm.id[s] * W;
+    uint32_t c = 0;
+    for (uint32_t w = 0; w < W; ++w) c += __popc(bits[w]);
+    const size_t g = (size_t)base + r;
+    out.cluster[g] = cl.id;
+    out.kmer[g] = unmix64(s < kDirectSlots ? sm.keys[s] : kEmptyKey);
+    out.count[g] = c;
+    if (out.key_words > W) out.cand[g * out.key_words + W] = out.cluster_pattern[seg];
+  }
+  for (uint32_t i = tid; i < n_pass * W; i += kLocalThreads) {
+    const uint32_t r = i / W, w = i - r * W;
+    out.cand[((size_t)base + r) * out.key_words + w] = sm.pool[(uint32_t)sm.id[sm.row_slot[r]] * W + w];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// general variant
+// ---------------------------------------------------------------------------
 constexpr int kLocalSlots = 4096;                         // >= 2 * kLocalTile
 constexpr uint32_t kLocalMaxUnique = 3072;
-constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint32_t kEmptyPair = 0xffffffffu;
-constexpr uint32_t kNoRow = 0xffffffffu;
 constexpr uint32_t kLocalMaxSamples = 1u << 19;           // (slot:13 | sample:19) pair word
-constexpr int kLocalPoolWords = kLocalSlots + 1 + kLocalSlots;
+constexpr int kLocalPoolWords = 2 * kLocalSlots;          // 32 KB of bitsets per round
 
 struct LocalSmem {
   uint64_t keys[kLocalSlots + 1];      // slot kLocalSlots: home of the key equal to kEmptyKey
   uint32_t cnt[kLocalSlots + 1];       // distinct samples
-  uint32_t last_prev[kLocalSlots + 1]; // 1 + largest sample before this chunk; phase 2+: row index
-  uint32_t last_next[kLocalSlots + 1]; // 1 + largest sample in this chunk   } phase 3: bitset pool
-  uint32_t pairs[kLocalSlots];         // chunk-local (slot, sample) set       }
+  uint32_t last[kLocalSlots + 1];      // 1 + largest sample of earlier chunks; phase 2+: row index
+  uint32_t pairs[kLocalSlots];         // chunk-local (slot, sample) set   } phase 3: bitset pool
+  uint32_t pool_tail[kLocalSlots];     //                                  }
   uint32_t n_unique, n_pass, row_base, special_used, overflow, ok;
 };
-
-enum { LC_ROWS = 0, LC_UNIQUE = 1, LC_TABLE_OVERFLOW = 2, LC_ROW_OVERFLOW = 3 };
 
 __device__ __forceinline__ uint32_t local_find_or_insert(LocalSmem& sm, uint64_t key) {
   if (key == kEmptyKey) {
@@ -96,6 +271,7 @@ k3_local(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
   const uint32_t n_runs = tile_first_run[n_ltiles];
   const uint32_t a = run_start[r0];
   const uint32_t b = (r1 < n_runs) ? run_start[r1] : n_records;
+  if (a >= b) return;
   const uint32_t seg = ltiles[t].seg;
   const ClusterDev cl = clusters[seg];
   const uint32_t W = out.pattern_words;
@@ -103,25 +279,17 @@ k3_local(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
   for (uint32_t i = tid; i <= kLocalSlots; i += kLocalThreads) {
     sm.keys[i] = kEmptyKey;
     sm.cnt[i] = 0;
-    sm.last_prev[i] = 0;
-    sm.last_next[i] = 0;
+    sm.last[i] = 0;
   }
+  for (uint32_t i = tid; i < kLocalSlots; i += kLocalThreads) sm.pairs[i] = kEmptyPair;
   if (tid == 0) { sm.n_unique = 0; sm.n_pass = 0; sm.special_used = 0; sm.overflow = 0; sm.ok = 1; }
+  __syncthreads();
 
   // ---- phase 1: group by full key, count distinct samples ---------------------
   for (uint32_t c0 = a; c0 < b; c0 += kLocalTile) {
-    for (uint32_t i = tid; i < kLocalSlots; i += kLocalThreads) {
-      sm.pairs[i] = kEmptyPair;
-      if (c0 > a) {
-        const uint32_t n = sm.last_next[i];
-        if (n > sm.last_prev[i]) sm.last_prev[i] = n;
-      }
-    }
-    if (tid == 0 && c0 > a && sm.last_next[kLocalSlots] > sm.last_prev[kLocalSlots])
-      sm.last_prev[kLocalSlots] = sm.last_next[kLocalSlots];
-    __syncthreads();
     uint64_t key[kLocalItems];
     uint32_t val[kLocalItems];
+    uint16_t slot[kLocalItems], pair_at[kLocalItems];
 #pragma unroll
     for (int j = 0; j < kLocalItems; ++j) {
       const uint32_t i = c0 + j * kLocalThreads + tid;
@@ -131,29 +299,36 @@ k3_local(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
     }
 #pragma unroll
     for (int j = 0; j < kLocalItems; ++j) {
+      pair_at[j] = 0xffff;
       const uint32_t v = val[j];
       if (v == kInvalidSample) continue;
-      const uint32_t slot = local_find_or_insert(sm, key[j]);
-      if (slot == kNoRow) continue;
-      const uint32_t e = (slot << 19) | v;
+      const uint32_t s = local_find_or_insert(sm, key[j]);
+      if (s == kNoRow) continue;
+      slot[j] = (uint16_t)s;
+      const uint32_t e = (s << 19) | v;
       uint32_t h = (e * 0x9e3779b1u) >> 20;              // 12 bits
-      bool fresh = false;
       for (;;) {
         const uint32_t old = atomicCAS(&sm.pairs[h], kEmptyPair, e);
-        if (old == kEmptyPair) { fresh = true; break; }
+        if (old == kEmptyPair) { pair_at[j] = (uint16_t)h; break; }
         if (old == e) break;
         h = (h + 1) & (kLocalSlots - 1);
       }
-      if (fresh) {
-        if (sm.last_prev[slot] != v + 1u) atomicAdd(&sm.cnt[slot], 1u);
-        atomicMax(&sm.last_next[slot], v + 1u);
-      }
+      if (pair_at[j] != 0xffff && sm.last[s] != v + 1u) atomicAdd(&sm.cnt[s], 1u);
     }
     __syncthreads();
     if (sm.overflow || sm.n_unique > kLocalMaxUnique) {
       if (tid == 0) atomicExch(&counters[LC_TABLE_OVERFLOW], 1u);
       return;
     }
+    // fold this chunk's samples into `last`, release the pair entries this thread set
+#pragma unroll
+    for (int j = 0; j < kLocalItems; ++j) {
+      if (pair_at[j] != 0xffff) {
+        atomicMax(&sm.last[slot[j]], val[j] + 1u);
+        sm.pairs[pair_at[j]] = kEmptyPair;
+      }
+    }
+    __syncthreads();
   }
 
   // ---- phase 2: which keys survive, row allocation -----------------------------
@@ -164,7 +339,7 @@ k3_local(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
       const uint32_t c = sm.cnt[i];
       if (c >= cl.lo && c <= cl.hi) row = atomicAdd(&sm.n_pass, 1u);
     }
-    sm.last_prev[i] = row;
+    sm.last[i] = row;
   }
   __syncthreads();
   if (tid == 0) {
@@ -183,7 +358,7 @@ k3_local(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
   if (n_pass == 0 || !sm.ok) return;
   const uint32_t base = sm.row_base;
   for (uint32_t i = tid; i <= kLocalSlots; i += kLocalThreads) {
-    const uint32_t row = sm.last_prev[i];
+    const uint32_t row = sm.last[i];
     if (row != kNoRow) {
       const size_t g = (size_t)base + row;
       out.cluster[g] = cl.id;
@@ -194,7 +369,7 @@ k3_local(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
   }
 
   // ---- phase 3: bitsets of the surviving keys, `per_round` rows at a time ----------
-  uint32_t* pool = sm.last_next;                 // last_next + pairs are contiguous
+  uint32_t* pool = sm.pairs;                     // pairs + pool_tail are contiguous
   const uint32_t per_round = max(1u, (uint32_t)kLocalPoolWords / W);
   for (uint32_t lo = 0; lo < n_pass; lo += per_round) {
     const uint32_t rows = min(per_round, n_pass - lo);
@@ -215,7 +390,7 @@ k3_local(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
       for (int j = 0; j < kLocalItems; ++j) {
         const uint32_t v = val[j];
         if (v == kInvalidSample) continue;
-        const uint32_t row = sm.last_prev[local_find(sm, key[j])];
+        const uint32_t row = sm.last[local_find(sm, key[j])];
         if (row - lo < rows)                      // also false for kNoRow
           atomicOr(&pool[(row - lo) * W + (v >> 5)], 1u << (v & 31u));
       }

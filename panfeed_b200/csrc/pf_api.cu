@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_map>
@@ -89,6 +90,8 @@ struct pf_ctx {
   DevBuf d_cl_pattern, d_cl_rep, d_cl_slot, d_cl_winner;
   DevBuf d_pos_kmer, d_pos_seq, d_pos_cstart, d_pos_gstart, d_pos_flags, d_pos_wide;
   bool partition = true;   // mode 0: few radix passes + shared-memory hash grouping (k3_local)
+  bool use_direct = true;  // S <= 1024: bitsets for every distinct key in shared memory
+  bool runs_from_hist = false;   // one pass: prefix-runs are the digit buckets of the histogram
   int extra_bits = 0;      // sort bits added after a table overflow (sticky)
   double row_ratio = 1.0 / 48;   // surviving rows per record, learned from earlier batches
   uint64_t row_cap = 0;
@@ -151,6 +154,20 @@ int pin_ensure(pf_ctx* ctx, PinBuf& b, size_t bytes) {
   return PF_OK;
 }
 #define TRY(x) do { int r_ = (x); if (r_ != PF_OK) return r_; } while (0)
+
+// PF_DEBUG_SYNC=1: synchronise after every stage so a device fault names its kernel.
+bool debug_sync(const char* name) {
+  static const char* v = getenv("PF_DEBUG_SYNC");
+  return v && (v[0] == '1' || strstr(name, v) != nullptr);
+}
+#define STAGE(name)                                                                      \
+  do {                                                                                   \
+    if (debug_sync(name)) {                                                                  \
+      cudaError_t e_ = cudaStreamSynchronize(ctx->stream);                               \
+      if (e_ != cudaSuccess)                                                             \
+        return fail(ctx, PF_ERR_CUDA, "stage %s: %s", name, cudaGetErrorString(e_));     \
+    }                                                                                    \
+  } while (0)
 
 inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 constexpr int kGridPersist = 148 * 4;
@@ -244,6 +261,8 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
   cudaFuncSetAttribute(k2_onesweep_pass<Key128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)sizeof(SortSmem<Key128>));
   cudaFuncSetAttribute(k3_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LocalSmem));
+  cudaFuncSetAttribute(k3_local_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DirectSmem));
+  ctx->use_direct = ctx->W <= kDirectMaxWords;
   const int k3_smem = (int)(8 * ctx->W * sizeof(uint32_t));
   if (k3_smem > 48 * 1024) {
     cudaFuncSetAttribute(k3_runs<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3_smem);
@@ -764,12 +783,31 @@ int launch_local(pf_ctx* ctx, RowOut ro) {
   cudaStream_t st = ctx->stream;
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
   const int other = N.final_buf ^ 1;
+  const uint32_t* run_start = ctx->runs_from_hist ? N.seg_hist.as<uint32_t>() : N.keys[other].as<uint32_t>();
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu);
   CU(cudaMemsetAsync(counters + C_LOCAL, 0, 4 * 4, st));
-  k3_local<<<N.n_ltiles, kLocalThreads, sizeof(LocalSmem), st>>>(
-      N.keys[N.final_buf].as<uint64_t>(), N.vals[N.final_buf].as<uint32_t>(), N.ltiles.as<TileDev>(),
-      N.n_ltiles, N.tile_first_run.as<uint32_t>(), N.keys[other].as<uint32_t>(), N.n_records,
-      ctx->d_clusters.as<ClusterDev>(), ro, (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu),
-      counters + C_LOCAL);
+  if (ctx->use_direct)
+    k3_local_direct<<<N.n_ltiles, kLocalThreads, sizeof(DirectSmem), st>>>(
+        N.keys[N.final_buf].as<uint64_t>(), N.vals[N.final_buf].as<uint32_t>(), N.ltiles.as<TileDev>(),
+        N.n_ltiles, N.tile_first_run.as<uint32_t>(), run_start, N.n_records,
+        ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL);
+  else
+    k3_local<<<N.n_ltiles, kLocalThreads, sizeof(LocalSmem), st>>>(
+        N.keys[N.final_buf].as<uint64_t>(), N.vals[N.final_buf].as<uint32_t>(), N.ltiles.as<TileDev>(),
+        N.n_ltiles, N.tile_first_run.as<uint32_t>(), run_start, N.n_records,
+        ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
+// partition mode, one pass: no key read is needed to find the prefix-runs
+int tiles_from_hist(pf_ctx* ctx) {
+  WidthState& N = ctx->nar;
+  if (N.n_records == 0) return PF_OK;
+  k3_tiles_from_hist<<<cdiv((uint64_t)N.n_ltiles + 1, 256), 256, 0, ctx->stream>>>(
+      N.ltiles.as<TileDev>(), N.n_ltiles, N.seg_hist.as<uint32_t>(), ctx->n_clusters,
+      N.tile_first_run.as<uint32_t>());
   ctx->launches++;
   CU(cudaGetLastError());
   return PF_OK;
@@ -823,6 +861,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   //      of k-mer pattern keys in cluster-absent mode ------------------------------
   TRY(dedup(ctx, ctx->cp, ctx->d_presence.as<uint32_t>(), ctx->n_clusters, ctx->d_cl_rep, ctx->d_cl_slot,
             ctx->d_cl_winner, ctx->d_cl_pattern.as<uint32_t>(), C_NEW_CP));
+  STAGE("k4 cluster rows");
 
   RowOut ro{};
   ro.key_words = ctx->Wk; ro.pattern_words = ctx->W;
@@ -831,17 +870,24 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   for (int attempt = 0;; ++attempt) {
     // ---- K1 -------------------------------------------------------------------
     TRY(launch_k1(ctx));
+    STAGE("k1_extract");
     CU(cudaEventRecord(ctx->ev[EV_EXTRACT], st));
     // ---- K2 -------------------------------------------------------------------
     TRY(hist_width<uint64_t>(ctx, N));
     TRY(hist_width<Key128>(ctx, Wd));
+    STAGE("k2_histogram");
     CU(cudaEventRecord(ctx->ev[EV_HIST], st));
     TRY(passes_width<uint64_t>(ctx, N, C_TICKET_N));
     TRY(passes_width<Key128>(ctx, Wd, C_TICKET_W));
+    STAGE("k2_onesweep_pass");
     CU(cudaEventRecord(ctx->ev[EV_SORT], st));
     // ---- K3: runs -----------------------------------------------------------------
-    TRY(mark_width<uint64_t>(ctx, N, C_TICKET_MARK_N, C_RUNS_N, part));
+    ctx->runs_from_hist = part && N.passes == 1;
+    if (ctx->runs_from_hist) TRY(tiles_from_hist(ctx));
+    else TRY(mark_width<uint64_t>(ctx, N, C_TICKET_MARK_N, C_RUNS_N, part));
+    STAGE("k3_mark_runs/k3_tiles_from_hist");
     TRY(mark_width<Key128>(ctx, Wd, C_TICKET_MARK_W, C_RUNS_W, false));
+    STAGE("k3_mark_runs<wide>");
     CU(cudaEventRecord(ctx->ev[EV_MARK], st));
     if (part) {
       ro.cluster = ctx->d_row_cluster.as<uint32_t>();
@@ -850,6 +896,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       ro.kmer = ctx->d_row_kmer.as<uint64_t>();
       ro.row_base = 0;
       TRY(launch_local(ctx, ro));
+      STAGE("k3_local");
     }
     CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
@@ -858,6 +905,14 @@ extern "C" int pf_execute(pf_ctx* ctx) {
     N.n_runs = N.n_records ? hcnt[C_RUNS_N] : 0;
     Wd.n_runs = Wd.n_records ? hcnt[C_RUNS_W] : 0;
     if (!part || N.n_records == 0) break;
+    if (hcnt[C_LOCAL + LC_TABLE_OVERFLOW] && ctx->use_direct) {
+      // more distinct k-mers in a tile than the direct variant has bitsets for:
+      // switch to the general variant for good and redo the reduction only
+      ctx->use_direct = false;
+      TRY(launch_local(ctx, ro));
+      CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+    }
     if (hcnt[C_LOCAL + LC_TABLE_OVERFLOW]) {
       // more distinct k-mers under one sorted prefix than a CTA's table holds:
       // sort 8 more bits and start over (at 64 bits this cannot happen)

@@ -125,6 +125,14 @@ def test_random_clusters_match_oracle(case, engine):
                          batch_clusters=bc, sort_bits=sb, mode=engine)
 
 
+def test_partition_general_variant_large_S():
+    """S > 1024 takes the general k3_local variant (pair set + rounds of bitsets)."""
+    rng = np.random.default_rng(5)
+    items, stroi = _random_items(rng, 1500, 31, 2, 260)
+    out, want = _compare_with_oracle(items, stroi, 1500, 31, True, True, False, 0.01,
+                                     batch_clusters=2, mode=0)
+
+
 def test_partition_mode_escalates_on_table_overflow():
     """One sorted byte, > 3072 distinct k-mers under a prefix: the CTA table
     overflows, the library must add sorted bits and still be exact."""
