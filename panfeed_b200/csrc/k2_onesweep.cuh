@@ -233,4 +233,123 @@ k2_onesweep_pass(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ 
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Unstable variant of the pass, for the direct local reduce (S <= 1024), which
+// ORs sample bits and therefore does not care about the order of records inside
+// a bucket.  The per-warp match/ballot ranking (a 16-deep dependent chain) is
+// replaced by one shared-memory atomicAdd per record on a per-tile histogram:
+// the 16 atomics of a thread are independent, so they pipeline.
+template <typename KeyT>
+struct ScatterSmem {
+  KeyT keys[kSortTile];
+  uint32_t vals[kSortTile];
+  uint32_t hist[kRadix];
+  uint32_t excl[kRadix];
+  uint32_t gbase[kRadix];
+  uint32_t warp_sums[kSortThreads / 32];
+  uint32_t tile;
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads, 3)
+k2_scatter_pass(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                const TileDev* __restrict__ tiles, uint32_t n_tiles,
+                const uint32_t* __restrict__ digit_start, int pass, int passes, int shift,
+                uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket,
+                uint32_t* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScatterSmem<KeyT>& sm = *reinterpret_cast<ScatterSmem<KeyT>*>(smem_raw);
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  constexpr int kWarps = kSortThreads / 32;
+  constexpr int kWarpItems = kSortItems * 32;
+
+  if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
+  sm.hist[tid] = 0;
+  __syncthreads();
+  const uint32_t tile = sm.tile;
+  if (tile >= n_tiles) return;
+  const TileDev td = tiles[tile];
+
+  KeyT key[kSortItems];
+  uint32_t val[kSortItems];
+  uint16_t rank[kSortItems];
+  const uint32_t wbase = warp * kWarpItems + lane;
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint32_t idx = wbase + i * 32;
+    if (idx < td.count) {
+      key[i] = keys_in[(size_t)td.start + idx];
+      val[i] = vals_in[(size_t)td.start + idx];
+    } else {
+      key[i] = KeyTraits<KeyT>::zero();
+      val[i] = 0;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint32_t idx = wbase + i * 32;
+    rank[i] = 0;
+    if (idx < td.count) rank[i] = (uint16_t)atomicAdd(&sm.hist[key_digit(key[i], shift)], 1u);
+  }
+  __syncthreads();
+  {
+    const uint32_t total = sm.hist[tid];
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(kFull, incl, o);
+      if (lane >= (uint32_t)o) incl += n;
+    }
+    if (lane == 31) sm.warp_sums[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) woff += (w < (int)warp) ? sm.warp_sums[w] : 0u;
+    const uint32_t excl = woff + incl - total;
+    sm.excl[tid] = excl;
+    uint32_t* my = lookback + (size_t)tile * kRadix + tid;
+    uint32_t prev = 0;
+    if (tile != td.first_tile) {
+      st_relaxed(my, kFlagAgg | total);
+      uint32_t j = tile, spins = 0;
+      bool failed = false;
+      for (;;) {
+        --j;
+        const uint32_t* p = lookback + (size_t)j * kRadix + tid;
+        uint32_t v = ld_relaxed(p);
+        while ((v & kFlagMask) == 0u) {
+          if (++spins > kSpinLimit) { failed = true; break; }
+          __nanosleep(40);
+          v = ld_relaxed(p);
+        }
+        if (failed) { atomicExch(err, 1u); break; }
+        prev += v & kValMask;
+        if ((v & kFlagMask) == kFlagIncl || j == td.first_tile) break;
+      }
+    }
+    st_relaxed(my, kFlagIncl | ((prev + total) & kValMask));
+    const size_t ds = ((size_t)td.seg * passes + pass) * kRadix + tid;
+    sm.gbase[tid] = digit_start[ds] + prev - excl;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < kSortItems; ++i) {
+    const uint32_t idx = wbase + i * 32;
+    if (idx < td.count) {
+      const uint32_t slot = sm.excl[key_digit(key[i], shift)] + rank[i];
+      sm.keys[slot] = key[i];
+      sm.vals[slot] = val[i];
+    }
+  }
+  __syncthreads();
+  for (uint32_t idx = tid; idx < td.count; idx += kSortThreads) {
+    const KeyT k = sm.keys[idx];
+    const uint32_t g = sm.gbase[key_digit(k, shift)] + idx;   // 32-bit wrap-around is intended
+    keys_out[g] = k;
+    vals_out[g] = sm.vals[idx];
+  }
+}
+
 }  // namespace pf

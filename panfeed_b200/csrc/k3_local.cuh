@@ -40,7 +40,7 @@ constexpr int kLocalItems = 8;
 constexpr int kLocalTile = kLocalThreads * kLocalItems;   // 2048 records
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr uint32_t kNoRow = 0xffffffffu;
-enum { LC_ROWS = 0, LC_UNIQUE = 1, LC_TABLE_OVERFLOW = 2, LC_ROW_OVERFLOW = 3 };
+enum { LC_ROWS = 0, LC_UNIQUE = 1, LC_TABLE_OVERFLOW = 2, LC_ROW_OVERFLOW = 3, LC_RESCUE = 4 };
 
 // prefix-runs of one radix pass are the digit buckets: their starts are the
 // scanned histogram itself.  first_run[t] = first bucket starting at or after tile t.
@@ -63,6 +63,7 @@ __global__ void k3_tiles_from_hist(const TileDev* __restrict__ ltiles, uint32_t 
 // ---------------------------------------------------------------------------
 // direct variant
 // ---------------------------------------------------------------------------
+constexpr int kDirectTile = 4096;                // records per CTA tile (2 chunks of 2048)
 constexpr int kDirectSlots = 2048;
 constexpr int kDirectPoolWords = 12288;          // 48 KB of bitsets
 constexpr uint32_t kDirectMaxUnique = 768;
@@ -72,7 +73,8 @@ struct DirectSmem {
   uint64_t keys[kDirectSlots + 1];     // slot kDirectSlots: home of the key equal to kEmptyKey
   alignas(16) uint32_t pool[kDirectPoolWords];   // dense id x W words
   uint16_t id[kDirectSlots + 2];       // slot -> dense id
-  uint16_t row_slot[kDirectMaxUnique]; // surviving row -> slot
+  uint16_t slot_of[kDirectMaxUnique];  // dense id -> slot
+  uint16_t row_id[kDirectMaxUnique];   // surviving row -> dense id
   uint32_t n_unique, n_pass, row_base, special_used, overflow, ok;
 };
 
@@ -82,27 +84,33 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
                 const uint32_t* __restrict__ tile_first_run /* [n_ltiles + 1] */,
                 const uint32_t* __restrict__ run_start, uint32_t n_records,
                 const ClusterDev* __restrict__ clusters, RowOut out, uint32_t row_capacity,
-                uint32_t* __restrict__ counters) {
+                uint32_t* __restrict__ counters,
+                uint32_t* __restrict__ rescue_runs /* out: runs of tiles that did not fit */,
+                const uint32_t* __restrict__ run_list /* null, or: one run per CTA (rescue launch) */,
+                const uint32_t* __restrict__ run_seg /* null: seg = run / 256 (runs from the histogram) */) {
   extern __shared__ __align__(16) unsigned char local_raw[];
   DirectSmem& sm = *reinterpret_cast<DirectSmem*>(local_raw);
   const uint32_t tid = threadIdx.x;
-  const uint32_t t = blockIdx.x;
-  const uint32_t r0 = tile_first_run[t], r1 = tile_first_run[t + 1];
-  if (r0 == r1) return;
   const uint32_t n_runs = tile_first_run[n_ltiles];
+  uint32_t r0, r1, seg;
+  if (run_list) {
+    r0 = run_list[blockIdx.x];
+    r1 = r0 + 1;
+    seg = run_seg ? run_seg[r0] : r0 / kRadix;
+  } else {
+    r0 = tile_first_run[blockIdx.x];
+    r1 = tile_first_run[blockIdx.x + 1];
+    if (r0 == r1) return;
+    seg = ltiles[blockIdx.x].seg;
+  }
   const uint32_t a = run_start[r0];
   const uint32_t b = (r1 < n_runs) ? run_start[r1] : n_records;
   if (a >= b) return;
-  const uint32_t seg = ltiles[t].seg;
   const ClusterDev cl = clusters[seg];
   const uint32_t W = out.pattern_words;
   const uint32_t max_unique = min(kDirectMaxUnique, (uint32_t)kDirectPoolWords / W);
 
   for (uint32_t i = tid; i <= kDirectSlots; i += kLocalThreads) sm.keys[i] = kEmptyKey;
-  {
-    uint4* p4 = reinterpret_cast<uint4*>(sm.pool);
-    for (uint32_t i = tid; i < kDirectPoolWords / 4; i += kLocalThreads) p4[i] = make_uint4(0, 0, 0, 0);
-  }
   if (tid == 0) { sm.n_unique = 0; sm.n_pass = 0; sm.special_used = 0; sm.overflow = 0; sm.ok = 1; }
   __syncthreads();
 
@@ -149,12 +157,26 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
     for (int j = 0; j < kLocalItems; ++j) {
       if (inserted >> j & 1u) {
         const uint32_t id = atomicAdd(&sm.n_unique, 1u);
-        if (id < max_unique) sm.id[slot[j]] = (uint16_t)id; else sm.overflow = 1;
+        if (id < max_unique) {
+          sm.id[slot[j]] = (uint16_t)id;
+          sm.slot_of[id] = slot[j];
+          for (uint32_t w = 0; w < W; ++w) sm.pool[id * W + w] = 0;   // bitsets are zeroed on demand
+        } else {
+          sm.overflow = 1;
+        }
       }
     }
     __syncthreads();
     if (sm.overflow) {
-      if (tid == 0) atomicExch(&counters[LC_TABLE_OVERFLOW], 1u);
+      // too many distinct keys for one CTA: hand the tile's runs to the rescue launch
+      // (one CTA per run); a single run that does not fit needs more sorted bits
+      if (run_list || r1 - r0 == 1) {
+        if (tid == 0) atomicExch(&counters[LC_TABLE_OVERFLOW], 1u);
+      } else {
+        if (tid == 0) sm.row_base = atomicAdd(&counters[LC_RESCUE], r1 - r0);
+        __syncthreads();
+        for (uint32_t r = r0 + tid; r < r1; r += kLocalThreads) rescue_runs[sm.row_base + (r - r0)] = r;
+      }
       return;
     }
     // (iii) one OR per record
@@ -168,17 +190,16 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
   __syncthreads();
 
   // ---- counts, filter, rows ---------------------------------------------------------
-  for (uint32_t i = tid; i <= kDirectSlots; i += kLocalThreads) {
-    const bool used = (i < kDirectSlots) ? (sm.keys[i] != kEmptyKey) : (sm.special_used != 0u);
-    if (!used) continue;
-    const uint32_t* bits = sm.pool + (uint32_t)sm.id[i] * W;
+  const uint32_t n_unique = sm.n_unique;
+  for (uint32_t id = tid; id < n_unique; id += kLocalThreads) {
+    const uint32_t* bits = sm.pool + id * W;
     uint32_t c = 0;
     for (uint32_t w = 0; w < W; ++w) c += __popc(bits[w]);
-    if (c >= cl.lo && c <= cl.hi) sm.row_slot[atomicAdd(&sm.n_pass, 1u)] = (uint16_t)i;
+    if (c >= cl.lo && c <= cl.hi) sm.row_id[atomicAdd(&sm.n_pass, 1u)] = (uint16_t)id;
   }
   __syncthreads();
   if (tid == 0) {
-    atomicAdd(&counters[LC_UNIQUE], sm.n_unique);
+    atomicAdd(&counters[LC_UNIQUE], n_unique);
     if (sm.n_pass) {
       const uint32_t base = atomicAdd(&counters[LC_ROWS], sm.n_pass);
       sm.row_base = base;
@@ -193,8 +214,9 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
   if (n_pass == 0 || !sm.ok) return;
   const uint32_t base = sm.row_base;
   for (uint32_t r = tid; r < n_pass; r += kLocalThreads) {
-    const uint32_t s = sm.row_slot[r];
-    const uint32_t* bits = sm.pool + (uint32_t)sm.id[s] * W;
+    const uint32_t id = sm.row_id[r];
+    const uint32_t s = sm.slot_of[id];
+    const uint32_t* bits = sm.pool + id * W;
     uint32_t c = 0;
     for (uint32_t w = 0; w < W; ++w) c += __popc(bits[w]);
     const size_t g = (size_t)base + r;
@@ -205,7 +227,7 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
   }
   for (uint32_t i = tid; i < n_pass * W; i += kLocalThreads) {
     const uint32_t r = i / W, w = i - r * W;
-    out.cand[((size_t)base + r) * out.key_words + w] = sm.pool[(uint32_t)sm.id[sm.row_slot[r]] * W + w];
+    out.cand[((size_t)base + r) * out.key_words + w] = sm.pool[(uint32_t)sm.row_id[r] * W + w];
   }
 }
 

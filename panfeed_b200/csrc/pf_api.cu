@@ -92,10 +92,13 @@ struct pf_ctx {
   bool partition = true;   // mode 0: few radix passes + shared-memory hash grouping (k3_local)
   bool use_direct = true;  // S <= 1024: bitsets for every distinct key in shared memory
   bool runs_from_hist = false;   // one pass: prefix-runs are the digit buckets of the histogram
+  uint32_t local_tile = 0;       // records per tile of the local reduce (8192 direct / 2048 general)
+  std::vector<std::pair<uint32_t, uint32_t>> nar_ranges;   // narrow record range of every cluster
   int extra_bits = 0;      // sort bits added after a table overflow (sticky)
   double row_ratio = 1.0 / 48;   // surviving rows per record, learned from earlier batches
   uint64_t row_cap = 0;
   uint64_t unique_last = 0;
+  uint32_t rescued_last = 0;
   PatternSpace kp, cp;     // k-mer patterns, cluster patterns
   uint64_t kp_base = 0, cp_base = 0;   // pool sizes before the resident batch
   // pinned results
@@ -175,7 +178,7 @@ constexpr int kGridPersist = 148 * 4;
 // counters layout in d_counters
 enum { C_TICKET_N = 0, C_TICKET_W = 1, C_RUNS_N = 2, C_RUNS_W = 3, C_ERR = 4, C_ROWS_N = 5,
        C_ROWS_W = 6, C_NEW_KP = 7, C_NEW_CP = 8, C_TICKET_MARK_N = 9, C_TICKET_MARK_W = 10,
-       C_LOCAL = 11 /* 4 words: rows, unique, table overflow, row overflow */, C_COUNT = 16 };
+       C_LOCAL = 11 /* 5 words: rows, unique, table overflow, row overflow, rescue runs */, C_COUNT = 16 };
 
 bool keep_count(double maf, uint32_t c, uint32_t n) {
   double af = (double)c / (double)n;      // numpy: vec.sum() / vec.shape[0]
@@ -260,6 +263,8 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
                        (int)sizeof(SortSmem<uint64_t>));
   cudaFuncSetAttribute(k2_onesweep_pass<Key128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)sizeof(SortSmem<Key128>));
+  cudaFuncSetAttribute(k2_scatter_pass<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(ScatterSmem<uint64_t>));
   cudaFuncSetAttribute(k3_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LocalSmem));
   cudaFuncSetAttribute(k3_local_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DirectSmem));
   ctx->use_direct = ctx->W <= kDirectMaxWords;
@@ -332,6 +337,39 @@ int auto_sort_bits(const pf_ctx* ctx, uint32_t max_seg_records, bool narrow) {
 }
 
 // Build the tile list of one key width from the per-cluster record ranges.
+// Tile list of the local reduce (partition mode): 8192-record tiles for the direct
+// variant, 2048 for the general one (its exactness guarantee needs <= 2048).
+int plan_local_tiles(pf_ctx* ctx) {
+  WidthState& w = ctx->nar;
+  if (!ctx->partition) { w.n_ltiles = 0; return PF_OK; }
+  const uint32_t tile = ctx->use_direct ? (uint32_t)kDirectTile : (uint32_t)kLocalTile;
+  ctx->local_tile = tile;
+  uint64_t nl = 0;
+  for (auto& r : ctx->nar_ranges) nl += cdiv(r.second - r.first, tile);
+  w.n_ltiles = (uint32_t)nl;
+  TRY(pin_ensure(ctx, w.h_ltiles, std::max<size_t>(1, nl) * sizeof(TileDev)));
+  TileDev* lt = w.h_ltiles.as<TileDev>();
+  uint32_t li = 0;
+  for (uint32_t c = 0; c < ctx->nar_ranges.size(); ++c) {
+    const uint32_t first = li;
+    for (uint32_t s = ctx->nar_ranges[c].first; s < ctx->nar_ranges[c].second; s += tile) {
+      lt[li].start = s;
+      lt[li].count = std::min<uint32_t>(tile, ctx->nar_ranges[c].second - s);
+      lt[li].seg = c;
+      lt[li].first_tile = first;
+      ++li;
+    }
+  }
+  if (w.n_ltiles) {
+    TRY(dev_ensure(ctx, w.ltiles, (size_t)w.n_ltiles * sizeof(TileDev)));
+    TRY(dev_ensure(ctx, w.tile_first_run, ((size_t)w.n_ltiles + 1) * 4));
+    TRY(dev_ensure(ctx, w.lookback, std::max<size_t>((size_t)w.n_tiles * kRadix * 4, (size_t)w.n_ltiles * 8)));
+    CU(cudaMemcpyAsync(w.ltiles.p, w.h_ltiles.p, w.n_ltiles * sizeof(TileDev), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return PF_OK;
+}
+
 int plan_tiles(pf_ctx* ctx, WidthState& w, const std::vector<std::pair<uint32_t, uint32_t>>& ranges, bool narrow) {
   uint64_t n_tiles = 0;
   uint32_t max_seg = 0;
@@ -345,26 +383,6 @@ int plan_tiles(pf_ctx* ctx, WidthState& w, const std::vector<std::pair<uint32_t,
   w.max_seg = max_seg;
   w.sort_bits = auto_sort_bits(ctx, max_seg, narrow);
   w.passes = w.sort_bits / 8;
-  if (narrow && ctx->partition) {      // second tile list: 2048-record tiles for mark + local reduce
-    uint64_t nl = 0;
-    for (auto& r : ranges) nl += cdiv(r.second - r.first, kLocalTile);
-    w.n_ltiles = (uint32_t)nl;
-    TRY(pin_ensure(ctx, w.h_ltiles, std::max<size_t>(1, nl) * sizeof(TileDev)));
-    TileDev* lt = w.h_ltiles.as<TileDev>();
-    uint32_t li = 0;
-    for (uint32_t c = 0; c < ranges.size(); ++c) {
-      const uint32_t first = li;
-      for (uint32_t s = ranges[c].first; s < ranges[c].second; s += kLocalTile) {
-        lt[li].start = s;
-        lt[li].count = std::min<uint32_t>(kLocalTile, ranges[c].second - s);
-        lt[li].seg = c;
-        lt[li].first_tile = first;
-        ++li;
-      }
-    }
-  } else {
-    w.n_ltiles = 0;
-  }
   TRY(pin_ensure(ctx, w.h_tiles, std::max<size_t>(1, n_tiles) * sizeof(TileDev)));
   TRY(pin_ensure(ctx, w.h_seg_start, std::max<size_t>(1, ranges.size()) * sizeof(uint32_t)));
   TileDev* t = w.h_tiles.as<TileDev>();
@@ -510,12 +528,9 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
     TRY(dev_ensure(ctx, w->seg_start, std::max<size_t>(1, b->n_clusters) * 4));
     TRY(dev_ensure(ctx, w->seg_hist, std::max<size_t>(1, (size_t)b->n_clusters * w->passes * kRadix) * 4));
     TRY(dev_ensure(ctx, w->lookback, std::max<size_t>(1, (size_t)w->n_tiles * kRadix) * 4));
-    if (w->n_ltiles) {
-      TRY(dev_ensure(ctx, w->ltiles, (size_t)w->n_ltiles * sizeof(TileDev)));
-      TRY(dev_ensure(ctx, w->tile_first_run, ((size_t)w->n_ltiles + 1) * 4));
-      TRY(dev_ensure(ctx, w->lookback, std::max<size_t>((size_t)w->n_tiles * kRadix * 4, (size_t)w->n_ltiles * 8)));
-    }
   }
+  ctx->nar_ranges = nr;
+  TRY(plan_local_tiles(ctx));
   cudaStream_t st = ctx->stream;
   CU(cudaEventRecord(ctx->ev_h2d[0], st));
   if (b->n_words) CU(cudaMemcpyAsync(ctx->d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, st));
@@ -527,7 +542,6 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
   }
   for (WidthState* w : {&ctx->nar, &ctx->wid}) {
     if (w->n_tiles) CU(cudaMemcpyAsync(w->tiles.p, w->h_tiles.p, w->n_tiles * sizeof(TileDev), cudaMemcpyHostToDevice, st));
-    if (w->n_ltiles) CU(cudaMemcpyAsync(w->ltiles.p, w->h_ltiles.p, w->n_ltiles * sizeof(TileDev), cudaMemcpyHostToDevice, st));
     if (b->n_clusters) CU(cudaMemcpyAsync(w->seg_start.p, w->h_seg_start.p, b->n_clusters * 4, cudaMemcpyHostToDevice, st));
   }
   if (n_wide) {
@@ -572,7 +586,7 @@ int hist_width(pf_ctx* ctx, WidthState& w) {
 }
 
 template <typename KeyT>
-int passes_width(pf_ctx* ctx, WidthState& w, int ticket_idx) {
+int passes_width(pf_ctx* ctx, WidthState& w, int ticket_idx, bool unstable = false) {
   if (w.n_records == 0) { w.final_buf = 0; return PF_OK; }
   cudaStream_t st = ctx->stream;
   const int shift0 = KeyTraits<KeyT>::kBits - w.sort_bits;
@@ -581,10 +595,16 @@ int passes_width(pf_ctx* ctx, WidthState& w, int ticket_idx) {
   for (int p = 0; p < w.passes; ++p) {
     CU(cudaMemsetAsync(w.lookback.p, 0, (size_t)w.n_tiles * kRadix * 4, st));
     CU(cudaMemsetAsync(counters + ticket_idx, 0, 4, st));
-    k2_onesweep_pass<KeyT><<<w.n_tiles, kSortThreads, sizeof(SortSmem<KeyT>), st>>>(
-        w.keys[src].as<KeyT>(), w.vals[src].as<uint32_t>(), w.keys[src ^ 1].as<KeyT>(),
-        w.vals[src ^ 1].as<uint32_t>(), w.tiles.as<TileDev>(), w.n_tiles, w.seg_hist.as<uint32_t>(), p,
-        w.passes, shift0 + 8 * p, w.lookback.as<uint32_t>(), counters + ticket_idx, counters + C_ERR);
+    if (unstable && p == 0)   // LSD: only the first pass may ignore the incoming order
+      k2_scatter_pass<KeyT><<<w.n_tiles, kSortThreads, sizeof(ScatterSmem<KeyT>), st>>>(
+          w.keys[src].as<KeyT>(), w.vals[src].as<uint32_t>(), w.keys[src ^ 1].as<KeyT>(),
+          w.vals[src ^ 1].as<uint32_t>(), w.tiles.as<TileDev>(), w.n_tiles, w.seg_hist.as<uint32_t>(), p,
+          w.passes, shift0 + 8 * p, w.lookback.as<uint32_t>(), counters + ticket_idx, counters + C_ERR);
+    else
+      k2_onesweep_pass<KeyT><<<w.n_tiles, kSortThreads, sizeof(SortSmem<KeyT>), st>>>(
+          w.keys[src].as<KeyT>(), w.vals[src].as<uint32_t>(), w.keys[src ^ 1].as<KeyT>(),
+          w.vals[src ^ 1].as<uint32_t>(), w.tiles.as<TileDev>(), w.n_tiles, w.seg_hist.as<uint32_t>(), p,
+          w.passes, shift0 + 8 * p, w.lookback.as<uint32_t>(), counters + ticket_idx, counters + C_ERR);
     ctx->launches++;
     src ^= 1;
   }
@@ -605,7 +625,12 @@ int mark_width(pf_ctx* ctx, WidthState& w, int ticket_idx, int runs_idx, bool lo
   const uint32_t nt = local_tiles ? w.n_ltiles : w.n_tiles;
   CU(cudaMemsetAsync(w.lookback.p, 0, (size_t)nt * 8, st));
   CU(cudaMemsetAsync(counters + ticket_idx, 0, 4, st));
-  if (local_tiles)
+  if (local_tiles && ctx->local_tile == (uint32_t)kDirectTile)
+    k3_mark_runs<KeyT, kDirectTile / kSortThreads><<<nt, kSortThreads, 0, st>>>(
+        w.keys[w.final_buf].as<KeyT>(), w.ltiles.as<TileDev>(), nt, w.sort_bits, run_start, run_seg,
+        w.tile_first_run.as<uint32_t>(), w.lookback.as<uint64_t>(), counters + ticket_idx,
+        counters + runs_idx, counters + C_ERR);
+  else if (local_tiles)
     k3_mark_runs<KeyT, kLocalItems><<<nt, kSortThreads, 0, st>>>(
         w.keys[w.final_buf].as<KeyT>(), w.ltiles.as<TileDev>(), nt, w.sort_bits, run_start, run_seg,
         w.tile_first_run.as<uint32_t>(), w.lookback.as<uint64_t>(), counters + ticket_idx,
@@ -777,20 +802,33 @@ int launch_k1(pf_ctx* ctx) {
   return PF_OK;
 }
 
-int launch_local(pf_ctx* ctx, RowOut ro) {
+int launch_local(pf_ctx* ctx, RowOut ro, uint32_t n_rescue = 0) {
   WidthState& N = ctx->nar;
   if (N.n_records == 0) return PF_OK;
   cudaStream_t st = ctx->stream;
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
   const int other = N.final_buf ^ 1;
   const uint32_t* run_start = ctx->runs_from_hist ? N.seg_hist.as<uint32_t>() : N.keys[other].as<uint32_t>();
+  const uint32_t* run_seg = ctx->runs_from_hist ? nullptr : N.keys[other].as<uint32_t>() + ((size_t)N.n_records + 1);
+  uint32_t* rescue = N.vals[other].as<uint32_t>();       // idle in partition mode
   const uint32_t cap = (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu);
-  CU(cudaMemsetAsync(counters + C_LOCAL, 0, 4 * 4, st));
+  if (n_rescue) {
+    // second launch of the direct variant: one CTA per run of the tiles that overflowed;
+    // rows/unique counters keep accumulating
+    k3_local_direct<<<n_rescue, kLocalThreads, sizeof(DirectSmem), st>>>(
+        N.keys[N.final_buf].as<uint64_t>(), N.vals[N.final_buf].as<uint32_t>(), N.ltiles.as<TileDev>(),
+        N.n_ltiles, N.tile_first_run.as<uint32_t>(), run_start, N.n_records,
+        ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL, rescue, rescue, run_seg);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return PF_OK;
+  }
+  CU(cudaMemsetAsync(counters + C_LOCAL, 0, 5 * 4, st));
   if (ctx->use_direct)
     k3_local_direct<<<N.n_ltiles, kLocalThreads, sizeof(DirectSmem), st>>>(
         N.keys[N.final_buf].as<uint64_t>(), N.vals[N.final_buf].as<uint32_t>(), N.ltiles.as<TileDev>(),
         N.n_ltiles, N.tile_first_run.as<uint32_t>(), run_start, N.n_records,
-        ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL);
+        ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL, rescue, nullptr, run_seg);
   else
     k3_local<<<N.n_ltiles, kLocalThreads, sizeof(LocalSmem), st>>>(
         N.keys[N.final_buf].as<uint64_t>(), N.vals[N.final_buf].as<uint32_t>(), N.ltiles.as<TileDev>(),
@@ -877,7 +915,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
     TRY(hist_width<Key128>(ctx, Wd));
     STAGE("k2_histogram");
     CU(cudaEventRecord(ctx->ev[EV_HIST], st));
-    TRY(passes_width<uint64_t>(ctx, N, C_TICKET_N));
+    TRY(passes_width<uint64_t>(ctx, N, C_TICKET_N, part && ctx->use_direct));
     TRY(passes_width<Key128>(ctx, Wd, C_TICKET_W));
     STAGE("k2_onesweep_pass");
     CU(cudaEventRecord(ctx->ev[EV_SORT], st));
@@ -889,54 +927,60 @@ extern "C" int pf_execute(pf_ctx* ctx) {
     TRY(mark_width<Key128>(ctx, Wd, C_TICKET_MARK_W, C_RUNS_W, false));
     STAGE("k3_mark_runs<wide>");
     CU(cudaEventRecord(ctx->ev[EV_MARK], st));
-    if (part) {
-      ro.cluster = ctx->d_row_cluster.as<uint32_t>();
-      ro.count = ctx->d_row_count.as<uint32_t>();
-      ro.cand = ctx->d_cand.as<uint32_t>();
-      ro.kmer = ctx->d_row_kmer.as<uint64_t>();
-      ro.row_base = 0;
-      TRY(launch_local(ctx, ro));
-      STAGE("k3_local");
-    }
-    CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    TRY(check_device_error(ctx));
+    // local reduce (+ rescue launch of the direct variant), then one sync to read the counters
+    auto run_local = [&]() -> int {
+      if (part) {
+        ro.cluster = ctx->d_row_cluster.as<uint32_t>();
+        ro.count = ctx->d_row_count.as<uint32_t>();
+        ro.cand = ctx->d_cand.as<uint32_t>();
+        ro.kmer = ctx->d_row_kmer.as<uint64_t>();
+        ro.row_base = 0;
+        TRY(launch_local(ctx, ro));
+        STAGE("k3_local");
+      }
+      CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      TRY(check_device_error(ctx));
+      ctx->rescued_last = 0;
+      if (part && ctx->use_direct && N.n_records && hcnt[C_LOCAL + LC_RESCUE] &&
+          !hcnt[C_LOCAL + LC_TABLE_OVERFLOW]) {
+        ctx->rescued_last = hcnt[C_LOCAL + LC_RESCUE];
+        TRY(launch_local(ctx, ro, hcnt[C_LOCAL + LC_RESCUE]));
+        CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+      }
+      return PF_OK;
+    };
+    TRY(run_local());
     ctx->cp.n = ctx->cp_base + hcnt[C_NEW_CP];
     N.n_runs = N.n_records ? hcnt[C_RUNS_N] : 0;
     Wd.n_runs = Wd.n_records ? hcnt[C_RUNS_W] : 0;
     if (!part || N.n_records == 0) break;
-    if (hcnt[C_LOCAL + LC_TABLE_OVERFLOW] && ctx->use_direct) {
-      // more distinct k-mers in a tile than the direct variant has bitsets for:
-      // switch to the general variant for good and redo the reduction only
-      ctx->use_direct = false;
-      TRY(launch_local(ctx, ro));
-      CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
-    }
+    if (attempt > 10) return fail(ctx, PF_ERR_INTERNAL, "partition mode did not converge");
     if (hcnt[C_LOCAL + LC_TABLE_OVERFLOW]) {
-      // more distinct k-mers under one sorted prefix than a CTA's table holds:
-      // sort 8 more bits and start over (at 64 bits this cannot happen)
-      if (N.sort_bits >= 64) return fail(ctx, PF_ERR_INTERNAL, "local table overflow at 64 sorted bits");
-      ctx->extra_bits += 8;
-      N.sort_bits = auto_sort_bits(ctx, N.max_seg, true);
-      N.passes = N.sort_bits / 8;
-      TRY(dev_ensure(ctx, N.seg_hist, std::max<size_t>(1, (size_t)ctx->n_clusters * N.passes * kRadix) * 4));
+      // one prefix-run alone holds more distinct k-mers than a CTA can hold: sort 8 more
+      // bits (runs get 256x smaller) and redo the batch.  At 64 bits the general variant
+      // always fits (<= 2048 + 1 keys per tile); the direct one falls back to it.
+      if (N.sort_bits < 64) {
+        ctx->extra_bits += 8;
+        N.sort_bits = auto_sort_bits(ctx, N.max_seg, true);
+        N.passes = N.sort_bits / 8;
+        TRY(dev_ensure(ctx, N.seg_hist, std::max<size_t>(1, (size_t)ctx->n_clusters * N.passes * kRadix) * 4));
+      } else if (ctx->use_direct) {
+        ctx->use_direct = false;
+        TRY(plan_local_tiles(ctx));
+      } else {
+        return fail(ctx, PF_ERR_INTERNAL, "local table overflow at 64 sorted bits");
+      }
       continue;
     }
     if (hcnt[C_LOCAL + LC_ROW_OVERFLOW]) {
       ctx->row_cap = (uint64_t)hcnt[C_LOCAL + LC_ROWS] + 1024;
       TRY(ensure_rows(ctx, ctx->row_cap, ctx->row_cap, false));
-      ro.cluster = ctx->d_row_cluster.as<uint32_t>();
-      ro.count = ctx->d_row_count.as<uint32_t>();
-      ro.cand = ctx->d_cand.as<uint32_t>();
-      ro.kmer = ctx->d_row_kmer.as<uint64_t>();
-      TRY(launch_local(ctx, ro));
-      CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
-      CU(cudaStreamSynchronize(st));
+      TRY(run_local());
       if (hcnt[C_LOCAL + LC_ROW_OVERFLOW] || hcnt[C_LOCAL + LC_TABLE_OVERFLOW])
         return fail(ctx, PF_ERR_INTERNAL, "local reduce overflowed twice");
     }
-    if (attempt > 8) return fail(ctx, PF_ERR_INTERNAL, "partition mode did not converge");
     break;
   }
 

@@ -125,6 +125,23 @@ def test_random_clusters_match_oracle(case, engine):
                          batch_clusters=bc, sort_bits=sb, mode=engine)
 
 
+def test_partition_direct_rescue_launch():
+    """Tiles with more distinct k-mers than the direct variant holds (768) are
+    re-run one prefix-run per CTA; result must stay exact with one sorted byte."""
+    rng = np.random.default_rng(78)
+    comp = str.maketrans("ACGT", "TGCA")
+    S = 6
+    names = [f"g{i}" for i in range(S)]
+    cluster = {}
+    for s in names:
+        q = "".join(rng.choice(list("ACGT"), 20000))
+        cluster[s] = [ref_port.CutSeq(q, q.translate(comp), s + "_f", "c", 1, 20000, 1, 0)]
+    items = [(cluster, "mid", np.ones(S, dtype=int))]
+    out, want = _compare_with_oracle(items, set(), S, 31, True, False, False, 0.0,
+                                     batch_clusters=1, mode=0)
+    assert out["stats"]["sort_passes"] == 1
+
+
 def test_partition_general_variant_large_S():
     """S > 1024 takes the general k3_local variant (pair set + rounds of bitsets)."""
     rng = np.random.default_rng(5)
