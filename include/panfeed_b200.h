@@ -61,7 +61,7 @@ typedef struct pf_params {
                                     in a shared-memory hash table (default);
                                     1 = full sort: LSD passes over sort_bits, then a
                                     segmented run reduction                          */
-  uint32_t reserved;
+  uint32_t debug_flags;          /* bit 0: do not fuse K1 into the histogram / first pass   */
   double   maf;                  /* --maf, compared in float64 exactly as
                                     panfeed.py:190-200 (see pf_maf_window)          */
 } pf_params;

@@ -31,7 +31,7 @@ class Params(C.Structure):
                 ("consider_missing", C.c_uint32),
                 ("cluster_equal_filter", C.c_uint32),
                 ("emit_positions", C.c_uint32), ("sort_bits", C.c_uint32),
-                ("mode", C.c_uint32), ("reserved", C.c_uint32),
+                ("mode", C.c_uint32), ("debug_flags", C.c_uint32),
                 ("maf", C.c_double)]
 
 
@@ -202,11 +202,11 @@ class Context:
 
     def __init__(self, k, n_samples, canonical=True, consider_missing=False,
                  cluster_equal_filter=False, emit_positions=False, maf=0.01,
-                 sort_bits=0, device=0, mode=0):
+                 sort_bits=0, device=0, mode=0, debug_flags=0):
         self.lib = load()
         self.params = Params(PF_ABI_VERSION, k, n_samples, int(canonical),
                              int(consider_missing), int(cluster_equal_filter),
-                             int(emit_positions), sort_bits, mode, 0, maf)
+                             int(emit_positions), sort_bits, mode, debug_flags, maf)
         self.h = C.c_void_p()
         rc = self.lib.pf_create(C.byref(self.h), device, C.byref(self.params))
         if rc != 0:

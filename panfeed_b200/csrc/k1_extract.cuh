@@ -33,7 +33,9 @@ __device__ __forceinline__ uint64_t revcomp2(uint64_t fwd, int k) {
   return v >> (64 - 2 * k);
 }
 
-template <bool CANON>
+// RECORDS = false: positional records only (target sequences); the k-mer records are
+// produced by the fused first pass (k1_fused.cuh) instead.
+template <bool CANON, bool RECORDS>
 __global__ void __launch_bounds__(kK1Warps * 32)
 k1_extract(const uint64_t* __restrict__ bases, const uint32_t* __restrict__ ambbits,
            const SeqDev* __restrict__ seqs, uint32_t n_seqs, int k,
@@ -51,6 +53,7 @@ k1_extract(const uint64_t* __restrict__ bases, const uint32_t* __restrict__ ambb
     const uint32_t nwin = d.len - (uint32_t)k + 1u;
     const uint64_t* w = bases + (d.base_off >> 5);
     const bool target = (d.flags & 1u) != 0u;
+    if (!RECORDS && !target) continue;
     const bool amb = (d.flags & 2u) != 0u;
     const uint32_t* ab = amb ? (ambbits + (d.amb_off >> 5)) : nullptr;
 
@@ -88,9 +91,11 @@ k1_extract(const uint64_t* __restrict__ bases, const uint32_t* __restrict__ ambb
         if (CANON) {
           const bool use_rc = rc < fwd;          // reference: fwd <= rc keeps fwd (+1)
           const uint64_t canon = use_rc ? rc : fwd;
-          const size_t r = (size_t)d.rec_off + p;
-          keys[r] = is_amb ? 0ull : mix64(canon);
-          vals[r] = is_amb ? kInvalidSample : d.sample;
+          if (RECORDS) {
+            const size_t r = (size_t)d.rec_off + p;
+            keys[r] = is_amb ? 0ull : mix64(canon);
+            vals[r] = is_amb ? kInvalidSample : d.sample;
+          }
           if (target) {
             const size_t q = (size_t)d.pos_off + p;
             pos.kmer[q] = is_amb ? (uint64_t)(d.pwide_off + p) : canon;
@@ -100,13 +105,15 @@ k1_extract(const uint64_t* __restrict__ bases, const uint32_t* __restrict__ ambb
             pos.flags[q] = (uint8_t)((use_rc ? 1u : 0u) | (is_amb ? 2u : 0u));
           }
         } else {
-          const size_t r = (size_t)d.rec_off + 2 * (size_t)p;
-          ulonglong2 kk;
-          kk.x = is_amb ? 0ull : mix64(fwd);
-          kk.y = is_amb ? 0ull : mix64(rc);
-          *reinterpret_cast<ulonglong2*>(keys + r) = kk;
-          const uint32_t sv = is_amb ? kInvalidSample : d.sample;
-          *reinterpret_cast<uint2*>(vals + r) = make_uint2(sv, sv);
+          if (RECORDS) {
+            const size_t r = (size_t)d.rec_off + 2 * (size_t)p;
+            ulonglong2 kk;
+            kk.x = is_amb ? 0ull : mix64(fwd);
+            kk.y = is_amb ? 0ull : mix64(rc);
+            *reinterpret_cast<ulonglong2*>(keys + r) = kk;
+            const uint32_t sv = is_amb ? kInvalidSample : d.sample;
+            *reinterpret_cast<uint2*>(vals + r) = make_uint2(sv, sv);
+          }
           if (target) {
             const size_t q = (size_t)d.pos_off + p;
             pos.kmer[q] = is_amb ? (uint64_t)(d.pwide_off + p) : fwd;

@@ -108,7 +108,10 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
   if (a >= b) return;
   const ClusterDev cl = clusters[seg];
   const uint32_t W = out.pattern_words;
-  const uint32_t max_unique = min(kDirectMaxUnique, (uint32_t)kDirectPoolWords / W);
+  // bitset rows are W words at an ODD stride: the records a warp handles together mostly
+  // carry the same sample (same word index), so distinct rows must fall in distinct banks
+  const uint32_t WS = W | 1u;
+  const uint32_t max_unique = min(kDirectMaxUnique, (uint32_t)kDirectPoolWords / WS);
 
   for (uint32_t i = tid; i <= kDirectSlots; i += kLocalThreads) sm.keys[i] = kEmptyKey;
   if (tid == 0) { sm.n_unique = 0; sm.n_pass = 0; sm.special_used = 0; sm.overflow = 0; sm.ok = 1; }
@@ -160,7 +163,7 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
         if (id < max_unique) {
           sm.id[slot[j]] = (uint16_t)id;
           sm.slot_of[id] = slot[j];
-          for (uint32_t w = 0; w < W; ++w) sm.pool[id * W + w] = 0;   // bitsets are zeroed on demand
+          for (uint32_t w = 0; w < W; ++w) sm.pool[id * WS + w] = 0;   // bitsets are zeroed on demand
         } else {
           sm.overflow = 1;
         }
@@ -184,7 +187,7 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
     for (int j = 0; j < kLocalItems; ++j) {
       if (slot[j] == 0xffff) continue;
       const uint32_t v = val[j];
-      atomicOr(&sm.pool[(uint32_t)sm.id[slot[j]] * W + (v >> 5)], 1u << (v & 31u));
+      atomicOr(&sm.pool[(uint32_t)sm.id[slot[j]] * WS + (v >> 5)], 1u << (v & 31u));
     }
   }
   __syncthreads();
@@ -192,7 +195,7 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
   // ---- counts, filter, rows ---------------------------------------------------------
   const uint32_t n_unique = sm.n_unique;
   for (uint32_t id = tid; id < n_unique; id += kLocalThreads) {
-    const uint32_t* bits = sm.pool + id * W;
+    const uint32_t* bits = sm.pool + id * WS;
     uint32_t c = 0;
     for (uint32_t w = 0; w < W; ++w) c += __popc(bits[w]);
     if (c >= cl.lo && c <= cl.hi) sm.row_id[atomicAdd(&sm.n_pass, 1u)] = (uint16_t)id;
@@ -216,7 +219,7 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
   for (uint32_t r = tid; r < n_pass; r += kLocalThreads) {
     const uint32_t id = sm.row_id[r];
     const uint32_t s = sm.slot_of[id];
-    const uint32_t* bits = sm.pool + id * W;
+    const uint32_t* bits = sm.pool + id * WS;
     uint32_t c = 0;
     for (uint32_t w = 0; w < W; ++w) c += __popc(bits[w]);
     const size_t g = (size_t)base + r;
@@ -227,7 +230,7 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
   }
   for (uint32_t i = tid; i < n_pass * W; i += kLocalThreads) {
     const uint32_t r = i / W, w = i - r * W;
-    out.cand[((size_t)base + r) * out.key_words + w] = sm.pool[(uint32_t)sm.row_id[r] * W + w];
+    out.cand[((size_t)base + r) * out.key_words + w] = sm.pool[(uint32_t)sm.row_id[r] * WS + w];
   }
 }
 
@@ -392,11 +395,12 @@ k3_local(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
 
   // ---- phase 3: bitsets of the surviving keys, `per_round` rows at a time ----------
   uint32_t* pool = sm.pairs;                     // pairs + pool_tail are contiguous
-  const uint32_t per_round = max(1u, (uint32_t)kLocalPoolWords / W);
+  const uint32_t WS = (W | 1u) <= (uint32_t)kLocalPoolWords ? (W | 1u) : W;   // odd stride: no bank aliasing between rows
+  const uint32_t per_round = max(1u, (uint32_t)kLocalPoolWords / WS);
   for (uint32_t lo = 0; lo < n_pass; lo += per_round) {
     const uint32_t rows = min(per_round, n_pass - lo);
     __syncthreads();
-    for (uint32_t i = tid; i < rows * W; i += kLocalThreads) pool[i] = 0;
+    for (uint32_t i = tid; i < rows * WS; i += kLocalThreads) pool[i] = 0;
     __syncthreads();
     for (uint32_t c0 = a; c0 < b; c0 += kLocalTile) {
       uint64_t key[kLocalItems];
@@ -414,13 +418,13 @@ k3_local(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals,
         if (v == kInvalidSample) continue;
         const uint32_t row = sm.last[local_find(sm, key[j])];
         if (row - lo < rows)                      // also false for kNoRow
-          atomicOr(&pool[(row - lo) * W + (v >> 5)], 1u << (v & 31u));
+          atomicOr(&pool[(row - lo) * WS + (v >> 5)], 1u << (v & 31u));
       }
     }
     __syncthreads();
     for (uint32_t i = tid; i < rows * W; i += kLocalThreads) {
       const uint32_t r = i / W, w = i - r * W;
-      out.cand[((size_t)base + lo + r) * out.key_words + w] = pool[i];
+      out.cand[((size_t)base + lo + r) * out.key_words + w] = pool[r * WS + w];
     }
   }
 }

@@ -23,7 +23,7 @@ __device__ __forceinline__ uint64_t warp_hash_words(const uint32_t* __restrict__
   for (uint32_t w = lane_id(); w < n; w += 32) h += word_hash(key[w], w);
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) h += __shfl_xor_sync(kFull, h, m);
-  return mix64(h);
+  return fmix64(h);
 }
 
 __device__ __forceinline__ bool warp_equal_words(const uint32_t* __restrict__ a,

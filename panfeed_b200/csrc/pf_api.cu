@@ -14,6 +14,7 @@
 
 #include "../../include/panfeed_b200.h"
 #include "k1_extract.cuh"
+#include "k1_fused.cuh"
 #include "k2_onesweep.cuh"
 #include "k3_reduce.cuh"
 #include "k3_local.cuh"
@@ -92,7 +93,10 @@ struct pf_ctx {
   bool partition = true;   // mode 0: few radix passes + shared-memory hash grouping (k3_local)
   bool use_direct = true;  // S <= 1024: bitsets for every distinct key in shared memory
   bool runs_from_hist = false;   // one pass: prefix-runs are the digit buckets of the histogram
-  uint32_t local_tile = 0;       // records per tile of the local reduce (8192 direct / 2048 general)
+  uint32_t local_tile = 0;       // records per tile of the local reduce (4096 direct / 2048 general)
+  bool fused = false;            // K1 fused into the histogram and the first pass (no record write in K1)
+  DevBuf d_seq_rec_off, d_tile_first_seq;
+  PinBuf h_seq_rec_off, h_tile_first_seq;
   std::vector<std::pair<uint32_t, uint32_t>> nar_ranges;   // narrow record range of every cluster
   int extra_bits = 0;      // sort bits added after a table overflow (sticky)
   double row_ratio = 1.0 / 48;   // surviving rows per record, learned from earlier batches
@@ -265,6 +269,10 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
                        (int)sizeof(SortSmem<Key128>));
   cudaFuncSetAttribute(k2_scatter_pass<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        (int)sizeof(ScatterSmem<uint64_t>));
+  cudaFuncSetAttribute(k2_extract_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(ScatterSmem<uint64_t>));
+  cudaFuncSetAttribute(k2_extract_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)sizeof(ScatterSmem<uint64_t>));
   cudaFuncSetAttribute(k3_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LocalSmem));
   cudaFuncSetAttribute(k3_local_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DirectSmem));
   ctx->use_direct = ctx->W <= kDirectMaxWords;
@@ -295,7 +303,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->d_row_pattern, &ctx->d_cand, &ctx->d_rep, &ctx->d_slot_of, &ctx->d_winner,
                     &ctx->d_cl_pattern, &ctx->d_cl_rep, &ctx->d_cl_slot, &ctx->d_cl_winner,
                     &ctx->d_pos_kmer, &ctx->d_pos_seq, &ctx->d_pos_cstart, &ctx->d_pos_gstart,
-                    &ctx->d_pos_flags, &ctx->d_pos_wide})
+                    &ctx->d_pos_flags, &ctx->d_pos_wide, &ctx->d_seq_rec_off, &ctx->d_tile_first_seq})
     fd(*b);
   for (WidthState* w : {&ctx->nar, &ctx->wid}) {
     for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
@@ -307,6 +315,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
     for (DevBuf* b : {&s->pool, &s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique})
       fd(*b);
   for (PinBuf* b : {&ctx->h_seqs, &ctx->h_clusters, &ctx->h_wide_seqs, &ctx->h_counters,
+                    &ctx->h_seq_rec_off, &ctx->h_tile_first_seq,
                     &ctx->r_row_cluster, &ctx->r_row_kmer, &ctx->r_wrow_kmer, &ctx->r_row_count,
                     &ctx->r_row_pattern, &ctx->r_cl_pattern, &ctx->r_new_kp, &ctx->r_new_cp,
                     &ctx->r_pos_kmer, &ctx->r_pos_seq, &ctx->r_pos_cstart, &ctx->r_pos_gstart,
@@ -531,6 +540,26 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
   }
   ctx->nar_ranges = nr;
   TRY(plan_local_tiles(ctx));
+  // fused first pass: record index -> sequence lookup tables
+  {
+    TRY(pin_ensure(ctx, ctx->h_seq_rec_off, ((size_t)b->n_seqs + 1) * 4));
+    TRY(pin_ensure(ctx, ctx->h_tile_first_seq, ((size_t)ctx->nar.n_tiles + 1) * 4));
+    uint32_t* ro = ctx->h_seq_rec_off.as<uint32_t>();
+    for (uint32_t i = 0; i < b->n_seqs; ++i) ro[i] = hs[i].rec_off;
+    ro[b->n_seqs] = (uint32_t)rec;
+    uint32_t* tf = ctx->h_tile_first_seq.as<uint32_t>();
+    const TileDev* tl = ctx->nar.h_tiles.as<TileDev>();
+    uint32_t sp = 0;
+    for (uint32_t t = 0; t < ctx->nar.n_tiles; ++t) {
+      while (sp + 1 < b->n_seqs && ro[sp + 1] <= tl[t].start) ++sp;
+      tf[t] = sp;
+    }
+    tf[ctx->nar.n_tiles] = b->n_seqs ? b->n_seqs - 1 : 0;
+    TRY(dev_ensure(ctx, ctx->d_seq_rec_off, ((size_t)b->n_seqs + 1) * 4));
+    TRY(dev_ensure(ctx, ctx->d_tile_first_seq, ((size_t)ctx->nar.n_tiles + 1) * 4));
+    CU(cudaMemcpyAsync(ctx->d_seq_rec_off.p, ro, ((size_t)b->n_seqs + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_tile_first_seq.p, tf, ((size_t)ctx->nar.n_tiles + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
   cudaStream_t st = ctx->stream;
   CU(cudaEventRecord(ctx->ev_h2d[0], st));
   if (b->n_words) CU(cudaMemcpyAsync(ctx->d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, st));
@@ -567,12 +596,29 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
 namespace {
 
 template <typename KeyT>
-int hist_width(pf_ctx* ctx, WidthState& w) {
+int hist_width(pf_ctx* ctx, WidthState& w, bool fused = false) {
   if (w.n_records == 0) return PF_OK;
   cudaStream_t st = ctx->stream;
   const int shift0 = KeyTraits<KeyT>::kBits - w.sort_bits;
   const uint32_t n_seg = ctx->n_clusters;
   CU(cudaMemsetAsync(w.seg_hist.p, 0, (size_t)n_seg * w.passes * kRadix * 4, st));
+  if (fused) {
+    const uint32_t chunks = cdiv(ctx->n_seqs, kHistSeqsPerChunk);
+    const uint32_t grid = std::min<uint32_t>(cdiv(chunks, kK1Warps), 148 * 8);
+    if (ctx->prm.canonical)
+      k1_histogram_fused<true><<<grid, kK1Warps * 32, 0, st>>>(
+          ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seqs.as<SeqDev>(), ctx->n_seqs,
+          (int)ctx->prm.k, w.passes, shift0, w.seg_hist.as<uint32_t>());
+    else
+      k1_histogram_fused<false><<<grid, kK1Warps * 32, 0, st>>>(
+          ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seqs.as<SeqDev>(), ctx->n_seqs,
+          (int)ctx->prm.k, w.passes, shift0, w.seg_hist.as<uint32_t>());
+    const uint32_t rows = n_seg * w.passes;
+    k2_scan_histogram<<<cdiv(rows, 8), 256, 0, st>>>(w.seg_hist.as<uint32_t>(), w.seg_start.as<uint32_t>(), rows, w.passes);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    return PF_OK;
+  }
   const uint32_t hist_ctas = std::min<uint32_t>(w.n_tiles, 148 * 8);
   const uint32_t per = cdiv(w.n_tiles, hist_ctas);
   k2_histogram<KeyT><<<cdiv(w.n_tiles, per), 256, 0, st>>>(w.keys[0].as<KeyT>(), w.tiles.as<TileDev>(),
@@ -586,7 +632,7 @@ int hist_width(pf_ctx* ctx, WidthState& w) {
 }
 
 template <typename KeyT>
-int passes_width(pf_ctx* ctx, WidthState& w, int ticket_idx, bool unstable = false) {
+int passes_width(pf_ctx* ctx, WidthState& w, int ticket_idx, bool unstable = false, bool fused = false) {
   if (w.n_records == 0) { w.final_buf = 0; return PF_OK; }
   cudaStream_t st = ctx->stream;
   const int shift0 = KeyTraits<KeyT>::kBits - w.sort_bits;
@@ -595,7 +641,22 @@ int passes_width(pf_ctx* ctx, WidthState& w, int ticket_idx, bool unstable = fal
   for (int p = 0; p < w.passes; ++p) {
     CU(cudaMemsetAsync(w.lookback.p, 0, (size_t)w.n_tiles * kRadix * 4, st));
     CU(cudaMemsetAsync(counters + ticket_idx, 0, 4, st));
-    if (unstable && p == 0)   // LSD: only the first pass may ignore the incoming order
+    if (fused && p == 0) {
+      if (ctx->prm.canonical)
+        k2_extract_scatter<true><<<w.n_tiles, kSortThreads, sizeof(ScatterSmem<uint64_t>), st>>>(
+            ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seqs.as<SeqDev>(),
+            ctx->d_seq_rec_off.as<uint32_t>(), ctx->n_seqs, ctx->d_tile_first_seq.as<uint32_t>(), (int)ctx->prm.k,
+            w.keys[src ^ 1].template as<uint64_t>(), w.vals[src ^ 1].template as<uint32_t>(), w.tiles.template as<TileDev>(),
+            w.n_tiles, w.seg_hist.template as<uint32_t>(), w.passes, shift0, w.lookback.template as<uint32_t>(),
+            counters + ticket_idx, counters + C_ERR);
+      else
+        k2_extract_scatter<false><<<w.n_tiles, kSortThreads, sizeof(ScatterSmem<uint64_t>), st>>>(
+            ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seqs.as<SeqDev>(),
+            ctx->d_seq_rec_off.as<uint32_t>(), ctx->n_seqs, ctx->d_tile_first_seq.as<uint32_t>(), (int)ctx->prm.k,
+            w.keys[src ^ 1].template as<uint64_t>(), w.vals[src ^ 1].template as<uint32_t>(), w.tiles.template as<TileDev>(),
+            w.n_tiles, w.seg_hist.template as<uint32_t>(), w.passes, shift0, w.lookback.template as<uint32_t>(),
+            counters + ticket_idx, counters + C_ERR);
+    } else if (unstable && p == 0)   // LSD: only the first pass may ignore the incoming order
       k2_scatter_pass<KeyT><<<w.n_tiles, kSortThreads, sizeof(ScatterSmem<KeyT>), st>>>(
           w.keys[src].as<KeyT>(), w.vals[src].as<uint32_t>(), w.keys[src ^ 1].as<KeyT>(),
           w.vals[src ^ 1].as<uint32_t>(), w.tiles.as<TileDev>(), w.n_tiles, w.seg_hist.as<uint32_t>(), p,
@@ -772,16 +833,15 @@ int launch_k1(pf_ctx* ctx) {
   WidthState& Wd = ctx->wid;
   PosOut po{ctx->d_pos_kmer.as<uint64_t>(), ctx->d_pos_seq.as<uint32_t>(), ctx->d_pos_cstart.as<int32_t>(),
             ctx->d_pos_gstart.as<int32_t>(), ctx->d_pos_flags.as<uint8_t>()};
-  if (ctx->n_seqs && N.n_records) {
+  if (ctx->n_seqs && N.n_records && !(ctx->fused && ctx->n_pos == 0)) {
     const uint32_t grid = std::min<uint32_t>(cdiv(ctx->n_seqs, kK1Warps), 148 * 8);
-    if (P.canonical)
-      k1_extract<true><<<grid, kK1Warps * 32, 0, st>>>(ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(),
-                                                      ctx->d_seqs.as<SeqDev>(), ctx->n_seqs, (int)P.k,
-                                                      N.keys[0].as<uint64_t>(), N.vals[0].as<uint32_t>(), po);
-    else
-      k1_extract<false><<<grid, kK1Warps * 32, 0, st>>>(ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(),
-                                                       ctx->d_seqs.as<SeqDev>(), ctx->n_seqs, (int)P.k,
-                                                       N.keys[0].as<uint64_t>(), N.vals[0].as<uint32_t>(), po);
+#define PF_K1(CANON, REC)                                                                              \
+    k1_extract<CANON, REC><<<grid, kK1Warps * 32, 0, st>>>(ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), \
+                                                      ctx->d_seqs.as<SeqDev>(), ctx->n_seqs, (int)P.k,  \
+                                                      N.keys[0].as<uint64_t>(), N.vals[0].as<uint32_t>(), po)
+    if (ctx->fused) { if (P.canonical) PF_K1(true, false); else PF_K1(false, false); }
+    else { if (P.canonical) PF_K1(true, true); else PF_K1(false, true); }
+#undef PF_K1
     ctx->launches++;
   }
   if (ctx->n_wide_seqs && Wd.n_records) {
@@ -906,16 +966,16 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   ro.cluster_pattern = ctx->d_cl_pattern.as<uint32_t>();
 
   for (int attempt = 0;; ++attempt) {
-    // ---- K1 -------------------------------------------------------------------
+    // ---- K1 + K2 -------------------------------------------------------------
+    ctx->fused = part && ctx->use_direct && N.passes <= 2 && !(ctx->prm.debug_flags & 1u);
     TRY(launch_k1(ctx));
     STAGE("k1_extract");
     CU(cudaEventRecord(ctx->ev[EV_EXTRACT], st));
-    // ---- K2 -------------------------------------------------------------------
-    TRY(hist_width<uint64_t>(ctx, N));
+    TRY(hist_width<uint64_t>(ctx, N, ctx->fused));
     TRY(hist_width<Key128>(ctx, Wd));
     STAGE("k2_histogram");
     CU(cudaEventRecord(ctx->ev[EV_HIST], st));
-    TRY(passes_width<uint64_t>(ctx, N, C_TICKET_N, part && ctx->use_direct));
+    TRY(passes_width<uint64_t>(ctx, N, C_TICKET_N, part && ctx->use_direct, ctx->fused));
     TRY(passes_width<Key128>(ctx, Wd, C_TICKET_W));
     STAGE("k2_onesweep_pass");
     CU(cudaEventRecord(ctx->ev[EV_SORT], st));
@@ -1291,7 +1351,7 @@ x_classify(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
     }
 #pragma unroll
     for (int m = 16; m >= 1; m >>= 1) h += __shfl_xor_sync(kFull, h, m);
-    h = mix64(h);
+    h = fmix64(h);
     if (lane == 0) {
       const uint32_t o = (uint32_t)((h >> 32) % world);
       owner[e] = o;

@@ -9,7 +9,7 @@ constexpr uint32_t kInvalidSample = 0xffffffffu;  // record of a window that bel
 constexpr int kWarp = 32;
 constexpr uint32_t kFull = 0xffffffffu;
 
-// ---- bijective 64-bit mixer (murmur3 finaliser) and its inverse ----------
+// ---- bijective 64-bit mixers and their inverses -----------------------------
 // The radix sort orders only the leading `sort_bits` of mix(kmer); mixing makes
 // those bits a uniform hash of the whole k-mer, so near-identical k-mers (SNP
 // neighbours) do not share a prefix.  K3 resolves the rare shared prefix
@@ -25,13 +25,24 @@ constexpr uint64_t kInvA = inv_odd(kMulA);
 constexpr uint64_t kInvB = inv_odd(kMulB);
 static_assert(kMulA * kInvA == 1ULL && kMulB * kInvB == 1ULL, "inverse");
 
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+// full-strength mixer (murmur3 finaliser): pattern hashing, synthetic data, wide keys
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t x) {
   x ^= x >> 33; x *= kMulA; x ^= x >> 33; x *= kMulB; x ^= x >> 33;
   return x;
 }
+// k-mer key mixer on the hot path: one odd multiply (every bit of the k-mer reaches
+// the leading digits) and one xor-shift (the leading half reaches the low bits the
+// shared-memory tables index with).  Bijective; exactness never depends on its quality.
+constexpr uint64_t kMulK = 0x9e3779b97f4a7c15ULL;
+constexpr uint64_t kInvK = inv_odd(kMulK);
+static_assert(kMulK * kInvK == 1ULL, "inverse");
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x *= kMulK;
+  return x ^ (x >> 32);
+}
 __host__ __device__ __forceinline__ uint64_t unmix64(uint64_t x) {
-  x ^= x >> 33; x *= kInvB; x ^= x >> 33; x *= kInvA; x ^= x >> 33;
-  return x;
+  x ^= x >> 32;
+  return x * kInvK;
 }
 
 // 128-bit key for windows holding N/IUPAC symbols (4 bits per symbol, k <= 32).
@@ -50,15 +61,15 @@ __host__ __device__ __forceinline__ bool operator<(const Key128& a, const Key128
 // Feistel-free bijection on 128 bits: mix each half with the other (invertible
 // step by step), enough to make the leading bits a hash of all 128.
 __host__ __device__ __forceinline__ Key128 mix128(Key128 k) {
-  k.hi ^= mix64(k.lo + 0x9e3779b97f4a7c15ULL);
-  k.lo ^= mix64(k.hi + 0xd1b54a32d192ed03ULL);
-  k.hi ^= mix64(k.lo + 0x8cb92ba72f3d8dd7ULL);
+  k.hi ^= fmix64(k.lo + 0x9e3779b97f4a7c15ULL);
+  k.lo ^= fmix64(k.hi + 0xd1b54a32d192ed03ULL);
+  k.hi ^= fmix64(k.lo + 0x8cb92ba72f3d8dd7ULL);
   return k;
 }
 __host__ __device__ __forceinline__ Key128 unmix128(Key128 k) {
-  k.hi ^= mix64(k.lo + 0x8cb92ba72f3d8dd7ULL);
-  k.lo ^= mix64(k.hi + 0xd1b54a32d192ed03ULL);
-  k.hi ^= mix64(k.lo + 0x9e3779b97f4a7c15ULL);
+  k.hi ^= fmix64(k.lo + 0x8cb92ba72f3d8dd7ULL);
+  k.lo ^= fmix64(k.hi + 0xd1b54a32d192ed03ULL);
+  k.hi ^= fmix64(k.lo + 0x9e3779b97f4a7c15ULL);
   return k;
 }
 
@@ -120,7 +131,7 @@ __device__ __forceinline__ uint32_t lanemask_lt() { return (1u << lane_id()) - 1
 // ---- hash of a pattern key (W words); commutative over words so a warp can
 // reduce it in any order.  Same function picks the owner rank in the exchange.
 __host__ __device__ __forceinline__ uint64_t word_hash(uint32_t w, uint32_t i) {
-  return mix64(((uint64_t)w << 32 | (uint64_t)(i + 1u)) * 0x9e3779b97f4a7c15ULL + 0x632be59bd9b4e019ULL);
+  return fmix64(((uint64_t)w << 32 | (uint64_t)(i + 1u)) * 0x9e3779b97f4a7c15ULL + 0x632be59bd9b4e019ULL);
 }
 
 // ---- device-side descriptors (built on the host in pf_upload) -------------

@@ -9,9 +9,9 @@ namespace pf {
 __host__ __device__ __forceinline__ uint64_t synth_hash(uint64_t seed, uint64_t a, uint64_t b,
                                                         uint64_t c, uint64_t tag) {
   uint64_t h = seed ^ (tag * 0x9e3779b97f4a7c15ULL);
-  h = mix64(h + a * 0xd6e8feb86659fd93ULL);
-  h = mix64(h + b * 0xca5a826395121157ULL);
-  h = mix64(h + c * 0x2545f4914f6cdd1dULL);
+  h = fmix64(h + a * 0xd6e8feb86659fd93ULL);
+  h = fmix64(h + b * 0xca5a826395121157ULL);
+  h = fmix64(h + c * 0x2545f4914f6cdd1dULL);
   return h;
 }
 

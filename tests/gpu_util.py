@@ -9,12 +9,12 @@ _COMP = str.maketrans("ACTGNYRWSKMDVHBX", "TGACNRYWSMKHBDVX")
 
 def run_gpu(items, stroi, S, k, canonical=True, consider_missing=False,
             cluster_equal_filter=False, maf=0.01, batch_clusters=3,
-            sort_bits=0, mode=0):
+            sort_bits=0, mode=0, debug_flags=0):
     """items: list of (cluster dict, idx, presab).  Returns a dict shaped like
     oracle_c.run()'s, plus the positional arrays the kernels computed."""
     ctx = capi.Context(k, S, canonical, consider_missing, cluster_equal_filter,
                        emit_positions=bool(stroi), maf=maf, sort_bits=sort_bits,
-                       mode=mode)
+                       mode=mode, debug_flags=debug_flags)
     res = {"row_cluster": [], "row_kmer": [], "row_count": [], "row_pattern": [],
            "cluster_pattern": [], "kp": [], "cp": [], "pos": [], "ids": [],
            "seq_meta": [], "seqs": [], "seq_cluster_idx": []}

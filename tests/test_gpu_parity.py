@@ -125,6 +125,16 @@ def test_random_clusters_match_oracle(case, engine):
                          batch_clusters=bc, sort_bits=sb, mode=engine)
 
 
+@pytest.mark.parametrize("case", CASES[:6], ids=[str(i) for i in range(6)])
+def test_unfused_partition_path(case):
+    """debug_flags=1: K1 writes records, separate histogram and first pass."""
+    S, k, nc, L, canon, cm, nf, maf, amb, sb, bc = case
+    rng = np.random.default_rng(1000 + S * 7 + k)
+    items, stroi = _random_items(rng, S, k, nc, L, amb)
+    _compare_with_oracle(items, stroi, S, k, canon, cm, nf, maf,
+                         batch_clusters=bc, sort_bits=sb, mode=0, debug_flags=1)
+
+
 def test_partition_direct_rescue_launch():
     """Tiles with more distinct k-mers than the direct variant holds (768) are
     re-run one prefix-run per CTA; result must stay exact with one sorted byte."""
