@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -434,56 +435,108 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
   uint32_t* hw = ctx->h_wide_seqs.as<uint32_t>();
 
   const uint32_t mult = P.canonical ? 1u : 2u;
+  // the packed plane is the bulk of the transfer: start it before the host-side planning
+  const size_t slack_words = 80;
+  TRY(dev_ensure(ctx, ctx->d_bases, (b->n_words + slack_words) * 8));
+  CU(cudaEventRecord(ctx->ev_h2d[0], ctx->stream));
+  if (b->n_words) CU(cudaMemcpyAsync(ctx->d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync((char*)ctx->d_bases.p + b->n_words * 8, 0, slack_words * 8, ctx->stream));
+
+  // ---- planning, in parallel over chunks of sequences --------------------------------
+  // phase A: validate + per-sequence sizes, per-chunk sums; phase B: prefix over chunks;
+  // phase C: offsets.  Cluster ranges come from the first sequence of every cluster.
   uint64_t rec = 0, wrec = 0, pos = 0, pwide = 0, bases = 0;
   uint32_t n_wide = 0;
   std::vector<std::pair<uint32_t, uint32_t>> nr(b->n_clusters), wr(b->n_clusters);
-  for (uint32_t c = 0; c < b->n_clusters; ++c) { nr[c] = {0u, 0u}; wr[c] = {0u, 0u}; }
-  uint32_t cur = 0;
-  bool opened = false;
-  uint32_t prev_sample = 0;
-  auto open_cluster = [&](uint32_t c) { nr[c].first = (uint32_t)rec; wr[c].first = (uint32_t)wrec; };
-  auto close_cluster = [&](uint32_t c) { nr[c].second = (uint32_t)rec; wr[c].second = (uint32_t)wrec; };
-  if (b->n_clusters) { open_cluster(0); opened = true; }
-  for (uint32_t i = 0; i < b->n_seqs; ++i) {
-    const pf_seq_desc& q = b->seqs[i];
-    if (q.cluster >= b->n_clusters) return fail(ctx, PF_ERR_INVALID, "seq %u: cluster %u out of range", i, q.cluster);
-    if (q.cluster < cur) return fail(ctx, PF_ERR_INVALID, "seq %u: clusters must be non-decreasing", i);
-    while (cur < q.cluster) { close_cluster(cur); ++cur; open_cluster(cur); prev_sample = 0; }
-    if (q.sample >= S) return fail(ctx, PF_ERR_INVALID, "seq %u: sample rank %u >= n_samples %u", i, q.sample, S);
-    if (q.sample < prev_sample)
-      return fail(ctx, PF_ERR_INVALID, "seq %u: sample ranks must be non-decreasing inside a cluster", i);
-    prev_sample = q.sample;
-    if (!((b->cluster_presence[(size_t)q.cluster * W + (q.sample >> 5)] >> (q.sample & 31)) & 1u))
-      return fail(ctx, PF_ERR_INVALID, "seq %u: sample %u is not marked present in cluster %u", i, q.sample, q.cluster);
-    if (q.base_off & 63u) return fail(ctx, PF_ERR_INVALID, "seq %u: base_off must be a multiple of 64", i);
-    if (q.base_off + q.len > b->n_words * 32ull)
-      return fail(ctx, PF_ERR_INVALID, "seq %u: bases run past the packed plane", i);
-    if (q.strand != 1 && q.strand != -1) return fail(ctx, PF_ERR_INVALID, "seq %u: strand must be +1/-1", i);
-    const bool amb = (q.flags & PF_SEQ_AMBIGUOUS) != 0;
-    if (amb) {
-      if (!b->amb_codes) return fail(ctx, PF_ERR_INVALID, "seq %u is ambiguous but amb_codes is NULL", i);
-      if (q.amb_off & 31u) return fail(ctx, PF_ERR_INVALID, "seq %u: amb_off must be a multiple of 32", i);
-      if (q.amb_off + q.len > b->n_amb_words * 16ull)
-        return fail(ctx, PF_ERR_INVALID, "seq %u: symbols run past the 4-bit plane", i);
+  {
+    const uint32_t n = b->n_seqs;
+    const uint32_t n_thr = std::max(1u, std::min<uint32_t>(std::min(16u, std::thread::hardware_concurrency()),
+                                                           (n + 65535u) / 65536u));
+    struct Part { uint64_t rec = 0, wrec = 0, pos = 0, pwide = 0, bases = 0; uint32_t wide = 0; std::string err; };
+    std::vector<Part> parts(n_thr);
+    const uint32_t per = (n + n_thr - 1) / std::max(1u, n_thr);
+    auto run = [&](auto&& fn) {
+      if (n_thr == 1) { fn(0u); return; }
+      std::vector<std::thread> th;
+      for (uint32_t t = 0; t < n_thr; ++t) th.emplace_back(fn, t);
+      for (auto& x : th) x.join();
+    };
+    auto errf = [](Part& p, const char* fmt, uint32_t i, uint32_t a2 = 0, uint32_t a3 = 0) {
+      char buf[256];
+      snprintf(buf, sizeof buf, fmt, i, a2, a3);
+      p.err = buf;
+    };
+    run([&](uint32_t t) {
+      Part& p = parts[t];
+      const uint32_t i0 = std::min(n, t * per), i1 = std::min(n, i0 + per);
+      for (uint32_t i = i0; i < i1; ++i) {
+        const pf_seq_desc& q = b->seqs[i];
+        if (q.cluster >= b->n_clusters) return errf(p, "seq %u: cluster %u out of range", i, q.cluster);
+        if (i && q.cluster < b->seqs[i - 1].cluster) return errf(p, "seq %u: clusters must be non-decreasing", i);
+        if (q.sample >= S) return errf(p, "seq %u: sample rank %u >= n_samples %u", i, q.sample, S);
+        if (i && q.cluster == b->seqs[i - 1].cluster && q.sample < b->seqs[i - 1].sample)
+          return errf(p, "seq %u: sample ranks must be non-decreasing inside a cluster", i);
+        if (!((b->cluster_presence[(size_t)q.cluster * W + (q.sample >> 5)] >> (q.sample & 31)) & 1u))
+          return errf(p, "seq %u: sample %u is not marked present in cluster %u", i, q.sample, q.cluster);
+        if (q.base_off & 63u) return errf(p, "seq %u: base_off must be a multiple of 64", i);
+        if (q.base_off + q.len > b->n_words * 32ull) return errf(p, "seq %u: bases run past the packed plane", i);
+        if (q.strand != 1 && q.strand != -1) return errf(p, "seq %u: strand must be +1/-1", i);
+        const bool amb = (q.flags & PF_SEQ_AMBIGUOUS) != 0;
+        if (amb) {
+          if (!b->amb_codes) return errf(p, "seq %u is ambiguous but amb_codes is NULL", i);
+          if (q.amb_off & 31u) return errf(p, "seq %u: amb_off must be a multiple of 32", i);
+          if (q.amb_off + q.len > b->n_amb_words * 16ull) return errf(p, "seq %u: symbols run past the 4-bit plane", i);
+        }
+        const bool target = P.emit_positions && (q.flags & PF_SEQ_TARGET);
+        const uint32_t nwin = q.len >= k ? q.len - k + 1 : 0;
+        p.rec += (uint64_t)nwin * mult;
+        if (target) p.pos += nwin;
+        if (amb) { p.wrec += (uint64_t)nwin * mult; p.wide++; if (target) p.pwide += nwin; }
+        p.bases += q.len;
+      }
+    });
+    for (auto& p : parts) if (!p.err.empty()) return fail(ctx, PF_ERR_INVALID, "%s", p.err.c_str());
+    std::vector<Part> base(n_thr);
+    for (uint32_t t = 0; t < n_thr; ++t) {
+      base[t].rec = rec; base[t].wrec = wrec; base[t].pos = pos; base[t].pwide = pwide; base[t].wide = n_wide;
+      rec += parts[t].rec; wrec += parts[t].wrec; pos += parts[t].pos; pwide += parts[t].pwide;
+      n_wide += parts[t].wide; bases += parts[t].bases;
     }
-    const bool target = P.emit_positions && (q.flags & PF_SEQ_TARGET);
-    const uint32_t nwin = q.len >= k ? q.len - k + 1 : 0;
-    SeqDev& d = hs[i];
-    d.base_off = q.base_off; d.amb_off = amb ? q.amb_off : 0; d.len = q.len; d.sample = q.sample;
-    d.cluster = q.cluster; d.flags = (target ? 1u : 0u) | (amb ? 2u : 0u);
-    d.start = q.start; d.end = q.end; d.offset = q.offset; d.strand = q.strand;
-    d.rec_off = (uint32_t)rec; d.pos_off = (uint32_t)pos; d.wrec_off = (uint32_t)wrec;
-    d.pwide_off = (uint32_t)pwide;
-    rec += (uint64_t)nwin * mult;
-    if (target) pos += nwin;
-    if (amb) { wrec += (uint64_t)nwin * mult; hw[n_wide++] = i; if (target) pwide += nwin; }
-    bases += q.len;
     if (rec >= (1ull << 32) - kSortTile || wrec >= (1ull << 32) - kSortTile)
       return fail(ctx, PF_ERR_INVALID, "batch holds more than 2^32 k-mer records; split it");
-  }
-  if (opened) {
-    while (cur + 1 < b->n_clusters) { close_cluster(cur); ++cur; open_cluster(cur); }
-    close_cluster(cur);
+    if (pos >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "more than 2^32 positional records; split the batch");
+    constexpr uint32_t kUnset = 0xffffffffu;
+    for (uint32_t c = 0; c < b->n_clusters; ++c) { nr[c] = {kUnset, kUnset}; wr[c] = {kUnset, kUnset}; }
+    run([&](uint32_t t) {
+      Part o = base[t];
+      const uint32_t i0 = std::min(n, t * per), i1 = std::min(n, i0 + per);
+      for (uint32_t i = i0; i < i1; ++i) {
+        const pf_seq_desc& q = b->seqs[i];
+        const bool amb = (q.flags & PF_SEQ_AMBIGUOUS) != 0;
+        const bool target = P.emit_positions && (q.flags & PF_SEQ_TARGET);
+        const uint32_t nwin = q.len >= k ? q.len - k + 1 : 0;
+        if (i == 0 || q.cluster != b->seqs[i - 1].cluster) {     // first sequence of its cluster
+          nr[q.cluster].first = (uint32_t)o.rec;
+          wr[q.cluster].first = (uint32_t)o.wrec;
+        }
+        SeqDev& d = hs[i];
+        d.base_off = q.base_off; d.amb_off = amb ? q.amb_off : 0; d.len = q.len; d.sample = q.sample;
+        d.cluster = q.cluster; d.flags = (target ? 1u : 0u) | (amb ? 2u : 0u);
+        d.start = q.start; d.end = q.end; d.offset = q.offset; d.strand = q.strand;
+        d.rec_off = (uint32_t)o.rec; d.pos_off = (uint32_t)o.pos; d.wrec_off = (uint32_t)o.wrec;
+        d.pwide_off = (uint32_t)o.pwide;
+        o.rec += (uint64_t)nwin * mult;
+        if (target) o.pos += nwin;
+        if (amb) { o.wrec += (uint64_t)nwin * mult; hw[o.wide++] = i; if (target) o.pwide += nwin; }
+      }
+    });
+    // clusters without sequences are empty ranges at the start of the next non-empty one
+    uint32_t next_n = (uint32_t)rec, next_w = (uint32_t)wrec;
+    for (uint32_t c = b->n_clusters; c-- > 0;) {
+      if (nr[c].first == kUnset) { nr[c].first = next_n; wr[c].first = next_w; }
+      nr[c].second = next_n; wr[c].second = next_w;
+      next_n = nr[c].first; next_w = wr[c].first;
+    }
   }
   for (uint32_t c = 0; c < b->n_clusters; ++c) {
     uint32_t np = 0;
@@ -520,13 +573,10 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
   ctx->n_words = b->n_words; ctx->n_amb_words = n_wide ? b->n_amb_words : 0; ctx->n_bases = bases;
   ctx->n_pos = (uint32_t)pos; ctx->n_pos_wide = (uint32_t)pwide;
   ctx->nar.n_records = (uint32_t)rec; ctx->wid.n_records = (uint32_t)wrec;
-  if (pos >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "more than 2^32 positional records; split the batch");
   TRY(plan_tiles(ctx, ctx->nar, nr, true));
   TRY(plan_tiles(ctx, ctx->wid, wr, false));
 
   // ---- device buffers + H2D ------------------------------------------------
-  const size_t slack_words = 80;
-  TRY(dev_ensure(ctx, ctx->d_bases, (b->n_words + slack_words) * 8));
   TRY(dev_ensure(ctx, ctx->d_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(SeqDev)));
   TRY(dev_ensure(ctx, ctx->d_clusters, std::max<size_t>(1, b->n_clusters) * sizeof(ClusterDev)));
   TRY(dev_ensure(ctx, ctx->d_presence, std::max<size_t>(1, (size_t)b->n_clusters * W) * 4));
@@ -561,9 +611,6 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
     CU(cudaMemcpyAsync(ctx->d_tile_first_seq.p, tf, ((size_t)ctx->nar.n_tiles + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
   }
   cudaStream_t st = ctx->stream;
-  CU(cudaEventRecord(ctx->ev_h2d[0], st));
-  if (b->n_words) CU(cudaMemcpyAsync(ctx->d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemsetAsync((char*)ctx->d_bases.p + b->n_words * 8, 0, slack_words * 8, st));
   if (b->n_seqs) CU(cudaMemcpyAsync(ctx->d_seqs.p, hs, b->n_seqs * sizeof(SeqDev), cudaMemcpyHostToDevice, st));
   if (b->n_clusters) {
     CU(cudaMemcpyAsync(ctx->d_clusters.p, hc, b->n_clusters * sizeof(ClusterDev), cudaMemcpyHostToDevice, st));
