@@ -286,11 +286,16 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    exch_ms = {}
+
     def step_resident():
         ctx.reset_patterns()
         ctx.execute()
         if exch is not None:
-            exch.run()
+            out = exch.run()
+            for ns in ("cluster", "kmer"):
+                for k_, v_ in out[ns]["ms"].items():
+                    exch_ms[ns + "_" + k_] = v_
 
     # ---- value: batch resident in HBM -------------------------------------
     ctx.upload(hb)
@@ -321,12 +326,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    value = world * n_bases / (ms_step * 1e-3)
+    total_bases = n_bases
+    if world > 1:
+        t = torch.tensor([n_bases], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        total_bases = int(t.item())
+    value = total_bases / (ms_step * 1e-3)
     # sizes of one step: read from a collect of the last execution
     ctx.collect(copy=False)
     st = ctx.stats()
     M = st["instances"]             # exactly one collected batch so far
     U = st["unique_kmers"]
+    U_total = U
+    if world > 1:
+        t = torch.tensor([U], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        U_total = int(t.item())
     rows = st["rows"]
     passes = st["sort_passes"]
     for key in stage_ms:
@@ -357,7 +372,7 @@ def main():
             dt = float(t.item())
         h2d = (hb.packed.nbytes + len(hb.seqs) * 64 + len(hb.clusters) * 32 + hb.presence.nbytes
                + (M // 4096 + len(hb.clusters)) * 16)
-        e2e = {"value": world * n_bases * args.steps / dt, "unit": "bases/s",
+        e2e = {"value": total_bases * args.steps / dt, "unit": "bases/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * dt / args.steps}
 
@@ -403,7 +418,7 @@ def main():
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": workload_config(args),
-            "unique_kmers_per_s": world * U / (ms_step * 1e-3),
+            "unique_kmers_per_s": U_total / (ms_step * 1e-3),
             "bases_per_step_per_gpu": n_bases, "kmer_instances_per_step_per_gpu": M,
             "unique_kmers_per_step_per_gpu": U, "rows_per_step_per_gpu": rows,
             "patterns_per_gpu": st["kmer_patterns"],
@@ -417,6 +432,8 @@ def main():
             "end_to_end_alg_bytes_per_base_declared": sum(alg.values()) / n_bases,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         }
+        if exch_ms:
+            line["exchange_ms_last_step_rank0"] = {k_: round(v_, 3) for k_, v_ in exch_ms.items()}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_c(hb, S, k, args.maf, args.consider_missing,
                                                   args.cpu_seconds)

@@ -217,7 +217,7 @@ typedef struct pf_synth_params {
   uint32_t n_founders;       /* 8                                                   */
   float    founder_div;      /* 0.01                                                */
   float    private_div;      /* 0.001                                               */
-  float    core_fraction;    /* 0.6: first fraction of clusters present w.p. 0.99   */
+  float    core_fraction;    /* 0.6: probability that a cluster is core (present w.p. 0.99) */
   float    paralog_rate;     /* 0.01                                                */
   uint32_t total_clusters;   /* C of the whole pangenome (core/accessory split)     */
   uint32_t all_targets;      /* 1: flag every sequence PF_SEQ_TARGET                */

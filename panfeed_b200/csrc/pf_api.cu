@@ -46,7 +46,7 @@ struct PatternSpace {
   DevBuf table;           // table_size x u32
   uint32_t table_size = 0;
   // exchange state
-  DevBuf x_owner, x_pos, x_perm, x_counts, x_unique;
+  DevBuf x_owner, x_pos, x_perm, x_counts, x_unique, x_table, x_rep, x_slot, x_winner;
   uint64_t x_n_unique = 0;
 };
 
@@ -313,7 +313,8 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
     fp(w->h_tiles); fp(w->h_seg_start); fp(w->h_ltiles);
   }
   for (PatternSpace* s : {&ctx->kp, &ctx->cp})
-    for (DevBuf* b : {&s->pool, &s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique})
+    for (DevBuf* b : {&s->pool, &s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique,
+                      &s->x_table, &s->x_rep, &s->x_slot, &s->x_winner})
       fd(*b);
   for (PinBuf* b : {&ctx->h_seqs, &ctx->h_clusters, &ctx->h_wide_seqs, &ctx->h_counters,
                     &ctx->h_seq_rec_off, &ctx->h_tile_first_seq,
@@ -1298,9 +1299,10 @@ inline uint64_t thr64(double p) {
   return (uint64_t)(p * 18446744073709551616.0);
 }
 inline SynthCell synth_cell(const pf_synth_params* p, uint32_t gc, uint32_t s) {
-  const uint32_t n_core = (uint32_t)((double)p->total_clusters * p->core_fraction);
+  // core / accessory is a per-cluster coin flip (core_fraction), so any shard of the
+  // pangenome has the same mix
   double pc = 0.99;
-  if (gc >= n_core) {
+  if (synth_hash(p->seed, gc, 0, 0, kTagCore) >= thr64(p->core_fraction)) {
     const uint64_t h = synth_hash(p->seed, gc, 0, 0, kTagAccessoryP);
     pc = 0.05 + 0.90 * ((double)(h >> 11) / 9007199254740992.0);
   }
@@ -1506,7 +1508,10 @@ extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint3
   const uint32_t n = (uint32_t)n_recv;
   uint32_t size = 1024;
   while (size < 2ull * n + 16) size *= 2;
-  DevBuf table, rep, slot_of, winner;
+  DevBuf& table = s.x_table;          // scratch kept across calls: no cudaMalloc in the steady state
+  DevBuf& rep = s.x_rep;
+  DevBuf& slot_of = s.x_slot;
+  DevBuf& winner = s.x_winner;
   TRY(dev_ensure(ctx, table, (size_t)size * 4));
   TRY(dev_ensure(ctx, rep, (size_t)n * 4));
   TRY(dev_ensure(ctx, slot_of, (size_t)n * 4));
@@ -1526,7 +1531,6 @@ extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint3
   CU(cudaMemcpyAsync(&total, counters + C_NEW_KP, 4, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
-  for (DevBuf* b : {&table, &rep, &slot_of, &winner}) cudaFree(b->p);
   s.x_n_unique = total;
   *n_unique_host = total;
   return PF_OK;

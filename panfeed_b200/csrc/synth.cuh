@@ -17,7 +17,7 @@ __host__ __device__ __forceinline__ uint64_t synth_hash(uint64_t seed, uint64_t 
 
 enum : uint64_t { kTagAnc = 1, kTagFounderSnp = 2, kTagFounderPick = 3, kTagPrivate = 4,
                   kTagPresence = 5, kTagAccessoryP = 6, kTagParalog = 7, kTagStrand = 8,
-                  kTagStart = 9 };
+                  kTagStart = 9, kTagCore = 10 };
 
 struct SynthSeq {        // one generated sequence
   uint64_t word_off;     // first word in the packed plane

@@ -96,11 +96,14 @@ class PatternExchange:
             else bool(getattr(backend, "consider_missing", False))
 
     def _exchange(self, ns, mask_remap):
+        import time
+        t0 = time.perf_counter()
         be, world, dev = self.backend, self.world, self.device
         kw = be.key_words(ns)
         n_local = be.n_local(ns)
         send = torch.empty((n_local, kw), dtype=torch.int32, device=dev)
         send_counts = be.pack(ns, world, mask_remap, send)
+        t1 = time.perf_counter()
         sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
         rc = torch.empty_like(sc)
         dist.all_to_all_single(rc, sc, group=self.group)
@@ -110,7 +113,11 @@ class PatternExchange:
         dist.all_to_all_single(recv, send, output_split_sizes=recv_counts,
                                input_split_sizes=send_counts, group=self.group)
         uniq_idx = torch.empty(n_recv, dtype=torch.int32, device=dev)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)      # NCCL ran on torch's stream; the library uses its own
+        t2 = time.perf_counter()
         n_unique = be.dedup(ns, recv, uniq_idx)
+        t3 = time.perf_counter()
         nu = torch.tensor([n_unique], dtype=torch.int64, device=dev)
         all_nu = [torch.empty_like(nu) for _ in range(world)]
         dist.all_gather(all_nu, nu, group=self.group)
@@ -121,9 +128,15 @@ class PatternExchange:
         dist.all_to_all_single(returned, uniq_idx, output_split_sizes=send_counts,
                                input_split_sizes=recv_counts, group=self.group)
         l2g = torch.empty(n_local, dtype=torch.int32, device=dev)
+        if dev.type == "cuda":
+            torch.cuda.synchronize(dev)
+        t4 = time.perf_counter()
         be.unpack(ns, returned, l2g)
+        t5 = time.perf_counter()
         return {"local_to_global": l2g, "n_global": sum(counts), "n_owned": n_unique,
-                "owned_base": base, "bytes_sent": int(send.numel() * 4)}
+                "owned_base": base, "bytes_sent": int(send.numel() * 4),
+                "ms": {"pack": (t1 - t0) * 1e3, "a2a_keys": (t2 - t1) * 1e3, "dedup": (t3 - t2) * 1e3,
+                       "a2a_ids": (t4 - t3) * 1e3, "unpack": (t5 - t4) * 1e3}}
 
     def run(self, want_unique=False):
         cl = self._exchange(CLUSTER, None)
