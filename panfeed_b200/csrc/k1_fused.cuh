@@ -142,19 +142,18 @@ k2_extract_scatter(const uint64_t* __restrict__ bases, const uint32_t* __restric
                    uint32_t n_seqs, const uint32_t* __restrict__ tile_first_seq /* [n_tiles+1] */, int k,
                    uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                    const TileDev* __restrict__ tiles, uint32_t n_tiles,
-                   const uint32_t* __restrict__ digit_start, int passes, int shift,
-                   uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket,
-                   uint32_t* __restrict__ err) {
+                   uint32_t* __restrict__ cursors /* copy of the scanned histogram: next free slot of
+                                                     every (segment, digit) bucket */,
+                   int passes, int shift) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem<uint64_t>& sm = *reinterpret_cast<ScatterSmem<uint64_t>*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   constexpr int kWarps = kSortThreads / 32;
   constexpr int kWarpItems = kSortItems * 32;
 
-  if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
   sm.hist[tid] = 0;
   __syncthreads();
-  const uint32_t tile = sm.tile;
+  const uint32_t tile = blockIdx.x;
   if (tile >= n_tiles) return;
   const TileDev td = tiles[tile];
   const uint32_t seq_lo = tile_first_seq[tile];
@@ -238,29 +237,13 @@ k2_extract_scatter(const uint64_t* __restrict__ bases, const uint32_t* __restric
     for (int w = 0; w < kWarps; ++w) woff += (w < (int)warp) ? sm.warp_sums[w] : 0u;
     const uint32_t excl = woff + incl - total;
     sm.excl[tid] = excl;
-    uint32_t* my = lookback + (size_t)tile * kRadix + tid;
-    uint32_t prev = 0;
-    if (tile != td.first_tile) {
-      st_relaxed(my, kFlagAgg | total);
-      uint32_t j = tile, spins = 0;
-      bool failed = false;
-      for (;;) {
-        --j;
-        const uint32_t* p = lookback + (size_t)j * kRadix + tid;
-        uint32_t v = ld_relaxed(p);
-        while ((v & kFlagMask) == 0u) {
-          if (++spins > kSpinLimit) { failed = true; break; }
-          __nanosleep(40);
-          v = ld_relaxed(p);
-        }
-        if (failed) { atomicExch(err, 1u); break; }
-        prev += v & kValMask;
-        if ((v & kFlagMask) == kFlagIncl || j == td.first_tile) break;
-      }
-    }
-    st_relaxed(my, kFlagIncl | ((prev + total) & kValMask));
+    // The bucket sizes are exact (histogram), so space inside a bucket can be handed out
+    // in any order: one global atomicAdd per (tile, digit) replaces the look-back chain.
+    // The order of records inside a bucket is then arbitrary, which the direct local
+    // reduce does not care about.
     const size_t ds = (size_t)td.seg * passes * kRadix + tid;      // pass 0
-    sm.gbase[tid] = digit_start[ds] + prev - excl;
+    const uint32_t first = total ? atomicAdd(&cursors[ds], total) : 0u;
+    sm.gbase[tid] = first - excl;
   }
   __syncthreads();
 #pragma unroll

@@ -238,8 +238,10 @@ k2_onesweep_pass(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ 
 // Unstable variant of the pass, for the direct local reduce (S <= 1024), which
 // ORs sample bits and therefore does not care about the order of records inside
 // a bucket.  The per-warp match/ballot ranking (a 16-deep dependent chain) is
-// replaced by one shared-memory atomicAdd per record on a per-tile histogram:
-// the 16 atomics of a thread are independent, so they pipeline.
+// replaced by one shared-memory atomicAdd per record on a per-tile histogram
+// (the 16 atomics of a thread are independent, so they pipeline), and the
+// decoupled look-back chain by one global atomicAdd per (tile, digit) on a cursor
+// array initialised with the exact bucket starts: tiles no longer wait for each other.
 template <typename KeyT>
 struct ScatterSmem {
   KeyT keys[kSortTile];
@@ -256,19 +258,17 @@ __global__ void __launch_bounds__(kSortThreads, 3)
 k2_scatter_pass(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                 KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                 const TileDev* __restrict__ tiles, uint32_t n_tiles,
-                const uint32_t* __restrict__ digit_start, int pass, int passes, int shift,
-                uint32_t* __restrict__ lookback, uint32_t* __restrict__ ticket,
-                uint32_t* __restrict__ err) {
+                uint32_t* __restrict__ cursors /* copy of the scanned histogram */, int pass, int passes,
+                int shift) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ScatterSmem<KeyT>& sm = *reinterpret_cast<ScatterSmem<KeyT>*>(smem_raw);
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   constexpr int kWarps = kSortThreads / 32;
   constexpr int kWarpItems = kSortItems * 32;
 
-  if (tid == 0) sm.tile = atomicAdd(ticket, 1u);
   sm.hist[tid] = 0;
   __syncthreads();
-  const uint32_t tile = sm.tile;
+  const uint32_t tile = blockIdx.x;
   if (tile >= n_tiles) return;
   const TileDev td = tiles[tile];
 
@@ -309,29 +309,10 @@ k2_scatter_pass(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ v
     for (int w = 0; w < kWarps; ++w) woff += (w < (int)warp) ? sm.warp_sums[w] : 0u;
     const uint32_t excl = woff + incl - total;
     sm.excl[tid] = excl;
-    uint32_t* my = lookback + (size_t)tile * kRadix + tid;
-    uint32_t prev = 0;
-    if (tile != td.first_tile) {
-      st_relaxed(my, kFlagAgg | total);
-      uint32_t j = tile, spins = 0;
-      bool failed = false;
-      for (;;) {
-        --j;
-        const uint32_t* p = lookback + (size_t)j * kRadix + tid;
-        uint32_t v = ld_relaxed(p);
-        while ((v & kFlagMask) == 0u) {
-          if (++spins > kSpinLimit) { failed = true; break; }
-          __nanosleep(40);
-          v = ld_relaxed(p);
-        }
-        if (failed) { atomicExch(err, 1u); break; }
-        prev += v & kValMask;
-        if ((v & kFlagMask) == kFlagIncl || j == td.first_tile) break;
-      }
-    }
-    st_relaxed(my, kFlagIncl | ((prev + total) & kValMask));
+    // exact bucket sizes are known: claim space with one atomicAdd per (tile, digit)
     const size_t ds = ((size_t)td.seg * passes + pass) * kRadix + tid;
-    sm.gbase[tid] = digit_start[ds] + prev - excl;
+    const uint32_t first = total ? atomicAdd(&cursors[ds], total) : 0u;
+    sm.gbase[tid] = first - excl;
   }
   __syncthreads();
 #pragma unroll

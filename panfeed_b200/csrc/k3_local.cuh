@@ -129,10 +129,12 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
       key[j] = 0;
       if (i < b) { key[j] = keys[i]; val[j] = vals[i]; }
     }
+    const int n_items = (int)min((uint32_t)kLocalItems, (b - c0 + kLocalThreads - 1) / kLocalThreads);   // CTA-uniform
     // (i) find or insert
 #pragma unroll
     for (int j = 0; j < kLocalItems; ++j) {
       slot[j] = 0xffff;
+      if (j >= n_items) break;
       if (val[j] == kInvalidSample) continue;
       const uint64_t k = key[j];
       if (k == kEmptyKey) {
@@ -185,6 +187,7 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
     // (iii) one OR per record
 #pragma unroll
     for (int j = 0; j < kLocalItems; ++j) {
+      if (j >= n_items) break;
       if (slot[j] == 0xffff) continue;
       const uint32_t v = val[j];
       atomicOr(&sm.pool[(uint32_t)sm.id[slot[j]] * WS + (v >> 5)], 1u << (v & 31u));

@@ -52,7 +52,7 @@ struct PatternSpace {
 
 struct WidthState {       // per key width (narrow u64 / wide Key128)
   DevBuf keys[2], vals[2];
-  DevBuf tiles, seg_start, seg_hist, lookback;
+  DevBuf tiles, seg_start, seg_hist, lookback, cursors;
   DevBuf ltiles, tile_first_run;     // partition mode: 2048-record tiles of the local reduce
   PinBuf h_tiles, h_seg_start, h_ltiles;
   uint32_t n_tiles = 0, n_ltiles = 0, max_seg = 0;
@@ -308,7 +308,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
     fd(*b);
   for (WidthState* w : {&ctx->nar, &ctx->wid}) {
     for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
-                      &w->seg_hist, &w->lookback, &w->ltiles, &w->tile_first_run})
+                      &w->seg_hist, &w->lookback, &w->cursors, &w->ltiles, &w->tile_first_run})
       fd(*b);
     fp(w->h_tiles); fp(w->h_seg_start); fp(w->h_ltiles);
   }
@@ -687,28 +687,33 @@ int passes_width(pf_ctx* ctx, WidthState& w, int ticket_idx, bool unstable = fal
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
   int src = 0;
   for (int p = 0; p < w.passes; ++p) {
-    CU(cudaMemsetAsync(w.lookback.p, 0, (size_t)w.n_tiles * kRadix * 4, st));
-    CU(cudaMemsetAsync(counters + ticket_idx, 0, 4, st));
+    const bool atomic_pass = (fused || unstable) && p == 0;
+    if (atomic_pass) {
+      const size_t hist_bytes = (size_t)ctx->n_clusters * w.passes * kRadix * 4;
+      TRY(dev_ensure(ctx, w.cursors, std::max<size_t>(hist_bytes, 4)));
+      CU(cudaMemcpyAsync(w.cursors.p, w.seg_hist.p, hist_bytes, cudaMemcpyDeviceToDevice, st));
+    } else {
+      CU(cudaMemsetAsync(w.lookback.p, 0, (size_t)w.n_tiles * kRadix * 4, st));
+      CU(cudaMemsetAsync(counters + ticket_idx, 0, 4, st));
+    }
     if (fused && p == 0) {
       if (ctx->prm.canonical)
         k2_extract_scatter<true><<<w.n_tiles, kSortThreads, sizeof(ScatterSmem<uint64_t>), st>>>(
             ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seqs.as<SeqDev>(),
             ctx->d_seq_rec_off.as<uint32_t>(), ctx->n_seqs, ctx->d_tile_first_seq.as<uint32_t>(), (int)ctx->prm.k,
             w.keys[src ^ 1].template as<uint64_t>(), w.vals[src ^ 1].template as<uint32_t>(), w.tiles.template as<TileDev>(),
-            w.n_tiles, w.seg_hist.template as<uint32_t>(), w.passes, shift0, w.lookback.template as<uint32_t>(),
-            counters + ticket_idx, counters + C_ERR);
+            w.n_tiles, w.cursors.template as<uint32_t>(), w.passes, shift0);
       else
         k2_extract_scatter<false><<<w.n_tiles, kSortThreads, sizeof(ScatterSmem<uint64_t>), st>>>(
             ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seqs.as<SeqDev>(),
             ctx->d_seq_rec_off.as<uint32_t>(), ctx->n_seqs, ctx->d_tile_first_seq.as<uint32_t>(), (int)ctx->prm.k,
             w.keys[src ^ 1].template as<uint64_t>(), w.vals[src ^ 1].template as<uint32_t>(), w.tiles.template as<TileDev>(),
-            w.n_tiles, w.seg_hist.template as<uint32_t>(), w.passes, shift0, w.lookback.template as<uint32_t>(),
-            counters + ticket_idx, counters + C_ERR);
+            w.n_tiles, w.cursors.template as<uint32_t>(), w.passes, shift0);
     } else if (unstable && p == 0)   // LSD: only the first pass may ignore the incoming order
       k2_scatter_pass<KeyT><<<w.n_tiles, kSortThreads, sizeof(ScatterSmem<KeyT>), st>>>(
           w.keys[src].as<KeyT>(), w.vals[src].as<uint32_t>(), w.keys[src ^ 1].as<KeyT>(),
-          w.vals[src ^ 1].as<uint32_t>(), w.tiles.as<TileDev>(), w.n_tiles, w.seg_hist.as<uint32_t>(), p,
-          w.passes, shift0 + 8 * p, w.lookback.as<uint32_t>(), counters + ticket_idx, counters + C_ERR);
+          w.vals[src ^ 1].as<uint32_t>(), w.tiles.as<TileDev>(), w.n_tiles, w.cursors.as<uint32_t>(), p,
+          w.passes, shift0 + 8 * p);
     else
       k2_onesweep_pass<KeyT><<<w.n_tiles, kSortThreads, sizeof(SortSmem<KeyT>), st>>>(
           w.keys[src].as<KeyT>(), w.vals[src].as<uint32_t>(), w.keys[src ^ 1].as<KeyT>(),
