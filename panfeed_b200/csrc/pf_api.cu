@@ -823,16 +823,23 @@ int dedup(pf_ctx* ctx, PatternSpace& s, const uint32_t* cand, uint32_t n, DevBuf
   TRY(dev_ensure(ctx, rep, (size_t)n * 4));
   TRY(dev_ensure(ctx, slot_of, (size_t)n * 4));
   TRY(dev_ensure(ctx, winner, ((size_t)n + 1) * 4));
-  const uint32_t grid = std::min<uint32_t>(cdiv(n, 8), kGridPersist * 2);
-  k4_probe<<<grid, 256, 0, st>>>(cand, n, s.key_words, s.pool.as<uint32_t>(), s.table.as<uint32_t>(),
-                                 s.table_size - 1, rep.as<uint32_t>(), slot_of.as<uint32_t>(),
-                                 winner.as<uint32_t>());
-  ctx->launches++;
-  TRY(scan_inplace(ctx, winner.as<uint32_t>(), n, counters + new_idx));
-  k4_commit<<<grid, 256, 0, st>>>(cand, n, s.key_words, s.pool.as<uint32_t>(), (uint32_t)s.n,
-                                  s.table.as<uint32_t>(), rep.as<uint32_t>(), slot_of.as<uint32_t>(),
-                                  winner.as<uint32_t>(), ids_out);
-  ctx->launches++;
+  // lanes per row: at most 4 words per lane
+  const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
+  const uint32_t grid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
+#define PF_K4(LL)                                                                                      \
+  do {                                                                                                 \
+    k4_probe<LL><<<grid, 256, 0, st>>>(cand, n, s.key_words, s.pool.as<uint32_t>(), s.table.as<uint32_t>(), \
+                                       s.table_size - 1, rep.as<uint32_t>(), slot_of.as<uint32_t>(),   \
+                                       winner.as<uint32_t>());                                         \
+    ctx->launches++;                                                                                   \
+    TRY(scan_inplace(ctx, winner.as<uint32_t>(), n, counters + new_idx));                              \
+    k4_commit<LL><<<grid, 256, 0, st>>>(cand, n, s.key_words, s.pool.as<uint32_t>(), (uint32_t)s.n,     \
+                                        s.table.as<uint32_t>(), rep.as<uint32_t>(), slot_of.as<uint32_t>(), \
+                                        winner.as<uint32_t>(), ids_out);                               \
+    ctx->launches++;                                                                                   \
+  } while (0)
+  if (L == 4) PF_K4(4); else if (L == 8) PF_K4(8); else if (L == 16) PF_K4(16); else PF_K4(32);
+#undef PF_K4
   CU(cudaGetLastError());
   return PF_OK;
 }
@@ -1526,8 +1533,8 @@ extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint3
   uint32_t* counters = ctx->d_counters.p ? ctx->d_counters.as<uint32_t>() : nullptr;
   if (!counters) { TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4)); TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4)); counters = ctx->d_counters.as<uint32_t>(); }
   const uint32_t grid = std::min<uint32_t>(cdiv(n, 8), kGridPersist * 2);
-  k4_probe<<<grid, 256, 0, st>>>(recv_words_dev, n, s.key_words, nullptr, table.as<uint32_t>(), size - 1,
-                                 rep.as<uint32_t>(), slot_of.as<uint32_t>(), winner.as<uint32_t>());
+  k4_probe<32><<<grid, 256, 0, st>>>(recv_words_dev, n, s.key_words, nullptr, table.as<uint32_t>(), size - 1,
+                                     rep.as<uint32_t>(), slot_of.as<uint32_t>(), winner.as<uint32_t>());
   TRY(scan_inplace(ctx, winner.as<uint32_t>(), n, counters + C_NEW_KP));
   x_finish<<<grid, 256, 0, st>>>(recv_words_dev, n, s.key_words, rep.as<uint32_t>(), winner.as<uint32_t>(),
                                  recv_unique_index_dev, s.x_unique.as<uint32_t>());
