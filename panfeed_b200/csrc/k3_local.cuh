@@ -158,18 +158,27 @@ k3_local_direct(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
     }
     __syncthreads();
     // (ii) dense ids for the keys this thread inserted
+    const uint32_t id_first = sm.n_unique;          // read by everyone before anyone adds
+    __syncthreads();
+    if (inserted) {
 #pragma unroll
-    for (int j = 0; j < kLocalItems; ++j) {
-      if (inserted >> j & 1u) {
-        const uint32_t id = atomicAdd(&sm.n_unique, 1u);
-        if (id < max_unique) {
-          sm.id[slot[j]] = (uint16_t)id;
-          sm.slot_of[id] = slot[j];
-          for (uint32_t w = 0; w < W; ++w) sm.pool[id * WS + w] = 0;   // bitsets are zeroed on demand
-        } else {
-          sm.overflow = 1;
+      for (int j = 0; j < kLocalItems; ++j) {
+        if (inserted >> j & 1u) {
+          const uint32_t id = atomicAdd(&sm.n_unique, 1u);
+          if (id < max_unique) {
+            sm.id[slot[j]] = (uint16_t)id;
+            sm.slot_of[id] = slot[j];
+          } else {
+            sm.overflow = 1;
+          }
         }
       }
+    }
+    __syncthreads();
+    // bitsets of the new ids are zeroed on demand, by the whole CTA
+    {
+      const uint32_t id_last = min(sm.n_unique, max_unique);
+      for (uint32_t i = id_first * WS + tid; i < id_last * WS; i += kLocalThreads) sm.pool[i] = 0;
     }
     __syncthreads();
     if (sm.overflow) {
