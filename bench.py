@@ -384,33 +384,51 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        fused = stage_ms["ms_extract"] < 0.2          # K1 ran inside the histogram / first pass
         pass_ms = stage_ms["ms_sort"] / max(1, passes)
-        pass_bytes = 2 * R_BYTES * M
-        achieved = pass_bytes / (pass_ms * 1e-3) / 1e9
-        traffic = None       # dram read+write bytes per launch, scaled from the ncu capture
+        k1_bytes = n_bases / 4 + 32 * len(hb.seqs) + R_BYTES * M
+        pass_bytes = 2 * R_BYTES * M                                       # SURVEY 8(d) one K2 pass
+        tr = {}
         try:
-            per_rec = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-                "k2_onesweep_pass_dram_bytes_per_record")
-            traffic = per_rec * M if per_rec else None
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             pass
-        # whole-path algorithmic bytes per SURVEY.md §8(d), declared 8-pass model
+        if fused:
+            kernel = "k2_extract_scatter<canonical> (K1 extraction fused into the first radix pass)"
+            alg_bytes = k1_bytes + pass_bytes
+            compulsory = n_bases / 4 + R_BYTES * M
+            per_rec = tr.get("k2_extract_scatter_dram_bytes_per_record")
+            note = ("algorithmic = SURVEY 8(d) K1 (N/4 + 32*seqs + R*M) + one declared K2 pass (2*R*M); "
+                    "the fused kernel never writes then re-reads the unsorted records, so its compulsory "
+                    "DRAM traffic is only N/4 + R*M (see traffic / frac_compulsory); it is instruction-bound")
+        else:
+            kernel = "k2_onesweep_pass<u64>"
+            alg_bytes = pass_bytes
+            compulsory = pass_bytes
+            per_rec = tr.get("k2_onesweep_pass_dram_bytes_per_record")
+            note = "one radix pass reads and writes every 12-byte record once (2*R*M)"
+        achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
+        traffic = per_rec * M if per_rec else None     # dram read+write per launch, scaled from the ncu capture
+        # whole-path algorithmic bytes per SURVEY.md 8(d), declared 8-pass model
         alg = {
-            "k1_extract": n_bases / 4 + 32 * len(hb.seqs) + R_BYTES * M,
+            "k1_extract": k1_bytes,
             "k2_sort_declared_8_passes": 8 * M + 8 * 2 * R_BYTES * M,
             "k3_reduce": R_BYTES * M + 12 * U + rows * 4 * ((S + 31) // 32),
         }
+        W4 = 4 * ((S + 31) // 32)
+        k3_ms = stage_ms["ms_mark"] + stage_ms["ms_count"] + stage_ms["ms_reduce"]
         stages = {
-            "k1_extract": {"ms": stage_ms["ms_extract"], "alg_GBps": alg["k1_extract"] / stage_ms["ms_extract"] / 1e6},
-            "k2_histogram": {"ms": stage_ms["ms_hist"], "alg_GBps": 8 * M / max(stage_ms["ms_hist"], 1e-6) / 1e6},
-            "k2_onesweep_passes": {"ms": stage_ms["ms_sort"], "passes": passes,
-                                   "alg_GBps": passes * pass_bytes / stage_ms["ms_sort"] / 1e6,
-                                   "declared_model_GBps": alg["k2_sort_declared_8_passes"] /
-                                   (stage_ms["ms_sort"] + stage_ms["ms_hist"]) / 1e6},
-            "k3_mark_count_emit": {"ms": stage_ms["ms_mark"] + stage_ms["ms_count"] + stage_ms["ms_reduce"],
-                                   "alg_GBps": alg["k3_reduce"] / (stage_ms["ms_mark"] + stage_ms["ms_count"]
-                                                                   + stage_ms["ms_reduce"]) / 1e6},
-            "k4_dedup": {"ms": stage_ms["ms_dedup"]},
+            "k1_histogram(+extract)": {"ms": stage_ms["ms_extract"] + stage_ms["ms_hist"],
+                                       "reads_GB": n_bases / 4 / 1e9},
+            "k2_radix_passes": {"ms": stage_ms["ms_sort"], "passes": passes, "first_pass_fused_with_k1": fused,
+                                "alg_GBps": (passes * pass_bytes + (k1_bytes if fused else 0)) /
+                                stage_ms["ms_sort"] / 1e6},
+            "k3_reduce(mark+local+rescue, incl. host sync)": {
+                "ms": k3_ms, "alg_GBps": alg["k3_reduce"] / k3_ms / 1e6,
+                "alg_bytes": alg["k3_reduce"]},
+            "k4_dedup": {"ms": stage_ms["ms_dedup"],
+                         "alg_GBps": (rows * W4 + st["kmer_patterns"] * W4 + 4 * rows) /
+                         max(stage_ms["ms_dedup"], 1e-6) / 1e6},
             "raw_ms": {k_: round(v_, 3) for k_, v_ in stage_ms.items()},
         }
         line = {
@@ -422,12 +440,14 @@ def main():
             "bases_per_step_per_gpu": n_bases, "kmer_instances_per_step_per_gpu": M,
             "unique_kmers_per_step_per_gpu": U, "rows_per_step_per_gpu": rows,
             "patterns_per_gpu": st["kmer_patterns"],
-            "roofline": {"bound": "hbm", "kernel": "k2_onesweep_pass<u64>",
+            "roofline": {"bound": "hbm", "kernel": kernel,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": pass_bytes,
-                         "launch_ms": pass_ms, "launches_per_step": passes,
-                         "note": "one radix pass reads and writes every 12-byte record once (2*R*M)"},
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "compulsory_bytes_per_launch": compulsory,
+                         "frac_compulsory": compulsory / (pass_ms * 1e-3) / 1e9 / peak,
+                         "launch_ms": pass_ms, "launches_per_step": passes, "note": note},
+            "whole_step_alg_GBps_declared_model": sum(alg.values()) / (ms_step * 1e-3) / 1e9,
             "stages": stages,
             "end_to_end_alg_bytes_per_base_declared": sum(alg.values()) / n_bases,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),

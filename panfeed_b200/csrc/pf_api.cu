@@ -24,6 +24,50 @@
 
 using namespace pf;
 
+namespace pf {
+// ---- planning helpers that run on the device (tile lists are pure functions of the
+//      per-cluster record ranges; generating them there saves host loops and H2D) -------
+__global__ void plan_expand_tiles(const ClusterDev* __restrict__ clusters, uint32_t n_clusters,
+                                  const uint32_t* __restrict__ tile_base, uint32_t tile_size, int wide,
+                                  TileDev* __restrict__ tiles) {
+  const uint32_t c = blockIdx.x;
+  if (c >= n_clusters) return;
+  const uint32_t lo = wide ? clusters[c].wrec_start : clusters[c].rec_start;
+  const uint32_t hi = wide ? clusters[c].wrec_end : clusters[c].rec_end;
+  const uint32_t first = tile_base[c];
+  const uint32_t n = (hi - lo + tile_size - 1) / tile_size;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    TileDev t;
+    t.start = lo + i * tile_size;
+    t.count = min(tile_size, hi - t.start);
+    t.seg = c;
+    t.first_tile = first;
+    tiles[first + i] = t;
+  }
+}
+__global__ void plan_seq_rec_off(const SeqDev* __restrict__ seqs, uint32_t n_seqs, uint32_t total,
+                                 uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_seqs) out[i] = seqs[i].rec_off;
+  else if (i == n_seqs) out[i] = total;
+}
+// sequence holding the first record of every tile (last s with rec_off[s] <= start, non-empty)
+__global__ void plan_tile_first_seq(const TileDev* __restrict__ tiles, uint32_t n_tiles,
+                                    const uint32_t* __restrict__ seq_rec_off, uint32_t n_seqs,
+                                    uint32_t* __restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  if (t == n_tiles) { out[t] = n_seqs ? n_seqs - 1 : 0; return; }
+  const uint32_t r = tiles[t].start;
+  uint32_t lo = 0, hi = n_seqs;                   // first index in [0, n_seqs] with rec_off > r
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (seq_rec_off[mid] <= r) lo = mid + 1; else hi = mid;
+  }
+  out[t] = lo ? lo - 1 : 0;
+}
+}  // namespace pf
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -54,7 +98,8 @@ struct WidthState {       // per key width (narrow u64 / wide Key128)
   DevBuf keys[2], vals[2];
   DevBuf tiles, seg_start, seg_hist, lookback, cursors;
   DevBuf ltiles, tile_first_run;     // partition mode: 2048-record tiles of the local reduce
-  PinBuf h_tiles, h_seg_start, h_ltiles;
+  PinBuf h_tiles, h_seg_start, h_ltiles;       // h_tiles / h_ltiles now hold per-cluster tile bases
+  DevBuf d_tile_base, d_ltile_base;
   uint32_t n_tiles = 0, n_ltiles = 0, max_seg = 0;
   uint32_t n_records = 0;
   uint32_t n_runs = 0;
@@ -71,6 +116,9 @@ struct pf_ctx {
   pf_params prm{};
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // D2H of finished row arrays while K4 still runs
+  cudaEvent_t ev_rows = nullptr;
+  bool rows_prefetched = false;
   std::string err;
   uint32_t W = 0, Wk = 0;
   std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> maf_cache;
@@ -260,6 +308,8 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
     delete ctx;
     return fail(nullptr, PF_ERR_CUDA, "cudaStreamCreate failed");
   }
+  cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_rows, cudaEventDisableTiming);
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   for (auto& ev : ctx->ev_h2d) cudaEventCreate(&ev);
   for (auto& ev : ctx->ev_d2h) cudaEventCreate(&ev);
@@ -308,7 +358,8 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
     fd(*b);
   for (WidthState* w : {&ctx->nar, &ctx->wid}) {
     for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
-                      &w->seg_hist, &w->lookback, &w->cursors, &w->ltiles, &w->tile_first_run})
+                      &w->seg_hist, &w->lookback, &w->cursors, &w->ltiles, &w->tile_first_run,
+                      &w->d_tile_base, &w->d_ltile_base})
       fd(*b);
     fp(w->h_tiles); fp(w->h_seg_start); fp(w->h_ltiles);
   }
@@ -326,6 +377,8 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_h2d) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_d2h) if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -355,28 +408,26 @@ int plan_local_tiles(pf_ctx* ctx) {
   if (!ctx->partition) { w.n_ltiles = 0; return PF_OK; }
   const uint32_t tile = ctx->use_direct ? (uint32_t)kDirectTile : (uint32_t)kLocalTile;
   ctx->local_tile = tile;
+  const uint32_t nc = (uint32_t)ctx->nar_ranges.size();
+  TRY(pin_ensure(ctx, w.h_ltiles, std::max<size_t>(1, nc) * 4));
+  uint32_t* base = w.h_ltiles.as<uint32_t>();
   uint64_t nl = 0;
-  for (auto& r : ctx->nar_ranges) nl += cdiv(r.second - r.first, tile);
-  w.n_ltiles = (uint32_t)nl;
-  TRY(pin_ensure(ctx, w.h_ltiles, std::max<size_t>(1, nl) * sizeof(TileDev)));
-  TileDev* lt = w.h_ltiles.as<TileDev>();
-  uint32_t li = 0;
-  for (uint32_t c = 0; c < ctx->nar_ranges.size(); ++c) {
-    const uint32_t first = li;
-    for (uint32_t s = ctx->nar_ranges[c].first; s < ctx->nar_ranges[c].second; s += tile) {
-      lt[li].start = s;
-      lt[li].count = std::min<uint32_t>(tile, ctx->nar_ranges[c].second - s);
-      lt[li].seg = c;
-      lt[li].first_tile = first;
-      ++li;
-    }
+  for (uint32_t c = 0; c < nc; ++c) {
+    base[c] = (uint32_t)nl;
+    nl += cdiv(ctx->nar_ranges[c].second - ctx->nar_ranges[c].first, tile);
   }
+  w.n_ltiles = (uint32_t)nl;
   if (w.n_ltiles) {
     TRY(dev_ensure(ctx, w.ltiles, (size_t)w.n_ltiles * sizeof(TileDev)));
     TRY(dev_ensure(ctx, w.tile_first_run, ((size_t)w.n_ltiles + 1) * 4));
     TRY(dev_ensure(ctx, w.lookback, std::max<size_t>((size_t)w.n_tiles * kRadix * 4, (size_t)w.n_ltiles * 8)));
-    CU(cudaMemcpyAsync(w.ltiles.p, w.h_ltiles.p, w.n_ltiles * sizeof(TileDev), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    TRY(dev_ensure(ctx, w.d_ltile_base, (size_t)nc * 4));
+    CU(cudaMemcpyAsync(w.d_ltile_base.p, base, (size_t)nc * 4, cudaMemcpyHostToDevice, ctx->stream));
+    // needs d_clusters: the caller uploads it first
+    plan_expand_tiles<<<nc, 128, 0, ctx->stream>>>(ctx->d_clusters.as<ClusterDev>(), nc, w.d_ltile_base.as<uint32_t>(),
+                                                   tile, 0, w.ltiles.as<TileDev>());
+    ctx->launches++;     // (the pinned `base` array must not be rewritten before this copy ran:
+                         //  pf_upload ends with a sync, the re-plan in pf_execute syncs itself)
   }
   return PF_OK;
 }
@@ -394,21 +445,15 @@ int plan_tiles(pf_ctx* ctx, WidthState& w, const std::vector<std::pair<uint32_t,
   w.max_seg = max_seg;
   w.sort_bits = auto_sort_bits(ctx, max_seg, narrow);
   w.passes = w.sort_bits / 8;
-  TRY(pin_ensure(ctx, w.h_tiles, std::max<size_t>(1, n_tiles) * sizeof(TileDev)));
+  TRY(pin_ensure(ctx, w.h_tiles, std::max<size_t>(1, ranges.size()) * 4));
   TRY(pin_ensure(ctx, w.h_seg_start, std::max<size_t>(1, ranges.size()) * sizeof(uint32_t)));
-  TileDev* t = w.h_tiles.as<TileDev>();
+  uint32_t* tb = w.h_tiles.as<uint32_t>();
   uint32_t* ss = w.h_seg_start.as<uint32_t>();
   uint32_t ti = 0;
   for (uint32_t c = 0; c < ranges.size(); ++c) {
     ss[c] = ranges[c].first;
-    const uint32_t first = ti;
-    for (uint32_t s = ranges[c].first; s < ranges[c].second; s += kSortTile) {
-      t[ti].start = s;
-      t[ti].count = std::min<uint32_t>(kSortTile, ranges[c].second - s);
-      t[ti].seg = c;
-      t[ti].first_tile = first;
-      ++ti;
-    }
+    tb[c] = ti;
+    ti += cdiv(ranges[c].second - ranges[c].first, kSortTile);
   }
   return PF_OK;
 }
@@ -589,37 +634,36 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
     TRY(dev_ensure(ctx, w->seg_hist, std::max<size_t>(1, (size_t)b->n_clusters * w->passes * kRadix) * 4));
     TRY(dev_ensure(ctx, w->lookback, std::max<size_t>(1, (size_t)w->n_tiles * kRadix) * 4));
   }
-  ctx->nar_ranges = nr;
-  TRY(plan_local_tiles(ctx));
-  // fused first pass: record index -> sequence lookup tables
-  {
-    TRY(pin_ensure(ctx, ctx->h_seq_rec_off, ((size_t)b->n_seqs + 1) * 4));
-    TRY(pin_ensure(ctx, ctx->h_tile_first_seq, ((size_t)ctx->nar.n_tiles + 1) * 4));
-    uint32_t* ro = ctx->h_seq_rec_off.as<uint32_t>();
-    for (uint32_t i = 0; i < b->n_seqs; ++i) ro[i] = hs[i].rec_off;
-    ro[b->n_seqs] = (uint32_t)rec;
-    uint32_t* tf = ctx->h_tile_first_seq.as<uint32_t>();
-    const TileDev* tl = ctx->nar.h_tiles.as<TileDev>();
-    uint32_t sp = 0;
-    for (uint32_t t = 0; t < ctx->nar.n_tiles; ++t) {
-      while (sp + 1 < b->n_seqs && ro[sp + 1] <= tl[t].start) ++sp;
-      tf[t] = sp;
-    }
-    tf[ctx->nar.n_tiles] = b->n_seqs ? b->n_seqs - 1 : 0;
-    TRY(dev_ensure(ctx, ctx->d_seq_rec_off, ((size_t)b->n_seqs + 1) * 4));
-    TRY(dev_ensure(ctx, ctx->d_tile_first_seq, ((size_t)ctx->nar.n_tiles + 1) * 4));
-    CU(cudaMemcpyAsync(ctx->d_seq_rec_off.p, ro, ((size_t)b->n_seqs + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_tile_first_seq.p, tf, ((size_t)ctx->nar.n_tiles + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-  }
   cudaStream_t st = ctx->stream;
   if (b->n_seqs) CU(cudaMemcpyAsync(ctx->d_seqs.p, hs, b->n_seqs * sizeof(SeqDev), cudaMemcpyHostToDevice, st));
   if (b->n_clusters) {
     CU(cudaMemcpyAsync(ctx->d_clusters.p, hc, b->n_clusters * sizeof(ClusterDev), cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(ctx->d_presence.p, b->cluster_presence, (size_t)b->n_clusters * W * 4, cudaMemcpyHostToDevice, st));
   }
+  // tile lists are generated on the device from the per-cluster record ranges
   for (WidthState* w : {&ctx->nar, &ctx->wid}) {
-    if (w->n_tiles) CU(cudaMemcpyAsync(w->tiles.p, w->h_tiles.p, w->n_tiles * sizeof(TileDev), cudaMemcpyHostToDevice, st));
     if (b->n_clusters) CU(cudaMemcpyAsync(w->seg_start.p, w->h_seg_start.p, b->n_clusters * 4, cudaMemcpyHostToDevice, st));
+    if (w->n_tiles) {
+      TRY(dev_ensure(ctx, w->d_tile_base, (size_t)b->n_clusters * 4));
+      CU(cudaMemcpyAsync(w->d_tile_base.p, w->h_tiles.p, (size_t)b->n_clusters * 4, cudaMemcpyHostToDevice, st));
+      plan_expand_tiles<<<b->n_clusters, 128, 0, st>>>(ctx->d_clusters.as<ClusterDev>(), b->n_clusters,
+                                                       w->d_tile_base.as<uint32_t>(), kSortTile,
+                                                       w == &ctx->wid ? 1 : 0, w->tiles.as<TileDev>());
+      ctx->launches++;
+    }
+  }
+  ctx->nar_ranges = nr;
+  TRY(plan_local_tiles(ctx));
+  // fused first pass: record index -> sequence lookup tables
+  if (b->n_seqs) {
+    TRY(dev_ensure(ctx, ctx->d_seq_rec_off, ((size_t)b->n_seqs + 1) * 4));
+    TRY(dev_ensure(ctx, ctx->d_tile_first_seq, ((size_t)ctx->nar.n_tiles + 1) * 4));
+    plan_seq_rec_off<<<cdiv((uint64_t)b->n_seqs + 1, 256), 256, 0, st>>>(
+        ctx->d_seqs.as<SeqDev>(), b->n_seqs, (uint32_t)rec, ctx->d_seq_rec_off.as<uint32_t>());
+    plan_tile_first_seq<<<cdiv((uint64_t)ctx->nar.n_tiles + 1, 256), 256, 0, st>>>(
+        ctx->nar.tiles.as<TileDev>(), ctx->nar.n_tiles, ctx->d_seq_rec_off.as<uint32_t>(), b->n_seqs,
+        ctx->d_tile_first_seq.as<uint32_t>());
+    ctx->launches += 2;
   }
   if (n_wide) {
     const size_t bit_words = (b->n_amb_words + 1) / 2 + 4;
@@ -848,6 +892,7 @@ int dedup(pf_ctx* ctx, PatternSpace& s, const uint32_t* cand, uint32_t n, DevBuf
 int finalize_pending(pf_ctx* ctx) {
   if (!ctx->executed) return PF_OK;
   CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->rows_prefetched) CU(cudaStreamSynchronize(ctx->copy_stream));
   ctx->kp.n = ctx->kp_base + ctx->h_counters.as<uint32_t>()[C_NEW_KP];
   return PF_OK;
 }
@@ -1089,6 +1134,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       } else if (ctx->use_direct) {
         ctx->use_direct = false;
         TRY(plan_local_tiles(ctx));
+        CU(cudaStreamSynchronize(st));
       } else {
         return fail(ctx, PF_ERR_INTERNAL, "local table overflow at 64 sorted bits");
       }
@@ -1149,6 +1195,23 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   }
   CU(cudaEventRecord(ctx->ev[EV_REDUCE], st));
 
+  // the (cluster, k-mer, count) arrays of the rows are final: start their D2H on the copy
+  // stream while K4 numbers the patterns
+  ctx->rows_prefetched = false;
+  if (rows) {
+    TRY(pin_ensure(ctx, ctx->r_row_cluster, rows * 4));
+    TRY(pin_ensure(ctx, ctx->r_row_count, rows * 4));
+    TRY(pin_ensure(ctx, ctx->r_row_kmer, std::max<size_t>(8, (size_t)N.n_rows * 8)));
+    TRY(pin_ensure(ctx, ctx->r_wrow_kmer, std::max<size_t>(8, (size_t)Wd.n_rows * 16)));
+    CU(cudaEventRecord(ctx->ev_rows, st));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_rows, 0));
+    CU(cudaMemcpyAsync(ctx->r_row_cluster.p, ctx->d_row_cluster.p, rows * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    CU(cudaMemcpyAsync(ctx->r_row_count.p, ctx->d_row_count.p, rows * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (N.n_rows) CU(cudaMemcpyAsync(ctx->r_row_kmer.p, ctx->d_row_kmer.p, (size_t)N.n_rows * 8, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (Wd.n_rows) CU(cudaMemcpyAsync(ctx->r_wrow_kmer.p, ctx->d_wrow_kmer.p, (size_t)Wd.n_rows * 16, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    ctx->rows_prefetched = true;
+  }
+
   // ---- K4 ---------------------------------------------------------------
   TRY(dedup(ctx, ctx->kp, ctx->d_cand.as<uint32_t>(), (uint32_t)rows, ctx->d_rep, ctx->d_slot_of,
             ctx->d_winner, ctx->d_row_pattern.as<uint32_t>(), C_NEW_KP));
@@ -1188,11 +1251,13 @@ extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
     if (bytes) CU(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyDeviceToHost, st));
     return PF_OK;
   };
-  TRY(d2h(ctx->r_row_cluster, ctx->d_row_cluster.p, rows * 4));
-  TRY(d2h(ctx->r_row_count, ctx->d_row_count.p, rows * 4));
+  if (!ctx->rows_prefetched) {
+    TRY(d2h(ctx->r_row_cluster, ctx->d_row_cluster.p, rows * 4));
+    TRY(d2h(ctx->r_row_count, ctx->d_row_count.p, rows * 4));
+    TRY(d2h(ctx->r_row_kmer, ctx->d_row_kmer.p, (size_t)N.n_rows * 8));
+    TRY(d2h(ctx->r_wrow_kmer, ctx->d_wrow_kmer.p, (size_t)Wd.n_rows * 16));
+  }
   TRY(d2h(ctx->r_row_pattern, ctx->d_row_pattern.p, rows * 4));
-  TRY(d2h(ctx->r_row_kmer, ctx->d_row_kmer.p, (size_t)N.n_rows * 8));
-  TRY(d2h(ctx->r_wrow_kmer, ctx->d_wrow_kmer.p, (size_t)Wd.n_rows * 16));
   TRY(d2h(ctx->r_cl_pattern, ctx->d_cl_pattern.p, (size_t)ctx->n_clusters * 4));
   TRY(d2h(ctx->r_new_kp, ctx->kp.pool.as<uint32_t>() + ctx->kp_base * ctx->Wk, new_kp * ctx->Wk * 4));
   TRY(d2h(ctx->r_new_cp, ctx->cp.pool.as<uint32_t>() + ctx->cp_base * ctx->W, new_cp * ctx->W * 4));
@@ -1206,6 +1271,8 @@ extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
   if (ctx->n_pos_wide) TRY(d2h(ctx->r_pos_wide, ctx->d_pos_wide.p, (size_t)ctx->n_pos_wide * 16));
   CU(cudaEventRecord(ctx->ev_d2h[1], st));
   CU(cudaStreamSynchronize(st));
+  if (ctx->rows_prefetched) CU(cudaStreamSynchronize(ctx->copy_stream));
+  ctx->rows_prefetched = false;
 
   if (out) {
     memset(out, 0, sizeof *out);
