@@ -203,6 +203,11 @@ int pf_maf_window(double maf, uint32_t n, uint32_t* lo, uint32_t* hi);
 /* Device-side pool access (full bitsets of every pattern seen so far). */
 int pf_patterns_export(pf_ctx* ctx, int cluster_namespace, uint64_t first,
                        uint64_t count, uint32_t* host_out);
+/* K5: the reference's pattern ids.  16-byte MD5 digests of the int64 (cluster namespace,
+ * panfeed.py:175) or float64 (k-mer namespace, panfeed.py:206, NaN where the cluster is
+ * absent) expansion of patterns [first, first+count); id = base64(digest)[:24]. */
+int pf_pattern_ids(pf_ctx* ctx, int cluster_namespace, uint64_t first, uint64_t count,
+                   uint8_t* host_digests);
 int pf_stats_get(pf_ctx* ctx, pf_stats* out);
 /* CUDA stream the context launches on, as an opaque handle (cudaStream_t). */
 void* pf_stream(pf_ctx* ctx);

@@ -106,7 +106,7 @@ class SynthParams(C.Structure):
 EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_upload", "pf_execute", "pf_submit", "pf_collect",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
-           "pf_maf_window", "pf_patterns_export", "pf_stats_get", "pf_stream",
+           "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_stream",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_export",
            "pf_exchange_unpack"]
@@ -140,6 +140,7 @@ def load():
     lib.pf_kmer_pattern_words.restype = u32
     lib.pf_maf_window.argtypes = [C.c_double, u32, C.POINTER(u32), C.POINTER(u32)]
     lib.pf_patterns_export.argtypes = [vp, C.c_int, u64, u64, vp]
+    lib.pf_pattern_ids.argtypes = [vp, C.c_int, u64, u64, vp]
     lib.pf_stats_get.argtypes = [vp, C.POINTER(Stats)]
     lib.pf_stream.argtypes = [vp]
     lib.pf_stream.restype = vp
@@ -166,6 +167,20 @@ def _np(ptr, n, dtype, copy=True):
         return np.zeros(0, dtype)
     a = np.ctypeslib.as_array(ptr, shape=(int(n),))
     return a.astype(dtype, copy=True) if copy else a
+
+
+_B64 = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/", np.uint8)
+
+
+def base64_ids(digests):
+    """[n,16] uint8 MD5 digests -> numpy S24 array of base64 strings (with '==')."""
+    d = np.zeros((len(digests), 18), np.uint32)
+    d[:, :16] = digests
+    t = (d[:, 0::3] << 16) | (d[:, 1::3] << 8) | d[:, 2::3]            # [n, 6] 24-bit groups
+    sx = np.stack([(t >> 18) & 63, (t >> 12) & 63, (t >> 6) & 63, t & 63], axis=2).reshape(len(d), 24)
+    out = _B64[sx]
+    out[:, 22:] = ord("=")
+    return np.ascontiguousarray(out).view("S24").ravel()
 
 
 class HostBatch:
@@ -294,6 +309,16 @@ class Context:
         self._check(self.lib.pf_patterns_export(self.h, int(cluster_namespace),
                                                 first, count, out.ctypes.data))
         return out
+
+    def pattern_ids(self, cluster_namespace, first, count):
+        """The reference's id strings (base64(md5(vector bytes))[:24]) of patterns
+        [first, first+count), MD5 computed on the device (K5)."""
+        if count == 0:
+            return np.zeros(0, "S24")
+        dig = np.zeros((count, 16), np.uint8)
+        self._check(self.lib.pf_pattern_ids(self.h, int(cluster_namespace), first, count,
+                                            dig.ctypes.data))
+        return base64_ids(dig)
 
     def stream_handle(self):
         return self.lib.pf_stream(self.h)

@@ -20,6 +20,7 @@
 #include "k3_reduce.cuh"
 #include "k3_local.cuh"
 #include "k4_dedup.cuh"
+#include "k5_md5.cuh"
 #include "synth.cuh"
 
 using namespace pf;
@@ -144,7 +145,7 @@ struct pf_ctx {
   bool runs_from_hist = false;   // one pass: prefix-runs are the digit buckets of the histogram
   uint32_t local_tile = 0;       // records per tile of the local reduce (4096 direct / 2048 general)
   bool fused = false;            // K1 fused into the histogram and the first pass (no record write in K1)
-  DevBuf d_seq_rec_off, d_tile_first_seq;
+  DevBuf d_seq_rec_off, d_tile_first_seq, d_digests;
   PinBuf h_seq_rec_off, h_tile_first_seq;
   std::vector<std::pair<uint32_t, uint32_t>> nar_ranges;   // narrow record range of every cluster
   int extra_bits = 0;      // sort bits added after a table overflow (sticky)
@@ -354,7 +355,8 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->d_row_pattern, &ctx->d_cand, &ctx->d_rep, &ctx->d_slot_of, &ctx->d_winner,
                     &ctx->d_cl_pattern, &ctx->d_cl_rep, &ctx->d_cl_slot, &ctx->d_cl_winner,
                     &ctx->d_pos_kmer, &ctx->d_pos_seq, &ctx->d_pos_cstart, &ctx->d_pos_gstart,
-                    &ctx->d_pos_flags, &ctx->d_pos_wide, &ctx->d_seq_rec_off, &ctx->d_tile_first_seq})
+                    &ctx->d_pos_flags, &ctx->d_pos_wide, &ctx->d_seq_rec_off, &ctx->d_tile_first_seq,
+                    &ctx->d_digests})
     fd(*b);
   for (WidthState* w : {&ctx->nar, &ctx->wid}) {
     for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
@@ -1351,6 +1353,27 @@ extern "C" int pf_patterns_export(pf_ctx* ctx, int cluster_namespace, uint64_t f
   if (count)
     CU(cudaMemcpy(host_out, s.pool.as<uint32_t>() + first * s.key_words, count * s.key_words * 4,
                   cudaMemcpyDeviceToHost));
+  return PF_OK;
+}
+
+extern "C" int pf_pattern_ids(pf_ctx* ctx, int cluster_namespace, uint64_t first, uint64_t count,
+                              uint8_t* host_digests) {
+  if (!ctx || (count && !host_digests)) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  TRY(finalize_pending(ctx));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  if (first + count > s.n) return fail(ctx, PF_ERR_INVALID, "pattern range [%llu,%llu) beyond %llu",
+                                       (unsigned long long)first, (unsigned long long)(first + count),
+                                       (unsigned long long)s.n);
+  if (count == 0) return PF_OK;
+  TRY(dev_ensure(ctx, ctx->d_digests, count * 16));
+  k5_md5_ids<<<cdiv(count, 128), 128, 0, ctx->stream>>>(
+      s.pool.as<uint32_t>(), (uint32_t)first, (uint32_t)count, s.key_words, ctx->W, ctx->prm.n_samples,
+      cluster_namespace ? 1 : 0, ctx->cp.pool.as<uint32_t>(), ctx->d_digests.as<uint8_t>());
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(host_digests, ctx->d_digests.p, count * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return PF_OK;
 }
 

@@ -38,7 +38,9 @@ _COMP = bytes.maketrans(b"ACTGNYRWSKMDVHBX", b"TGACNRYWSMKHBDVX")
 
 def pattern_id(vec):
     """base64(md5(raw little-endian bytes of the vector))[:24] (panfeed.py:175-176,
-    206-207): int64 bytes for cluster rows, float64 bytes for k-mer rows."""
+    206-207): int64 bytes for cluster rows, float64 bytes for k-mer rows.  Host-side
+    definition of the id, kept for tools and tests; the product derives ids on the
+    device (`Context.pattern_ids`, kernel K5)."""
     return binascii.b2a_base64(hashlib.md5(np.ascontiguousarray(vec).view(np.uint8)).digest()
                                ).decode()[:24]
 
@@ -137,16 +139,14 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
     ctx.submit(hb)
     r = ctx.collect()
 
-    # ---- new patterns -> ids + hashes_to_patterns rows ------------------------
+    # ---- new patterns -> ids (MD5 on the device, K5) + hashes_to_patterns rows ----
     pat_text = []
     new_cp = r["new_cluster_patterns"]
     if len(new_cp):
         cells = _expand_bits(new_cp, S)
-        ints = cells.astype(np.int64)
-        new_ids, fresh = [], []
-        for row in ints:
-            pid = pattern_id(row)
-            new_ids.append(pid)
+        new_ids = [x.decode() for x in ctx.pattern_ids(True, r["cluster_pattern_base"], len(new_cp))]
+        fresh = []
+        for pid in new_ids:
             fresh.append(pid not in store.seen)
             store.seen.add(pid)
         store.cluster_ids += new_ids
@@ -157,16 +157,13 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
     if len(new_kp):
         W = (S + 31) // 32
         cells = _expand_bits(new_kp[:, :W], S)
-        vecs = cells.astype(np.float64)
         nan_mask = None
         if consider_missing:
             present = _expand_bits(np.stack([store.cluster_bits[c] for c in new_kp[:, W]]), S)
             nan_mask = present == 0
-            vecs[nan_mask] = np.nan
-        new_ids, fresh = [], []
-        for row in vecs:
-            pid = pattern_id(row)
-            new_ids.append(pid)
+        new_ids = [x.decode() for x in ctx.pattern_ids(False, r["kmer_pattern_base"], len(new_kp))]
+        fresh = []
+        for pid in new_ids:
             fresh.append(pid not in store.seen)
             store.seen.add(pid)
         store.kmer_ids += new_ids
