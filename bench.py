@@ -45,6 +45,9 @@ def parse():
     p.add_argument("-k", type=int, default=31)
     p.add_argument("--maf", type=float, default=0.01)
     p.add_argument("--consider-missing", action="store_true")
+    p.add_argument("--targets-all", action="store_true",
+                   help="second pass (BASELINE config 3): every sample is a --targets strain, "
+                        "positional kmers.tsv records are produced")
     p.add_argument("--sort-bits", type=int, default=0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -270,10 +273,10 @@ def main():
     S, C, L, k = args.samples, args.clusters, args.gene_len, args.k
     total_clusters = C * world
     hb = capi.synth_batch(local, SEED, S, C, first_cluster=rank * C, total_clusters=total_clusters,
-                          gene_len=L, pinned=True)
+                          gene_len=L, pinned=True, all_targets=args.targets_all)
     n_bases = hb.n_bases
     ctx = capi.Context(k, S, canonical=True, consider_missing=args.consider_missing,
-                       cluster_equal_filter=False, emit_positions=False, maf=args.maf,
+                       cluster_equal_filter=False, emit_positions=args.targets_all, maf=args.maf,
                        sort_bits=args.sort_bits, device=local)
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
     exch = None
@@ -452,6 +455,9 @@ def main():
             "end_to_end_alg_bytes_per_base_declared": sum(alg.values()) / n_bases,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
         }
+        if args.targets_all:
+            line["positional_records_per_s"] = world * M / (ms_step * 1e-3)
+            line["config"]["workload"] = line["config"]["workload"].replace("first pass", "second pass, all samples --targets")
         if exch_ms:
             line["exchange_ms_last_step_rank0"] = {k_: round(v_, 3) for k_, v_ in exch_ms.items()}
         if not args.no_cpu_baseline:
