@@ -61,7 +61,8 @@ typedef struct pf_params {
                                     in a shared-memory hash table (default);
                                     1 = full sort: LSD passes over sort_bits, then a
                                     segmented run reduction                          */
-  uint32_t debug_flags;          /* bit 0: do not fuse K1 into the histogram / first pass   */
+  uint32_t debug_flags;          /* bit 0: do not fuse K1 into the histogram / first pass;
+                                    bit 1: no block aggregation (always go through records)  */
   double   maf;                  /* --maf, compared in float64 exactly as
                                     panfeed.py:190-200 (see pf_maf_window)          */
 } pf_params;
@@ -169,9 +170,18 @@ typedef struct pf_stats {
   /* device time of the last batch, CUDA events on the context stream:
      h2d | K1 extract | K2 histogram | K2 onesweep passes | K3 mark runs |
      K3 count (incl. the host sync for the run count) | K3 emit + cluster-row
-     dedup (incl. the host sync for the row count) | K4 dedup | d2h | K1..K4 */
+     dedup (incl. the host sync for the row count) | K4 dedup | d2h | K1..K4.
+     Engine 2: ms_sort = kA_block_aggregate, ms_count = kB_merge (incl. the host sync). */
   float ms_h2d, ms_extract, ms_hist, ms_sort, ms_mark, ms_count, ms_reduce, ms_dedup, ms_d2h, ms_total;
   uint64_t total_launches;   /* kernels launched since pf_create                     */
+  /* engine the last batch went through: 0 = records, partition mode (K1 fused into one radix
+     pass + shared-memory grouping); 1 = records, full sort; 2 = block aggregation (rolling
+     k-mers grouped per position block in shared memory, no records; S <= 1024) */
+  uint32_t engine;
+  uint32_t block_windows;    /* engine 2: windows per position block                  */
+  uint32_t block_slots;      /* engine 2: shared-memory table slots per block         */
+  uint32_t reserved;
+  uint64_t partial_rows;     /* engine 2: (k-mer, bitset) partial rows of the last batch */
 } pf_stats;
 
 /* ---- lifetime ---- */

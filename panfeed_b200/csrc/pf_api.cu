@@ -19,6 +19,7 @@
 #include "k2_onesweep.cuh"
 #include "k3_reduce.cuh"
 #include "k3_local.cuh"
+#include "k3_block.cuh"
 #include "k4_dedup.cuh"
 #include "k5_md5.cuh"
 #include "synth.cuh"
@@ -153,6 +154,21 @@ struct pf_ctx {
   uint64_t row_cap = 0;
   uint64_t unique_last = 0;
   uint32_t rescued_last = 0;
+  // block aggregation (k3_block.cuh): no records, partial (k-mer, bitset) rows per position block
+  bool block_mode = false;       // S <= 1024 and not disabled: kA_block_aggregate + kB_merge
+  uint32_t block_windows = 16;   // B: windows per position block (halved after an overflow, >= 16)
+  uint32_t blk_slots = 512, merge_slots = 1024;   // shared-memory table sizes of kA / kB (powers of two)
+  uint32_t merge_target = 0;     // distinct keys a merge group should hold
+  uint32_t n_items = 0;          // (cluster, block) work items of the resident batch
+  uint32_t block_fallbacks = 0;
+  double partial_ratio = 1.0 / 16;   // partial rows per window, learned from earlier batches
+  uint64_t partial_cap = 0;
+  uint64_t partials_last = 0;
+  bool used_block = false;       // the last batch went through kA/kB
+  DevBuf d_seq_lite, d_cblk, d_item_base, d_item_cluster, d_slab_base, d_slab_count, d_slab_keys,
+      d_slab_rows, d_group_base, d_group_cluster, d_group_cnt, d_group_off, d_part_list, d_plan_total,
+      d_rescue[2];
+  PinBuf h_plan;
   PatternSpace kp, cp;     // k-mer patterns, cluster patterns
   uint64_t kp_base = 0, cp_base = 0;   // pool sizes before the resident batch
   // pinned results
@@ -228,11 +244,14 @@ bool debug_sync(const char* name) {
 
 inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 constexpr int kGridPersist = 148 * 4;
+constexpr uint32_t kBlkMaxSmem = 200u * 1024u;   // largest kA / kB table we ask for
 
 // counters layout in d_counters
 enum { C_TICKET_N = 0, C_TICKET_W = 1, C_RUNS_N = 2, C_RUNS_W = 3, C_ERR = 4, C_ROWS_N = 5,
        C_ROWS_W = 6, C_NEW_KP = 7, C_NEW_CP = 8, C_TICKET_MARK_N = 9, C_TICKET_MARK_W = 10,
-       C_LOCAL = 11 /* 5 words: rows, unique, table overflow, row overflow, rescue runs */, C_COUNT = 16 };
+       C_LOCAL = 11 /* LC_COUNT words: rows, unique, table overflow, row overflow, rescue runs,
+                        partial rows, partial overflow */, C_TICKET_MERGE = 18, C_COUNT = 24 };
+static_assert(C_LOCAL + LC_COUNT <= C_TICKET_MERGE, "counter layout");
 
 bool keep_count(double maf, uint32_t c, uint32_t n) {
   double af = (double)c / (double)n;      // numpy: vec.sum() / vec.shape[0]
@@ -328,6 +347,40 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
   cudaFuncSetAttribute(k3_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LocalSmem));
   cudaFuncSetAttribute(k3_local_direct, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DirectSmem));
   ctx->use_direct = ctx->W <= kDirectMaxWords;
+  {
+    // block aggregation: debug_flags bit 1 disables it; PF_BLOCK_WINDOWS / PF_BLOCK_SMEM_KB tune it
+    ctx->block_mode = ctx->partition && ctx->use_direct && !(p->debug_flags & 2u);
+    if (const char* e = getenv("PF_BLOCK_MODE")) ctx->block_mode = ctx->block_mode && atoi(e) != 0;
+    if (const char* e = getenv("PF_BLOCK_WINDOWS")) {
+      const int b = atoi(e);
+      if (b >= kBlkRun && b <= kBlkRun * kBlkWarps && b % kBlkRun == 0 && (kBlkWarps % (b / kBlkRun)) == 0)
+        ctx->block_windows = (uint32_t)b;
+    }
+    // table of kA: one slot per expected distinct k-mer of a 16-window block at ~50 % load
+    // (about one haplotype per 30 samples and position); doubled after an overflow
+    uint32_t slots = 256;
+    while (slots < p->n_samples * ctx->block_windows / 16u && slots < 4096u) slots *= 2;
+    if (const char* e = getenv("PF_BLOCK_SLOTS")) {
+      const int v = atoi(e);
+      if (v >= 64 && v <= 8192 && (v & (v - 1)) == 0) slots = (uint32_t)v;
+    }
+    while (slots > 64u && blk_smem_bytes(slots, ctx->W) > kBlkMaxSmem) slots /= 2;
+    ctx->blk_slots = slots;
+    uint32_t mslots = 1024;
+    if (const char* e = getenv("PF_MERGE_SLOTS")) {
+      const int v = atoi(e);
+      if (v >= 64 && v <= 8192 && (v & (v - 1)) == 0) mslots = (uint32_t)v;
+    }
+    while (mslots > 64u && blk_smem_bytes(mslots, ctx->W) > 100u * 1024u) mslots /= 2;
+    ctx->merge_slots = mslots;
+    ctx->merge_target = std::max<uint32_t>(16u, mslots * 5u / 8u);
+    if (p->k == 32 && !p->canonical) ctx->block_mode = false;   // all-T k-mer == the empty-slot mark
+    cudaFuncSetAttribute(kA_block_aggregate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
+    cudaFuncSetAttribute(kA_block_aggregate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
+    cudaFuncSetAttribute(kA_block_aggregate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
+    cudaFuncSetAttribute(kA_block_aggregate<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
+    cudaFuncSetAttribute(kB_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
+  }
   const int k3_smem = (int)(8 * ctx->W * sizeof(uint32_t));
   if (k3_smem > 48 * 1024) {
     cudaFuncSetAttribute(k3_runs<uint64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, k3_smem);
@@ -356,7 +409,10 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->d_cl_pattern, &ctx->d_cl_rep, &ctx->d_cl_slot, &ctx->d_cl_winner,
                     &ctx->d_pos_kmer, &ctx->d_pos_seq, &ctx->d_pos_cstart, &ctx->d_pos_gstart,
                     &ctx->d_pos_flags, &ctx->d_pos_wide, &ctx->d_seq_rec_off, &ctx->d_tile_first_seq,
-                    &ctx->d_digests})
+                    &ctx->d_digests, &ctx->d_seq_lite, &ctx->d_cblk, &ctx->d_item_base, &ctx->d_slab_base,
+                    &ctx->d_slab_count, &ctx->d_slab_keys, &ctx->d_slab_rows, &ctx->d_group_base,
+                    &ctx->d_item_cluster, &ctx->d_group_cluster, &ctx->d_group_cnt, &ctx->d_group_off,
+                    &ctx->d_part_list, &ctx->d_plan_total, &ctx->d_rescue[0], &ctx->d_rescue[1]})
     fd(*b);
   for (WidthState* w : {&ctx->nar, &ctx->wid}) {
     for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
@@ -369,7 +425,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
     for (DevBuf* b : {&s->pool, &s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique,
                       &s->x_table, &s->x_rep, &s->x_slot, &s->x_winner})
       fd(*b);
-  for (PinBuf* b : {&ctx->h_seqs, &ctx->h_clusters, &ctx->h_wide_seqs, &ctx->h_counters,
+  for (PinBuf* b : {&ctx->h_seqs, &ctx->h_clusters, &ctx->h_wide_seqs, &ctx->h_counters, &ctx->h_plan,
                     &ctx->h_seq_rec_off, &ctx->h_tile_first_seq,
                     &ctx->r_row_cluster, &ctx->r_row_kmer, &ctx->r_wrow_kmer, &ctx->r_row_count,
                     &ctx->r_row_pattern, &ctx->r_cl_pattern, &ctx->r_new_kp, &ctx->r_new_cp,
@@ -461,6 +517,8 @@ int plan_tiles(pf_ctx* ctx, WidthState& w, const std::vector<std::pair<uint32_t,
 }
 
 }  // namespace
+
+namespace { int plan_blocks(pf_ctx* ctx); int scan_inplace(pf_ctx* ctx, uint32_t* data, uint32_t n, uint32_t* total_dev); }
 
 extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
   if (!ctx) return PF_ERR_INVALID;
@@ -679,7 +737,14 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
                                                        ctx->d_ambbits.as<uint32_t>(), bit_words);
     ctx->launches++;
   }
+  if (ctx->block_mode && b->n_seqs) {
+    if (b->n_words >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "packed plane holds 2^32 words or more; split the batch");
+    TRY(dev_ensure(ctx, ctx->d_seq_lite, (size_t)b->n_seqs * sizeof(SeqLite)));
+    plan_seq_lite<<<cdiv(b->n_seqs, 256), 256, 0, st>>>(ctx->d_seqs.as<SeqDev>(), b->n_seqs, ctx->d_seq_lite.as<SeqLite>());
+    ctx->launches++;
+  }
   CU(cudaEventRecord(ctx->ev_h2d[1], st));
+  if (ctx->block_mode) TRY(plan_blocks(ctx));
   // caller buffers may be pageable: make sure the copies have consumed them
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
@@ -912,6 +977,10 @@ void fill_timings(pf_ctx* ctx) {
   s.ms_dedup = ms(ctx->ev[EV_REDUCE], ctx->ev[EV_DEDUP]);
   s.ms_total = ms(ctx->ev[EV_START], ctx->ev[EV_END]);
   s.sort_passes = (uint32_t)ctx->nar.passes;
+  s.engine = ctx->used_block ? 2u : (ctx->partition ? 0u : 1u);
+  s.block_windows = ctx->block_windows;
+  s.block_slots = ctx->blk_slots;
+  s.partial_rows = ctx->used_block ? ctx->partials_last : 0;
 }
 
 int check_device_error(pf_ctx* ctx) {
@@ -1006,6 +1075,124 @@ int launch_local(pf_ctx* ctx, RowOut ro, uint32_t n_rescue = 0) {
   return PF_OK;
 }
 
+// ---- block aggregation: work items = (cluster, position block) -----------------------
+// (re)computes the per-cluster block counts for ctx->block_windows; syncs to learn n_items
+int plan_blocks(pf_ctx* ctx) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t nc = ctx->n_clusters;
+  ctx->n_items = 0;
+  if (nc == 0 || ctx->n_seqs == 0) return PF_OK;
+  TRY(dev_ensure(ctx, ctx->d_cblk, (size_t)nc * sizeof(ClusterBlk)));
+  TRY(dev_ensure(ctx, ctx->d_item_base, ((size_t)nc + 1) * 4));
+  TRY(dev_ensure(ctx, ctx->d_group_base, ((size_t)nc + 1) * 4));
+  TRY(dev_ensure(ctx, ctx->d_plan_total, 16));
+  TRY(pin_ensure(ctx, ctx->h_plan, 16));
+  plan_cluster_blocks<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(
+      ctx->d_seqs.as<SeqDev>(), ctx->n_seqs, nc, (int)ctx->prm.k, ctx->block_windows,
+      ctx->d_cblk.as<ClusterBlk>(), ctx->d_item_base.as<uint32_t>());
+  ctx->launches++;
+  TRY(scan_inplace(ctx, ctx->d_item_base.as<uint32_t>(), nc, ctx->d_plan_total.as<uint32_t>()));
+  CU(cudaMemcpyAsync(ctx->h_plan.p, ctx->d_plan_total.p, 4, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  ctx->n_items = ctx->h_plan.as<uint32_t>()[0];
+  TRY(dev_ensure(ctx, ctx->d_slab_base, std::max<size_t>(1, ctx->n_items) * 4));
+  TRY(dev_ensure(ctx, ctx->d_slab_count, std::max<size_t>(1, ctx->n_items) * 4));
+  TRY(dev_ensure(ctx, ctx->d_item_cluster, std::max<size_t>(1, ctx->n_items) * 4));
+  TRY(dev_ensure(ctx, ctx->d_rescue[0], std::max<size_t>(1, ctx->n_items) * 4));
+  TRY(dev_ensure(ctx, ctx->d_rescue[1], std::max<size_t>(1, ctx->n_items) * 4));
+  plan_expand_owner<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(ctx->d_item_base.as<uint32_t>(), nc,
+                                                                  ctx->d_item_cluster.as<uint32_t>());
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
+BlkPlan block_plan(const pf_ctx* ctx) {
+  BlkPlan bp;
+  bp.item_base = ctx->d_item_base.as<uint32_t>();
+  bp.item_cluster = ctx->d_item_cluster.as<uint32_t>();
+  bp.cblk = ctx->d_cblk.as<ClusterBlk>();
+  bp.n_clusters = ctx->n_clusters;
+  bp.block_windows = ctx->block_windows;
+  bp.slots = ctx->blk_slots;
+  bp.max_unique = ctx->blk_slots * 13u / 16u;
+  bp.W = ctx->W;
+  bp.WP = (ctx->W + 3u) & ~3u;
+  return bp;
+}
+
+// items == nullptr: all (cluster, block) items with the context's table size; else the listed
+// items (a rescue launch) with `slots` slots.  Items that overflow are appended to `rescue_out`.
+int launch_block_aggregate(pf_ctx* ctx, const uint32_t* items, uint32_t n, uint32_t slots, uint32_t* rescue_out) {
+  if (n == 0) return PF_OK;
+  cudaStream_t st = ctx->stream;
+  BlkPlan bp = block_plan(ctx);
+  bp.slots = slots;
+  bp.max_unique = slots;
+  const uint32_t cap32 = (uint32_t)std::min<uint64_t>(ctx->partial_cap, 0xfffffff0u);
+  uint32_t* counters = ctx->d_counters.as<uint32_t>() + C_LOCAL;
+  const uint32_t smem = blk_smem_bytes(slots, ctx->W);
+#define PF_KA(CANON, KHI)                                                                              \
+  kA_block_aggregate<CANON, KHI><<<n, kBlkThreads, smem, st>>>(                                        \
+      ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seq_lite.as<SeqLite>(), bp,   \
+      (int)ctx->prm.k, ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),               \
+      ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(), cap32, counters, items,       \
+      rescue_out)
+  const bool khi = ctx->prm.k > 16;
+  if (ctx->prm.canonical) { if (khi) PF_KA(true, true); else PF_KA(true, false); }
+  else { if (khi) PF_KA(false, true); else PF_KA(false, false); }
+#undef PF_KA
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
+int launch_block_merge(pf_ctx* ctx, RowOut ro) {
+  if (ctx->n_items == 0) return PF_OK;
+  cudaStream_t st = ctx->stream;
+  const BlkPlan bp = block_plan(ctx);
+  const uint32_t nc = ctx->n_clusters;
+  uint32_t* counters = ctx->d_counters.as<uint32_t>();
+  plan_merge_groups<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(
+      ctx->d_item_base.as<uint32_t>(), nc, ctx->d_slab_count.as<uint32_t>(), ctx->merge_target,
+      ctx->d_group_base.as<uint32_t>());
+  ctx->launches++;
+  TRY(scan_inplace(ctx, ctx->d_group_base.as<uint32_t>(), nc, ctx->d_plan_total.as<uint32_t>() + 1));
+  // counting sort of the partial rows by (cluster, group): sizes, scan, scatter
+  const uint32_t n_scan = (uint32_t)std::min<uint64_t>(ctx->partial_cap / ctx->merge_target + nc + 2, 0xfffffff0u);
+  TRY(dev_ensure(ctx, ctx->d_group_cluster, (size_t)n_scan * 4));
+  TRY(dev_ensure(ctx, ctx->d_group_cnt, ((size_t)n_scan + 1) * 4));
+  TRY(dev_ensure(ctx, ctx->d_group_off, ((size_t)n_scan + 1) * 4));
+  TRY(dev_ensure(ctx, ctx->d_part_list, std::max<uint64_t>(1, ctx->partial_cap) * 4));
+  plan_expand_owner<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(ctx->d_group_base.as<uint32_t>(), nc,
+                                                                  ctx->d_group_cluster.as<uint32_t>());
+  CU(cudaMemsetAsync(ctx->d_group_cnt.p, 0, ((size_t)n_scan + 1) * 4, st));
+  const uint32_t g0 = cdiv((uint64_t)ctx->n_items * 32, 256);
+  kB0_group<false><<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_base.as<uint32_t>(),
+                                       ctx->d_slab_count.as<uint32_t>(), ctx->d_item_cluster.as<uint32_t>(),
+                                       ctx->n_items, ctx->d_group_base.as<uint32_t>(),
+                                       ctx->d_group_cnt.as<uint32_t>(), nullptr);
+  TRY(scan_inplace(ctx, ctx->d_group_cnt.as<uint32_t>(), n_scan, ctx->d_plan_total.as<uint32_t>() + 2));
+  CU(cudaMemcpyAsync(ctx->d_group_off.p, ctx->d_group_cnt.p, ((size_t)n_scan + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  kB0_group<true><<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_base.as<uint32_t>(),
+                                      ctx->d_slab_count.as<uint32_t>(), ctx->d_item_cluster.as<uint32_t>(),
+                                      ctx->n_items, ctx->d_group_base.as<uint32_t>(),
+                                      ctx->d_group_cnt.as<uint32_t>(), ctx->d_part_list.as<uint32_t>());
+  ctx->launches += 3;
+  CU(cudaMemsetAsync(counters + C_TICKET_MERGE, 0, 4, st));
+  const uint32_t cap = (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu);
+  const uint32_t smem = blk_smem_bytes(ctx->merge_slots, ctx->W);
+  const uint32_t per_sm = std::max<uint32_t>(1u, std::min<uint32_t>(8u, (227u * 1024u) / (smem + 1024u)));
+  kB_merge<<<148 * per_sm, kBlkThreads, smem, st>>>(
+      ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(), bp, ctx->d_group_base.as<uint32_t>(),
+      ctx->d_group_cluster.as<uint32_t>(), ctx->d_group_off.as<uint32_t>(), ctx->d_part_list.as<uint32_t>(),
+      ctx->merge_slots, ctx->merge_slots * 13u / 16u, ctx->d_clusters.as<ClusterDev>(), ro, cap,
+      counters + C_LOCAL, counters + C_TICKET_MERGE);
+  ctx->launches++;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
 // partition mode, one pass: no key read is needed to find the prefix-runs
 int tiles_from_hist(pf_ctx* ctx) {
   WidthState& N = ctx->nar;
@@ -1038,9 +1225,16 @@ extern "C" int pf_execute(pf_ctx* ctx) {
 
   // record buffers (ping-pong); the idle one later holds the run lists, so give
   // it room for n+1 run starts + n run segments (8n+4 bytes <= 8n+16)
+  bool blk = ctx->block_mode && part && ctx->use_direct && N.n_records > 0 && ctx->n_items > 0;
+  auto ensure_records = [&]() -> int {     // the record path needs the narrow ping-pong buffers
+    for (int i = 0; i < 2; ++i) {
+      TRY(dev_ensure(ctx, N.keys[i], ((size_t)N.n_records + 2) * 8));
+      TRY(dev_ensure(ctx, N.vals[i], ((size_t)N.n_records + 2) * 4));
+    }
+    return PF_OK;
+  };
+  if (!blk) TRY(ensure_records());
   for (int i = 0; i < 2; ++i) {
-    TRY(dev_ensure(ctx, N.keys[i], ((size_t)N.n_records + 2) * 8));
-    TRY(dev_ensure(ctx, N.vals[i], ((size_t)N.n_records + 2) * 4));
     TRY(dev_ensure(ctx, Wd.keys[i], ((size_t)Wd.n_records + 2) * 16));
     TRY(dev_ensure(ctx, Wd.vals[i], ((size_t)Wd.n_records + 2) * 4));
   }
@@ -1072,7 +1266,109 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   ro.key_words = ctx->Wk; ro.pattern_words = ctx->W;
   ro.cluster_pattern = ctx->d_cl_pattern.as<uint32_t>();
 
+  const uint64_t n_windows = N.n_records / (ctx->prm.canonical ? 1u : 2u);
+  ctx->used_block = false;
   for (int attempt = 0;; ++attempt) {
+    if (blk) {
+      // ---- block aggregation: kA (K1+K2+K3 grouping, no records) + kB (merge, filter, rows) ----
+      if (attempt > 12) return fail(ctx, PF_ERR_INTERNAL, "block aggregation did not converge");
+      ctx->fused = true;                    // K1 proper only emits positional records
+      TRY(launch_k1(ctx));
+      STAGE("k1_extract");
+      CU(cudaEventRecord(ctx->ev[EV_EXTRACT], st));
+      TRY(hist_width<Key128>(ctx, Wd));
+      CU(cudaEventRecord(ctx->ev[EV_HIST], st));
+      ctx->partial_cap = std::max<uint64_t>(ctx->partial_cap, std::max<uint64_t>(
+          65536, (uint64_t)(ctx->partial_ratio * 1.3 * (double)n_windows) + 4096));
+      ctx->partial_cap = std::min<uint64_t>(ctx->partial_cap, 0xfffffff0ull);
+      const uint32_t WP = (ctx->W + 3u) & ~3u;
+      TRY(dev_ensure(ctx, ctx->d_slab_keys, ctx->partial_cap * 8));
+      TRY(dev_ensure(ctx, ctx->d_slab_rows, ctx->partial_cap * WP * 4));
+      CU(cudaMemsetAsync(counters + C_LOCAL, 0, LC_COUNT * 4, st));
+      TRY(launch_block_aggregate(ctx, nullptr, ctx->n_items, ctx->blk_slots, ctx->d_rescue[0].as<uint32_t>()));
+      STAGE("kA_block_aggregate");
+      TRY(passes_width<Key128>(ctx, Wd, C_TICKET_W));
+      TRY(mark_width<Key128>(ctx, Wd, C_TICKET_MARK_W, C_RUNS_W, false));
+      // blocks holding more distinct k-mers than the table takes are rerun with a table twice
+      // the size, then four times, ...; past the largest table the batch takes the record path
+      CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      TRY(check_device_error(ctx));
+      bool too_big = false;
+      {
+        uint32_t slots = ctx->blk_slots;
+        int cur = 0;
+        const uint32_t first_rescue = hcnt[C_LOCAL + LC_RESCUE];
+        while (hcnt[C_LOCAL + LC_TABLE_OVERFLOW] == 1u) {
+          const uint32_t n_resc = hcnt[C_LOCAL + LC_RESCUE];
+          if (slots >= 8192u || blk_smem_bytes(slots * 2u, ctx->W) > kBlkMaxSmem) { too_big = true; break; }
+          slots *= 2;
+          CU(cudaMemsetAsync(counters + C_LOCAL + LC_TABLE_OVERFLOW, 0, 4, st));
+          CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));
+          TRY(launch_block_aggregate(ctx, ctx->d_rescue[cur].as<uint32_t>(), n_resc, slots,
+                                     ctx->d_rescue[cur ^ 1].as<uint32_t>()));
+          cur ^= 1;
+          CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+          CU(cudaStreamSynchronize(st));
+        }
+        // many rescued blocks: start the next batches with the larger table
+        if (!too_big && first_rescue > ctx->n_items / 8u && ctx->blk_slots < 8192u &&
+            blk_smem_bytes(ctx->blk_slots * 2u, ctx->W) <= kBlkMaxSmem)
+          ctx->blk_slots *= 2;
+      }
+      CU(cudaEventRecord(ctx->ev[EV_SORT], st));
+      CU(cudaEventRecord(ctx->ev[EV_MARK], st));
+      if (too_big) {
+        // a position block holds more distinct k-mers than the largest table: shorter blocks,
+        // then the record path (for this batch; for good after the second time)
+        if (ctx->block_windows > (uint32_t)kBlkRun) {
+          ctx->block_windows /= 2;
+          TRY(plan_blocks(ctx));
+        } else {
+          blk = false;
+          if (++ctx->block_fallbacks >= 2) ctx->block_mode = false;
+          TRY(ensure_records());
+        }
+        continue;
+      }
+      if (hcnt[C_LOCAL + LC_PARTIAL_OVERFLOW]) {
+        ctx->partial_cap = (uint64_t)hcnt[C_LOCAL + LC_PARTIALS] + 4096;
+        continue;
+      }
+      ro.cluster = ctx->d_row_cluster.as<uint32_t>();
+      ro.count = ctx->d_row_count.as<uint32_t>();
+      ro.cand = ctx->d_cand.as<uint32_t>();
+      ro.kmer = ctx->d_row_kmer.as<uint64_t>();
+      ro.row_base = 0;
+      TRY(launch_block_merge(ctx, ro));
+      STAGE("kB_merge");
+      CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      TRY(check_device_error(ctx));
+      ctx->rescued_last = 0;
+      ctx->cp.n = ctx->cp_base + hcnt[C_NEW_CP];
+      N.n_runs = 0;
+      Wd.n_runs = Wd.n_records ? hcnt[C_RUNS_W] : 0;
+      const uint32_t tov = hcnt[C_LOCAL + LC_TABLE_OVERFLOW];
+      if (hcnt[C_LOCAL + LC_PARTIAL_OVERFLOW]) {
+        ctx->partial_cap = (uint64_t)hcnt[C_LOCAL + LC_PARTIALS] + 4096;
+        continue;
+      }
+      if (tov == 2u) {          // a merge group outgrew its table: smaller groups
+        if (ctx->merge_target <= 16u) return fail(ctx, PF_ERR_INTERNAL, "merge group overflow at the smallest group size");
+        ctx->merge_target = std::max<uint32_t>(16u, ctx->merge_target / 2);
+        continue;
+      }
+      if (hcnt[C_LOCAL + LC_ROW_OVERFLOW]) {
+        ctx->row_cap = (uint64_t)hcnt[C_LOCAL + LC_ROWS] + 1024;
+        TRY(ensure_rows(ctx, ctx->row_cap, ctx->row_cap, false));
+        continue;
+      }
+      ctx->used_block = true;
+      ctx->partials_last = hcnt[C_LOCAL + LC_PARTIALS];
+      if (n_windows) ctx->partial_ratio = std::max(1e-4, (double)ctx->partials_last / (double)n_windows);
+      break;
+    }
     // ---- K1 + K2 -------------------------------------------------------------
     ctx->fused = part && ctx->use_direct && N.passes <= 2 && !(ctx->prm.debug_flags & 1u);
     TRY(launch_k1(ctx));

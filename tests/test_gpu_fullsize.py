@@ -64,17 +64,22 @@ def test_full_size_properties(full_run):
     assert np.array_equal(r["new_cluster_patterns"][r["cluster_pattern"].astype(np.int64)], hb.presence)
 
 
-def test_full_size_engines_agree(full_run):
-    """Partition mode (fused, unstable, hashed) and the plain full-sort engine produce
-    the same multiset of rows (checksum of checksums)."""
+@pytest.mark.parametrize("engine", ["records", "fullsort"])
+def test_full_size_engines_agree(full_run, engine):
+    """The block-aggregation engine (default), the record path in partition mode (fused,
+    unstable, hashed) and the plain full-sort engine produce the same multiset of rows
+    (checksum of checksums)."""
     hb, r, st = full_run
+    assert st["engine"] == 2
     W = (S + 31) // 32
-    ctx = capi.Context(K, S, maf=0.01, mode=1)
+    ctx = capi.Context(K, S, maf=0.01, mode=1 if engine == "fullsort" else 0, debug_flags=2)
     ctx.submit(hb)
     r2 = ctx.collect()
     st2 = ctx.stats()
     ctx.close()
+    assert st2["engine"] == (1 if engine == "fullsort" else 0)
     assert st2["rows"] == st["rows"] and st2["kmer_patterns"] == st["kmer_patterns"]
+    assert st2["unique_kmers"] == st["unique_kmers"]
     assert _checksum(r, W) == _checksum(r2, W)
 
 

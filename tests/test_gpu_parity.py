@@ -14,6 +14,12 @@ from test_oracle_c import _items
 
 pytestmark = pytest.mark.gpu
 
+# engines of the library (pf_stats.engine): block aggregation (default for S <= 1024),
+# records + partition mode, records + full sort
+ENGINES = {"block": dict(mode=0, debug_flags=0),
+           "records": dict(mode=0, debug_flags=2),
+           "fullsort": dict(mode=1, debug_flags=2)}
+
 
 def _render_gpu(out, S, k, consider_missing, canonical):
     res = dict(out)
@@ -25,7 +31,7 @@ def _render_gpu(out, S, k, consider_missing, canonical):
     return got
 
 
-@pytest.mark.parametrize("engine", [0, 1], ids=["partition", "fullsort"])
+@pytest.mark.parametrize("engine", sorted(ENGINES))
 @pytest.mark.parametrize("mode", sorted(helpers.modes()))
 def test_fixture_modes_match_reference_goldens(mode, engine):
     kw = helpers.cli_kwargs(helpers.modes()[mode])
@@ -37,7 +43,7 @@ def test_fixture_modes_match_reference_goldens(mode, engine):
         os.chdir(cwd)
     out = gpu_util.run_gpu(items, stroi, S, kw["k"], not kw["non_canonical"],
                            kw["consider_missing"], kw["no_filter"], kw["maf"],
-                           batch_clusters=3, mode=engine)
+                           batch_clusters=3, **ENGINES[engine])
     got = _render_gpu(out, S, kw["k"], kw["consider_missing"],
                       not kw["non_canonical"])
     for name in helpers.FILES:
@@ -115,14 +121,18 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("engine", [0, 1], ids=["partition", "fullsort"])
+@pytest.mark.parametrize("engine", sorted(ENGINES))
 @pytest.mark.parametrize("case", CASES, ids=[str(i) for i in range(len(CASES))])
 def test_random_clusters_match_oracle(case, engine):
     S, k, nc, L, canon, cm, nf, maf, amb, sb, bc = case
     rng = np.random.default_rng(1000 + S * 7 + k)
     items, stroi = _random_items(rng, S, k, nc, L, amb)
-    _compare_with_oracle(items, stroi, S, k, canon, cm, nf, maf,
-                         batch_clusters=bc, sort_bits=sb, mode=engine)
+    out, _ = _compare_with_oracle(items, stroi, S, k, canon, cm, nf, maf,
+                                  batch_clusters=bc, sort_bits=sb, **ENGINES[engine])
+    if engine == "block" and not (k == 32 and not canon):
+        assert out["stats"]["engine"] == 2
+    else:
+        assert out["stats"]["engine"] == (1 if engine == "fullsort" else 0)
 
 
 @pytest.mark.parametrize("case", CASES[:6], ids=[str(i) for i in range(6)])
@@ -132,7 +142,7 @@ def test_unfused_partition_path(case):
     rng = np.random.default_rng(1000 + S * 7 + k)
     items, stroi = _random_items(rng, S, k, nc, L, amb)
     _compare_with_oracle(items, stroi, S, k, canon, cm, nf, maf,
-                         batch_clusters=bc, sort_bits=sb, mode=0, debug_flags=1)
+                         batch_clusters=bc, sort_bits=sb, mode=0, debug_flags=3)
 
 
 def test_partition_direct_rescue_launch():
@@ -148,7 +158,7 @@ def test_partition_direct_rescue_launch():
         cluster[s] = [ref_port.CutSeq(q, q.translate(comp), s + "_f", "c", 1, 20000, 1, 0)]
     items = [(cluster, "mid", np.ones(S, dtype=int))]
     out, want = _compare_with_oracle(items, set(), S, 31, True, False, False, 0.0,
-                                     batch_clusters=1, mode=0)
+                                     batch_clusters=1, mode=0, debug_flags=2)
     assert out["stats"]["sort_passes"] == 1
 
 
@@ -173,8 +183,83 @@ def test_partition_mode_escalates_on_table_overflow():
         cluster[s] = [ref_port.CutSeq(q, q.translate(comp), s + "_f", "c", 1, 300000, 1, 0)]
     items = [(cluster, "big", np.ones(S, dtype=int))]
     out, want = _compare_with_oracle(items, set(), S, 31, True, False, False, 0.0,
-                                     batch_clusters=1, sort_bits=8, mode=0)
+                                     batch_clusters=1, sort_bits=8, mode=0, debug_flags=2)
     assert out["stats"]["sort_passes"] >= 2
+
+
+def _unrelated_cluster(rng, S, L, name="u"):
+    """Every sequence is independent random DNA: no k-mer is shared, so a position
+    block holds 16 * S distinct k-mers."""
+    comp = str.maketrans("ACGT", "TGCA")
+    names = [f"g{i:04d}" for i in range(S)]
+    cluster = {}
+    for s in names:
+        q = "".join(rng.choice(list("ACGT"), L))
+        cluster[s] = [ref_port.CutSeq(q, q.translate(comp), s + "_f", "c", 1, L, 1, 0)]
+    return (cluster, name, np.ones(S, dtype=int))
+
+
+def test_block_engine_grows_its_table():
+    """16 * 150 = 2400 distinct k-mers per block: the first table (256 slots) overflows,
+    the overflowing blocks are rerun with tables of 512 ... 4096 slots until they fit, and
+    the batch stays on the block engine."""
+    rng = np.random.default_rng(11)
+    items = [_unrelated_cluster(rng, 150, 120)]
+    out, want = _compare_with_oracle(items, set(), 150, 31, True, False, False, 0.0,
+                                     batch_clusters=1)
+    assert out["stats"]["engine"] == 2
+    assert out["stats"]["block_slots"] >= 512     # every block overflowed: next batch starts larger
+
+
+def test_block_engine_falls_back_to_records():
+    """16 * 700 distinct k-mers per block exceed the largest table: the batch is rerun
+    through the record path and is still exact."""
+    rng = np.random.default_rng(12)
+    items = [_unrelated_cluster(rng, 700, 80)]
+    out, want = _compare_with_oracle(items, set(), 700, 31, True, False, False, 0.0,
+                                     batch_clusters=1)
+    assert out["stats"]["engine"] == 0
+
+
+def test_block_engine_merges_misaligned_copies():
+    """Indels, shifted starts and paralogs put the same k-mer into different position
+    blocks of different sequences: kB must merge the partial bitsets by key."""
+    rng = np.random.default_rng(13)
+    comp = str.maketrans("ACGT", "TGCA")
+    S, k = 90, 31
+    names = [f"g{i:04d}" for i in range(S)]
+    items = []
+    for c in range(4):
+        anc = rng.choice(list("ACGT"), 700)
+        presab = np.zeros(S, dtype=int)
+        cluster = {}
+        for i, s in enumerate(names):
+            if rng.random() < 0.15:
+                cluster[s] = []
+                continue
+            presab[i] = 1
+            lst = []
+            for _ in range(3 if rng.random() < 0.1 else 1):
+                q = list(anc[int(rng.integers(0, 40)):700 - int(rng.integers(0, 40))])
+                for _ in range(int(rng.integers(0, 4))):        # indels
+                    p = int(rng.integers(0, len(q)))
+                    if rng.random() < 0.5:
+                        del q[p:p + int(rng.integers(1, 9))]
+                    else:
+                        q[p:p] = list(rng.choice(list("ACGT"), int(rng.integers(1, 9))))
+                m = rng.random(len(q)) < 0.003
+                q = np.array(q)
+                q[m] = rng.choice(list("ACGT"), int(m.sum()))
+                q = "".join(q)
+                lst.append(ref_port.CutSeq(q, q.translate(comp), s + "_f", "ctg", 11,
+                                           10 + len(q), int(rng.choice([1, -1])), 3))
+            cluster[s] = lst
+        items.append((cluster, f"mis{c}", presab))
+    stroi = set(names[:5])
+    for canon in (True, False):
+        out, want = _compare_with_oracle(items, stroi, S, k, canon, True, False, 0.02,
+                                         batch_clusters=3)
+        assert out["stats"]["engine"] == 2
 
 
 def test_empty_and_ragged_batches():
