@@ -5,25 +5,22 @@
 // every sequence of the cluster hold only a few hundred distinct k-mers between
 // them (one per haplotype and position), however many samples there are.
 //
-//   kA_block_aggregate  one CTA per (cluster, position block).  Every thread walks
-//                       runs of 16 consecutive windows of one sequence with a ROLLING
-//                       forward / reverse-complement k-mer (two funnel shifts each per
-//                       window instead of a fresh extraction), looks the canonical
-//                       k-mer up in a shared-memory open-addressing table and ORs the
-//                       sample's bit into that k-mer's W-word bitset, also in shared
-//                       memory.  Lanes of a warp work on DIFFERENT sequences at the
-//                       SAME positions: their table probes hit the same slot (a
-//                       broadcast) and their bits fall into different words.  The CTA
-//                       ends by writing its distinct k-mers and bitsets ("partials")
-//                       to its own slab in HBM: ~1/30 of the bytes the records would
-//                       have taken, written once.
-//   kB_merge            a k-mer can start in two blocks (indels, clamped flanks,
-//                       paralogs), so partials of one cluster are merged by FULL key:
-//                       the key space of the cluster is cut into G hash groups small
-//                       enough for one CTA; CTA (cluster, g) scans all partial keys of
-//                       the cluster (L2-resident), keeps those of its group, ORs their
-//                       bitsets in shared memory, then counts, applies the integer MAF
-//                       window and emits rows exactly like k3_local_direct.
+//   kA_block_aggregate  one CTA per (cluster, run of 16 window positions).
+//                       Level 1: every sequence contributes the R = k + 15 bases its 16
+//                       windows cover as ONE 128-bit chunk; identical chunks (same haplotype)
+//                       meet in a shared-memory chunk table and only OR one sample bit there:
+//                       ~25 instructions per sequence and run instead of per window.
+//                       Level 2: the few dozen DISTINCT chunks are cut into their 16 k-mers
+//                       (forward / reverse complement / canonical), each k-mer is looked up in
+//                       a shared-memory open-addressing table and takes the chunk's whole
+//                       W-word sample bitset.  The CTA ends by writing its distinct k-mers and
+//                       bitsets ("partials") to a slab in HBM: ~1/30 of the bytes the records
+//                       would have taken, written once.
+//   kB1/kB2/kB3         a k-mer can start in two runs (indels, clamped flanks, paralogs), so
+//                       the partials of one cluster are merged by FULL key in a per-cluster
+//                       open-addressing table in global memory: the first partial of a key
+//                       owns it, later ones OR their bitset into the owner's; owners are then
+//                       counted, filtered with the integer MAF window and emitted as rows.
 //
 // Exact for any input: nothing depends on the sequences being aligned — alignment
 // only decides how few partials there are.  A block holding more distinct k-mers
@@ -58,6 +55,10 @@ struct ClusterBlk {        // 16 bytes
 constexpr int kBlkThreads = 256;
 constexpr int kBlkWarps = kBlkThreads / 32;
 constexpr int kBlkRun = 16;                       // windows per task
+#ifndef PF_BLK_MIN_CTAS
+#define PF_BLK_MIN_CTAS 5
+#endif
+constexpr int kBlkMinCtas = PF_BLK_MIN_CTAS;      // register budget of kA: 65536 / (256 * n)
 constexpr uint32_t kBlkOverflow = 0xffffffffu;    // slab count of a block that did not fit
 
 __global__ void plan_seq_lite(const SeqDev* __restrict__ seqs, uint32_t n, SeqLite* __restrict__ out) {
@@ -107,9 +108,9 @@ __global__ void plan_cluster_blocks(const SeqDev* __restrict__ seqs, uint32_t n_
 // ---------------------------------------------------------------------------
 // shared-memory table
 // ---------------------------------------------------------------------------
-struct BlkHead {           // 32 bytes, then keys[slots], list[slots] (u16), pool[(slots + 1) * WS]
+struct BlkHead {           // 64 bytes, then keys[slots], list[slots] (u16), pool[(slots + 1) * WS]
                            // (row `slots` is a scratch row: lookups of a full table land there)
-  uint32_t n_unique, overflow, n_pass, row_base, ok, work, pad[2];
+  uint32_t n_unique, overflow, n_pass, row_base, ok, work, pad[10];
 };
 __host__ __device__ inline uint32_t blk_smem_bytes(uint32_t slots, uint32_t W) {
   return (uint32_t)sizeof(BlkHead) + slots * 8u + slots * 2u + (slots + 1u) * (W | 1u) * 4u;
@@ -130,6 +131,9 @@ __device__ __forceinline__ BlkView blk_view(unsigned char* raw, uint32_t slots) 
   v.mask = slots - 1u;
   v.shift = 32u - (uint32_t)__popc(v.mask);
   return v;
+}
+__device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
+  return *reinterpret_cast<const volatile uint32_t*>(p);
 }
 __device__ __forceinline__ uint32_t blk_hash(uint32_t kh, uint32_t kl, uint32_t shift) {
   return ((kl ^ (kh * 0x85ebca6bu)) * 0x9e3779b1u) >> shift;
@@ -182,13 +186,137 @@ struct BlkPlan {
   const uint32_t* item_cluster;  // [n_items] inverse of item_base
   const ClusterBlk* cblk;
   uint32_t n_clusters;
-  uint32_t block_windows;        // B, multiple of kBlkRun, kBlkRun .. kBlkRun * kBlkWarps
-  uint32_t slots, max_unique;    // table size of kA (power of two), fill limit
+  uint32_t block_windows;        // B = kBlkRun
+  uint32_t slots, cslots;        // k-mer table / chunk table sizes of kA (powers of two)
   uint32_t W, WP;                // bitset words, slab row stride (W rounded up to 4)
 };
 
-template <bool CANON, bool KHI /* k > 16 */>
-__global__ void __launch_bounds__(kBlkThreads)
+// Shared memory of kA.  Both tables hand out DENSE row ids on insertion and the inserting
+// thread clears its row before publishing the id, so nothing but the (small) key / state
+// arrays is initialised per block and the epilogue needs no compaction pass.
+//
+// chunk table: the R = k + 15 bases that the 16 windows of a run cover, as a 128-bit key
+//   (top-aligned).  Sequences of a cluster are copies of a few haplotypes, so the ~500
+//   sequences of a run collapse into a few dozen distinct chunks; only those are cut into
+//   k-mers.  A slot's state word goes empty -> locked -> (full | chunk id).
+// k-mer table: 64-bit keys claimed with one CAS; rowid[slot] is published afterwards
+//   (0xffff = not yet), readers of a freshly claimed slot spin for those few cycles.
+constexpr uint32_t kChunkEmpty = 0u, kChunkLocked = 1u, kChunkFull = 0x80000000u;
+struct ARunView {
+  BlkHead* h;              // n_unique = k-mer rows handed out, work = chunk ids handed out
+  uint64_t* keys;          // [slots]
+  uint64_t* rkey;          // [cap + 1]   key of row id
+  uint64_t* ckhi;          // [ccap]
+  uint64_t* cklo;          // [ccap]
+  uint32_t* cstate;        // [cslots]
+  uint32_t* pool;          // [(cap + 1) * WS]   row `cap` takes the ORs of an overflowing block
+  uint32_t* crows;         // [ccap * WS]
+  uint16_t* rowid;         // [slots]
+  uint32_t mask, shift, cmask, cshift, cap, ccap;
+};
+__host__ __device__ inline uint32_t blkA_cap(uint32_t slots) { return slots * 5u / 8u; }
+__host__ __device__ inline uint32_t blkA_ccap(uint32_t cslots) { return cslots * 3u / 4u; }
+__host__ __device__ inline uint32_t blkA_smem_bytes(uint32_t slots, uint32_t cslots, uint32_t W) {
+  const uint32_t cap = blkA_cap(slots), ccap = blkA_ccap(cslots), WS = W | 1u;
+  return (uint32_t)sizeof(BlkHead) + slots * 8u + (cap + 1u) * 8u + ccap * 16u + cslots * 4u +
+         (cap + 1u) * WS * 4u + ccap * WS * 4u + slots * 2u + 16u;
+}
+__device__ __forceinline__ ARunView arun_view(unsigned char* raw, uint32_t slots, uint32_t cslots, uint32_t W) {
+  ARunView a;
+  const uint32_t WS = W | 1u;
+  a.cap = blkA_cap(slots);
+  a.ccap = blkA_ccap(cslots);
+  a.h = reinterpret_cast<BlkHead*>(raw);
+  a.keys = reinterpret_cast<uint64_t*>(raw + sizeof(BlkHead));
+  a.rkey = a.keys + slots;
+  a.ckhi = a.rkey + (a.cap + 1u);
+  a.cklo = a.ckhi + a.ccap;
+  a.cstate = reinterpret_cast<uint32_t*>(a.cklo + a.ccap);
+  a.pool = a.cstate + cslots;
+  a.crows = a.pool + (a.cap + 1u) * WS;
+  a.rowid = reinterpret_cast<uint16_t*>(a.crows + a.ccap * WS);
+  a.mask = slots - 1u;
+  a.shift = 32u - (uint32_t)__popc(a.mask);
+  a.cmask = cslots - 1u;
+  a.cshift = 32u - (uint32_t)__popc(a.cmask);
+  return a;
+}
+// chunk id of (hi, lo); 0xffffffff if the chunk table is full (the caller then cuts the run
+// into k-mers itself)
+__device__ __noinline__ uint32_t chunk_find_or_insert(const ARunView a, uint64_t hi, uint64_t lo, uint32_t WS) {
+  const uint64_t m = (hi ^ (hi >> 29)) * 0x9e3779b97f4a7c15ULL + (lo ^ (lo >> 31)) * 0xc2b2ae3d27d4eb4fULL;
+  uint32_t s = (uint32_t)(m >> 32) >> a.cshift;
+  uint32_t spins = 0;
+  for (uint32_t probes = 0; probes <= a.cmask;) {
+    const uint32_t st = ld_volatile_shared(&a.cstate[s]);
+    if (st & kChunkFull) {
+      const uint32_t id = st & 0xffffu;
+      if (*reinterpret_cast<const volatile uint64_t*>(&a.ckhi[id]) == hi &&
+          *reinterpret_cast<const volatile uint64_t*>(&a.cklo[id]) == lo)
+        return id;
+      s = (s + 1u) & a.cmask;
+      ++probes;
+      continue;
+    }
+    if (st == kChunkEmpty) {
+      if (atomicCAS(&a.cstate[s], kChunkEmpty, kChunkLocked) == kChunkEmpty) {
+        const uint32_t id = atomicAdd(&a.h->work, 1u);
+        if (id >= a.ccap) {                                   // no row left: give the slot back
+          *reinterpret_cast<volatile uint32_t*>(&a.cstate[s]) = kChunkEmpty;
+          return 0xffffffffu;
+        }
+        uint32_t* row = a.crows + id * WS;
+        for (uint32_t w = 0; w < WS; ++w) row[w] = 0u;
+        *reinterpret_cast<volatile uint64_t*>(&a.ckhi[id]) = hi;
+        *reinterpret_cast<volatile uint64_t*>(&a.cklo[id]) = lo;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint32_t*>(&a.cstate[s]) = kChunkFull | id;
+        return id;
+      }
+      continue;
+    }
+    if (++spins > (1u << 14)) break;          // locked: its owner publishes it in a few cycles
+    __nanosleep(20);                          // (lets the owner run if it is a lane of this warp)
+  }
+  return 0xffffffffu;
+}
+// row id of a k-mer (insert if new); a.cap = the scratch row when the block overflows
+__device__ __noinline__ uint32_t kmer_row_slow(const ARunView a, uint64_t key, uint32_t h, uint32_t WS) {
+  const uint32_t limit = min(a.mask, 96u);
+  bool found = false;
+  for (uint32_t probes = 0; probes < limit; ++probes) {
+    uint64_t cur = *reinterpret_cast<const volatile uint64_t*>(&a.keys[h]);
+    if (cur == ~0ull) {
+      cur = atomicCAS(reinterpret_cast<unsigned long long*>(&a.keys[h]), ~0ull, (unsigned long long)key);
+      if (cur == ~0ull) {                                     // this thread owns the new slot
+        uint32_t id = atomicAdd(&a.h->n_unique, 1u);
+        if (id >= a.cap) { a.h->overflow = 1u; id = a.cap; }
+        uint32_t* row = a.pool + id * WS;
+        for (uint32_t w = 0; w < WS; ++w) row[w] = 0u;
+        a.rkey[id] = key;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint16_t*>(&a.rowid[h]) = (uint16_t)id;
+        return id;
+      }
+    }
+    if (cur == key) { found = true; break; }
+    h = (h + 1u) & a.mask;
+  }
+  if (!found) { a.h->overflow = 1u; return a.cap; }
+  for (uint32_t spins = 0; spins < (1u << 14); ++spins) {
+    const uint32_t id = *reinterpret_cast<const volatile uint16_t*>(&a.rowid[h]);
+    if (id != 0xffffu) return id;
+    __nanosleep(20);                          // (lets the owner run if it is a lane of this warp)
+  }
+  a.h->overflow = 1u;
+  return a.cap;
+}
+
+#ifndef PF_KA_MIN_CTAS
+#define PF_KA_MIN_CTAS 4
+#endif
+template <bool CANON>
+__global__ void __launch_bounds__(kBlkThreads, PF_KA_MIN_CTAS)
 kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restrict__ ambbits,
                    const SeqLite* __restrict__ seqs, BlkPlan plan, int k,
                    uint64_t* __restrict__ slab_keys, uint32_t* __restrict__ slab_rows,
@@ -197,144 +325,100 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
                    const uint32_t* __restrict__ item_list /* null: item = blockIdx.x */,
                    uint32_t* __restrict__ rescue_items /* out: items whose table overflowed */) {
   extern __shared__ __align__(16) unsigned char blk_raw[];
-  const BlkView v = blk_view(blk_raw, plan.slots);
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t W = plan.W, WS = W | 1u;
+  const ARunView a = arun_view(blk_raw, plan.slots, plan.cslots, W);
+  const uint32_t tid = threadIdx.x;
   const uint32_t item = item_list ? item_list[blockIdx.x] : blockIdx.x;
 
   const uint32_t c = plan.item_cluster[item];
   const ClusterBlk cb = plan.cblk[c];
-  const uint32_t p0 = (item - plan.item_base[c]) * plan.block_windows;
-  const uint32_t W = plan.W, WS = W | 1u;
+  const uint32_t s_rel = (item - plan.item_base[c]) * (uint32_t)kBlkRun;   // first window of the run
 
-  for (uint32_t i = tid; i < plan.slots; i += kBlkThreads) v.keys[i] = ~0ull;
-  for (uint32_t i = tid; i < plan.slots * WS; i += kBlkThreads) v.pool[i] = 0;
-  if (tid == 0) { v.h->n_unique = 0; v.h->overflow = 0; v.h->n_pass = 0; }
+  for (uint32_t i = tid; i < plan.slots; i += kBlkThreads) { a.keys[i] = ~0ull; a.rowid[i] = 0xffffu; }
+  for (uint32_t i = tid; i < plan.cslots; i += kBlkThreads) a.cstate[i] = kChunkEmpty;
+  if (tid == 0) { a.h->n_unique = 0; a.h->overflow = 0; a.h->work = 0; }
   __syncthreads();
 
-  // task = (sequence, run of 16 windows).  Warp -> run of the block and phase over the
-  // sequences; lane -> a contiguous chunk of the cluster's sequences (sample order), so
-  // the 32 lanes sit in 32 different sample ranges at the same positions.
-  const uint32_t n_sub = plan.block_windows / kBlkRun;
-  const uint32_t sub = warp % n_sub, phase = warp / n_sub, n_phase = max(1u, (uint32_t)kBlkWarps / n_sub);
-  const uint32_t chunk = (cb.n_seqs + 31u) >> 5;
-  const uint32_t s_rel = p0 + sub * kBlkRun;                  // first window of the run
   const uint32_t sh64 = 64u - 2u * (uint32_t)k;
-  const uint32_t mask_h = KHI ? (k == 32 ? 0xffffffffu : ((1u << (2 * k - 32)) - 1u)) : 0u;
-  const uint32_t mask_l = KHI ? 0xffffffffu : (k == 16 ? 0xffffffffu : ((1u << (2 * k)) - 1u));
-  const uint32_t hshift = v.shift;
-  const uint32_t WS4 = WS * 4u;
+  const uint32_t R = (uint32_t)k + (uint32_t)kBlkRun - 1u;      // bases a full run covers (<= 47)
+  // top-aligned masks of the R bases
+  const uint64_t cm_hi = R >= 32u ? ~0ull : (~0ull << (64u - 2u * R));
+  const uint64_t cm_lo = R > 32u ? (~0ull << (64u - 2u * (R - 32u))) : 0ull;
 
-  if (warp < n_sub * n_phase) {
-    for (uint32_t j = phase; j < chunk; j += n_phase) {
-      const uint32_t si = lane * chunk + j;
-      if (si >= cb.n_seqs) continue;
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(seqs + cb.seq_start + si));
-      const uint32_t len = raw.y;
-      if (len < (uint32_t)k) continue;
-      const uint32_t nwin = len - (uint32_t)k + 1u;
-      if (s_rel >= nwin) continue;
-      const uint32_t nv = min((uint32_t)kBlkRun, nwin - s_rel);
-      const uint32_t sample = raw.z & 0x7fffffffu;
-      const bool amb = (raw.z >> 31) != 0u;
-      unsigned char* row_word = reinterpret_cast<unsigned char*>(v.pool + (sample >> 5));
-      const uint32_t bit = 1u << (sample & 31u);
+  // one k-mer (in the low 2k bits) -> row, OR `nw` words starting at src into it
+  auto put_bits = [&](uint64_t key, const uint32_t* src, uint32_t first_word, uint32_t nw) {
+    const uint32_t h = blk_hash((uint32_t)(key >> 32), (uint32_t)key, a.shift);
+    uint32_t id = 0xffffu;
+    if (*reinterpret_cast<const volatile uint64_t*>(&a.keys[h]) == key)
+      id = *reinterpret_cast<const volatile uint16_t*>(&a.rowid[h]);
+    if (id == 0xffffu) id = kmer_row_slow(a, key, h, WS);
+    uint32_t* dst = a.pool + id * WS + first_word;
+    for (uint32_t w = 0; w < nw; ++w) {
+      const uint32_t x = src[w];
+      if (x) atomicOr(dst + w, x);
+    }
+  };
+  auto put_kmer = [&](uint64_t fwd, const uint32_t* src, uint32_t first_word, uint32_t nw) {
+    const uint64_t rc = revcomp2(fwd, k);
+    if (CANON) put_bits(rc < fwd ? rc : fwd, src, first_word, nw);
+    else { put_bits(fwd, src, first_word, nw); put_bits(rc, src, first_word, nw); }
+  };
 
-      // three words cover the run: 16 + k - 1 <= 47 bases from an offset < 32
-      const uint64_t* w = bases + raw.x + (s_rel >> 5);
-      const uint64_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
-      const uint32_t o0 = s_rel & 31u;
-      const uint64_t x = (w0 << (2u * o0)) | ((w1 >> 1) >> (63u - 2u * o0));
-      const uint64_t f0 = x >> sh64;
-      uint32_t fh = (uint32_t)(f0 >> 32), fl = (uint32_t)f0;
-      uint64_t r0 = __brevll(~f0);                            // left-aligned reverse complement (+ junk below)
-      r0 = ((r0 & 0xaaaaaaaaaaaaaaaaULL) >> 1) | ((r0 & 0x5555555555555555ULL) << 1);
-      uint32_t rh = (uint32_t)(r0 >> 32), rl = (uint32_t)r0;
-      // the 16 bases that follow the first window, next base in the top two bits
-      const uint32_t off = o0 + (uint32_t)k;
-      const uint64_t pa = off >= 32u ? w1 : w0, pb = off >= 32u ? w2 : w1;
-      const uint32_t o1 = off & 31u;
-      uint32_t cs = (uint32_t)(((pa << (2u * o1)) | ((pb >> 1) >> (63u - 2u * o1))) >> 32);
-      // the same 16 bases complemented and in reverse order: next base in the low two bits
-      uint32_t rs = __brev(~cs);
-      rs = ((rs & 0xaaaaaaaau) >> 1) | ((rs & 0x55555555u) << 1);
-
-      auto roll = [&]() {
-        fh = __funnelshift_l(fl, fh, 2) & mask_h;
-        fl = __funnelshift_l(cs, fl, 2);
-        if (!KHI) fl &= mask_l;
-        cs <<= 2;
-        rl = __funnelshift_r(rl, rh, 2);
-        rh = __funnelshift_r(rh, rs, 2);          // complement of the entering base on top
-        rs >>= 2;
-      };
-      auto rc_right = [&]() -> uint64_t {
-        if (KHI) return ((uint64_t)(rh >> sh64) << 32) | __funnelshift_r(rl, rh, sh64);
-        return (uint64_t)(rh >> (sh64 - 32u));
-      };
-      auto put = [&](uint64_t key) {
-        uint32_t h = blk_hash((uint32_t)(key >> 32), (uint32_t)key, hshift);
-        const uint64_t kk = *reinterpret_cast<const volatile uint64_t*>(&v.keys[h]);
-        if (kk != key) h = blk_resolve(v, key, h, kk);
-        atomicOr(reinterpret_cast<uint32_t*>(row_word + h * WS4), bit);
-      };
-
-      if (nv == (uint32_t)kBlkRun && !amb) {
-        // fast path: 4 windows at a time so that the probes of a batch overlap
-#pragma unroll
-        for (int q0 = 0; q0 < kBlkRun; q0 += 4) {
-          uint64_t key[4], key2[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const uint64_t f = ((uint64_t)fh << 32) | fl;
-            const uint64_t r = rc_right();
-            if (CANON) key[q] = r < f ? r : f;
-            else { key[q] = f; key2[q] = r; }
-            roll();
-          }
-          uint32_t h[4];
-          uint64_t kk[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            h[q] = blk_hash((uint32_t)(key[q] >> 32), (uint32_t)key[q], hshift);
-            kk[q] = *reinterpret_cast<const volatile uint64_t*>(&v.keys[h[q]]);
-          }
-          if ((kk[0] != key[0]) | (kk[1] != key[1]) | (kk[2] != key[2]) | (kk[3] != key[3])) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (kk[q] != key[q]) h[q] = blk_resolve(v, key[q], h[q], kk[q]);
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) atomicOr(reinterpret_cast<uint32_t*>(row_word + h[q] * WS4), bit);
-          if (!CANON) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) put(key2[q]);
-          }
+  // ---- phase 1: every sequence's run -> chunk table (or, for ragged / ambiguous runs and a
+  //      full chunk table, straight into the k-mer table) ------------------------------------
+  for (uint32_t si = tid; si < cb.n_seqs; si += kBlkThreads) {
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(seqs + cb.seq_start + si));
+    const uint32_t len = raw.y;
+    if (len < (uint32_t)k) continue;
+    const uint32_t nwin = len - (uint32_t)k + 1u;
+    if (s_rel >= nwin) continue;
+    const uint32_t nv = min((uint32_t)kBlkRun, nwin - s_rel);
+    const uint32_t sample = raw.z & 0x7fffffffu;
+    const bool amb = (raw.z >> 31) != 0u;
+    const uint32_t wofs = sample >> 5, bit = 1u << (sample & 31u);
+    // three words cover the run: 16 + k - 1 <= 47 bases from an offset < 32
+    const uint64_t* w = bases + raw.x + (s_rel >> 5);
+    const uint64_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const uint32_t o0 = s_rel & 31u;
+    uint64_t hi = w0, lo = w1;
+    if (o0) {
+      hi = (w0 << (2u * o0)) | (w1 >> (64u - 2u * o0));
+      lo = (w1 << (2u * o0)) | (w2 >> (64u - 2u * o0));
+    }
+    uint32_t cs = 0xffffffffu;
+    if (nv == (uint32_t)kBlkRun && !amb) cs = chunk_find_or_insert(a, hi & cm_hi, lo & cm_lo, WS);
+    if (cs != 0xffffffffu) {
+      atomicOr(&a.crows[cs * WS + wofs], bit);
+    } else {
+      const uint32_t* ab = amb ? ambbits + raw.w : nullptr;
+      for (uint32_t q = 0; q < nv; ++q) {
+        bool dead = false;
+        if (amb) {
+          const uint32_t p = s_rel + q;
+          const uint32_t wi = p >> 5, bs = p & 31u;
+          const uint64_t two = ((uint64_t)ab[wi] << 32) | (uint64_t)ab[wi + 1];
+          dead = ((two << bs) >> (64 - k)) != 0ull;
         }
-      } else {
-        const uint32_t* ab = amb ? ambbits + raw.w : nullptr;
-        for (uint32_t q = 0; q < nv; ++q) {
-          bool dead = false;
-          if (amb) {
-            const uint32_t p = s_rel + q;
-            const uint32_t wi = p >> 5, bs = p & 31u;
-            const uint64_t two = ((uint64_t)ab[wi] << 32) | (uint64_t)ab[wi + 1];
-            dead = ((two << bs) >> (64 - k)) != 0ull;
-          }
-          if (!dead) {
-            const uint64_t f = ((uint64_t)fh << 32) | fl;
-            const uint64_t r = rc_right();
-            if (CANON) put(r < f ? r : f);
-            else { put(f); put(r); }
-          }
-          roll();
+        if (!dead) {
+          const uint64_t x = q ? ((hi << (2u * q)) | (lo >> (64u - 2u * q))) : hi;
+          put_kmer(x >> sh64, &bit, wofs, 1u);
         }
       }
-      if (*reinterpret_cast<const volatile uint32_t*>(&v.h->overflow)) break;
     }
   }
   __syncthreads();
 
-  if (v.h->overflow) {
+  // ---- phase 2: distinct chunks x 16 windows -> k-mer table, whole sample bitsets at a time ----
+  const uint32_t n_chunks = min(a.h->work, a.ccap);
+  for (uint32_t p = tid; p < n_chunks * (uint32_t)kBlkRun; p += kBlkThreads) {
+    const uint32_t cs = p >> 4, q = p & 15u;
+    const uint64_t hi = a.ckhi[cs], lo = a.cklo[cs];
+    const uint64_t x = q ? ((hi << (2u * q)) | (lo >> (64u - 2u * q))) : hi;
+    put_kmer(x >> sh64, a.crows + cs * WS, 0u, W);
+  }
+  __syncthreads();
+
+  if (a.h->overflow) {
     if (tid == 0) {
       slab_count[item] = kBlkOverflow;
       slab_base[item] = 0;
@@ -343,30 +427,27 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
     }
     return;
   }
-  blk_list_occupied(v, plan.slots, &v.h->n_pass);
-  __syncthreads();
   // the slab of this block: n partial rows from a bump allocator
-  const uint32_t n = v.h->n_pass;
+  const uint32_t n = a.h->n_unique;
   if (tid == 0) {
     const uint32_t b = atomicAdd(&counters[LC_PARTIALS], n);
-    v.h->row_base = b;
-    v.h->ok = 1;
+    a.h->row_base = b;
+    a.h->ok = 1;
     slab_base[item] = b;
     slab_count[item] = n;
     if ((uint64_t)b + n > partial_capacity) {
-      v.h->ok = 0;
+      a.h->ok = 0;
       slab_count[item] = 0;
       atomicExch(&counters[LC_PARTIAL_OVERFLOW], 1u);
     }
   }
   __syncthreads();
-  if (!v.h->ok) return;
-  const size_t base = v.h->row_base;
+  if (!a.h->ok) return;
+  const size_t base = a.h->row_base;
   const uint32_t WP = plan.WP;
   for (uint32_t r = tid; r < n; r += kBlkThreads) {
-    const uint32_t h = v.list[r];
-    slab_keys[base + r] = v.keys[h];
-    const uint32_t* src = v.pool + h * WS;
+    slab_keys[base + r] = a.rkey[r];
+    const uint32_t* src = a.pool + r * WS;
     uint4* dst = reinterpret_cast<uint4*>(slab_rows + (base + r) * WP);
     for (uint32_t q = 0; q < WP; q += 4) {
       uint4 x;
@@ -380,12 +461,23 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
 }
 
 // ---------------------------------------------------------------------------
-// kB
+// kB: merge the partial rows of a cluster by k-mer, count, filter, emit rows
 // ---------------------------------------------------------------------------
-// one warp per cluster: partial rows of the cluster -> groups of about `target` distinct keys
-__global__ void plan_merge_groups(const uint32_t* __restrict__ item_base, uint32_t n_clusters,
-                                  const uint32_t* __restrict__ slab_count, uint32_t target,
-                                  uint32_t* __restrict__ n_groups) {
+// A k-mer usually has ONE partial row (its windows start in one run of every sequence);
+// indels, clamped flanks and paralogs give it a second one in a neighbouring run.  So the
+// merge is a find-or-insert of every partial key into a per-cluster open-addressing table in
+// global memory (L2-resident while the cluster's slabs are being inserted): the first row of
+// a key becomes its owner, later rows OR their bitset into the owner's (rare), and the owners
+// are counted, filtered with the cluster's integer MAF window and written out.
+struct MergeEntry {        // 16 bytes; key == ~0 marks an empty slot
+  unsigned long long key;
+  uint32_t owner;          // partial row that claimed the slot
+  uint32_t reserved;
+};
+
+// one warp per cluster: partial rows of the cluster -> table slots (load factor <= 2/3)
+__global__ void plan_merge_tables(const uint32_t* __restrict__ item_base, uint32_t n_clusters,
+                                  const uint32_t* __restrict__ slab_count, uint32_t* __restrict__ n_slots) {
   const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (c >= n_clusters) return;
   const uint32_t lane = lane_id();
@@ -396,7 +488,7 @@ __global__ void plan_merge_groups(const uint32_t* __restrict__ item_base, uint32
   }
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(kFull, p, m);
-  if (lane == 0) n_groups[c] = (p + target - 1) / target;
+  if (lane == 0) n_slots[c] = p + (p >> 1) + 2u;
 }
 
 // expand an exclusive scan into its inverse map: out[base[c] + i] = c
@@ -407,134 +499,134 @@ __global__ void plan_expand_owner(const uint32_t* __restrict__ base, uint32_t n_
   for (uint32_t i = base[c] + lane_id(); i < base[c + 1]; i += 32) out[i] = c;
 }
 
-__device__ __forceinline__ uint32_t merge_group_of(uint64_t key, uint32_t G) {
-  return __umulhi((uint32_t)(mix64(key) >> 32), G);
-}
-
-// Counting sort of the partial rows by (cluster, hash group), one warp per slab.
-// SCATTER = false: group sizes (group_cnt, zeroed by the caller).
-// SCATTER = true:  group_cnt holds the scanned offsets (cursors); part_list[cursor++] = row.
-template <bool SCATTER>
+// kB1: one warp per slab; every partial key finds or claims its slot
 __global__ void __launch_bounds__(256)
-kB0_group(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_base,
-          const uint32_t* __restrict__ slab_count, const uint32_t* __restrict__ item_cluster,
-          uint32_t n_items, const uint32_t* __restrict__ group_base,
-          uint32_t* __restrict__ group_cnt, uint32_t* __restrict__ part_list) {
+kB1_insert(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_base,
+           const uint32_t* __restrict__ slab_count, const uint32_t* __restrict__ item_cluster,
+           uint32_t n_items, const uint32_t* __restrict__ table_base /* [n_clusters + 1] */,
+           MergeEntry* __restrict__ table, uint32_t* __restrict__ pslot) {
   const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (item >= n_items) return;
   const uint32_t n = slab_count[item];
   if (n == kBlkOverflow || n == 0) return;
   const uint32_t c = item_cluster[item];
-  const uint32_t gb = group_base[c], G = group_base[c + 1] - gb;
+  const uint32_t tb = table_base[c], ts = table_base[c + 1] - tb;
   const uint32_t base = slab_base[item];
   for (uint32_t i = lane_id(); i < n; i += 32) {
-    const uint32_t g = gb + merge_group_of(slab_keys[base + i], G);
-    if (SCATTER) part_list[atomicAdd(&group_cnt[g], 1u)] = base + i;
-    else atomicAdd(&group_cnt[g], 1u);
+    const uint64_t key = slab_keys[base + i];
+    uint32_t s = __umulhi((uint32_t)(mix64(key) >> 32), ts);
+    for (;;) {
+      MergeEntry* e = table + tb + s;
+      const unsigned long long old = atomicCAS(&e->key, ~0ull, (unsigned long long)key);
+      if (old == ~0ull) { e->owner = base + i; break; }
+      if (old == key) break;
+      if (++s == ts) s = 0;
+    }
+    pslot[base + i] = tb + s;
   }
 }
 
-__global__ void __launch_bounds__(kBlkThreads)
-kB_merge(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_rows, BlkPlan plan,
-         const uint32_t* __restrict__ group_base /* [n_clusters + 1] */,
-         const uint32_t* __restrict__ group_cluster, const uint32_t* __restrict__ group_off,
-         const uint32_t* __restrict__ part_list, uint32_t merge_slots, uint32_t merge_max_unique,
-         const ClusterDev* __restrict__ clusters, RowOut out, uint32_t row_capacity,
-         uint32_t* __restrict__ counters, uint32_t* __restrict__ ticket) {
-  extern __shared__ __align__(16) unsigned char blk_raw[];
-  const BlkView v = blk_view(blk_raw, merge_slots);
-  const uint32_t tid = threadIdx.x;
-  const uint32_t W = plan.W, WS = W | 1u, WP = plan.WP;
-  const uint32_t total_work = group_base[plan.n_clusters];
+// kB2: one thread per partial row; a row that does not own its slot ORs its bitset into the
+// owner's and is marked dead (counted: distinct k-mers = partial rows - dead rows)
+__global__ void __launch_bounds__(256)
+kB2_fold(uint32_t n_partials, uint32_t* __restrict__ pslot, const MergeEntry* __restrict__ table,
+         uint32_t* __restrict__ slab_rows, uint32_t WP, uint32_t* __restrict__ counters) {
+  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_partials) return;
+  const uint32_t o = table[pslot[p]].owner;
+  if (o == p) return;
+  const uint32_t* src = slab_rows + (size_t)p * WP;
+  uint32_t* dst = slab_rows + (size_t)o * WP;
+  for (uint32_t w = 0; w < WP; ++w) {
+    const uint32_t x = src[w];
+    if (x) atomicOr(dst + w, x);
+  }
+  pslot[p] = 0xffffffffu;
+  atomicAdd(&counters[LC_RESCUE], 1u);      // (the rescue counter is free again after kA)
+}
 
-  for (;;) {
-    __syncthreads();
-    if (tid == 0) v.h->work = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t work = v.h->work;
-    if (work >= total_work) return;
-    const uint32_t c = group_cluster[work];
-    const uint32_t p0 = group_off[work], p1 = group_off[work + 1];
-    if (p0 == p1) continue;
-    const ClusterDev cl = clusters[c];
-
-    for (uint32_t i = tid; i < merge_slots; i += kBlkThreads) v.keys[i] = ~0ull;
-    for (uint32_t i = tid; i < merge_slots * WS; i += kBlkThreads) v.pool[i] = 0;
-    if (tid == 0) { v.h->n_unique = 0; v.h->overflow = 0; v.h->n_pass = 0; v.h->ok = 1; }
-    __syncthreads();
-    for (uint32_t i = p0 + tid; i < p1; i += kBlkThreads) {
-      const uint32_t pi = part_list[i];
-      const uint64_t key = slab_keys[pi];
-      uint32_t h = blk_hash((uint32_t)(key >> 32), (uint32_t)key, v.shift);
-      const uint64_t kk = *reinterpret_cast<const volatile uint64_t*>(&v.keys[h]);
-      if (kk != key) h = blk_resolve(v, key, h, kk);
-      if (h >= merge_slots) continue;
-      const uint4* src = reinterpret_cast<const uint4*>(slab_rows + (size_t)pi * WP);
-      uint32_t* dst = v.pool + h * WS;
+// kB3: one warp per slab; owners are counted, filtered and written out as rows.  Rows are
+// handed out with ONE global atomic per CTA (a counter shared by 300,000 warps serialises).
+__global__ void __launch_bounds__(256)
+kB3_emit(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_rows,
+         const uint32_t* __restrict__ slab_base, const uint32_t* __restrict__ slab_count,
+         const uint32_t* __restrict__ item_cluster, uint32_t n_items,
+         const uint32_t* __restrict__ pslot, const ClusterDev* __restrict__ clusters, RowOut out,
+         uint32_t row_capacity, uint32_t* __restrict__ counters, uint32_t W, uint32_t WP) {
+  __shared__ uint32_t w_pass[8];
+  __shared__ uint32_t cta_base, cta_ok;
+  const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  uint32_t n = 0, c = 0, base = 0;
+  if (item < n_items) {
+    n = slab_count[item];
+    if (n == kBlkOverflow) n = 0;
+    c = item_cluster[item];
+    base = slab_base[item];
+  }
+  ClusterDev cl{};
+  if (n) cl = clusters[c];
+  auto row_of = [&](uint32_t i) { return reinterpret_cast<const uint4*>(slab_rows + (size_t)(base + i) * WP); };
+  auto count_of = [&](uint32_t i, bool& owner) {
+    owner = i < n && pslot[base + i] != 0xffffffffu;
+    uint32_t cnt = 0;
+    if (owner) {
+      const uint4* row = row_of(i);
       for (uint32_t q = 0; q < WP / 4; ++q) {
-        const uint4 x = __ldg(src + q);
-        if (x.x) atomicOr(dst + 4 * q, x.x);
-        if (x.y) atomicOr(dst + 4 * q + 1, x.y);
-        if (x.z) atomicOr(dst + 4 * q + 2, x.z);
-        if (x.w) atomicOr(dst + 4 * q + 3, x.w);
+        const uint4 x = row[q];
+        cnt += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
       }
     }
-    __syncthreads();
-    if (v.h->overflow) {
-      if (tid == 0) atomicExch(&counters[LC_TABLE_OVERFLOW], 2u);
-      continue;
+    return cnt;
+  };
+  // pass 1: rows this warp will write
+  uint32_t my = 0;
+  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+    bool owner;
+    const uint32_t cnt = count_of(i0 + lane, owner);
+    my += __popc(__ballot_sync(kFull, owner && cnt >= cl.lo && cnt <= cl.hi));
+  }
+  if (lane == 0) w_pass[warp] = my;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int w = 0; w < 8; ++w) { const uint32_t x = w_pass[w]; w_pass[w] = total; total += x; }
+    uint32_t b = 0, ok = 1;
+    if (total) {
+      b = atomicAdd(&counters[LC_ROWS], total);
+      if ((uint64_t)b + total > row_capacity) { ok = 0; atomicExch(&counters[LC_ROW_OVERFLOW], 1u); }
     }
-    // ---- counts, filter, rows (as k3_local_direct) ------------------------------------
-    for (uint32_t h0 = 0; h0 < merge_slots; h0 += kBlkThreads) {
-      const uint32_t h = h0 + tid;
-      const bool used = h < merge_slots && v.keys[h] != ~0ull;
-      uint32_t cnt = 0;
-      if (used) {
-        const uint32_t* bits = v.pool + h * WS;
-        for (uint32_t w = 0; w < W; ++w) cnt += __popc(bits[w]);
-      }
-      const bool pass = used && cnt >= cl.lo && cnt <= cl.hi;
-      const uint32_t mu = __ballot_sync(kFull, used), mp = __ballot_sync(kFull, pass);
-      const uint32_t lane = tid & 31u;
-      if (lane == 0 && mu) atomicAdd(&v.h->n_unique, (uint32_t)__popc(mu));
-      if (mp) {
-        uint32_t b = 0;
-        if (lane == (uint32_t)__ffs(mp) - 1u) b = atomicAdd(&v.h->n_pass, (uint32_t)__popc(mp));
-        b = __shfl_sync(kFull, b, __ffs(mp) - 1);
-        if (pass) v.list[b + __popc(mp & lanemask_lt())] = (uint16_t)h;
-      }
-    }
-    __syncthreads();
-    if (tid == 0) {
-      atomicAdd(&counters[LC_UNIQUE], v.h->n_unique);
-      if (v.h->n_pass) {
-        const uint32_t b = atomicAdd(&counters[LC_ROWS], v.h->n_pass);
-        v.h->row_base = b;
-        if ((uint64_t)b + v.h->n_pass > row_capacity) {
-          v.h->ok = 0;
-          atomicExch(&counters[LC_ROW_OVERFLOW], 1u);
-        }
-      }
-    }
-    __syncthreads();
-    const uint32_t n_pass = v.h->n_pass;
-    if (n_pass == 0 || !v.h->ok) continue;
-    const uint32_t rbase = v.h->row_base;
-    for (uint32_t r = tid; r < n_pass; r += kBlkThreads) {
-      const uint32_t h = v.list[r];
-      const uint32_t* bits = v.pool + h * WS;
-      uint32_t cnt = 0;
-      for (uint32_t w = 0; w < W; ++w) cnt += __popc(bits[w]);
-      const size_t gi = (size_t)rbase + r;
+    cta_base = b;
+    cta_ok = ok;
+  }
+  __syncthreads();
+  if (!cta_ok || my == 0) return;
+  // pass 2: write them (the bitsets come back from L2)
+  uint32_t g = cta_base + w_pass[warp];
+  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+    const uint32_t i = i0 + lane;
+    bool owner;
+    const uint32_t cnt = count_of(i, owner);
+    const bool pass = owner && cnt >= cl.lo && cnt <= cl.hi;
+    const uint32_t mp = __ballot_sync(kFull, pass);
+    if (pass) {
+      const size_t gi = (size_t)g + __popc(mp & lanemask_lt());
       out.cluster[gi] = cl.id;
-      out.kmer[gi] = v.keys[h];
+      out.kmer[gi] = slab_keys[base + i];
       out.count[gi] = cnt;
-      if (out.key_words > W) out.cand[gi * out.key_words + W] = out.cluster_pattern[c];
+      uint32_t* dst = out.cand + gi * out.key_words;
+      const uint4* row = row_of(i);
+      for (uint32_t q = 0; q < WP / 4; ++q) {
+        const uint4 x = row[q];
+        const uint32_t w = 4 * q;
+        if (w < W) dst[w] = x.x;
+        if (w + 1 < W) dst[w + 1] = x.y;
+        if (w + 2 < W) dst[w + 2] = x.z;
+        if (w + 3 < W) dst[w + 3] = x.w;
+      }
+      if (out.key_words > W) dst[W] = out.cluster_pattern[c];
     }
-    for (uint32_t i = tid; i < n_pass * W; i += kBlkThreads) {
-      const uint32_t r = i / W, wd = i - r * W;
-      out.cand[((size_t)rbase + r) * out.key_words + wd] = v.pool[(uint32_t)v.list[r] * WS + wd];
-    }
+    g += __popc(mp);
   }
 }
 

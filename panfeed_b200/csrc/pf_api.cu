@@ -157,8 +157,7 @@ struct pf_ctx {
   // block aggregation (k3_block.cuh): no records, partial (k-mer, bitset) rows per position block
   bool block_mode = false;       // S <= 1024 and not disabled: kA_block_aggregate + kB_merge
   uint32_t block_windows = 16;   // B: windows per position block (halved after an overflow, >= 16)
-  uint32_t blk_slots = 512, merge_slots = 1024;   // shared-memory table sizes of kA / kB (powers of two)
-  uint32_t merge_target = 0;     // distinct keys a merge group should hold
+  uint32_t blk_slots = 512, blk_cslots = 128;   // shared-memory table sizes of kA (k-mers, chunks)
   uint32_t n_items = 0;          // (cluster, block) work items of the resident batch
   uint32_t block_fallbacks = 0;
   double partial_ratio = 1.0 / 16;   // partial rows per window, learned from earlier batches
@@ -166,7 +165,7 @@ struct pf_ctx {
   uint64_t partials_last = 0;
   bool used_block = false;       // the last batch went through kA/kB
   DevBuf d_seq_lite, d_cblk, d_item_base, d_item_cluster, d_slab_base, d_slab_count, d_slab_keys,
-      d_slab_rows, d_group_base, d_group_cluster, d_group_cnt, d_group_off, d_part_list, d_plan_total,
+      d_slab_rows, d_group_base /* merge-table offsets per cluster */, d_mtable, d_pslot, d_plan_total,
       d_rescue[2];
   PinBuf h_plan;
   PatternSpace kp, cp;     // k-mer patterns, cluster patterns
@@ -351,35 +350,27 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
     // block aggregation: debug_flags bit 1 disables it; PF_BLOCK_WINDOWS / PF_BLOCK_SMEM_KB tune it
     ctx->block_mode = ctx->partition && ctx->use_direct && !(p->debug_flags & 2u);
     if (const char* e = getenv("PF_BLOCK_MODE")) ctx->block_mode = ctx->block_mode && atoi(e) != 0;
-    if (const char* e = getenv("PF_BLOCK_WINDOWS")) {
-      const int b = atoi(e);
-      if (b >= kBlkRun && b <= kBlkRun * kBlkWarps && b % kBlkRun == 0 && (kBlkWarps % (b / kBlkRun)) == 0)
-        ctx->block_windows = (uint32_t)b;
-    }
-    // table of kA: one slot per expected distinct k-mer of a 16-window block at ~50 % load
-    // (about one haplotype per 30 samples and position); doubled after an overflow
+    // tables of kA: one k-mer slot per expected distinct k-mer of a 16-window run at ~50 % load
+    // (about one haplotype per 30 samples and position), a quarter as many chunk slots;
+    // overflowing blocks are rerun with both doubled
+    ctx->block_windows = (uint32_t)kBlkRun;
     uint32_t slots = 256;
-    while (slots < p->n_samples * ctx->block_windows / 16u && slots < 4096u) slots *= 2;
+    while (slots < p->n_samples && slots < 4096u) slots *= 2;
     if (const char* e = getenv("PF_BLOCK_SLOTS")) {
       const int v = atoi(e);
       if (v >= 64 && v <= 8192 && (v & (v - 1)) == 0) slots = (uint32_t)v;
     }
-    while (slots > 64u && blk_smem_bytes(slots, ctx->W) > kBlkMaxSmem) slots /= 2;
-    ctx->blk_slots = slots;
-    uint32_t mslots = 1024;
-    if (const char* e = getenv("PF_MERGE_SLOTS")) {
+    uint32_t cslots = std::max<uint32_t>(64u, slots / 4u);
+    if (const char* e = getenv("PF_BLOCK_CSLOTS")) {
       const int v = atoi(e);
-      if (v >= 64 && v <= 8192 && (v & (v - 1)) == 0) mslots = (uint32_t)v;
+      if (v >= 32 && v <= 8192 && (v & (v - 1)) == 0) cslots = (uint32_t)v;
     }
-    while (mslots > 64u && blk_smem_bytes(mslots, ctx->W) > 100u * 1024u) mslots /= 2;
-    ctx->merge_slots = mslots;
-    ctx->merge_target = std::max<uint32_t>(16u, mslots * 5u / 8u);
+    while (slots > 64u && blkA_smem_bytes(slots, cslots, ctx->W) > kBlkMaxSmem) { slots /= 2; cslots = std::max<uint32_t>(32u, cslots / 2); }
+    ctx->blk_slots = slots;
+    ctx->blk_cslots = cslots;
     if (p->k == 32 && !p->canonical) ctx->block_mode = false;   // all-T k-mer == the empty-slot mark
-    cudaFuncSetAttribute(kA_block_aggregate<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
-    cudaFuncSetAttribute(kA_block_aggregate<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
-    cudaFuncSetAttribute(kA_block_aggregate<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
-    cudaFuncSetAttribute(kA_block_aggregate<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
-    cudaFuncSetAttribute(kB_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
+    cudaFuncSetAttribute(kA_block_aggregate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
+    cudaFuncSetAttribute(kA_block_aggregate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
   }
   const int k3_smem = (int)(8 * ctx->W * sizeof(uint32_t));
   if (k3_smem > 48 * 1024) {
@@ -411,8 +402,8 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->d_pos_flags, &ctx->d_pos_wide, &ctx->d_seq_rec_off, &ctx->d_tile_first_seq,
                     &ctx->d_digests, &ctx->d_seq_lite, &ctx->d_cblk, &ctx->d_item_base, &ctx->d_slab_base,
                     &ctx->d_slab_count, &ctx->d_slab_keys, &ctx->d_slab_rows, &ctx->d_group_base,
-                    &ctx->d_item_cluster, &ctx->d_group_cluster, &ctx->d_group_cnt, &ctx->d_group_off,
-                    &ctx->d_part_list, &ctx->d_plan_total, &ctx->d_rescue[0], &ctx->d_rescue[1]})
+                    &ctx->d_item_cluster, &ctx->d_mtable, &ctx->d_pslot, &ctx->d_plan_total,
+                    &ctx->d_rescue[0], &ctx->d_rescue[1]})
     fd(*b);
   for (WidthState* w : {&ctx->nar, &ctx->wid}) {
     for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
@@ -1115,7 +1106,7 @@ BlkPlan block_plan(const pf_ctx* ctx) {
   bp.n_clusters = ctx->n_clusters;
   bp.block_windows = ctx->block_windows;
   bp.slots = ctx->blk_slots;
-  bp.max_unique = ctx->blk_slots * 13u / 16u;
+  bp.cslots = ctx->blk_cslots;
   bp.W = ctx->W;
   bp.WP = (ctx->W + 3u) & ~3u;
   return bp;
@@ -1123,72 +1114,61 @@ BlkPlan block_plan(const pf_ctx* ctx) {
 
 // items == nullptr: all (cluster, block) items with the context's table size; else the listed
 // items (a rescue launch) with `slots` slots.  Items that overflow are appended to `rescue_out`.
-int launch_block_aggregate(pf_ctx* ctx, const uint32_t* items, uint32_t n, uint32_t slots, uint32_t* rescue_out) {
+int launch_block_aggregate(pf_ctx* ctx, const uint32_t* items, uint32_t n, uint32_t slots, uint32_t cslots,
+                           uint32_t* rescue_out) {
   if (n == 0) return PF_OK;
   cudaStream_t st = ctx->stream;
   BlkPlan bp = block_plan(ctx);
   bp.slots = slots;
-  bp.max_unique = slots;
+  bp.cslots = cslots;
   const uint32_t cap32 = (uint32_t)std::min<uint64_t>(ctx->partial_cap, 0xfffffff0u);
   uint32_t* counters = ctx->d_counters.as<uint32_t>() + C_LOCAL;
-  const uint32_t smem = blk_smem_bytes(slots, ctx->W);
-#define PF_KA(CANON, KHI)                                                                              \
-  kA_block_aggregate<CANON, KHI><<<n, kBlkThreads, smem, st>>>(                                        \
+  const uint32_t smem = blkA_smem_bytes(slots, cslots, ctx->W);
+#define PF_KA(CANON)                                                                                   \
+  kA_block_aggregate<CANON><<<n, kBlkThreads, smem, st>>>(                                             \
       ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seq_lite.as<SeqLite>(), bp,   \
       (int)ctx->prm.k, ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),               \
       ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(), cap32, counters, items,       \
       rescue_out)
-  const bool khi = ctx->prm.k > 16;
-  if (ctx->prm.canonical) { if (khi) PF_KA(true, true); else PF_KA(true, false); }
-  else { if (khi) PF_KA(false, true); else PF_KA(false, false); }
+  if (ctx->prm.canonical) PF_KA(true); else PF_KA(false);
 #undef PF_KA
   ctx->launches++;
   CU(cudaGetLastError());
   return PF_OK;
 }
 
-int launch_block_merge(pf_ctx* ctx, RowOut ro) {
-  if (ctx->n_items == 0) return PF_OK;
+// kB1..kB3 over the `n_partials` partial rows kA left in the slabs
+int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
+  if (ctx->n_items == 0 || n_partials == 0) return PF_OK;
   cudaStream_t st = ctx->stream;
-  const BlkPlan bp = block_plan(ctx);
   const uint32_t nc = ctx->n_clusters;
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
-  plan_merge_groups<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(
-      ctx->d_item_base.as<uint32_t>(), nc, ctx->d_slab_count.as<uint32_t>(), ctx->merge_target,
-      ctx->d_group_base.as<uint32_t>());
+  const uint32_t WP = (ctx->W + 3u) & ~3u;
+  // per-cluster tables: 1.5 slots per partial row (+2), offsets by a scan
+  plan_merge_tables<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(
+      ctx->d_item_base.as<uint32_t>(), nc, ctx->d_slab_count.as<uint32_t>(), ctx->d_group_base.as<uint32_t>());
   ctx->launches++;
   TRY(scan_inplace(ctx, ctx->d_group_base.as<uint32_t>(), nc, ctx->d_plan_total.as<uint32_t>() + 1));
-  // counting sort of the partial rows by (cluster, group): sizes, scan, scatter
-  const uint32_t n_scan = (uint32_t)std::min<uint64_t>(ctx->partial_cap / ctx->merge_target + nc + 2, 0xfffffff0u);
-  TRY(dev_ensure(ctx, ctx->d_group_cluster, (size_t)n_scan * 4));
-  TRY(dev_ensure(ctx, ctx->d_group_cnt, ((size_t)n_scan + 1) * 4));
-  TRY(dev_ensure(ctx, ctx->d_group_off, ((size_t)n_scan + 1) * 4));
-  TRY(dev_ensure(ctx, ctx->d_part_list, std::max<uint64_t>(1, ctx->partial_cap) * 4));
-  plan_expand_owner<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(ctx->d_group_base.as<uint32_t>(), nc,
-                                                                  ctx->d_group_cluster.as<uint32_t>());
-  CU(cudaMemsetAsync(ctx->d_group_cnt.p, 0, ((size_t)n_scan + 1) * 4, st));
+  const uint64_t n_slots = (uint64_t)n_partials + n_partials / 2 + 2ull * nc + 16;
+  if (n_slots >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "too many partial rows for one batch; split it");
+  TRY(dev_ensure(ctx, ctx->d_mtable, n_slots * sizeof(MergeEntry)));
+  TRY(dev_ensure(ctx, ctx->d_pslot, (size_t)n_partials * 4));
+  CU(cudaMemsetAsync(ctx->d_mtable.p, 0xff, n_slots * sizeof(MergeEntry), st));
   const uint32_t g0 = cdiv((uint64_t)ctx->n_items * 32, 256);
-  kB0_group<false><<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_base.as<uint32_t>(),
-                                       ctx->d_slab_count.as<uint32_t>(), ctx->d_item_cluster.as<uint32_t>(),
-                                       ctx->n_items, ctx->d_group_base.as<uint32_t>(),
-                                       ctx->d_group_cnt.as<uint32_t>(), nullptr);
-  TRY(scan_inplace(ctx, ctx->d_group_cnt.as<uint32_t>(), n_scan, ctx->d_plan_total.as<uint32_t>() + 2));
-  CU(cudaMemcpyAsync(ctx->d_group_off.p, ctx->d_group_cnt.p, ((size_t)n_scan + 1) * 4, cudaMemcpyDeviceToDevice, st));
-  kB0_group<true><<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_base.as<uint32_t>(),
-                                      ctx->d_slab_count.as<uint32_t>(), ctx->d_item_cluster.as<uint32_t>(),
-                                      ctx->n_items, ctx->d_group_base.as<uint32_t>(),
-                                      ctx->d_group_cnt.as<uint32_t>(), ctx->d_part_list.as<uint32_t>());
-  ctx->launches += 3;
-  CU(cudaMemsetAsync(counters + C_TICKET_MERGE, 0, 4, st));
+  kB1_insert<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_base.as<uint32_t>(),
+                                 ctx->d_slab_count.as<uint32_t>(), ctx->d_item_cluster.as<uint32_t>(), ctx->n_items,
+                                 ctx->d_group_base.as<uint32_t>(), ctx->d_mtable.as<MergeEntry>(),
+                                 ctx->d_pslot.as<uint32_t>());
+  CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));     // kB2 counts the folded rows there
+  kB2_fold<<<cdiv(n_partials, 256), 256, 0, st>>>(n_partials, ctx->d_pslot.as<uint32_t>(),
+                                                  ctx->d_mtable.as<MergeEntry>(), ctx->d_slab_rows.as<uint32_t>(), WP,
+                                                  counters + C_LOCAL);
   const uint32_t cap = (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu);
-  const uint32_t smem = blk_smem_bytes(ctx->merge_slots, ctx->W);
-  const uint32_t per_sm = std::max<uint32_t>(1u, std::min<uint32_t>(8u, (227u * 1024u) / (smem + 1024u)));
-  kB_merge<<<148 * per_sm, kBlkThreads, smem, st>>>(
-      ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(), bp, ctx->d_group_base.as<uint32_t>(),
-      ctx->d_group_cluster.as<uint32_t>(), ctx->d_group_off.as<uint32_t>(), ctx->d_part_list.as<uint32_t>(),
-      ctx->merge_slots, ctx->merge_slots * 13u / 16u, ctx->d_clusters.as<ClusterDev>(), ro, cap,
-      counters + C_LOCAL, counters + C_TICKET_MERGE);
-  ctx->launches++;
+  kB3_emit<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
+                               ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(),
+                               ctx->d_item_cluster.as<uint32_t>(), ctx->n_items, ctx->d_pslot.as<uint32_t>(),
+                               ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL, ctx->W, WP);
+  ctx->launches += 3;
   CU(cudaGetLastError());
   return PF_OK;
 }
@@ -1285,7 +1265,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       TRY(dev_ensure(ctx, ctx->d_slab_keys, ctx->partial_cap * 8));
       TRY(dev_ensure(ctx, ctx->d_slab_rows, ctx->partial_cap * WP * 4));
       CU(cudaMemsetAsync(counters + C_LOCAL, 0, LC_COUNT * 4, st));
-      TRY(launch_block_aggregate(ctx, nullptr, ctx->n_items, ctx->blk_slots, ctx->d_rescue[0].as<uint32_t>()));
+      TRY(launch_block_aggregate(ctx, nullptr, ctx->n_items, ctx->blk_slots, ctx->blk_cslots, ctx->d_rescue[0].as<uint32_t>()));
       STAGE("kA_block_aggregate");
       TRY(passes_width<Key128>(ctx, Wd, C_TICKET_W));
       TRY(mark_width<Key128>(ctx, Wd, C_TICKET_MARK_W, C_RUNS_W, false));
@@ -1295,26 +1275,37 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       CU(cudaStreamSynchronize(st));
       TRY(check_device_error(ctx));
       bool too_big = false;
+      static const bool dbg = getenv("PF_DEBUG_BLOCK") != nullptr;
+      if (dbg)
+        fprintf(stderr, "[pf] kA: items %u slots %u cslots %u -> overflow %u rescue %u partials %u part_ovf %u\n",
+                ctx->n_items, ctx->blk_slots, ctx->blk_cslots, hcnt[C_LOCAL + LC_TABLE_OVERFLOW],
+                hcnt[C_LOCAL + LC_RESCUE], hcnt[C_LOCAL + LC_PARTIALS], hcnt[C_LOCAL + LC_PARTIAL_OVERFLOW]);
       {
-        uint32_t slots = ctx->blk_slots;
+        uint32_t slots = ctx->blk_slots, cslots = ctx->blk_cslots;
         int cur = 0;
         const uint32_t first_rescue = hcnt[C_LOCAL + LC_RESCUE];
         while (hcnt[C_LOCAL + LC_TABLE_OVERFLOW] == 1u) {
           const uint32_t n_resc = hcnt[C_LOCAL + LC_RESCUE];
-          if (slots >= 8192u || blk_smem_bytes(slots * 2u, ctx->W) > kBlkMaxSmem) { too_big = true; break; }
+          if (slots >= 8192u || blkA_smem_bytes(slots * 2u, cslots * 2u, ctx->W) > kBlkMaxSmem) { too_big = true; break; }
           slots *= 2;
+          cslots *= 2;
           CU(cudaMemsetAsync(counters + C_LOCAL + LC_TABLE_OVERFLOW, 0, 4, st));
           CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));
-          TRY(launch_block_aggregate(ctx, ctx->d_rescue[cur].as<uint32_t>(), n_resc, slots,
+          TRY(launch_block_aggregate(ctx, ctx->d_rescue[cur].as<uint32_t>(), n_resc, slots, cslots,
                                      ctx->d_rescue[cur ^ 1].as<uint32_t>()));
           cur ^= 1;
           CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
           CU(cudaStreamSynchronize(st));
+          if (dbg)
+            fprintf(stderr, "[pf] kA rescue: %u items slots %u cslots %u -> overflow %u rescue %u\n", n_resc, slots,
+                    cslots, hcnt[C_LOCAL + LC_TABLE_OVERFLOW], hcnt[C_LOCAL + LC_RESCUE]);
         }
-        // many rescued blocks: start the next batches with the larger table
+        // many rescued blocks: start the next batches with the larger tables
         if (!too_big && first_rescue > ctx->n_items / 8u && ctx->blk_slots < 8192u &&
-            blk_smem_bytes(ctx->blk_slots * 2u, ctx->W) <= kBlkMaxSmem)
+            blkA_smem_bytes(ctx->blk_slots * 2u, ctx->blk_cslots * 2u, ctx->W) <= kBlkMaxSmem) {
           ctx->blk_slots *= 2;
+          ctx->blk_cslots *= 2;
+        }
       }
       CU(cudaEventRecord(ctx->ev[EV_SORT], st));
       CU(cudaEventRecord(ctx->ev[EV_MARK], st));
@@ -1340,7 +1331,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       ro.cand = ctx->d_cand.as<uint32_t>();
       ro.kmer = ctx->d_row_kmer.as<uint64_t>();
       ro.row_base = 0;
-      TRY(launch_block_merge(ctx, ro));
+      TRY(launch_block_merge(ctx, ro, hcnt[C_LOCAL + LC_PARTIALS]));
       STAGE("kB_merge");
       CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
       CU(cudaStreamSynchronize(st));
@@ -1349,14 +1340,8 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       ctx->cp.n = ctx->cp_base + hcnt[C_NEW_CP];
       N.n_runs = 0;
       Wd.n_runs = Wd.n_records ? hcnt[C_RUNS_W] : 0;
-      const uint32_t tov = hcnt[C_LOCAL + LC_TABLE_OVERFLOW];
       if (hcnt[C_LOCAL + LC_PARTIAL_OVERFLOW]) {
         ctx->partial_cap = (uint64_t)hcnt[C_LOCAL + LC_PARTIALS] + 4096;
-        continue;
-      }
-      if (tov == 2u) {          // a merge group outgrew its table: smaller groups
-        if (ctx->merge_target <= 16u) return fail(ctx, PF_ERR_INTERNAL, "merge group overflow at the smallest group size");
-        ctx->merge_target = std::max<uint32_t>(16u, ctx->merge_target / 2);
         continue;
       }
       if (hcnt[C_LOCAL + LC_ROW_OVERFLOW]) {
@@ -1451,6 +1436,8 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   if (part) {
     N.n_rows = N.n_records ? hcnt[C_LOCAL + LC_ROWS] : 0;
     ctx->unique_last = N.n_records ? hcnt[C_LOCAL + LC_UNIQUE] : 0;
+    if (ctx->used_block)      // distinct k-mers = partial rows - rows folded into an earlier one
+      ctx->unique_last = (uint64_t)hcnt[C_LOCAL + LC_PARTIALS] - hcnt[C_LOCAL + LC_RESCUE];
     if (N.n_records) ctx->row_ratio = std::max(1e-4, (double)N.n_rows / (double)N.n_records);
   } else {
     TRY((runs_width<uint64_t, false>(ctx, N, ro)));
