@@ -180,7 +180,7 @@ typedef struct pf_stats {
   uint32_t engine;
   uint32_t block_windows;    /* engine 2: windows per position block                  */
   uint32_t block_slots;      /* engine 2: shared-memory table slots per block         */
-  uint32_t reserved;
+  uint32_t sub_batches;      /* sub-batches the last pf_submit was pipelined through (1 = not split) */
   uint64_t partial_rows;     /* engine 2: (k-mer, bitset) partial rows of the last batch */
 } pf_stats;
 
@@ -192,7 +192,12 @@ int  pf_abi_version(void);
 
 /* ---- the hot path ---- */
 /* pf_submit = pf_upload + pf_execute.  Host buffers of the batch must stay
- * valid until pf_upload returns (they are staged through pinned memory). */
+ * valid until pf_upload / pf_submit returns.  A batch of >= ~400,000 sequences without
+ * N/IUPAC symbols is cut by pf_submit into sub-batches of whole clusters that flow through
+ * two device slots: the H2D of sub-batch j+1 and the D2H of sub-batch j-1 run under the
+ * kernels of sub-batch j (results are those of the one big batch; PF_PIPELINE_SEQS sets the
+ * sub-batch size, 0 disables).  For that, sequences must lie in the packed plane in array
+ * order (base_off non-decreasing), as panfeed_b200/packer.py and pf_synth_fill produce. */
 int pf_upload(pf_ctx* ctx, const pf_batch* batch);   /* validate, H2D, plan tiles   */
 int pf_execute(pf_ctx* ctx);                         /* K1..K4 on the resident batch */
 int pf_submit(pf_ctx* ctx, const pf_batch* batch);

@@ -93,7 +93,7 @@ class Stats(C.Structure):
                 ("ms_d2h", C.c_float), ("ms_total", C.c_float),
                 ("total_launches", C.c_uint64), ("engine", C.c_uint32),
                 ("block_windows", C.c_uint32), ("block_slots", C.c_uint32),
-                ("reserved", C.c_uint32), ("partial_rows", C.c_uint64)]
+                ("sub_batches", C.c_uint32), ("partial_rows", C.c_uint64)]
 
 
 class SynthParams(C.Structure):

@@ -7,7 +7,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -52,6 +55,22 @@ __global__ void plan_seq_rec_off(const SeqDev* __restrict__ seqs, uint32_t n_seq
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_seqs) out[i] = seqs[i].rec_off;
   else if (i == n_seqs) out[i] = total;
+}
+// Counter read-back without a copy engine: the D2H engine may be busy with the previous
+// batch's rows, and a 64-byte memcpy queued behind them would stall the pipeline's host side.
+// `dst` is pinned host memory (device-accessible under UVA).
+__global__ void mirror_counters(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+// pipelined submit: positional records of a sub-batch index its own sequences / wide k-mers
+__global__ void pos_rebase(uint32_t* __restrict__ pos_seq, uint64_t* __restrict__ pos_kmer,
+                           const uint8_t* __restrict__ pos_flags, uint32_t n, uint32_t seq_base,
+                           uint64_t wide_base) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pos_seq[i] += seq_base;
+  if (wide_base && (pos_flags[i] & 2u)) pos_kmer[i] += wide_base;
 }
 // sequence holding the first record of every tile (last s with rec_off[s] <= start, non-empty)
 __global__ void plan_tile_first_seq(const TileDev* __restrict__ tiles, uint32_t n_tiles,
@@ -114,18 +133,11 @@ enum Ev { EV_START, EV_EXTRACT, EV_HIST, EV_SORT, EV_MARK, EV_COUNTED, EV_REDUCE
 
 }  // namespace
 
-struct pf_ctx {
-  pf_params prm{};
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;   // D2H of finished row arrays while K4 still runs
-  cudaEvent_t ev_rows = nullptr;
-  bool rows_prefetched = false;
-  std::string err;
-  uint32_t W = 0, Wk = 0;
-  std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> maf_cache;
-
-  // resident batch
+// Everything that belongs to ONE batch of whole clusters: what pf_upload builds, the record /
+// row buffers of that batch and its result arrays on the device.  A context holds two of these
+// so that the upload of sub-batch j+1 and the D2H of sub-batch j-1 can overlap the kernels of
+// sub-batch j (pf_submit on a large batch; see submit_pipelined).
+struct BatchState {
   bool have_batch = false, executed = false;
   uint32_t n_seqs = 0, n_clusters = 0, n_wide_seqs = 0;
   uint64_t n_words = 0, n_amb_words = 0, n_bases = 0;
@@ -133,51 +145,83 @@ struct pf_ctx {
   PinBuf h_seqs, h_clusters, h_wide_seqs;
   DevBuf d_bases, d_amb, d_ambbits, d_seqs, d_clusters, d_wide_seqs, d_presence;
   WidthState nar, wid;
-  DevBuf d_counters;       // u32[16]: tickets, n_runs, errors, totals
+  // rows (narrow first, then wide)
+  DevBuf d_row_cluster, d_row_kmer, d_wrow_kmer, d_row_count, d_row_pattern;
+  DevBuf d_cl_pattern;
+  DevBuf d_pos_kmer, d_pos_seq, d_pos_cstart, d_pos_gstart, d_pos_flags, d_pos_wide;
+  DevBuf d_seq_rec_off, d_tile_first_seq;
+  PinBuf h_seq_rec_off, h_tile_first_seq;
+  std::vector<std::pair<uint32_t, uint32_t>> nar_ranges;   // narrow record range of every cluster
+  uint32_t n_items = 0;          // (cluster, block) work items of the batch (block aggregation)
+  DevBuf d_seq_lite, d_cblk, d_item_base, d_item_cluster, d_plan_total, d_bsum_slot;
+  PinBuf h_plan;
+  uint64_t kp_base = 0, cp_base = 0;   // pool sizes before the batch
+  bool rows_prefetched = false;
+  uint64_t row_cap = 0;          // capacity of the row arrays above
+};
+
+struct pf_ctx : BatchState {
+  pf_params prm{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // D2H of finished row arrays while K4 still runs
+  cudaStream_t up_stream = nullptr;     // H2D of the next sub-batch while the current one computes
+  cudaEvent_t ev_rows = nullptr;
+  std::string err;
+  uint32_t W = 0, Wk = 0;
+  std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> maf_cache;
+  std::mutex maf_mu;       // the upload helper thread of the pipelined submit shares the cache
+
+  BatchState alt;          // the other batch slot (pipelined submit)
+  DevBuf d_counters;       // u32[C_COUNT]: tickets, n_runs, errors, totals
   PinBuf h_counters;
   DevBuf d_bsum;
-  // rows (narrow first, then wide)
-  DevBuf d_row_cluster, d_row_kmer, d_wrow_kmer, d_row_count, d_row_pattern, d_cand;
+  DevBuf d_cand;
   DevBuf d_rep, d_slot_of, d_winner;
-  DevBuf d_cl_pattern, d_cl_rep, d_cl_slot, d_cl_winner;
-  DevBuf d_pos_kmer, d_pos_seq, d_pos_cstart, d_pos_gstart, d_pos_flags, d_pos_wide;
+  DevBuf d_cl_rep, d_cl_slot, d_cl_winner;
   bool partition = true;   // mode 0: few radix passes + shared-memory hash grouping (k3_local)
   bool use_direct = true;  // S <= 1024: bitsets for every distinct key in shared memory
   bool runs_from_hist = false;   // one pass: prefix-runs are the digit buckets of the histogram
   uint32_t local_tile = 0;       // records per tile of the local reduce (4096 direct / 2048 general)
   bool fused = false;            // K1 fused into the histogram and the first pass (no record write in K1)
-  DevBuf d_seq_rec_off, d_tile_first_seq, d_digests;
-  PinBuf h_seq_rec_off, h_tile_first_seq;
-  std::vector<std::pair<uint32_t, uint32_t>> nar_ranges;   // narrow record range of every cluster
+  DevBuf d_digests;
   int extra_bits = 0;      // sort bits added after a table overflow (sticky)
   double row_ratio = 1.0 / 48;   // surviving rows per record, learned from earlier batches
-  uint64_t row_cap = 0;
   uint64_t unique_last = 0;
   uint32_t rescued_last = 0;
   // block aggregation (k3_block.cuh): no records, partial (k-mer, bitset) rows per position block
-  bool block_mode = false;       // S <= 1024 and not disabled: kA_block_aggregate + kB_merge
-  uint32_t block_windows = 16;   // B: windows per position block (halved after an overflow, >= 16)
+  bool block_mode = false;       // S <= 1024 and not disabled: kA_block_aggregate + kB1..kB3
+  uint32_t block_windows = 16;   // windows per position block (= kBlkRun)
   uint32_t blk_slots = 512, blk_cslots = 128;   // shared-memory table sizes of kA (k-mers, chunks)
-  uint32_t n_items = 0;          // (cluster, block) work items of the resident batch
   uint32_t block_fallbacks = 0;
   double partial_ratio = 1.0 / 16;   // partial rows per window, learned from earlier batches
   uint64_t partial_cap = 0;
   uint64_t partials_last = 0;
   bool used_block = false;       // the last batch went through kA/kB
-  DevBuf d_seq_lite, d_cblk, d_item_base, d_item_cluster, d_slab_base, d_slab_count, d_slab_keys,
-      d_slab_rows, d_group_base /* merge-table offsets per cluster */, d_mtable, d_pslot, d_plan_total,
-      d_rescue[2];
-  PinBuf h_plan;
+  DevBuf d_slab_base, d_slab_count, d_slab_keys, d_slab_rows,
+      d_group_base /* merge-table offsets per cluster */, d_mtable, d_pslot, d_rescue[2];
   PatternSpace kp, cp;     // k-mer patterns, cluster patterns
-  uint64_t kp_base = 0, cp_base = 0;   // pool sizes before the resident batch
   // pinned results
   PinBuf r_row_cluster, r_row_kmer, r_wrow_kmer, r_row_count, r_row_pattern, r_cl_pattern;
   PinBuf r_new_kp, r_new_cp, r_pos_kmer, r_pos_seq, r_pos_cstart, r_pos_gstart, r_pos_flags,
       r_pos_wide;
+  PinBuf r_wrow_cluster, r_wrow_count, r_wrow_pattern;   // pipelined submit: wide rows apart
   cudaEvent_t ev[EV_COUNT]{};
   cudaEvent_t ev_h2d[2]{}, ev_d2h[2]{};
   pf_stats stats{};
-  uint32_t launches = 0;
+  std::atomic<uint32_t> launches{0};
+  // pipelined submit (submit_pipelined / collect_pipelined)
+  bool pipe_pending = false;     // results of a pipelined submit wait for pf_collect
+  uint32_t pipe_subs = 1;        // sub-batches of the last submit
+  bool pipe_mode = false;        // inside submit_pipelined: pf_execute leaves the D2H to it
+  double pipe_ms[10] = {0};      // stage times summed over the sub-batches
+  uint64_t pipe_rows = 0, pipe_wide_rows = 0, pipe_pos = 0, pipe_pos_wide = 0;
+  uint32_t pipe_clusters = 0;
+  uint64_t pipe_kp_base = 0, pipe_cp_base = 0, pipe_kp_copied = 0;
+  uint64_t pipe_row_cap = 0, pipe_wide_cap = 0;
+  cudaEvent_t ev_up[2]{}, ev_exec_end[2]{}, ev_out_done[2]{}, ev_pipe[2]{};
+  uint32_t pipe_min_seqs = 200000;   // batches with fewer sequences are not split
+  uint32_t pipe_target_seqs = 262144;   // sequences per sub-batch
 };
 
 namespace {
@@ -328,6 +372,18 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
     return fail(nullptr, PF_ERR_CUDA, "cudaStreamCreate failed");
   }
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 2; ++i) {
+    cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_exec_end[i], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_out_done[i], cudaEventDisableTiming);
+    cudaEventCreate(&ctx->ev_pipe[i]);
+  }
+  if (const char* e = getenv("PF_PIPELINE_SEQS")) {      // 0 disables the pipelined submit
+    const long v = atol(e);
+    if (v <= 0) ctx->pipe_min_seqs = 0xffffffffu;
+    else { ctx->pipe_target_seqs = (uint32_t)std::max<long>(1024, v); ctx->pipe_min_seqs = ctx->pipe_target_seqs + ctx->pipe_target_seqs / 2; }
+  }
   cudaEventCreateWithFlags(&ctx->ev_rows, cudaEventDisableTiming);
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
   for (auto& ev : ctx->ev_h2d) cudaEventCreate(&ev);
@@ -390,43 +446,53 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
 extern "C" void pf_destroy(pf_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaDeviceSynchronize();
   auto fd = [](DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
   auto fp = [](PinBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; };
-  for (DevBuf* b : {&ctx->d_bases, &ctx->d_amb, &ctx->d_ambbits, &ctx->d_seqs, &ctx->d_clusters,
-                    &ctx->d_wide_seqs, &ctx->d_presence, &ctx->d_counters, &ctx->d_bsum,
-                    &ctx->d_row_cluster, &ctx->d_row_kmer, &ctx->d_wrow_kmer, &ctx->d_row_count,
-                    &ctx->d_row_pattern, &ctx->d_cand, &ctx->d_rep, &ctx->d_slot_of, &ctx->d_winner,
-                    &ctx->d_cl_pattern, &ctx->d_cl_rep, &ctx->d_cl_slot, &ctx->d_cl_winner,
-                    &ctx->d_pos_kmer, &ctx->d_pos_seq, &ctx->d_pos_cstart, &ctx->d_pos_gstart,
-                    &ctx->d_pos_flags, &ctx->d_pos_wide, &ctx->d_seq_rec_off, &ctx->d_tile_first_seq,
-                    &ctx->d_digests, &ctx->d_seq_lite, &ctx->d_cblk, &ctx->d_item_base, &ctx->d_slab_base,
-                    &ctx->d_slab_count, &ctx->d_slab_keys, &ctx->d_slab_rows, &ctx->d_group_base,
-                    &ctx->d_item_cluster, &ctx->d_mtable, &ctx->d_pslot, &ctx->d_plan_total,
-                    &ctx->d_rescue[0], &ctx->d_rescue[1]})
-    fd(*b);
-  for (WidthState* w : {&ctx->nar, &ctx->wid}) {
-    for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
-                      &w->seg_hist, &w->lookback, &w->cursors, &w->ltiles, &w->tile_first_run,
-                      &w->d_tile_base, &w->d_ltile_base})
+  for (BatchState* bs : {static_cast<BatchState*>(ctx), &ctx->alt}) {
+    for (DevBuf* b : {&bs->d_bases, &bs->d_amb, &bs->d_ambbits, &bs->d_seqs, &bs->d_clusters, &bs->d_wide_seqs,
+                      &bs->d_presence, &bs->d_row_cluster, &bs->d_row_kmer, &bs->d_wrow_kmer, &bs->d_row_count,
+                      &bs->d_row_pattern, &bs->d_cl_pattern, &bs->d_pos_kmer, &bs->d_pos_seq, &bs->d_pos_cstart,
+                      &bs->d_pos_gstart, &bs->d_pos_flags, &bs->d_pos_wide, &bs->d_seq_rec_off,
+                      &bs->d_tile_first_seq, &bs->d_seq_lite, &bs->d_cblk, &bs->d_item_base, &bs->d_item_cluster,
+                      &bs->d_plan_total, &bs->d_bsum_slot})
       fd(*b);
-    fp(w->h_tiles); fp(w->h_seg_start); fp(w->h_ltiles);
+    for (WidthState* w : {&bs->nar, &bs->wid}) {
+      for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
+                        &w->seg_hist, &w->lookback, &w->cursors, &w->ltiles, &w->tile_first_run,
+                        &w->d_tile_base, &w->d_ltile_base})
+        fd(*b);
+      fp(w->h_tiles); fp(w->h_seg_start); fp(w->h_ltiles);
+    }
+    for (PinBuf* b : {&bs->h_seqs, &bs->h_clusters, &bs->h_wide_seqs, &bs->h_seq_rec_off, &bs->h_tile_first_seq,
+                      &bs->h_plan})
+      fp(*b);
   }
+  for (DevBuf* b : {&ctx->d_counters, &ctx->d_bsum, &ctx->d_cand, &ctx->d_rep, &ctx->d_slot_of, &ctx->d_winner,
+                    &ctx->d_cl_rep, &ctx->d_cl_slot, &ctx->d_cl_winner, &ctx->d_digests, &ctx->d_slab_base,
+                    &ctx->d_slab_count, &ctx->d_slab_keys, &ctx->d_slab_rows, &ctx->d_group_base, &ctx->d_mtable,
+                    &ctx->d_pslot, &ctx->d_rescue[0], &ctx->d_rescue[1]})
+    fd(*b);
   for (PatternSpace* s : {&ctx->kp, &ctx->cp})
     for (DevBuf* b : {&s->pool, &s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique,
                       &s->x_table, &s->x_rep, &s->x_slot, &s->x_winner})
       fd(*b);
-  for (PinBuf* b : {&ctx->h_seqs, &ctx->h_clusters, &ctx->h_wide_seqs, &ctx->h_counters, &ctx->h_plan,
-                    &ctx->h_seq_rec_off, &ctx->h_tile_first_seq,
-                    &ctx->r_row_cluster, &ctx->r_row_kmer, &ctx->r_wrow_kmer, &ctx->r_row_count,
-                    &ctx->r_row_pattern, &ctx->r_cl_pattern, &ctx->r_new_kp, &ctx->r_new_cp,
-                    &ctx->r_pos_kmer, &ctx->r_pos_seq, &ctx->r_pos_cstart, &ctx->r_pos_gstart,
-                    &ctx->r_pos_flags, &ctx->r_pos_wide})
+  for (PinBuf* b : {&ctx->h_counters, &ctx->r_row_cluster, &ctx->r_row_kmer, &ctx->r_wrow_kmer, &ctx->r_row_count,
+                    &ctx->r_row_pattern, &ctx->r_cl_pattern, &ctx->r_new_kp, &ctx->r_new_cp, &ctx->r_pos_kmer,
+                    &ctx->r_pos_seq, &ctx->r_pos_cstart, &ctx->r_pos_gstart, &ctx->r_pos_flags, &ctx->r_pos_wide,
+                    &ctx->r_wrow_cluster, &ctx->r_wrow_count, &ctx->r_wrow_pattern})
     fp(*b);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_h2d) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_d2h) if (ev) cudaEventDestroy(ev);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
+    if (ctx->ev_exec_end[i]) cudaEventDestroy(ctx->ev_exec_end[i]);
+    if (ctx->ev_out_done[i]) cudaEventDestroy(ctx->ev_out_done[i]);
+    if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);
+  }
   if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
+  if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -452,18 +518,18 @@ int auto_sort_bits(const pf_ctx* ctx, uint32_t max_seg_records, bool narrow) {
 // Build the tile list of one key width from the per-cluster record ranges.
 // Tile list of the local reduce (partition mode): 8192-record tiles for the direct
 // variant, 2048 for the general one (its exactness guarantee needs <= 2048).
-int plan_local_tiles(pf_ctx* ctx) {
-  WidthState& w = ctx->nar;
+int plan_local_tiles(pf_ctx* ctx, BatchState& B, cudaStream_t st) {
+  WidthState& w = B.nar;
   if (!ctx->partition) { w.n_ltiles = 0; return PF_OK; }
   const uint32_t tile = ctx->use_direct ? (uint32_t)kDirectTile : (uint32_t)kLocalTile;
   ctx->local_tile = tile;
-  const uint32_t nc = (uint32_t)ctx->nar_ranges.size();
+  const uint32_t nc = (uint32_t)B.nar_ranges.size();
   TRY(pin_ensure(ctx, w.h_ltiles, std::max<size_t>(1, nc) * 4));
   uint32_t* base = w.h_ltiles.as<uint32_t>();
   uint64_t nl = 0;
   for (uint32_t c = 0; c < nc; ++c) {
     base[c] = (uint32_t)nl;
-    nl += cdiv(ctx->nar_ranges[c].second - ctx->nar_ranges[c].first, tile);
+    nl += cdiv(B.nar_ranges[c].second - B.nar_ranges[c].first, tile);
   }
   w.n_ltiles = (uint32_t)nl;
   if (w.n_ltiles) {
@@ -471,9 +537,9 @@ int plan_local_tiles(pf_ctx* ctx) {
     TRY(dev_ensure(ctx, w.tile_first_run, ((size_t)w.n_ltiles + 1) * 4));
     TRY(dev_ensure(ctx, w.lookback, std::max<size_t>((size_t)w.n_tiles * kRadix * 4, (size_t)w.n_ltiles * 8)));
     TRY(dev_ensure(ctx, w.d_ltile_base, (size_t)nc * 4));
-    CU(cudaMemcpyAsync(w.d_ltile_base.p, base, (size_t)nc * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(w.d_ltile_base.p, base, (size_t)nc * 4, cudaMemcpyHostToDevice, st));
     // needs d_clusters: the caller uploads it first
-    plan_expand_tiles<<<nc, 128, 0, ctx->stream>>>(ctx->d_clusters.as<ClusterDev>(), nc, w.d_ltile_base.as<uint32_t>(),
+    plan_expand_tiles<<<nc, 128, 0, st>>>(B.d_clusters.as<ClusterDev>(), nc, w.d_ltile_base.as<uint32_t>(),
                                                    tile, 0, w.ltiles.as<TileDev>());
     ctx->launches++;     // (the pinned `base` array must not be rewritten before this copy ran:
                          //  pf_upload ends with a sync, the re-plan in pf_execute syncs itself)
@@ -509,14 +575,35 @@ int plan_tiles(pf_ctx* ctx, WidthState& w, const std::vector<std::pair<uint32_t,
 
 }  // namespace
 
-namespace { int plan_blocks(pf_ctx* ctx); int scan_inplace(pf_ctx* ctx, uint32_t* data, uint32_t n, uint32_t* total_dev); }
+namespace {
+int plan_blocks(pf_ctx* ctx, BatchState& B, cudaStream_t st, bool sync);
+int plan_blocks_finish(pf_ctx* ctx, BatchState& B, cudaStream_t st);
+int scan_inplace(pf_ctx* ctx, uint32_t* data, uint32_t n, uint32_t* total_dev, cudaStream_t st = nullptr, DevBuf* scratch = nullptr);
+}
 
-extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
-  if (!ctx) return PF_ERR_INVALID;
-  if (!b) return fail(ctx, PF_ERR_INVALID, "pf_upload: null batch");
-  CU(cudaSetDevice(ctx->device));
-  ctx->have_batch = false;
-  ctx->executed = false;
+namespace {
+// A sub-range of a caller batch: sequences [s0,s1) of clusters [c0,c1), whose bases are words
+// [w0,w1) of the 2-bit plane and [a0,a1) of the 4-bit plane.
+struct SubRange { uint32_t s0, s1, c0, c1; uint64_t w0, w1, a0, a1; };
+
+// Validate + plan + H2D of the sub-range into the CURRENT batch slot, all asynchronous on `st`
+// (the caller's buffers must stay valid until `st` has passed).  upload_finish completes it.
+int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRange& r, cudaStream_t st) {
+  pf_batch view = *full;
+  view.seqs = full->seqs ? full->seqs + r.s0 : nullptr;
+  view.n_seqs = r.s1 - r.s0;
+  view.clusters = full->clusters ? full->clusters + r.c0 : nullptr;
+  view.n_clusters = r.c1 - r.c0;
+  view.cluster_presence = full->cluster_presence ? full->cluster_presence + (size_t)r.c0 * ctx->W : nullptr;
+  view.packed_bases = full->packed_bases ? full->packed_bases + r.w0 : nullptr;
+  view.n_words = r.w1 - r.w0;
+  view.amb_codes = full->amb_codes ? full->amb_codes + r.a0 : nullptr;
+  view.n_amb_words = r.a1 - r.a0;
+  const pf_batch* b = &view;
+  const uint32_t rc = r.c0;                       // rebase of cluster indices
+  const uint64_t rb = r.w0 * 32ull, ra = r.a0 * 16ull;   // ... of base / symbol offsets
+  B.have_batch = false;
+  B.executed = false;
   const pf_params& P = ctx->prm;
   const uint32_t k = P.k, S = P.n_samples, W = ctx->W;
   if (b->n_seqs && (!b->seqs || !b->packed_bases)) return fail(ctx, PF_ERR_INVALID, "null seqs/packed_bases");
@@ -524,20 +611,20 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
     return fail(ctx, PF_ERR_INVALID, "null clusters/cluster_presence");
   if (b->n_clusters == 0 && b->n_seqs) return fail(ctx, PF_ERR_INVALID, "sequences without clusters");
 
-  TRY(pin_ensure(ctx, ctx->h_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(SeqDev)));
-  TRY(pin_ensure(ctx, ctx->h_clusters, std::max<size_t>(1, b->n_clusters) * sizeof(ClusterDev)));
-  TRY(pin_ensure(ctx, ctx->h_wide_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(uint32_t)));
-  SeqDev* hs = ctx->h_seqs.as<SeqDev>();
-  ClusterDev* hc = ctx->h_clusters.as<ClusterDev>();
-  uint32_t* hw = ctx->h_wide_seqs.as<uint32_t>();
+  TRY(pin_ensure(ctx, B.h_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(SeqDev)));
+  TRY(pin_ensure(ctx, B.h_clusters, std::max<size_t>(1, b->n_clusters) * sizeof(ClusterDev)));
+  TRY(pin_ensure(ctx, B.h_wide_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(uint32_t)));
+  SeqDev* hs = B.h_seqs.as<SeqDev>();
+  ClusterDev* hc = B.h_clusters.as<ClusterDev>();
+  uint32_t* hw = B.h_wide_seqs.as<uint32_t>();
 
   const uint32_t mult = P.canonical ? 1u : 2u;
   // the packed plane is the bulk of the transfer: start it before the host-side planning
   const size_t slack_words = 80;
-  TRY(dev_ensure(ctx, ctx->d_bases, (b->n_words + slack_words) * 8));
-  CU(cudaEventRecord(ctx->ev_h2d[0], ctx->stream));
-  if (b->n_words) CU(cudaMemcpyAsync(ctx->d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync((char*)ctx->d_bases.p + b->n_words * 8, 0, slack_words * 8, ctx->stream));
+  TRY(dev_ensure(ctx, B.d_bases, (b->n_words + slack_words) * 8));
+  CU(cudaEventRecord(ctx->ev_h2d[0], st));
+  if (b->n_words) CU(cudaMemcpyAsync(B.d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync((char*)B.d_bases.p + b->n_words * 8, 0, slack_words * 8, st));
 
   // ---- planning, in parallel over chunks of sequences --------------------------------
   // phase A: validate + per-sequence sizes, per-chunk sums; phase B: prefix over chunks;
@@ -567,11 +654,12 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
       Part& p = parts[t];
       const uint32_t i0 = std::min(n, t * per), i1 = std::min(n, i0 + per);
       for (uint32_t i = i0; i < i1; ++i) {
-        const pf_seq_desc& q = b->seqs[i];
+        pf_seq_desc q = b->seqs[i];
+        q.cluster -= rc; q.base_off -= rb; q.amb_off -= (q.flags & PF_SEQ_AMBIGUOUS) ? ra : 0;
         if (q.cluster >= b->n_clusters) return errf(p, "seq %u: cluster %u out of range", i, q.cluster);
-        if (i && q.cluster < b->seqs[i - 1].cluster) return errf(p, "seq %u: clusters must be non-decreasing", i);
+        if (i && q.cluster + rc < b->seqs[i - 1].cluster) return errf(p, "seq %u: clusters must be non-decreasing", i);
         if (q.sample >= S) return errf(p, "seq %u: sample rank %u >= n_samples %u", i, q.sample, S);
-        if (i && q.cluster == b->seqs[i - 1].cluster && q.sample < b->seqs[i - 1].sample)
+        if (i && q.cluster + rc == b->seqs[i - 1].cluster && q.sample < b->seqs[i - 1].sample)
           return errf(p, "seq %u: sample ranks must be non-decreasing inside a cluster", i);
         if (!((b->cluster_presence[(size_t)q.cluster * W + (q.sample >> 5)] >> (q.sample & 31)) & 1u))
           return errf(p, "seq %u: sample %u is not marked present in cluster %u", i, q.sample, q.cluster);
@@ -608,11 +696,12 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
       Part o = base[t];
       const uint32_t i0 = std::min(n, t * per), i1 = std::min(n, i0 + per);
       for (uint32_t i = i0; i < i1; ++i) {
-        const pf_seq_desc& q = b->seqs[i];
+        pf_seq_desc q = b->seqs[i];
+        q.cluster -= rc; q.base_off -= rb; q.amb_off -= (q.flags & PF_SEQ_AMBIGUOUS) ? ra : 0;
         const bool amb = (q.flags & PF_SEQ_AMBIGUOUS) != 0;
         const bool target = P.emit_positions && (q.flags & PF_SEQ_TARGET);
         const uint32_t nwin = q.len >= k ? q.len - k + 1 : 0;
-        if (i == 0 || q.cluster != b->seqs[i - 1].cluster) {     // first sequence of its cluster
+        if (i == 0 || q.cluster + rc != b->seqs[i - 1].cluster) {     // first sequence of its cluster
           nr[q.cluster].first = (uint32_t)o.rec;
           wr[q.cluster].first = (uint32_t)o.wrec;
         }
@@ -649,13 +738,17 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
     d.wrec_start = wr[c].first; d.wrec_end = wr[c].second;
     d.id = b->clusters[c].id; d.n_present = np;
     const uint32_t n = P.consider_missing ? np : S;
-    auto it = ctx->maf_cache.find(n);
-    if (it == ctx->maf_cache.end()) {
-      uint32_t lo, hi;
-      pf_maf_window(P.maf, n, &lo, &hi);
-      it = ctx->maf_cache.emplace(n, std::make_pair(lo, hi)).first;
+    uint32_t lo, hi;
+    {
+      std::lock_guard<std::mutex> lk(ctx->maf_mu);
+      auto it = ctx->maf_cache.find(n);
+      if (it == ctx->maf_cache.end()) {
+        uint32_t wl, wh;
+        pf_maf_window(P.maf, n, &wl, &wh);
+        it = ctx->maf_cache.emplace(n, std::make_pair(wl, wh)).first;
+      }
+      lo = it->second.first; hi = it->second.second;
     }
-    uint32_t lo = it->second.first, hi = it->second.second;
     // "same as cluster" (panfeed.py:202-204): k-mer bits are a subset of the
     // cluster's, so equality <=> count == n_present; NaN entries never compare equal.
     if (P.cluster_equal_filter && (!P.consider_missing || np == S)) {
@@ -666,81 +759,99 @@ extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
     d.lo = lo; d.hi = hi;
   }
 
-  ctx->n_seqs = b->n_seqs; ctx->n_clusters = b->n_clusters; ctx->n_wide_seqs = n_wide;
-  ctx->n_words = b->n_words; ctx->n_amb_words = n_wide ? b->n_amb_words : 0; ctx->n_bases = bases;
-  ctx->n_pos = (uint32_t)pos; ctx->n_pos_wide = (uint32_t)pwide;
-  ctx->nar.n_records = (uint32_t)rec; ctx->wid.n_records = (uint32_t)wrec;
-  TRY(plan_tiles(ctx, ctx->nar, nr, true));
-  TRY(plan_tiles(ctx, ctx->wid, wr, false));
+  B.n_seqs = b->n_seqs; B.n_clusters = b->n_clusters; B.n_wide_seqs = n_wide;
+  B.n_words = b->n_words; B.n_amb_words = n_wide ? b->n_amb_words : 0; B.n_bases = bases;
+  B.n_pos = (uint32_t)pos; B.n_pos_wide = (uint32_t)pwide;
+  B.nar.n_records = (uint32_t)rec; B.wid.n_records = (uint32_t)wrec;
+  TRY(plan_tiles(ctx, B.nar, nr, true));
+  TRY(plan_tiles(ctx, B.wid, wr, false));
 
   // ---- device buffers + H2D ------------------------------------------------
-  TRY(dev_ensure(ctx, ctx->d_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(SeqDev)));
-  TRY(dev_ensure(ctx, ctx->d_clusters, std::max<size_t>(1, b->n_clusters) * sizeof(ClusterDev)));
-  TRY(dev_ensure(ctx, ctx->d_presence, std::max<size_t>(1, (size_t)b->n_clusters * W) * 4));
+  TRY(dev_ensure(ctx, B.d_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(SeqDev)));
+  TRY(dev_ensure(ctx, B.d_clusters, std::max<size_t>(1, b->n_clusters) * sizeof(ClusterDev)));
+  TRY(dev_ensure(ctx, B.d_presence, std::max<size_t>(1, (size_t)b->n_clusters * W) * 4));
   TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4));
   TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4));
-  for (WidthState* w : {&ctx->nar, &ctx->wid}) {
+  for (WidthState* w : {&B.nar, &B.wid}) {
     TRY(dev_ensure(ctx, w->tiles, std::max<size_t>(1, w->n_tiles) * sizeof(TileDev)));
     TRY(dev_ensure(ctx, w->seg_start, std::max<size_t>(1, b->n_clusters) * 4));
     TRY(dev_ensure(ctx, w->seg_hist, std::max<size_t>(1, (size_t)b->n_clusters * w->passes * kRadix) * 4));
     TRY(dev_ensure(ctx, w->lookback, std::max<size_t>(1, (size_t)w->n_tiles * kRadix) * 4));
   }
-  cudaStream_t st = ctx->stream;
-  if (b->n_seqs) CU(cudaMemcpyAsync(ctx->d_seqs.p, hs, b->n_seqs * sizeof(SeqDev), cudaMemcpyHostToDevice, st));
+  if (b->n_seqs) CU(cudaMemcpyAsync(B.d_seqs.p, hs, b->n_seqs * sizeof(SeqDev), cudaMemcpyHostToDevice, st));
   if (b->n_clusters) {
-    CU(cudaMemcpyAsync(ctx->d_clusters.p, hc, b->n_clusters * sizeof(ClusterDev), cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->d_presence.p, b->cluster_presence, (size_t)b->n_clusters * W * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B.d_clusters.p, hc, b->n_clusters * sizeof(ClusterDev), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(B.d_presence.p, b->cluster_presence, (size_t)b->n_clusters * W * 4, cudaMemcpyHostToDevice, st));
   }
   // tile lists are generated on the device from the per-cluster record ranges
-  for (WidthState* w : {&ctx->nar, &ctx->wid}) {
+  for (WidthState* w : {&B.nar, &B.wid}) {
     if (b->n_clusters) CU(cudaMemcpyAsync(w->seg_start.p, w->h_seg_start.p, b->n_clusters * 4, cudaMemcpyHostToDevice, st));
     if (w->n_tiles) {
       TRY(dev_ensure(ctx, w->d_tile_base, (size_t)b->n_clusters * 4));
       CU(cudaMemcpyAsync(w->d_tile_base.p, w->h_tiles.p, (size_t)b->n_clusters * 4, cudaMemcpyHostToDevice, st));
-      plan_expand_tiles<<<b->n_clusters, 128, 0, st>>>(ctx->d_clusters.as<ClusterDev>(), b->n_clusters,
+      plan_expand_tiles<<<b->n_clusters, 128, 0, st>>>(B.d_clusters.as<ClusterDev>(), b->n_clusters,
                                                        w->d_tile_base.as<uint32_t>(), kSortTile,
-                                                       w == &ctx->wid ? 1 : 0, w->tiles.as<TileDev>());
+                                                       w == &B.wid ? 1 : 0, w->tiles.as<TileDev>());
       ctx->launches++;
     }
   }
-  ctx->nar_ranges = nr;
-  TRY(plan_local_tiles(ctx));
+  B.nar_ranges = nr;
+  TRY(plan_local_tiles(ctx, B, st));
   // fused first pass: record index -> sequence lookup tables
   if (b->n_seqs) {
-    TRY(dev_ensure(ctx, ctx->d_seq_rec_off, ((size_t)b->n_seqs + 1) * 4));
-    TRY(dev_ensure(ctx, ctx->d_tile_first_seq, ((size_t)ctx->nar.n_tiles + 1) * 4));
+    TRY(dev_ensure(ctx, B.d_seq_rec_off, ((size_t)b->n_seqs + 1) * 4));
+    TRY(dev_ensure(ctx, B.d_tile_first_seq, ((size_t)B.nar.n_tiles + 1) * 4));
     plan_seq_rec_off<<<cdiv((uint64_t)b->n_seqs + 1, 256), 256, 0, st>>>(
-        ctx->d_seqs.as<SeqDev>(), b->n_seqs, (uint32_t)rec, ctx->d_seq_rec_off.as<uint32_t>());
-    plan_tile_first_seq<<<cdiv((uint64_t)ctx->nar.n_tiles + 1, 256), 256, 0, st>>>(
-        ctx->nar.tiles.as<TileDev>(), ctx->nar.n_tiles, ctx->d_seq_rec_off.as<uint32_t>(), b->n_seqs,
-        ctx->d_tile_first_seq.as<uint32_t>());
+        B.d_seqs.as<SeqDev>(), b->n_seqs, (uint32_t)rec, B.d_seq_rec_off.as<uint32_t>());
+    plan_tile_first_seq<<<cdiv((uint64_t)B.nar.n_tiles + 1, 256), 256, 0, st>>>(
+        B.nar.tiles.as<TileDev>(), B.nar.n_tiles, B.d_seq_rec_off.as<uint32_t>(), b->n_seqs,
+        B.d_tile_first_seq.as<uint32_t>());
     ctx->launches += 2;
   }
   if (n_wide) {
     const size_t bit_words = (b->n_amb_words + 1) / 2 + 4;
-    TRY(dev_ensure(ctx, ctx->d_amb, (b->n_amb_words + 8) * 8));
-    TRY(dev_ensure(ctx, ctx->d_ambbits, bit_words * 4));
-    TRY(dev_ensure(ctx, ctx->d_wide_seqs, n_wide * 4));
-    CU(cudaMemcpyAsync(ctx->d_amb.p, b->amb_codes, b->n_amb_words * 8, cudaMemcpyHostToDevice, st));
-    CU(cudaMemsetAsync((char*)ctx->d_amb.p + b->n_amb_words * 8, 0, 8 * 8, st));
-    CU(cudaMemcpyAsync(ctx->d_wide_seqs.p, hw, n_wide * 4, cudaMemcpyHostToDevice, st));
-    k1_amb_bits<<<cdiv(bit_words, 256), 256, 0, st>>>(ctx->d_amb.as<uint64_t>(), b->n_amb_words,
-                                                       ctx->d_ambbits.as<uint32_t>(), bit_words);
+    TRY(dev_ensure(ctx, B.d_amb, (b->n_amb_words + 8) * 8));
+    TRY(dev_ensure(ctx, B.d_ambbits, bit_words * 4));
+    TRY(dev_ensure(ctx, B.d_wide_seqs, n_wide * 4));
+    CU(cudaMemcpyAsync(B.d_amb.p, b->amb_codes, b->n_amb_words * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemsetAsync((char*)B.d_amb.p + b->n_amb_words * 8, 0, 8 * 8, st));
+    CU(cudaMemcpyAsync(B.d_wide_seqs.p, hw, n_wide * 4, cudaMemcpyHostToDevice, st));
+    k1_amb_bits<<<cdiv(bit_words, 256), 256, 0, st>>>(B.d_amb.as<uint64_t>(), b->n_amb_words,
+                                                       B.d_ambbits.as<uint32_t>(), bit_words);
     ctx->launches++;
   }
   if (ctx->block_mode && b->n_seqs) {
     if (b->n_words >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "packed plane holds 2^32 words or more; split the batch");
-    TRY(dev_ensure(ctx, ctx->d_seq_lite, (size_t)b->n_seqs * sizeof(SeqLite)));
-    plan_seq_lite<<<cdiv(b->n_seqs, 256), 256, 0, st>>>(ctx->d_seqs.as<SeqDev>(), b->n_seqs, ctx->d_seq_lite.as<SeqLite>());
+    TRY(dev_ensure(ctx, B.d_seq_lite, (size_t)b->n_seqs * sizeof(SeqLite)));
+    plan_seq_lite<<<cdiv(b->n_seqs, 256), 256, 0, st>>>(B.d_seqs.as<SeqDev>(), b->n_seqs, B.d_seq_lite.as<SeqLite>());
     ctx->launches++;
   }
   CU(cudaEventRecord(ctx->ev_h2d[1], st));
-  if (ctx->block_mode) TRY(plan_blocks(ctx));
-  // caller buffers may be pageable: make sure the copies have consumed them
-  CU(cudaStreamSynchronize(st));
+  if (ctx->block_mode) TRY(plan_blocks(ctx, B, st, false));
   CU(cudaGetLastError());
-  ctx->have_batch = true;
   return PF_OK;
+}
+
+// Second half of an upload: wait for the copies and the planning kernels, read n_items back.
+int upload_finish(pf_ctx* ctx, BatchState& B, cudaStream_t up) {
+  CU(cudaStreamSynchronize(up));
+  if (ctx->block_mode) TRY(plan_blocks_finish(ctx, B, up));
+  CU(cudaStreamSynchronize(up));
+  CU(cudaGetLastError());
+  B.have_batch = true;
+  return PF_OK;
+}
+}  // namespace
+
+extern "C" int pf_upload(pf_ctx* ctx, const pf_batch* b) {
+  if (!ctx) return PF_ERR_INVALID;
+  if (!b) return fail(ctx, PF_ERR_INVALID, "pf_upload: null batch");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->pipe_pending) return fail(ctx, PF_ERR_STATE, "pf_upload: results of the previous pf_submit were not collected");
+  SubRange r{0, b->n_seqs, 0, b->n_clusters, 0, b->n_words, 0, b->n_amb_words};
+  TRY(upload_async(ctx, *ctx, b, r, ctx->stream));
+  // caller buffers may be pageable: upload_finish makes sure the copies have consumed them
+  return upload_finish(ctx, *ctx, ctx->stream);
 }
 
 namespace {
@@ -860,13 +971,14 @@ int mark_width(pf_ctx* ctx, WidthState& w, int ticket_idx, int runs_idx, bool lo
   return PF_OK;
 }
 
-int scan_inplace(pf_ctx* ctx, uint32_t* data, uint32_t n, uint32_t* total_dev) {
-  cudaStream_t st = ctx->stream;
+int scan_inplace(pf_ctx* ctx, uint32_t* data, uint32_t n, uint32_t* total_dev, cudaStream_t st, DevBuf* scratch) {
+  if (!st) st = ctx->stream;
+  DevBuf& bsum = scratch ? *scratch : ctx->d_bsum;
   const uint32_t nb = std::max(1u, cdiv(n, kScanBlock));
-  TRY(dev_ensure(ctx, ctx->d_bsum, ((size_t)nb + 1) * 4));
-  scan_block_sums<<<nb, 256, 0, st>>>(data, n, ctx->d_bsum.as<uint32_t>());
-  scan_of_sums<<<1, 1024, 0, st>>>(ctx->d_bsum.as<uint32_t>(), nb, total_dev);
-  scan_apply<<<nb, 256, 0, st>>>(data, n, ctx->d_bsum.as<uint32_t>(), nb);
+  TRY(dev_ensure(ctx, bsum, ((size_t)nb + 1) * 4));
+  scan_block_sums<<<nb, 256, 0, st>>>(data, n, bsum.as<uint32_t>());
+  scan_of_sums<<<1, 1024, 0, st>>>(bsum.as<uint32_t>(), nb, total_dev);
+  scan_apply<<<nb, 256, 0, st>>>(data, n, bsum.as<uint32_t>(), nb);
   ctx->launches += 3;
   CU(cudaGetLastError());
   return PF_OK;
@@ -972,6 +1084,7 @@ void fill_timings(pf_ctx* ctx) {
   s.block_windows = ctx->block_windows;
   s.block_slots = ctx->blk_slots;
   s.partial_rows = ctx->used_block ? ctx->partials_last : 0;
+  s.sub_batches = ctx->pipe_subs;
 }
 
 int check_device_error(pf_ctx* ctx) {
@@ -1068,32 +1181,33 @@ int launch_local(pf_ctx* ctx, RowOut ro, uint32_t n_rescue = 0) {
 
 // ---- block aggregation: work items = (cluster, position block) -----------------------
 // (re)computes the per-cluster block counts for ctx->block_windows; syncs to learn n_items
-int plan_blocks(pf_ctx* ctx) {
-  cudaStream_t st = ctx->stream;
-  const uint32_t nc = ctx->n_clusters;
-  ctx->n_items = 0;
-  if (nc == 0 || ctx->n_seqs == 0) return PF_OK;
-  TRY(dev_ensure(ctx, ctx->d_cblk, (size_t)nc * sizeof(ClusterBlk)));
-  TRY(dev_ensure(ctx, ctx->d_item_base, ((size_t)nc + 1) * 4));
-  TRY(dev_ensure(ctx, ctx->d_group_base, ((size_t)nc + 1) * 4));
-  TRY(dev_ensure(ctx, ctx->d_plan_total, 16));
-  TRY(pin_ensure(ctx, ctx->h_plan, 16));
+int plan_blocks(pf_ctx* ctx, BatchState& B, cudaStream_t st, bool sync) {
+  const uint32_t nc = B.n_clusters;
+  B.n_items = 0;
+  if (nc == 0 || B.n_seqs == 0) return PF_OK;
+  TRY(dev_ensure(ctx, B.d_cblk, (size_t)nc * sizeof(ClusterBlk)));
+  TRY(dev_ensure(ctx, B.d_item_base, ((size_t)nc + 1) * 4));
+  TRY(dev_ensure(ctx, B.d_plan_total, 16));
+  TRY(pin_ensure(ctx, B.h_plan, 16));
   plan_cluster_blocks<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(
-      ctx->d_seqs.as<SeqDev>(), ctx->n_seqs, nc, (int)ctx->prm.k, ctx->block_windows,
-      ctx->d_cblk.as<ClusterBlk>(), ctx->d_item_base.as<uint32_t>());
-  ctx->launches++;
-  TRY(scan_inplace(ctx, ctx->d_item_base.as<uint32_t>(), nc, ctx->d_plan_total.as<uint32_t>()));
-  CU(cudaMemcpyAsync(ctx->h_plan.p, ctx->d_plan_total.p, 4, cudaMemcpyDeviceToHost, st));
+      B.d_seqs.as<SeqDev>(), B.n_seqs, nc, (int)ctx->prm.k, ctx->block_windows,
+      B.d_cblk.as<ClusterBlk>(), B.d_item_base.as<uint32_t>());
+  TRY(scan_inplace(ctx, B.d_item_base.as<uint32_t>(), nc, B.d_plan_total.as<uint32_t>(), st, &B.d_bsum_slot));
+  // n_items is read back through pinned memory (no copy engine); plan_blocks_finish takes it
+  mirror_counters<<<1, 32, 0, st>>>(B.h_plan.as<uint32_t>(), B.d_plan_total.as<uint32_t>(), 1);
+  CU(cudaGetLastError());
+  if (sync) return plan_blocks_finish(ctx, B, st);
+  return PF_OK;
+}
+// after the stream has passed plan_blocks: the item -> cluster map
+int plan_blocks_finish(pf_ctx* ctx, BatchState& B, cudaStream_t st) {
+  const uint32_t nc = B.n_clusters;
+  if (nc == 0 || B.n_seqs == 0) return PF_OK;
   CU(cudaStreamSynchronize(st));
-  ctx->n_items = ctx->h_plan.as<uint32_t>()[0];
-  TRY(dev_ensure(ctx, ctx->d_slab_base, std::max<size_t>(1, ctx->n_items) * 4));
-  TRY(dev_ensure(ctx, ctx->d_slab_count, std::max<size_t>(1, ctx->n_items) * 4));
-  TRY(dev_ensure(ctx, ctx->d_item_cluster, std::max<size_t>(1, ctx->n_items) * 4));
-  TRY(dev_ensure(ctx, ctx->d_rescue[0], std::max<size_t>(1, ctx->n_items) * 4));
-  TRY(dev_ensure(ctx, ctx->d_rescue[1], std::max<size_t>(1, ctx->n_items) * 4));
-  plan_expand_owner<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(ctx->d_item_base.as<uint32_t>(), nc,
-                                                                  ctx->d_item_cluster.as<uint32_t>());
-  ctx->launches++;
+  B.n_items = B.h_plan.as<uint32_t>()[0];
+  TRY(dev_ensure(ctx, B.d_item_cluster, std::max<size_t>(1, B.n_items) * 4));
+  plan_expand_owner<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(B.d_item_base.as<uint32_t>(), nc,
+                                                                  B.d_item_cluster.as<uint32_t>());
   CU(cudaGetLastError());
   return PF_OK;
 }
@@ -1145,6 +1259,7 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
   const uint32_t WP = (ctx->W + 3u) & ~3u;
   // per-cluster tables: 1.5 slots per partial row (+2), offsets by a scan
+  TRY(dev_ensure(ctx, ctx->d_group_base, ((size_t)nc + 1) * 4));
   plan_merge_tables<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(
       ctx->d_item_base.as<uint32_t>(), nc, ctx->d_slab_count.as<uint32_t>(), ctx->d_group_base.as<uint32_t>());
   ctx->launches++;
@@ -1262,6 +1377,10 @@ extern "C" int pf_execute(pf_ctx* ctx) {
           65536, (uint64_t)(ctx->partial_ratio * 1.3 * (double)n_windows) + 4096));
       ctx->partial_cap = std::min<uint64_t>(ctx->partial_cap, 0xfffffff0ull);
       const uint32_t WP = (ctx->W + 3u) & ~3u;
+      TRY(dev_ensure(ctx, ctx->d_slab_base, std::max<size_t>(1, ctx->n_items) * 4));
+      TRY(dev_ensure(ctx, ctx->d_slab_count, std::max<size_t>(1, ctx->n_items) * 4));
+      TRY(dev_ensure(ctx, ctx->d_rescue[0], std::max<size_t>(1, ctx->n_items) * 4));
+      TRY(dev_ensure(ctx, ctx->d_rescue[1], std::max<size_t>(1, ctx->n_items) * 4));
       TRY(dev_ensure(ctx, ctx->d_slab_keys, ctx->partial_cap * 8));
       TRY(dev_ensure(ctx, ctx->d_slab_rows, ctx->partial_cap * WP * 4));
       CU(cudaMemsetAsync(counters + C_LOCAL, 0, LC_COUNT * 4, st));
@@ -1271,7 +1390,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       TRY(mark_width<Key128>(ctx, Wd, C_TICKET_MARK_W, C_RUNS_W, false));
       // blocks holding more distinct k-mers than the table takes are rerun with a table twice
       // the size, then four times, ...; past the largest table the batch takes the record path
-      CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+      mirror_counters<<<1, 32, 0, st>>>(hcnt, counters, C_COUNT);
       CU(cudaStreamSynchronize(st));
       TRY(check_device_error(ctx));
       bool too_big = false;
@@ -1294,7 +1413,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
           TRY(launch_block_aggregate(ctx, ctx->d_rescue[cur].as<uint32_t>(), n_resc, slots, cslots,
                                      ctx->d_rescue[cur ^ 1].as<uint32_t>()));
           cur ^= 1;
-          CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+          mirror_counters<<<1, 32, 0, st>>>(hcnt, counters, C_COUNT);
           CU(cudaStreamSynchronize(st));
           if (dbg)
             fprintf(stderr, "[pf] kA rescue: %u items slots %u cslots %u -> overflow %u rescue %u\n", n_resc, slots,
@@ -1314,7 +1433,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
         // then the record path (for this batch; for good after the second time)
         if (ctx->block_windows > (uint32_t)kBlkRun) {
           ctx->block_windows /= 2;
-          TRY(plan_blocks(ctx));
+          TRY(plan_blocks(ctx, *ctx, st, true));
         } else {
           blk = false;
           if (++ctx->block_fallbacks >= 2) ctx->block_mode = false;
@@ -1333,7 +1452,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       ro.row_base = 0;
       TRY(launch_block_merge(ctx, ro, hcnt[C_LOCAL + LC_PARTIALS]));
       STAGE("kB_merge");
-      CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+      mirror_counters<<<1, 32, 0, st>>>(hcnt, counters, C_COUNT);
       CU(cudaStreamSynchronize(st));
       TRY(check_device_error(ctx));
       ctx->rescued_last = 0;
@@ -1386,7 +1505,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
         TRY(launch_local(ctx, ro));
         STAGE("k3_local");
       }
-      CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+      mirror_counters<<<1, 32, 0, st>>>(hcnt, counters, C_COUNT);
       CU(cudaStreamSynchronize(st));
       TRY(check_device_error(ctx));
       ctx->rescued_last = 0;
@@ -1394,7 +1513,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
           !hcnt[C_LOCAL + LC_TABLE_OVERFLOW]) {
         ctx->rescued_last = hcnt[C_LOCAL + LC_RESCUE];
         TRY(launch_local(ctx, ro, hcnt[C_LOCAL + LC_RESCUE]));
-        CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+        mirror_counters<<<1, 32, 0, st>>>(hcnt, counters, C_COUNT);
         CU(cudaStreamSynchronize(st));
       }
       return PF_OK;
@@ -1416,7 +1535,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
         TRY(dev_ensure(ctx, N.seg_hist, std::max<size_t>(1, (size_t)ctx->n_clusters * N.passes * kRadix) * 4));
       } else if (ctx->use_direct) {
         ctx->use_direct = false;
-        TRY(plan_local_tiles(ctx));
+        TRY(plan_local_tiles(ctx, *ctx, st));
         CU(cudaStreamSynchronize(st));
       } else {
         return fail(ctx, PF_ERR_INTERNAL, "local table overflow at 64 sorted bits");
@@ -1449,7 +1568,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
     if (!part && N.n_runs)
       TRY(scan_inplace(ctx, N.vals[N.final_buf ^ 1].as<uint32_t>(), N.n_runs, counters + C_ROWS_N));
     if (Wd.n_runs) TRY(scan_inplace(ctx, Wd.vals[Wd.final_buf ^ 1].as<uint32_t>(), Wd.n_runs, counters + C_ROWS_W));
-    CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+    mirror_counters<<<1, 32, 0, st>>>(hcnt, counters, C_COUNT);
     CU(cudaStreamSynchronize(st));
     if (!part) N.n_rows = N.n_runs ? hcnt[C_ROWS_N] : 0;
     Wd.n_rows = Wd.n_runs ? hcnt[C_ROWS_W] : 0;
@@ -1483,7 +1602,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   // the (cluster, k-mer, count) arrays of the rows are final: start their D2H on the copy
   // stream while K4 numbers the patterns
   ctx->rows_prefetched = false;
-  if (rows) {
+  if (rows && !ctx->pipe_mode) {
     TRY(pin_ensure(ctx, ctx->r_row_cluster, rows * 4));
     TRY(pin_ensure(ctx, ctx->r_row_count, rows * 4));
     TRY(pin_ensure(ctx, ctx->r_row_kmer, std::max<size_t>(8, (size_t)N.n_rows * 8)));
@@ -1501,21 +1620,335 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   TRY(dedup(ctx, ctx->kp, ctx->d_cand.as<uint32_t>(), (uint32_t)rows, ctx->d_rep, ctx->d_slot_of,
             ctx->d_winner, ctx->d_row_pattern.as<uint32_t>(), C_NEW_KP));
   CU(cudaEventRecord(ctx->ev[EV_DEDUP], st));
-  CU(cudaMemcpyAsync(hcnt, counters, C_COUNT * 4, cudaMemcpyDeviceToHost, st));
+  mirror_counters<<<1, 32, 0, st>>>(hcnt, counters, C_COUNT);
   CU(cudaEventRecord(ctx->ev[EV_END], st));
   ctx->executed = true;
   ctx->stats.launches = ctx->launches - launches0;
   return PF_OK;
 }
 
+namespace {
+
+// grow a pinned result array, keeping the `used` bytes already copied into it
+int pin_grow(pf_ctx* ctx, PinBuf& b, size_t need, size_t used) {
+  if (need <= b.cap) return PF_OK;
+  CU(cudaStreamSynchronize(ctx->copy_stream));     // copies into the old array are in flight
+  size_t want = std::max(need, b.cap + b.cap / 2);
+  want = (want + 4095) & ~size_t(4095);
+  void* np = nullptr;
+  CU(cudaMallocHost(&np, want));
+  if (b.p && used) memcpy(np, b.p, used);
+  if (b.p) CU(cudaFreeHost(b.p));
+  b.p = np;
+  b.cap = want;
+  return PF_OK;
+}
+
+// cut a batch into sub-batches of whole clusters with about `target` sequences each
+std::vector<SubRange> split_batch(const pf_batch* b, uint32_t target) {
+  std::vector<SubRange> subs;
+  const uint32_t n = b->n_seqs;
+  uint32_t s0 = 0, c0 = 0;
+  while (s0 < n) {
+    uint32_t s1 = n, c1 = b->n_clusters;
+    if ((uint64_t)s0 + target + target / 2 < n) {
+      // first sequence of the cluster that holds sequence s0 + target (clusters are sorted)
+      const uint32_t c = b->seqs[s0 + target].cluster;
+      uint32_t lo = s0, hi = s0 + target;
+      while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (b->seqs[mid].cluster < c) lo = mid + 1; else hi = mid;
+      }
+      if (lo > s0) { s1 = lo; c1 = c; }
+      else {            // one cluster longer than the target: take it whole
+        lo = s0 + target; hi = n;
+        while (lo < hi) {
+          const uint32_t mid = lo + (hi - lo) / 2;
+          if (b->seqs[mid].cluster <= c) lo = mid + 1; else hi = mid;
+        }
+        s1 = lo;
+        c1 = s1 < n ? b->seqs[s1].cluster : b->n_clusters;
+      }
+    }
+    SubRange r{};
+    r.s0 = s0; r.s1 = s1; r.c0 = c0; r.c1 = std::max(c1, c0);
+    r.w0 = b->seqs[s0].base_off >> 5;
+    r.w1 = s1 < n ? (b->seqs[s1].base_off >> 5) : b->n_words;
+    r.a0 = 0; r.a1 = 0;
+    subs.push_back(r);
+    s0 = s1;
+    c0 = r.c1;
+  }
+  if (!subs.empty()) subs.back().c1 = b->n_clusters;     // trailing clusters without sequences
+  return subs;
+}
+
+void pipe_add_timings(pf_ctx* ctx) {
+  fill_timings(ctx);
+  const pf_stats& t = ctx->stats;
+  const float v[10] = {t.ms_h2d, t.ms_extract, t.ms_hist, t.ms_sort, t.ms_mark, t.ms_count, t.ms_reduce,
+                       t.ms_dedup, 0.f, 0.f};
+  for (int i = 0; i < 10; ++i) ctx->pipe_ms[i] += v[i];
+}
+
+// D2H of the current slot's results behind everything it executed, appended to the pinned
+// result arrays of the pipelined submit
+int pipe_enqueue_results(pf_ctx* ctx, const SubRange& r, int slot) {
+  cudaStream_t st = ctx->stream, cp = ctx->copy_stream;
+  WidthState& N = ctx->nar;
+  WidthState& Wd = ctx->wid;
+  const uint64_t nr = N.n_rows, nw = Wd.n_rows;
+  const uint64_t R = ctx->pipe_rows, RW = ctx->pipe_wide_rows;
+  TRY(pin_grow(ctx, ctx->r_row_cluster, (R + nr) * 4, R * 4));
+  TRY(pin_grow(ctx, ctx->r_row_count, (R + nr) * 4, R * 4));
+  TRY(pin_grow(ctx, ctx->r_row_pattern, (R + nr) * 4, R * 4));
+  TRY(pin_grow(ctx, ctx->r_row_kmer, (R + nr) * 8, R * 8));
+  TRY(pin_grow(ctx, ctx->r_wrow_cluster, std::max<uint64_t>(8, (RW + nw) * 4), RW * 4));
+  TRY(pin_grow(ctx, ctx->r_wrow_count, std::max<uint64_t>(8, (RW + nw) * 4), RW * 4));
+  TRY(pin_grow(ctx, ctx->r_wrow_pattern, std::max<uint64_t>(8, (RW + nw) * 4), RW * 4));
+  TRY(pin_grow(ctx, ctx->r_wrow_kmer, std::max<uint64_t>(8, (RW + nw) * 16), RW * 16));
+  if (ctx->n_pos) {
+    const uint64_t P0 = ctx->pipe_pos, np = ctx->n_pos;
+    TRY(pin_grow(ctx, ctx->r_pos_kmer, (P0 + np) * 8, P0 * 8));
+    TRY(pin_grow(ctx, ctx->r_pos_seq, (P0 + np) * 4, P0 * 4));
+    TRY(pin_grow(ctx, ctx->r_pos_cstart, (P0 + np) * 4, P0 * 4));
+    TRY(pin_grow(ctx, ctx->r_pos_gstart, (P0 + np) * 4, P0 * 4));
+    TRY(pin_grow(ctx, ctx->r_pos_flags, (P0 + np), P0));
+    if (ctx->n_pos_wide)
+      TRY(pin_grow(ctx, ctx->r_pos_wide, (ctx->pipe_pos_wide + ctx->n_pos_wide) * 16, ctx->pipe_pos_wide * 16));
+    pos_rebase<<<cdiv(ctx->n_pos, 256), 256, 0, st>>>(ctx->d_pos_seq.as<uint32_t>(), ctx->d_pos_kmer.as<uint64_t>(),
+                                                      ctx->d_pos_flags.as<uint8_t>(), ctx->n_pos, r.s0,
+                                                      ctx->pipe_pos_wide);
+    ctx->launches++;
+  }
+  CU(cudaEventRecord(ctx->ev_rows, st));
+  CU(cudaStreamWaitEvent(cp, ctx->ev_rows, 0));
+  auto d2h = [&](PinBuf& dst, size_t dst_off, const void* src, size_t bytes) -> int {
+    if (bytes) CU(cudaMemcpyAsync((char*)dst.p + dst_off, src, bytes, cudaMemcpyDeviceToHost, cp));
+    return PF_OK;
+  };
+  TRY(d2h(ctx->r_row_cluster, R * 4, ctx->d_row_cluster.p, nr * 4));
+  TRY(d2h(ctx->r_row_count, R * 4, ctx->d_row_count.p, nr * 4));
+  TRY(d2h(ctx->r_row_pattern, R * 4, ctx->d_row_pattern.p, nr * 4));
+  TRY(d2h(ctx->r_row_kmer, R * 8, ctx->d_row_kmer.p, nr * 8));
+  TRY(d2h(ctx->r_wrow_cluster, RW * 4, ctx->d_row_cluster.as<uint32_t>() + nr, nw * 4));
+  TRY(d2h(ctx->r_wrow_count, RW * 4, ctx->d_row_count.as<uint32_t>() + nr, nw * 4));
+  TRY(d2h(ctx->r_wrow_pattern, RW * 4, ctx->d_row_pattern.as<uint32_t>() + nr, nw * 4));
+  TRY(d2h(ctx->r_wrow_kmer, RW * 16, ctx->d_wrow_kmer.p, nw * 16));
+  TRY(d2h(ctx->r_cl_pattern, (size_t)ctx->pipe_clusters * 4, ctx->d_cl_pattern.p, (size_t)ctx->n_clusters * 4));
+  if (ctx->n_pos) {
+    const uint64_t P0 = ctx->pipe_pos, np = ctx->n_pos;
+    TRY(d2h(ctx->r_pos_kmer, P0 * 8, ctx->d_pos_kmer.p, np * 8));
+    TRY(d2h(ctx->r_pos_seq, P0 * 4, ctx->d_pos_seq.p, np * 4));
+    TRY(d2h(ctx->r_pos_cstart, P0 * 4, ctx->d_pos_cstart.p, np * 4));
+    TRY(d2h(ctx->r_pos_gstart, P0 * 4, ctx->d_pos_gstart.p, np * 4));
+    TRY(d2h(ctx->r_pos_flags, P0, ctx->d_pos_flags.p, np));
+    if (ctx->n_pos_wide)
+      TRY(d2h(ctx->r_pos_wide, ctx->pipe_pos_wide * 16, ctx->d_pos_wide.p, (size_t)ctx->n_pos_wide * 16));
+  }
+  CU(cudaEventRecord(ctx->ev_out_done[slot], cp));
+  ctx->pipe_rows += nr;
+  ctx->pipe_wide_rows += nw;
+  ctx->pipe_pos += ctx->n_pos;
+  ctx->pipe_pos_wide += ctx->n_pos_wide;
+  ctx->pipe_clusters += ctx->n_clusters;
+  pf_stats& s = ctx->stats;
+  s.bases += ctx->n_bases;
+  s.instances += (uint64_t)N.n_records + Wd.n_records;
+  s.unique_kmers += ctx->unique_last;
+  s.rows += nr + nw;
+  return PF_OK;
+}
+
+// D2H (copy stream) of the k-mer patterns numbered since the last call; the compute stream
+// must have passed the K4 that appended them
+int pipe_copy_new_patterns(pf_ctx* ctx) {
+  const uint64_t done = ctx->kp.n, from = ctx->pipe_kp_copied, base = ctx->pipe_kp_base;
+  if (done <= from) return PF_OK;
+  const size_t row = (size_t)ctx->Wk * 4;
+  TRY(pin_grow(ctx, ctx->r_new_kp, (done - base) * row, (from - base) * row));
+  CU(cudaMemcpyAsync((char*)ctx->r_new_kp.p + (from - base) * row, ctx->kp.pool.as<uint32_t>() + from * ctx->Wk,
+                     (done - from) * row, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  ctx->pipe_kp_copied = done;
+  return PF_OK;
+}
+
+// pf_submit of a large batch: sub-batches of whole clusters flow through two batch slots, so
+// that the H2D of sub-batch j+1 (up_stream) and the D2H of sub-batch j-1 (copy_stream) run
+// under the kernels of sub-batch j (stream).  The pattern tables are shared, K4 of the
+// sub-batches is ordered by the compute stream, so pattern ids are those of one big batch.
+int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>& subs) {
+  cudaStream_t st = ctx->stream, up = ctx->up_stream;
+  TRY(finalize_pending(ctx));
+  ctx->executed = false;
+  ctx->alt.executed = false;
+  ctx->pipe_rows = ctx->pipe_wide_rows = ctx->pipe_pos = ctx->pipe_pos_wide = 0;
+  ctx->pipe_clusters = 0;
+  ctx->pipe_kp_base = ctx->kp.n;
+  ctx->pipe_kp_copied = ctx->kp.n;
+  ctx->pipe_cp_base = ctx->cp.n;
+  for (double& m : ctx->pipe_ms) m = 0;
+  TRY(pin_ensure(ctx, ctx->r_cl_pattern, std::max<size_t>(8, (size_t)b->n_clusters * 4)));
+  {
+    // row arrays: learned rows-per-base ratio, grown on demand
+    const uint64_t est = (uint64_t)(ctx->row_ratio * 1.3 * (double)b->n_words * 32.0) + 65536;
+    TRY(pin_grow(ctx, ctx->r_row_cluster, est * 4, 0));
+    TRY(pin_grow(ctx, ctx->r_row_count, est * 4, 0));
+    TRY(pin_grow(ctx, ctx->r_row_pattern, est * 4, 0));
+    TRY(pin_grow(ctx, ctx->r_row_kmer, est * 8, 0));
+  }
+  auto swap_slots = [&]() { std::swap(static_cast<BatchState&>(*ctx), ctx->alt); };
+  struct Guard { pf_ctx* c; ~Guard() { c->pipe_mode = false; } } guard{ctx};
+  ctx->pipe_mode = true;
+  int cur = 0;
+  const size_t J = subs.size();
+  ctx->pipe_subs = (uint32_t)J;
+  static const bool dbg = getenv("PF_DEBUG_PIPE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  double t_up = 0, t_ex = 0, t_out = 0, t_fin = 0;
+  CU(cudaEventRecord(ctx->ev_pipe[0], st));
+  TRY(upload_async(ctx, *ctx, b, subs[0], up));
+  TRY(upload_finish(ctx, *ctx, up));
+  for (size_t j = 0; j < J; ++j) {
+    // a helper thread validates, plans and uploads sub-batch j+1 into the other slot while
+    // this thread drives the kernels of sub-batch j (pf_execute blocks on its read-backs)
+    std::thread helper;
+    int up_rc = PF_OK;
+    if (j + 1 < J) {
+      // the other slot's last occupant (sub-batch j-1) must have left: kernels and D2H
+      CU(cudaStreamWaitEvent(up, ctx->ev_exec_end[cur ^ 1], 0));
+      CU(cudaStreamWaitEvent(up, ctx->ev_out_done[cur ^ 1], 0));
+      helper = std::thread([&, j]() {
+        cudaSetDevice(ctx->device);
+        const double t0 = now();
+        up_rc = upload_async(ctx, ctx->alt, b, subs[j + 1], up);
+        t_up += now() - t0;
+      });
+    }
+    // this slot's previous rows must have left the device before they are overwritten
+    int rc = PF_OK;
+    if (cudaStreamWaitEvent(st, ctx->ev_out_done[cur], 0) != cudaSuccess) rc = fail(ctx, PF_ERR_CUDA, "cudaStreamWaitEvent failed");
+    double t0 = now();
+    if (rc == PF_OK) rc = pf_execute(ctx);
+    t_ex += now() - t0;
+    if (rc == PF_OK && cudaEventRecord(ctx->ev_exec_end[cur], st) != cudaSuccess) rc = fail(ctx, PF_ERR_CUDA, "cudaEventRecord failed");
+    t0 = now();
+    if (rc == PF_OK) rc = pipe_enqueue_results(ctx, subs[j], cur);
+    t_out += now() - t0;
+    if (helper.joinable()) helper.join();
+    if (rc != PF_OK) return rc;
+    if (up_rc != PF_OK) return up_rc;
+    t0 = now();
+    if (j + 1 < J) {
+      // sub-batch j's K4 must be over before the next one reserves table space
+      const uint64_t kpb = ctx->kp_base;
+      CU(cudaStreamSynchronize(st));
+      TRY(check_device_error(ctx));
+      ctx->kp.n = kpb + ctx->h_counters.as<uint32_t>()[C_NEW_KP];
+      ctx->executed = false;
+      pipe_add_timings(ctx);
+      TRY(pipe_copy_new_patterns(ctx));
+      swap_slots();
+      cur ^= 1;
+      TRY(upload_finish(ctx, *ctx, up));
+      t_fin += now() - t0;
+    }
+  }
+  if (dbg)
+    fprintf(stderr, "[pf] pipeline: %zu sub-batches, host ms: total %.2f  upload_async %.2f  execute %.2f  enqueue %.2f  finish %.2f\n",
+            J, now() - t_begin, t_up, t_ex, t_out, t_fin);
+  CU(cudaEventRecord(ctx->ev_pipe[1], st));
+  ctx->pipe_pending = true;
+  return PF_OK;
+}
+
+}  // namespace
+
 extern "C" int pf_submit(pf_ctx* ctx, const pf_batch* batch) {
+  if (!ctx) return PF_ERR_INVALID;
+  if (!batch) return fail(ctx, PF_ERR_INVALID, "pf_submit: null batch");
+  if (ctx->pipe_pending) return fail(ctx, PF_ERR_STATE, "pf_submit: results of the previous pf_submit were not collected");
+  if (batch->n_seqs >= ctx->pipe_min_seqs && batch->n_amb_words == 0 && batch->seqs && batch->n_clusters > 1) {
+    CU(cudaSetDevice(ctx->device));
+    const std::vector<SubRange> subs = split_batch(batch, ctx->pipe_target_seqs);
+    if (subs.size() > 1) return submit_pipelined(ctx, batch, subs);
+  }
+  ctx->pipe_subs = 1;
   int r = pf_upload(ctx, batch);
   if (r != PF_OK) return r;
   return pf_execute(ctx);
 }
 
+namespace {
+int collect_pipelined(pf_ctx* ctx, pf_batch_result* out) {
+  cudaStream_t st = ctx->stream;
+  CU(cudaStreamSynchronize(st));
+  TRY(check_device_error(ctx));
+  uint32_t* hcnt = ctx->h_counters.as<uint32_t>();
+  ctx->kp.n = ctx->kp_base + hcnt[C_NEW_KP];      // last sub-batch
+  ctx->executed = false;
+  ctx->alt.executed = false;
+  ctx->pipe_pending = false;
+  pipe_add_timings(ctx);
+  const uint64_t new_kp = ctx->kp.n - ctx->pipe_kp_base, new_cp = ctx->cp.n - ctx->pipe_cp_base;
+  CU(cudaEventRecord(ctx->ev_d2h[0], st));
+  TRY(pipe_copy_new_patterns(ctx));
+  if (!ctx->r_new_kp.p) TRY(pin_ensure(ctx, ctx->r_new_kp, 8));
+  TRY(pin_ensure(ctx, ctx->r_new_cp, std::max<size_t>(8, new_cp * ctx->W * 4)));
+  if (new_cp)
+    CU(cudaMemcpyAsync(ctx->r_new_cp.p, ctx->cp.pool.as<uint32_t>() + ctx->pipe_cp_base * ctx->W, new_cp * ctx->W * 4,
+                       cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(ctx->ev_d2h[1], st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(ctx->copy_stream));
+  if (out) {
+    memset(out, 0, sizeof *out);
+    out->n_rows = ctx->pipe_rows;
+    out->row_cluster = ctx->r_row_cluster.as<uint32_t>();
+    out->row_kmer = ctx->r_row_kmer.as<uint64_t>();
+    out->row_count = ctx->r_row_count.as<uint32_t>();
+    out->row_pattern = ctx->r_row_pattern.as<uint32_t>();
+    out->n_wide_rows = ctx->pipe_wide_rows;
+    out->wide_row_cluster = ctx->r_wrow_cluster.as<uint32_t>();
+    out->wide_row_kmer = ctx->r_wrow_kmer.as<uint64_t>();
+    out->wide_row_count = ctx->r_wrow_count.as<uint32_t>();
+    out->wide_row_pattern = ctx->r_wrow_pattern.as<uint32_t>();
+    out->n_clusters = ctx->pipe_clusters;
+    out->cluster_pattern = ctx->r_cl_pattern.as<uint32_t>();
+    out->kmer_pattern_base = ctx->pipe_kp_base;
+    out->n_new_kmer_patterns = new_kp;
+    out->new_kmer_patterns = ctx->r_new_kp.as<uint32_t>();
+    out->cluster_pattern_base = ctx->pipe_cp_base;
+    out->n_new_cluster_patterns = new_cp;
+    out->new_cluster_patterns = ctx->r_new_cp.as<uint32_t>();
+    out->n_pos = ctx->pipe_pos;
+    out->pos_kmer = ctx->r_pos_kmer.as<uint64_t>();
+    out->pos_seq = ctx->r_pos_seq.as<uint32_t>();
+    out->pos_contig_start = ctx->r_pos_cstart.as<int32_t>();
+    out->pos_gene_start = ctx->r_pos_gstart.as<int32_t>();
+    out->pos_flags = ctx->r_pos_flags.as<uint8_t>();
+    out->pos_wide_kmer = ctx->r_pos_wide.as<uint64_t>();
+    out->n_pos_wide = ctx->pipe_pos_wide;
+  }
+  pf_stats& s = ctx->stats;
+  s.batches++;
+  s.kmer_patterns = ctx->kp.n;
+  s.cluster_patterns = ctx->cp.n;
+  s.total_launches = ctx->launches;
+  s.ms_h2d = (float)ctx->pipe_ms[0]; s.ms_extract = (float)ctx->pipe_ms[1]; s.ms_hist = (float)ctx->pipe_ms[2];
+  s.ms_sort = (float)ctx->pipe_ms[3]; s.ms_mark = (float)ctx->pipe_ms[4]; s.ms_count = (float)ctx->pipe_ms[5];
+  s.ms_reduce = (float)ctx->pipe_ms[6]; s.ms_dedup = (float)ctx->pipe_ms[7];
+  float m = 0;
+  if (cudaEventElapsedTime(&m, ctx->ev_pipe[0], ctx->ev_pipe[1]) == cudaSuccess) s.ms_total = m;
+  if (cudaEventElapsedTime(&m, ctx->ev_d2h[0], ctx->ev_d2h[1]) == cudaSuccess) s.ms_d2h = m;
+  return PF_OK;
+}
+}  // namespace
+
 extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
   if (!ctx) return PF_ERR_INVALID;
+  if (ctx->pipe_pending) { CU(cudaSetDevice(ctx->device)); return collect_pipelined(ctx, out); }
   if (!ctx->executed) return fail(ctx, PF_ERR_STATE, "pf_collect: nothing executed");
   CU(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;

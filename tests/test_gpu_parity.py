@@ -262,6 +262,23 @@ def test_block_engine_merges_misaligned_copies():
         assert out["stats"]["engine"] == 2
 
 
+@pytest.mark.parametrize("engine", ["block", "records"])
+def test_pipelined_submit_matches_oracle(engine, monkeypatch):
+    """pf_submit of a batch above the split threshold: sub-batches of whole clusters through
+    two device slots (H2D / kernels / D2H overlapped); rows, pattern ids, cluster rows and
+    positional records must be those of the one big batch."""
+    monkeypatch.setenv("PF_PIPELINE_SEQS", "1024")       # sub-batches of ~1024 sequences
+    rng = np.random.default_rng(21)
+    S, k = 60, 31
+    items, stroi = _random_items(rng, S, k, 70, 260)
+    names = sorted(items[0][0].keys())
+    empty = ({s: [] for s in names}, "cl_empty", np.zeros(S, dtype=int))
+    items = items[:20] + [empty] + items[20:50] + [empty, empty] + items[50:] + [empty]
+    out, want = _compare_with_oracle(items, stroi, S, k, True, True, False, 0.02,
+                                     batch_clusters=len(items), **ENGINES[engine])
+    assert out["stats"]["sub_batches"] >= 3
+
+
 def test_empty_and_ragged_batches():
     rng = np.random.default_rng(3)
     items, stroi = _random_items(rng, 12, 31, 3, 120)
