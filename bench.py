@@ -247,7 +247,8 @@ def workload_config(args):
                         f"gene clusters (~1 kb + 100 bp flanks = {args.gene_len} bp), first pass, k={args.k}",
             "samples": args.samples, "clusters_per_gpu": args.clusters, "gene_len": args.gene_len,
             "k": args.k, "maf": args.maf, "consider_missing": bool(args.consider_missing),
-            "l2": "inputs (>= 0.6 GB packed bases, >= 28 GB of records per step) far exceed the 126 MB L2"}
+            "l2": "inputs larger than L2: every step reads the whole packed plane (0.6 GB at 500 x 4000) and "
+                  "writes / re-reads GBs of partial rows, far beyond the 126 MB L2; nothing survives between steps"}
 
 
 # --------------------------------------------------------------------------
@@ -373,11 +374,10 @@ def main():
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        h2d = (hb.packed.nbytes + len(hb.seqs) * 64 + len(hb.clusters) * 32 + hb.presence.nbytes
-               + (M // 4096 + len(hb.clusters)) * 16)
+        h2d = hb.packed.nbytes + len(hb.seqs) * 64 + len(hb.clusters) * 32 + hb.presence.nbytes
         e2e = {"value": total_bases * args.steps / dt, "unit": "bases/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": 1e3 * dt / args.steps}
+               "ms_per_step": 1e3 * dt / args.steps, "sub_batches": ctx.stats()["sub_batches"]}
 
     if rank == 0:
         peaks = {}
@@ -388,15 +388,32 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         fused = stage_ms["ms_extract"] < 0.2          # K1 ran inside the histogram / first pass
+        block = st["engine"] == 2                     # block aggregation: no records at all
         pass_ms = stage_ms["ms_sort"] / max(1, passes)
         k1_bytes = n_bases / 4 + 32 * len(hb.seqs) + R_BYTES * M
         pass_bytes = 2 * R_BYTES * M                                       # SURVEY 8(d) one K2 pass
+        W4 = 4 * ((S + 31) // 32)
         tr = {}
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         except Exception:
             pass
-        if fused:
+        n_launch = passes
+        if block:
+            kernel = ("kA_block_aggregate<canonical> (K1 extraction + all of K2 + the grouping of K3 in one "
+                      "kernel: sequence chunks and k-mers are grouped in shared memory, no record reaches HBM)")
+            pass_ms = stage_ms["ms_sort"]
+            n_launch = 1
+            alg_bytes = k1_bytes
+            partial_bytes = st["partial_rows"] * (8 + 4 * ((W4 // 4 + 3) // 4 * 4))
+            compulsory = n_bases / 4 + 16 * len(hb.seqs) + partial_bytes
+            per_rec = tr.get("kA_block_aggregate_dram_bytes_per_window")
+            note = ("algorithmic = SURVEY 8(d) K1 only (N/4 + 32*seqs + R*M): the figure of the cheapest stage this "
+                    "kernel replaces; it also does the declared K2 (195 B/base) and the record read of K3 without "
+                    "touching HBM, so its real DRAM traffic (traffic / compulsory: packed bases in, partial "
+                    "(k-mer, bitset) rows out) is ~1/5 of that and it is bound by instruction issue and "
+                    "shared-memory latency, not by HBM; launch_ms includes the rescue launches and their host syncs")
+        elif fused:
             kernel = "k2_extract_scatter<canonical> (K1 extraction fused into the first radix pass)"
             alg_bytes = k1_bytes + pass_bytes
             compulsory = n_bases / 4 + R_BYTES * M
@@ -418,22 +435,36 @@ def main():
             "k2_sort_declared_8_passes": 8 * M + 8 * 2 * R_BYTES * M,
             "k3_reduce": R_BYTES * M + 12 * U + rows * 4 * ((S + 31) // 32),
         }
-        W4 = 4 * ((S + 31) // 32)
         k3_ms = stage_ms["ms_mark"] + stage_ms["ms_count"] + stage_ms["ms_reduce"]
-        stages = {
-            "k1_histogram(+extract)": {"ms": stage_ms["ms_extract"] + stage_ms["ms_hist"],
-                                       "reads_GB": n_bases / 4 / 1e9},
-            "k2_radix_passes": {"ms": stage_ms["ms_sort"], "passes": passes, "first_pass_fused_with_k1": fused,
-                                "alg_GBps": (passes * pass_bytes + (k1_bytes if fused else 0)) /
-                                stage_ms["ms_sort"] / 1e6},
-            "k3_reduce(mark+local+rescue, incl. host sync)": {
-                "ms": k3_ms, "alg_GBps": alg["k3_reduce"] / k3_ms / 1e6,
-                "alg_bytes": alg["k3_reduce"]},
-            "k4_dedup": {"ms": stage_ms["ms_dedup"],
-                         "alg_GBps": (rows * W4 + st["kmer_patterns"] * W4 + 4 * rows) /
-                         max(stage_ms["ms_dedup"], 1e-6) / 1e6},
-            "raw_ms": {k_: round(v_, 3) for k_, v_ in stage_ms.items()},
-        }
+        k4_stage = {"ms": stage_ms["ms_dedup"],
+                    "alg_GBps": (rows * W4 + st["kmer_patterns"] * W4 + 4 * rows) /
+                    max(stage_ms["ms_dedup"], 1e-6) / 1e6}
+        if block:
+            stages = {
+                "kA_block_aggregate(+rescue launches, host syncs)": {
+                    "ms": stage_ms["ms_sort"], "reads_GB": n_bases / 4 / 1e9,
+                    "partial_rows": st["partial_rows"], "writes_GB": partial_bytes / 1e9,
+                    "alg_GBps_k1_k2_k3read_declared": (k1_bytes + alg["k2_sort_declared_8_passes"] + R_BYTES * M) /
+                    stage_ms["ms_sort"] / 1e6},
+                "kB_merge(kB1 insert + kB2 fold + kB3 emit, incl. host sync)": {
+                    "ms": k3_ms, "alg_bytes": 2 * partial_bytes + 12 * U + rows * W4,
+                    "alg_GBps": (2 * partial_bytes + 12 * U + rows * W4) / k3_ms / 1e6},
+                "k4_dedup": k4_stage,
+                "raw_ms": {k_: round(v_, 3) for k_, v_ in stage_ms.items()},
+            }
+        else:
+            stages = {
+                "k1_histogram(+extract)": {"ms": stage_ms["ms_extract"] + stage_ms["ms_hist"],
+                                           "reads_GB": n_bases / 4 / 1e9},
+                "k2_radix_passes": {"ms": stage_ms["ms_sort"], "passes": passes, "first_pass_fused_with_k1": fused,
+                                    "alg_GBps": (passes * pass_bytes + (k1_bytes if fused else 0)) /
+                                    stage_ms["ms_sort"] / 1e6},
+                "k3_reduce(mark+local+rescue, incl. host sync)": {
+                    "ms": k3_ms, "alg_GBps": alg["k3_reduce"] / k3_ms / 1e6,
+                    "alg_bytes": alg["k3_reduce"]},
+                "k4_dedup": k4_stage,
+                "raw_ms": {k_: round(v_, 3) for k_, v_ in stage_ms.items()},
+            }
         line = {
             "metric": "input_bases_per_s", "value": value, "unit": "bases/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step,
@@ -443,13 +474,14 @@ def main():
             "bases_per_step_per_gpu": n_bases, "kmer_instances_per_step_per_gpu": M,
             "unique_kmers_per_step_per_gpu": U, "rows_per_step_per_gpu": rows,
             "patterns_per_gpu": st["kmer_patterns"],
+            "engine": {0: "records (partition mode)", 1: "records (full sort)", 2: "block aggregation"}[st["engine"]],
             "roofline": {"bound": "hbm", "kernel": kernel,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
                          "compulsory_bytes_per_launch": compulsory,
                          "frac_compulsory": compulsory / (pass_ms * 1e-3) / 1e9 / peak,
-                         "launch_ms": pass_ms, "launches_per_step": passes, "note": note},
+                         "launch_ms": pass_ms, "launches_per_step": n_launch, "note": note},
             "whole_step_alg_GBps_declared_model": sum(alg.values()) / (ms_step * 1e-3) / 1e9,
             "stages": stages,
             "end_to_end_alg_bytes_per_base_declared": sum(alg.values()) / n_bases,

@@ -188,6 +188,7 @@ struct BlkPlan {
   uint32_t n_clusters;
   uint32_t block_windows;        // B = kBlkRun
   uint32_t slots, cslots;        // k-mer table / chunk table sizes of kA (powers of two)
+  uint32_t cap;                  // k-mer rows of kA (dense, handed out on insertion)
   uint32_t W, WP;                // bitset words, slab row stride (W rounded up to 4)
 };
 
@@ -214,17 +215,17 @@ struct ARunView {
   uint16_t* rowid;         // [slots]
   uint32_t mask, shift, cmask, cshift, cap, ccap;
 };
-__host__ __device__ inline uint32_t blkA_cap(uint32_t slots) { return slots * 5u / 8u; }
 __host__ __device__ inline uint32_t blkA_ccap(uint32_t cslots) { return cslots * 3u / 4u; }
-__host__ __device__ inline uint32_t blkA_smem_bytes(uint32_t slots, uint32_t cslots, uint32_t W) {
-  const uint32_t cap = blkA_cap(slots), ccap = blkA_ccap(cslots), WS = W | 1u;
+// slots: k-mer key slots (power of two); cap: k-mer rows (<= 13/16 slots); cslots: chunk slots
+__host__ __device__ inline uint32_t blkA_smem_bytes(uint32_t slots, uint32_t cap, uint32_t cslots, uint32_t W) {
+  const uint32_t ccap = blkA_ccap(cslots), WS = W | 1u;
   return (uint32_t)sizeof(BlkHead) + slots * 8u + (cap + 1u) * 8u + ccap * 16u + cslots * 4u +
          (cap + 1u) * WS * 4u + ccap * WS * 4u + slots * 2u + 16u;
 }
-__device__ __forceinline__ ARunView arun_view(unsigned char* raw, uint32_t slots, uint32_t cslots, uint32_t W) {
+__device__ __forceinline__ ARunView arun_view(unsigned char* raw, uint32_t slots, uint32_t cap, uint32_t cslots, uint32_t W) {
   ARunView a;
   const uint32_t WS = W | 1u;
-  a.cap = blkA_cap(slots);
+  a.cap = cap;
   a.ccap = blkA_ccap(cslots);
   a.h = reinterpret_cast<BlkHead*>(raw);
   a.keys = reinterpret_cast<uint64_t*>(raw + sizeof(BlkHead));
@@ -326,7 +327,7 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
                    uint32_t* __restrict__ rescue_items /* out: items whose table overflowed */) {
   extern __shared__ __align__(16) unsigned char blk_raw[];
   const uint32_t W = plan.W, WS = W | 1u;
-  const ARunView a = arun_view(blk_raw, plan.slots, plan.cslots, W);
+  const ARunView a = arun_view(blk_raw, plan.slots, plan.cap, plan.cslots, W);
   const uint32_t tid = threadIdx.x;
   const uint32_t item = item_list ? item_list[blockIdx.x] : blockIdx.x;
 
@@ -579,9 +580,21 @@ kB3_emit(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ sl
     }
     return cnt;
   };
-  // pass 1: rows this warp will write
+  // pass 1: rows this warp will write (verdicts of the first 256 partial rows stay in registers)
   uint32_t my = 0;
-  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+  uint32_t verdict[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    verdict[it] = 0u;
+    if ((uint32_t)it * 32u < n) {
+      bool owner;
+      const uint32_t cnt = count_of((uint32_t)it * 32u + lane, owner);
+      const bool pass = owner && cnt >= cl.lo && cnt <= cl.hi;
+      verdict[it] = pass ? (0x80000000u | cnt) : 0u;
+      my += __popc(__ballot_sync(kFull, pass));
+    }
+  }
+  for (uint32_t i0 = 256; i0 < n; i0 += 32) {
     bool owner;
     const uint32_t cnt = count_of(i0 + lane, owner);
     my += __popc(__ballot_sync(kFull, owner && cnt >= cl.lo && cnt <= cl.hi));
@@ -603,11 +616,7 @@ kB3_emit(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ sl
   if (!cta_ok || my == 0) return;
   // pass 2: write them (the bitsets come back from L2)
   uint32_t g = cta_base + w_pass[warp];
-  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-    const uint32_t i = i0 + lane;
-    bool owner;
-    const uint32_t cnt = count_of(i, owner);
-    const bool pass = owner && cnt >= cl.lo && cnt <= cl.hi;
+  auto emit = [&](uint32_t i, bool pass, uint32_t cnt) {
     const uint32_t mp = __ballot_sync(kFull, pass);
     if (pass) {
       const size_t gi = (size_t)g + __popc(mp & lanemask_lt());
@@ -627,6 +636,14 @@ kB3_emit(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ sl
       if (out.key_words > W) dst[W] = out.cluster_pattern[c];
     }
     g += __popc(mp);
+  };
+#pragma unroll
+  for (int it = 0; it < 8; ++it)
+    if ((uint32_t)it * 32u < n) emit((uint32_t)it * 32u + lane, (verdict[it] >> 31) != 0u, verdict[it] & 0x7fffffffu);
+  for (uint32_t i0 = 256; i0 < n; i0 += 32) {
+    bool owner;
+    const uint32_t cnt = count_of(i0 + lane, owner);
+    emit(i0 + lane, owner && cnt >= cl.lo && cnt <= cl.hi, cnt);
   }
 }
 

@@ -192,7 +192,7 @@ struct pf_ctx : BatchState {
   // block aggregation (k3_block.cuh): no records, partial (k-mer, bitset) rows per position block
   bool block_mode = false;       // S <= 1024 and not disabled: kA_block_aggregate + kB1..kB3
   uint32_t block_windows = 16;   // windows per position block (= kBlkRun)
-  uint32_t blk_slots = 512, blk_cslots = 128;   // shared-memory table sizes of kA (k-mers, chunks)
+  uint32_t blk_slots = 1024, blk_cap = 448, blk_cslots = 128;   // shared memory of kA: k-mer key slots / rows, chunk slots
   uint32_t block_fallbacks = 0;
   double partial_ratio = 1.0 / 16;   // partial rows per window, learned from earlier batches
   uint64_t partial_cap = 0;
@@ -287,7 +287,7 @@ bool debug_sync(const char* name) {
 
 inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
 constexpr int kGridPersist = 148 * 4;
-constexpr uint32_t kBlkMaxSmem = 200u * 1024u;   // largest kA / kB table we ask for
+constexpr uint32_t kBlkMaxSmem = 220u * 1024u;   // largest kA table we ask for
 
 // counters layout in d_counters
 enum { C_TICKET_N = 0, C_TICKET_W = 1, C_RUNS_N = 2, C_RUNS_W = 3, C_ERR = 4, C_ROWS_N = 5,
@@ -410,19 +410,28 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
     // (about one haplotype per 30 samples and position), a quarter as many chunk slots;
     // overflowing blocks are rerun with both doubled
     ctx->block_windows = (uint32_t)kBlkRun;
+    // (about one new k-mer per sample and run of 16 windows, plus the haplotypes' own)
     uint32_t slots = 256;
-    while (slots < p->n_samples && slots < 4096u) slots *= 2;
+    while (slots < 2u * p->n_samples && slots < 4096u) slots *= 2;
     if (const char* e = getenv("PF_BLOCK_SLOTS")) {
       const int v = atoi(e);
       if (v >= 64 && v <= 8192 && (v & (v - 1)) == 0) slots = (uint32_t)v;
     }
-    uint32_t cslots = std::max<uint32_t>(64u, slots / 4u);
+    uint32_t cap = std::min<uint32_t>(slots * 13u / 16u, std::max<uint32_t>(96u, p->n_samples * 9u / 10u));
+    if (const char* e = getenv("PF_BLOCK_CAP")) {
+      const int v = atoi(e);
+      if (v >= 32 && (uint32_t)v <= slots * 13u / 16u) cap = (uint32_t)v;
+    }
+    uint32_t cslots = std::max<uint32_t>(64u, slots / 8u);
     if (const char* e = getenv("PF_BLOCK_CSLOTS")) {
       const int v = atoi(e);
       if (v >= 32 && v <= 8192 && (v & (v - 1)) == 0) cslots = (uint32_t)v;
     }
-    while (slots > 64u && blkA_smem_bytes(slots, cslots, ctx->W) > kBlkMaxSmem) { slots /= 2; cslots = std::max<uint32_t>(32u, cslots / 2); }
+    while (slots > 64u && blkA_smem_bytes(slots, cap, cslots, ctx->W) > kBlkMaxSmem) {
+      slots /= 2; cap /= 2; cslots = std::max<uint32_t>(32u, cslots / 2);
+    }
     ctx->blk_slots = slots;
+    ctx->blk_cap = cap;
     ctx->blk_cslots = cslots;
     if (p->k == 32 && !p->canonical) ctx->block_mode = false;   // all-T k-mer == the empty-slot mark
     cudaFuncSetAttribute(kA_block_aggregate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
@@ -1220,6 +1229,7 @@ BlkPlan block_plan(const pf_ctx* ctx) {
   bp.n_clusters = ctx->n_clusters;
   bp.block_windows = ctx->block_windows;
   bp.slots = ctx->blk_slots;
+  bp.cap = ctx->blk_cap;
   bp.cslots = ctx->blk_cslots;
   bp.W = ctx->W;
   bp.WP = (ctx->W + 3u) & ~3u;
@@ -1228,16 +1238,17 @@ BlkPlan block_plan(const pf_ctx* ctx) {
 
 // items == nullptr: all (cluster, block) items with the context's table size; else the listed
 // items (a rescue launch) with `slots` slots.  Items that overflow are appended to `rescue_out`.
-int launch_block_aggregate(pf_ctx* ctx, const uint32_t* items, uint32_t n, uint32_t slots, uint32_t cslots,
-                           uint32_t* rescue_out) {
+int launch_block_aggregate(pf_ctx* ctx, const uint32_t* items, uint32_t n, uint32_t slots, uint32_t cap,
+                           uint32_t cslots, uint32_t* rescue_out) {
   if (n == 0) return PF_OK;
   cudaStream_t st = ctx->stream;
   BlkPlan bp = block_plan(ctx);
   bp.slots = slots;
+  bp.cap = cap;
   bp.cslots = cslots;
   const uint32_t cap32 = (uint32_t)std::min<uint64_t>(ctx->partial_cap, 0xfffffff0u);
   uint32_t* counters = ctx->d_counters.as<uint32_t>() + C_LOCAL;
-  const uint32_t smem = blkA_smem_bytes(slots, cslots, ctx->W);
+  const uint32_t smem = blkA_smem_bytes(slots, cap, cslots, ctx->W);
 #define PF_KA(CANON)                                                                                   \
   kA_block_aggregate<CANON><<<n, kBlkThreads, smem, st>>>(                                             \
       ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seq_lite.as<SeqLite>(), bp,   \
@@ -1384,7 +1395,8 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       TRY(dev_ensure(ctx, ctx->d_slab_keys, ctx->partial_cap * 8));
       TRY(dev_ensure(ctx, ctx->d_slab_rows, ctx->partial_cap * WP * 4));
       CU(cudaMemsetAsync(counters + C_LOCAL, 0, LC_COUNT * 4, st));
-      TRY(launch_block_aggregate(ctx, nullptr, ctx->n_items, ctx->blk_slots, ctx->blk_cslots, ctx->d_rescue[0].as<uint32_t>()));
+      TRY(launch_block_aggregate(ctx, nullptr, ctx->n_items, ctx->blk_slots, ctx->blk_cap, ctx->blk_cslots,
+                                 ctx->d_rescue[0].as<uint32_t>()));
       STAGE("kA_block_aggregate");
       TRY(passes_width<Key128>(ctx, Wd, C_TICKET_W));
       TRY(mark_width<Key128>(ctx, Wd, C_TICKET_MARK_W, C_RUNS_W, false));
@@ -1396,34 +1408,52 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       bool too_big = false;
       static const bool dbg = getenv("PF_DEBUG_BLOCK") != nullptr;
       if (dbg)
-        fprintf(stderr, "[pf] kA: items %u slots %u cslots %u -> overflow %u rescue %u partials %u part_ovf %u\n",
-                ctx->n_items, ctx->blk_slots, ctx->blk_cslots, hcnt[C_LOCAL + LC_TABLE_OVERFLOW],
+        fprintf(stderr, "[pf] kA: items %u slots %u cap %u cslots %u -> overflow %u rescue %u partials %u part_ovf %u\n",
+                ctx->n_items, ctx->blk_slots, ctx->blk_cap, ctx->blk_cslots, hcnt[C_LOCAL + LC_TABLE_OVERFLOW],
                 hcnt[C_LOCAL + LC_RESCUE], hcnt[C_LOCAL + LC_PARTIALS], hcnt[C_LOCAL + LC_PARTIAL_OVERFLOW]);
       {
-        uint32_t slots = ctx->blk_slots, cslots = ctx->blk_cslots;
+        uint32_t slots = ctx->blk_slots, cap = ctx->blk_cap, cslots = ctx->blk_cslots;
         int cur = 0;
         const uint32_t first_rescue = hcnt[C_LOCAL + LC_RESCUE];
         while (hcnt[C_LOCAL + LC_TABLE_OVERFLOW] == 1u) {
           const uint32_t n_resc = hcnt[C_LOCAL + LC_RESCUE];
-          if (slots >= 8192u || blkA_smem_bytes(slots * 2u, cslots * 2u, ctx->W) > kBlkMaxSmem) { too_big = true; break; }
-          slots *= 2;
-          cslots *= 2;
+          // twice the key slots, as many rows as then fit (the chunk table stays: a full one only
+          // sends runs down the direct path)
+          uint32_t slots2 = slots * 2u, cap2 = 0;
+          if (slots2 <= 8192u && blkA_smem_bytes(slots2, 0u, cslots, ctx->W) < kBlkMaxSmem) {
+            const uint32_t per_row = 8u + (ctx->W | 1u) * 4u;
+            const uint32_t fit = (kBlkMaxSmem - blkA_smem_bytes(slots2, 0u, cslots, ctx->W)) / per_row;
+            cap2 = std::min<uint32_t>(std::min<uint32_t>(fit, slots2 * 13u / 16u),
+                                      std::max<uint32_t>(cap * 2u, slots2 * 5u / 8u));
+          }
+          if (cap2 <= cap) {        // no more rows with more slots: try all the rows the current slots allow
+            slots2 = slots;
+            const uint32_t per_row = 8u + (ctx->W | 1u) * 4u;
+            const uint32_t fit = (kBlkMaxSmem - blkA_smem_bytes(slots, 0u, cslots, ctx->W)) / per_row;
+            cap2 = std::min<uint32_t>(fit, slots * 13u / 16u);
+          }
+          if (cap2 <= cap) { too_big = true; break; }
+          slots = slots2;
+          cap = cap2;
           CU(cudaMemsetAsync(counters + C_LOCAL + LC_TABLE_OVERFLOW, 0, 4, st));
           CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));
-          TRY(launch_block_aggregate(ctx, ctx->d_rescue[cur].as<uint32_t>(), n_resc, slots, cslots,
+          TRY(launch_block_aggregate(ctx, ctx->d_rescue[cur].as<uint32_t>(), n_resc, slots, cap, cslots,
                                      ctx->d_rescue[cur ^ 1].as<uint32_t>()));
           cur ^= 1;
           mirror_counters<<<1, 32, 0, st>>>(hcnt, counters, C_COUNT);
           CU(cudaStreamSynchronize(st));
           if (dbg)
-            fprintf(stderr, "[pf] kA rescue: %u items slots %u cslots %u -> overflow %u rescue %u\n", n_resc, slots,
-                    cslots, hcnt[C_LOCAL + LC_TABLE_OVERFLOW], hcnt[C_LOCAL + LC_RESCUE]);
+            fprintf(stderr, "[pf] kA rescue: %u items slots %u cap %u cslots %u -> overflow %u rescue %u\n", n_resc, slots,
+                    cap, cslots, hcnt[C_LOCAL + LC_TABLE_OVERFLOW], hcnt[C_LOCAL + LC_RESCUE]);
         }
-        // many rescued blocks: start the next batches with the larger tables
-        if (!too_big && first_rescue > ctx->n_items / 8u && ctx->blk_slots < 8192u &&
-            blkA_smem_bytes(ctx->blk_slots * 2u, ctx->blk_cslots * 2u, ctx->W) <= kBlkMaxSmem) {
-          ctx->blk_slots *= 2;
-          ctx->blk_cslots *= 2;
+        // many rescued blocks: start the next batches with more rows (and key slots to match)
+        if (!too_big && first_rescue > ctx->n_items / 8u) {
+          uint32_t ns = ctx->blk_slots, ncap = ctx->blk_cap + ctx->blk_cap / 2;
+          while (ncap > ns * 13u / 16u) ns *= 2;
+          if (ns <= 8192u && blkA_smem_bytes(ns, ncap, ctx->blk_cslots, ctx->W) <= kBlkMaxSmem) {
+            ctx->blk_slots = ns;
+            ctx->blk_cap = ncap;
+          }
         }
       }
       CU(cudaEventRecord(ctx->ev[EV_SORT], st));

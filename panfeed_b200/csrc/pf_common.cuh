@@ -131,7 +131,10 @@ __device__ __forceinline__ uint32_t lanemask_lt() { return (1u << lane_id()) - 1
 // ---- hash of a pattern key (W words); commutative over words so a warp can
 // reduce it in any order.  Same function picks the owner rank in the exchange.
 __host__ __device__ __forceinline__ uint64_t word_hash(uint32_t w, uint32_t i) {
-  return fmix64(((uint64_t)w << 32 | (uint64_t)(i + 1u)) * 0x9e3779b97f4a7c15ULL + 0x632be59bd9b4e019ULL);
+  // one odd multiply of (position, word) + one xor-shift: the sum over the words is
+  // finalised with fmix64 by the caller, and table / owner decisions never rest on the hash
+  const uint64_t x = (((uint64_t)(i + 1u) << 32) | (uint64_t)w) * 0x9e3779b97f4a7c15ULL;
+  return x ^ (x >> 29);
 }
 
 // ---- device-side descriptors (built on the host in pf_upload) -------------
