@@ -211,6 +211,9 @@ struct pf_ctx : BatchState {
   pf_stats stats{};
   std::atomic<uint32_t> launches{0};
   // pipelined submit (submit_pipelined / collect_pipelined)
+  bool prefetch_rows = false;    // start the D2H of the row arrays under K4 (PF_PREFETCH_ROWS=1): off by
+                                 // default, the copy engine it occupies delays every small read-back that
+                                 // follows (multi-GPU exchange), and large submits are pipelined anyway
   bool pipe_pending = false;     // results of a pipelined submit wait for pf_collect
   uint32_t pipe_subs = 1;        // sub-batches of the last submit
   bool pipe_mode = false;        // inside submit_pipelined: pf_execute leaves the D2H to it
@@ -379,6 +382,7 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
     cudaEventCreateWithFlags(&ctx->ev_out_done[i], cudaEventDisableTiming);
     cudaEventCreate(&ctx->ev_pipe[i]);
   }
+  if (const char* e = getenv("PF_PREFETCH_ROWS")) ctx->prefetch_rows = atoi(e) != 0;
   if (const char* e = getenv("PF_PIPELINE_SEQS")) {      // 0 disables the pipelined submit
     const long v = atol(e);
     if (v <= 0) ctx->pipe_min_seqs = 0xffffffffu;
@@ -780,7 +784,7 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
   TRY(dev_ensure(ctx, B.d_clusters, std::max<size_t>(1, b->n_clusters) * sizeof(ClusterDev)));
   TRY(dev_ensure(ctx, B.d_presence, std::max<size_t>(1, (size_t)b->n_clusters * W) * 4));
   TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4));
-  TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4));
+  TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 32 * 4));
   for (WidthState* w : {&B.nar, &B.wid}) {
     TRY(dev_ensure(ctx, w->tiles, std::max<size_t>(1, w->n_tiles) * sizeof(TileDev)));
     TRY(dev_ensure(ctx, w->seg_start, std::max<size_t>(1, b->n_clusters) * 4));
@@ -1071,7 +1075,8 @@ int dedup(pf_ctx* ctx, PatternSpace& s, const uint32_t* cand, uint32_t n, DevBuf
 int finalize_pending(pf_ctx* ctx) {
   if (!ctx->executed) return PF_OK;
   CU(cudaStreamSynchronize(ctx->stream));
-  if (ctx->rows_prefetched) CU(cudaStreamSynchronize(ctx->copy_stream));
+  // (a row prefetch of results nobody collected may still be draining on the copy stream: it is
+  //  not waited for — the next prefetch queues behind it on that stream, pf_collect syncs it)
   ctx->kp.n = ctx->kp_base + ctx->h_counters.as<uint32_t>()[C_NEW_KP];
   return PF_OK;
 }
@@ -1632,7 +1637,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   // the (cluster, k-mer, count) arrays of the rows are final: start their D2H on the copy
   // stream while K4 numbers the patterns
   ctx->rows_prefetched = false;
-  if (rows && !ctx->pipe_mode) {
+  if (rows && !ctx->pipe_mode && ctx->prefetch_rows) {
     TRY(pin_ensure(ctx, ctx->r_row_cluster, rows * 4));
     TRY(pin_ensure(ctx, ctx->r_row_count, rows * 4));
     TRY(pin_ensure(ctx, ctx->r_row_kmer, std::max<size_t>(8, (size_t)N.n_rows * 8)));
@@ -2238,21 +2243,33 @@ x_classify(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
            uint32_t* __restrict__ pos, uint32_t* __restrict__ counts) {
   const uint32_t lane = lane_id();
   const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += total_warps) {
-    const uint32_t* key = pool + (size_t)e * key_words;
-    uint64_t h = 0;
-    for (uint32_t w = lane; w < key_words; w += 32) {
-      uint32_t v = key[w];
-      if (mask_remap && w == key_words - 1) v = mask_remap[v];
-      h += word_hash(v, w);
-    }
+  // a warp takes 32 consecutive patterns: it hashes them one after the other (all lanes on one
+  // key), then hands out their bucket positions with ONE atomic per distinct owner — a counter
+  // per rank shared by millions of patterns would serialise in L2
+  for (uint32_t e0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; e0 < n; e0 += total_warps * 32u) {
+    uint32_t my_owner = 0xffffffffu;
+    const uint32_t cnt = min(32u, n - e0);
+    for (uint32_t p = 0; p < cnt; ++p) {
+      const uint32_t* key = pool + (size_t)(e0 + p) * key_words;
+      uint64_t h = 0;
+      for (uint32_t w = lane; w < key_words; w += 32) {
+        uint32_t v = key[w];
+        if (mask_remap && w == key_words - 1) v = mask_remap[v];
+        h += word_hash(v, w);
+      }
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) h += __shfl_xor_sync(kFull, h, m);
-    h = fmix64(h);
-    if (lane == 0) {
-      const uint32_t o = (uint32_t)((h >> 32) % world);
-      owner[e] = o;
-      pos[e] = atomicAdd(&counts[o], 1u);
+      for (int m = 16; m >= 1; m >>= 1) h += __shfl_xor_sync(kFull, h, m);
+      h = fmix64(h);
+      if (lane == p) my_owner = (uint32_t)((h >> 32) % world);
+    }
+    const uint32_t m = __match_any_sync(kFull, my_owner);
+    if (lane < cnt) {
+      const int leader = __ffs(m) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(&counts[my_owner], (uint32_t)__popc(m));
+      base = __shfl_sync(m, base, leader);
+      owner[e0 + lane] = my_owner;
+      pos[e0 + lane] = base + __popc(m & lanemask_lt());
     }
   }
 }
@@ -2327,8 +2344,12 @@ extern "C" int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t wor
     const uint32_t grid = std::min<uint32_t>(cdiv(n, 8), kGridPersist);
     x_classify<<<grid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev, world,
                                      s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(), s.x_counts.as<uint32_t>());
-    CU(cudaMemcpyAsync(counts.data(), s.x_counts.p, world * 4, cudaMemcpyDeviceToHost, st));
+    if (world > 32) return fail(ctx, PF_ERR_UNSUPPORTED, "exchange over more than 32 ranks");
+    TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 32 * 4));
+    uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;
+    mirror_counters<<<1, 32, 0, st>>>(hx, s.x_counts.as<uint32_t>(), world);
     CU(cudaStreamSynchronize(st));
+    for (uint32_t r = 0; r < world; ++r) counts[r] = hx[r];
     for (uint32_t r = 1; r < world; ++r) offsets[r] = offsets[r - 1] + counts[r - 1];
     CU(cudaMemcpyAsync(s.x_counts.as<uint32_t>() + world, offsets.data(), world * 4, cudaMemcpyHostToDevice, st));
     x_pack<<<grid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev, s.x_owner.as<uint32_t>(),
@@ -2369,16 +2390,26 @@ extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint3
   uint32_t* counters = ctx->d_counters.p ? ctx->d_counters.as<uint32_t>() : nullptr;
   if (!counters) { TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4)); TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4)); counters = ctx->d_counters.as<uint32_t>(); }
   const uint32_t grid = std::min<uint32_t>(cdiv(n, 8), kGridPersist * 2);
-  k4_probe<32><<<grid, 256, 0, st>>>(recv_words_dev, n, s.key_words, nullptr, table.as<uint32_t>(), size - 1,
-                                     rep.as<uint32_t>(), slot_of.as<uint32_t>(), winner.as<uint32_t>());
+  {
+    // lanes per pattern as in K4: short keys would leave most of a warp idle
+    const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
+    const uint32_t pgrid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
+#define PF_XP(LL)                                                                                          \
+    k4_probe<LL><<<pgrid, 256, 0, st>>>(recv_words_dev, n, s.key_words, nullptr, table.as<uint32_t>(), size - 1, \
+                                        rep.as<uint32_t>(), slot_of.as<uint32_t>(), winner.as<uint32_t>())
+    if (L == 4) PF_XP(4); else if (L == 8) PF_XP(8); else if (L == 16) PF_XP(16); else PF_XP(32);
+#undef PF_XP
+  }
   TRY(scan_inplace(ctx, winner.as<uint32_t>(), n, counters + C_NEW_KP));
   x_finish<<<grid, 256, 0, st>>>(recv_words_dev, n, s.key_words, rep.as<uint32_t>(), winner.as<uint32_t>(),
                                  recv_unique_index_dev, s.x_unique.as<uint32_t>());
   ctx->launches += 2;
-  uint32_t total = 0;
-  CU(cudaMemcpyAsync(&total, counters + C_NEW_KP, 4, cudaMemcpyDeviceToHost, st));
+  TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 32 * 4));
+  uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;
+  mirror_counters<<<1, 32, 0, st>>>(hx, counters + C_NEW_KP, 1);
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
+  const uint32_t total = hx[0];
   s.x_n_unique = total;
   *n_unique_host = total;
   return PF_OK;
