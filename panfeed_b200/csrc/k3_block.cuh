@@ -105,6 +105,24 @@ __global__ void plan_cluster_blocks(const SeqDev* __restrict__ seqs, uint32_t n_
   }
 }
 
+// one warp per cluster: first sequence of every sample slice (sequences are in sample order)
+__global__ void plan_cluster_slices(const SeqDev* __restrict__ seqs, const ClusterBlk* __restrict__ cb,
+                                    uint32_t n_clusters, uint32_t n_slices, uint32_t slice_samples,
+                                    uint32_t* __restrict__ slice_seq) {
+  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (c >= n_clusters) return;
+  const ClusterBlk b = cb[c];
+  for (uint32_t s = lane_id(); s <= n_slices; s += 32) {
+    const uint32_t first_sample = s * slice_samples;
+    uint32_t lo = 0, hi = b.n_seqs;                 // first sequence with sample >= first_sample
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (seqs[b.seq_start + mid].sample < first_sample) lo = mid + 1; else hi = mid;
+    }
+    slice_seq[(size_t)c * (n_slices + 1) + s] = s == n_slices ? b.n_seqs : lo;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // shared-memory table
 // ---------------------------------------------------------------------------
@@ -189,7 +207,12 @@ struct BlkPlan {
   uint32_t block_windows;        // B = kBlkRun
   uint32_t slots, cslots;        // k-mer table / chunk table sizes of kA (powers of two)
   uint32_t cap;                  // k-mer rows of kA (dense, handed out on insertion)
-  uint32_t W, WP;                // bitset words, slab row stride (W rounded up to 4)
+  uint32_t W, WP;                // bitset words of a partial row, slab row stride (W rounded up to 4)
+  // sample slices (S > 1024): a work item is (cluster, run, slice); a partial row holds the
+  // bits of `slice_samples` consecutive sample ranks only
+  uint32_t n_slices;             // 1: no slicing
+  uint32_t slice_samples;        // multiple of 32
+  const uint32_t* slice_seq;     // [n_clusters][n_slices + 1] first sequence (cluster-relative) of every slice
 };
 
 // Shared memory of kA.  Both tables hand out DENSE row ids on insertion and the inserting
@@ -331,9 +354,21 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
   const uint32_t tid = threadIdx.x;
   const uint32_t item = item_list ? item_list[blockIdx.x] : blockIdx.x;
 
-  const uint32_t c = plan.item_cluster[item];
+  const uint32_t run_item = plan.n_slices > 1 ? item / plan.n_slices : item;
+  const uint32_t slice = item - run_item * plan.n_slices;
+  const uint32_t c = plan.item_cluster[run_item];
   const ClusterBlk cb = plan.cblk[c];
-  const uint32_t s_rel = (item - plan.item_base[c]) * (uint32_t)kBlkRun;   // first window of the run
+  const uint32_t s_rel = (run_item - plan.item_base[c]) * (uint32_t)kBlkRun;   // first window of the run
+  uint32_t seq_lo = 0, seq_hi = cb.n_seqs;
+  if (plan.n_slices > 1) {
+    seq_lo = plan.slice_seq[(size_t)c * (plan.n_slices + 1) + slice];
+    seq_hi = plan.slice_seq[(size_t)c * (plan.n_slices + 1) + slice + 1];
+    if (seq_lo == seq_hi) {                          // no sample of this slice carries the cluster
+      if (tid == 0) { slab_count[item] = 0; slab_base[item] = 0; }
+      return;
+    }
+  }
+  const uint32_t sample0 = slice * plan.slice_samples;
 
   for (uint32_t i = tid; i < plan.slots; i += kBlkThreads) { a.keys[i] = ~0ull; a.rowid[i] = 0xffffu; }
   for (uint32_t i = tid; i < plan.cslots; i += kBlkThreads) a.cstate[i] = kChunkEmpty;
@@ -367,14 +402,14 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
 
   // ---- phase 1: every sequence's run -> chunk table (or, for ragged / ambiguous runs and a
   //      full chunk table, straight into the k-mer table) ------------------------------------
-  for (uint32_t si = tid; si < cb.n_seqs; si += kBlkThreads) {
+  for (uint32_t si = seq_lo + tid; si < seq_hi; si += kBlkThreads) {
     const uint4 raw = __ldg(reinterpret_cast<const uint4*>(seqs + cb.seq_start + si));
     const uint32_t len = raw.y;
     if (len < (uint32_t)k) continue;
     const uint32_t nwin = len - (uint32_t)k + 1u;
     if (s_rel >= nwin) continue;
     const uint32_t nv = min((uint32_t)kBlkRun, nwin - s_rel);
-    const uint32_t sample = raw.z & 0x7fffffffu;
+    const uint32_t sample = (raw.z & 0x7fffffffu) - sample0;      // rank inside the slice
     const bool amb = (raw.z >> 31) != 0u;
     const uint32_t wofs = sample >> 5, bit = 1u << (sample & 31u);
     // three words cover the run: 16 + k - 1 <= 47 bases from an offset < 32
@@ -476,20 +511,34 @@ struct MergeEntry {        // 16 bytes; key == ~0 marks an empty slot
   uint32_t reserved;
 };
 
-// one warp per cluster: partial rows of the cluster -> table slots (load factor <= 2/3)
-__global__ void plan_merge_tables(const uint32_t* __restrict__ item_base, uint32_t n_clusters,
-                                  const uint32_t* __restrict__ slab_count, uint32_t* __restrict__ n_slots) {
-  const uint32_t c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (c >= n_clusters) return;
+// one warp per (cluster, slice): partial rows -> table slots (load factor <= 2/3).  With
+// slices, table2_ctas[c] additionally sizes the cluster's cross-slice table in units of 256
+// slots (so that a CTA of kB5 belongs to one cluster).
+__global__ void plan_merge_tables(const uint32_t* __restrict__ item_base, uint32_t n_clusters, uint32_t n_slices,
+                                  const uint32_t* __restrict__ slab_count, uint32_t* __restrict__ n_slots,
+                                  uint32_t* __restrict__ table2_ctas) {
+  const uint32_t cs = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (cs >= n_clusters * n_slices) return;
+  const uint32_t c = cs / n_slices, slice = cs - c * n_slices;
   const uint32_t lane = lane_id();
   uint32_t p = 0;
-  for (uint32_t i = item_base[c] + lane; i < item_base[c + 1]; i += 32) {
-    const uint32_t n = slab_count[i];
+  for (uint32_t r = item_base[c] + lane; r < item_base[c + 1]; r += 32) {
+    const uint32_t n = slab_count[(size_t)r * n_slices + slice];
     if (n != kBlkOverflow) p += n;
   }
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(kFull, p, m);
-  if (lane == 0) n_slots[c] = p + (p >> 1) + 2u;
+  if (lane == 0) {
+    n_slots[cs] = p + (p >> 1) + 2u;
+    if (table2_ctas) atomicAdd(&table2_ctas[c], p);       // partial rows of the cluster (all slices)
+  }
+}
+// table2_ctas[c]: partial rows -> CTAs of 256 slots at load factor <= 2/3
+__global__ void plan_table2_ctas(uint32_t* __restrict__ table2_ctas, uint32_t n_clusters) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_clusters) return;
+  const uint32_t p = table2_ctas[c];
+  table2_ctas[c] = (p + (p >> 1) + 2u + 255u) / 256u;
 }
 
 // expand an exclusive scan into its inverse map: out[base[c] + i] = c
@@ -504,15 +553,21 @@ __global__ void plan_expand_owner(const uint32_t* __restrict__ base, uint32_t n_
 __global__ void __launch_bounds__(256)
 kB1_insert(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_base,
            const uint32_t* __restrict__ slab_count, const uint32_t* __restrict__ item_cluster,
-           uint32_t n_items, const uint32_t* __restrict__ table_base /* [n_clusters + 1] */,
-           MergeEntry* __restrict__ table, uint32_t* __restrict__ pslot) {
+           uint32_t n_items /* incl. slices */, uint32_t n_slices,
+           const uint32_t* __restrict__ table_base /* [n_clusters * n_slices + 1] */,
+           MergeEntry* __restrict__ table, uint32_t* __restrict__ pslot,
+           uint16_t* __restrict__ pslice /* null without slices */) {
   const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (item >= n_items) return;
   const uint32_t n = slab_count[item];
   if (n == kBlkOverflow || n == 0) return;
-  const uint32_t c = item_cluster[item];
+  const uint32_t run_item = n_slices > 1 ? item / n_slices : item;
+  const uint32_t slice = item - run_item * n_slices;
+  const uint32_t c = item_cluster[run_item] * n_slices + slice;
   const uint32_t tb = table_base[c], ts = table_base[c + 1] - tb;
   const uint32_t base = slab_base[item];
+  if (pslice)
+    for (uint32_t i = lane_id(); i < n; i += 32) pslice[base + i] = (uint16_t)slice;
   for (uint32_t i = lane_id(); i < n; i += 32) {
     const uint64_t key = slab_keys[base + i];
     uint32_t s = __umulhi((uint32_t)(mix64(key) >> 32), ts);
@@ -644,6 +699,115 @@ kB3_emit(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ sl
     bool owner;
     const uint32_t cnt = count_of(i0 + lane, owner);
     emit(i0 + lane, owner && cnt >= cl.lo && cnt <= cl.hi, cnt);
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// sample slices: a k-mer's bitset is spread over up to n_slices partial rows (one per slice,
+// after kB1/kB2 merged the rows of the same slice).  kB4 links them per k-mer in a cross-slice
+// table of the cluster and sums the popcounts; kB5 applies the MAF window to the sum and
+// assembles the full-width bitsets of the survivors.
+// ---------------------------------------------------------------------------
+struct LinkEntry {         // 16 bytes, memset to 0xff: key empty, head nil, count = -1
+  unsigned long long key;
+  uint32_t head;           // last linked partial row (chain through `next`)
+  uint32_t count;          // (sum of popcounts) - 1
+};
+
+__global__ void __launch_bounds__(256)
+kB4_link(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_rows,
+         const uint32_t* __restrict__ slab_base, const uint32_t* __restrict__ slab_count,
+         const uint32_t* __restrict__ item_cluster, uint32_t n_items, uint32_t n_slices,
+         const uint32_t* __restrict__ pslot, const uint32_t* __restrict__ table2_base /* CTAs of 256 slots */,
+         LinkEntry* __restrict__ table2, uint32_t* __restrict__ next, uint32_t WP) {
+  const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (item >= n_items) return;
+  const uint32_t n = slab_count[item];
+  if (n == kBlkOverflow || n == 0) return;
+  const uint32_t c = item_cluster[item / n_slices];
+  const uint32_t tb = table2_base[c] * 256u, ts = (table2_base[c + 1] - table2_base[c]) * 256u;
+  const uint32_t base = slab_base[item];
+  for (uint32_t i = lane_id(); i < n; i += 32) {
+    const uint32_t p = base + i;
+    if (pslot[p] == 0xffffffffu) continue;                 // folded into an earlier row of its slice
+    const uint4* row = reinterpret_cast<const uint4*>(slab_rows + (size_t)p * WP);
+    uint32_t cnt = 0;
+    for (uint32_t q = 0; q < WP / 4; ++q) {
+      const uint4 x = row[q];
+      cnt += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+    }
+    const uint64_t key = slab_keys[p];
+    uint32_t s = __umulhi((uint32_t)(mix64(key) >> 32), ts);
+    for (;;) {
+      const unsigned long long old = atomicCAS(&table2[tb + s].key, ~0ull, (unsigned long long)key);
+      if (old == ~0ull || old == key) break;
+      if (++s == ts) s = 0;
+    }
+    atomicAdd(&table2[tb + s].count, cnt);
+    next[p] = atomicExch(&table2[tb + s].head, p);
+  }
+}
+
+// one CTA per 256 slots of a cluster's cross-slice table
+__global__ void __launch_bounds__(256)
+kB5_emit(const LinkEntry* __restrict__ table2, const uint32_t* __restrict__ cta_cluster,
+         const uint32_t* __restrict__ next, const uint16_t* __restrict__ pslice,
+         const uint32_t* __restrict__ slab_rows, const ClusterDev* __restrict__ clusters, RowOut out,
+         uint32_t row_capacity, uint32_t* __restrict__ counters, uint32_t W, uint32_t Ws, uint32_t WP) {
+  __shared__ uint32_t w_pass[8], w_used[8];
+  __shared__ uint32_t cta_base, cta_ok;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t c = cta_cluster[blockIdx.x];
+  const ClusterDev cl = clusters[c];
+  const LinkEntry e = table2[(size_t)blockIdx.x * 256u + threadIdx.x];
+  const bool used = e.key != ~0ull;
+  const uint32_t total = e.count + 1u;
+  const bool pass = used && total >= cl.lo && total <= cl.hi;
+  const uint32_t mp = __ballot_sync(kFull, pass), mu = __ballot_sync(kFull, used);
+  if (lane == 0) { w_pass[warp] = (uint32_t)__popc(mp); w_used[warp] = (uint32_t)__popc(mu); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0, tu = 0;
+    for (int w = 0; w < 8; ++w) { const uint32_t x = w_pass[w]; w_pass[w] = tot; tot += x; tu += w_used[w]; }
+    uint32_t b = 0, ok = 1;
+    if (tu) atomicAdd(&counters[LC_UNIQUE], tu);
+    if (tot) {
+      b = atomicAdd(&counters[LC_ROWS], tot);
+      if ((uint64_t)b + tot > row_capacity) { ok = 0; atomicExch(&counters[LC_ROW_OVERFLOW], 1u); }
+    }
+    cta_base = b;
+    cta_ok = ok;
+  }
+  __syncthreads();
+  if (!cta_ok || mp == 0u) return;
+  const uint32_t g0 = cta_base + w_pass[warp];
+  // the warp writes its surviving rows one after the other: clear the row, then copy every
+  // linked slice to its place
+  uint32_t rest = mp, r = 0;
+  while (rest) {
+    const int src_lane = __ffs(rest) - 1;
+    rest &= rest - 1u;
+    const unsigned long long key = __shfl_sync(kFull, e.key, src_lane);
+    const uint32_t tot = __shfl_sync(kFull, total, src_lane);
+    uint32_t p = __shfl_sync(kFull, e.head, src_lane);
+    const size_t gi = (size_t)g0 + r;
+    ++r;
+    uint32_t* dst = out.cand + gi * out.key_words;
+    for (uint32_t w = lane; w < W; w += 32) dst[w] = 0u;
+    if (lane == 0) {
+      out.cluster[gi] = cl.id;
+      out.kmer[gi] = key;
+      out.count[gi] = tot;
+      if (out.key_words > W) dst[W] = out.cluster_pattern[c];
+    }
+    __syncwarp();
+    while (p != 0xffffffffu) {
+      const uint32_t w0 = (uint32_t)pslice[p] * Ws;
+      const uint32_t* src = slab_rows + (size_t)p * WP;
+      for (uint32_t w = lane; w < Ws && w0 + w < W; w += 32) dst[w0 + w] = src[w];
+      p = next[p];
+    }
   }
 }
 

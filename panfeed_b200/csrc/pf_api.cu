@@ -153,7 +153,7 @@ struct BatchState {
   PinBuf h_seq_rec_off, h_tile_first_seq;
   std::vector<std::pair<uint32_t, uint32_t>> nar_ranges;   // narrow record range of every cluster
   uint32_t n_items = 0;          // (cluster, block) work items of the batch (block aggregation)
-  DevBuf d_seq_lite, d_cblk, d_item_base, d_item_cluster, d_plan_total, d_bsum_slot;
+  DevBuf d_seq_lite, d_cblk, d_item_base, d_item_cluster, d_plan_total, d_bsum_slot, d_slice_seq;
   PinBuf h_plan;
   uint64_t kp_base = 0, cp_base = 0;   // pool sizes before the batch
   bool rows_prefetched = false;
@@ -193,13 +193,16 @@ struct pf_ctx : BatchState {
   bool block_mode = false;       // S <= 1024 and not disabled: kA_block_aggregate + kB1..kB3
   uint32_t block_windows = 16;   // windows per position block (= kBlkRun)
   uint32_t blk_slots = 1024, blk_cap = 448, blk_cslots = 128;   // shared memory of kA: k-mer key slots / rows, chunk slots
+  uint32_t n_slices = 1, slice_samples = 0, Ws = 0;   // sample slices of the block engine (S > 1024): slices,
+                                                       // samples per slice, bitset words of a partial row
   uint32_t block_fallbacks = 0;
   double partial_ratio = 1.0 / 16;   // partial rows per window, learned from earlier batches
   uint64_t partial_cap = 0;
   uint64_t partials_last = 0;
   bool used_block = false;       // the last batch went through kA/kB
   DevBuf d_slab_base, d_slab_count, d_slab_keys, d_slab_rows,
-      d_group_base /* merge-table offsets per cluster */, d_mtable, d_pslot, d_rescue[2];
+      d_group_base /* merge-table offsets per (cluster, slice) */, d_mtable, d_pslot,
+      d_table2_base, d_table2, d_next, d_pslice, d_cta_cluster, d_rescue[2];
   PatternSpace kp, cp;     // k-mer patterns, cluster patterns
   // pinned results
   PinBuf r_row_cluster, r_row_kmer, r_wrow_kmer, r_row_count, r_row_pattern, r_cl_pattern;
@@ -408,7 +411,18 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
   ctx->use_direct = ctx->W <= kDirectMaxWords;
   {
     // block aggregation: debug_flags bit 1 disables it; PF_BLOCK_WINDOWS / PF_BLOCK_SMEM_KB tune it
-    ctx->block_mode = ctx->partition && ctx->use_direct && !(p->debug_flags & 2u);
+    ctx->block_mode = ctx->partition && !(p->debug_flags & 2u);
+    if (ctx->W > kDirectMaxWords) {            // S > 1024: partial rows per slice of 512 samples
+      ctx->slice_samples = 512;
+      ctx->n_slices = (p->n_samples + 511u) / 512u;
+      ctx->Ws = 16;
+      if (ctx->n_slices > 0xffffu) ctx->block_mode = false;
+    } else {
+      ctx->slice_samples = 32u * ctx->W;
+      ctx->n_slices = 1;
+      ctx->Ws = ctx->W;
+    }
+    if (const char* e = getenv("PF_BLOCK_SLICED")) if (atoi(e) == 0 && ctx->n_slices > 1) ctx->block_mode = false;
     if (const char* e = getenv("PF_BLOCK_MODE")) ctx->block_mode = ctx->block_mode && atoi(e) != 0;
     // tables of kA: one k-mer slot per expected distinct k-mer of a 16-window run at ~50 % load
     // (about one haplotype per 30 samples and position), a quarter as many chunk slots;
@@ -416,12 +430,13 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
     ctx->block_windows = (uint32_t)kBlkRun;
     // (about one new k-mer per sample and run of 16 windows, plus the haplotypes' own)
     uint32_t slots = 256;
-    while (slots < 2u * p->n_samples && slots < 4096u) slots *= 2;
+    const uint32_t s_eff = std::min<uint32_t>(p->n_samples, ctx->slice_samples);   // samples a kA block sees
+    while (slots < 2u * s_eff && slots < 4096u) slots *= 2;
     if (const char* e = getenv("PF_BLOCK_SLOTS")) {
       const int v = atoi(e);
       if (v >= 64 && v <= 8192 && (v & (v - 1)) == 0) slots = (uint32_t)v;
     }
-    uint32_t cap = std::min<uint32_t>(slots * 13u / 16u, std::max<uint32_t>(96u, p->n_samples * 9u / 10u));
+    uint32_t cap = std::min<uint32_t>(slots * 13u / 16u, std::max<uint32_t>(96u, s_eff * 9u / 10u));
     if (const char* e = getenv("PF_BLOCK_CAP")) {
       const int v = atoi(e);
       if (v >= 32 && (uint32_t)v <= slots * 13u / 16u) cap = (uint32_t)v;
@@ -431,7 +446,7 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
       const int v = atoi(e);
       if (v >= 32 && v <= 8192 && (v & (v - 1)) == 0) cslots = (uint32_t)v;
     }
-    while (slots > 64u && blkA_smem_bytes(slots, cap, cslots, ctx->W) > kBlkMaxSmem) {
+    while (slots > 64u && blkA_smem_bytes(slots, cap, cslots, ctx->Ws) > kBlkMaxSmem) {
       slots /= 2; cap /= 2; cslots = std::max<uint32_t>(32u, cslots / 2);
     }
     ctx->blk_slots = slots;
@@ -468,7 +483,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                       &bs->d_row_pattern, &bs->d_cl_pattern, &bs->d_pos_kmer, &bs->d_pos_seq, &bs->d_pos_cstart,
                       &bs->d_pos_gstart, &bs->d_pos_flags, &bs->d_pos_wide, &bs->d_seq_rec_off,
                       &bs->d_tile_first_seq, &bs->d_seq_lite, &bs->d_cblk, &bs->d_item_base, &bs->d_item_cluster,
-                      &bs->d_plan_total, &bs->d_bsum_slot})
+                      &bs->d_plan_total, &bs->d_bsum_slot, &bs->d_slice_seq})
       fd(*b);
     for (WidthState* w : {&bs->nar, &bs->wid}) {
       for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
@@ -484,7 +499,8 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
   for (DevBuf* b : {&ctx->d_counters, &ctx->d_bsum, &ctx->d_cand, &ctx->d_rep, &ctx->d_slot_of, &ctx->d_winner,
                     &ctx->d_cl_rep, &ctx->d_cl_slot, &ctx->d_cl_winner, &ctx->d_digests, &ctx->d_slab_base,
                     &ctx->d_slab_count, &ctx->d_slab_keys, &ctx->d_slab_rows, &ctx->d_group_base, &ctx->d_mtable,
-                    &ctx->d_pslot, &ctx->d_rescue[0], &ctx->d_rescue[1]})
+                    &ctx->d_pslot, &ctx->d_rescue[0], &ctx->d_rescue[1], &ctx->d_table2_base, &ctx->d_table2,
+                    &ctx->d_next, &ctx->d_pslice, &ctx->d_cta_cluster})
     fd(*b);
   for (PatternSpace* s : {&ctx->kp, &ctx->cp})
     for (DevBuf* b : {&s->pool, &s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique,
@@ -1207,6 +1223,12 @@ int plan_blocks(pf_ctx* ctx, BatchState& B, cudaStream_t st, bool sync) {
       B.d_seqs.as<SeqDev>(), B.n_seqs, nc, (int)ctx->prm.k, ctx->block_windows,
       B.d_cblk.as<ClusterBlk>(), B.d_item_base.as<uint32_t>());
   TRY(scan_inplace(ctx, B.d_item_base.as<uint32_t>(), nc, B.d_plan_total.as<uint32_t>(), st, &B.d_bsum_slot));
+  if (ctx->n_slices > 1) {
+    TRY(dev_ensure(ctx, B.d_slice_seq, (size_t)nc * (ctx->n_slices + 1) * 4));
+    plan_cluster_slices<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(
+        B.d_seqs.as<SeqDev>(), B.d_cblk.as<ClusterBlk>(), nc, ctx->n_slices, ctx->slice_samples,
+        B.d_slice_seq.as<uint32_t>());
+  }
   // n_items is read back through pinned memory (no copy engine); plan_blocks_finish takes it
   mirror_counters<<<1, 32, 0, st>>>(B.h_plan.as<uint32_t>(), B.d_plan_total.as<uint32_t>(), 1);
   CU(cudaGetLastError());
@@ -1236,8 +1258,11 @@ BlkPlan block_plan(const pf_ctx* ctx) {
   bp.slots = ctx->blk_slots;
   bp.cap = ctx->blk_cap;
   bp.cslots = ctx->blk_cslots;
-  bp.W = ctx->W;
-  bp.WP = (ctx->W + 3u) & ~3u;
+  bp.W = ctx->Ws;
+  bp.WP = (ctx->Ws + 3u) & ~3u;
+  bp.n_slices = ctx->n_slices;
+  bp.slice_samples = ctx->slice_samples;
+  bp.slice_seq = ctx->n_slices > 1 ? ctx->d_slice_seq.as<uint32_t>() : nullptr;
   return bp;
 }
 
@@ -1253,7 +1278,7 @@ int launch_block_aggregate(pf_ctx* ctx, const uint32_t* items, uint32_t n, uint3
   bp.cslots = cslots;
   const uint32_t cap32 = (uint32_t)std::min<uint64_t>(ctx->partial_cap, 0xfffffff0u);
   uint32_t* counters = ctx->d_counters.as<uint32_t>() + C_LOCAL;
-  const uint32_t smem = blkA_smem_bytes(slots, cap, cslots, ctx->W);
+  const uint32_t smem = blkA_smem_bytes(slots, cap, cslots, ctx->Ws);
 #define PF_KA(CANON)                                                                                   \
   kA_block_aggregate<CANON><<<n, kBlkThreads, smem, st>>>(                                             \
       ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seq_lite.as<SeqLite>(), bp,   \
@@ -1267,39 +1292,78 @@ int launch_block_aggregate(pf_ctx* ctx, const uint32_t* items, uint32_t n, uint3
   return PF_OK;
 }
 
-// kB1..kB3 over the `n_partials` partial rows kA left in the slabs
+// kB1..kB3 (kB1, kB2, kB4, kB5 with sample slices) over the `n_partials` partial rows kA left
 int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
   if (ctx->n_items == 0 || n_partials == 0) return PF_OK;
   cudaStream_t st = ctx->stream;
-  const uint32_t nc = ctx->n_clusters;
+  const uint32_t nc = ctx->n_clusters, ns = ctx->n_slices;
+  const uint32_t n_cs = nc * ns;                    // (cluster, slice) merge tables
+  const uint32_t n_it = ctx->n_items * ns;          // kA work items
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
-  const uint32_t WP = (ctx->W + 3u) & ~3u;
-  // per-cluster tables: 1.5 slots per partial row (+2), offsets by a scan
-  TRY(dev_ensure(ctx, ctx->d_group_base, ((size_t)nc + 1) * 4));
-  plan_merge_tables<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(
-      ctx->d_item_base.as<uint32_t>(), nc, ctx->d_slab_count.as<uint32_t>(), ctx->d_group_base.as<uint32_t>());
+  const uint32_t WP = (ctx->Ws + 3u) & ~3u;
+  // per-(cluster, slice) tables: 1.5 slots per partial row (+2), offsets by a scan
+  TRY(dev_ensure(ctx, ctx->d_group_base, ((size_t)n_cs + 1) * 4));
+  if (ns > 1) {
+    TRY(dev_ensure(ctx, ctx->d_table2_base, ((size_t)nc + 1) * 4));
+    CU(cudaMemsetAsync(ctx->d_table2_base.p, 0, ((size_t)nc + 1) * 4, st));
+  }
+  plan_merge_tables<<<cdiv((uint64_t)n_cs * 32, 256), 256, 0, st>>>(
+      ctx->d_item_base.as<uint32_t>(), nc, ns, ctx->d_slab_count.as<uint32_t>(), ctx->d_group_base.as<uint32_t>(),
+      ns > 1 ? ctx->d_table2_base.as<uint32_t>() : nullptr);
   ctx->launches++;
-  TRY(scan_inplace(ctx, ctx->d_group_base.as<uint32_t>(), nc, ctx->d_plan_total.as<uint32_t>() + 1));
-  const uint64_t n_slots = (uint64_t)n_partials + n_partials / 2 + 2ull * nc + 16;
+  TRY(scan_inplace(ctx, ctx->d_group_base.as<uint32_t>(), n_cs, ctx->d_plan_total.as<uint32_t>() + 1));
+  const uint64_t n_slots = (uint64_t)n_partials + n_partials / 2 + 2ull * n_cs + 16;
   if (n_slots >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "too many partial rows for one batch; split it");
   TRY(dev_ensure(ctx, ctx->d_mtable, n_slots * sizeof(MergeEntry)));
   TRY(dev_ensure(ctx, ctx->d_pslot, (size_t)n_partials * 4));
+  if (ns > 1) TRY(dev_ensure(ctx, ctx->d_pslice, (size_t)n_partials * 2));
   CU(cudaMemsetAsync(ctx->d_mtable.p, 0xff, n_slots * sizeof(MergeEntry), st));
-  const uint32_t g0 = cdiv((uint64_t)ctx->n_items * 32, 256);
+  const uint32_t g0 = cdiv((uint64_t)n_it * 32, 256);
   kB1_insert<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_base.as<uint32_t>(),
-                                 ctx->d_slab_count.as<uint32_t>(), ctx->d_item_cluster.as<uint32_t>(), ctx->n_items,
+                                 ctx->d_slab_count.as<uint32_t>(), ctx->d_item_cluster.as<uint32_t>(), n_it, ns,
                                  ctx->d_group_base.as<uint32_t>(), ctx->d_mtable.as<MergeEntry>(),
-                                 ctx->d_pslot.as<uint32_t>());
+                                 ctx->d_pslot.as<uint32_t>(), ns > 1 ? ctx->d_pslice.as<uint16_t>() : nullptr);
   CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));     // kB2 counts the folded rows there
   kB2_fold<<<cdiv(n_partials, 256), 256, 0, st>>>(n_partials, ctx->d_pslot.as<uint32_t>(),
                                                   ctx->d_mtable.as<MergeEntry>(), ctx->d_slab_rows.as<uint32_t>(), WP,
                                                   counters + C_LOCAL);
   const uint32_t cap = (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu);
-  kB3_emit<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
+  if (ns == 1) {
+    kB3_emit<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
+                                 ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(),
+                                 ctx->d_item_cluster.as<uint32_t>(), ctx->n_items, ctx->d_pslot.as<uint32_t>(),
+                                 ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL, ctx->W, WP);
+    ctx->launches += 3;
+    CU(cudaGetLastError());
+    return PF_OK;
+  }
+  // ---- sample slices: link the per-slice rows of a k-mer, filter on the summed count, assemble ----
+  plan_table2_ctas<<<cdiv(nc, 256), 256, 0, st>>>(ctx->d_table2_base.as<uint32_t>(), nc);
+  TRY(scan_inplace(ctx, ctx->d_table2_base.as<uint32_t>(), nc, ctx->d_plan_total.as<uint32_t>() + 2));
+  const uint64_t max_ctas = ((uint64_t)n_partials + n_partials / 2) / 256 + 2ull * nc + 2;
+  TRY(dev_ensure(ctx, ctx->d_table2, max_ctas * 256 * sizeof(LinkEntry)));
+  TRY(dev_ensure(ctx, ctx->d_cta_cluster, max_ctas * 4));
+  TRY(dev_ensure(ctx, ctx->d_next, (size_t)n_partials * 4));
+  CU(cudaMemsetAsync(ctx->d_table2.p, 0xff, max_ctas * 256 * sizeof(LinkEntry), st));
+  plan_expand_owner<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(ctx->d_table2_base.as<uint32_t>(), nc,
+                                                                  ctx->d_cta_cluster.as<uint32_t>());
+  kB4_link<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
                                ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(),
-                               ctx->d_item_cluster.as<uint32_t>(), ctx->n_items, ctx->d_pslot.as<uint32_t>(),
-                               ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL, ctx->W, WP);
-  ctx->launches += 3;
+                               ctx->d_item_cluster.as<uint32_t>(), n_it, ns, ctx->d_pslot.as<uint32_t>(),
+                               ctx->d_table2_base.as<uint32_t>(), ctx->d_table2.as<LinkEntry>(),
+                               ctx->d_next.as<uint32_t>(), WP);
+  // grid of kB5 = CTAs of all cross-slice tables: one small read-back
+  TRY(pin_ensure(ctx, ctx->h_plan, 16));
+  mirror_counters<<<1, 32, 0, st>>>(ctx->h_plan.as<uint32_t>() + 2, ctx->d_plan_total.as<uint32_t>() + 2, 1);
+  CU(cudaStreamSynchronize(st));
+  const uint32_t n_ctas = ctx->h_plan.as<uint32_t>()[2];
+  if (n_ctas > max_ctas) return fail(ctx, PF_ERR_INTERNAL, "cross-slice table larger than planned");
+  if (n_ctas)
+    kB5_emit<<<n_ctas, 256, 0, st>>>(ctx->d_table2.as<LinkEntry>(), ctx->d_cta_cluster.as<uint32_t>(),
+                                     ctx->d_next.as<uint32_t>(), ctx->d_pslice.as<uint16_t>(),
+                                     ctx->d_slab_rows.as<uint32_t>(), ctx->d_clusters.as<ClusterDev>(), ro, cap,
+                                     counters + C_LOCAL, ctx->W, ctx->Ws, WP);
+  ctx->launches += 7;
   CU(cudaGetLastError());
   return PF_OK;
 }
@@ -1336,7 +1400,8 @@ extern "C" int pf_execute(pf_ctx* ctx) {
 
   // record buffers (ping-pong); the idle one later holds the run lists, so give
   // it room for n+1 run starts + n run segments (8n+4 bytes <= 8n+16)
-  bool blk = ctx->block_mode && part && ctx->use_direct && N.n_records > 0 && ctx->n_items > 0;
+  bool blk = ctx->block_mode && part && N.n_records > 0 && ctx->n_items > 0;
+  const uint32_t n_ka_items = ctx->n_items * ctx->n_slices;
   auto ensure_records = [&]() -> int {     // the record path needs the narrow ping-pong buffers
     for (int i = 0; i < 2; ++i) {
       TRY(dev_ensure(ctx, N.keys[i], ((size_t)N.n_records + 2) * 8));
@@ -1392,15 +1457,15 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       ctx->partial_cap = std::max<uint64_t>(ctx->partial_cap, std::max<uint64_t>(
           65536, (uint64_t)(ctx->partial_ratio * 1.3 * (double)n_windows) + 4096));
       ctx->partial_cap = std::min<uint64_t>(ctx->partial_cap, 0xfffffff0ull);
-      const uint32_t WP = (ctx->W + 3u) & ~3u;
-      TRY(dev_ensure(ctx, ctx->d_slab_base, std::max<size_t>(1, ctx->n_items) * 4));
-      TRY(dev_ensure(ctx, ctx->d_slab_count, std::max<size_t>(1, ctx->n_items) * 4));
-      TRY(dev_ensure(ctx, ctx->d_rescue[0], std::max<size_t>(1, ctx->n_items) * 4));
-      TRY(dev_ensure(ctx, ctx->d_rescue[1], std::max<size_t>(1, ctx->n_items) * 4));
+      const uint32_t WP = (ctx->Ws + 3u) & ~3u;
+      TRY(dev_ensure(ctx, ctx->d_slab_base, std::max<size_t>(1, n_ka_items) * 4));
+      TRY(dev_ensure(ctx, ctx->d_slab_count, std::max<size_t>(1, n_ka_items) * 4));
+      TRY(dev_ensure(ctx, ctx->d_rescue[0], std::max<size_t>(1, n_ka_items) * 4));
+      TRY(dev_ensure(ctx, ctx->d_rescue[1], std::max<size_t>(1, n_ka_items) * 4));
       TRY(dev_ensure(ctx, ctx->d_slab_keys, ctx->partial_cap * 8));
       TRY(dev_ensure(ctx, ctx->d_slab_rows, ctx->partial_cap * WP * 4));
       CU(cudaMemsetAsync(counters + C_LOCAL, 0, LC_COUNT * 4, st));
-      TRY(launch_block_aggregate(ctx, nullptr, ctx->n_items, ctx->blk_slots, ctx->blk_cap, ctx->blk_cslots,
+      TRY(launch_block_aggregate(ctx, nullptr, n_ka_items, ctx->blk_slots, ctx->blk_cap, ctx->blk_cslots,
                                  ctx->d_rescue[0].as<uint32_t>()));
       STAGE("kA_block_aggregate");
       TRY(passes_width<Key128>(ctx, Wd, C_TICKET_W));
@@ -1425,16 +1490,16 @@ extern "C" int pf_execute(pf_ctx* ctx) {
           // twice the key slots, as many rows as then fit (the chunk table stays: a full one only
           // sends runs down the direct path)
           uint32_t slots2 = slots * 2u, cap2 = 0;
-          if (slots2 <= 8192u && blkA_smem_bytes(slots2, 0u, cslots, ctx->W) < kBlkMaxSmem) {
-            const uint32_t per_row = 8u + (ctx->W | 1u) * 4u;
-            const uint32_t fit = (kBlkMaxSmem - blkA_smem_bytes(slots2, 0u, cslots, ctx->W)) / per_row;
+          if (slots2 <= 8192u && blkA_smem_bytes(slots2, 0u, cslots, ctx->Ws) < kBlkMaxSmem) {
+            const uint32_t per_row = 8u + (ctx->Ws | 1u) * 4u;
+            const uint32_t fit = (kBlkMaxSmem - blkA_smem_bytes(slots2, 0u, cslots, ctx->Ws)) / per_row;
             cap2 = std::min<uint32_t>(std::min<uint32_t>(fit, slots2 * 13u / 16u),
                                       std::max<uint32_t>(cap * 2u, slots2 * 5u / 8u));
           }
           if (cap2 <= cap) {        // no more rows with more slots: try all the rows the current slots allow
             slots2 = slots;
-            const uint32_t per_row = 8u + (ctx->W | 1u) * 4u;
-            const uint32_t fit = (kBlkMaxSmem - blkA_smem_bytes(slots, 0u, cslots, ctx->W)) / per_row;
+            const uint32_t per_row = 8u + (ctx->Ws | 1u) * 4u;
+            const uint32_t fit = (kBlkMaxSmem - blkA_smem_bytes(slots, 0u, cslots, ctx->Ws)) / per_row;
             cap2 = std::min<uint32_t>(fit, slots * 13u / 16u);
           }
           if (cap2 <= cap) { too_big = true; break; }
@@ -1452,10 +1517,10 @@ extern "C" int pf_execute(pf_ctx* ctx) {
                     cap, cslots, hcnt[C_LOCAL + LC_TABLE_OVERFLOW], hcnt[C_LOCAL + LC_RESCUE]);
         }
         // many rescued blocks: start the next batches with more rows (and key slots to match)
-        if (!too_big && first_rescue > ctx->n_items / 8u) {
+        if (!too_big && first_rescue > n_ka_items / 8u) {
           uint32_t ns = ctx->blk_slots, ncap = ctx->blk_cap + ctx->blk_cap / 2;
           while (ncap > ns * 13u / 16u) ns *= 2;
-          if (ns <= 8192u && blkA_smem_bytes(ns, ncap, ctx->blk_cslots, ctx->W) <= kBlkMaxSmem) {
+          if (ns <= 8192u && blkA_smem_bytes(ns, ncap, ctx->blk_cslots, ctx->Ws) <= kBlkMaxSmem) {
             ctx->blk_slots = ns;
             ctx->blk_cap = ncap;
           }
@@ -1590,7 +1655,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   if (part) {
     N.n_rows = N.n_records ? hcnt[C_LOCAL + LC_ROWS] : 0;
     ctx->unique_last = N.n_records ? hcnt[C_LOCAL + LC_UNIQUE] : 0;
-    if (ctx->used_block)      // distinct k-mers = partial rows - rows folded into an earlier one
+    if (ctx->used_block && ctx->n_slices == 1)   // distinct k-mers = partial rows - rows folded into an earlier one
       ctx->unique_last = (uint64_t)hcnt[C_LOCAL + LC_PARTIALS] - hcnt[C_LOCAL + LC_RESCUE];
     if (N.n_records) ctx->row_ratio = std::max(1e-4, (double)N.n_rows / (double)N.n_records);
   } else {

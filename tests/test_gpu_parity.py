@@ -262,6 +262,26 @@ def test_block_engine_merges_misaligned_copies():
         assert out["stats"]["engine"] == 2
 
 
+@pytest.mark.parametrize("canon,cm", [(True, True), (False, False)])
+def test_block_engine_sample_slices(canon, cm):
+    """S > 1024: kA works per slice of 512 samples, kB4/kB5 link the slices of a k-mer, sum the
+    counts for the MAF window and assemble the full-width bitsets."""
+    rng = np.random.default_rng(31)
+    S = 1300
+    items, stroi = _random_items(rng, S, 31, 3, 220)
+    out, want = _compare_with_oracle(items, stroi, S, 31, canon, cm, False, 0.01, batch_clusters=2)
+    assert out["stats"]["engine"] == 2
+
+
+def test_block_engine_sample_slices_10k():
+    """BASELINE config #4's sample count on short clusters (the oracle's limit)."""
+    rng = np.random.default_rng(32)
+    S = 10000
+    items, stroi = _random_items(rng, S, 31, 2, 90)
+    out, want = _compare_with_oracle(items, set(), S, 31, True, False, False, 0.01, batch_clusters=2)
+    assert out["stats"]["engine"] == 2
+
+
 @pytest.mark.parametrize("engine", ["block", "records"])
 def test_pipelined_submit_matches_oracle(engine, monkeypatch):
     """pf_submit of a batch above the split threshold: sub-batches of whole clusters through
