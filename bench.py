@@ -267,9 +267,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner out of it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # rank 0 prints ONE JSON line on stdout: NCCL's version banner / warnings go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -408,7 +407,8 @@ def main():
             pass_ms = stage_ms["ms_sort"]
             n_launch = 1
             alg_bytes = k1_bytes
-            partial_bytes = st["partial_rows"] * (8 + 4 * ((W4 // 4 + 3) // 4 * 4))
+            wp = 16 if S > 1024 else (W4 // 4 + 3) // 4 * 4      # S > 1024: 512-sample slices, 16-word rows
+            partial_bytes = st["partial_rows"] * (8 + 4 * wp)
             compulsory = n_bases / 4 + 16 * len(hb.seqs) + partial_bytes
             per_rec = tr.get("kA_block_aggregate_dram_bytes_per_window")
             note = ("algorithmic = SURVEY 8(d) K1 only (N/4 + 32*seqs + R*M): the figure of the cheapest stage this "

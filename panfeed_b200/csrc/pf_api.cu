@@ -158,6 +158,8 @@ struct BatchState {
   uint64_t kp_base = 0, cp_base = 0;   // pool sizes before the batch
   bool rows_prefetched = false;
   uint64_t row_cap = 0;          // capacity of the row arrays above
+  cudaEvent_t ev[EV_COUNT]{};    // stage timestamps of the batch's pf_execute
+  PinBuf h_done;                 // pinned mirror of the batch's new k-mer pattern count (K4)
 };
 
 struct pf_ctx : BatchState {
@@ -209,9 +211,12 @@ struct pf_ctx : BatchState {
   PinBuf r_new_kp, r_new_cp, r_pos_kmer, r_pos_seq, r_pos_cstart, r_pos_gstart, r_pos_flags,
       r_pos_wide;
   PinBuf r_wrow_cluster, r_wrow_count, r_wrow_pattern;   // pipelined submit: wide rows apart
-  cudaEvent_t ev[EV_COUNT]{};
   cudaEvent_t ev_h2d[2]{}, ev_d2h[2]{};
   pf_stats stats{};
+  // the k-mer pattern count of the last pf_execute is folded into kp.n lazily (its K4 may still run)
+  bool kp_pending = false;
+  uint64_t kp_pending_base = 0;
+  const uint32_t* kp_pending_count = nullptr;
   std::atomic<uint32_t> launches{0};
   // pipelined submit (submit_pipelined / collect_pipelined)
   bool prefetch_rows = false;    // start the D2H of the row arrays under K4 (PF_PREFETCH_ROWS=1): off by
@@ -393,6 +398,7 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
   }
   cudaEventCreateWithFlags(&ctx->ev_rows, cudaEventDisableTiming);
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  for (auto& ev : ctx->alt.ev) cudaEventCreate(&ev);
   for (auto& ev : ctx->ev_h2d) cudaEventCreate(&ev);
   for (auto& ev : ctx->ev_d2h) cudaEventCreate(&ev);
   // opt in to > 48 KB dynamic shared memory for the sort passes
@@ -493,7 +499,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
       fp(w->h_tiles); fp(w->h_seg_start); fp(w->h_ltiles);
     }
     for (PinBuf* b : {&bs->h_seqs, &bs->h_clusters, &bs->h_wide_seqs, &bs->h_seq_rec_off, &bs->h_tile_first_seq,
-                      &bs->h_plan})
+                      &bs->h_plan, &bs->h_done})
       fp(*b);
   }
   for (DevBuf* b : {&ctx->d_counters, &ctx->d_bsum, &ctx->d_cand, &ctx->d_rep, &ctx->d_slot_of, &ctx->d_winner,
@@ -512,6 +518,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->r_wrow_cluster, &ctx->r_wrow_count, &ctx->r_wrow_pattern})
     fp(*b);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->alt.ev) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_h2d) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_d2h) if (ev) cudaEventDestroy(ev);
   for (int i = 0; i < 2; ++i) {
@@ -1089,26 +1096,28 @@ int dedup(pf_ctx* ctx, PatternSpace& s, const uint32_t* cand, uint32_t n, DevBuf
 
 // A previous pf_execute that was never collected: fold its new-pattern count in.
 int finalize_pending(pf_ctx* ctx) {
-  if (!ctx->executed) return PF_OK;
+  if (!ctx->kp_pending) return PF_OK;
   CU(cudaStreamSynchronize(ctx->stream));
   // (a row prefetch of results nobody collected may still be draining on the copy stream: it is
   //  not waited for — the next prefetch queues behind it on that stream, pf_collect syncs it)
-  ctx->kp.n = ctx->kp_base + ctx->h_counters.as<uint32_t>()[C_NEW_KP];
+  ctx->kp.n = ctx->kp_pending_base + *ctx->kp_pending_count;
+  ctx->kp_pending = false;
   return PF_OK;
 }
 
-void fill_timings(pf_ctx* ctx) {
+void fill_timings(pf_ctx* ctx, const BatchState* slot = nullptr) {
+  const BatchState& B = slot ? *slot : *ctx;
   pf_stats& s = ctx->stats;
   auto ms = [](cudaEvent_t a, cudaEvent_t b) { float m = 0; if (cudaEventElapsedTime(&m, a, b) != cudaSuccess) { cudaGetLastError(); m = 0; } return m; };
   s.ms_h2d = ms(ctx->ev_h2d[0], ctx->ev_h2d[1]);
-  s.ms_extract = ms(ctx->ev[EV_START], ctx->ev[EV_EXTRACT]);
-  s.ms_hist = ms(ctx->ev[EV_EXTRACT], ctx->ev[EV_HIST]);
-  s.ms_sort = ms(ctx->ev[EV_HIST], ctx->ev[EV_SORT]);
-  s.ms_mark = ms(ctx->ev[EV_SORT], ctx->ev[EV_MARK]);
-  s.ms_count = ms(ctx->ev[EV_MARK], ctx->ev[EV_COUNTED]);
-  s.ms_reduce = ms(ctx->ev[EV_COUNTED], ctx->ev[EV_REDUCE]);
-  s.ms_dedup = ms(ctx->ev[EV_REDUCE], ctx->ev[EV_DEDUP]);
-  s.ms_total = ms(ctx->ev[EV_START], ctx->ev[EV_END]);
+  s.ms_extract = ms(B.ev[EV_START], B.ev[EV_EXTRACT]);
+  s.ms_hist = ms(B.ev[EV_EXTRACT], B.ev[EV_HIST]);
+  s.ms_sort = ms(B.ev[EV_HIST], B.ev[EV_SORT]);
+  s.ms_mark = ms(B.ev[EV_SORT], B.ev[EV_MARK]);
+  s.ms_count = ms(B.ev[EV_MARK], B.ev[EV_COUNTED]);
+  s.ms_reduce = ms(B.ev[EV_COUNTED], B.ev[EV_REDUCE]);
+  s.ms_dedup = ms(B.ev[EV_REDUCE], B.ev[EV_DEDUP]);
+  s.ms_total = ms(B.ev[EV_START], B.ev[EV_END]);
   s.sort_passes = (uint32_t)ctx->nar.passes;
   s.engine = ctx->used_block ? 2u : (ctx->partition ? 0u : 1u);
   s.block_windows = ctx->block_windows;
@@ -1392,9 +1401,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   WidthState& Wd = ctx->wid;
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
   uint32_t* hcnt = ctx->h_counters.as<uint32_t>();
-  TRY(finalize_pending(ctx));
   ctx->executed = false;
-  ctx->kp_base = ctx->kp.n;
   ctx->cp_base = ctx->cp.n;
   const bool part = ctx->partition;
 
@@ -1717,11 +1724,20 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   }
 
   // ---- K4 ---------------------------------------------------------------
+  // the previous batch's K4 is long over by now (this call has synchronised the stream at least
+  // once since): fold its pattern count in, then number this batch's patterns behind it
+  TRY(finalize_pending(ctx));
+  ctx->kp_base = ctx->kp.n;
   TRY(dedup(ctx, ctx->kp, ctx->d_cand.as<uint32_t>(), (uint32_t)rows, ctx->d_rep, ctx->d_slot_of,
             ctx->d_winner, ctx->d_row_pattern.as<uint32_t>(), C_NEW_KP));
   CU(cudaEventRecord(ctx->ev[EV_DEDUP], st));
+  TRY(pin_ensure(ctx, ctx->h_done, 16));
   mirror_counters<<<1, 32, 0, st>>>(hcnt, counters, C_COUNT);
+  mirror_counters<<<1, 32, 0, st>>>(ctx->h_done.as<uint32_t>(), counters + C_NEW_KP, 1);
   CU(cudaEventRecord(ctx->ev[EV_END], st));
+  ctx->kp_pending = true;
+  ctx->kp_pending_base = ctx->kp_base;
+  ctx->kp_pending_count = ctx->h_done.as<uint32_t>();
   ctx->executed = true;
   ctx->stats.launches = ctx->launches - launches0;
   return PF_OK;
@@ -1783,8 +1799,8 @@ std::vector<SubRange> split_batch(const pf_batch* b, uint32_t target) {
   return subs;
 }
 
-void pipe_add_timings(pf_ctx* ctx) {
-  fill_timings(ctx);
+void pipe_add_timings(pf_ctx* ctx, const BatchState* slot = nullptr) {
+  fill_timings(ctx, slot);
   const pf_stats& t = ctx->stats;
   const float v[10] = {t.ms_h2d, t.ms_extract, t.ms_hist, t.ms_sort, t.ms_mark, t.ms_count, t.ms_reduce,
                        t.ms_dedup, 0.f, 0.f};
@@ -1916,9 +1932,9 @@ int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>
     std::thread helper;
     int up_rc = PF_OK;
     if (j + 1 < J) {
-      // the other slot's last occupant (sub-batch j-1) must have left: kernels and D2H
+      // the kernels of the other slot's last occupant (sub-batch j-1) must be done with its
+      // inputs; its result arrays are still draining, but an upload does not touch those
       CU(cudaStreamWaitEvent(up, ctx->ev_exec_end[cur ^ 1], 0));
-      CU(cudaStreamWaitEvent(up, ctx->ev_out_done[cur ^ 1], 0));
       helper = std::thread([&, j]() {
         cudaSetDevice(ctx->device);
         const double t0 = now();
@@ -1940,15 +1956,12 @@ int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>
     if (rc != PF_OK) return rc;
     if (up_rc != PF_OK) return up_rc;
     t0 = now();
+    // pf_execute folded sub-batch j-1's pattern count in before its own K4: those patterns are
+    // final, and so are the other slot's stage timestamps
+    TRY(pipe_copy_new_patterns(ctx));
+    if (j > 0) pipe_add_timings(ctx, &ctx->alt);
     if (j + 1 < J) {
-      // sub-batch j's K4 must be over before the next one reserves table space
-      const uint64_t kpb = ctx->kp_base;
-      CU(cudaStreamSynchronize(st));
-      TRY(check_device_error(ctx));
-      ctx->kp.n = kpb + ctx->h_counters.as<uint32_t>()[C_NEW_KP];
       ctx->executed = false;
-      pipe_add_timings(ctx);
-      TRY(pipe_copy_new_patterns(ctx));
       swap_slots();
       cur ^= 1;
       TRY(upload_finish(ctx, *ctx, up));
@@ -1987,6 +2000,7 @@ int collect_pipelined(pf_ctx* ctx, pf_batch_result* out) {
   TRY(check_device_error(ctx));
   uint32_t* hcnt = ctx->h_counters.as<uint32_t>();
   ctx->kp.n = ctx->kp_base + hcnt[C_NEW_KP];      // last sub-batch
+  ctx->kp_pending = false;
   ctx->executed = false;
   ctx->alt.executed = false;
   ctx->pipe_pending = false;
@@ -2061,6 +2075,7 @@ extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
   const uint64_t new_kp = hcnt[C_NEW_KP];
   const uint64_t new_cp = ctx->cp.n - ctx->cp_base;
   ctx->kp.n = ctx->kp_base + new_kp;
+  ctx->kp_pending = false;
   ctx->executed = false;      // results are handed out once
 
   CU(cudaEventRecord(ctx->ev_d2h[0], st));
@@ -2145,6 +2160,7 @@ extern "C" int pf_reset_patterns(pf_ctx* ctx) {
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->executed = false;
+  ctx->kp_pending = false;
   for (PatternSpace* s : {&ctx->kp, &ctx->cp}) {
     s->n = 0;
     s->x_n_unique = 0;
@@ -2197,6 +2213,7 @@ extern "C" int pf_stats_get(pf_ctx* ctx, pf_stats* out) {
   if (!ctx || !out) return PF_ERR_INVALID;
   if (ctx->executed) {
     TRY(finalize_pending(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
     fill_timings(ctx);
   }
   ctx->stats.kmer_patterns = ctx->kp.n;
