@@ -265,6 +265,8 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    if world > 1:      # the ranks share the host: split its cores between their planning threads
+        os.environ.setdefault("PF_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // world)))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         # rank 0 prints ONE JSON line on stdout: NCCL's version banner / warnings go to stderr

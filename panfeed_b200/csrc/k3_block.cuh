@@ -123,6 +123,25 @@ __global__ void plan_cluster_slices(const SeqDev* __restrict__ seqs, const Clust
   }
 }
 
+// one thread per kA work item (cluster, run, slice): everything the kernel needs to find its
+// sequences, in one 16-byte load instead of a chain of three dependent ones
+__global__ void plan_item_desc(const uint32_t* __restrict__ item_base, const uint32_t* __restrict__ item_cluster,
+                               const ClusterBlk* __restrict__ cb, const uint32_t* __restrict__ slice_seq,
+                               uint32_t n_run_items, uint32_t n_slices, uint32_t run_windows,
+                               uint4* __restrict__ desc) {
+  const uint32_t item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_run_items * n_slices) return;
+  const uint32_t run_item = item / n_slices, slice = item - run_item * n_slices;
+  const uint32_t c = item_cluster[run_item];
+  const ClusterBlk b = cb[c];
+  uint32_t lo = 0, hi = b.n_seqs;
+  if (n_slices > 1) {
+    lo = slice_seq[(size_t)c * (n_slices + 1) + slice];
+    hi = slice_seq[(size_t)c * (n_slices + 1) + slice + 1];
+  }
+  desc[item] = make_uint4(b.seq_start + lo, b.seq_start + hi, (run_item - item_base[c]) * run_windows, c);
+}
+
 // ---------------------------------------------------------------------------
 // shared-memory table
 // ---------------------------------------------------------------------------
@@ -213,6 +232,7 @@ struct BlkPlan {
   uint32_t n_slices;             // 1: no slicing
   uint32_t slice_samples;        // multiple of 32
   const uint32_t* slice_seq;     // [n_clusters][n_slices + 1] first sequence (cluster-relative) of every slice
+  const uint4* item_desc;        // [n_items * n_slices] {first seq, end seq (absolute), first window, cluster}
 };
 
 // Shared memory of kA.  Both tables hand out DENSE row ids on insertion and the inserting
@@ -289,8 +309,6 @@ __device__ __noinline__ uint32_t chunk_find_or_insert(const ARunView a, uint64_t
           *reinterpret_cast<volatile uint32_t*>(&a.cstate[s]) = kChunkEmpty;
           return 0xffffffffu;
         }
-        uint32_t* row = a.crows + id * WS;
-        for (uint32_t w = 0; w < WS; ++w) row[w] = 0u;
         *reinterpret_cast<volatile uint64_t*>(&a.ckhi[id]) = hi;
         *reinterpret_cast<volatile uint64_t*>(&a.cklo[id]) = lo;
         __threadfence_block();
@@ -315,8 +333,6 @@ __device__ __noinline__ uint32_t kmer_row_slow(const ARunView a, uint64_t key, u
       if (cur == ~0ull) {                                     // this thread owns the new slot
         uint32_t id = atomicAdd(&a.h->n_unique, 1u);
         if (id >= a.cap) { a.h->overflow = 1u; id = a.cap; }
-        uint32_t* row = a.pool + id * WS;
-        for (uint32_t w = 0; w < WS; ++w) row[w] = 0u;
         a.rkey[id] = key;
         __threadfence_block();
         *reinterpret_cast<volatile uint16_t*>(&a.rowid[h]) = (uint16_t)id;
@@ -354,25 +370,29 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
   const uint32_t tid = threadIdx.x;
   const uint32_t item = item_list ? item_list[blockIdx.x] : blockIdx.x;
 
-  const uint32_t run_item = plan.n_slices > 1 ? item / plan.n_slices : item;
-  const uint32_t slice = item - run_item * plan.n_slices;
-  const uint32_t c = plan.item_cluster[run_item];
-  const ClusterBlk cb = plan.cblk[c];
-  const uint32_t s_rel = (run_item - plan.item_base[c]) * (uint32_t)kBlkRun;   // first window of the run
-  uint32_t seq_lo = 0, seq_hi = cb.n_seqs;
-  if (plan.n_slices > 1) {
-    seq_lo = plan.slice_seq[(size_t)c * (plan.n_slices + 1) + slice];
-    seq_hi = plan.slice_seq[(size_t)c * (plan.n_slices + 1) + slice + 1];
-    if (seq_lo == seq_hi) {                          // no sample of this slice carries the cluster
-      if (tid == 0) { slab_count[item] = 0; slab_base[item] = 0; }
-      return;
-    }
+  const uint4 desc = __ldg(plan.item_desc + item);
+  const uint32_t seq_lo = desc.x, seq_hi = desc.y, s_rel = desc.z;    // sequences, first window of the run
+  if (seq_lo == seq_hi) {                            // no sample of this slice carries the cluster
+    if (tid == 0) { slab_count[item] = 0; slab_base[item] = 0; }
+    return;
   }
-  const uint32_t sample0 = slice * plan.slice_samples;
+  const uint32_t sample0 = plan.n_slices > 1 ? (item % plan.n_slices) * plan.slice_samples : 0u;
+  // the thread's first sequence is requested before the tables are initialised
+  uint4 raw_first = make_uint4(0, 0, 0, 0);
+  if (seq_lo + tid < seq_hi) raw_first = __ldg(reinterpret_cast<const uint4*>(seqs + seq_lo + tid));
 
   for (uint32_t i = tid; i < plan.slots; i += kBlkThreads) { a.keys[i] = ~0ull; a.rowid[i] = 0xffffu; }
   for (uint32_t i = tid; i < plan.cslots; i += kBlkThreads) a.cstate[i] = kChunkEmpty;
+  // all bitset rows are cleared here by the whole CTA: a lone inserting lane clearing its own
+  // row costs a warp instruction per word
+  for (uint32_t i = tid; i < (a.cap + 1u) * WS; i += kBlkThreads) a.pool[i] = 0u;
+  for (uint32_t i = tid; i < a.ccap * WS; i += kBlkThreads) a.crows[i] = 0u;
   if (tid == 0) { a.h->n_unique = 0; a.h->overflow = 0; a.h->work = 0; }
+  uint64_t wf0 = 0, wf1 = 0, wf2 = 0;
+  if (raw_first.y >= (uint32_t)k && s_rel < raw_first.y - (uint32_t)k + 1u) {
+    const uint64_t* w = bases + raw_first.x + (s_rel >> 5);
+    wf0 = __ldg(w); wf1 = __ldg(w + 1); wf2 = __ldg(w + 2);
+  }
   __syncthreads();
 
   const uint32_t sh64 = 64u - 2u * (uint32_t)k;
@@ -403,7 +423,8 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
   // ---- phase 1: every sequence's run -> chunk table (or, for ragged / ambiguous runs and a
   //      full chunk table, straight into the k-mer table) ------------------------------------
   for (uint32_t si = seq_lo + tid; si < seq_hi; si += kBlkThreads) {
-    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(seqs + cb.seq_start + si));
+    const bool first = si == seq_lo + tid;
+    const uint4 raw = first ? raw_first : __ldg(reinterpret_cast<const uint4*>(seqs + si));
     const uint32_t len = raw.y;
     if (len < (uint32_t)k) continue;
     const uint32_t nwin = len - (uint32_t)k + 1u;
@@ -414,7 +435,7 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
     const uint32_t wofs = sample >> 5, bit = 1u << (sample & 31u);
     // three words cover the run: 16 + k - 1 <= 47 bases from an offset < 32
     const uint64_t* w = bases + raw.x + (s_rel >> 5);
-    const uint64_t w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+    const uint64_t w0 = first ? wf0 : __ldg(w), w1 = first ? wf1 : __ldg(w + 1), w2 = first ? wf2 : __ldg(w + 2);
     const uint32_t o0 = s_rel & 31u;
     uint64_t hi = w0, lo = w1;
     if (o0) {

@@ -153,7 +153,7 @@ struct BatchState {
   PinBuf h_seq_rec_off, h_tile_first_seq;
   std::vector<std::pair<uint32_t, uint32_t>> nar_ranges;   // narrow record range of every cluster
   uint32_t n_items = 0;          // (cluster, block) work items of the batch (block aggregation)
-  DevBuf d_seq_lite, d_cblk, d_item_base, d_item_cluster, d_plan_total, d_bsum_slot, d_slice_seq;
+  DevBuf d_seq_lite, d_cblk, d_item_base, d_item_cluster, d_plan_total, d_bsum_slot, d_slice_seq, d_item_desc;
   PinBuf h_plan;
   uint64_t kp_base = 0, cp_base = 0;   // pool sizes before the batch
   bool rows_prefetched = false;
@@ -489,7 +489,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                       &bs->d_row_pattern, &bs->d_cl_pattern, &bs->d_pos_kmer, &bs->d_pos_seq, &bs->d_pos_cstart,
                       &bs->d_pos_gstart, &bs->d_pos_flags, &bs->d_pos_wide, &bs->d_seq_rec_off,
                       &bs->d_tile_first_seq, &bs->d_seq_lite, &bs->d_cblk, &bs->d_item_base, &bs->d_item_cluster,
-                      &bs->d_plan_total, &bs->d_bsum_slot, &bs->d_slice_seq})
+                      &bs->d_plan_total, &bs->d_bsum_slot, &bs->d_slice_seq, &bs->d_item_desc})
       fd(*b);
     for (WidthState* w : {&bs->nar, &bs->wid}) {
       for (DevBuf* b : {&w->keys[0], &w->keys[1], &w->vals[0], &w->vals[1], &w->tiles, &w->seg_start,
@@ -670,7 +670,10 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
   std::vector<std::pair<uint32_t, uint32_t>> nr(b->n_clusters), wr(b->n_clusters);
   {
     const uint32_t n = b->n_seqs;
-    const uint32_t n_thr = std::max(1u, std::min<uint32_t>(std::min(16u, std::thread::hardware_concurrency()),
+    // PF_HOST_THREADS caps the planning threads (several contexts / ranks share the host's cores)
+    static const uint32_t host_thr = []() { const char* e = getenv("PF_HOST_THREADS"); const int v = e ? atoi(e) : 0;
+                                            return v > 0 ? (uint32_t)v : 16u; }();
+    const uint32_t n_thr = std::max(1u, std::min<uint32_t>(std::min(host_thr, std::thread::hardware_concurrency()),
                                                            (n + 65535u) / 65536u));
     struct Part { uint64_t rec = 0, wrec = 0, pos = 0, pwide = 0, bases = 0; uint32_t wide = 0; std::string err; };
     std::vector<Part> parts(n_thr);
@@ -1253,6 +1256,14 @@ int plan_blocks_finish(pf_ctx* ctx, BatchState& B, cudaStream_t st) {
   TRY(dev_ensure(ctx, B.d_item_cluster, std::max<size_t>(1, B.n_items) * 4));
   plan_expand_owner<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(B.d_item_base.as<uint32_t>(), nc,
                                                                   B.d_item_cluster.as<uint32_t>());
+  const uint64_t n_ka = (uint64_t)B.n_items * ctx->n_slices;
+  if (n_ka >= (1ull << 31)) return fail(ctx, PF_ERR_INVALID, "too many (cluster, run, slice) work items; split the batch");
+  TRY(dev_ensure(ctx, B.d_item_desc, std::max<size_t>(1, n_ka) * 16));
+  if (n_ka)
+    plan_item_desc<<<cdiv(n_ka, 256), 256, 0, st>>>(
+        B.d_item_base.as<uint32_t>(), B.d_item_cluster.as<uint32_t>(), B.d_cblk.as<ClusterBlk>(),
+        ctx->n_slices > 1 ? B.d_slice_seq.as<uint32_t>() : nullptr, B.n_items, ctx->n_slices,
+        (uint32_t)kBlkRun, B.d_item_desc.as<uint4>());
   CU(cudaGetLastError());
   return PF_OK;
 }
@@ -1272,6 +1283,7 @@ BlkPlan block_plan(const pf_ctx* ctx) {
   bp.n_slices = ctx->n_slices;
   bp.slice_samples = ctx->slice_samples;
   bp.slice_seq = ctx->n_slices > 1 ? ctx->d_slice_seq.as<uint32_t>() : nullptr;
+  bp.item_desc = ctx->d_item_desc.as<uint4>();
   return bp;
 }
 
