@@ -175,8 +175,10 @@ typedef struct pf_stats {
   float ms_h2d, ms_extract, ms_hist, ms_sort, ms_mark, ms_count, ms_reduce, ms_dedup, ms_d2h, ms_total;
   uint64_t total_launches;   /* kernels launched since pf_create                     */
   /* engine the last batch went through: 0 = records, partition mode (K1 fused into one radix
-     pass + shared-memory grouping); 1 = records, full sort; 2 = block aggregation (rolling
-     k-mers grouped per position block in shared memory, no records; S <= 1024) */
+     pass + shared-memory grouping); 1 = records, full sort; 2 = block aggregation (per run of
+     16 window positions the sequences of a cluster are grouped as 128-bit chunks, the distinct
+     chunks are cut into k-mers and per-k-mer sample bitsets are built in shared memory: no
+     records; above 1024 samples in slices of 512 samples) */
   uint32_t engine;
   uint32_t block_windows;    /* engine 2: windows per position block                  */
   uint32_t block_slots;      /* engine 2: shared-memory table slots per block         */
@@ -224,6 +226,10 @@ int pf_patterns_export(pf_ctx* ctx, int cluster_namespace, uint64_t first,
 int pf_pattern_ids(pf_ctx* ctx, int cluster_namespace, uint64_t first, uint64_t count,
                    uint8_t* host_digests);
 int pf_stats_get(pf_ctx* ctx, pf_stats* out);
+/* sizeof of the ABI structs as the library was built: 0 pf_params, 1 pf_seq_desc,
+ * 2 pf_cluster_desc, 3 pf_batch, 4 pf_batch_result, 5 pf_stats, 6 pf_synth_params; 0 for an
+ * unknown id.  Lets a binding check its own struct mirrors. */
+uint32_t pf_struct_size(int which);
 /* CUDA stream the context launches on, as an opaque handle (cudaStream_t). */
 void* pf_stream(pf_ctx* ctx);
 

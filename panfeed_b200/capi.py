@@ -108,7 +108,7 @@ class SynthParams(C.Structure):
 EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_upload", "pf_execute", "pf_submit", "pf_collect",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
-           "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_stream",
+           "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_export",
            "pf_exchange_unpack"]

@@ -336,6 +336,18 @@ extern "C" int pf_maf_window(double maf, uint32_t n, uint32_t* lo, uint32_t* hi)
 
 extern "C" uint32_t pf_pattern_words(uint32_t n_samples) { return (n_samples + 31u) / 32u; }
 extern "C" int pf_abi_version(void) { return PF_ABI_VERSION; }
+extern "C" uint32_t pf_struct_size(int which) {
+  switch (which) {
+    case 0: return (uint32_t)sizeof(pf_params);
+    case 1: return (uint32_t)sizeof(pf_seq_desc);
+    case 2: return (uint32_t)sizeof(pf_cluster_desc);
+    case 3: return (uint32_t)sizeof(pf_batch);
+    case 4: return (uint32_t)sizeof(pf_batch_result);
+    case 5: return (uint32_t)sizeof(pf_stats);
+    case 6: return (uint32_t)sizeof(pf_synth_params);
+    default: return 0;
+  }
+}
 extern "C" const char* pf_last_error(const pf_ctx* ctx) {
   return ctx ? ctx->err.c_str() : g_create_error.c_str();
 }

@@ -30,6 +30,20 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(capi.Batch) == 72
 
 
+def test_ctypes_mirrors_match_the_library():
+    """Every struct the binding mirrors has the size the library was compiled with."""
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    lib.pf_struct_size.restype = ctypes.c_uint32
+    lib.pf_struct_size.argtypes = [ctypes.c_int]
+    mirrors = {0: ctypes.sizeof(capi.Params), 1: capi.SEQ_DTYPE.itemsize,
+               2: capi.CLUSTER_DTYPE.itemsize, 3: ctypes.sizeof(capi.Batch),
+               4: ctypes.sizeof(capi.BatchResult), 5: ctypes.sizeof(capi.Stats),
+               6: ctypes.sizeof(capi.SynthParams)}
+    for which, size in mirrors.items():
+        assert lib.pf_struct_size(which) == size, which
+    assert lib.pf_struct_size(99) == 0
+
+
 def test_maf_window_known_answers():
     for kat in helpers.hot_kats()["maf_windows"]:
         got = capi.maf_window(kat["maf"], kat["n"])
