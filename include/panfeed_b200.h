@@ -233,6 +233,19 @@ uint32_t pf_struct_size(int which);
 /* CUDA stream the context launches on, as an opaque handle (cudaStream_t). */
 void* pf_stream(pf_ctx* ctx);
 
+/* ---- native text formatting of the positional records (host threads, no device work) ----
+ * The kmers.tsv rows cluster_cutter writes at panfeed.py:90-107,
+ *   {idx}\t{strain}\t{gene_id}\t{contig}\t{strand}\t{truestart}\t{trueend}\t{genestart}\t{geneend}\t{used_strand}\t{kmer}\n
+ * for records [first, first + count) of a result.  lead_blob / lead_off give, per sequence of the
+ * batch, the first five fields with their tabs ("idx\tstrain\tgene_id\tcontig\tstrand\t");
+ * seq_strand the Seqinfo.strand of every sequence (only read when canonical == 0, where every
+ * record yields two rows: the forward k-mer on `strand`, its reverse complement on `-strand`).
+ * out == NULL: only *out_len (bytes needed) is computed.  n_threads == 0: all host cores. */
+int pf_format_positions(const pf_batch_result* result, uint32_t k, int canonical, uint64_t first,
+                        uint64_t count, const char* lead_blob, const uint64_t* lead_off,
+                        const int32_t* seq_strand, char* out, uint64_t out_cap, uint64_t* out_len,
+                        uint32_t n_threads);
+
 /* ---- synthetic pangenome, generated on the device ---- */
 typedef struct pf_synth_params {
   uint64_t seed;

@@ -108,7 +108,7 @@ class SynthParams(C.Structure):
 EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_upload", "pf_execute", "pf_submit", "pf_collect",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
-           "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream",
+           "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream", "pf_format_positions",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_export",
            "pf_exchange_unpack"]
@@ -142,6 +142,9 @@ def load():
     lib.pf_kmer_pattern_words.restype = u32
     lib.pf_maf_window.argtypes = [C.c_double, u32, C.POINTER(u32), C.POINTER(u32)]
     lib.pf_patterns_export.argtypes = [vp, C.c_int, u64, u64, vp]
+    lib.pf_format_positions.argtypes = [C.POINTER(BatchResult), u32, C.c_int, u64, u64, C.c_char_p,
+                                        C.POINTER(u64), C.POINTER(C.c_int32), C.c_char_p, u64,
+                                        C.POINTER(u64), u32]
     lib.pf_pattern_ids.argtypes = [vp, C.c_int, u64, u64, vp]
     lib.pf_stats_get.argtypes = [vp, C.POINTER(Stats)]
     lib.pf_stream.argtypes = [vp]
@@ -162,6 +165,51 @@ def maf_window(maf, n):
     lo, hi = C.c_uint32(), C.c_uint32()
     ok = load().pf_maf_window(maf, n, C.byref(lo), C.byref(hi))
     return (lo.value, hi.value) if ok else None
+
+
+def format_positions(r, k, canonical, leads, seq_strand, n_threads=0):
+    """kmers.tsv text (bytes) of the positional records in `r` (a dict as returned by
+    Context.collect(), or any dict with the pos_* arrays), formatted by the library's
+    host threads (pf_format_positions).  leads[i] = b"idx\tstrain\tgene_id\tcontig\tstrand\t"
+    of sequence i of the batch; seq_strand[i] its Seqinfo.strand."""
+    lib = load()
+    n = len(r["pos_seq"])
+    if n == 0:
+        return b""
+    keep = {}
+
+    def ptr(a, dtype, ctype):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        keep[id(a)] = a
+        return a.ctypes.data_as(C.POINTER(ctype))
+
+    res = BatchResult()
+    res.n_pos = n
+    res.pos_kmer = ptr(r["pos_kmer"], np.uint64, C.c_uint64)
+    res.pos_seq = ptr(r["pos_seq"], np.uint32, C.c_uint32)
+    res.pos_contig_start = ptr(r["pos_contig_start"], np.int32, C.c_int32)
+    res.pos_gene_start = ptr(r["pos_gene_start"], np.int32, C.c_int32)
+    res.pos_flags = ptr(r["pos_flags"], np.uint8, C.c_uint8)
+    wide = np.ascontiguousarray(r.get("pos_wide_kmer", np.zeros((0, 2), np.uint64)), dtype=np.uint64).reshape(-1)
+    if wide.size == 0:
+        wide = np.zeros(2, np.uint64)
+    res.pos_wide_kmer = ptr(wide, np.uint64, C.c_uint64)
+    res.n_pos_wide = wide.size // 2
+    blob = b"".join(leads)
+    off = np.zeros(len(leads) + 1, np.uint64)
+    np.cumsum([len(x) for x in leads], out=off[1:])
+    strand = np.ascontiguousarray(seq_strand, dtype=np.int32)
+    need = C.c_uint64()
+    args = (C.byref(res), int(k), int(bool(canonical)), 0, n, blob, off.ctypes.data_as(C.POINTER(C.c_uint64)),
+            strand.ctypes.data_as(C.POINTER(C.c_int32)))
+    rc = lib.pf_format_positions(*args, None, 0, C.byref(need), int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_format_positions (sizing) failed")
+    out = np.empty(int(need.value), np.uint8)
+    rc = lib.pf_format_positions(*args, out.ctypes.data_as(C.c_char_p), out.size, C.byref(need), int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_format_positions failed")
+    return out.tobytes()
 
 
 def _np(ptr, n, dtype, copy=True):

@@ -1,0 +1,164 @@
+// Native (multi-threaded, host) text formatting of the positional records: the kmers.tsv rows
+// the reference's cluster_cutter writes at /root/reference/panfeed/panfeed.py:90-107,
+//
+//   {idx}\t{strain}\t{gene_id}\t{contig}\t{strand}\t{truestart}\t{trueend}\t{genestart}\t{geneend}\t{used_strand}\t{kmer}\n
+//
+// from the binary records pf_collect returns (21 bytes per k-mer instance).  A second pass
+// over a few hundred clusters yields 1e8 rows; formatting them in the Python host costs minutes,
+// here it is a memory-bound loop over host threads.  No device code in this file.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../include/panfeed_b200.h"
+
+namespace {
+
+const char kAcgt[5] = "ACGT";
+const char kAmb[17] = PF_AMB_ALPHABET;
+// complement of the 16 symbols (pyfaidx table restricted to upper case, as input.py:448-452 uses it)
+inline char comp_symbol(char c) {
+  switch (c) {
+    case 'A': return 'T'; case 'C': return 'G'; case 'T': return 'A'; case 'G': return 'C';
+    case 'N': return 'N'; case 'Y': return 'R'; case 'R': return 'Y'; case 'W': return 'W';
+    case 'S': return 'S'; case 'K': return 'M'; case 'M': return 'K'; case 'D': return 'H';
+    case 'V': return 'B'; case 'H': return 'D'; case 'B': return 'V'; case 'X': return 'X';
+    default: return c;
+  }
+}
+
+inline int put_int(char* p, int64_t v) {          // decimal, like Python's str(int); returns the length
+  char tmp[24];
+  int n = 0;
+  uint64_t u = v < 0 ? (uint64_t)(-v) : (uint64_t)v;
+  do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+  int len = 0;
+  if (v < 0) p[len++] = '-';
+  while (n) p[len++] = tmp[--n];
+  return len;
+}
+inline int len_int(int64_t v) {
+  int len = v < 0 ? 1 : 0;
+  uint64_t u = v < 0 ? (uint64_t)(-v) : (uint64_t)v;
+  do { ++len; u /= 10; } while (u);
+  return len;
+}
+
+struct Job {
+  const pf_batch_result* r;
+  uint32_t k;
+  int canonical;
+  const char* lead_blob;
+  const uint64_t* lead_off;
+  const int32_t* seq_strand;
+};
+
+// k-mer text of record i into `out` (k bytes)
+inline void kmer_text(const Job& j, uint64_t i, char* out) {
+  const uint32_t k = j.k;
+  if (j.r->pos_flags[i] & 2u) {
+    const uint64_t* w = j.r->pos_wide_kmer + 2 * j.r->pos_kmer[i];      // [hi, lo], 4 bits per symbol
+    for (uint32_t s = 0; s < k; ++s) {
+      const uint32_t nib = k - 1 - s;
+      const uint64_t word = nib < 16 ? w[1] : w[0];
+      out[s] = kAmb[(word >> (4 * (nib % 16))) & 15u];
+    }
+  } else {
+    const uint64_t v = j.r->pos_kmer[i];
+    for (uint32_t s = 0; s < k; ++s) out[s] = kAcgt[(v >> (2 * (k - 1 - s))) & 3u];
+  }
+}
+
+inline uint64_t row_len(const Job& j, uint64_t i) {
+  const uint32_t seq = j.r->pos_seq[i];
+  const uint64_t lead = j.lead_off[seq + 1] - j.lead_off[seq];
+  const int64_t c0 = j.r->pos_contig_start[i], g0 = j.r->pos_gene_start[i];
+  const uint64_t coords = (uint64_t)len_int(c0) + len_int(c0 + j.k) + len_int(g0) + len_int(g0 + j.k) + 4;
+  if (j.canonical) {
+    const int used = (j.r->pos_flags[i] & 1u) ? 2 : 1;                  // "-1" / "1"
+    return lead + coords + used + 1 + j.k + 1;
+  }
+  const int32_t st = j.seq_strand[seq];                                  // rows for st and -st
+  return 2 * (lead + coords + 1 + j.k + 1) + len_int(st) + len_int(-(int64_t)st);
+}
+
+inline char* write_row(const Job& j, uint64_t i, char* p) {
+  const uint32_t seq = j.r->pos_seq[i];
+  const uint64_t lead = j.lead_off[seq + 1] - j.lead_off[seq];
+  const int64_t c0 = j.r->pos_contig_start[i], g0 = j.r->pos_gene_start[i];
+  char km[40];
+  kmer_text(j, i, km);
+  auto head = [&](char* q) {
+    memcpy(q, j.lead_blob + j.lead_off[seq], lead);
+    q += lead;
+    q += put_int(q, c0); *q++ = '\t';
+    q += put_int(q, c0 + j.k); *q++ = '\t';
+    q += put_int(q, g0); *q++ = '\t';
+    q += put_int(q, g0 + j.k); *q++ = '\t';
+    return q;
+  };
+  if (j.canonical) {
+    p = head(p);
+    if (j.r->pos_flags[i] & 1u) { *p++ = '-'; *p++ = '1'; } else { *p++ = '1'; }
+    *p++ = '\t';
+    memcpy(p, km, j.k); p += j.k;
+    *p++ = '\n';
+    return p;
+  }
+  const int32_t st = j.seq_strand[seq];
+  p = head(p);
+  p += put_int(p, st); *p++ = '\t';
+  memcpy(p, km, j.k); p += j.k;
+  *p++ = '\n';
+  p = head(p);
+  p += put_int(p, -(int64_t)st); *p++ = '\t';
+  for (uint32_t s = 0; s < j.k; ++s) p[s] = comp_symbol(km[j.k - 1 - s]);   // reverse complement
+  p += j.k;
+  *p++ = '\n';
+  return p;
+}
+
+}  // namespace
+
+extern "C" int pf_format_positions(const pf_batch_result* r, uint32_t k, int canonical, uint64_t first,
+                                   uint64_t count, const char* lead_blob, const uint64_t* lead_off,
+                                   const int32_t* seq_strand, char* out, uint64_t out_cap, uint64_t* out_len,
+                                   uint32_t n_threads) {
+  if (!r || !out_len || k < 1 || k > 32) return PF_ERR_INVALID;
+  if (first + count > r->n_pos) return PF_ERR_INVALID;
+  *out_len = 0;
+  if (count == 0) return PF_OK;
+  if (!lead_blob || !lead_off || (!canonical && !seq_strand)) return PF_ERR_INVALID;
+  Job j{r, k, canonical, lead_blob, lead_off, seq_strand};
+  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  uint32_t nt = n_threads ? n_threads : hw;
+  nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nt, (count + 65535) / 65536));
+  const uint64_t per = (count + nt - 1) / nt;
+  std::vector<uint64_t> bytes(nt, 0);
+  auto run = [&](auto&& fn) {
+    if (nt == 1) { fn(0u); return; }
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < nt; ++t) th.emplace_back(fn, t);
+    for (auto& x : th) x.join();
+  };
+  run([&](uint32_t t) {
+    const uint64_t a = first + std::min<uint64_t>(count, t * per), b = first + std::min<uint64_t>(count, (t + 1) * per);
+    uint64_t s = 0;
+    for (uint64_t i = a; i < b; ++i) s += row_len(j, i);
+    bytes[t] = s;
+  });
+  uint64_t total = 0;
+  std::vector<uint64_t> start(nt, 0);
+  for (uint32_t t = 0; t < nt; ++t) { start[t] = total; total += bytes[t]; }
+  *out_len = total;
+  if (!out) return PF_OK;                       // sizing call
+  if (out_cap < total) return PF_ERR_NOMEM;
+  run([&](uint32_t t) {
+    const uint64_t a = first + std::min<uint64_t>(count, t * per), b = first + std::min<uint64_t>(count, (t + 1) * per);
+    char* p = out + start[t];
+    for (uint64_t i = a; i < b; ++i) p = write_row(j, i, p);
+  });
+  return PF_OK;
+}

@@ -173,13 +173,19 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
 
     # ---- kmers_to_hashes rows, cluster by cluster ------------------------------
     kmer_ids = np.array(store.kmer_ids, dtype="S24") if store.kmer_ids else np.zeros(0, "S24")
-    row_cluster = np.concatenate([r["row_cluster"], r["wide_row_cluster"]])
-    row_kmer = np.concatenate([packer.kmers_to_str(r["row_kmer"], k),
-                               packer.wide_kmers_to_str(r["wide_row_kmer"], k)])
-    row_pid = kmer_ids[np.concatenate([r["row_pattern"], r["wide_row_pattern"]]).astype(np.int64)] \
-        if len(row_cluster) else np.zeros(0, "S24")
-    order = np.lexsort((row_kmer, row_cluster))
-    row_cluster, row_kmer, row_pid = row_cluster[order], row_kmer[order], row_pid[order]
+    # rows grouped by cluster; inside a cluster the narrow rows in numeric (= alphabetical) k-mer
+    # order, then the rows holding N/IUPAC symbols (the reference's order is arbitrary too)
+    n_order = np.lexsort((r["row_kmer"], r["row_cluster"]))
+    w_order = np.lexsort((r["wide_row_kmer"][:, 1], r["wide_row_kmer"][:, 0], r["wide_row_cluster"])) \
+        if len(r["wide_row_cluster"]) else np.zeros(0, np.int64)
+    row_cluster = np.concatenate([r["row_cluster"][n_order], r["wide_row_cluster"][w_order]])
+    row_kmer = np.concatenate([packer.kmers_to_str(r["row_kmer"][n_order], k),
+                               packer.wide_kmers_to_str(r["wide_row_kmer"][w_order], k)])
+    row_pat = np.concatenate([r["row_pattern"][n_order], r["wide_row_pattern"][w_order]]).astype(np.int64)
+    row_pid = kmer_ids[row_pat] if len(row_cluster) else np.zeros(0, "S24")
+    if len(r["wide_row_cluster"]):
+        order = np.argsort(row_cluster, kind="stable")
+        row_cluster, row_kmer, row_pid = row_cluster[order], row_kmer[order], row_pid[order]
     bounds = np.searchsorted(row_cluster, np.arange(len(pcs) + 1))
     hash_texts = []
     for c, idx in enumerate(idxs):
@@ -199,36 +205,13 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
         buf[:, -1] = ord("\n")
         hash_texts.append(head + buf.tobytes().decode())
 
-    # ---- kmers.tsv rows from the positional records -----------------------------
+    # ---- kmers.tsv rows from the positional records: formatted by the library's host
+    #      threads (pf_format_positions), 1e8 rows are too many for Python ----------------
     pos_text = ""
     if len(r["pos_seq"]):
-        kmer_s = packer.kmers_to_str(r["pos_kmer"], k)
-        amb = (r["pos_flags"] & 2) != 0
-        if amb.any():
-            wide_s = packer.wide_kmers_to_str(r["pos_wide_kmer"], k)
-            kmer_s = kmer_s.copy()
-            kmer_s[amb] = wide_s[r["pos_kmer"][amb].astype(np.int64)]
-        seq = r["pos_seq"].astype(np.int64)
-        strand = hb.seqs["strand"][seq]
-        lead = np.array([f"{idxs[hb.seqs['cluster'][i]]}\t{meta[i][0]}\t{meta[i][1]}\t{meta[i][2]}\t"
-                         f"{hb.seqs['strand'][i]}\t" for i in range(len(hb.seqs))], dtype=object)
-        c0 = r["pos_contig_start"].astype(np.int64)
-        g0 = r["pos_gene_start"].astype(np.int64)
-        coords = (np.char.add(np.char.add(np.char.add(c0.astype(str), "\t"),
-                                          np.char.add((c0 + k).astype(str), "\t")),
-                              np.char.add(np.char.add(g0.astype(str), "\t"),
-                                          np.char.add((g0 + k).astype(str), "\t"))))
-        kmer_u = kmer_s.astype(str)
-        if canonical:
-            used = np.where((r["pos_flags"] & 1) != 0, "-1", "1")
-            rows = [a + b + u + "\t" + km + "\n"
-                    for a, b, u, km in zip(lead[seq], coords, used, kmer_u)]
-        else:
-            rows = []
-            for a, b, st, km in zip(lead[seq], coords, strand, kmer_s):
-                rc = km.translate(_COMP)[::-1].decode()
-                rows.append(f"{a}{b}{st}\t{km.decode()}\n{a}{b}{-st}\t{rc}\n")
-        pos_text = "".join(rows)
+        leads = [f"{idxs[hb.seqs['cluster'][i]]}\t{meta[i][0]}\t{meta[i][1]}\t{meta[i][2]}\t"
+                 f"{hb.seqs['strand'][i]}\t".encode() for i in range(len(hb.seqs))]
+        pos_text = capi.format_positions(r, k, canonical, leads, hb.seqs["strand"]).decode()
     return pos_text, "".join(pat_text), hash_texts
 
 
