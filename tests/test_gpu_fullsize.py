@@ -113,3 +113,25 @@ def test_full_size_sample_of_clusters_matches_oracle(full_run):
         exp = sorted(zip(want["row_kmer"].tolist(), want["row_count"].tolist(),
                          [want["kmer_pattern_bits"][p].tobytes() for p in want["row_pattern"]]))
         assert got == exp, f"cluster {c}"
+
+
+@pytest.mark.parametrize("samples,clusters,cm", [(10000, 48, False), (50000, 8, True)])
+def test_sample_sliced_engine_agrees_with_records(samples, clusters, cm):
+    """BASELINE configs #4 / #5 sample counts (10,000 / 50,000 genomes, the latter with the
+    cluster-absent encoding): the block engine in 512-sample slices and the record engine
+    produce the same multiset of (cluster, k-mer, count, bitset) rows and the same patterns."""
+    hb = capi.synth_batch(0, 20261018 + 4, samples, clusters, total_clusters=clusters, gene_len=L)
+    W = (samples + 31) // 32
+    res = {}
+    for name, flags in (("block", 0), ("records", 2)):
+        ctx = capi.Context(K, samples, consider_missing=cm, maf=0.01, debug_flags=flags)
+        ctx.submit(hb)
+        r = ctx.collect()
+        st = ctx.stats()
+        ctx.close()
+        res[name] = (st, _checksum(r, W), len(r["new_kmer_patterns"]))
+    assert res["block"][0]["engine"] == 2 and res["records"][0]["engine"] == 0
+    assert res["block"][0]["rows"] == res["records"][0]["rows"] > 10000
+    assert res["block"][0]["unique_kmers"] == res["records"][0]["unique_kmers"]
+    assert res["block"][1] == res["records"][1]
+    assert res["block"][2] == res["records"][2]
