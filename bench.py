@@ -497,7 +497,7 @@ def main():
             line["config"]["workload"] = line["config"]["workload"].replace("first pass", "second pass, all samples --targets")
         if exch_ms:
             line["exchange_ms_last_step_rank0"] = {k_: round(v_, 3) for k_, v_ in exch_ms.items()}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only
             line["cpu_baseline"] = cpu_baseline_c(hb, S, k, args.maf, args.consider_missing,
                                                   args.cpu_seconds)
         print(json.dumps(line))

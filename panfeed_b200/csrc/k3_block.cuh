@@ -256,6 +256,7 @@ struct ARunView {
   uint32_t* pool;          // [(cap + 1) * WS]   row `cap` takes the ORs of an overflowing block
   uint32_t* crows;         // [ccap * WS]
   uint16_t* rowid;         // [slots]
+  uint16_t* cmeta;         // [ccap]  low byte: bitset word of the chunk's first sample; bit 15: other words too
   uint32_t mask, shift, cmask, cshift, cap, ccap;
 };
 __host__ __device__ inline uint32_t blkA_ccap(uint32_t cslots) { return cslots * 3u / 4u; }
@@ -263,7 +264,7 @@ __host__ __device__ inline uint32_t blkA_ccap(uint32_t cslots) { return cslots *
 __host__ __device__ inline uint32_t blkA_smem_bytes(uint32_t slots, uint32_t cap, uint32_t cslots, uint32_t W) {
   const uint32_t ccap = blkA_ccap(cslots), WS = W | 1u;
   return (uint32_t)sizeof(BlkHead) + slots * 8u + (cap + 1u) * 8u + ccap * 16u + cslots * 4u +
-         (cap + 1u) * WS * 4u + ccap * WS * 4u + slots * 2u + 16u;
+         (cap + 1u) * WS * 4u + ccap * WS * 4u + slots * 2u + ccap * 2u + 16u;
 }
 __device__ __forceinline__ ARunView arun_view(unsigned char* raw, uint32_t slots, uint32_t cap, uint32_t cslots, uint32_t W) {
   ARunView a;
@@ -279,6 +280,7 @@ __device__ __forceinline__ ARunView arun_view(unsigned char* raw, uint32_t slots
   a.pool = a.cstate + cslots;
   a.crows = a.pool + (a.cap + 1u) * WS;
   a.rowid = reinterpret_cast<uint16_t*>(a.crows + a.ccap * WS);
+  a.cmeta = a.rowid + slots;
   a.mask = slots - 1u;
   a.shift = 32u - (uint32_t)__popc(a.mask);
   a.cmask = cslots - 1u;
@@ -287,7 +289,7 @@ __device__ __forceinline__ ARunView arun_view(unsigned char* raw, uint32_t slots
 }
 // chunk id of (hi, lo); 0xffffffff if the chunk table is full (the caller then cuts the run
 // into k-mers itself)
-__device__ __noinline__ uint32_t chunk_find_or_insert(const ARunView a, uint64_t hi, uint64_t lo, uint32_t WS) {
+__device__ __noinline__ uint32_t chunk_find_or_insert(const ARunView a, uint64_t hi, uint64_t lo, uint32_t wofs) {
   const uint64_t m = (hi ^ (hi >> 29)) * 0x9e3779b97f4a7c15ULL + (lo ^ (lo >> 31)) * 0xc2b2ae3d27d4eb4fULL;
   uint32_t s = (uint32_t)(m >> 32) >> a.cshift;
   uint32_t spins = 0;
@@ -309,6 +311,7 @@ __device__ __noinline__ uint32_t chunk_find_or_insert(const ARunView a, uint64_t
           *reinterpret_cast<volatile uint32_t*>(&a.cstate[s]) = kChunkEmpty;
           return 0xffffffffu;
         }
+        a.cmeta[id] = (uint16_t)wofs;
         *reinterpret_cast<volatile uint64_t*>(&a.ckhi[id]) = hi;
         *reinterpret_cast<volatile uint64_t*>(&a.cklo[id]) = lo;
         __threadfence_block();
@@ -443,9 +446,11 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
       lo = (w1 << (2u * o0)) | (w2 >> (64u - 2u * o0));
     }
     uint32_t cs = 0xffffffffu;
-    if (nv == (uint32_t)kBlkRun && !amb) cs = chunk_find_or_insert(a, hi & cm_hi, lo & cm_lo, WS);
+    if (nv == (uint32_t)kBlkRun && !amb) cs = chunk_find_or_insert(a, hi & cm_hi, lo & cm_lo, wofs);
     if (cs != 0xffffffffu) {
       atomicOr(&a.crows[cs * WS + wofs], bit);
+      const uint16_t meta = a.cmeta[cs];            // most chunks are one sample's: remember if not
+      if ((meta & 0xffu) != wofs && !(meta & 0x8000u)) a.cmeta[cs] = meta | 0x8000u;
     } else {
       const uint32_t* ab = amb ? ambbits + raw.w : nullptr;
       for (uint32_t q = 0; q < nv; ++q) {
@@ -471,7 +476,9 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
     const uint32_t cs = p >> 4, q = p & 15u;
     const uint64_t hi = a.ckhi[cs], lo = a.cklo[cs];
     const uint64_t x = q ? ((hi << (2u * q)) | (lo >> (64u - 2u * q))) : hi;
-    put_kmer(x >> sh64, a.crows + cs * WS, 0u, W);
+    const uint16_t meta = a.cmeta[cs];
+    if (meta & 0x8000u) put_kmer(x >> sh64, a.crows + cs * WS, 0u, W);
+    else put_kmer(x >> sh64, a.crows + cs * WS + (meta & 0xffu), meta & 0xffu, 1u);
   }
   __syncthreads();
 
