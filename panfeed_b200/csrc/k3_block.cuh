@@ -60,6 +60,9 @@ constexpr int kBlkRun = 16;                       // windows per task
 #endif
 constexpr int kBlkMinCtas = PF_BLK_MIN_CTAS;      // register budget of kA: 65536 / (256 * n)
 constexpr uint32_t kBlkOverflow = 0xffffffffu;    // slab count of a block that did not fit
+// slab_cnt[p]: popcount of partial row p as kA wrote it; after kB2: kCntDead = folded into an
+// earlier row of the same k-mer, kCntDirty = received another row's bits (recount from the row)
+constexpr uint32_t kCntDead = 0xfffffffeu, kCntDirty = 0xffffffffu;
 
 __global__ void plan_seq_lite(const SeqDev* __restrict__ seqs, uint32_t n, SeqLite* __restrict__ out) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -364,6 +367,7 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
                    const SeqLite* __restrict__ seqs, BlkPlan plan, int k,
                    uint64_t* __restrict__ slab_keys, uint32_t* __restrict__ slab_rows,
                    uint32_t* __restrict__ slab_base, uint32_t* __restrict__ slab_count,
+                   uint32_t* __restrict__ slab_cnt /* popcount of every partial row */,
                    uint32_t partial_capacity, uint32_t* __restrict__ counters,
                    const uint32_t* __restrict__ item_list /* null: item = blockIdx.x */,
                    uint32_t* __restrict__ rescue_items /* out: items whose table overflowed */) {
@@ -513,6 +517,7 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
     slab_keys[base + r] = a.rkey[r];
     const uint32_t* src = a.pool + r * WS;
     uint4* dst = reinterpret_cast<uint4*>(slab_rows + (base + r) * WP);
+    uint32_t cnt = 0;
     for (uint32_t q = 0; q < WP; q += 4) {
       uint4 x;
       x.x = src[q];
@@ -520,7 +525,9 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
       x.z = q + 2 < W ? src[q + 2] : 0u;
       x.w = q + 3 < W ? src[q + 3] : 0u;
       dst[q >> 2] = x;
+      cnt += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
     }
+    slab_cnt[base + r] = cnt;
   }
 }
 
@@ -613,8 +620,9 @@ kB1_insert(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ 
 // kB2: one thread per partial row; a row that does not own its slot ORs its bitset into the
 // owner's and is marked dead (counted: distinct k-mers = partial rows - dead rows)
 __global__ void __launch_bounds__(256)
-kB2_fold(uint32_t n_partials, uint32_t* __restrict__ pslot, const MergeEntry* __restrict__ table,
-         uint32_t* __restrict__ slab_rows, uint32_t WP, uint32_t* __restrict__ counters) {
+kB2_fold(uint32_t n_partials, const uint32_t* __restrict__ pslot, const MergeEntry* __restrict__ table,
+         uint32_t* __restrict__ slab_rows, uint32_t* __restrict__ slab_cnt, uint32_t WP,
+         uint32_t* __restrict__ counters) {
   const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_partials) return;
   const uint32_t o = table[pslot[p]].owner;
@@ -625,7 +633,8 @@ kB2_fold(uint32_t n_partials, uint32_t* __restrict__ pslot, const MergeEntry* __
     const uint32_t x = src[w];
     if (x) atomicOr(dst + w, x);
   }
-  pslot[p] = 0xffffffffu;
+  slab_cnt[p] = kCntDead;
+  slab_cnt[o] = kCntDirty;
   atomicAdd(&counters[LC_RESCUE], 1u);      // (the rescue counter is free again after kA)
 }
 
@@ -635,7 +644,7 @@ __global__ void __launch_bounds__(256)
 kB3_emit(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_rows,
          const uint32_t* __restrict__ slab_base, const uint32_t* __restrict__ slab_count,
          const uint32_t* __restrict__ item_cluster, uint32_t n_items,
-         const uint32_t* __restrict__ pslot, const ClusterDev* __restrict__ clusters, RowOut out,
+         const uint32_t* __restrict__ slab_cnt, const ClusterDev* __restrict__ clusters, RowOut out,
          uint32_t row_capacity, uint32_t* __restrict__ counters, uint32_t W, uint32_t WP) {
   __shared__ uint32_t w_pass[8];
   __shared__ uint32_t cta_base, cta_ok;
@@ -652,9 +661,10 @@ kB3_emit(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ sl
   if (n) cl = clusters[c];
   auto row_of = [&](uint32_t i) { return reinterpret_cast<const uint4*>(slab_rows + (size_t)(base + i) * WP); };
   auto count_of = [&](uint32_t i, bool& owner) {
-    owner = i < n && pslot[base + i] != 0xffffffffu;
-    uint32_t cnt = 0;
-    if (owner) {
+    uint32_t cnt = i < n ? slab_cnt[base + i] : kCntDead;
+    owner = cnt != kCntDead;
+    if (cnt == kCntDirty) {                    // another row of the k-mer was folded in: recount
+      cnt = 0;
       const uint4* row = row_of(i);
       for (uint32_t q = 0; q < WP / 4; ++q) {
         const uint4 x = row[q];
@@ -747,7 +757,7 @@ __global__ void __launch_bounds__(256)
 kB4_link(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_rows,
          const uint32_t* __restrict__ slab_base, const uint32_t* __restrict__ slab_count,
          const uint32_t* __restrict__ item_cluster, uint32_t n_items, uint32_t n_slices,
-         const uint32_t* __restrict__ pslot, const uint32_t* __restrict__ table2_base /* CTAs of 256 slots */,
+         const uint32_t* __restrict__ slab_cnt, const uint32_t* __restrict__ table2_base /* CTAs of 256 slots */,
          LinkEntry* __restrict__ table2, uint32_t* __restrict__ next, uint32_t WP) {
   const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (item >= n_items) return;
@@ -758,12 +768,15 @@ kB4_link(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ sl
   const uint32_t base = slab_base[item];
   for (uint32_t i = lane_id(); i < n; i += 32) {
     const uint32_t p = base + i;
-    if (pslot[p] == 0xffffffffu) continue;                 // folded into an earlier row of its slice
-    const uint4* row = reinterpret_cast<const uint4*>(slab_rows + (size_t)p * WP);
-    uint32_t cnt = 0;
-    for (uint32_t q = 0; q < WP / 4; ++q) {
-      const uint4 x = row[q];
-      cnt += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+    uint32_t cnt = slab_cnt[p];
+    if (cnt == kCntDead) continue;                          // folded into an earlier row of its slice
+    if (cnt == kCntDirty) {
+      const uint4* row = reinterpret_cast<const uint4*>(slab_rows + (size_t)p * WP);
+      cnt = 0;
+      for (uint32_t q = 0; q < WP / 4; ++q) {
+        const uint4 x = row[q];
+        cnt += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+      }
     }
     const uint64_t key = slab_keys[p];
     uint32_t s = __umulhi((uint32_t)(mix64(key) >> 32), ts);

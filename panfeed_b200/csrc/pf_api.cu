@@ -204,7 +204,7 @@ struct pf_ctx : BatchState {
   bool used_block = false;       // the last batch went through kA/kB
   DevBuf d_slab_base, d_slab_count, d_slab_keys, d_slab_rows,
       d_group_base /* merge-table offsets per (cluster, slice) */, d_mtable, d_pslot,
-      d_table2_base, d_table2, d_next, d_pslice, d_cta_cluster, d_rescue[2];
+      d_table2_base, d_table2, d_next, d_pslice, d_cta_cluster, d_slab_cnt, d_rescue[2];
   PatternSpace kp, cp;     // k-mer patterns, cluster patterns
   // pinned results
   PinBuf r_row_cluster, r_row_kmer, r_wrow_kmer, r_row_count, r_row_pattern, r_cl_pattern;
@@ -518,7 +518,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->d_cl_rep, &ctx->d_cl_slot, &ctx->d_cl_winner, &ctx->d_digests, &ctx->d_slab_base,
                     &ctx->d_slab_count, &ctx->d_slab_keys, &ctx->d_slab_rows, &ctx->d_group_base, &ctx->d_mtable,
                     &ctx->d_pslot, &ctx->d_rescue[0], &ctx->d_rescue[1], &ctx->d_table2_base, &ctx->d_table2,
-                    &ctx->d_next, &ctx->d_pslice, &ctx->d_cta_cluster})
+                    &ctx->d_next, &ctx->d_pslice, &ctx->d_cta_cluster, &ctx->d_slab_cnt})
     fd(*b);
   for (PatternSpace* s : {&ctx->kp, &ctx->cp})
     for (DevBuf* b : {&s->pool, &s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique,
@@ -1316,7 +1316,8 @@ int launch_block_aggregate(pf_ctx* ctx, const uint32_t* items, uint32_t n, uint3
   kA_block_aggregate<CANON><<<n, kBlkThreads, smem, st>>>(                                             \
       ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), ctx->d_seq_lite.as<SeqLite>(), bp,   \
       (int)ctx->prm.k, ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),               \
-      ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(), cap32, counters, items,       \
+      ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(), ctx->d_slab_cnt.as<uint32_t>(), \
+      cap32, counters, items,                                                                          \
       rescue_out)
   if (ctx->prm.canonical) PF_KA(true); else PF_KA(false);
 #undef PF_KA
@@ -1358,13 +1359,13 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
                                  ctx->d_pslot.as<uint32_t>(), ns > 1 ? ctx->d_pslice.as<uint16_t>() : nullptr);
   CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));     // kB2 counts the folded rows there
   kB2_fold<<<cdiv(n_partials, 256), 256, 0, st>>>(n_partials, ctx->d_pslot.as<uint32_t>(),
-                                                  ctx->d_mtable.as<MergeEntry>(), ctx->d_slab_rows.as<uint32_t>(), WP,
-                                                  counters + C_LOCAL);
+                                                  ctx->d_mtable.as<MergeEntry>(), ctx->d_slab_rows.as<uint32_t>(),
+                                                  ctx->d_slab_cnt.as<uint32_t>(), WP, counters + C_LOCAL);
   const uint32_t cap = (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu);
   if (ns == 1) {
     kB3_emit<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
                                  ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(),
-                                 ctx->d_item_cluster.as<uint32_t>(), ctx->n_items, ctx->d_pslot.as<uint32_t>(),
+                                 ctx->d_item_cluster.as<uint32_t>(), ctx->n_items, ctx->d_slab_cnt.as<uint32_t>(),
                                  ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL, ctx->W, WP);
     ctx->launches += 3;
     CU(cudaGetLastError());
@@ -1382,7 +1383,7 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
                                                                   ctx->d_cta_cluster.as<uint32_t>());
   kB4_link<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
                                ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(),
-                               ctx->d_item_cluster.as<uint32_t>(), n_it, ns, ctx->d_pslot.as<uint32_t>(),
+                               ctx->d_item_cluster.as<uint32_t>(), n_it, ns, ctx->d_slab_cnt.as<uint32_t>(),
                                ctx->d_table2_base.as<uint32_t>(), ctx->d_table2.as<LinkEntry>(),
                                ctx->d_next.as<uint32_t>(), WP);
   // grid of kB5 = CTAs of all cross-slice tables: one small read-back
@@ -1494,6 +1495,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
       TRY(dev_ensure(ctx, ctx->d_rescue[0], std::max<size_t>(1, n_ka_items) * 4));
       TRY(dev_ensure(ctx, ctx->d_rescue[1], std::max<size_t>(1, n_ka_items) * 4));
       TRY(dev_ensure(ctx, ctx->d_slab_keys, ctx->partial_cap * 8));
+      TRY(dev_ensure(ctx, ctx->d_slab_cnt, ctx->partial_cap * 4));
       TRY(dev_ensure(ctx, ctx->d_slab_rows, ctx->partial_cap * WP * 4));
       CU(cudaMemsetAsync(counters + C_LOCAL, 0, LC_COUNT * 4, st));
       TRY(launch_block_aggregate(ctx, nullptr, n_ka_items, ctx->blk_slots, ctx->blk_cap, ctx->blk_cslots,
