@@ -2344,31 +2344,39 @@ extern "C" int pf_synth_fill(int device, const pf_synth_params* p, pf_seq_desc* 
 // ---------------------------------------------------------------------------
 namespace pf {
 
-// owner of every local pattern + its position inside the owner's bucket
+// owner of every local pattern + its position inside the owner's bucket.  L lanes hash one
+// key (as in K4: short keys would leave most of a warp idle), a warp handles 32 consecutive
+// patterns and hands out their bucket positions with ONE atomic per distinct owner — a counter
+// per rank shared by millions of patterns would serialise in L2.
+template <int L>
 __global__ void __launch_bounds__(256)
 x_classify(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
            const uint32_t* __restrict__ mask_remap, uint32_t world, uint32_t* __restrict__ owner,
            uint32_t* __restrict__ pos, uint32_t* __restrict__ counts) {
-  const uint32_t lane = lane_id();
+  const uint32_t lane = lane_id(), gl = lane & (L - 1), g = lane / L;
+  constexpr uint32_t G = 32 / L;                   // patterns hashed at once by a warp
   const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
-  // a warp takes 32 consecutive patterns: it hashes them one after the other (all lanes on one
-  // key), then hands out their bucket positions with ONE atomic per distinct owner — a counter
-  // per rank shared by millions of patterns would serialise in L2
   for (uint32_t e0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; e0 < n; e0 += total_warps * 32u) {
     uint32_t my_owner = 0xffffffffu;
     const uint32_t cnt = min(32u, n - e0);
-    for (uint32_t p = 0; p < cnt; ++p) {
-      const uint32_t* key = pool + (size_t)(e0 + p) * key_words;
+    for (uint32_t p0 = 0; p0 < 32u; p0 += G) {     // (uniform trip count: the shuffles need all lanes)
+      const uint32_t p = p0 + g;
       uint64_t h = 0;
-      for (uint32_t w = lane; w < key_words; w += 32) {
-        uint32_t v = key[w];
-        if (mask_remap && w == key_words - 1) v = mask_remap[v];
-        h += word_hash(v, w);
+      if (p < cnt) {
+        const uint32_t* key = pool + (size_t)(e0 + p) * key_words;
+        for (uint32_t w = gl; w < key_words; w += L) {
+          uint32_t v = key[w];
+          if (mask_remap && w == key_words - 1) v = mask_remap[v];
+          h += word_hash(v, w);
+        }
       }
 #pragma unroll
-      for (int m = 16; m >= 1; m >>= 1) h += __shfl_xor_sync(kFull, h, m);
+      for (int m = L / 2; m >= 1; m >>= 1) h += __shfl_xor_sync(kFull, h, m);
       h = fmix64(h);
-      if (lane == p) my_owner = (uint32_t)((h >> 32) % world);
+      const uint32_t o = (uint32_t)((h >> 32) % world);
+      // lane p of the warp keeps pattern p's owner: it sits in group p - p0, any lane of it
+      const uint32_t got = __shfl_sync(kFull, o, (lane - p0) * L);
+      if (lane >= p0 && lane < p0 + G && lane < cnt) my_owner = got;
     }
     const uint32_t m = __match_any_sync(kFull, my_owner);
     if (lane < cnt) {
@@ -2382,41 +2390,51 @@ x_classify(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
   }
 }
 
+// exclusive offsets of the `world` buckets behind the counts (counts[world .. 2 world))
+__global__ void x_offsets(uint32_t* __restrict__ counts, uint32_t world) {
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (uint32_t r = 0; r < world; ++r) { counts[world + r] = run; run += counts[r]; }
+  }
+}
+
+template <int L>
 __global__ void __launch_bounds__(256)
 x_pack(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
        const uint32_t* __restrict__ mask_remap, const uint32_t* __restrict__ owner,
        const uint32_t* __restrict__ pos, const uint32_t* __restrict__ offsets,
        uint32_t* __restrict__ send, uint32_t* __restrict__ perm) {
-  const uint32_t lane = lane_id();
-  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += total_warps) {
+  const uint32_t gl = lane_id() & (L - 1);
+  const uint32_t total = gridDim.x * (blockDim.x / L);
+  for (uint32_t e = blockIdx.x * (blockDim.x / L) + threadIdx.x / L; e < n; e += total) {
     const uint32_t dst = offsets[owner[e]] + pos[e];
     const uint32_t* key = pool + (size_t)e * key_words;
     uint32_t* out = send + (size_t)dst * key_words;
-    for (uint32_t w = lane; w < key_words; w += 32) {
+    for (uint32_t w = gl; w < key_words; w += L) {
       uint32_t v = key[w];
       if (mask_remap && w == key_words - 1) v = mask_remap[v];
       out[w] = v;
     }
-    if (lane == 0) perm[e] = dst;
+    if (gl == 0) perm[e] = dst;
   }
 }
 
 // unique index of every received key + compacted unique keys
+template <int L>
 __global__ void __launch_bounds__(256)
 x_finish(const uint32_t* __restrict__ recv, uint32_t n, uint32_t key_words,
          const uint32_t* __restrict__ rep, const uint32_t* __restrict__ winner_rank,
          uint32_t* __restrict__ unique_index, uint32_t* __restrict__ unique_keys) {
-  const uint32_t lane = lane_id();
-  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
-  for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += total_warps) {
+  const uint32_t gl = lane_id() & (L - 1);
+  const uint32_t total = gridDim.x * (blockDim.x / L);
+  for (uint32_t e = blockIdx.x * (blockDim.x / L) + threadIdx.x / L; e < n; e += total) {
     const uint32_t q = rep[e] & ~kTentative;         // every rep is tentative here (empty pool)
     const uint32_t u = winner_rank[q];
-    if (lane == 0) unique_index[e] = u;
+    if (gl == 0) unique_index[e] = u;
     if (q == e) {
       const uint32_t* src = recv + (size_t)e * key_words;
       uint32_t* dst = unique_keys + (size_t)u * key_words;
-      for (uint32_t w = lane; w < key_words; w += 32) dst[w] = src[w];
+      for (uint32_t w = gl; w < key_words; w += L) dst[w] = src[w];
     }
   }
 }
@@ -2446,26 +2464,33 @@ extern "C" int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t wor
   TRY(dev_ensure(ctx, s.x_perm, std::max<size_t>(1, n) * 4));
   TRY(dev_ensure(ctx, s.x_counts, (size_t)world * 2 * 4));
   CU(cudaMemsetAsync(s.x_counts.p, 0, (size_t)world * 2 * 4, st));
-  std::vector<uint32_t> counts(world, 0), offsets(world, 0);
+  std::vector<uint32_t> counts(world, 0);
   if (n) {
     if (!send_words_dev) return fail(ctx, PF_ERR_INVALID, "null send buffer");
-    const uint32_t grid = std::min<uint32_t>(cdiv(n, 8), kGridPersist);
-    x_classify<<<grid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev, world,
-                                     s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(), s.x_counts.as<uint32_t>());
     if (world > 32) return fail(ctx, PF_ERR_UNSUPPORTED, "exchange over more than 32 ranks");
     TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 32 * 4));
     uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;
+    const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
+    const uint32_t cgrid = std::min<uint32_t>(cdiv(n, 256), kGridPersist * 2);
+    const uint32_t pgrid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
+#define PF_XC(LL)                                                                                          \
+    do {                                                                                                   \
+      x_classify<LL><<<cgrid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev, world,  \
+                                            s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(),              \
+                                            s.x_counts.as<uint32_t>());                                    \
+      x_offsets<<<1, 32, 0, st>>>(s.x_counts.as<uint32_t>(), world);                                       \
+      x_pack<LL><<<pgrid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev,             \
+                                        s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(),                  \
+                                        s.x_counts.as<uint32_t>() + world, send_words_dev,                 \
+                                        s.x_perm.as<uint32_t>());                                          \
+    } while (0)
+    if (L == 4) PF_XC(4); else if (L == 8) PF_XC(8); else if (L == 16) PF_XC(16); else PF_XC(32);
+#undef PF_XC
     mirror_counters<<<1, 32, 0, st>>>(hx, s.x_counts.as<uint32_t>(), world);
-    CU(cudaStreamSynchronize(st));
-    for (uint32_t r = 0; r < world; ++r) counts[r] = hx[r];
-    for (uint32_t r = 1; r < world; ++r) offsets[r] = offsets[r - 1] + counts[r - 1];
-    CU(cudaMemcpyAsync(s.x_counts.as<uint32_t>() + world, offsets.data(), world * 4, cudaMemcpyHostToDevice, st));
-    x_pack<<<grid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev, s.x_owner.as<uint32_t>(),
-                                 s.x_pos.as<uint32_t>(), s.x_counts.as<uint32_t>() + world, send_words_dev,
-                                 s.x_perm.as<uint32_t>());
-    ctx->launches += 2;
-    CU(cudaStreamSynchronize(st));
+    ctx->launches += 3;
+    CU(cudaStreamSynchronize(st));           // the only sync: bucket sizes for the caller's all-to-all
     CU(cudaGetLastError());
+    for (uint32_t r = 0; r < world; ++r) counts[r] = hx[r];
   }
   for (uint32_t r = 0; r < world; ++r) counts_host[r] = counts[r];
   return PF_OK;
@@ -2509,8 +2534,15 @@ extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint3
 #undef PF_XP
   }
   TRY(scan_inplace(ctx, winner.as<uint32_t>(), n, counters + C_NEW_KP));
-  x_finish<<<grid, 256, 0, st>>>(recv_words_dev, n, s.key_words, rep.as<uint32_t>(), winner.as<uint32_t>(),
-                                 recv_unique_index_dev, s.x_unique.as<uint32_t>());
+  {
+    const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
+    const uint32_t fgrid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
+#define PF_XF(LL)                                                                                          \
+    x_finish<LL><<<fgrid, 256, 0, st>>>(recv_words_dev, n, s.key_words, rep.as<uint32_t>(), winner.as<uint32_t>(), \
+                                        recv_unique_index_dev, s.x_unique.as<uint32_t>())
+    if (L == 4) PF_XF(4); else if (L == 8) PF_XF(8); else if (L == 16) PF_XF(16); else PF_XF(32);
+#undef PF_XF
+  }
   ctx->launches += 2;
   TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 32 * 4));
   uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;

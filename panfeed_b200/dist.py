@@ -121,7 +121,7 @@ class PatternExchange:
         nu = torch.tensor([n_unique], dtype=torch.int64, device=dev)
         all_nu = [torch.empty_like(nu) for _ in range(world)]
         dist.all_gather(all_nu, nu, group=self.group)
-        counts = [int(x.item()) for x in all_nu]
+        counts = [int(x) for x in torch.cat(all_nu).tolist()]      # one read-back, not one per rank
         base = sum(counts[:self.rank])
         uniq_idx += base
         returned = torch.empty(n_local, dtype=torch.int32, device=dev)
