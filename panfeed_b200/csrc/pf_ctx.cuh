@@ -1,0 +1,288 @@
+// pf_ctx.cuh — context and batch state, device-side planning kernels, error / buffer helpers.
+// Part of libpanfeed_b200.so's single translation unit: included once, in order, by pf_api.cu.
+
+namespace pf {
+// ---- planning helpers that run on the device (tile lists are pure functions of the
+//      per-cluster record ranges; generating them there saves host loops and H2D) -------
+__global__ void plan_expand_tiles(const ClusterDev* __restrict__ clusters, uint32_t n_clusters,
+                                  const uint32_t* __restrict__ tile_base, uint32_t tile_size, int wide,
+                                  TileDev* __restrict__ tiles) {
+  const uint32_t c = blockIdx.x;
+  if (c >= n_clusters) return;
+  const uint32_t lo = wide ? clusters[c].wrec_start : clusters[c].rec_start;
+  const uint32_t hi = wide ? clusters[c].wrec_end : clusters[c].rec_end;
+  const uint32_t first = tile_base[c];
+  const uint32_t n = (hi - lo + tile_size - 1) / tile_size;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    TileDev t;
+    t.start = lo + i * tile_size;
+    t.count = min(tile_size, hi - t.start);
+    t.seg = c;
+    t.first_tile = first;
+    tiles[first + i] = t;
+  }
+}
+__global__ void plan_seq_rec_off(const SeqDev* __restrict__ seqs, uint32_t n_seqs, uint32_t total,
+                                 uint32_t* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_seqs) out[i] = seqs[i].rec_off;
+  else if (i == n_seqs) out[i] = total;
+}
+// Counter read-back without a copy engine: the D2H engine may be busy with the previous
+// batch's rows, and a 64-byte memcpy queued behind them would stall the pipeline's host side.
+// `dst` is pinned host memory (device-accessible under UVA).
+__global__ void mirror_counters(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t n) {
+  if (threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+// pipelined submit: positional records of a sub-batch index its own sequences / wide k-mers
+__global__ void pos_rebase(uint32_t* __restrict__ pos_seq, uint64_t* __restrict__ pos_kmer,
+                           const uint8_t* __restrict__ pos_flags, uint32_t n, uint32_t seq_base,
+                           uint64_t wide_base) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  pos_seq[i] += seq_base;
+  if (wide_base && (pos_flags[i] & 2u)) pos_kmer[i] += wide_base;
+}
+// sequence holding the first record of every tile (last s with rec_off[s] <= start, non-empty)
+__global__ void plan_tile_first_seq(const TileDev* __restrict__ tiles, uint32_t n_tiles,
+                                    const uint32_t* __restrict__ seq_rec_off, uint32_t n_seqs,
+                                    uint32_t* __restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > n_tiles) return;
+  if (t == n_tiles) { out[t] = n_seqs ? n_seqs - 1 : 0; return; }
+  const uint32_t r = tiles[t].start;
+  uint32_t lo = 0, hi = n_seqs;                   // first index in [0, n_seqs] with rec_off > r
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (seq_rec_off[mid] <= r) lo = mid + 1; else hi = mid;
+  }
+  out[t] = lo ? lo - 1 : 0;
+}
+}  // namespace pf
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PatternSpace {
+  uint32_t key_words = 0;
+  DevBuf pool;            // n x key_words
+  uint64_t n = 0;         // committed patterns
+  DevBuf table;           // table_size x u32
+  uint32_t table_size = 0;
+  // exchange state
+  DevBuf x_owner, x_pos, x_perm, x_counts, x_unique, x_table, x_rep, x_slot, x_winner;
+  uint64_t x_n_unique = 0;
+};
+
+struct WidthState {       // per key width (narrow u64 / wide Key128)
+  DevBuf keys[2], vals[2];
+  DevBuf tiles, seg_start, seg_hist, lookback, cursors;
+  DevBuf ltiles, tile_first_run;     // partition mode: 2048-record tiles of the local reduce
+  PinBuf h_tiles, h_seg_start, h_ltiles;       // h_tiles / h_ltiles now hold per-cluster tile bases
+  DevBuf d_tile_base, d_ltile_base;
+  uint32_t n_tiles = 0, n_ltiles = 0, max_seg = 0;
+  uint32_t n_records = 0;
+  uint32_t n_runs = 0;
+  uint32_t n_rows = 0;
+  int sort_bits = 0, passes = 0;
+  int final_buf = 0;      // which of keys[]/vals[] holds the sorted records
+};
+
+enum Ev { EV_START, EV_EXTRACT, EV_HIST, EV_SORT, EV_MARK, EV_COUNTED, EV_REDUCE, EV_DEDUP, EV_END, EV_COUNT };
+
+}  // namespace
+
+// Everything that belongs to ONE batch of whole clusters: what pf_upload builds, the record /
+// row buffers of that batch and its result arrays on the device.  A context holds two of these
+// so that the upload of sub-batch j+1 and the D2H of sub-batch j-1 can overlap the kernels of
+// sub-batch j (pf_submit on a large batch; see submit_pipelined).
+struct BatchState {
+  bool have_batch = false, executed = false;
+  uint32_t n_seqs = 0, n_clusters = 0, n_wide_seqs = 0;
+  uint64_t n_words = 0, n_amb_words = 0, n_bases = 0;
+  uint32_t n_pos = 0, n_pos_wide = 0;
+  PinBuf h_seqs, h_clusters, h_wide_seqs;
+  DevBuf d_bases, d_amb, d_ambbits, d_seqs, d_clusters, d_wide_seqs, d_presence;
+  WidthState nar, wid;
+  // rows (narrow first, then wide)
+  DevBuf d_row_cluster, d_row_kmer, d_wrow_kmer, d_row_count, d_row_pattern;
+  DevBuf d_cl_pattern;
+  DevBuf d_pos_kmer, d_pos_seq, d_pos_cstart, d_pos_gstart, d_pos_flags, d_pos_wide;
+  DevBuf d_seq_rec_off, d_tile_first_seq;
+  PinBuf h_seq_rec_off, h_tile_first_seq;
+  std::vector<std::pair<uint32_t, uint32_t>> nar_ranges;   // narrow record range of every cluster
+  uint32_t n_items = 0;          // (cluster, block) work items of the batch (block aggregation)
+  DevBuf d_seq_lite, d_cblk, d_item_base, d_item_cluster, d_plan_total, d_bsum_slot, d_slice_seq, d_item_desc;
+  PinBuf h_plan;
+  uint64_t kp_base = 0, cp_base = 0;   // pool sizes before the batch
+  bool rows_prefetched = false;
+  uint64_t row_cap = 0;          // capacity of the row arrays above
+  cudaEvent_t ev[EV_COUNT]{};    // stage timestamps of the batch's pf_execute
+  PinBuf h_done;                 // pinned mirror of the batch's new k-mer pattern count (K4)
+};
+
+struct pf_ctx : BatchState {
+  pf_params prm{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // D2H of finished row arrays while K4 still runs
+  cudaStream_t up_stream = nullptr;     // H2D of the next sub-batch while the current one computes
+  cudaEvent_t ev_rows = nullptr;
+  std::string err;
+  uint32_t W = 0, Wk = 0;
+  std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> maf_cache;
+  std::mutex maf_mu;       // the upload helper thread of the pipelined submit shares the cache
+
+  BatchState alt;          // the other batch slot (pipelined submit)
+  DevBuf d_counters;       // u32[C_COUNT]: tickets, n_runs, errors, totals
+  PinBuf h_counters;
+  DevBuf d_bsum;
+  DevBuf d_cand;
+  DevBuf d_rep, d_slot_of, d_winner;
+  DevBuf d_cl_rep, d_cl_slot, d_cl_winner;
+  bool partition = true;   // mode 0: few radix passes + shared-memory hash grouping (k3_local)
+  bool use_direct = true;  // S <= 1024: bitsets for every distinct key in shared memory
+  bool runs_from_hist = false;   // one pass: prefix-runs are the digit buckets of the histogram
+  uint32_t local_tile = 0;       // records per tile of the local reduce (4096 direct / 2048 general)
+  bool fused = false;            // K1 fused into the histogram and the first pass (no record write in K1)
+  DevBuf d_digests;
+  int extra_bits = 0;      // sort bits added after a table overflow (sticky)
+  double row_ratio = 1.0 / 48;   // surviving rows per record, learned from earlier batches
+  uint64_t unique_last = 0;
+  uint32_t rescued_last = 0;
+  // block aggregation (k3_block.cuh): no records, partial (k-mer, bitset) rows per position block
+  bool block_mode = false;       // S <= 1024 and not disabled: kA_block_aggregate + kB1..kB3
+  uint32_t block_windows = 16;   // windows per position block (= kBlkRun)
+  uint32_t blk_slots = 1024, blk_cap = 448, blk_cslots = 128;   // shared memory of kA: k-mer key slots / rows, chunk slots
+  uint32_t n_slices = 1, slice_samples = 0, Ws = 0;   // sample slices of the block engine (S > 1024): slices,
+                                                       // samples per slice, bitset words of a partial row
+  uint32_t block_fallbacks = 0;
+  double partial_ratio = 1.0 / 16;   // partial rows per window, learned from earlier batches
+  uint64_t partial_cap = 0;
+  uint64_t partials_last = 0;
+  bool used_block = false;       // the last batch went through kA/kB
+  DevBuf d_slab_base, d_slab_count, d_slab_keys, d_slab_rows,
+      d_group_base /* merge-table offsets per (cluster, slice) */, d_mtable, d_pslot,
+      d_table2_base, d_table2, d_next, d_pslice, d_cta_cluster, d_slab_cnt, d_rescue[2];
+  PatternSpace kp, cp;     // k-mer patterns, cluster patterns
+  // pinned results
+  PinBuf r_row_cluster, r_row_kmer, r_wrow_kmer, r_row_count, r_row_pattern, r_cl_pattern;
+  PinBuf r_new_kp, r_new_cp, r_pos_kmer, r_pos_seq, r_pos_cstart, r_pos_gstart, r_pos_flags,
+      r_pos_wide;
+  PinBuf r_wrow_cluster, r_wrow_count, r_wrow_pattern;   // pipelined submit: wide rows apart
+  cudaEvent_t ev_h2d[2]{}, ev_d2h[2]{};
+  pf_stats stats{};
+  // the k-mer pattern count of the last pf_execute is folded into kp.n lazily (its K4 may still run)
+  bool kp_pending = false;
+  uint64_t kp_pending_base = 0;
+  const uint32_t* kp_pending_count = nullptr;
+  std::atomic<uint32_t> launches{0};
+  // pipelined submit (submit_pipelined / collect_pipelined)
+  bool prefetch_rows = false;    // start the D2H of the row arrays under K4 (PF_PREFETCH_ROWS=1): off by
+                                 // default, the copy engine it occupies delays every small read-back that
+                                 // follows (multi-GPU exchange), and large submits are pipelined anyway
+  bool pipe_pending = false;     // results of a pipelined submit wait for pf_collect
+  uint32_t pipe_subs = 1;        // sub-batches of the last submit
+  bool pipe_mode = false;        // inside submit_pipelined: pf_execute leaves the D2H to it
+  double pipe_ms[10] = {0};      // stage times summed over the sub-batches
+  uint64_t pipe_rows = 0, pipe_wide_rows = 0, pipe_pos = 0, pipe_pos_wide = 0;
+  uint32_t pipe_clusters = 0;
+  uint64_t pipe_kp_base = 0, pipe_cp_base = 0, pipe_kp_copied = 0;
+  uint64_t pipe_row_cap = 0, pipe_wide_cap = 0;
+  cudaEvent_t ev_up[2]{}, ev_exec_end[2]{}, ev_out_done[2]{}, ev_pipe[2]{};
+  uint32_t pipe_min_seqs = 200000;   // batches with fewer sequences are not split
+  uint32_t pipe_target_seqs = 262144;   // sequences per sub-batch
+};
+
+namespace {
+
+int fail(pf_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess)                                                             \
+      return fail(ctx, PF_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                  __FILE__, __LINE__);                                                 \
+  } while (0)
+
+int dev_ensure(pf_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false) {
+  if (bytes <= b.cap) return PF_OK;
+  size_t want = std::max(bytes, b.cap + b.cap / 2);
+  want = (want + 255) & ~size_t(255);
+  void* np = nullptr;
+  CU(cudaMalloc(&np, want));
+  if (keep && b.p && b.cap) {
+    CU(cudaMemcpyAsync(np, b.p, b.cap, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  if (b.p) CU(cudaFree(b.p));
+  b.p = np;
+  b.cap = want;
+  return PF_OK;
+}
+int pin_ensure(pf_ctx* ctx, PinBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return PF_OK;
+  size_t want = std::max(bytes, b.cap + b.cap / 2);
+  want = (want + 4095) & ~size_t(4095);
+  if (b.p) CU(cudaFreeHost(b.p));
+  b.p = nullptr; b.cap = 0;
+  CU(cudaMallocHost(&b.p, want));
+  b.cap = want;
+  return PF_OK;
+}
+#define TRY(x) do { int r_ = (x); if (r_ != PF_OK) return r_; } while (0)
+
+// PF_DEBUG_SYNC=1: synchronise after every stage so a device fault names its kernel.
+bool debug_sync(const char* name) {
+  static const char* v = getenv("PF_DEBUG_SYNC");
+  return v && (v[0] == '1' || strstr(name, v) != nullptr);
+}
+#define STAGE(name)                                                                      \
+  do {                                                                                   \
+    if (debug_sync(name)) {                                                                  \
+      cudaError_t e_ = cudaStreamSynchronize(ctx->stream);                               \
+      if (e_ != cudaSuccess)                                                             \
+        return fail(ctx, PF_ERR_CUDA, "stage %s: %s", name, cudaGetErrorString(e_));     \
+    }                                                                                    \
+  } while (0)
+
+inline uint32_t cdiv(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+constexpr int kGridPersist = 148 * 4;
+constexpr uint32_t kBlkMaxSmem = 220u * 1024u;   // largest kA table we ask for
+
+// counters layout in d_counters
+enum { C_TICKET_N = 0, C_TICKET_W = 1, C_RUNS_N = 2, C_RUNS_W = 3, C_ERR = 4, C_ROWS_N = 5,
+       C_ROWS_W = 6, C_NEW_KP = 7, C_NEW_CP = 8, C_TICKET_MARK_N = 9, C_TICKET_MARK_W = 10,
+       C_LOCAL = 11 /* LC_COUNT words: rows, unique, table overflow, row overflow, rescue runs,
+                        partial rows, partial overflow */, C_TICKET_MERGE = 18, C_COUNT = 24 };
+static_assert(C_LOCAL + LC_COUNT <= C_TICKET_MERGE, "counter layout");
+
+bool keep_count(double maf, uint32_t c, uint32_t n) {
+  double af = (double)c / (double)n;      // numpy: vec.sum() / vec.shape[0]
+  if (af >= 0.5) af = 1 - af;
+  return !(af < maf);
+}
+
+}  // namespace

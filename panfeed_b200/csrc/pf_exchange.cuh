@@ -1,0 +1,243 @@
+// pf_exchange.cuh — multi-GPU pattern exchange kernels and the pf_exchange_* entry points.
+// Part of libpanfeed_b200.so's single translation unit: included once, in order, by pf_api.cu.
+
+// ---------------------------------------------------------------------------
+// multi-GPU exchange
+// ---------------------------------------------------------------------------
+namespace pf {
+
+// owner of every local pattern + its position inside the owner's bucket.  L lanes hash one
+// key (as in K4: short keys would leave most of a warp idle), a warp handles 32 consecutive
+// patterns and hands out their bucket positions with ONE atomic per distinct owner — a counter
+// per rank shared by millions of patterns would serialise in L2.
+template <int L>
+__global__ void __launch_bounds__(256)
+x_classify(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
+           const uint32_t* __restrict__ mask_remap, uint32_t world, uint32_t* __restrict__ owner,
+           uint32_t* __restrict__ pos, uint32_t* __restrict__ counts) {
+  const uint32_t lane = lane_id(), gl = lane & (L - 1), g = lane / L;
+  constexpr uint32_t G = 32 / L;                   // patterns hashed at once by a warp
+  const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+  for (uint32_t e0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u; e0 < n; e0 += total_warps * 32u) {
+    uint32_t my_owner = 0xffffffffu;
+    const uint32_t cnt = min(32u, n - e0);
+    for (uint32_t p0 = 0; p0 < 32u; p0 += G) {     // (uniform trip count: the shuffles need all lanes)
+      const uint32_t p = p0 + g;
+      uint64_t h = 0;
+      if (p < cnt) {
+        const uint32_t* key = pool + (size_t)(e0 + p) * key_words;
+        for (uint32_t w = gl; w < key_words; w += L) {
+          uint32_t v = key[w];
+          if (mask_remap && w == key_words - 1) v = mask_remap[v];
+          h += word_hash(v, w);
+        }
+      }
+#pragma unroll
+      for (int m = L / 2; m >= 1; m >>= 1) h += __shfl_xor_sync(kFull, h, m);
+      h = fmix64(h);
+      const uint32_t o = (uint32_t)((h >> 32) % world);
+      // lane p of the warp keeps pattern p's owner: it sits in group p - p0, any lane of it
+      const uint32_t got = __shfl_sync(kFull, o, (lane - p0) * L);
+      if (lane >= p0 && lane < p0 + G && lane < cnt) my_owner = got;
+    }
+    const uint32_t m = __match_any_sync(kFull, my_owner);
+    if (lane < cnt) {
+      const int leader = __ffs(m) - 1;
+      uint32_t base = 0;
+      if ((int)lane == leader) base = atomicAdd(&counts[my_owner], (uint32_t)__popc(m));
+      base = __shfl_sync(m, base, leader);
+      owner[e0 + lane] = my_owner;
+      pos[e0 + lane] = base + __popc(m & lanemask_lt());
+    }
+  }
+}
+
+// exclusive offsets of the `world` buckets behind the counts (counts[world .. 2 world))
+__global__ void x_offsets(uint32_t* __restrict__ counts, uint32_t world) {
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (uint32_t r = 0; r < world; ++r) { counts[world + r] = run; run += counts[r]; }
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(256)
+x_pack(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
+       const uint32_t* __restrict__ mask_remap, const uint32_t* __restrict__ owner,
+       const uint32_t* __restrict__ pos, const uint32_t* __restrict__ offsets,
+       uint32_t* __restrict__ send, uint32_t* __restrict__ perm) {
+  const uint32_t gl = lane_id() & (L - 1);
+  const uint32_t total = gridDim.x * (blockDim.x / L);
+  for (uint32_t e = blockIdx.x * (blockDim.x / L) + threadIdx.x / L; e < n; e += total) {
+    const uint32_t dst = offsets[owner[e]] + pos[e];
+    const uint32_t* key = pool + (size_t)e * key_words;
+    uint32_t* out = send + (size_t)dst * key_words;
+    for (uint32_t w = gl; w < key_words; w += L) {
+      uint32_t v = key[w];
+      if (mask_remap && w == key_words - 1) v = mask_remap[v];
+      out[w] = v;
+    }
+    if (gl == 0) perm[e] = dst;
+  }
+}
+
+// unique index of every received key + compacted unique keys
+template <int L>
+__global__ void __launch_bounds__(256)
+x_finish(const uint32_t* __restrict__ recv, uint32_t n, uint32_t key_words,
+         const uint32_t* __restrict__ rep, const uint32_t* __restrict__ winner_rank,
+         uint32_t* __restrict__ unique_index, uint32_t* __restrict__ unique_keys) {
+  const uint32_t gl = lane_id() & (L - 1);
+  const uint32_t total = gridDim.x * (blockDim.x / L);
+  for (uint32_t e = blockIdx.x * (blockDim.x / L) + threadIdx.x / L; e < n; e += total) {
+    const uint32_t q = rep[e] & ~kTentative;         // every rep is tentative here (empty pool)
+    const uint32_t u = winner_rank[q];
+    if (gl == 0) unique_index[e] = u;
+    if (q == e) {
+      const uint32_t* src = recv + (size_t)e * key_words;
+      uint32_t* dst = unique_keys + (size_t)u * key_words;
+      for (uint32_t w = gl; w < key_words; w += L) dst[w] = src[w];
+    }
+  }
+}
+
+__global__ void x_unpack(const uint32_t* __restrict__ returned, const uint32_t* __restrict__ perm,
+                         uint32_t n, uint32_t* __restrict__ local_to_global) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) local_to_global[i] = returned[perm[i]];
+}
+
+}  // namespace pf
+
+extern "C" int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t world,
+                                const uint32_t* mask_remap_dev, uint32_t* send_words_dev,
+                                uint64_t capacity_patterns, uint64_t* counts_host) {
+  if (!ctx || !counts_host || world == 0) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  TRY(finalize_pending(ctx));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  cudaStream_t st = ctx->stream;
+  const uint32_t n = (uint32_t)s.n;
+  if (n > capacity_patterns) return fail(ctx, PF_ERR_INVALID, "send buffer too small: %u patterns", n);
+  if (mask_remap_dev && (cluster_namespace || !ctx->prm.consider_missing))
+    return fail(ctx, PF_ERR_INVALID, "mask_remap only applies to k-mer patterns with consider_missing");
+  TRY(dev_ensure(ctx, s.x_owner, std::max<size_t>(1, n) * 4));
+  TRY(dev_ensure(ctx, s.x_pos, std::max<size_t>(1, n) * 4));
+  TRY(dev_ensure(ctx, s.x_perm, std::max<size_t>(1, n) * 4));
+  TRY(dev_ensure(ctx, s.x_counts, (size_t)world * 2 * 4));
+  CU(cudaMemsetAsync(s.x_counts.p, 0, (size_t)world * 2 * 4, st));
+  std::vector<uint32_t> counts(world, 0);
+  if (n) {
+    if (!send_words_dev) return fail(ctx, PF_ERR_INVALID, "null send buffer");
+    if (world > 32) return fail(ctx, PF_ERR_UNSUPPORTED, "exchange over more than 32 ranks");
+    TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 32 * 4));
+    uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;
+    const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
+    const uint32_t cgrid = std::min<uint32_t>(cdiv(n, 256), kGridPersist * 2);
+    const uint32_t pgrid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
+#define PF_XC(LL)                                                                                          \
+    do {                                                                                                   \
+      x_classify<LL><<<cgrid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev, world,  \
+                                            s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(),              \
+                                            s.x_counts.as<uint32_t>());                                    \
+      x_offsets<<<1, 32, 0, st>>>(s.x_counts.as<uint32_t>(), world);                                       \
+      x_pack<LL><<<pgrid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev,             \
+                                        s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(),                  \
+                                        s.x_counts.as<uint32_t>() + world, send_words_dev,                 \
+                                        s.x_perm.as<uint32_t>());                                          \
+    } while (0)
+    if (L == 4) PF_XC(4); else if (L == 8) PF_XC(8); else if (L == 16) PF_XC(16); else PF_XC(32);
+#undef PF_XC
+    mirror_counters<<<1, 32, 0, st>>>(hx, s.x_counts.as<uint32_t>(), world);
+    ctx->launches += 3;
+    CU(cudaStreamSynchronize(st));           // the only sync: bucket sizes for the caller's all-to-all
+    CU(cudaGetLastError());
+    for (uint32_t r = 0; r < world; ++r) counts[r] = hx[r];
+  }
+  for (uint32_t r = 0; r < world; ++r) counts_host[r] = counts[r];
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint32_t* recv_words_dev,
+                                 uint64_t n_recv, uint32_t* recv_unique_index_dev, uint64_t* n_unique_host) {
+  if (!ctx || !n_unique_host) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  cudaStream_t st = ctx->stream;
+  *n_unique_host = 0;
+  s.x_n_unique = 0;
+  if (n_recv == 0) return PF_OK;
+  if (n_recv >= (1ull << 30)) return fail(ctx, PF_ERR_INVALID, "too many received patterns");
+  if (!recv_words_dev || !recv_unique_index_dev) return fail(ctx, PF_ERR_INVALID, "null exchange buffer");
+  const uint32_t n = (uint32_t)n_recv;
+  uint32_t size = 1024;
+  while (size < 2ull * n + 16) size *= 2;
+  DevBuf& table = s.x_table;          // scratch kept across calls: no cudaMalloc in the steady state
+  DevBuf& rep = s.x_rep;
+  DevBuf& slot_of = s.x_slot;
+  DevBuf& winner = s.x_winner;
+  TRY(dev_ensure(ctx, table, (size_t)size * 4));
+  TRY(dev_ensure(ctx, rep, (size_t)n * 4));
+  TRY(dev_ensure(ctx, slot_of, (size_t)n * 4));
+  TRY(dev_ensure(ctx, winner, ((size_t)n + 1) * 4));
+  TRY(dev_ensure(ctx, s.x_unique, (size_t)n * s.key_words * 4));
+  CU(cudaMemsetAsync(table.p, 0xff, (size_t)size * 4, st));
+  uint32_t* counters = ctx->d_counters.p ? ctx->d_counters.as<uint32_t>() : nullptr;
+  if (!counters) { TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4)); TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4)); counters = ctx->d_counters.as<uint32_t>(); }
+  const uint32_t grid = std::min<uint32_t>(cdiv(n, 8), kGridPersist * 2);
+  {
+    // lanes per pattern as in K4: short keys would leave most of a warp idle
+    const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
+    const uint32_t pgrid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
+#define PF_XP(LL)                                                                                          \
+    k4_probe<LL><<<pgrid, 256, 0, st>>>(recv_words_dev, n, s.key_words, nullptr, table.as<uint32_t>(), size - 1, \
+                                        rep.as<uint32_t>(), slot_of.as<uint32_t>(), winner.as<uint32_t>())
+    if (L == 4) PF_XP(4); else if (L == 8) PF_XP(8); else if (L == 16) PF_XP(16); else PF_XP(32);
+#undef PF_XP
+  }
+  TRY(scan_inplace(ctx, winner.as<uint32_t>(), n, counters + C_NEW_KP));
+  {
+    const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
+    const uint32_t fgrid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
+#define PF_XF(LL)                                                                                          \
+    x_finish<LL><<<fgrid, 256, 0, st>>>(recv_words_dev, n, s.key_words, rep.as<uint32_t>(), winner.as<uint32_t>(), \
+                                        recv_unique_index_dev, s.x_unique.as<uint32_t>())
+    if (L == 4) PF_XF(4); else if (L == 8) PF_XF(8); else if (L == 16) PF_XF(16); else PF_XF(32);
+#undef PF_XF
+  }
+  ctx->launches += 2;
+  TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 32 * 4));
+  uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;
+  mirror_counters<<<1, 32, 0, st>>>(hx, counters + C_NEW_KP, 1);
+  CU(cudaStreamSynchronize(st));
+  CU(cudaGetLastError());
+  const uint32_t total = hx[0];
+  s.x_n_unique = total;
+  *n_unique_host = total;
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_unique_export(pf_ctx* ctx, int cluster_namespace, uint32_t* host_out) {
+  if (!ctx) return PF_ERR_INVALID;
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  if (s.x_n_unique == 0) return PF_OK;
+  if (!host_out) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpy(host_out, s.x_unique.p, s.x_n_unique * s.key_words * 4, cudaMemcpyDeviceToHost));
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_unpack(pf_ctx* ctx, int cluster_namespace, const uint32_t* returned_ids_dev,
+                                  uint32_t* local_to_global_dev) {
+  if (!ctx) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  const uint32_t n = (uint32_t)s.n;
+  if (n == 0) return PF_OK;
+  if (!returned_ids_dev || !local_to_global_dev) return fail(ctx, PF_ERR_INVALID, "null exchange buffer");
+  x_unpack<<<cdiv(n, 256), 256, 0, ctx->stream>>>(returned_ids_dev, s.x_perm.as<uint32_t>(), n, local_to_global_dev);
+  ctx->launches++;
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
+  return PF_OK;
+}

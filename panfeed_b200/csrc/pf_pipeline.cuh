@@ -1,0 +1,482 @@
+// pf_pipeline.cuh — pipelined pf_submit (two batch slots), pf_collect, pattern export / ids, stats.
+// Part of libpanfeed_b200.so's single translation unit: included once, in order, by pf_api.cu.
+
+namespace {
+
+// grow a pinned result array, keeping the `used` bytes already copied into it
+int pin_grow(pf_ctx* ctx, PinBuf& b, size_t need, size_t used) {
+  if (need <= b.cap) return PF_OK;
+  CU(cudaStreamSynchronize(ctx->copy_stream));     // copies into the old array are in flight
+  size_t want = std::max(need, b.cap + b.cap / 2);
+  want = (want + 4095) & ~size_t(4095);
+  void* np = nullptr;
+  CU(cudaMallocHost(&np, want));
+  if (b.p && used) memcpy(np, b.p, used);
+  if (b.p) CU(cudaFreeHost(b.p));
+  b.p = np;
+  b.cap = want;
+  return PF_OK;
+}
+
+// cut a batch into sub-batches of whole clusters with about `target` sequences each
+std::vector<SubRange> split_batch(const pf_batch* b, uint32_t target) {
+  std::vector<SubRange> subs;
+  const uint32_t n = b->n_seqs;
+  uint32_t s0 = 0, c0 = 0;
+  while (s0 < n) {
+    uint32_t s1 = n, c1 = b->n_clusters;
+    if ((uint64_t)s0 + target + target / 2 < n) {
+      // first sequence of the cluster that holds sequence s0 + target (clusters are sorted)
+      const uint32_t c = b->seqs[s0 + target].cluster;
+      uint32_t lo = s0, hi = s0 + target;
+      while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (b->seqs[mid].cluster < c) lo = mid + 1; else hi = mid;
+      }
+      if (lo > s0) { s1 = lo; c1 = c; }
+      else {            // one cluster longer than the target: take it whole
+        lo = s0 + target; hi = n;
+        while (lo < hi) {
+          const uint32_t mid = lo + (hi - lo) / 2;
+          if (b->seqs[mid].cluster <= c) lo = mid + 1; else hi = mid;
+        }
+        s1 = lo;
+        c1 = s1 < n ? b->seqs[s1].cluster : b->n_clusters;
+      }
+    }
+    SubRange r{};
+    r.s0 = s0; r.s1 = s1; r.c0 = c0; r.c1 = std::max(c1, c0);
+    r.w0 = b->seqs[s0].base_off >> 5;
+    r.w1 = s1 < n ? (b->seqs[s1].base_off >> 5) : b->n_words;
+    r.a0 = 0; r.a1 = 0;
+    subs.push_back(r);
+    s0 = s1;
+    c0 = r.c1;
+  }
+  if (!subs.empty()) subs.back().c1 = b->n_clusters;     // trailing clusters without sequences
+  return subs;
+}
+
+void pipe_add_timings(pf_ctx* ctx, const BatchState* slot = nullptr) {
+  fill_timings(ctx, slot);
+  const pf_stats& t = ctx->stats;
+  const float v[10] = {t.ms_h2d, t.ms_extract, t.ms_hist, t.ms_sort, t.ms_mark, t.ms_count, t.ms_reduce,
+                       t.ms_dedup, 0.f, 0.f};
+  for (int i = 0; i < 10; ++i) ctx->pipe_ms[i] += v[i];
+}
+
+// D2H of the current slot's results behind everything it executed, appended to the pinned
+// result arrays of the pipelined submit
+int pipe_enqueue_results(pf_ctx* ctx, const SubRange& r, int slot) {
+  cudaStream_t st = ctx->stream, cp = ctx->copy_stream;
+  WidthState& N = ctx->nar;
+  WidthState& Wd = ctx->wid;
+  const uint64_t nr = N.n_rows, nw = Wd.n_rows;
+  const uint64_t R = ctx->pipe_rows, RW = ctx->pipe_wide_rows;
+  TRY(pin_grow(ctx, ctx->r_row_cluster, (R + nr) * 4, R * 4));
+  TRY(pin_grow(ctx, ctx->r_row_count, (R + nr) * 4, R * 4));
+  TRY(pin_grow(ctx, ctx->r_row_pattern, (R + nr) * 4, R * 4));
+  TRY(pin_grow(ctx, ctx->r_row_kmer, (R + nr) * 8, R * 8));
+  TRY(pin_grow(ctx, ctx->r_wrow_cluster, std::max<uint64_t>(8, (RW + nw) * 4), RW * 4));
+  TRY(pin_grow(ctx, ctx->r_wrow_count, std::max<uint64_t>(8, (RW + nw) * 4), RW * 4));
+  TRY(pin_grow(ctx, ctx->r_wrow_pattern, std::max<uint64_t>(8, (RW + nw) * 4), RW * 4));
+  TRY(pin_grow(ctx, ctx->r_wrow_kmer, std::max<uint64_t>(8, (RW + nw) * 16), RW * 16));
+  if (ctx->n_pos) {
+    const uint64_t P0 = ctx->pipe_pos, np = ctx->n_pos;
+    TRY(pin_grow(ctx, ctx->r_pos_kmer, (P0 + np) * 8, P0 * 8));
+    TRY(pin_grow(ctx, ctx->r_pos_seq, (P0 + np) * 4, P0 * 4));
+    TRY(pin_grow(ctx, ctx->r_pos_cstart, (P0 + np) * 4, P0 * 4));
+    TRY(pin_grow(ctx, ctx->r_pos_gstart, (P0 + np) * 4, P0 * 4));
+    TRY(pin_grow(ctx, ctx->r_pos_flags, (P0 + np), P0));
+    if (ctx->n_pos_wide)
+      TRY(pin_grow(ctx, ctx->r_pos_wide, (ctx->pipe_pos_wide + ctx->n_pos_wide) * 16, ctx->pipe_pos_wide * 16));
+    pos_rebase<<<cdiv(ctx->n_pos, 256), 256, 0, st>>>(ctx->d_pos_seq.as<uint32_t>(), ctx->d_pos_kmer.as<uint64_t>(),
+                                                      ctx->d_pos_flags.as<uint8_t>(), ctx->n_pos, r.s0,
+                                                      ctx->pipe_pos_wide);
+    ctx->launches++;
+  }
+  CU(cudaEventRecord(ctx->ev_rows, st));
+  CU(cudaStreamWaitEvent(cp, ctx->ev_rows, 0));
+  auto d2h = [&](PinBuf& dst, size_t dst_off, const void* src, size_t bytes) -> int {
+    if (bytes) CU(cudaMemcpyAsync((char*)dst.p + dst_off, src, bytes, cudaMemcpyDeviceToHost, cp));
+    return PF_OK;
+  };
+  TRY(d2h(ctx->r_row_cluster, R * 4, ctx->d_row_cluster.p, nr * 4));
+  TRY(d2h(ctx->r_row_count, R * 4, ctx->d_row_count.p, nr * 4));
+  TRY(d2h(ctx->r_row_pattern, R * 4, ctx->d_row_pattern.p, nr * 4));
+  TRY(d2h(ctx->r_row_kmer, R * 8, ctx->d_row_kmer.p, nr * 8));
+  TRY(d2h(ctx->r_wrow_cluster, RW * 4, ctx->d_row_cluster.as<uint32_t>() + nr, nw * 4));
+  TRY(d2h(ctx->r_wrow_count, RW * 4, ctx->d_row_count.as<uint32_t>() + nr, nw * 4));
+  TRY(d2h(ctx->r_wrow_pattern, RW * 4, ctx->d_row_pattern.as<uint32_t>() + nr, nw * 4));
+  TRY(d2h(ctx->r_wrow_kmer, RW * 16, ctx->d_wrow_kmer.p, nw * 16));
+  TRY(d2h(ctx->r_cl_pattern, (size_t)ctx->pipe_clusters * 4, ctx->d_cl_pattern.p, (size_t)ctx->n_clusters * 4));
+  if (ctx->n_pos) {
+    const uint64_t P0 = ctx->pipe_pos, np = ctx->n_pos;
+    TRY(d2h(ctx->r_pos_kmer, P0 * 8, ctx->d_pos_kmer.p, np * 8));
+    TRY(d2h(ctx->r_pos_seq, P0 * 4, ctx->d_pos_seq.p, np * 4));
+    TRY(d2h(ctx->r_pos_cstart, P0 * 4, ctx->d_pos_cstart.p, np * 4));
+    TRY(d2h(ctx->r_pos_gstart, P0 * 4, ctx->d_pos_gstart.p, np * 4));
+    TRY(d2h(ctx->r_pos_flags, P0, ctx->d_pos_flags.p, np));
+    if (ctx->n_pos_wide)
+      TRY(d2h(ctx->r_pos_wide, ctx->pipe_pos_wide * 16, ctx->d_pos_wide.p, (size_t)ctx->n_pos_wide * 16));
+  }
+  CU(cudaEventRecord(ctx->ev_out_done[slot], cp));
+  ctx->pipe_rows += nr;
+  ctx->pipe_wide_rows += nw;
+  ctx->pipe_pos += ctx->n_pos;
+  ctx->pipe_pos_wide += ctx->n_pos_wide;
+  ctx->pipe_clusters += ctx->n_clusters;
+  pf_stats& s = ctx->stats;
+  s.bases += ctx->n_bases;
+  s.instances += (uint64_t)N.n_records + Wd.n_records;
+  s.unique_kmers += ctx->unique_last;
+  s.rows += nr + nw;
+  return PF_OK;
+}
+
+// D2H (copy stream) of the k-mer patterns numbered since the last call; the compute stream
+// must have passed the K4 that appended them
+int pipe_copy_new_patterns(pf_ctx* ctx) {
+  const uint64_t done = ctx->kp.n, from = ctx->pipe_kp_copied, base = ctx->pipe_kp_base;
+  if (done <= from) return PF_OK;
+  const size_t row = (size_t)ctx->Wk * 4;
+  TRY(pin_grow(ctx, ctx->r_new_kp, (done - base) * row, (from - base) * row));
+  CU(cudaMemcpyAsync((char*)ctx->r_new_kp.p + (from - base) * row, ctx->kp.pool.as<uint32_t>() + from * ctx->Wk,
+                     (done - from) * row, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  ctx->pipe_kp_copied = done;
+  return PF_OK;
+}
+
+// pf_submit of a large batch: sub-batches of whole clusters flow through two batch slots, so
+// that the H2D of sub-batch j+1 (up_stream) and the D2H of sub-batch j-1 (copy_stream) run
+// under the kernels of sub-batch j (stream).  The pattern tables are shared, K4 of the
+// sub-batches is ordered by the compute stream, so pattern ids are those of one big batch.
+int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>& subs) {
+  cudaStream_t st = ctx->stream, up = ctx->up_stream;
+  TRY(finalize_pending(ctx));
+  ctx->executed = false;
+  ctx->alt.executed = false;
+  ctx->pipe_rows = ctx->pipe_wide_rows = ctx->pipe_pos = ctx->pipe_pos_wide = 0;
+  ctx->pipe_clusters = 0;
+  ctx->pipe_kp_base = ctx->kp.n;
+  ctx->pipe_kp_copied = ctx->kp.n;
+  ctx->pipe_cp_base = ctx->cp.n;
+  for (double& m : ctx->pipe_ms) m = 0;
+  TRY(pin_ensure(ctx, ctx->r_cl_pattern, std::max<size_t>(8, (size_t)b->n_clusters * 4)));
+  {
+    // row arrays: learned rows-per-base ratio, grown on demand
+    const uint64_t est = (uint64_t)(ctx->row_ratio * 1.3 * (double)b->n_words * 32.0) + 65536;
+    TRY(pin_grow(ctx, ctx->r_row_cluster, est * 4, 0));
+    TRY(pin_grow(ctx, ctx->r_row_count, est * 4, 0));
+    TRY(pin_grow(ctx, ctx->r_row_pattern, est * 4, 0));
+    TRY(pin_grow(ctx, ctx->r_row_kmer, est * 8, 0));
+  }
+  auto swap_slots = [&]() { std::swap(static_cast<BatchState&>(*ctx), ctx->alt); };
+  struct Guard { pf_ctx* c; ~Guard() { c->pipe_mode = false; } } guard{ctx};
+  ctx->pipe_mode = true;
+  int cur = 0;
+  const size_t J = subs.size();
+  ctx->pipe_subs = (uint32_t)J;
+  static const bool dbg = getenv("PF_DEBUG_PIPE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = now();
+  double t_up = 0, t_ex = 0, t_out = 0, t_fin = 0;
+  CU(cudaEventRecord(ctx->ev_pipe[0], st));
+  TRY(upload_async(ctx, *ctx, b, subs[0], up));
+  TRY(upload_finish(ctx, *ctx, up));
+  for (size_t j = 0; j < J; ++j) {
+    // a helper thread validates, plans and uploads sub-batch j+1 into the other slot while
+    // this thread drives the kernels of sub-batch j (pf_execute blocks on its read-backs)
+    std::thread helper;
+    int up_rc = PF_OK;
+    if (j + 1 < J) {
+      // the kernels of the other slot's last occupant (sub-batch j-1) must be done with its
+      // inputs; its result arrays are still draining, but an upload does not touch those
+      CU(cudaStreamWaitEvent(up, ctx->ev_exec_end[cur ^ 1], 0));
+      helper = std::thread([&, j]() {
+        cudaSetDevice(ctx->device);
+        const double t0 = now();
+        up_rc = upload_async(ctx, ctx->alt, b, subs[j + 1], up);
+        t_up += now() - t0;
+      });
+    }
+    // this slot's previous rows must have left the device before they are overwritten
+    int rc = PF_OK;
+    if (cudaStreamWaitEvent(st, ctx->ev_out_done[cur], 0) != cudaSuccess) rc = fail(ctx, PF_ERR_CUDA, "cudaStreamWaitEvent failed");
+    double t0 = now();
+    if (rc == PF_OK) rc = pf_execute(ctx);
+    t_ex += now() - t0;
+    if (rc == PF_OK && cudaEventRecord(ctx->ev_exec_end[cur], st) != cudaSuccess) rc = fail(ctx, PF_ERR_CUDA, "cudaEventRecord failed");
+    t0 = now();
+    if (rc == PF_OK) rc = pipe_enqueue_results(ctx, subs[j], cur);
+    t_out += now() - t0;
+    if (helper.joinable()) helper.join();
+    if (rc != PF_OK) return rc;
+    if (up_rc != PF_OK) return up_rc;
+    t0 = now();
+    // pf_execute folded sub-batch j-1's pattern count in before its own K4: those patterns are
+    // final, and so are the other slot's stage timestamps
+    TRY(pipe_copy_new_patterns(ctx));
+    if (j > 0) pipe_add_timings(ctx, &ctx->alt);
+    if (j + 1 < J) {
+      ctx->executed = false;
+      swap_slots();
+      cur ^= 1;
+      TRY(upload_finish(ctx, *ctx, up));
+      t_fin += now() - t0;
+    }
+  }
+  if (dbg)
+    fprintf(stderr, "[pf] pipeline: %zu sub-batches, host ms: total %.2f  upload_async %.2f  execute %.2f  enqueue %.2f  finish %.2f\n",
+            J, now() - t_begin, t_up, t_ex, t_out, t_fin);
+  CU(cudaEventRecord(ctx->ev_pipe[1], st));
+  ctx->pipe_pending = true;
+  return PF_OK;
+}
+
+}  // namespace
+
+extern "C" int pf_submit(pf_ctx* ctx, const pf_batch* batch) {
+  if (!ctx) return PF_ERR_INVALID;
+  if (!batch) return fail(ctx, PF_ERR_INVALID, "pf_submit: null batch");
+  if (ctx->pipe_pending) return fail(ctx, PF_ERR_STATE, "pf_submit: results of the previous pf_submit were not collected");
+  if (batch->n_seqs >= ctx->pipe_min_seqs && batch->n_amb_words == 0 && batch->seqs && batch->n_clusters > 1) {
+    CU(cudaSetDevice(ctx->device));
+    const std::vector<SubRange> subs = split_batch(batch, ctx->pipe_target_seqs);
+    if (subs.size() > 1) return submit_pipelined(ctx, batch, subs);
+  }
+  ctx->pipe_subs = 1;
+  int r = pf_upload(ctx, batch);
+  if (r != PF_OK) return r;
+  return pf_execute(ctx);
+}
+
+namespace {
+int collect_pipelined(pf_ctx* ctx, pf_batch_result* out) {
+  cudaStream_t st = ctx->stream;
+  CU(cudaStreamSynchronize(st));
+  TRY(check_device_error(ctx));
+  uint32_t* hcnt = ctx->h_counters.as<uint32_t>();
+  ctx->kp.n = ctx->kp_base + hcnt[C_NEW_KP];      // last sub-batch
+  ctx->kp_pending = false;
+  ctx->executed = false;
+  ctx->alt.executed = false;
+  ctx->pipe_pending = false;
+  pipe_add_timings(ctx);
+  const uint64_t new_kp = ctx->kp.n - ctx->pipe_kp_base, new_cp = ctx->cp.n - ctx->pipe_cp_base;
+  CU(cudaEventRecord(ctx->ev_d2h[0], st));
+  TRY(pipe_copy_new_patterns(ctx));
+  if (!ctx->r_new_kp.p) TRY(pin_ensure(ctx, ctx->r_new_kp, 8));
+  TRY(pin_ensure(ctx, ctx->r_new_cp, std::max<size_t>(8, new_cp * ctx->W * 4)));
+  if (new_cp)
+    CU(cudaMemcpyAsync(ctx->r_new_cp.p, ctx->cp.pool.as<uint32_t>() + ctx->pipe_cp_base * ctx->W, new_cp * ctx->W * 4,
+                       cudaMemcpyDeviceToHost, st));
+  CU(cudaEventRecord(ctx->ev_d2h[1], st));
+  CU(cudaStreamSynchronize(st));
+  CU(cudaStreamSynchronize(ctx->copy_stream));
+  if (out) {
+    memset(out, 0, sizeof *out);
+    out->n_rows = ctx->pipe_rows;
+    out->row_cluster = ctx->r_row_cluster.as<uint32_t>();
+    out->row_kmer = ctx->r_row_kmer.as<uint64_t>();
+    out->row_count = ctx->r_row_count.as<uint32_t>();
+    out->row_pattern = ctx->r_row_pattern.as<uint32_t>();
+    out->n_wide_rows = ctx->pipe_wide_rows;
+    out->wide_row_cluster = ctx->r_wrow_cluster.as<uint32_t>();
+    out->wide_row_kmer = ctx->r_wrow_kmer.as<uint64_t>();
+    out->wide_row_count = ctx->r_wrow_count.as<uint32_t>();
+    out->wide_row_pattern = ctx->r_wrow_pattern.as<uint32_t>();
+    out->n_clusters = ctx->pipe_clusters;
+    out->cluster_pattern = ctx->r_cl_pattern.as<uint32_t>();
+    out->kmer_pattern_base = ctx->pipe_kp_base;
+    out->n_new_kmer_patterns = new_kp;
+    out->new_kmer_patterns = ctx->r_new_kp.as<uint32_t>();
+    out->cluster_pattern_base = ctx->pipe_cp_base;
+    out->n_new_cluster_patterns = new_cp;
+    out->new_cluster_patterns = ctx->r_new_cp.as<uint32_t>();
+    out->n_pos = ctx->pipe_pos;
+    out->pos_kmer = ctx->r_pos_kmer.as<uint64_t>();
+    out->pos_seq = ctx->r_pos_seq.as<uint32_t>();
+    out->pos_contig_start = ctx->r_pos_cstart.as<int32_t>();
+    out->pos_gene_start = ctx->r_pos_gstart.as<int32_t>();
+    out->pos_flags = ctx->r_pos_flags.as<uint8_t>();
+    out->pos_wide_kmer = ctx->r_pos_wide.as<uint64_t>();
+    out->n_pos_wide = ctx->pipe_pos_wide;
+  }
+  pf_stats& s = ctx->stats;
+  s.batches++;
+  s.kmer_patterns = ctx->kp.n;
+  s.cluster_patterns = ctx->cp.n;
+  s.total_launches = ctx->launches;
+  s.ms_h2d = (float)ctx->pipe_ms[0]; s.ms_extract = (float)ctx->pipe_ms[1]; s.ms_hist = (float)ctx->pipe_ms[2];
+  s.ms_sort = (float)ctx->pipe_ms[3]; s.ms_mark = (float)ctx->pipe_ms[4]; s.ms_count = (float)ctx->pipe_ms[5];
+  s.ms_reduce = (float)ctx->pipe_ms[6]; s.ms_dedup = (float)ctx->pipe_ms[7];
+  float m = 0;
+  if (cudaEventElapsedTime(&m, ctx->ev_pipe[0], ctx->ev_pipe[1]) == cudaSuccess) s.ms_total = m;
+  if (cudaEventElapsedTime(&m, ctx->ev_d2h[0], ctx->ev_d2h[1]) == cudaSuccess) s.ms_d2h = m;
+  return PF_OK;
+}
+}  // namespace
+
+extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
+  if (!ctx) return PF_ERR_INVALID;
+  if (ctx->pipe_pending) { CU(cudaSetDevice(ctx->device)); return collect_pipelined(ctx, out); }
+  if (!ctx->executed) return fail(ctx, PF_ERR_STATE, "pf_collect: nothing executed");
+  CU(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  CU(cudaStreamSynchronize(st));
+  uint32_t* hcnt = ctx->h_counters.as<uint32_t>();
+  TRY(check_device_error(ctx));
+  WidthState& N = ctx->nar;
+  WidthState& Wd = ctx->wid;
+  const uint64_t rows = (uint64_t)N.n_rows + Wd.n_rows;
+  const uint64_t new_kp = hcnt[C_NEW_KP];
+  const uint64_t new_cp = ctx->cp.n - ctx->cp_base;
+  ctx->kp.n = ctx->kp_base + new_kp;
+  ctx->kp_pending = false;
+  ctx->executed = false;      // results are handed out once
+
+  CU(cudaEventRecord(ctx->ev_d2h[0], st));
+  auto d2h = [&](PinBuf& dst, const void* src, size_t bytes) -> int {
+    TRY(pin_ensure(ctx, dst, std::max<size_t>(bytes, 8)));
+    if (bytes) CU(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyDeviceToHost, st));
+    return PF_OK;
+  };
+  if (!ctx->rows_prefetched) {
+    TRY(d2h(ctx->r_row_cluster, ctx->d_row_cluster.p, rows * 4));
+    TRY(d2h(ctx->r_row_count, ctx->d_row_count.p, rows * 4));
+    TRY(d2h(ctx->r_row_kmer, ctx->d_row_kmer.p, (size_t)N.n_rows * 8));
+    TRY(d2h(ctx->r_wrow_kmer, ctx->d_wrow_kmer.p, (size_t)Wd.n_rows * 16));
+  }
+  TRY(d2h(ctx->r_row_pattern, ctx->d_row_pattern.p, rows * 4));
+  TRY(d2h(ctx->r_cl_pattern, ctx->d_cl_pattern.p, (size_t)ctx->n_clusters * 4));
+  TRY(d2h(ctx->r_new_kp, ctx->kp.pool.as<uint32_t>() + ctx->kp_base * ctx->Wk, new_kp * ctx->Wk * 4));
+  TRY(d2h(ctx->r_new_cp, ctx->cp.pool.as<uint32_t>() + ctx->cp_base * ctx->W, new_cp * ctx->W * 4));
+  if (ctx->n_pos) {
+    TRY(d2h(ctx->r_pos_kmer, ctx->d_pos_kmer.p, (size_t)ctx->n_pos * 8));
+    TRY(d2h(ctx->r_pos_seq, ctx->d_pos_seq.p, (size_t)ctx->n_pos * 4));
+    TRY(d2h(ctx->r_pos_cstart, ctx->d_pos_cstart.p, (size_t)ctx->n_pos * 4));
+    TRY(d2h(ctx->r_pos_gstart, ctx->d_pos_gstart.p, (size_t)ctx->n_pos * 4));
+    TRY(d2h(ctx->r_pos_flags, ctx->d_pos_flags.p, (size_t)ctx->n_pos));
+  }
+  if (ctx->n_pos_wide) TRY(d2h(ctx->r_pos_wide, ctx->d_pos_wide.p, (size_t)ctx->n_pos_wide * 16));
+  CU(cudaEventRecord(ctx->ev_d2h[1], st));
+  CU(cudaStreamSynchronize(st));
+  if (ctx->rows_prefetched) CU(cudaStreamSynchronize(ctx->copy_stream));
+  ctx->rows_prefetched = false;
+
+  if (out) {
+    memset(out, 0, sizeof *out);
+    out->n_rows = N.n_rows;
+    out->row_cluster = ctx->r_row_cluster.as<uint32_t>();
+    out->row_kmer = ctx->r_row_kmer.as<uint64_t>();
+    out->row_count = ctx->r_row_count.as<uint32_t>();
+    out->row_pattern = ctx->r_row_pattern.as<uint32_t>();
+    out->n_wide_rows = Wd.n_rows;
+    out->wide_row_cluster = out->row_cluster + N.n_rows;
+    out->wide_row_kmer = ctx->r_wrow_kmer.as<uint64_t>();
+    out->wide_row_count = out->row_count + N.n_rows;
+    out->wide_row_pattern = out->row_pattern + N.n_rows;
+    out->n_clusters = ctx->n_clusters;
+    out->cluster_pattern = ctx->r_cl_pattern.as<uint32_t>();
+    out->kmer_pattern_base = ctx->kp_base;
+    out->n_new_kmer_patterns = new_kp;
+    out->new_kmer_patterns = ctx->r_new_kp.as<uint32_t>();
+    out->cluster_pattern_base = ctx->cp_base;
+    out->n_new_cluster_patterns = new_cp;
+    out->new_cluster_patterns = ctx->r_new_cp.as<uint32_t>();
+    out->n_pos = ctx->n_pos;
+    out->pos_kmer = ctx->r_pos_kmer.as<uint64_t>();
+    out->pos_seq = ctx->r_pos_seq.as<uint32_t>();
+    out->pos_contig_start = ctx->r_pos_cstart.as<int32_t>();
+    out->pos_gene_start = ctx->r_pos_gstart.as<int32_t>();
+    out->pos_flags = ctx->r_pos_flags.as<uint8_t>();
+    out->pos_wide_kmer = ctx->r_pos_wide.as<uint64_t>();
+    out->n_pos_wide = ctx->n_pos_wide;
+  }
+  // ---- stats ---------------------------------------------------------------
+  pf_stats& s = ctx->stats;
+  s.batches++;
+  s.bases += ctx->n_bases;
+  s.instances += (uint64_t)N.n_records + Wd.n_records;
+  s.unique_kmers += ctx->unique_last;
+  s.rows += rows;
+  s.kmer_patterns = ctx->kp.n;
+  s.cluster_patterns = ctx->cp.n;
+  s.sort_passes = (uint32_t)N.passes;
+  s.total_launches = ctx->launches;
+  fill_timings(ctx);
+  {
+    float m = 0;
+    if (cudaEventElapsedTime(&m, ctx->ev_d2h[0], ctx->ev_d2h[1]) == cudaSuccess) s.ms_d2h = m;
+  }
+  return PF_OK;
+}
+
+extern "C" int pf_reset_patterns(pf_ctx* ctx) {
+  if (!ctx) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->executed = false;
+  ctx->kp_pending = false;
+  for (PatternSpace* s : {&ctx->kp, &ctx->cp}) {
+    s->n = 0;
+    s->x_n_unique = 0;
+    if (s->table.p) CU(cudaMemsetAsync(s->table.p, 0xff, (size_t)s->table_size * 4, ctx->stream));
+  }
+  ctx->kp_base = ctx->cp_base = 0;
+  ctx->stats.kmer_patterns = ctx->stats.cluster_patterns = 0;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return PF_OK;
+}
+
+extern "C" int pf_patterns_export(pf_ctx* ctx, int cluster_namespace, uint64_t first, uint64_t count,
+                                  uint32_t* host_out) {
+  if (!ctx || !host_out) return PF_ERR_INVALID;
+  TRY(finalize_pending(ctx));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  if (first + count > s.n) return fail(ctx, PF_ERR_INVALID, "pattern range [%llu,%llu) beyond %llu",
+                                       (unsigned long long)first, (unsigned long long)(first + count),
+                                       (unsigned long long)s.n);
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (count)
+    CU(cudaMemcpy(host_out, s.pool.as<uint32_t>() + first * s.key_words, count * s.key_words * 4,
+                  cudaMemcpyDeviceToHost));
+  return PF_OK;
+}
+
+extern "C" int pf_pattern_ids(pf_ctx* ctx, int cluster_namespace, uint64_t first, uint64_t count,
+                              uint8_t* host_digests) {
+  if (!ctx || (count && !host_digests)) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  TRY(finalize_pending(ctx));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  if (first + count > s.n) return fail(ctx, PF_ERR_INVALID, "pattern range [%llu,%llu) beyond %llu",
+                                       (unsigned long long)first, (unsigned long long)(first + count),
+                                       (unsigned long long)s.n);
+  if (count == 0) return PF_OK;
+  TRY(dev_ensure(ctx, ctx->d_digests, count * 16));
+  k5_md5_ids<<<cdiv(count, 128), 128, 0, ctx->stream>>>(
+      s.pool.as<uint32_t>(), (uint32_t)first, (uint32_t)count, s.key_words, ctx->W, ctx->prm.n_samples,
+      cluster_namespace ? 1 : 0, ctx->cp.pool.as<uint32_t>(), ctx->d_digests.as<uint8_t>());
+  ctx->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(host_digests, ctx->d_digests.p, count * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return PF_OK;
+}
+
+extern "C" int pf_stats_get(pf_ctx* ctx, pf_stats* out) {
+  if (!ctx || !out) return PF_ERR_INVALID;
+  if (ctx->executed) {
+    TRY(finalize_pending(ctx));
+    CU(cudaStreamSynchronize(ctx->stream));
+    fill_timings(ctx);
+  }
+  ctx->stats.kmer_patterns = ctx->kp.n;
+  ctx->stats.cluster_patterns = ctx->cp.n;
+  *out = ctx->stats;
+  out->total_launches = ctx->launches;
+  return PF_OK;
+}
