@@ -1,11 +1,11 @@
-// Block aggregation (S <= 1024): K1 + K2 + K3 without ever materialising a record.
+// Block aggregation: K1 + K2 + K3 without ever materialising a record.
 //
-// The sequences of one gene cluster are near-identical copies of one gene, so
-// the windows that START inside the same short position block [p0, p0 + B) of
-// every sequence of the cluster hold only a few hundred distinct k-mers between
-// them (one per haplotype and position), however many samples there are.
+// The sequences of one gene cluster are near-identical copies of one gene, so the windows
+// that START inside the same run of 16 positions of every sequence of the cluster hold only
+// a few hundred distinct k-mers between them (one per haplotype and position), however many
+// samples there are.
 //
-//   kA_block_aggregate  one CTA per (cluster, run of 16 window positions).
+//   kA_block_aggregate  one CTA per (cluster, run of 16 window positions[, slice of 512 samples]).
 //                       Level 1: every sequence contributes the R = k + 15 bases its 16
 //                       windows cover as ONE 128-bit chunk; identical chunks (same haplotype)
 //                       meet in a shared-memory chunk table and only OR one sample bit there:
@@ -13,25 +13,26 @@
 //                       Level 2: the few dozen DISTINCT chunks are cut into their 16 k-mers
 //                       (forward / reverse complement / canonical), each k-mer is looked up in
 //                       a shared-memory open-addressing table and takes the chunk's whole
-//                       W-word sample bitset.  The CTA ends by writing its distinct k-mers and
-//                       bitsets ("partials") to a slab in HBM: ~1/30 of the bytes the records
-//                       would have taken, written once.
-//   kB1/kB2/kB3         a k-mer can start in two runs (indels, clamped flanks, paralogs), so
-//                       the partials of one cluster are merged by FULL key in a per-cluster
-//                       open-addressing table in global memory: the first partial of a key
-//                       owns it, later ones OR their bitset into the owner's; owners are then
-//                       counted, filtered with the integer MAF window and emitted as rows.
+//                       W-word sample bitset.  The CTA ends by writing its distinct k-mers,
+//                       bitsets and popcounts ("partial rows") to a slab in HBM: ~1/30 of the
+//                       bytes the records would have taken, written once.
+//   kB1/kB2/kB3         a k-mer can start in two runs (indels, clamped flanks, paralogs,
+//                       repeats), so the partial rows of one cluster are merged by FULL key in a
+//                       per-cluster open-addressing table in global memory: the first row of a
+//                       key owns it, later ones OR their bitset into the owner's; owners are
+//                       filtered on their popcount with the integer MAF window and emitted.
+//   kB4/kB5             with sample slices (S > 1024) kB1/kB2 merge per (cluster, slice); kB4
+//                       links the slices of a k-mer and sums their popcounts, kB5 filters on the
+//                       sum and assembles the full-width bitsets of the survivors.
 //
-// Exact for any input: nothing depends on the sequences being aligned — alignment
-// only decides how few partials there are.  A block holding more distinct k-mers
-// than the shared-memory table takes raises a flag and the host reruns the batch
-// through the record path (k2_extract_scatter + k3_local_direct).
+// Exact for any input: nothing depends on the sequences being aligned — alignment only
+// decides how few partial rows there are.  A run holding more distinct k-mers than the
+// shared-memory tables take flags itself; the host reruns just those runs with larger tables
+// and, past the largest, sends the batch through the record path (k2_extract_scatter +
+// k3_local_direct / k3_local).
 //
-// Shared-memory table of both kernels: `slots` 64-bit keys (open addressing, linear
-// probing, claimed with one 64-bit atomicCAS) and one W-word bitset PER SLOT, so a
-// lookup is one LDS.64 and the OR goes straight to slot * stride: no dense-id
-// indirection on the hot path.  The all-ones word marks an empty slot; it is a valid
-// k-mer only for k = 32 in --non-canonical mode, which stays on the record path.
+// Shared memory of kA: see ARunView.  The all-ones word marks an empty k-mer slot; it is a
+// valid k-mer only for k = 32 in --non-canonical mode, which stays on the record path.
 //
 // Replaces the window loop and `cluster_dict[kmer][sortstrain[strain]] = 1` of
 // /root/reference/panfeed/panfeed.py:54-88 and the filters of :190-204.
@@ -55,10 +56,6 @@ struct ClusterBlk {        // 16 bytes
 constexpr int kBlkThreads = 256;
 constexpr int kBlkWarps = kBlkThreads / 32;
 constexpr int kBlkRun = 16;                       // windows per task
-#ifndef PF_BLK_MIN_CTAS
-#define PF_BLK_MIN_CTAS 5
-#endif
-constexpr int kBlkMinCtas = PF_BLK_MIN_CTAS;      // register budget of kA: 65536 / (256 * n)
 constexpr uint32_t kBlkOverflow = 0xffffffffu;    // slab count of a block that did not fit
 // slab_cnt[p]: popcount of partial row p as kA wrote it; after kB2: kCntDead = folded into an
 // earlier row of the same k-mer, kCntDirty = received another row's bits (recount from the row)
@@ -148,74 +145,14 @@ __global__ void plan_item_desc(const uint32_t* __restrict__ item_base, const uin
 // ---------------------------------------------------------------------------
 // shared-memory table
 // ---------------------------------------------------------------------------
-struct BlkHead {           // 64 bytes, then keys[slots], list[slots] (u16), pool[(slots + 1) * WS]
-                           // (row `slots` is a scratch row: lookups of a full table land there)
+struct BlkHead {           // 64 bytes at the start of kA's shared memory (see ARunView)
   uint32_t n_unique, overflow, n_pass, row_base, ok, work, pad[10];
 };
-__host__ __device__ inline uint32_t blk_smem_bytes(uint32_t slots, uint32_t W) {
-  return (uint32_t)sizeof(BlkHead) + slots * 8u + slots * 2u + (slots + 1u) * (W | 1u) * 4u;
-}
-struct BlkView {
-  BlkHead* h;
-  uint64_t* keys;
-  uint16_t* list;
-  uint32_t* pool;
-  uint32_t mask, shift;    // slots - 1, 32 - log2(slots)
-};
-__device__ __forceinline__ BlkView blk_view(unsigned char* raw, uint32_t slots) {
-  BlkView v;
-  v.h = reinterpret_cast<BlkHead*>(raw);
-  v.keys = reinterpret_cast<uint64_t*>(raw + sizeof(BlkHead));
-  v.list = reinterpret_cast<uint16_t*>(v.keys + slots);
-  v.pool = reinterpret_cast<uint32_t*>(v.list + slots);
-  v.mask = slots - 1u;
-  v.shift = 32u - (uint32_t)__popc(v.mask);
-  return v;
-}
 __device__ __forceinline__ uint32_t ld_volatile_shared(const uint32_t* p) {
   return *reinterpret_cast<const volatile uint32_t*>(p);
 }
 __device__ __forceinline__ uint32_t blk_hash(uint32_t kh, uint32_t kl, uint32_t shift) {
   return ((kl ^ (kh * 0x85ebca6bu)) * 0x9e3779b1u) >> shift;
-}
-
-// Collision chain of the lookup (the home slot holds another key): linear probing from h.
-// Returns the slot (the scratch row `slots` if the chain is too long; overflow is then flagged).
-__device__ __noinline__ uint32_t blk_probe_chain(const BlkView v, uint64_t key, uint32_t h) {
-  const uint32_t limit = min(v.mask, 96u);
-  for (uint32_t probes = 0; probes < limit; ++probes) {
-    uint64_t cur = *reinterpret_cast<const volatile uint64_t*>(&v.keys[h]);
-    if (cur == ~0ull)
-      cur = atomicCAS(reinterpret_cast<unsigned long long*>(&v.keys[h]), ~0ull, (unsigned long long)key);
-    if (cur == ~0ull || cur == key) return h;
-    h = (h + 1u) & v.mask;
-  }
-  v.h->overflow = 1u;
-  return v.mask + 1u;
-}
-// The home slot h held `kk` != key: claim it if it is empty (one CAS, inline: this is how
-// every k-mer seen by a single sample enters the table), else walk the chain.
-__device__ __forceinline__ uint32_t blk_resolve(const BlkView v, uint64_t key, uint32_t h, uint64_t kk) {
-  if (kk == ~0ull) {
-    kk = atomicCAS(reinterpret_cast<unsigned long long*>(&v.keys[h]), ~0ull, (unsigned long long)key);
-    if (kk == ~0ull || kk == key) return h;
-  }
-  return blk_probe_chain(v, key, (h + 1u) & v.mask);
-}
-// list[pos] = h for every occupied slot; one shared-memory atomic per warp.  Returns nothing;
-// *counter ends as the number of occupied slots.  Call with all threads of the CTA.
-__device__ __forceinline__ void blk_list_occupied(const BlkView v, uint32_t slots, uint32_t* counter) {
-  const uint32_t lane = lane_id();
-  for (uint32_t h0 = 0; h0 < slots; h0 += kBlkThreads) {
-    const uint32_t h = h0 + threadIdx.x;
-    const bool used = h < slots && v.keys[h] != ~0ull;
-    const uint32_t m = __ballot_sync(kFull, used);
-    if (m == 0u) continue;
-    uint32_t base = 0;
-    if (lane == (uint32_t)__ffs(m) - 1u) base = atomicAdd(counter, (uint32_t)__popc(m));
-    base = __shfl_sync(kFull, base, __ffs(m) - 1);
-    if (used) v.list[base + __popc(m & lanemask_lt())] = (uint16_t)h;
-  }
 }
 
 // ---------------------------------------------------------------------------
