@@ -483,12 +483,12 @@ struct MergeEntry {        // 16 bytes; key == ~0 marks an empty slot
   uint32_t reserved;
 };
 
-// one warp per (cluster, slice): partial rows -> table slots (load factor <= 2/3).  With
+// one warp per (cluster, slice): partial rows -> table slots (eighths / 8 slots per row).  With
 // slices, table2_ctas[c] additionally sizes the cluster's cross-slice table in units of 256
 // slots (so that a CTA of kB5 belongs to one cluster).
 __global__ void plan_merge_tables(const uint32_t* __restrict__ item_base, uint32_t n_clusters, uint32_t n_slices,
-                                  const uint32_t* __restrict__ slab_count, uint32_t* __restrict__ n_slots,
-                                  uint32_t* __restrict__ table2_ctas) {
+                                  const uint32_t* __restrict__ slab_count, uint32_t eighths /* slots per row x 8 */,
+                                  uint32_t* __restrict__ n_slots, uint32_t* __restrict__ table2_ctas) {
   const uint32_t cs = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (cs >= n_clusters * n_slices) return;
   const uint32_t c = cs / n_slices, slice = cs - c * n_slices;
@@ -501,7 +501,7 @@ __global__ void plan_merge_tables(const uint32_t* __restrict__ item_base, uint32
 #pragma unroll
   for (int m = 16; m >= 1; m >>= 1) p += __shfl_xor_sync(kFull, p, m);
   if (lane == 0) {
-    n_slots[cs] = p + (p >> 1) + 2u;
+    n_slots[cs] = (uint32_t)(((uint64_t)p * eighths + 7u) >> 3) + 2u;
     if (table2_ctas) atomicAdd(&table2_ctas[c], p);       // partial rows of the cluster (all slices)
   }
 }

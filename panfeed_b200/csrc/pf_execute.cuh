@@ -431,18 +431,20 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
   const uint32_t n_it = ctx->n_items * ns;          // kA work items
   uint32_t* counters = ctx->d_counters.as<uint32_t>();
   const uint32_t WP = (ctx->Ws + 3u) & ~3u;
-  // per-(cluster, slice) tables: 1.5 slots per partial row (+2), offsets by a scan
+  // per-(cluster, slice) tables: 2 slots per partial row (+2; PF_MERGE_EIGHTHS / 8), offsets by a scan
+  static const uint32_t eighths = []() { const char* e = getenv("PF_MERGE_EIGHTHS"); const int v = e ? atoi(e) : 0;
+                                         return (v >= 9 && v <= 32) ? (uint32_t)v : 16u; }();
   TRY(dev_ensure(ctx, ctx->d_group_base, ((size_t)n_cs + 1) * 4));
   if (ns > 1) {
     TRY(dev_ensure(ctx, ctx->d_table2_base, ((size_t)nc + 1) * 4));
     CU(cudaMemsetAsync(ctx->d_table2_base.p, 0, ((size_t)nc + 1) * 4, st));
   }
   plan_merge_tables<<<cdiv((uint64_t)n_cs * 32, 256), 256, 0, st>>>(
-      ctx->d_item_base.as<uint32_t>(), nc, ns, ctx->d_slab_count.as<uint32_t>(), ctx->d_group_base.as<uint32_t>(),
-      ns > 1 ? ctx->d_table2_base.as<uint32_t>() : nullptr);
+      ctx->d_item_base.as<uint32_t>(), nc, ns, ctx->d_slab_count.as<uint32_t>(), eighths,
+      ctx->d_group_base.as<uint32_t>(), ns > 1 ? ctx->d_table2_base.as<uint32_t>() : nullptr);
   ctx->launches++;
   TRY(scan_inplace(ctx, ctx->d_group_base.as<uint32_t>(), n_cs, ctx->d_plan_total.as<uint32_t>() + 1));
-  const uint64_t n_slots = (uint64_t)n_partials + n_partials / 2 + 2ull * n_cs + 16;
+  const uint64_t n_slots = ((uint64_t)n_partials * eighths + 7) / 8 + 3ull * n_cs + 16;   // >= sum of ceil(p e / 8) + 2
   if (n_slots >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "too many partial rows for one batch; split it");
   TRY(dev_ensure(ctx, ctx->d_mtable, n_slots * sizeof(MergeEntry)));
   TRY(dev_ensure(ctx, ctx->d_pslot, (size_t)n_partials * 4));
