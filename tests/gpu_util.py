@@ -20,8 +20,15 @@ def run_gpu(items, stroi, S, k, canonical=True, consider_missing=False,
            "seq_meta": [], "seqs": [], "seq_cluster_idx": []}
     seq_base = 0
     try:
-        for b0 in range(0, len(items), batch_clusters):
-            chunk = items[b0:b0 + batch_clusters]
+        # batch_clusters: clusters per batch, or a list of batch sizes used in turn
+        sizes = batch_clusters if isinstance(batch_clusters, (list, tuple)) else [batch_clusters]
+        starts, b0, i = [], 0, 0
+        while b0 < len(items):
+            starts.append((b0, sizes[i % len(sizes)]))
+            b0 += sizes[i % len(sizes)]
+            i += 1
+        for b0, bc in starts:
+            chunk = items[b0:b0 + bc]
             pcs = [packer.PackedCluster(c, idx, pa, stroi) for c, idx, pa in chunk]
             hb, meta, ids = packer.pack_batch(pcs, list(range(b0, b0 + len(chunk))))
             ctx.submit(hb)

@@ -299,6 +299,28 @@ def test_pipelined_submit_matches_oracle(engine, monkeypatch):
     assert out["stats"]["sub_batches"] >= 3
 
 
+def test_pipelined_and_plain_submits_share_one_context(monkeypatch):
+    """Batches above and below the split threshold alternate on one context: pattern numbering
+    continues across pipelined and plain submits, results are those of the oracle."""
+    monkeypatch.setenv("PF_PIPELINE_SEQS", "600")
+    rng = np.random.default_rng(22)
+    S, k = 50, 21
+    items, stroi = _random_items(rng, S, k, 90, 200)
+    out, want = _compare_with_oracle(items, stroi, S, k, False, False, True, 0.04,
+                                     batch_clusters=[40, 3, 35, 12])
+
+
+def test_pipelined_submit_with_sample_slices(monkeypatch):
+    """Pipelined sub-batches through the sample-sliced block engine (S > 1024)."""
+    monkeypatch.setenv("PF_PIPELINE_SEQS", "2000")
+    rng = np.random.default_rng(23)
+    S = 1100
+    items, stroi = _random_items(rng, S, 31, 8, 150)
+    out, want = _compare_with_oracle(items, stroi, S, 31, True, True, False, 0.01,
+                                     batch_clusters=len(items))
+    assert out["stats"]["engine"] == 2 and out["stats"]["sub_batches"] >= 2
+
+
 def test_empty_and_ragged_batches():
     rng = np.random.default_rng(3)
     items, stroi = _random_items(rng, 12, 31, 3, 120)
