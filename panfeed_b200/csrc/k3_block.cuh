@@ -331,7 +331,7 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
   // row costs a warp instruction per word
   for (uint32_t i = tid; i < (a.cap + 1u) * WS; i += kBlkThreads) a.pool[i] = 0u;
   for (uint32_t i = tid; i < a.ccap * WS; i += kBlkThreads) a.crows[i] = 0u;
-  if (tid == 0) { a.h->n_unique = 0; a.h->overflow = 0; a.h->work = 0; }
+  if (tid == 0) { a.h->n_unique = 0; a.h->overflow = 0; a.h->work = 0; a.h->n_pass = 0; }
   uint64_t wf0 = 0, wf1 = 0, wf2 = 0;
   if (raw_first.y >= (uint32_t)k && s_rel < raw_first.y - (uint32_t)k + 1u) {
     const uint64_t* w = bases + raw_first.x + (s_rel >> 5);
@@ -413,13 +413,24 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
 
   // ---- phase 2: distinct chunks x 16 windows -> k-mer table, whole sample bitsets at a time ----
   const uint32_t n_chunks = min(a.h->work, a.ccap);
-  for (uint32_t p = tid; p < n_chunks * (uint32_t)kBlkRun; p += kBlkThreads) {
-    const uint32_t cs = p >> 4, q = p & 15u;
-    const uint64_t hi = a.ckhi[cs], lo = a.cklo[cs];
-    const uint64_t x = q ? ((hi << (2u * q)) | (lo >> (64u - 2u * q))) : hi;
-    const uint16_t meta = a.cmeta[cs];
-    if (meta & 0x8000u) put_kmer(x >> sh64, a.crows + cs * WS, 0u, W);
-    else put_kmer(x >> sh64, a.crows + cs * WS + (meta & 0xffu), meta & 0xffu, 1u);
+  const uint32_t n_pairs = n_chunks * (uint32_t)kBlkRun;
+  // pairs cost very different amounts (a new k-mer is an insertion, a many-sample chunk ORs W
+  // words): the first round is static, after it the warps take 32 pairs at a time from a counter
+  for (uint32_t p0 = (tid & ~31u);;) {
+    const uint32_t p = p0 + (tid & 31u);
+    if (p < n_pairs) {
+      const uint32_t cs = p >> 4, q = p & 15u;
+      const uint64_t hi = a.ckhi[cs], lo = a.cklo[cs];
+      const uint64_t x = q ? ((hi << (2u * q)) | (lo >> (64u - 2u * q))) : hi;
+      const uint16_t meta = a.cmeta[cs];
+      if (meta & 0x8000u) put_kmer(x >> sh64, a.crows + cs * WS, 0u, W);
+      else put_kmer(x >> sh64, a.crows + cs * WS + (meta & 0xffu), meta & 0xffu, 1u);
+    }
+    __syncwarp();
+    uint32_t nx = 0;
+    if ((tid & 31u) == 0u) nx = atomicAdd(&a.h->n_pass, 32u);
+    p0 = (uint32_t)kBlkThreads + __shfl_sync(kFull, nx, 0);
+    if (p0 >= n_pairs) break;
   }
   __syncthreads();
 
