@@ -246,6 +246,20 @@ int pf_format_positions(const pf_batch_result* result, uint32_t k, int canonical
                         const int32_t* seq_strand, char* out, uint64_t out_cap, uint64_t* out_len,
                         uint32_t n_threads);
 
+/* ---- native packer (host threads): ASCII sequences -> the planes of a pf_batch ----
+ * What the feeder has after cutting (input.py:455-459: Seqinfo.sequence, upper case) goes into
+ * the 2-bit plane; sequences holding N/IUPAC symbols are flagged and additionally packed into
+ * the 4-bit plane.  ascii / seq_off: the sequences of the batch back to back, sequence i =
+ * [seq_off[i], seq_off[i+1]).  pf_pack_plan lays the sequences out (base_off[i], multiples of 64;
+ * n_words of the 2-bit plane); pf_pack_2bit fills the plane and is_amb[i]; pf_pack_4bit lays out
+ * and fills the 4-bit plane (amb_plane == NULL: only amb_off / n_amb_words), returning
+ * PF_ERR_UNSUPPORTED and the offending byte in *bad_symbol for symbols outside PF_AMB_ALPHABET. */
+int pf_pack_plan(const uint64_t* seq_off, uint32_t n_seqs, uint64_t* base_off, uint64_t* n_words);
+int pf_pack_2bit(const char* ascii, const uint64_t* seq_off, uint32_t n_seqs, const uint64_t* base_off,
+                 uint64_t* packed, uint8_t* is_amb, uint32_t n_threads);
+int pf_pack_4bit(const char* ascii, const uint64_t* seq_off, uint32_t n_seqs, const uint8_t* is_amb,
+                 uint64_t* amb_off, uint64_t* amb_plane, uint64_t* n_amb_words, int* bad_symbol);
+
 /* ---- synthetic pangenome, generated on the device ---- */
 typedef struct pf_synth_params {
   uint64_t seed;

@@ -109,6 +109,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_upload", "pf_execute", "pf_submit", "pf_collect",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
            "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream", "pf_format_positions",
+           "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_export",
            "pf_exchange_unpack"]
@@ -142,6 +143,9 @@ def load():
     lib.pf_kmer_pattern_words.restype = u32
     lib.pf_maf_window.argtypes = [C.c_double, u32, C.POINTER(u32), C.POINTER(u32)]
     lib.pf_patterns_export.argtypes = [vp, C.c_int, u64, u64, vp]
+    lib.pf_pack_plan.argtypes = [vp, u32, vp, C.POINTER(u64)]
+    lib.pf_pack_2bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, u32]
+    lib.pf_pack_4bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, C.POINTER(u64), C.POINTER(C.c_int)]
     lib.pf_format_positions.argtypes = [C.POINTER(BatchResult), u32, C.c_int, u64, u64, C.c_char_p,
                                         C.POINTER(u64), C.POINTER(C.c_int32), C.c_char_p, u64,
                                         C.POINTER(u64), u32]
@@ -165,6 +169,47 @@ def maf_window(maf, n):
     lo, hi = C.c_uint32(), C.c_uint32()
     ok = load().pf_maf_window(maf, n, C.byref(lo), C.byref(hi))
     return (lo.value, hi.value) if ok else None
+
+
+def pack_sequences(seq_bytes, n_threads=0):
+    """Native packer (pf_pack_*): list of upper-case ASCII sequences -> (packed 2-bit plane,
+    base_off, is_amb, amb_plane or None, amb_off).  Raises ValueError on a symbol outside
+    AMB_ALPHABET."""
+    lib = load()
+    n = len(seq_bytes)
+    blob = b"".join(seq_bytes)
+    seq_off = np.zeros(n + 1, np.uint64)
+    if n:
+        np.cumsum(np.fromiter((len(b) for b in seq_bytes), np.uint64, n), out=seq_off[1:])
+    base_off = np.zeros(n, np.uint64)
+    n_words = C.c_uint64()
+    rc = lib.pf_pack_plan(seq_off.ctypes.data, n, base_off.ctypes.data, C.byref(n_words))
+    if rc != 0:
+        raise PfError(rc, "pf_pack_plan failed")
+    packed = np.zeros(int(n_words.value), np.uint64)
+    is_amb = np.zeros(n, np.uint8)
+    rc = lib.pf_pack_2bit(blob, seq_off.ctypes.data, n, base_off.ctypes.data, packed.ctypes.data,
+                          is_amb.ctypes.data, int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_pack_2bit failed")
+    amb_off = np.zeros(n, np.uint64)
+    amb_plane = None
+    if is_amb.any():
+        n_amb = C.c_uint64()
+        bad = C.c_int()
+        rc = lib.pf_pack_4bit(blob, seq_off.ctypes.data, n, is_amb.ctypes.data, amb_off.ctypes.data, None,
+                              C.byref(n_amb), C.byref(bad))
+        if rc != 0:
+            raise PfError(rc, "pf_pack_4bit (sizing) failed")
+        amb_plane = np.zeros(int(n_amb.value), np.uint64)
+        rc = lib.pf_pack_4bit(blob, seq_off.ctypes.data, n, is_amb.ctypes.data, amb_off.ctypes.data,
+                              amb_plane.ctypes.data, C.byref(n_amb), C.byref(bad))
+        if rc == -4:
+            raise ValueError(f"unsupported sequence symbol {chr(bad.value)!r}: only "
+                             f"{AMB_ALPHABET} (IUPAC, upper case) are accepted")
+        if rc != 0:
+            raise PfError(rc, "pf_pack_4bit failed")
+    return packed, base_off, is_amb.astype(bool), amb_plane, amb_off
 
 
 def format_positions(r, k, canonical, leads, seq_strand, n_threads=0):

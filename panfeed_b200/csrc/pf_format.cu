@@ -162,3 +162,108 @@ extern "C" int pf_format_positions(const pf_batch_result* r, uint32_t k, int can
   });
   return PF_OK;
 }
+
+// ---------------------------------------------------------------------------
+// Native packer: ASCII sequences -> the 2-bit / 4-bit planes of a pf_batch (what
+// panfeed_b200/packer.py:pack_batch does with numpy look-up tables), host threads.
+// ---------------------------------------------------------------------------
+namespace {
+struct Lut {
+  uint8_t two[256], four[256];
+  Lut() {
+    memset(two, 255, sizeof two);
+    memset(four, 255, sizeof four);
+    two[(unsigned char)'A'] = 0; two[(unsigned char)'C'] = 1; two[(unsigned char)'G'] = 2; two[(unsigned char)'T'] = 3;
+    for (int i = 0; i < 16; ++i) four[(unsigned char)kAmb[i]] = (uint8_t)i;
+  }
+};
+const Lut kLut;
+
+template <typename F>
+void parallel_for(uint32_t n, uint32_t n_threads, F&& fn) {
+  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  uint32_t nt = n_threads ? n_threads : hw;
+  nt = std::max(1u, std::min<uint32_t>(nt, (n + 4095u) / 4096u));
+  if (nt == 1) { fn(0u, n); return; }
+  const uint32_t per = (n + nt - 1) / nt;
+  std::vector<std::thread> th;
+  for (uint32_t t = 0; t < nt; ++t) th.emplace_back(fn, std::min(n, t * per), std::min(n, (t + 1) * per));
+  for (auto& x : th) x.join();
+}
+}  // namespace
+
+extern "C" int pf_pack_plan(const uint64_t* seq_off, uint32_t n_seqs, uint64_t* base_off, uint64_t* n_words) {
+  if (!seq_off || !base_off || !n_words) return PF_ERR_INVALID;
+  uint64_t pos = 0;
+  for (uint32_t i = 0; i < n_seqs; ++i) {
+    if (seq_off[i + 1] < seq_off[i]) return PF_ERR_INVALID;
+    base_off[i] = pos;
+    pos += (seq_off[i + 1] - seq_off[i] + 63) / 64 * 64;     // every sequence starts on a 64-base boundary
+  }
+  *n_words = pos / 32;
+  return PF_OK;
+}
+
+extern "C" int pf_pack_2bit(const char* ascii, const uint64_t* seq_off, uint32_t n_seqs, const uint64_t* base_off,
+                            uint64_t* packed, uint8_t* is_amb, uint32_t n_threads) {
+  if (!seq_off || !base_off || !packed || !is_amb || (n_seqs && !ascii)) return PF_ERR_INVALID;
+  parallel_for(n_seqs, n_threads, [&](uint32_t a, uint32_t b) {
+    for (uint32_t i = a; i < b; ++i) {
+      const unsigned char* s = reinterpret_cast<const unsigned char*>(ascii) + seq_off[i];
+      const uint64_t len = seq_off[i + 1] - seq_off[i];
+      uint64_t* out = packed + base_off[i] / 32;
+      const uint64_t words = (len + 63) / 64 * 2;
+      bool amb = false;
+      for (uint64_t w = 0; w < words; ++w) {
+        uint64_t v = 0;
+        const uint64_t p0 = w * 32;
+        for (uint32_t j = 0; j < 32; ++j) {
+          const uint64_t p = p0 + j;
+          uint32_t c = 0;                                   // padding and non-ACGT symbols pack as A
+          if (p < len) {
+            c = kLut.two[s[p]];
+            if (c == 255u) { amb = true; c = 0; }
+          }
+          v = (v << 2) | c;
+        }
+        out[w] = v;
+      }
+      is_amb[i] = amb ? 1 : 0;
+    }
+  });
+  return PF_OK;
+}
+
+extern "C" int pf_pack_4bit(const char* ascii, const uint64_t* seq_off, uint32_t n_seqs, const uint8_t* is_amb,
+                            uint64_t* amb_off, uint64_t* amb_plane, uint64_t* n_amb_words, int* bad_symbol) {
+  if (!seq_off || !is_amb || !amb_off || !n_amb_words) return PF_ERR_INVALID;
+  if (bad_symbol) *bad_symbol = 0;
+  uint64_t pos = 0;                                         // in symbols; 64-symbol blocks like the 2-bit plane
+  for (uint32_t i = 0; i < n_seqs; ++i) {
+    amb_off[i] = 0;
+    if (!is_amb[i]) continue;
+    const unsigned char* s = reinterpret_cast<const unsigned char*>(ascii) + seq_off[i];
+    const uint64_t len = seq_off[i + 1] - seq_off[i];
+    const uint64_t padded = (len + 63) / 64 * 64;
+    amb_off[i] = pos;
+    if (amb_plane) {
+      uint64_t* out = amb_plane + pos / 16;
+      for (uint64_t w = 0; w < padded / 16; ++w) {
+        uint64_t v = 0;
+        for (uint32_t j = 0; j < 16; ++j) {
+          const uint64_t p = w * 16 + j;
+          uint32_t c = kLut.four[(unsigned char)'A'];       // padding packs as A
+          if (p < len) {
+            c = kLut.four[s[p]];
+            if (c == 255u) { if (bad_symbol) *bad_symbol = s[p]; return PF_ERR_UNSUPPORTED; }
+          }
+          v = (v << 4) | c;
+        }
+        out[w] = v;
+      }
+    }
+    pos += padded;
+  }
+  *n_amb_words = pos / 16;
+  return PF_OK;
+}

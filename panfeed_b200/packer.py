@@ -62,11 +62,10 @@ def presence_words(presab):
             np.arange(32, dtype=np.uint32)).sum(axis=1, dtype=np.uint64).astype(np.uint32)
 
 
-def pack_batch(packed_clusters, cluster_ids=None):
-    """-> (capi.HostBatch, seq_meta list, cluster idx list)."""
-    seq_bytes, lens = [], []
-    for pc in packed_clusters:
-        seq_bytes.extend(pc.seq_bytes)
+def pack_planes_numpy(seq_bytes):
+    """Reference implementation of the plane packing with numpy look-up tables (the product
+    uses the library's native packer, `capi.pack_sequences`; the tests compare the two).
+    -> (packed, base_off, amb_seq, amb_plane or None, amb_off)."""
     n_seqs = len(seq_bytes)
     lens = np.array([len(b) for b in seq_bytes], np.int64)
     padded = (lens + 63) // 64 * 64
@@ -101,6 +100,17 @@ def pack_batch(packed_clusters, cluster_ids=None):
         code2[bad] = 0
     packed = (code2.reshape(-1, 32).astype(np.uint64) << _SHIFT2).sum(
         axis=1, dtype=np.uint64)
+    return packed, offs[:-1].astype(np.uint64), amb_seq, amb_plane, amb_off
+
+
+def pack_batch(packed_clusters, cluster_ids=None):
+    """-> (capi.HostBatch, seq_meta list, cluster idx list)."""
+    seq_bytes = []
+    for pc in packed_clusters:
+        seq_bytes.extend(pc.seq_bytes)
+    n_seqs = len(seq_bytes)
+    lens = np.fromiter((len(b) for b in seq_bytes), np.int64, n_seqs)
+    packed, base_off, amb_seq, amb_plane, amb_off = capi.pack_sequences(seq_bytes)
 
     seqs = np.zeros(n_seqs, capi.SEQ_DTYPE)
     clusters = np.zeros(len(packed_clusters), capi.CLUSTER_DTYPE)
@@ -124,7 +134,7 @@ def pack_batch(packed_clusters, cluster_ids=None):
         meta.extend(pc.meta)
         ids.append(pc.idx)
         i += n
-    seqs["base_off"] = offs[:-1].astype(np.uint64)
+    seqs["base_off"] = base_off
     seqs["len"] = lens.astype(np.uint32)
     seqs["flags"] |= amb_seq.astype(np.uint32) * capi.PF_SEQ_AMBIGUOUS
     seqs["amb_off"] = amb_off
