@@ -246,6 +246,15 @@ int pf_format_positions(const pf_batch_result* result, uint32_t k, int canonical
                         const int32_t* seq_strand, char* out, uint64_t out_cap, uint64_t* out_len,
                         uint32_t n_threads);
 
+/* The hashes_to_patterns rows of n patterns (panfeed.py:183-187,217-223): ids (n x 24 chars,
+ * e.g. from pf_pattern_ids + base64), then per sample a tab and '0' / '1' — or nothing where
+ * present_words (n x present_stride words, bit s = sample s's cluster is present; NULL = all
+ * present) has a 0: the reference writes NaN cells as empty fields with --consider-missing. */
+int pf_format_patterns(const uint32_t* pattern_words, uint64_t n, uint32_t stride_words,
+                       uint32_t n_samples, const char* ids, const uint32_t* present_words,
+                       uint32_t present_stride, char* out, uint64_t out_cap, uint64_t* out_len,
+                       uint32_t n_threads);
+
 /* ---- native packer (host threads): ASCII sequences -> the planes of a pf_batch ----
  * What the feeder has after cutting (input.py:455-459: Seqinfo.sequence, upper case) goes into
  * the 2-bit plane; sequences holding N/IUPAC symbols are flagged and additionally packed into

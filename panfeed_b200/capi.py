@@ -109,7 +109,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_upload", "pf_execute", "pf_submit", "pf_collect",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
            "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream", "pf_format_positions",
-           "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit",
+           "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_export",
            "pf_exchange_unpack"]
@@ -143,6 +143,8 @@ def load():
     lib.pf_kmer_pattern_words.restype = u32
     lib.pf_maf_window.argtypes = [C.c_double, u32, C.POINTER(u32), C.POINTER(u32)]
     lib.pf_patterns_export.argtypes = [vp, C.c_int, u64, u64, vp]
+    lib.pf_format_patterns.argtypes = [vp, u64, u32, u32, C.c_char_p, vp, u32, C.c_char_p, u64,
+                                       C.POINTER(u64), u32]
     lib.pf_pack_plan.argtypes = [vp, u32, vp, C.POINTER(u64)]
     lib.pf_pack_2bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, u32]
     lib.pf_pack_4bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, C.POINTER(u64), C.POINTER(C.c_int)]
@@ -210,6 +212,30 @@ def pack_sequences(seq_bytes, n_threads=0):
         if rc != 0:
             raise PfError(rc, "pf_pack_4bit failed")
     return packed, base_off, is_amb.astype(bool), amb_plane, amb_off
+
+
+def format_patterns(words, n_samples, ids, present=None, n_threads=0):
+    """hashes_to_patterns text (bytes) of the patterns `words` ([n, >= W] uint32) with their
+    24-character ids; `present` ([n, >= W] uint32) marks the samples whose cell is not NaN."""
+    lib = load()
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    n = len(words)
+    if n == 0:
+        return b""
+    idb = b"".join(x if isinstance(x, bytes) else x.encode() for x in ids)
+    assert len(idb) == 24 * n
+    pres = None if present is None else np.ascontiguousarray(present, dtype=np.uint32)
+    need = C.c_uint64()
+    args = (words.ctypes.data, n, words.shape[1], int(n_samples), idb,
+            None if pres is None else pres.ctypes.data, 0 if pres is None else pres.shape[1])
+    rc = lib.pf_format_patterns(*args, None, 0, C.byref(need), int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_format_patterns (sizing) failed")
+    out = np.empty(int(need.value), np.uint8)
+    rc = lib.pf_format_patterns(*args, out.ctypes.data_as(C.c_char_p), out.size, C.byref(need), int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_format_patterns failed")
+    return out.tobytes()
 
 
 def format_positions(r, k, canonical, leads, seq_strand, n_threads=0):

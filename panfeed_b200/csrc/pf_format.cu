@@ -267,3 +267,55 @@ extern "C" int pf_pack_4bit(const char* ascii, const uint64_t* seq_off, uint32_t
   *n_amb_words = pos / 16;
   return PF_OK;
 }
+
+// ---------------------------------------------------------------------------
+// hashes_to_patterns rows (panfeed.py:183-187,217-223): id, then one field per sample:
+// '0' / '1', or empty where the vector holds NaN (cluster absent, --consider-missing).
+// ---------------------------------------------------------------------------
+extern "C" int pf_format_patterns(const uint32_t* pattern_words, uint64_t n, uint32_t stride_words,
+                                  uint32_t n_samples, const char* ids, const uint32_t* present_words,
+                                  uint32_t present_stride, char* out, uint64_t out_cap, uint64_t* out_len,
+                                  uint32_t n_threads) {
+  if (!out_len || (n && (!pattern_words || !ids)) || n_samples == 0) return PF_ERR_INVALID;
+  const uint32_t W = (n_samples + 31u) / 32u;
+  if (stride_words < W || (present_words && present_stride < W)) return PF_ERR_INVALID;
+  *out_len = 0;
+  if (n == 0) return PF_OK;
+  if (n >= (1ull << 32)) return PF_ERR_INVALID;
+  std::vector<uint64_t> len(n + 1, 0);
+  parallel_for((uint32_t)n, n_threads, [&](uint32_t a, uint32_t b) {
+    for (uint32_t i = a; i < b; ++i) {
+      uint64_t cells = n_samples;
+      if (present_words) {
+        cells = 0;
+        const uint32_t* pw = present_words + (size_t)i * present_stride;
+        for (uint32_t w = 0; w < W; ++w) {
+          uint32_t x = pw[w];
+          if (w == W - 1 && (n_samples & 31u)) x &= (1u << (n_samples & 31u)) - 1u;
+          cells += (uint64_t)__builtin_popcount(x);
+        }
+      }
+      len[i + 1] = 24 + (uint64_t)n_samples + cells + 1;
+    }
+  });
+  for (uint64_t i = 0; i < n; ++i) len[i + 1] += len[i];
+  *out_len = len[n];
+  if (!out) return PF_OK;
+  if (out_cap < len[n]) return PF_ERR_NOMEM;
+  parallel_for((uint32_t)n, n_threads, [&](uint32_t a, uint32_t b) {
+    for (uint32_t i = a; i < b; ++i) {
+      char* p = out + len[i];
+      memcpy(p, ids + (size_t)i * 24, 24);
+      p += 24;
+      const uint32_t* bits = pattern_words + (size_t)i * stride_words;
+      const uint32_t* pw = present_words ? present_words + (size_t)i * present_stride : nullptr;
+      for (uint32_t s = 0; s < n_samples; ++s) {
+        *p++ = '\t';
+        if (pw && !((pw[s >> 5] >> (s & 31u)) & 1u)) continue;          // NaN: empty field
+        *p++ = ((bits[s >> 5] >> (s & 31u)) & 1u) ? '1' : '0';
+      }
+      *p++ = '\n';
+    }
+  });
+  return PF_OK;
+}

@@ -106,32 +106,6 @@ class PatternStore:
             self.ctx = None
 
 
-def _expand_bits(words, S):
-    """uint32 [n, W] -> uint8 [n, S] of 0/1."""
-    b = np.unpackbits(np.ascontiguousarray(words).view(np.uint8), axis=1, bitorder="little")
-    return b[:, :S]
-
-
-def _pattern_lines(ids, cells, nan_mask):
-    """hashes_to_patterns rows: id + one '0'/'1' (or empty for NaN) per sample."""
-    n, S = cells.shape
-    if n == 0:
-        return ""
-    if nan_mask is None:
-        # fixed layout: id(24) \t c0 \t c1 ... \t c(S-1) \n
-        fixed = np.empty((n, 24 + 2 * S + 1), np.uint8)
-        fixed[:, :24] = np.frombuffer("".join(ids).encode(), np.uint8).reshape(n, 24)
-        fixed[:, 24:24 + 2 * S:2] = ord("\t")
-        fixed[:, 25:25 + 2 * S:2] = cells + ord("0")
-        fixed[:, -1] = ord("\n")
-        return fixed.tobytes().decode()
-    lines = []
-    for pid, c, m in zip(ids, cells, nan_mask):
-        lines.append(pid + "\t" + "\t".join("" if isnan else str(v)
-                                            for v, isnan in zip(c.tolist(), m.tolist())) + "\n")
-    return "".join(lines)
-
-
 def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
     """One GPU batch -> (kmers.tsv text, hashes_to_patterns text, per-cluster
     kmers_to_hashes texts)."""
@@ -143,7 +117,6 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
     pat_text = []
     new_cp = r["new_cluster_patterns"]
     if len(new_cp):
-        cells = _expand_bits(new_cp, S)
         new_ids = [x.decode() for x in ctx.pattern_ids(True, r["cluster_pattern_base"], len(new_cp))]
         fresh = []
         for pid in new_ids:
@@ -152,15 +125,13 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
         store.cluster_ids += new_ids
         store.cluster_bits += [w for w in new_cp]
         sel = np.array(fresh, bool)
-        pat_text.append(_pattern_lines([p for p, f in zip(new_ids, fresh) if f], cells[sel], None))
+        pat_text.append(capi.format_patterns(new_cp[sel], S, [p for p, f in zip(new_ids, fresh) if f]).decode())
     new_kp = r["new_kmer_patterns"]
     if len(new_kp):
         W = (S + 31) // 32
-        cells = _expand_bits(new_kp[:, :W], S)
-        nan_mask = None
-        if consider_missing:
-            present = _expand_bits(np.stack([store.cluster_bits[c] for c in new_kp[:, W]]), S)
-            nan_mask = present == 0
+        present = None
+        if consider_missing:      # NaN cells = samples whose cluster is absent (the key's last word
+            present = np.stack([store.cluster_bits[c] for c in new_kp[:, W]])   # names that cluster pattern)
         new_ids = [x.decode() for x in ctx.pattern_ids(False, r["kmer_pattern_base"], len(new_kp))]
         fresh = []
         for pid in new_ids:
@@ -168,8 +139,8 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
             store.seen.add(pid)
         store.kmer_ids += new_ids
         sel = np.array(fresh, bool)
-        pat_text.append(_pattern_lines([p for p, f in zip(new_ids, fresh) if f], cells[sel],
-                                       None if nan_mask is None else nan_mask[sel]))
+        pat_text.append(capi.format_patterns(new_kp[sel], S, [p for p, f in zip(new_ids, fresh) if f],
+                                             None if present is None else present[sel]).decode())
 
     # ---- kmers_to_hashes rows, cluster by cluster ------------------------------
     kmer_ids = np.array(store.kmer_ids, dtype="S24") if store.kmer_ids else np.zeros(0, "S24")

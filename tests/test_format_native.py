@@ -77,3 +77,26 @@ def test_native_position_rows_empty_and_bad_range():
          "pos_contig_start": np.zeros(0, np.int32), "pos_gene_start": np.zeros(0, np.int32),
          "pos_flags": np.zeros(0, np.uint8)}
     assert capi.format_positions(r, 31, True, [], []) == b""
+
+
+@pytest.mark.parametrize("S", [1, 31, 32, 33, 500, 1300])
+@pytest.mark.parametrize("with_nan", [False, True])
+def test_native_pattern_rows_match_python(S, with_nan):
+    """pf_format_patterns against the reference's join (panfeed.py:183-187,217-223)."""
+    rng = np.random.default_rng(S + with_nan)
+    n, W = 300, (S + 31) // 32
+    bits = rng.integers(0, 2, (n, S)).astype(np.uint8)
+    pres = rng.integers(0, 2, (n, S)).astype(np.uint8) if with_nan else np.ones((n, S), np.uint8)
+    bits &= pres                                   # a k-mer's bits are a subset of the presence
+
+    def words(m):
+        pad = np.zeros((n, W * 32), np.uint8)
+        pad[:, :S] = m
+        return np.packbits(pad.reshape(n, W, 32), axis=2, bitorder="little").view(np.uint32).reshape(n, W)
+
+    ids = ["%024d" % i for i in range(n)]
+    got = capi.format_patterns(np.hstack([words(bits), np.full((n, 1), 7, np.uint32)]), S, ids,
+                               words(pres) if with_nan else None, n_threads=3)
+    want = "".join(pid + "\t" + "\t".join("" if not p else str(int(v)) for v, p in zip(b, pr)) + "\n"
+                   for pid, b, pr in zip(ids, bits, pres))
+    assert got.decode() == want
