@@ -16,12 +16,12 @@
 //                       W-word sample bitset.  The CTA ends by writing its distinct k-mers,
 //                       bitsets and popcounts ("partial rows") to a slab in HBM: ~1/30 of the
 //                       bytes the records would have taken, written once.
-//   kB1/kB2/kB3         a k-mer can start in two runs (indels, clamped flanks, paralogs,
+//   kB1/kB3             a k-mer can start in two runs (indels, clamped flanks, paralogs,
 //                       repeats), so the partial rows of one cluster are merged by FULL key in a
 //                       per-cluster open-addressing table in global memory: the first row of a
 //                       key owns it, later ones OR their bitset into the owner's; owners are
 //                       filtered on their popcount with the integer MAF window and emitted.
-//   kB4/kB5             with sample slices (S > 1024) kB1/kB2 merge per (cluster, slice); kB4
+//   kB4/kB5             with sample slices (S > 1024) kB1 merges per (cluster, slice); kB4
 //                       links the slices of a k-mer and sums their popcounts, kB5 filters on the
 //                       sum and assembles the full-width bitsets of the survivors.
 //
@@ -57,7 +57,7 @@ constexpr int kBlkThreads = 256;
 constexpr int kBlkWarps = kBlkThreads / 32;
 constexpr int kBlkRun = 16;                       // windows per task
 constexpr uint32_t kBlkOverflow = 0xffffffffu;    // slab count of a block that did not fit
-// slab_cnt[p]: popcount of partial row p as kA wrote it; after kB2: kCntDead = folded into an
+// slab_cnt[p]: popcount of partial row p as kA wrote it; after kB1: kCntDead = folded into an
 // earlier row of the same k-mer, kCntDirty = received another row's bits (recount from the row)
 constexpr uint32_t kCntDead = 0xfffffffeu, kCntDirty = 0xffffffffu;
 
@@ -488,11 +488,10 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
 // global memory (L2-resident while the cluster's slabs are being inserted): the first row of
 // a key becomes its owner, later rows OR their bitset into the owner's (rare), and the owners
 // are counted, filtered with the cluster's integer MAF window and written out.
-struct MergeEntry {        // 16 bytes; key == ~0 marks an empty slot
-  unsigned long long key;
-  uint32_t owner;          // partial row that claimed the slot
-  uint32_t reserved;
-};
+// Table entry: 64 bits = (32-bit fingerprint of the key) << 32 | index of the partial row that
+// owns the slot; all ones = empty.  A fingerprint match is confirmed on the owner's full key
+// (slab_keys), so nothing is ever merged on a hash.
+typedef unsigned long long MergeEntry;
 
 // one warp per (cluster, slice): partial rows -> table slots (eighths / 8 slots per row).  With
 // slices, table2_ctas[c] additionally sizes the cluster's cross-slice table in units of 256
@@ -532,14 +531,17 @@ __global__ void plan_expand_owner(const uint32_t* __restrict__ base, uint32_t n_
   for (uint32_t i = base[c] + lane_id(); i < base[c + 1]; i += 32) out[i] = c;
 }
 
-// kB1: one warp per slab; every partial key finds or claims its slot
+// kB1: one warp per slab; every partial key finds or claims its slot.  A row that meets an
+// earlier row of the same k-mer ORs its bitset into that one on the spot and is marked dead
+// (counted: distinct k-mers = partial rows - dead rows); the owner's stored popcount is dirty.
 __global__ void __launch_bounds__(256)
-kB1_insert(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_base,
+kB1_insert(const uint64_t* __restrict__ slab_keys, uint32_t* __restrict__ slab_rows,
+           uint32_t* __restrict__ slab_cnt, const uint32_t* __restrict__ slab_base,
            const uint32_t* __restrict__ slab_count, const uint32_t* __restrict__ item_cluster,
            uint32_t n_items /* incl. slices */, uint32_t n_slices,
            const uint32_t* __restrict__ table_base /* [n_clusters * n_slices + 1] */,
-           MergeEntry* __restrict__ table, uint32_t* __restrict__ pslot,
-           uint16_t* __restrict__ pslice /* null without slices */) {
+           MergeEntry* __restrict__ table, uint16_t* __restrict__ pslice /* null without slices */,
+           uint32_t WP, uint32_t* __restrict__ counters) {
   const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (item >= n_items) return;
   const uint32_t n = slab_count[item];
@@ -552,38 +554,33 @@ kB1_insert(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ 
   if (pslice)
     for (uint32_t i = lane_id(); i < n; i += 32) pslice[base + i] = (uint16_t)slice;
   for (uint32_t i = lane_id(); i < n; i += 32) {
-    const uint64_t key = slab_keys[base + i];
-    uint32_t s = __umulhi((uint32_t)(mix64(key) >> 32), ts);
+    const uint32_t p = base + i;
+    const uint64_t key = slab_keys[p];
+    const uint64_t mixed = mix64(key);
+    const uint32_t fp = (uint32_t)mixed;
+    const MergeEntry mine = ((MergeEntry)fp << 32) | p;
+    uint32_t s = __umulhi((uint32_t)(mixed >> 32), ts);
     for (;;) {
-      MergeEntry* e = table + tb + s;
-      const unsigned long long old = atomicCAS(&e->key, ~0ull, (unsigned long long)key);
-      if (old == ~0ull) { e->owner = base + i; break; }
-      if (old == key) break;
+      const MergeEntry old = atomicCAS(&table[tb + s], ~0ull, mine);
+      if (old == ~0ull) break;                              // this row owns the k-mer
+      if ((uint32_t)(old >> 32) == fp) {
+        const uint32_t q = (uint32_t)old;
+        if (slab_keys[q] == key) {                          // an earlier row of the same k-mer
+          const uint32_t* src = slab_rows + (size_t)p * WP;
+          uint32_t* dst = slab_rows + (size_t)q * WP;
+          for (uint32_t w = 0; w < WP; ++w) {
+            const uint32_t x = src[w];
+            if (x) atomicOr(dst + w, x);
+          }
+          slab_cnt[p] = kCntDead;
+          slab_cnt[q] = kCntDirty;
+          atomicAdd(&counters[LC_RESCUE], 1u);              // (the rescue counter is free again after kA)
+          break;
+        }
+      }
       if (++s == ts) s = 0;
     }
-    pslot[base + i] = tb + s;
   }
-}
-
-// kB2: one thread per partial row; a row that does not own its slot ORs its bitset into the
-// owner's and is marked dead (counted: distinct k-mers = partial rows - dead rows)
-__global__ void __launch_bounds__(256)
-kB2_fold(uint32_t n_partials, const uint32_t* __restrict__ pslot, const MergeEntry* __restrict__ table,
-         uint32_t* __restrict__ slab_rows, uint32_t* __restrict__ slab_cnt, uint32_t WP,
-         uint32_t* __restrict__ counters) {
-  const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_partials) return;
-  const uint32_t o = table[pslot[p]].owner;
-  if (o == p) return;
-  const uint32_t* src = slab_rows + (size_t)p * WP;
-  uint32_t* dst = slab_rows + (size_t)o * WP;
-  for (uint32_t w = 0; w < WP; ++w) {
-    const uint32_t x = src[w];
-    if (x) atomicOr(dst + w, x);
-  }
-  slab_cnt[p] = kCntDead;
-  slab_cnt[o] = kCntDirty;
-  atomicAdd(&counters[LC_RESCUE], 1u);      // (the rescue counter is free again after kA)
 }
 
 // kB3: one warp per slab; owners are counted, filtered and written out as rows.  Rows are
@@ -691,7 +688,7 @@ kB3_emit(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ sl
 
 // ---------------------------------------------------------------------------
 // sample slices: a k-mer's bitset is spread over up to n_slices partial rows (one per slice,
-// after kB1/kB2 merged the rows of the same slice).  kB4 links them per k-mer in a cross-slice
+// after kB1 merged the rows of the same slice).  kB4 links them per k-mer in a cross-slice
 // table of the cluster and sums the popcounts; kB5 applies the MAF window to the sum and
 // assembles the full-width bitsets of the survivors.
 // ---------------------------------------------------------------------------

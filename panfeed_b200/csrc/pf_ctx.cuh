@@ -175,7 +175,7 @@ struct pf_ctx : BatchState {
   uint64_t partials_last = 0;
   bool used_block = false;       // the last batch went through kA/kB
   DevBuf d_slab_base, d_slab_count, d_slab_keys, d_slab_rows,
-      d_group_base /* merge-table offsets per (cluster, slice) */, d_mtable, d_pslot,
+      d_group_base /* merge-table offsets per (cluster, slice) */, d_mtable,
       d_table2_base, d_table2, d_next, d_pslice, d_cta_cluster, d_slab_cnt, d_rescue[2];
   PatternSpace kp, cp;     // k-mer patterns, cluster patterns
   // pinned results

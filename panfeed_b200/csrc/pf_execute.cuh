@@ -422,7 +422,7 @@ int launch_block_aggregate(pf_ctx* ctx, const uint32_t* items, uint32_t n, uint3
   return PF_OK;
 }
 
-// kB1..kB3 (kB1, kB2, kB4, kB5 with sample slices) over the `n_partials` partial rows kA left
+// kB1 + kB3 (kB1, kB4, kB5 with sample slices) over the `n_partials` partial rows kA left
 int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
   if (ctx->n_items == 0 || n_partials == 0) return PF_OK;
   cudaStream_t st = ctx->stream;
@@ -447,25 +447,22 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
   const uint64_t n_slots = ((uint64_t)n_partials * eighths + 7) / 8 + 3ull * n_cs + 16;   // >= sum of ceil(p e / 8) + 2
   if (n_slots >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "too many partial rows for one batch; split it");
   TRY(dev_ensure(ctx, ctx->d_mtable, n_slots * sizeof(MergeEntry)));
-  TRY(dev_ensure(ctx, ctx->d_pslot, (size_t)n_partials * 4));
   if (ns > 1) TRY(dev_ensure(ctx, ctx->d_pslice, (size_t)n_partials * 2));
   CU(cudaMemsetAsync(ctx->d_mtable.p, 0xff, n_slots * sizeof(MergeEntry), st));
+  CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));     // kB1 counts the folded rows there
   const uint32_t g0 = cdiv((uint64_t)n_it * 32, 256);
-  kB1_insert<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_base.as<uint32_t>(),
+  kB1_insert<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
+                                 ctx->d_slab_cnt.as<uint32_t>(), ctx->d_slab_base.as<uint32_t>(),
                                  ctx->d_slab_count.as<uint32_t>(), ctx->d_item_cluster.as<uint32_t>(), n_it, ns,
                                  ctx->d_group_base.as<uint32_t>(), ctx->d_mtable.as<MergeEntry>(),
-                                 ctx->d_pslot.as<uint32_t>(), ns > 1 ? ctx->d_pslice.as<uint16_t>() : nullptr);
-  CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));     // kB2 counts the folded rows there
-  kB2_fold<<<cdiv(n_partials, 256), 256, 0, st>>>(n_partials, ctx->d_pslot.as<uint32_t>(),
-                                                  ctx->d_mtable.as<MergeEntry>(), ctx->d_slab_rows.as<uint32_t>(),
-                                                  ctx->d_slab_cnt.as<uint32_t>(), WP, counters + C_LOCAL);
+                                 ns > 1 ? ctx->d_pslice.as<uint16_t>() : nullptr, WP, counters + C_LOCAL);
   const uint32_t cap = (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu);
   if (ns == 1) {
     kB3_emit<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
                                  ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(),
                                  ctx->d_item_cluster.as<uint32_t>(), ctx->n_items, ctx->d_slab_cnt.as<uint32_t>(),
                                  ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL, ctx->W, WP);
-    ctx->launches += 3;
+    ctx->launches += 2;
     CU(cudaGetLastError());
     return PF_OK;
   }
@@ -495,7 +492,7 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
                                      ctx->d_next.as<uint32_t>(), ctx->d_pslice.as<uint16_t>(),
                                      ctx->d_slab_rows.as<uint32_t>(), ctx->d_clusters.as<ClusterDev>(), ro, cap,
                                      counters + C_LOCAL, ctx->W, ctx->Ws, WP);
-  ctx->launches += 7;
+  ctx->launches += 6;
   CU(cudaGetLastError());
   return PF_OK;
 }
