@@ -451,7 +451,7 @@ def main():
                     "partial_rows": st["partial_rows"], "writes_GB": partial_bytes / 1e9,
                     "alg_GBps_k1_k2_k3read_declared": (k1_bytes + alg["k2_sort_declared_8_passes"] + R_BYTES * M) /
                     stage_ms["ms_sort"] / 1e6},
-                "kB_merge(kB1 insert + kB2 fold + kB3 emit, incl. host sync)": {
+                "kB_merge(kB1 insert/fold + kB3 emit, incl. host sync)": {
                     "ms": k3_ms, "alg_bytes": 2 * partial_bytes + 12 * U + rows * W4,
                     "alg_GBps": (2 * partial_bytes + 12 * U + rows * W4) / k3_ms / 1e6},
                 "k4_dedup": k4_stage,

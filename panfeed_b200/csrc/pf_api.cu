@@ -14,6 +14,8 @@
 #include <chrono>
 #include <cstring>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>

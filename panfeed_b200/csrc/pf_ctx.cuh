@@ -106,9 +106,9 @@ enum Ev { EV_START, EV_EXTRACT, EV_HIST, EV_SORT, EV_MARK, EV_COUNTED, EV_REDUCE
 }  // namespace
 
 // Everything that belongs to ONE batch of whole clusters: what pf_upload builds, the record /
-// row buffers of that batch and its result arrays on the device.  A context holds two of these
-// so that the upload of sub-batch j+1 and the D2H of sub-batch j-1 can overlap the kernels of
-// sub-batch j (pf_submit on a large batch; see submit_pipelined).
+// row buffers of that batch and its result arrays on the device.  A context holds three of these
+// so that the uploads of sub-batches j+1 and j+2 and the D2H of sub-batch j-1 can overlap the
+// kernels of sub-batch j (pf_submit on a large batch; see submit_pipelined).
 struct BatchState {
   bool have_batch = false, executed = false;
   uint32_t n_seqs = 0, n_clusters = 0, n_wide_seqs = 0;
@@ -131,7 +131,113 @@ struct BatchState {
   bool rows_prefetched = false;
   uint64_t row_cap = 0;          // capacity of the row arrays above
   cudaEvent_t ev[EV_COUNT]{};    // stage timestamps of the batch's pf_execute
+  cudaEvent_t ev_h2d[2]{};       // around the batch's H2D
+  // pipelined submit: the upload has been enqueued / the kernels are done with the slot's inputs /
+  // the slot's result arrays have left the device
+  cudaEvent_t ev_up_done = nullptr, ev_exec_end = nullptr, ev_out_done = nullptr;
   PinBuf h_done;                 // pinned mirror of the batch's new k-mer pattern count (K4)
+};
+
+
+// Host worker threads that stay alive with the context: the per-sequence planning of an upload
+// runs on them (a std::thread per chunk and phase cost more than the planning of a sub-batch),
+// and one of them enqueues the uploads of the pipelined submit.
+class WorkerPool {
+ public:
+  ~WorkerPool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_go_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // fn(t) for t in [0, n), on up to n - 1 workers and the calling thread; returns when all ran
+  void parallel(unsigned n, const std::function<void(unsigned)>& fn) {
+    if (n <= 1) { if (n) fn(0); return; }
+    std::lock_guard<std::mutex> one(call_mu_);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      while (th_.size() + 1 < n) th_.emplace_back([this]() { worker(); });
+      fn_ = &fn; n_tasks_ = n; next_ = 0; done_ = 0; ++gen_;
+    }
+    cv_go_.notify_all();
+    run_tasks();
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&]() { return done_ == n_tasks_; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void run_tasks() {
+    std::unique_lock<std::mutex> lk(mu_);
+    while (fn_ && next_ < n_tasks_) {
+      const unsigned t = next_++;
+      const std::function<void(unsigned)>* f = fn_;
+      lk.unlock();
+      (*f)(t);
+      lk.lock();
+      if (++done_ == n_tasks_) cv_done_.notify_all();
+    }
+  }
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_go_.wait(lk, [&]() { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+      }
+      run_tasks();
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_, call_mu_;
+  std::condition_variable cv_go_, cv_done_;
+  const std::function<void(unsigned)>* fn_ = nullptr;
+  unsigned n_tasks_ = 0, next_ = 0, done_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
+// One thread that runs one job at a time, started and joined by its owner.
+class AsyncWorker {
+ public:
+  ~AsyncWorker() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+    cv_.notify_all();
+    if (th_.joinable()) th_.join();
+  }
+  void start(std::function<void()> job) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&]() { return !busy_; });
+    if (!th_.joinable()) th_ = std::thread([this]() { loop(); });
+    job_ = std::move(job);
+    busy_ = true;
+    cv_.notify_all();
+  }
+  void join() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&]() { return !busy_; });
+  }
+
+ private:
+  void loop() {
+    std::unique_lock<std::mutex> lk(mu_);
+    for (;;) {
+      cv_.wait(lk, [&]() { return stop_ || busy_; });
+      if (stop_) return;
+      std::function<void()> job = std::move(job_);
+      lk.unlock();
+      job();
+      lk.lock();
+      busy_ = false;
+      cv_.notify_all();
+    }
+  }
+  std::thread th_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::function<void()> job_;
+  bool busy_ = false, stop_ = false;
 };
 
 struct pf_ctx : BatchState {
@@ -145,8 +251,10 @@ struct pf_ctx : BatchState {
   uint32_t W = 0, Wk = 0;
   std::unordered_map<uint32_t, std::pair<uint32_t, uint32_t>> maf_cache;
   std::mutex maf_mu;       // the upload helper thread of the pipelined submit shares the cache
+  WorkerPool pool;         // planning threads
+  AsyncWorker uploader;    // enqueues the uploads of the pipelined submit
 
-  BatchState alt;          // the other batch slot (pipelined submit)
+  BatchState alt, alt2;    // the other batch slots (pipelined submit)
   DevBuf d_counters;       // u32[C_COUNT]: tickets, n_runs, errors, totals
   PinBuf h_counters;
   DevBuf d_bsum;
@@ -183,7 +291,7 @@ struct pf_ctx : BatchState {
   PinBuf r_new_kp, r_new_cp, r_pos_kmer, r_pos_seq, r_pos_cstart, r_pos_gstart, r_pos_flags,
       r_pos_wide;
   PinBuf r_wrow_cluster, r_wrow_count, r_wrow_pattern;   // pipelined submit: wide rows apart
-  cudaEvent_t ev_h2d[2]{}, ev_d2h[2]{};
+  cudaEvent_t ev_d2h[2]{};
   pf_stats stats{};
   // the k-mer pattern count of the last pf_execute is folded into kp.n lazily (its K4 may still run)
   bool kp_pending = false;
@@ -202,9 +310,10 @@ struct pf_ctx : BatchState {
   uint32_t pipe_clusters = 0;
   uint64_t pipe_kp_base = 0, pipe_cp_base = 0, pipe_kp_copied = 0;
   uint64_t pipe_row_cap = 0, pipe_wide_cap = 0;
-  cudaEvent_t ev_up[2]{}, ev_exec_end[2]{}, ev_out_done[2]{}, ev_pipe[2]{};
+  cudaEvent_t ev_pipe[2]{};
   uint32_t pipe_min_seqs = 200000;   // batches with fewer sequences are not split
   uint32_t pipe_target_seqs = 262144;   // sequences per sub-batch
+  uint32_t pipe_first_seqs = 98304;     // ... of the first one (its upload is not hidden)
 };
 
 namespace {

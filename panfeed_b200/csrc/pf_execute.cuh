@@ -220,7 +220,7 @@ void fill_timings(pf_ctx* ctx, const BatchState* slot = nullptr) {
   const BatchState& B = slot ? *slot : *ctx;
   pf_stats& s = ctx->stats;
   auto ms = [](cudaEvent_t a, cudaEvent_t b) { float m = 0; if (cudaEventElapsedTime(&m, a, b) != cudaSuccess) { cudaGetLastError(); m = 0; } return m; };
-  s.ms_h2d = ms(ctx->ev_h2d[0], ctx->ev_h2d[1]);
+  s.ms_h2d = ms(B.ev_h2d[0], B.ev_h2d[1]);
   s.ms_extract = ms(B.ev[EV_START], B.ev[EV_EXTRACT]);
   s.ms_hist = ms(B.ev[EV_EXTRACT], B.ev[EV_HIST]);
   s.ms_sort = ms(B.ev[EV_HIST], B.ev[EV_SORT]);
@@ -356,10 +356,10 @@ int plan_blocks(pf_ctx* ctx, BatchState& B, cudaStream_t st, bool sync) {
   return PF_OK;
 }
 // after the stream has passed plan_blocks: the item -> cluster map
-int plan_blocks_finish(pf_ctx* ctx, BatchState& B, cudaStream_t st) {
+int plan_blocks_finish(pf_ctx* ctx, BatchState& B, cudaStream_t st, bool sync) {
   const uint32_t nc = B.n_clusters;
   if (nc == 0 || B.n_seqs == 0) return PF_OK;
-  CU(cudaStreamSynchronize(st));
+  if (sync) CU(cudaStreamSynchronize(st));     // (else the caller has waited for plan_blocks)
   B.n_items = B.h_plan.as<uint32_t>()[0];
   TRY(dev_ensure(ctx, B.d_item_cluster, std::max<size_t>(1, B.n_items) * 4));
   plan_expand_owner<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(B.d_item_base.as<uint32_t>(), nc,

@@ -82,22 +82,26 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
   }
   cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
   cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking);
-  for (int i = 0; i < 2; ++i) {
-    cudaEventCreateWithFlags(&ctx->ev_up[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_exec_end[i], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ctx->ev_out_done[i], cudaEventDisableTiming);
-    cudaEventCreate(&ctx->ev_pipe[i]);
+  for (int i = 0; i < 2; ++i) cudaEventCreate(&ctx->ev_pipe[i]);
+  for (BatchState* bs : {static_cast<BatchState*>(ctx), &ctx->alt, &ctx->alt2}) {
+    cudaEventCreateWithFlags(&bs->ev_up_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&bs->ev_exec_end, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&bs->ev_out_done, cudaEventDisableTiming);
+    for (auto& ev : bs->ev) cudaEventCreate(&ev);
+    for (auto& ev : bs->ev_h2d) cudaEventCreate(&ev);
   }
   if (const char* e = getenv("PF_PREFETCH_ROWS")) ctx->prefetch_rows = atoi(e) != 0;
   if (const char* e = getenv("PF_PIPELINE_SEQS")) {      // 0 disables the pipelined submit
     const long v = atol(e);
     if (v <= 0) ctx->pipe_min_seqs = 0xffffffffu;
-    else { ctx->pipe_target_seqs = (uint32_t)std::max<long>(1024, v); ctx->pipe_min_seqs = ctx->pipe_target_seqs + ctx->pipe_target_seqs / 2; }
+    else {
+      ctx->pipe_target_seqs = (uint32_t)std::max<long>(1024, v);
+      ctx->pipe_min_seqs = ctx->pipe_target_seqs + ctx->pipe_target_seqs / 2;
+      ctx->pipe_first_seqs = std::max(1024u, ctx->pipe_target_seqs * 3 / 8);
+    }
   }
+  if (const char* e = getenv("PF_PIPELINE_FIRST")) { const long v = atol(e); if (v > 0) ctx->pipe_first_seqs = (uint32_t)std::max<long>(1024, v); }
   cudaEventCreateWithFlags(&ctx->ev_rows, cudaEventDisableTiming);
-  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
-  for (auto& ev : ctx->alt.ev) cudaEventCreate(&ev);
-  for (auto& ev : ctx->ev_h2d) cudaEventCreate(&ev);
   for (auto& ev : ctx->ev_d2h) cudaEventCreate(&ev);
   // opt in to > 48 KB dynamic shared memory for the sort passes
   cudaFuncSetAttribute(k2_onesweep_pass<uint64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -181,7 +185,10 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
   cudaDeviceSynchronize();
   auto fd = [](DevBuf& b) { if (b.p) cudaFree(b.p); b.p = nullptr; b.cap = 0; };
   auto fp = [](PinBuf& b) { if (b.p) cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; };
-  for (BatchState* bs : {static_cast<BatchState*>(ctx), &ctx->alt}) {
+  for (BatchState* bs : {static_cast<BatchState*>(ctx), &ctx->alt, &ctx->alt2}) {
+    for (cudaEvent_t* e : {&bs->ev_up_done, &bs->ev_exec_end, &bs->ev_out_done, &bs->ev_h2d[0], &bs->ev_h2d[1]})
+      if (*e) cudaEventDestroy(*e);
+    for (auto& ev : bs->ev) if (ev) cudaEventDestroy(ev);
     for (DevBuf* b : {&bs->d_bases, &bs->d_amb, &bs->d_ambbits, &bs->d_seqs, &bs->d_clusters, &bs->d_wide_seqs,
                       &bs->d_presence, &bs->d_row_cluster, &bs->d_row_kmer, &bs->d_wrow_kmer, &bs->d_row_count,
                       &bs->d_row_pattern, &bs->d_cl_pattern, &bs->d_pos_kmer, &bs->d_pos_seq, &bs->d_pos_cstart,
@@ -215,16 +222,8 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->r_pos_seq, &ctx->r_pos_cstart, &ctx->r_pos_gstart, &ctx->r_pos_flags, &ctx->r_pos_wide,
                     &ctx->r_wrow_cluster, &ctx->r_wrow_count, &ctx->r_wrow_pattern})
     fp(*b);
-  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
-  for (auto& ev : ctx->alt.ev) if (ev) cudaEventDestroy(ev);
-  for (auto& ev : ctx->ev_h2d) if (ev) cudaEventDestroy(ev);
   for (auto& ev : ctx->ev_d2h) if (ev) cudaEventDestroy(ev);
-  for (int i = 0; i < 2; ++i) {
-    if (ctx->ev_up[i]) cudaEventDestroy(ctx->ev_up[i]);
-    if (ctx->ev_exec_end[i]) cudaEventDestroy(ctx->ev_exec_end[i]);
-    if (ctx->ev_out_done[i]) cudaEventDestroy(ctx->ev_out_done[i]);
-    if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);
-  }
+  for (int i = 0; i < 2; ++i) if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);
   if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
   if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

@@ -19,23 +19,32 @@ int pin_grow(pf_ctx* ctx, PinBuf& b, size_t need, size_t used) {
 }
 
 // cut a batch into sub-batches of whole clusters with about `target` sequences each
-std::vector<SubRange> split_batch(const pf_batch* b, uint32_t target) {
+// (`first` for the first and the last one: nothing runs under the upload of the first or under
+// the D2H of the last, so they are kept short)
+std::vector<SubRange> split_batch(const pf_batch* b, uint32_t target_all, uint32_t first) {
   std::vector<SubRange> subs;
   const uint32_t n = b->n_seqs;
+  first = std::min(first, target_all);
   uint32_t s0 = 0, c0 = 0;
   while (s0 < n) {
+    const uint64_t rem = n - s0;
+    uint64_t target = s0 == 0 ? first : target_all;
+    if (rem <= target + target / 2) {
+      // the tail: all of it, or all but a short last sub-batch
+      target = (s0 > 0 && rem >= 3ull * first) ? rem - first : rem;
+    }
     uint32_t s1 = n, c1 = b->n_clusters;
-    if ((uint64_t)s0 + target + target / 2 < n) {
+    if (target < rem) {
       // first sequence of the cluster that holds sequence s0 + target (clusters are sorted)
       const uint32_t c = b->seqs[s0 + target].cluster;
-      uint32_t lo = s0, hi = s0 + target;
+      uint32_t lo = s0, hi = s0 + (uint32_t)target;
       while (lo < hi) {
         const uint32_t mid = lo + (hi - lo) / 2;
         if (b->seqs[mid].cluster < c) lo = mid + 1; else hi = mid;
       }
       if (lo > s0) { s1 = lo; c1 = c; }
       else {            // one cluster longer than the target: take it whole
-        lo = s0 + target; hi = n;
+        lo = s0 + (uint32_t)target; hi = n;
         while (lo < hi) {
           const uint32_t mid = lo + (hi - lo) / 2;
           if (b->seqs[mid].cluster <= c) lo = mid + 1; else hi = mid;
@@ -60,14 +69,16 @@ std::vector<SubRange> split_batch(const pf_batch* b, uint32_t target) {
 void pipe_add_timings(pf_ctx* ctx, const BatchState* slot = nullptr) {
   fill_timings(ctx, slot);
   const pf_stats& t = ctx->stats;
-  const float v[10] = {t.ms_h2d, t.ms_extract, t.ms_hist, t.ms_sort, t.ms_mark, t.ms_count, t.ms_reduce,
+  // (the H2D time of a slot is added when its upload is waited for: by now the slot's H2D
+  //  events may belong to a later upload)
+  const float v[10] = {0.f, t.ms_extract, t.ms_hist, t.ms_sort, t.ms_mark, t.ms_count, t.ms_reduce,
                        t.ms_dedup, 0.f, 0.f};
   for (int i = 0; i < 10; ++i) ctx->pipe_ms[i] += v[i];
 }
 
 // D2H of the current slot's results behind everything it executed, appended to the pinned
 // result arrays of the pipelined submit
-int pipe_enqueue_results(pf_ctx* ctx, const SubRange& r, int slot) {
+int pipe_enqueue_results(pf_ctx* ctx, const SubRange& r) {
   cudaStream_t st = ctx->stream, cp = ctx->copy_stream;
   WidthState& N = ctx->nar;
   WidthState& Wd = ctx->wid;
@@ -120,7 +131,7 @@ int pipe_enqueue_results(pf_ctx* ctx, const SubRange& r, int slot) {
     if (ctx->n_pos_wide)
       TRY(d2h(ctx->r_pos_wide, ctx->pipe_pos_wide * 16, ctx->d_pos_wide.p, (size_t)ctx->n_pos_wide * 16));
   }
-  CU(cudaEventRecord(ctx->ev_out_done[slot], cp));
+  CU(cudaEventRecord(ctx->ev_out_done, cp));
   ctx->pipe_rows += nr;
   ctx->pipe_wide_rows += nw;
   ctx->pipe_pos += ctx->n_pos;
@@ -147,15 +158,21 @@ int pipe_copy_new_patterns(pf_ctx* ctx) {
   return PF_OK;
 }
 
-// pf_submit of a large batch: sub-batches of whole clusters flow through two batch slots, so
-// that the H2D of sub-batch j+1 (up_stream) and the D2H of sub-batch j-1 (copy_stream) run
-// under the kernels of sub-batch j (stream).  The pattern tables are shared, K4 of the
-// sub-batches is ordered by the compute stream, so pattern ids are those of one big batch.
+// pf_submit of a large batch: sub-batches of whole clusters flow through three batch slots, so
+// that the H2D of sub-batches j+1 and j+2 (up_stream, enqueued by a helper thread) and the D2H
+// of sub-batch j-1 (copy_stream) run under the kernels of sub-batch j (stream).  The pattern
+// tables are shared, K4 of the sub-batches is ordered by the compute stream, so pattern ids are
+// those of one big batch.
+//
+// Slots: *ctx holds sub-batch j; `nx` the uploaded (or uploading) j+1; `nx2` is where j+2 goes —
+// the slot sub-batch j-1 ran in.  After the kernels of j are enqueued, *ctx and *nx swap
+// contents (the helper that filled *nx has been joined; the one filling *nx2 is not touched).
 int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>& subs) {
   cudaStream_t st = ctx->stream, up = ctx->up_stream;
   TRY(finalize_pending(ctx));
   ctx->executed = false;
   ctx->alt.executed = false;
+  ctx->alt2.executed = false;
   ctx->pipe_rows = ctx->pipe_wide_rows = ctx->pipe_pos = ctx->pipe_pos_wide = 0;
   ctx->pipe_clusters = 0;
   ctx->pipe_kp_base = ctx->kp.n;
@@ -171,64 +188,82 @@ int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>
     TRY(pin_grow(ctx, ctx->r_row_pattern, est * 4, 0));
     TRY(pin_grow(ctx, ctx->r_row_kmer, est * 8, 0));
   }
-  auto swap_slots = [&]() { std::swap(static_cast<BatchState&>(*ctx), ctx->alt); };
   struct Guard { pf_ctx* c; ~Guard() { c->pipe_mode = false; } } guard{ctx};
   ctx->pipe_mode = true;
-  int cur = 0;
   const size_t J = subs.size();
   ctx->pipe_subs = (uint32_t)J;
   static const bool dbg = getenv("PF_DEBUG_PIPE") != nullptr;
   auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_begin = now();
-  double t_up = 0, t_ex = 0, t_out = 0, t_fin = 0;
+  double t_up = 0, t_ex = 0, t_out = 0, t_fin = 0, t_join = 0;
   CU(cudaEventRecord(ctx->ev_pipe[0], st));
+  auto add_h2d = [&]() {
+    float m = 0;
+    if (cudaEventElapsedTime(&m, ctx->ev_h2d[0], ctx->ev_h2d[1]) == cudaSuccess) ctx->pipe_ms[0] += m;
+    else cudaGetLastError();
+  };
   TRY(upload_async(ctx, *ctx, b, subs[0], up));
-  TRY(upload_finish(ctx, *ctx, up));
-  for (size_t j = 0; j < J; ++j) {
-    // a helper thread validates, plans and uploads sub-batch j+1 into the other slot while
-    // this thread drives the kernels of sub-batch j (pf_execute blocks on its read-backs)
-    std::thread helper;
-    int up_rc = PF_OK;
-    if (j + 1 < J) {
-      // the kernels of the other slot's last occupant (sub-batch j-1) must be done with its
-      // inputs; its result arrays are still draining, but an upload does not touch those
-      CU(cudaStreamWaitEvent(up, ctx->ev_exec_end[cur ^ 1], 0));
-      helper = std::thread([&, j]() {
-        cudaSetDevice(ctx->device);
-        const double t0 = now();
-        up_rc = upload_async(ctx, ctx->alt, b, subs[j + 1], up);
-        t_up += now() - t0;
-      });
-    }
-    // this slot's previous rows must have left the device before they are overwritten
+  TRY(upload_finish_slot(ctx, *ctx, st));
+  add_h2d();
+
+  // One upload runs at a time (the context's uploader thread: validation, planning and the
+  // enqueue of the copies of ONE sub-batch), next to this thread driving the kernels
+  // (pf_execute blocks on its read-backs).  It is joined before the next one starts and before
+  // any return.
+  struct Helper {
+    AsyncWorker& w;
     int rc = PF_OK;
-    if (cudaStreamWaitEvent(st, ctx->ev_out_done[cur], 0) != cudaSuccess) rc = fail(ctx, PF_ERR_CUDA, "cudaStreamWaitEvent failed");
+    void join() { w.join(); }
+    ~Helper() { w.join(); }
+  } helper{ctx->uploader};
+  auto start_upload = [&](size_t j, BatchState* slot) -> int {
+    // the kernels of the slot's last occupant must be done with its inputs; its result arrays
+    // may still be draining, but an upload does not touch those
+    if (cudaStreamWaitEvent(up, slot->ev_exec_end, 0) != cudaSuccess) return fail(ctx, PF_ERR_CUDA, "cudaStreamWaitEvent failed");
+    helper.rc = PF_OK;
+    helper.w.start([&, j, slot]() {
+      cudaSetDevice(ctx->device);
+      const double t0 = now();
+      helper.rc = upload_async(ctx, *slot, b, subs[j], up);
+      t_up += now() - t0;
+    });
+    return PF_OK;
+  };
+  BatchState* nx = &ctx->alt;
+  BatchState* nx2 = &ctx->alt2;
+  if (J > 1) TRY(start_upload(1, nx));
+  for (size_t j = 0; j < J; ++j) {
     double t0 = now();
-    if (rc == PF_OK) rc = pf_execute(ctx);
-    t_ex += now() - t0;
-    if (rc == PF_OK && cudaEventRecord(ctx->ev_exec_end[cur], st) != cudaSuccess) rc = fail(ctx, PF_ERR_CUDA, "cudaEventRecord failed");
+    helper.join();                       // sub-batch j+1 is enqueued (started one iteration ago)
+    t_join += now() - t0;
+    if (helper.rc != PF_OK) return helper.rc;
+    if (j + 2 < J) TRY(start_upload(j + 2, nx2));
+    // this slot's previous rows must have left the device before they are overwritten
+    CU(cudaStreamWaitEvent(st, ctx->ev_out_done, 0));
     t0 = now();
-    if (rc == PF_OK) rc = pipe_enqueue_results(ctx, subs[j], cur);
+    TRY(pf_execute(ctx));
+    t_ex += now() - t0;
+    CU(cudaEventRecord(ctx->ev_exec_end, st));
+    t0 = now();
+    TRY(pipe_enqueue_results(ctx, subs[j]));
     t_out += now() - t0;
-    if (helper.joinable()) helper.join();
-    if (rc != PF_OK) return rc;
-    if (up_rc != PF_OK) return up_rc;
     t0 = now();
     // pf_execute folded sub-batch j-1's pattern count in before its own K4: those patterns are
-    // final, and so are the other slot's stage timestamps
+    // final, and so are the stage timestamps of the slot it ran in (now *nx2)
     TRY(pipe_copy_new_patterns(ctx));
-    if (j > 0) pipe_add_timings(ctx, &ctx->alt);
+    if (j > 0) pipe_add_timings(ctx, nx2);
     if (j + 1 < J) {
       ctx->executed = false;
-      swap_slots();
-      cur ^= 1;
-      TRY(upload_finish(ctx, *ctx, up));
+      std::swap(static_cast<BatchState&>(*ctx), *nx);     // *ctx: sub-batch j+1; *nx: free (j's slot)
+      std::swap(nx, nx2);                                  // j+2 is (being) uploaded into the new nx
+      TRY(upload_finish_slot(ctx, *ctx, st));
+      add_h2d();
       t_fin += now() - t0;
     }
   }
   if (dbg)
-    fprintf(stderr, "[pf] pipeline: %zu sub-batches, host ms: total %.2f  upload_async %.2f  execute %.2f  enqueue %.2f  finish %.2f\n",
-            J, now() - t_begin, t_up, t_ex, t_out, t_fin);
+    fprintf(stderr, "[pf] pipeline: %zu sub-batches, host ms: total %.2f  upload_async %.2f  join %.2f  execute %.2f  enqueue %.2f  finish %.2f\n",
+            J, now() - t_begin, t_up, t_join, t_ex, t_out, t_fin);
   CU(cudaEventRecord(ctx->ev_pipe[1], st));
   ctx->pipe_pending = true;
   return PF_OK;
@@ -242,7 +277,7 @@ extern "C" int pf_submit(pf_ctx* ctx, const pf_batch* batch) {
   if (ctx->pipe_pending) return fail(ctx, PF_ERR_STATE, "pf_submit: results of the previous pf_submit were not collected");
   if (batch->n_seqs >= ctx->pipe_min_seqs && batch->n_amb_words == 0 && batch->seqs && batch->n_clusters > 1) {
     CU(cudaSetDevice(ctx->device));
-    const std::vector<SubRange> subs = split_batch(batch, ctx->pipe_target_seqs);
+    const std::vector<SubRange> subs = split_batch(batch, ctx->pipe_target_seqs, ctx->pipe_first_seqs);
     if (subs.size() > 1) return submit_pipelined(ctx, batch, subs);
   }
   ctx->pipe_subs = 1;
@@ -261,6 +296,7 @@ int collect_pipelined(pf_ctx* ctx, pf_batch_result* out) {
   ctx->kp_pending = false;
   ctx->executed = false;
   ctx->alt.executed = false;
+  ctx->alt2.executed = false;
   ctx->pipe_pending = false;
   pipe_add_timings(ctx);
   const uint64_t new_kp = ctx->kp.n - ctx->pipe_kp_base, new_cp = ctx->cp.n - ctx->pipe_cp_base;

@@ -80,7 +80,7 @@ int plan_tiles(pf_ctx* ctx, WidthState& w, const std::vector<std::pair<uint32_t,
 
 namespace {
 int plan_blocks(pf_ctx* ctx, BatchState& B, cudaStream_t st, bool sync);
-int plan_blocks_finish(pf_ctx* ctx, BatchState& B, cudaStream_t st);
+int plan_blocks_finish(pf_ctx* ctx, BatchState& B, cudaStream_t st, bool sync = true);
 int scan_inplace(pf_ctx* ctx, uint32_t* data, uint32_t n, uint32_t* total_dev, cudaStream_t st = nullptr, DevBuf* scratch = nullptr);
 }
 
@@ -92,6 +92,7 @@ struct SubRange { uint32_t s0, s1, c0, c1; uint64_t w0, w1, a0, a1; };
 // Validate + plan + H2D of the sub-range into the CURRENT batch slot, all asynchronous on `st`
 // (the caller's buffers must stay valid until `st` has passed).  upload_finish completes it.
 int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRange& r, cudaStream_t st) {
+  const double t_dbg_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   pf_batch view = *full;
   view.seqs = full->seqs ? full->seqs + r.s0 : nullptr;
   view.n_seqs = r.s1 - r.s0;
@@ -125,10 +126,13 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
   // the packed plane is the bulk of the transfer: start it before the host-side planning
   const size_t slack_words = 80;
   TRY(dev_ensure(ctx, B.d_bases, (b->n_words + slack_words) * 8));
-  CU(cudaEventRecord(ctx->ev_h2d[0], st));
+  CU(cudaEventRecord(B.ev_h2d[0], st));
   if (b->n_words) CU(cudaMemcpyAsync(B.d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync((char*)B.d_bases.p + b->n_words * 8, 0, slack_words * 8, st));
 
+  static const bool dbg_up = getenv("PF_DEBUG_PIPE") != nullptr;
+  auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_dbg0 = now_ms();
   // ---- planning, in parallel over chunks of sequences --------------------------------
   // phase A: validate + per-sequence sizes, per-chunk sums; phase B: prefix over chunks;
   // phase C: offsets.  Cluster ranges come from the first sequence of every cluster.
@@ -141,16 +145,11 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
     static const uint32_t host_thr = []() { const char* e = getenv("PF_HOST_THREADS"); const int v = e ? atoi(e) : 0;
                                             return v > 0 ? (uint32_t)v : 16u; }();
     const uint32_t n_thr = std::max(1u, std::min<uint32_t>(std::min(host_thr, std::thread::hardware_concurrency()),
-                                                           (n + 65535u) / 65536u));
+                                                           (n + 16383u) / 16384u));
     struct Part { uint64_t rec = 0, wrec = 0, pos = 0, pwide = 0, bases = 0; uint32_t wide = 0; std::string err; };
     std::vector<Part> parts(n_thr);
     const uint32_t per = (n + n_thr - 1) / std::max(1u, n_thr);
-    auto run = [&](auto&& fn) {
-      if (n_thr == 1) { fn(0u); return; }
-      std::vector<std::thread> th;
-      for (uint32_t t = 0; t < n_thr; ++t) th.emplace_back(fn, t);
-      for (auto& x : th) x.join();
-    };
+    auto run = [&](const std::function<void(uint32_t)>& fn) { ctx->pool.parallel(n_thr, fn); };
     auto errf = [](Part& p, const char* fmt, uint32_t i, uint32_t a2 = 0, uint32_t a3 = 0) {
       char buf[256];
       snprintf(buf, sizeof buf, fmt, i, a2, a3);
@@ -230,6 +229,7 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
       next_n = nr[c].first; next_w = wr[c].first;
     }
   }
+  const double t_dbg1 = now_ms();
   for (uint32_t c = 0; c < b->n_clusters; ++c) {
     uint32_t np = 0;
     for (uint32_t w = 0; w < W; ++w) {
@@ -265,6 +265,7 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
     d.lo = lo; d.hi = hi;
   }
 
+  const double t_dbg2 = now_ms();
   B.n_seqs = b->n_seqs; B.n_clusters = b->n_clusters; B.n_wide_seqs = n_wide;
   B.n_words = b->n_words; B.n_amb_words = n_wide ? b->n_amb_words : 0; B.n_bases = bases;
   B.n_pos = (uint32_t)pos; B.n_pos_wide = (uint32_t)pwide;
@@ -332,9 +333,13 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
     plan_seq_lite<<<cdiv(b->n_seqs, 256), 256, 0, st>>>(B.d_seqs.as<SeqDev>(), b->n_seqs, B.d_seq_lite.as<SeqLite>());
     ctx->launches++;
   }
-  CU(cudaEventRecord(ctx->ev_h2d[1], st));
+  CU(cudaEventRecord(B.ev_h2d[1], st));
   if (ctx->block_mode) TRY(plan_blocks(ctx, B, st, false));
+  CU(cudaEventRecord(B.ev_up_done, st));
   CU(cudaGetLastError());
+  if (dbg_up)
+    fprintf(stderr, "[pf] upload %u seqs: head %.3f  seq planning %.3f  clusters %.3f  enqueue %.3f ms\n", b->n_seqs,
+            t_dbg0 - t_dbg_in, t_dbg1 - t_dbg0, t_dbg2 - t_dbg1, now_ms() - t_dbg2);
   return PF_OK;
 }
 
@@ -343,6 +348,16 @@ int upload_finish(pf_ctx* ctx, BatchState& B, cudaStream_t up) {
   CU(cudaStreamSynchronize(up));
   if (ctx->block_mode) TRY(plan_blocks_finish(ctx, B, up));
   CU(cudaStreamSynchronize(up));
+  CU(cudaGetLastError());
+  B.have_batch = true;
+  return PF_OK;
+}
+// The same for a slot of the pipelined submit: waits for THAT upload only (later ones may be
+// queued behind it on the upload stream) and leaves the last planning kernels to the compute
+// stream, which runs the slot's kernels next.
+int upload_finish_slot(pf_ctx* ctx, BatchState& B, cudaStream_t compute) {
+  CU(cudaEventSynchronize(B.ev_up_done));
+  if (ctx->block_mode) TRY(plan_blocks_finish(ctx, B, compute, false));
   CU(cudaGetLastError());
   B.have_batch = true;
   return PF_OK;

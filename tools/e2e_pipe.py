@@ -6,7 +6,7 @@ from panfeed_b200 import capi
 S, C = 500, int(sys.argv[1]) if len(sys.argv) > 1 else 4000
 hb = capi.synth_batch(0, 20261020, S, C, total_clusters=C, gene_len=1200, pinned=True)
 ctx = capi.Context(31, S, maf=0.01)
-for rep in range(5):
+for rep in range(int(sys.argv[2]) if len(sys.argv) > 2 else 5):
     ctx.reset_patterns()
     t0 = time.perf_counter(); ctx.submit(hb); t1 = time.perf_counter()
     r = ctx.collect(copy=False); t2 = time.perf_counter()
