@@ -36,7 +36,7 @@ R_BYTES = 12                 # record: 8-byte key + 4-byte sample rank
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--samples", type=int, default=500)
@@ -59,25 +59,91 @@ def parse():
 # clocks
 # --------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and clock-event reasons of one GPU, sampled every 2 ms through NVML from a
+    thread of this process while the timed region runs (the timed region is tens of ms: an
+    `nvidia-smi -lms` child would not have printed its first line by the time it ends).
+    Falls back to `nvidia-smi -lms 20` when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device = device
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.f = None
+        self.thread = None
+        self.stop_flag = False
+        self.samples = []        # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self.nvml = None
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(device).uuid)
+                if not uuid.startswith("GPU-"):
+                    uuid = "GPU-" + uuid
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                idx = device
+                if vis:
+                    ent = vis.split(",")[device].strip()
+                    idx = int(ent) if ent.isdigit() else device
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((float(mhz), int(why)))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self.stop_flag = False
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.device)], stdout=self.f,
+                 "-lms", "20", "-i", str(self.device)], stdout=self.f,
                 stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["no samples"]}
+            names = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap),
+                     ("hw_power_brake_slowdown", nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown))
+            reasons = sorted({n for _, why in self.samples for n, bit in names if why & bit})
+            sm = [m for m, _ in self.samples]
+            return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": self.max_mhz,
+                    "reasons": reasons, "samples": len(sm), "source": "nvml, 2 ms period, timed region only"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -102,7 +168,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 # --------------------------------------------------------------------------
@@ -307,11 +373,11 @@ def main():
 
     # ---- value: batch resident in HBM -------------------------------------
     ctx.upload(hb)
+    sampler = ClockSampler(local)
     for _ in range(max(3, args.warmup)):
         step_resident()
     launches0 = ctx.stats()["total_launches"]
     barrier()
-    sampler = ClockSampler(local)
     sampler.start()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)

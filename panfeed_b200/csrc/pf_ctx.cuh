@@ -284,7 +284,9 @@ struct pf_ctx : BatchState {
   bool used_block = false;       // the last batch went through kA/kB
   DevBuf d_slab_base, d_slab_count, d_slab_keys, d_slab_rows,
       d_group_base /* merge-table offsets per (cluster, slice) */, d_mtable,
-      d_table2_base, d_table2, d_next, d_pslice, d_cta_cluster, d_slab_cnt, d_rescue[2];
+      d_table2_base, d_table2, d_next, d_pslice, d_cta_cluster, d_slab_cnt, d_rescue[2],
+      d_spill /* (cluster, slice) merged in the global table */;
+  uint32_t merge_slots = 49152;  // shared-memory merge table of kB1_local (PF_MERGE_SMEM_KB)
   PatternSpace kp, cp;     // k-mer patterns, cluster patterns
   // pinned results
   PinBuf r_row_cluster, r_row_kmer, r_wrow_kmer, r_row_count, r_row_pattern, r_cl_pattern;

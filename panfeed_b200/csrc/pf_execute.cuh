@@ -448,14 +448,24 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
   if (n_slots >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "too many partial rows for one batch; split it");
   TRY(dev_ensure(ctx, ctx->d_mtable, n_slots * sizeof(MergeEntry)));
   if (ns > 1) TRY(dev_ensure(ctx, ctx->d_pslice, (size_t)n_partials * 2));
-  CU(cudaMemsetAsync(ctx->d_mtable.p, 0xff, n_slots * sizeof(MergeEntry), st));
+  TRY(dev_ensure(ctx, ctx->d_spill, std::max<size_t>(1, n_cs)));
   CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));     // kB1 counts the folded rows there
+  // shared-memory merge per (cluster, slice); clusters too large for it clear their region of the
+  // global table (nothing else does) and are merged there by kB1_insert
+  kB1_local<<<n_cs, kMergeLocalThreads, merge_local_smem_bytes(ctx->merge_slots), st>>>(
+      ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(), ctx->d_slab_cnt.as<uint32_t>(),
+      ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(), ctx->d_item_base.as<uint32_t>(), ns,
+      ctx->d_group_base.as<uint32_t>(), ctx->d_mtable.as<MergeEntry>(),
+      ns > 1 ? ctx->d_pslice.as<uint16_t>() : nullptr, WP, counters + C_LOCAL, ctx->merge_slots,
+      ctx->d_spill.as<uint8_t>());
+  ctx->launches++;
   const uint32_t g0 = cdiv((uint64_t)n_it * 32, 256);
   kB1_insert<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
                                  ctx->d_slab_cnt.as<uint32_t>(), ctx->d_slab_base.as<uint32_t>(),
                                  ctx->d_slab_count.as<uint32_t>(), ctx->d_item_cluster.as<uint32_t>(), n_it, ns,
                                  ctx->d_group_base.as<uint32_t>(), ctx->d_mtable.as<MergeEntry>(),
-                                 ns > 1 ? ctx->d_pslice.as<uint16_t>() : nullptr, WP, counters + C_LOCAL);
+                                 ns > 1 ? ctx->d_pslice.as<uint16_t>() : nullptr, WP, counters + C_LOCAL,
+                                 ctx->d_spill.as<uint8_t>());
   const uint32_t cap = (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu);
   if (ns == 1) {
     kB3_emit<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),

@@ -161,6 +161,12 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
     ctx->blk_cap = cap;
     ctx->blk_cslots = cslots;
     if (p->k == 32 && !p->canonical) ctx->block_mode = false;   // all-T k-mer == the empty-slot mark
+    if (const char* e = getenv("PF_MERGE_SMEM_KB")) {       // 0: every cluster through the global table
+      const long kb = atol(e);
+      if (kb >= 0 && kb <= 216) ctx->merge_slots = (uint32_t)(kb * 256);
+    }
+    cudaFuncSetAttribute(kB1_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)merge_local_smem_bytes(ctx->merge_slots));
     cudaFuncSetAttribute(kA_block_aggregate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
     cudaFuncSetAttribute(kA_block_aggregate<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);
   }
@@ -211,7 +217,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->d_cl_rep, &ctx->d_cl_slot, &ctx->d_cl_winner, &ctx->d_digests, &ctx->d_slab_base,
                     &ctx->d_slab_count, &ctx->d_slab_keys, &ctx->d_slab_rows, &ctx->d_group_base, &ctx->d_mtable,
                     &ctx->d_rescue[0], &ctx->d_rescue[1], &ctx->d_table2_base, &ctx->d_table2,
-                    &ctx->d_next, &ctx->d_pslice, &ctx->d_cta_cluster, &ctx->d_slab_cnt})
+                    &ctx->d_next, &ctx->d_pslice, &ctx->d_cta_cluster, &ctx->d_slab_cnt, &ctx->d_spill})
     fd(*b);
   for (PatternSpace* s : {&ctx->kp, &ctx->cp})
     for (DevBuf* b : {&s->pool, &s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique,

@@ -19,8 +19,8 @@ int pin_grow(pf_ctx* ctx, PinBuf& b, size_t need, size_t used) {
 }
 
 // cut a batch into sub-batches of whole clusters with about `target` sequences each
-// (`first` for the first and the last one: nothing runs under the upload of the first or under
-// the D2H of the last, so they are kept short)
+// (`first` for the first one: nothing runs under its upload, so it is kept short; a short LAST
+// one does not pay: the D2H of the one before it would no longer be hidden)
 std::vector<SubRange> split_batch(const pf_batch* b, uint32_t target_all, uint32_t first) {
   std::vector<SubRange> subs;
   const uint32_t n = b->n_seqs;
@@ -29,10 +29,7 @@ std::vector<SubRange> split_batch(const pf_batch* b, uint32_t target_all, uint32
   while (s0 < n) {
     const uint64_t rem = n - s0;
     uint64_t target = s0 == 0 ? first : target_all;
-    if (rem <= target + target / 2) {
-      // the tail: all of it, or all but a short last sub-batch
-      target = (s0 > 0 && rem >= 3ull * first) ? rem - first : rem;
-    }
+    if (rem <= target + target / 2) target = rem;     // the tail: all of it
     uint32_t s1 = n, c1 = b->n_clusters;
     if (target < rem) {
       // first sequence of the cluster that holds sequence s0 + target (clusters are sorted)

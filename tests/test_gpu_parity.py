@@ -282,6 +282,19 @@ def test_block_engine_sample_slices_10k():
     assert out["stats"]["engine"] == 2
 
 
+@pytest.mark.parametrize("smem_kb,S", [("0", 90), ("2", 90), ("2", 1300)])
+def test_block_engine_merge_spills_to_global_table(smem_kb, S, monkeypatch):
+    """kB1_local merges a cluster's partial rows in shared memory; a cluster with more rows than
+    its table holds goes through the global-memory table instead (kB1_insert).  With the table cut
+    to 0 / 2 KB every / the larger (cluster, slice) takes that path; results must not change
+    (paralogs and the 0 / 5 base offsets of the random clusters put k-mers into several runs)."""
+    monkeypatch.setenv("PF_MERGE_SMEM_KB", smem_kb)
+    rng = np.random.default_rng(41)
+    items, stroi = _random_items(rng, S, 31, 6, 300 if S < 1000 else 200)
+    out, want = _compare_with_oracle(items, stroi, S, 31, True, False, False, 0.01, batch_clusters=3)
+    assert out["stats"]["engine"] == 2
+
+
 @pytest.mark.parametrize("engine", ["block", "records"])
 def test_pipelined_submit_matches_oracle(engine, monkeypatch):
     """pf_submit of a batch above the split threshold: sub-batches of whole clusters through
