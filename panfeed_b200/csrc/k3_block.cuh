@@ -531,6 +531,27 @@ __global__ void plan_expand_owner(const uint32_t* __restrict__ base, uint32_t n_
   for (uint32_t i = base[c] + lane_id(); i < base[c + 1]; i += 32) out[i] = c;
 }
 
+// OR partial row p into row q (both WP words, WP a multiple of 4): the words are loaded four
+// uint4 at a time before the first atomic goes out (one round trip, not one per word)
+__device__ __forceinline__ void fold_partial_row(uint32_t* __restrict__ slab_rows, uint32_t p, uint32_t q, uint32_t WP) {
+  const uint4* src = reinterpret_cast<const uint4*>(slab_rows + (size_t)p * WP);
+  uint32_t* dst = slab_rows + (size_t)q * WP;
+  const uint32_t n4 = WP >> 2;
+  for (uint32_t w0 = 0; w0 < n4; w0 += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = w0 + u < n4 ? src[w0 + u] : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      uint32_t* d = dst + (size_t)(w0 + u) * 4;
+      if (v[u].x) atomicOr(d + 0, v[u].x);
+      if (v[u].y) atomicOr(d + 1, v[u].y);
+      if (v[u].z) atomicOr(d + 2, v[u].z);
+      if (v[u].w) atomicOr(d + 3, v[u].w);
+    }
+  }
+}
+
 // kB1 in shared memory: one CTA per (cluster, slice).  The partial rows of a cluster number a few
 // ten thousand, so the find-or-insert table of the merge fits shared memory when an entry is 32
 // bits: a 15-bit fingerprint of the key and the 17-bit index of the owning row in the cluster's
@@ -552,11 +573,13 @@ kB1_local(const uint64_t* __restrict__ slab_keys, uint32_t* __restrict__ slab_ro
           const uint32_t* __restrict__ slab_count, const uint32_t* __restrict__ item_base /* [n_clusters + 1] */,
           uint32_t n_slices, const uint32_t* __restrict__ table_base /* [n_clusters * n_slices + 1] */,
           MergeEntry* __restrict__ table, uint16_t* __restrict__ pslice /* null without slices */,
-          uint32_t WP, uint32_t* __restrict__ counters, uint32_t max_slots, uint8_t* __restrict__ spill) {
+          uint32_t WP, uint32_t* __restrict__ counters, uint32_t max_slots, uint8_t* __restrict__ spill,
+          uint32_t fp_mask /* 0x7fff; fewer bits only to test the mismatch path */) {
   extern __shared__ uint32_t merge_sm[];
   uint32_t* prefix = merge_sm;                                  // [n_it + 1] rows before run i
   uint32_t* tab = merge_sm + kMergeLocalMaxItems + 1;           // [slots]
-  __shared__ uint32_t s_total, s_dups;
+  __shared__ uint32_t s_wsum[32];
+  __shared__ uint32_t s_dups, s_next;
   const uint32_t c = blockIdx.x;
   const uint32_t cluster = c / n_slices, slice = c - cluster * n_slices;
   const uint32_t it0 = item_base[cluster], n_it = item_base[cluster + 1] - it0;
@@ -564,28 +587,34 @@ kB1_local(const uint64_t* __restrict__ slab_keys, uint32_t* __restrict__ slab_ro
   bool spilled = n_it > kMergeLocalMaxItems;
   uint32_t total = 0;
   if (!spilled) {
-    if (warp == 0) {
-      uint32_t run = 0;
-      for (uint32_t b0 = 0; b0 < n_it; b0 += 32) {
-        const uint32_t i = b0 + lane;
-        uint32_t v = 0;
-        if (i < n_it) {
-          v = slab_count[(size_t)(it0 + i) * n_slices + slice];
-          if (v == kBlkOverflow) v = 0;
-        }
-        uint32_t x = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t y = __shfl_up_sync(kFull, x, d);
-          if ((int)lane >= d) x += y;
-        }
-        if (i < n_it) prefix[i] = run + x - v;
-        run += __shfl_sync(kFull, x, 31);
+    // prefix sums of the runs' row counts: 1024 runs per round, a warp per 32 of them
+    for (uint32_t b0 = 0; b0 < n_it; b0 += kMergeLocalThreads) {
+      const uint32_t i = b0 + tid;
+      uint32_t v = 0;
+      if (i < n_it) {
+        v = slab_count[(size_t)(it0 + i) * n_slices + slice];
+        if (v == kBlkOverflow) v = 0;
       }
-      if (lane == 0) { prefix[n_it] = run; s_total = run; s_dups = 0; }
+      uint32_t x = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFull, x, d);
+        if ((int)lane >= d) x += y;
+      }
+      if (lane == 31) s_wsum[warp] = x;
+      __syncthreads();
+      uint32_t ws = s_wsum[lane], wx = ws;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(kFull, wx, d);
+        if ((int)lane >= d) wx += y;
+      }
+      const uint32_t before = __shfl_sync(kFull, wx - ws, warp);   // rows of the warps before this one
+      if (i < n_it) prefix[i] = total + before + x - v;
+      total += __shfl_sync(kFull, wx, 31);
+      __syncthreads();
     }
-    __syncthreads();
-    total = s_total;
+    if (tid == 0) { prefix[n_it] = total; s_dups = 0; s_next = 0; }
     if (total == 0) { if (tid == 0) spill[c] = 0; return; }
     spilled = total >= (1u << kMergeLocalIdxBits) - 1u || total > max_slots / 16u * 13u;
   }
@@ -600,44 +629,68 @@ kB1_local(const uint64_t* __restrict__ slab_keys, uint32_t* __restrict__ slab_ro
   for (uint32_t i = tid; i < slots; i += kMergeLocalThreads) tab[i] = 0xffffffffu;
   __syncthreads();
   uint32_t dups = 0;
-  for (uint32_t it = warp; it < n_it; it += kMergeLocalThreads / 32u) {
+  // partial-row index of row `ql` of the cluster's numbering
+  auto global_row = [&](uint32_t ql) -> uint32_t {
+    uint32_t lo = 0, hi = n_it;                                 // last run with prefix <= ql
+    while (hi - lo > 1) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if (prefix[mid] <= ql) lo = mid; else hi = mid;
+    }
+    return slab_base[(size_t)(it0 + lo) * n_slices + slice] + (ql - prefix[lo]);
+  };
+  auto fold = [&](uint32_t p, uint32_t q) {
+    fold_partial_row(slab_rows, p, q, WP);
+    slab_cnt[p] = kCntDead;
+    slab_cnt[q] = kCntDirty;
+    ++dups;
+  };
+  // find-or-insert of one row: key, its index in the cluster's numbering, its partial-row index.
+  // A fingerprint match is a row of the same k-mer but for one in 2^15; the full keys decide.
+  // (Deferring the matches to a list that the whole CTA works off afterwards, so that their
+  // global-memory round trips overlap, was measured and is slower: 84 vs 74 us per 200 clusters.)
+  auto insert = [&](uint64_t key, uint32_t local, uint32_t p) {
+    const uint64_t mixed = mix64(key);
+    const uint32_t fp = (uint32_t)mixed & fp_mask;
+    const uint32_t mine = (fp << kMergeLocalIdxBits) | local;
+    uint32_t s = __umulhi((uint32_t)(mixed >> 32), slots);
+    for (;;) {
+      const uint32_t old = atomicCAS(&tab[s], 0xffffffffu, mine);
+      if (old == 0xffffffffu) return;                           // this row owns the k-mer
+      if ((old >> kMergeLocalIdxBits) == fp) {
+        const uint32_t q = global_row(old & ((1u << kMergeLocalIdxBits) - 1u));
+        if (slab_keys[q] == key) { fold(p, q); return; }        // an earlier row of the same k-mer
+      }
+      if (++s == slots) s = 0;
+    }
+  };
+  // warps take half a run at a time (dynamic; ~128 rows: the tail of the CTA is short); the keys
+  // of four rows per lane are loaded before the first of them is inserted
+  for (;;) {
+    uint32_t unit = 0;
+    if (lane == 0) unit = atomicAdd(&s_next, 1u);
+    unit = __shfl_sync(kFull, unit, 0);
+    const uint32_t it = unit >> 1;
+    if (it >= n_it) break;
     const size_t item = (size_t)(it0 + it) * n_slices + slice;
     const uint32_t n = slab_count[item];
     if (n == kBlkOverflow || n == 0) continue;
+    const uint32_t half = (((n + 1u) >> 1) + 31u) & ~31u;
+    const uint32_t r0 = (unit & 1u) * half, r1 = min(n, r0 + half);
     const uint32_t base = slab_base[item], lbase = prefix[it];
-    for (uint32_t i = lane; i < n; i += 32) {
-      const uint32_t p = base + i;
-      if (pslice) pslice[p] = (uint16_t)slice;
-      const uint64_t key = slab_keys[p];
-      const uint64_t mixed = mix64(key);
-      const uint32_t fp = (uint32_t)mixed & 0x7fffu;
-      const uint32_t mine = (fp << kMergeLocalIdxBits) | (lbase + i);
-      uint32_t s = __umulhi((uint32_t)(mixed >> 32), slots);
-      for (;;) {
-        const uint32_t old = atomicCAS(&tab[s], 0xffffffffu, mine);
-        if (old == 0xffffffffu) break;                          // this row owns the k-mer
-        if ((old >> kMergeLocalIdxBits) == fp) {
-          const uint32_t ql = old & ((1u << kMergeLocalIdxBits) - 1u);
-          uint32_t lo = 0, hi = n_it;                           // last run with prefix <= ql
-          while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (prefix[mid] <= ql) lo = mid; else hi = mid;
-          }
-          const uint32_t q = slab_base[(size_t)(it0 + lo) * n_slices + slice] + (ql - prefix[lo]);
-          if (slab_keys[q] == key) {                            // an earlier row of the same k-mer
-            const uint32_t* src = slab_rows + (size_t)p * WP;
-            uint32_t* dst = slab_rows + (size_t)q * WP;
-            for (uint32_t w = 0; w < WP; ++w) {
-              const uint32_t x = src[w];
-              if (x) atomicOr(dst + w, x);
-            }
-            slab_cnt[p] = kCntDead;
-            slab_cnt[q] = kCntDirty;
-            ++dups;
-            break;
-          }
+    for (uint32_t i0 = r0 + lane; i0 < r1; i0 += 128) {
+      uint64_t key[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = i0 + 32u * u;
+        key[u] = i < r1 ? slab_keys[base + i] : 0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t i = i0 + 32u * u;
+        if (i < r1) {
+          if (pslice) pslice[base + i] = (uint16_t)slice;
+          insert(key[u], lbase + i, base + i);
         }
-        if (++s == slots) s = 0;
       }
     }
   }
@@ -685,12 +738,7 @@ kB1_insert(const uint64_t* __restrict__ slab_keys, uint32_t* __restrict__ slab_r
       if ((uint32_t)(old >> 32) == fp) {
         const uint32_t q = (uint32_t)old;
         if (slab_keys[q] == key) {                          // an earlier row of the same k-mer
-          const uint32_t* src = slab_rows + (size_t)p * WP;
-          uint32_t* dst = slab_rows + (size_t)q * WP;
-          for (uint32_t w = 0; w < WP; ++w) {
-            const uint32_t x = src[w];
-            if (x) atomicOr(dst + w, x);
-          }
+          fold_partial_row(slab_rows, p, q, WP);
           slab_cnt[p] = kCntDead;
           slab_cnt[q] = kCntDirty;
           atomicAdd(&counters[LC_RESCUE], 1u);              // (the rescue counter is free again after kA)

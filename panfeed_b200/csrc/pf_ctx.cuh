@@ -286,6 +286,7 @@ struct pf_ctx : BatchState {
       d_group_base /* merge-table offsets per (cluster, slice) */, d_mtable,
       d_table2_base, d_table2, d_next, d_pslice, d_cta_cluster, d_slab_cnt, d_rescue[2],
       d_spill /* (cluster, slice) merged in the global table */;
+  uint32_t merge_fp_mask = 0x7fffu;   // PF_MERGE_FP_BITS (tests: a 1-bit fingerprint exercises the mismatch path)
   uint32_t merge_slots = 49152;  // shared-memory merge table of kB1_local (PF_MERGE_SMEM_KB)
   PatternSpace kp, cp;     // k-mer patterns, cluster patterns
   // pinned results

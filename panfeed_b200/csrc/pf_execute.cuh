@@ -457,7 +457,7 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
       ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(), ctx->d_item_base.as<uint32_t>(), ns,
       ctx->d_group_base.as<uint32_t>(), ctx->d_mtable.as<MergeEntry>(),
       ns > 1 ? ctx->d_pslice.as<uint16_t>() : nullptr, WP, counters + C_LOCAL, ctx->merge_slots,
-      ctx->d_spill.as<uint8_t>());
+      ctx->d_spill.as<uint8_t>(), ctx->merge_fp_mask);
   ctx->launches++;
   const uint32_t g0 = cdiv((uint64_t)n_it * 32, 256);
   kB1_insert<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),

@@ -165,6 +165,10 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
       const long kb = atol(e);
       if (kb >= 0 && kb <= 216) ctx->merge_slots = (uint32_t)(kb * 256);
     }
+    if (const char* e = getenv("PF_MERGE_FP_BITS")) {
+      const long b = atol(e);
+      if (b >= 0 && b <= 15) ctx->merge_fp_mask = (1u << b) - 1u;
+    }
     cudaFuncSetAttribute(kB1_local, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)merge_local_smem_bytes(ctx->merge_slots));
     cudaFuncSetAttribute(kA_block_aggregate<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkMaxSmem);

@@ -295,6 +295,18 @@ def test_block_engine_merge_spills_to_global_table(smem_kb, S, monkeypatch):
     assert out["stats"]["engine"] == 2
 
 
+@pytest.mark.parametrize("fp_bits,S", [("0", 90), ("2", 90), ("1", 1300)])
+def test_block_engine_merge_fingerprint_mismatches(fp_bits, S, monkeypatch):
+    """kB1_local stores a 15-bit fingerprint per table entry and confirms a match on the full key;
+    a match between different k-mers must keep probing.  With a 0..2-bit fingerprint nearly every
+    probe of an occupied slot is such a match; results must not change."""
+    monkeypatch.setenv("PF_MERGE_FP_BITS", fp_bits)
+    rng = np.random.default_rng(43)
+    items, stroi = _random_items(rng, S, 31, 5, 300 if S < 1000 else 200)
+    out, want = _compare_with_oracle(items, stroi, S, 31, True, False, False, 0.01, batch_clusters=3)
+    assert out["stats"]["engine"] == 2
+
+
 @pytest.mark.parametrize("engine", ["block", "records"])
 def test_pipelined_submit_matches_oracle(engine, monkeypatch):
     """pf_submit of a batch above the split threshold: sub-batches of whole clusters through
