@@ -255,6 +255,21 @@ int pf_format_patterns(const uint32_t* pattern_words, uint64_t n, uint32_t strid
                        uint32_t present_stride, char* out, uint64_t out_cap, uint64_t* out_len,
                        uint32_t n_threads);
 
+/* The kmers_to_hashes rows of a batch (panfeed.py:177 "<idx>\t\t<cluster hash>", :208
+ * "<idx>\t<kmer>\t<hash>"): for every cluster of `result`, in order, the header row and then its
+ * k-mer rows — the plain ones in alphabetical k-mer order, then those holding N/IUPAC symbols
+ * (the reference's order inside a cluster is the insertion order of a Python dict; consumers
+ * key on the k-mer).  tag_blob + tag_off[c .. c+1]: the text of the first column for cluster c.
+ * kmer_ids / cluster_ids: 24 characters per pattern, indexed by row_pattern / cluster_pattern
+ * (all patterns numbered so far, e.g. from pf_pattern_ids + base64).  cluster_off (may be NULL):
+ * [n_clusters + 1] byte offsets of every cluster's text.  out == NULL: only *out_len (and
+ * cluster_off).  Uses row_*, wide_row_*, cluster_pattern and n_clusters of the result. */
+int pf_format_kmer_rows(const pf_batch_result* result, uint32_t k, const char* tag_blob,
+                        const uint64_t* tag_off, const char* kmer_ids, uint64_t n_kmer_ids,
+                        const char* cluster_ids, uint64_t n_cluster_ids, char* out,
+                        uint64_t out_cap, uint64_t* out_len, uint64_t* cluster_off,
+                        uint32_t n_threads);
+
 /* ---- native packer (host threads): ASCII sequences -> the planes of a pf_batch ----
  * What the feeder has after cutting (input.py:455-459: Seqinfo.sequence, upper case) goes into
  * the 2-bit plane; sequences holding N/IUPAC symbols are flagged and additionally packed into

@@ -109,7 +109,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_upload", "pf_execute", "pf_submit", "pf_collect",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
            "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream", "pf_format_positions",
-           "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns",
+           "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns", "pf_format_kmer_rows",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_export",
            "pf_exchange_unpack"]
@@ -145,6 +145,8 @@ def load():
     lib.pf_patterns_export.argtypes = [vp, C.c_int, u64, u64, vp]
     lib.pf_format_patterns.argtypes = [vp, u64, u32, u32, C.c_char_p, vp, u32, C.c_char_p, u64,
                                        C.POINTER(u64), u32]
+    lib.pf_format_kmer_rows.argtypes = [C.POINTER(BatchResult), u32, C.c_char_p, vp, vp, u64, vp, u64, vp, u64,
+                                        C.POINTER(u64), vp, u32]
     lib.pf_pack_plan.argtypes = [vp, u32, vp, C.POINTER(u64)]
     lib.pf_pack_2bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, u32]
     lib.pf_pack_4bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, C.POINTER(u64), C.POINTER(C.c_int)]
@@ -236,6 +238,54 @@ def format_patterns(words, n_samples, ids, present=None, n_threads=0):
     if rc != 0:
         raise PfError(rc, "pf_format_patterns failed")
     return out.tobytes()
+
+
+def format_kmer_rows(r, k, tags, kmer_ids, cluster_ids, n_threads=0):
+    """kmers_to_hashes text of the batch result `r` (a dict as returned by Context.collect(), or
+    any dict with row_*, wide_row_* and cluster_pattern), formatted by the library's host threads
+    (pf_format_kmer_rows).  tags[c] = first column of cluster c (bytes); kmer_ids / cluster_ids:
+    numpy S24 arrays of all pattern ids numbered so far.  Returns (bytes, offsets[n_clusters+1])."""
+    lib = load()
+    keep = []
+
+    def ptr(a, dtype, ctype):
+        a = np.ascontiguousarray(a, dtype=dtype)
+        keep.append(a)
+        return a.ctypes.data_as(C.POINTER(ctype))
+
+    nc = len(r["cluster_pattern"])
+    if nc == 0:
+        return b"", np.zeros(1, np.uint64)
+    res = BatchResult()
+    res.n_clusters = nc
+    res.cluster_pattern = ptr(r["cluster_pattern"], np.uint32, C.c_uint32)
+    res.n_rows = len(r["row_cluster"])
+    res.row_cluster = ptr(r["row_cluster"], np.uint32, C.c_uint32)
+    res.row_kmer = ptr(r["row_kmer"], np.uint64, C.c_uint64)
+    res.row_pattern = ptr(r["row_pattern"], np.uint32, C.c_uint32)
+    wide = np.ascontiguousarray(r.get("wide_row_kmer", np.zeros((0, 2), np.uint64)), dtype=np.uint64).reshape(-1)
+    res.n_wide_rows = wide.size // 2
+    if wide.size:
+        res.wide_row_kmer = ptr(wide, np.uint64, C.c_uint64)
+        res.wide_row_cluster = ptr(r["wide_row_cluster"], np.uint32, C.c_uint32)
+        res.wide_row_pattern = ptr(r["wide_row_pattern"], np.uint32, C.c_uint32)
+    blob = b"".join(tags)
+    off = np.zeros(nc + 1, np.uint64)
+    np.cumsum([len(x) for x in tags], out=off[1:])
+    kid = np.ascontiguousarray(kmer_ids, dtype="S24")
+    cid = np.ascontiguousarray(cluster_ids, dtype="S24")
+    cl_off = np.zeros(nc + 1, np.uint64)
+    need = C.c_uint64()
+    args = (C.byref(res), int(k), blob, off.ctypes.data, kid.ctypes.data if len(kid) else None, len(kid),
+            cid.ctypes.data if len(cid) else None, len(cid))
+    rc = lib.pf_format_kmer_rows(*args, None, 0, C.byref(need), cl_off.ctypes.data, int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_format_kmer_rows (sizing) failed")
+    out = np.empty(int(need.value), np.uint8)
+    rc = lib.pf_format_kmer_rows(*args, out.ctypes.data, out.size, C.byref(need), cl_off.ctypes.data, int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_format_kmer_rows failed")
+    return out.tobytes(), cl_off
 
 
 def format_positions(r, k, canonical, leads, seq_strand, n_threads=0):

@@ -7,6 +7,7 @@
 // over a few hundred clusters yields 1e8 rows; formatting them in the Python host costs minutes,
 // here it is a memory-bound loop over host threads.  No device code in this file.
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <thread>
@@ -317,5 +318,123 @@ extern "C" int pf_format_patterns(const uint32_t* pattern_words, uint64_t n, uin
       *p++ = '\n';
     }
   });
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kmers_to_hashes rows (panfeed.py:177 "<idx>\t\t<cluster hash>", :208 "<idx>\t<kmer>\t<hash>"):
+// per cluster of the batch, in order, the header row and then its k-mer rows — the plain ones in
+// alphabetical (= numeric) k-mer order, then those holding N/IUPAC symbols in the numeric order of
+// their 4-bit codes.  (The reference's order inside a cluster is that of a Python dict of
+// k-mers filled in window order; consumers key on the k-mer, not on the row order.)
+// ---------------------------------------------------------------------------
+extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const char* tag_blob,
+                                   const uint64_t* tag_off, const char* kmer_ids, uint64_t n_kmer_ids,
+                                   const char* cluster_ids, uint64_t n_cluster_ids, char* out, uint64_t out_cap,
+                                   uint64_t* out_len, uint64_t* cluster_off, uint32_t n_threads) {
+  if (!r || !out_len || !tag_off || k == 0 || k > 32) return PF_ERR_INVALID;
+  const uint64_t nc = r->n_clusters, nn = r->n_rows, nw = r->n_wide_rows;
+  *out_len = 0;
+  if (nc >= (1ull << 32) || nn >= (1ull << 32) || nw >= (1ull << 32)) return PF_ERR_INVALID;
+  if (nc && (!tag_blob || !cluster_ids || !r->cluster_pattern)) return PF_ERR_INVALID;
+  if (nn && (!r->row_cluster || !r->row_kmer || !r->row_pattern || !kmer_ids)) return PF_ERR_INVALID;
+  if (nw && (!r->wide_row_cluster || !r->wide_row_kmer || !r->wide_row_pattern || !kmer_ids)) return PF_ERR_INVALID;
+  if (nc == 0) return (nn || nw) ? PF_ERR_INVALID : PF_OK;
+  // rows of every cluster: counting sort of the row indices (narrow rows first, then wide)
+  std::vector<uint32_t> first(nc + 1, 0), first_w(nc + 1, 0);
+  for (uint64_t i = 0; i < nn; ++i) {
+    if (r->row_cluster[i] >= nc || r->row_pattern[i] >= n_kmer_ids) return PF_ERR_INVALID;
+    ++first[r->row_cluster[i] + 1];
+  }
+  for (uint64_t i = 0; i < nw; ++i) {
+    if (r->wide_row_cluster[i] >= nc || r->wide_row_pattern[i] >= n_kmer_ids) return PF_ERR_INVALID;
+    ++first_w[r->wide_row_cluster[i] + 1];
+  }
+  for (uint64_t c = 0; c < nc; ++c) {
+    if (r->cluster_pattern[c] >= n_cluster_ids || tag_off[c + 1] < tag_off[c]) return PF_ERR_INVALID;
+    first[c + 1] += first[c];
+    first_w[c + 1] += first_w[c];
+  }
+  std::vector<uint32_t> order(nn), order_w(nw);
+  {
+    std::vector<uint32_t> at(first.begin(), first.end() - 1), at_w(first_w.begin(), first_w.end() - 1);
+    for (uint64_t i = 0; i < nn; ++i) order[at[r->row_cluster[i]]++] = (uint32_t)i;
+    for (uint64_t i = 0; i < nw; ++i) order_w[at_w[r->wide_row_cluster[i]]++] = (uint32_t)i;
+  }
+  // byte offsets of the clusters' texts
+  std::vector<uint64_t> off(nc + 1, 0);
+  for (uint64_t c = 0; c < nc; ++c) {
+    const uint64_t tag = tag_off[c + 1] - tag_off[c];
+    const uint64_t rows = (uint64_t)(first[c + 1] - first[c]) + (first_w[c + 1] - first_w[c]);
+    off[c + 1] = off[c] + (tag + 2 + 24 + 1) + rows * (tag + 1 + k + 1 + 24 + 1);
+  }
+  *out_len = off[nc];
+  if (cluster_off) memcpy(cluster_off, off.data(), (nc + 1) * sizeof(uint64_t));
+  if (!out) return PF_OK;
+  if (out_cap < off[nc]) return PF_ERR_NOMEM;
+  // clusters are taken one at a time by the threads (they differ in rows): sort, then write
+  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  uint32_t nt = n_threads ? n_threads : hw;
+  nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nt, (nn + nw + nc + 16383) / 16384));
+  std::atomic<uint32_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const uint32_t c = next.fetch_add(1);
+      if (c >= nc) return;
+      uint32_t* o = order.data() + first[c];
+      const uint32_t n = first[c + 1] - first[c];
+      std::sort(o, o + n, [&](uint32_t a, uint32_t b) {
+        return r->row_kmer[a] != r->row_kmer[b] ? r->row_kmer[a] < r->row_kmer[b] : a < b;
+      });
+      uint32_t* ow = order_w.data() + first_w[c];
+      const uint32_t n_w = first_w[c + 1] - first_w[c];
+      std::sort(ow, ow + n_w, [&](uint32_t a, uint32_t b) {
+        const uint64_t* x = r->wide_row_kmer + 2 * (uint64_t)a;
+        const uint64_t* y = r->wide_row_kmer + 2 * (uint64_t)b;
+        if (x[0] != y[0]) return x[0] < y[0];
+        if (x[1] != y[1]) return x[1] < y[1];
+        return a < b;
+      });
+      const char* tag = tag_blob + tag_off[c];
+      const uint64_t tl = tag_off[c + 1] - tag_off[c];
+      char* p = out + off[c];
+      memcpy(p, tag, tl); p += tl;
+      *p++ = '\t'; *p++ = '\t';
+      memcpy(p, cluster_ids + (size_t)r->cluster_pattern[c] * 24, 24); p += 24;
+      *p++ = '\n';
+      for (uint32_t j = 0; j < n; ++j) {
+        const uint32_t i = o[j];
+        memcpy(p, tag, tl); p += tl;
+        *p++ = '\t';
+        const uint64_t v = r->row_kmer[i];
+        for (uint32_t s = 0; s < k; ++s) p[s] = kAcgt[(v >> (2 * (k - 1 - s))) & 3u];
+        p += k;
+        *p++ = '\t';
+        memcpy(p, kmer_ids + (size_t)r->row_pattern[i] * 24, 24); p += 24;
+        *p++ = '\n';
+      }
+      for (uint32_t j = 0; j < n_w; ++j) {
+        const uint32_t i = ow[j];
+        memcpy(p, tag, tl); p += tl;
+        *p++ = '\t';
+        const uint64_t* w = r->wide_row_kmer + 2 * (uint64_t)i;            // [hi, lo], 4 bits per symbol
+        for (uint32_t s = 0; s < k; ++s) {
+          const uint32_t nib = k - 1 - s;
+          const uint64_t word = nib < 16 ? w[1] : w[0];
+          p[s] = kAmb[(word >> (4 * (nib % 16))) & 15u];
+        }
+        p += k;
+        *p++ = '\t';
+        memcpy(p, kmer_ids + (size_t)r->wide_row_pattern[i] * 24, 24); p += 24;
+        *p++ = '\n';
+      }
+    }
+  };
+  if (nt == 1) work();
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < nt; ++t) th.emplace_back(work);
+    for (auto& x : th) x.join();
+  }
   return PF_OK;
 }

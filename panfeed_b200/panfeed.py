@@ -142,39 +142,13 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
         pat_text.append(capi.format_patterns(new_kp[sel], S, [p for p, f in zip(new_ids, fresh) if f],
                                              None if present is None else present[sel]).decode())
 
-    # ---- kmers_to_hashes rows, cluster by cluster ------------------------------
+    # ---- kmers_to_hashes rows, cluster by cluster: formatted by the library's host threads
+    #      (pf_format_kmer_rows; inside a cluster the plain k-mers in alphabetical order, then the
+    #      rows holding N/IUPAC symbols - the reference's order is arbitrary too) --------------
     kmer_ids = np.array(store.kmer_ids, dtype="S24") if store.kmer_ids else np.zeros(0, "S24")
-    # rows grouped by cluster; inside a cluster the narrow rows in numeric (= alphabetical) k-mer
-    # order, then the rows holding N/IUPAC symbols (the reference's order is arbitrary too)
-    n_order = np.lexsort((r["row_kmer"], r["row_cluster"]))
-    w_order = np.lexsort((r["wide_row_kmer"][:, 1], r["wide_row_kmer"][:, 0], r["wide_row_cluster"])) \
-        if len(r["wide_row_cluster"]) else np.zeros(0, np.int64)
-    row_cluster = np.concatenate([r["row_cluster"][n_order], r["wide_row_cluster"][w_order]])
-    row_kmer = np.concatenate([packer.kmers_to_str(r["row_kmer"][n_order], k),
-                               packer.wide_kmers_to_str(r["wide_row_kmer"][w_order], k)])
-    row_pat = np.concatenate([r["row_pattern"][n_order], r["wide_row_pattern"][w_order]]).astype(np.int64)
-    row_pid = kmer_ids[row_pat] if len(row_cluster) else np.zeros(0, "S24")
-    if len(r["wide_row_cluster"]):
-        order = np.argsort(row_cluster, kind="stable")
-        row_cluster, row_kmer, row_pid = row_cluster[order], row_kmer[order], row_pid[order]
-    bounds = np.searchsorted(row_cluster, np.arange(len(pcs) + 1))
-    hash_texts = []
-    for c, idx in enumerate(idxs):
-        head = f"{idx}\t\t{store.cluster_ids[r['cluster_pattern'][c]]}\n"
-        lo, hi = bounds[c], bounds[c + 1]
-        n = hi - lo
-        if n == 0:
-            hash_texts.append(head)
-            continue
-        tag = (str(idx) + "\t").encode()
-        width = len(tag) + k + 1 + 24 + 1
-        buf = np.empty((n, width), np.uint8)
-        buf[:, :len(tag)] = np.frombuffer(tag, np.uint8)
-        buf[:, len(tag):len(tag) + k] = row_kmer[lo:hi].view(np.uint8).reshape(n, k)
-        buf[:, len(tag) + k] = ord("\t")
-        buf[:, len(tag) + k + 1:width - 1] = row_pid[lo:hi].view(np.uint8).reshape(n, 24)
-        buf[:, -1] = ord("\n")
-        hash_texts.append(head + buf.tobytes().decode())
+    cluster_ids = np.array(store.cluster_ids, dtype="S24") if store.cluster_ids else np.zeros(0, "S24")
+    text, off = capi.format_kmer_rows(r, k, [str(idx).encode() for idx in idxs], kmer_ids, cluster_ids)
+    hash_texts = [text[int(off[c]):int(off[c + 1])].decode() for c in range(len(idxs))]
 
     # ---- kmers.tsv rows from the positional records: formatted by the library's host
     #      threads (pf_format_positions), 1e8 rows are too many for Python ----------------

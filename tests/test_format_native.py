@@ -100,3 +100,82 @@ def test_native_pattern_rows_match_python(S, with_nan):
     want = "".join(pid + "\t" + "\t".join("" if not p else str(int(v)) for v, p in zip(b, pr)) + "\n"
                    for pid, b, pr in zip(ids, bits, pres))
     assert got.decode() == want
+
+
+def _kmer_rows_python(r, k, tags, kmer_ids, cluster_ids):
+    """kmers_to_hashes text rendered with numpy / Python (what the host mirror did before the
+    native formatter): per cluster the header, the narrow rows by k-mer, then the wide rows."""
+    from panfeed_b200 import packer
+    out = []
+    nk = packer.kmers_to_str(r["row_kmer"], k)
+    wk = packer.wide_kmers_to_str(r["wide_row_kmer"], k)
+    for c, tag in enumerate(tags):
+        out.append(tag + b"\t\t" + cluster_ids[r["cluster_pattern"][c]] + b"\n")
+        sel = np.flatnonzero(r["row_cluster"] == c)
+        sel = sel[np.argsort(r["row_kmer"][sel], kind="stable")]
+        for i in sel:
+            out.append(tag + b"\t" + nk[i] + b"\t" + kmer_ids[r["row_pattern"][i]] + b"\n")
+        sel = np.flatnonzero(r["wide_row_cluster"] == c)
+        if len(sel):
+            w = r["wide_row_kmer"][sel]
+            sel = sel[np.lexsort((w[:, 1], w[:, 0]))]
+        for i in sel:
+            out.append(tag + b"\t" + wk[i] + b"\t" + kmer_ids[r["wide_row_pattern"][i]] + b"\n")
+    return out
+
+
+@pytest.mark.parametrize("k", [1, 17, 31, 32])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_native_kmer_rows_match_python(k, threads):
+    """pf_format_kmer_rows against the reference's f-strings (panfeed.py:177, :208): header row
+    per cluster (also for clusters without rows), k-mer rows sorted inside the cluster."""
+    rng = np.random.default_rng(7 * k + threads)
+    nc = 23
+    n = 40_000 if threads > 1 else 2_000
+    nw = 300
+    ids = np.array([("%022d==" % i).encode() for i in range(500)], "S24")
+    cids = np.array([("c%021d==" % i).encode() for i in range(40)], "S24")
+    tags = [str(int(x)).encode() for x in rng.integers(0, 100000, nc)]
+    row_cluster = rng.integers(0, nc, n).astype(np.uint32)
+    row_cluster[row_cluster == 5] = 6                      # cluster 5 has no narrow rows
+    # distinct k-mers per cluster are what the library returns; duplicates across clusters are fine
+    row_kmer = rng.integers(0, 1 << min(62, 2 * k), n, dtype=np.uint64) if k < 32 else \
+        rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+    if k == 1:
+        row_kmer = rng.integers(0, 4, n, dtype=np.uint64)
+    wide = np.zeros((nw, 2), np.uint64)
+    for i in range(nw):
+        t = "".join(rng.choice(list("ACGTNRYKMSWBDHVX"), k))
+        wide[i] = _pack4(t)
+    r = {"cluster_pattern": rng.integers(0, 40, nc).astype(np.uint32),
+         "row_cluster": row_cluster, "row_kmer": row_kmer,
+         "row_pattern": rng.integers(0, 500, n).astype(np.uint32),
+         "wide_row_cluster": rng.integers(0, nc, nw).astype(np.uint32), "wide_row_kmer": wide,
+         "wide_row_pattern": rng.integers(0, 500, nw).astype(np.uint32)}
+    got, off = capi.format_kmer_rows(r, k, tags, ids, cids, n_threads=threads)
+    want = _kmer_rows_python(r, k, tags, ids, cids)
+    # equal k-mers inside a cluster (possible in this random input only) may swap: compare sorted
+    assert sorted(got.split(b"\n")) == sorted(b"".join(want).split(b"\n"))
+    assert len(got) == len(b"".join(want)) == int(off[-1])
+    # per-cluster slices: header first, then rows in k-mer order
+    for c in range(nc):
+        lines = got[int(off[c]):int(off[c + 1])].split(b"\n")[:-1]
+        assert lines[0] == tags[c] + b"\t\t" + cids[r["cluster_pattern"][c]]
+        n_c = int((row_cluster == c).sum())
+        kms = [ln.split(b"\t")[1] for ln in lines[1:1 + n_c]]
+        assert kms == sorted(kms)
+        assert len(lines) == 1 + n_c + int((r["wide_row_cluster"] == c).sum())
+
+
+def test_native_kmer_rows_reject_bad_indices():
+    ids = np.array([b"x" * 24], "S24")
+    r = {"cluster_pattern": np.zeros(2, np.uint32), "row_cluster": np.array([0, 2], np.uint32),
+         "row_kmer": np.zeros(2, np.uint64), "row_pattern": np.zeros(2, np.uint32),
+         "wide_row_cluster": np.zeros(0, np.uint32), "wide_row_kmer": np.zeros((0, 2), np.uint64),
+         "wide_row_pattern": np.zeros(0, np.uint32)}
+    with pytest.raises(capi.PfError):
+        capi.format_kmer_rows(r, 5, [b"0", b"1"], ids, ids)          # row of cluster 2 of 2
+    r["row_cluster"] = np.array([0, 1], np.uint32)
+    r["row_pattern"] = np.array([0, 1], np.uint32)
+    with pytest.raises(capi.PfError):
+        capi.format_kmer_rows(r, 5, [b"0", b"1"], ids, ids)          # pattern 1 of 1
