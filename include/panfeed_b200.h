@@ -270,6 +270,15 @@ int pf_format_kmer_rows(const pf_batch_result* result, uint32_t k, const char* t
                         uint64_t out_cap, uint64_t* out_len, uint64_t* cluster_off,
                         uint32_t n_threads);
 
+/* --compress (input.py:235-259: gzip.open(..., "wt", compresslevel=9) on the three outputs):
+ * `text` is cut into members of member_bytes (0 = 4 MiB), every member becomes a complete gzip
+ * member deflated at `level` by a host thread, the members are concatenated in order — a valid
+ * gzip file or a piece of one (RFC 1952: any number of members; zcat / Python gzip / pandas read
+ * them as one stream).  len == 0 yields one empty member.  out == NULL: *out_len = an upper bound
+ * of the size; otherwise *out_len = the bytes written (PF_ERR_NOMEM if out_cap is too small). */
+int pf_gzip_members(const char* text, uint64_t len, int level, uint64_t member_bytes, char* out,
+                    uint64_t out_cap, uint64_t* out_len, uint32_t n_threads);
+
 /* ---- native packer (host threads): ASCII sequences -> the planes of a pf_batch ----
  * What the feeder has after cutting (input.py:455-459: Seqinfo.sequence, upper case) goes into
  * the 2-bit plane; sequences holding N/IUPAC symbols are flagged and additionally packed into

@@ -109,7 +109,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_upload", "pf_execute", "pf_submit", "pf_collect",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
            "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream", "pf_format_positions",
-           "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns", "pf_format_kmer_rows",
+           "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns", "pf_format_kmer_rows", "pf_gzip_members",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_export",
            "pf_exchange_unpack"]
@@ -147,6 +147,7 @@ def load():
                                        C.POINTER(u64), u32]
     lib.pf_format_kmer_rows.argtypes = [C.POINTER(BatchResult), u32, C.c_char_p, vp, vp, u64, vp, u64, vp, u64,
                                         C.POINTER(u64), vp, u32]
+    lib.pf_gzip_members.argtypes = [C.c_char_p, u64, C.c_int, u64, vp, u64, C.POINTER(u64), u32]
     lib.pf_pack_plan.argtypes = [vp, u32, vp, C.POINTER(u64)]
     lib.pf_pack_2bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, u32]
     lib.pf_pack_4bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, C.POINTER(u64), C.POINTER(C.c_int)]
@@ -238,6 +239,22 @@ def format_patterns(words, n_samples, ids, present=None, n_threads=0):
     if rc != 0:
         raise PfError(rc, "pf_format_patterns failed")
     return out.tobytes()
+
+
+def gzip_members(data, level=9, member_bytes=0, n_threads=0):
+    """gzip of `data` (bytes) as a sequence of independently deflated members (pf_gzip_members,
+    library host threads): a valid gzip file, or a piece to append to one."""
+    lib = load()
+    need = C.c_uint64()
+    rc = lib.pf_gzip_members(data, len(data), int(level), int(member_bytes), None, 0, C.byref(need), int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_gzip_members (sizing) failed")
+    out = np.empty(int(need.value), np.uint8)
+    rc = lib.pf_gzip_members(data, len(data), int(level), int(member_bytes), out.ctypes.data, out.size,
+                             C.byref(need), int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_gzip_members failed")
+    return out[:int(need.value)].tobytes()
 
 
 def format_kmer_rows(r, k, tags, kmer_ids, cluster_ids, n_threads=0):

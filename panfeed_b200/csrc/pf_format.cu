@@ -13,6 +13,8 @@
 #include <thread>
 #include <vector>
 
+#include <zlib.h>
+
 #include "../../include/panfeed_b200.h"
 
 namespace {
@@ -435,6 +437,75 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
     std::vector<std::thread> th;
     for (uint32_t t = 0; t < nt; ++t) th.emplace_back(work);
     for (auto& x : th) x.join();
+  }
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// --compress: the reference opens its three outputs with gzip.open(..., "wt", compresslevel=9)
+// (input.py:235-259) and deflates every row on the one writer process; with --cores > 2 its
+// writers interleave and the file is corrupt.  Here a text buffer is cut into
+// members of `member_bytes`, every member is deflated by a host thread into a complete gzip member
+// (RFC 1952 allows any number of members per file: zcat, Python's gzip and pandas read them as one
+// stream), and the members are concatenated in order.
+// ---------------------------------------------------------------------------
+extern "C" int pf_gzip_members(const char* text, uint64_t len, int level, uint64_t member_bytes, char* out,
+                               uint64_t out_cap, uint64_t* out_len, uint32_t n_threads) {
+  if (!out_len || (len && !text) || level < 0 || level > 9) return PF_ERR_INVALID;
+  if (member_bytes == 0) member_bytes = 4ull << 20;
+  if (member_bytes > (1ull << 30)) member_bytes = 1ull << 30;          // zlib counts in 32 bits
+  const uint64_t n_members = std::max<uint64_t>(1, (len + member_bytes - 1) / member_bytes);
+  if (n_members >= (1ull << 31)) return PF_ERR_INVALID;
+  // worst-case size of every member (deflateBound + gzip header / trailer)
+  z_stream probe;
+  memset(&probe, 0, sizeof probe);
+  if (deflateInit2(&probe, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return PF_ERR_INTERNAL;
+  const uint64_t bound_full = deflateBound(&probe, (uLong)std::min<uint64_t>(member_bytes, len)) + 32;
+  deflateEnd(&probe);
+  *out_len = n_members * bound_full;                                    // an upper bound when out == NULL
+  if (!out) return PF_OK;
+  std::vector<std::vector<unsigned char>> parts(n_members);
+  std::vector<int> rc(n_members, Z_OK);
+  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  uint32_t nt = n_threads ? n_threads : hw;
+  nt = (uint32_t)std::min<uint64_t>(nt, n_members);
+  std::atomic<uint32_t> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const uint32_t m = next.fetch_add(1);
+      if (m >= n_members) return;
+      const uint64_t a = (uint64_t)m * member_bytes, b = std::min(len, a + member_bytes);
+      z_stream z;
+      memset(&z, 0, sizeof z);
+      if (deflateInit2(&z, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) { rc[m] = Z_MEM_ERROR; continue; }
+      parts[m].resize(deflateBound(&z, (uLong)(b - a)) + 32);
+      z.next_in = reinterpret_cast<Bytef*>(const_cast<char*>(text ? text + a : ""));
+      z.avail_in = (uInt)(b - a);
+      z.next_out = parts[m].data();
+      z.avail_out = (uInt)parts[m].size();
+      const int r = deflate(&z, Z_FINISH);
+      rc[m] = r == Z_STREAM_END ? Z_OK : (r == Z_OK ? Z_BUF_ERROR : r);
+      parts[m].resize(z.total_out);
+      deflateEnd(&z);
+    }
+  };
+  if (nt <= 1) work();
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < nt; ++t) th.emplace_back(work);
+    for (auto& x : th) x.join();
+  }
+  uint64_t total = 0;
+  for (uint64_t m = 0; m < n_members; ++m) {
+    if (rc[m] != Z_OK) return PF_ERR_INTERNAL;
+    total += parts[m].size();
+  }
+  *out_len = total;
+  if (out_cap < total) return PF_ERR_NOMEM;
+  uint64_t at = 0;
+  for (uint64_t m = 0; m < n_members; ++m) {
+    memcpy(out + at, parts[m].data(), parts[m].size());
+    at += parts[m].size();
   }
   return PF_OK;
 }

@@ -12,7 +12,6 @@ Behavioural spec: SURVEY.md App. A1.  Differences from the reference, on purpose
     silently producing misaligned presence vectors (reference defect,
     SURVEY.md App. A1.4).
 """
-import gzip
 import logging
 import os
 import sys
@@ -138,10 +137,63 @@ def clean_up_fasta(filelist, fastalist, output, fastadir):
     return None
 
 
+class GzipTextWriter:
+    """Text handle over a .gz file, like gzip.open(path, "wt", compresslevel=9) (input.py:235-259),
+    but the deflate runs on the library's host threads: text is collected and written as a run of
+    complete gzip members (pf_gzip_members) whenever `flush_bytes` have accumulated.  Any gzip
+    reader sees one stream; unlike the reference's handles this one is also safe to fill from the
+    single writer of a multi-core run."""
+
+    def __init__(self, path, level=9, flush_bytes=64 << 20):
+        self.f = open(path, "wb")
+        self.level = level
+        self.flush_bytes = flush_bytes
+        self.parts = []
+        self.size = 0
+        self.wrote = False
+
+    def write(self, text):
+        if not text:
+            return 0
+        data = text.encode() if isinstance(text, str) else bytes(text)
+        self.parts.append(data)
+        self.size += len(data)
+        if self.size >= self.flush_bytes:
+            self._emit()
+        return len(text)
+
+    def _emit(self):
+        if self.size == 0:
+            return
+        from . import capi
+        self.f.write(capi.gzip_members(b"".join(self.parts), self.level))
+        self.parts, self.size, self.wrote = [], 0, True
+
+    def flush(self):
+        """Keeps the text buffered (a gzip member per flush() would bloat the file); the file on
+        disk is complete after close()."""
+        self.f.flush()
+
+    def close(self):
+        if self.f.closed:
+            return
+        self._emit()
+        if not self.wrote:                      # nothing was written: still a valid (empty) gzip file
+            from . import capi
+            self.f.write(capi.gzip_members(b"", self.level))
+        self.f.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def create_kmer_stroi(output, compress=False):
     """kmers.tsv(.gz) with its header.  input.py:235-246."""
     if compress:
-        handle = gzip.open(os.path.join(output, "kmers.tsv.gz"), "wt", compresslevel=9)
+        handle = GzipTextWriter(os.path.join(output, "kmers.tsv.gz"))
     else:
         handle = open(os.path.join(output, "kmers.tsv"), "w")
     handle.write("cluster\tstrain\tfeature_id\tcontig\tfeature_strand\tcontig_start\t"
@@ -153,8 +205,8 @@ def create_kmer_stroi(output, compress=False):
 def create_hash_files(output, compress=False):
     """(hashes_to_patterns, kmers_to_hashes) handles.  input.py:249-259."""
     if compress:
-        return (gzip.open(os.path.join(output, "hashes_to_patterns.tsv.gz"), "wt", compresslevel=9),
-                gzip.open(os.path.join(output, "kmers_to_hashes.tsv.gz"), "wt", compresslevel=9))
+        return (GzipTextWriter(os.path.join(output, "hashes_to_patterns.tsv.gz")),
+                GzipTextWriter(os.path.join(output, "kmers_to_hashes.tsv.gz")))
     return (open(os.path.join(output, "hashes_to_patterns.tsv"), "w"),
             open(os.path.join(output, "kmers_to_hashes.tsv"), "w"))
 

@@ -179,3 +179,44 @@ def test_native_kmer_rows_reject_bad_indices():
     r["row_pattern"] = np.array([0, 1], np.uint32)
     with pytest.raises(capi.PfError):
         capi.format_kmer_rows(r, 5, [b"0", b"1"], ids, ids)          # pattern 1 of 1
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+@pytest.mark.parametrize("member_bytes", [0, 1 << 16, 1 << 20])
+def test_native_gzip_members_round_trip(threads, member_bytes):
+    """pf_gzip_members: independently deflated members, concatenated - Python's gzip must read
+    them back as the one text (what `--compress` readers do with the three outputs)."""
+    import gzip
+    rng = np.random.default_rng(member_bytes + threads)
+    rows = [b"%d\t%s\t%s\n" % (i % 97, bytes(rng.choice(np.frombuffer(b"ACGT", np.uint8), 31)), b"x" * 22 + b"==")
+            for i in range(40_000)]
+    data = b"".join(rows)
+    z = capi.gzip_members(data, 9, member_bytes, threads)
+    assert gzip.decompress(z) == data
+    assert len(z) < len(data) // 2
+    if member_bytes == 1 << 16:
+        assert z.count(b"\x1f\x8b\x08") >= len(data) // member_bytes      # one header per member
+    # pieces written one after the other form one stream
+    assert gzip.decompress(capi.gzip_members(data[:1000], 1) + capi.gzip_members(data[1000:5000], 9)) == data[:5000]
+    assert gzip.decompress(capi.gzip_members(b"")) == b""
+
+
+def test_gzip_text_writer_matches_gzip_open(tmp_path):
+    """The --compress handles of the host mirror: same text back as gzip.open(..., "wt")."""
+    import gzip
+    from panfeed_b200.input import GzipTextWriter
+    path = str(tmp_path / "kmers_to_hashes.tsv.gz")
+    w = GzipTextWriter(path, flush_bytes=10_000)
+    text = []
+    for i in range(3000):
+        row = f"{i}\t{'ACGT' * 7}\t{'h' * 22}==\n"
+        w.write(row)
+        text.append(row)
+        if i % 500 == 0:
+            w.flush()
+    w.close()
+    w.close()
+    assert gzip.open(path, "rt").read() == "".join(text)
+    empty = str(tmp_path / "empty.tsv.gz")
+    GzipTextWriter(empty).close()
+    assert gzip.open(empty, "rt").read() == ""
