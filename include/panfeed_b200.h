@@ -334,6 +334,55 @@ int pf_exchange_unpack(pf_ctx* ctx, int cluster_namespace,
                        const uint32_t* returned_ids_dev, /* in send order */
                        uint32_t* local_to_global_dev /* [n local patterns] */);
 
+/* ---- native feeder (host threads of the caller): GFF3 + FASTA -> cut sequences of a cluster ----
+ * Replaces, for the feeding side of the path, the reference's parse_gff (input.py:274-332), its
+ * pyfaidx contigs (input.py:262-266) and the per-strain loop of iter_gene_clusters
+ * (input.py:335-468, window arithmetic :413-446).  Genomes are parsed once; a cluster is cut by one
+ * call into ASCII sequences + descriptors that pf_pack_plan / pf_pack_2bit / pf_pack_4bit read as
+ * they are.  Semantics are those of the reference line by line (malformed GFF lines are skipped
+ * and counted, a repeated feature id / contig name replaces the earlier one, slices clamp like
+ * Python's, the minus strand is reverse-complemented with pyfaidx's table). */
+typedef struct pf_feeder pf_feeder;
+
+typedef struct pf_cut_result {
+  uint32_t n_seqs;
+  const char*     ascii;      /* the sequences, back to back (upper case as read)                    */
+  const uint64_t* seq_off;    /* [n_seqs + 1] offsets into ascii                                     */
+  const uint32_t* cell;       /* [n_seqs] index of the panaroo cell (= strain) the sequence is from  */
+  const uint32_t* feature;    /* [n_seqs] feature index inside that strain's genome (pf_feeder_feature) */
+  const int32_t*  start;      /* Seqinfo.start / end / offset / strand (classes.py:11-18)            */
+  const int32_t*  end;
+  const int32_t*  offset;
+  const int32_t*  strand;
+  uint32_t n_missing;         /* feature ids (kind 0) / contigs (kind 1) that were not found:        */
+  const uint32_t* missing_cell;   /* the reference logs a warning and skips the gene (input.py:396-411) */
+  const uint8_t*  missing_kind;
+  const char*     missing_text;   /* names, back to back                                             */
+  const uint64_t* missing_off;    /* [n_missing + 1]                                                 */
+} pf_cut_result;
+
+int  pf_feeder_create(pf_feeder** out);
+void pf_feeder_destroy(pf_feeder* f);
+const char* pf_feeder_last_error(const pf_feeder* f);
+/* One genome: CDS features with an ID= attribute from the GFF3 (up to "##FASTA"), contigs from
+ * fasta_path or, if NULL, from the GFF's ##FASTA section.  Returns the genome's index (>= 0, in
+ * order of the calls) or a negative PF_ERR_*.  skipped_lines (may be NULL): malformed GFF lines. */
+int  pf_feeder_add_genome(pf_feeder* f, const char* name, const char* gff_path, const char* fasta_path,
+                          uint32_t* skipped_lines);
+int  pf_feeder_add_genome_text(pf_feeder* f, const char* name, const char* gff, uint64_t gff_len,
+                               const char* fasta /* NULL: ##FASTA section of gff */, uint64_t fasta_len,
+                               uint32_t* skipped_lines);
+int  pf_feeder_genome_info(const pf_feeder* f, uint32_t genome, uint32_t* n_features, uint32_t* n_contigs,
+                           uint64_t* n_bases);
+int  pf_feeder_feature(const pf_feeder* f, uint32_t genome, uint32_t feature, const char** id,
+                       const char** contig, int64_t* start, int64_t* end, int32_t* strand);
+/* One cluster: cells_blob = the n_cells panaroo cells (';'-separated feature ids) of the strains
+ * that have the cluster, joined with '\n'; genome[i] = genome index of cell i.  The result (valid
+ * until the next call on this feeder) lists the sequences cell by cell, genes in cell order. */
+int  pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
+                   uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
+                   pf_cut_result* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,9 @@ def get_options(argv=None):
     p.add_argument("--consider-missing", action="store_true", default=False)
     p.add_argument("--multiple-files", action="store_true", default=False)
     p.add_argument("--compress", action="store_true", default=False)
+    p.add_argument("--native-feeder", action="store_true", default=False,
+                   help="parse GFF/FASTA and cut the cluster sequences in the library (pf_feeder_*) "
+                        "instead of the Python loops; same outputs")
     p.add_argument("--cores", type=int, default=1, help="accepted for compatibility (GPU build)")
     p.add_argument("-ql", "--queue-limit", type=int, default=3,
                    help="accepted for compatibility (GPU build)")
@@ -84,25 +87,33 @@ def main(argv=None):
         args.targets, args.genes, args.presence_absence, args.output,
         not args.multiple_files, args.compress)
     logger.info("Preparing inputs")
-    data = prep_data_n_fasta(filelist, fastalist, args.gff, args.fasta, args.output)
     if not args.multiple_files:
         write_headers(hash_pat, kmer_hash, genepres)
-
     logger.info("Extracting k-mers")
-    iter_i = iter_gene_clusters(genepres, data, args.upstream, args.downstream,
-                                args.downstream_start_codon, not args.no_filter, genes,
-                                args.stop_on_missing)
-    iter_o = partial(cluster_cutter, klength=klength, stroi=stroi,
-                     multiple_files=args.multiple_files, canon=not args.non_canonical,
-                     consider_missing_cluster=args.consider_missing, output=args.output,
-                     compress=args.compress)
+    if args.native_feeder:
+        from .feeder import iter_packed_clusters, prep_feeder
+        native, genome_index = prep_feeder(filelist, fastalist, args.gff, args.fasta, args.output)
+        cut_clusters = iter_packed_clusters(genepres, native, genome_index, args.upstream, args.downstream,
+                                            args.downstream_start_codon, stroi, klength,
+                                            not args.non_canonical, args.consider_missing, genes,
+                                            args.stop_on_missing)
+    else:
+        data = prep_data_n_fasta(filelist, fastalist, args.gff, args.fasta, args.output)
+        iter_i = iter_gene_clusters(genepres, data, args.upstream, args.downstream,
+                                    args.downstream_start_codon, not args.no_filter, genes,
+                                    args.stop_on_missing)
+        iter_o = partial(cluster_cutter, klength=klength, stroi=stroi,
+                         multiple_files=args.multiple_files, canon=not args.non_canonical,
+                         consider_missing_cluster=args.consider_missing, output=args.output,
+                         compress=args.compress)
+        cut_clusters = (iter_o(x) for x in iter_i)
     patterns = PatternStore()
     func_w = partial(pattern_hasher, kmer_stroi=kmer_stroi, hash_pat=hash_pat,
                      kmer_hash=kmer_hash, genepres=genepres, patfilt=not args.no_filter,
                      maf=args.maf, consider_missing_cluster=args.consider_missing,
                      output=args.output, compress=args.compress, device=args.device)
     # one streaming call: the generator packs clusters while the GPU batches them
-    patterns = func_w((iter_o(x) for x in iter_i), patterns=patterns)
+    patterns = func_w(cut_clusters, patterns=patterns)
     patterns.close()
 
     for handle in (kmer_stroi, hash_pat, kmer_hash):

@@ -105,11 +105,31 @@ class SynthParams(C.Structure):
                 ("total_clusters", C.c_uint32), ("all_targets", C.c_uint32)]
 
 
+class CutResult(C.Structure):
+    """pf_cut_result (include/panfeed_b200.h)."""
+    _fields_ = [("n_seqs", C.c_uint32),
+                ("ascii", C.c_void_p),
+                ("seq_off", C.POINTER(C.c_uint64)),
+                ("cell", C.POINTER(C.c_uint32)),
+                ("feature", C.POINTER(C.c_uint32)),
+                ("start", C.POINTER(C.c_int32)),
+                ("end", C.POINTER(C.c_int32)),
+                ("offset", C.POINTER(C.c_int32)),
+                ("strand", C.POINTER(C.c_int32)),
+                ("n_missing", C.c_uint32),
+                ("missing_cell", C.POINTER(C.c_uint32)),
+                ("missing_kind", C.POINTER(C.c_uint8)),
+                ("missing_text", C.c_void_p),
+                ("missing_off", C.POINTER(C.c_uint64))]
+
+
 EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_upload", "pf_execute", "pf_submit", "pf_collect",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
            "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream", "pf_format_positions",
            "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns", "pf_format_kmer_rows", "pf_gzip_members",
+           "pf_feeder_create", "pf_feeder_destroy", "pf_feeder_last_error", "pf_feeder_add_genome",
+           "pf_feeder_add_genome_text", "pf_feeder_genome_info", "pf_feeder_feature", "pf_feeder_cut",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_export",
            "pf_exchange_unpack"]
@@ -148,6 +168,18 @@ def load():
     lib.pf_format_kmer_rows.argtypes = [C.POINTER(BatchResult), u32, C.c_char_p, vp, vp, u64, vp, u64, vp, u64,
                                         C.POINTER(u64), vp, u32]
     lib.pf_gzip_members.argtypes = [C.c_char_p, u64, C.c_int, u64, vp, u64, C.POINTER(u64), u32]
+    lib.pf_feeder_create.argtypes = [C.POINTER(vp)]
+    lib.pf_feeder_destroy.argtypes = [vp]
+    lib.pf_feeder_destroy.restype = None
+    lib.pf_feeder_last_error.argtypes = [vp]
+    lib.pf_feeder_last_error.restype = C.c_char_p
+    lib.pf_feeder_add_genome.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(u32)]
+    lib.pf_feeder_add_genome_text.argtypes = [vp, C.c_char_p, C.c_char_p, u64, C.c_char_p, u64, C.POINTER(u32)]
+    lib.pf_feeder_genome_info.argtypes = [vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
+    lib.pf_feeder_feature.argtypes = [vp, u32, u32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
+                                      C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    lib.pf_feeder_cut.argtypes = [vp, u32, vp, C.c_char_p, u64, C.c_int32, C.c_int32, C.c_int32,
+                                  C.POINTER(CutResult)]
     lib.pf_pack_plan.argtypes = [vp, u32, vp, C.POINTER(u64)]
     lib.pf_pack_2bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, u32]
     lib.pf_pack_4bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, C.POINTER(u64), C.POINTER(C.c_int)]
@@ -180,12 +212,20 @@ def pack_sequences(seq_bytes, n_threads=0):
     """Native packer (pf_pack_*): list of upper-case ASCII sequences -> (packed 2-bit plane,
     base_off, is_amb, amb_plane or None, amb_off).  Raises ValueError on a symbol outside
     AMB_ALPHABET."""
-    lib = load()
     n = len(seq_bytes)
     blob = b"".join(seq_bytes)
     seq_off = np.zeros(n + 1, np.uint64)
     if n:
         np.cumsum(np.fromiter((len(b) for b in seq_bytes), np.uint64, n), out=seq_off[1:])
+    return pack_blob(blob, seq_off, n_threads)
+
+
+def pack_blob(blob, seq_off, n_threads=0):
+    """The same from the sequences back to back (`blob`, bytes) and their offsets
+    (`seq_off`, uint64 [n + 1]): what the native feeder hands over."""
+    lib = load()
+    seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
+    n = len(seq_off) - 1
     base_off = np.zeros(n, np.uint64)
     n_words = C.c_uint64()
     rc = lib.pf_pack_plan(seq_off.ctypes.data, n, base_off.ctypes.data, C.byref(n_words))

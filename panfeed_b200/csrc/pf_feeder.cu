@@ -1,0 +1,389 @@
+// Native feeder (host only): GFF3 + FASTA -> the cut, oriented sequences of gene clusters.
+//
+// What the reference does per cluster in Python (/root/reference/panfeed/input.py): parse_gff
+// (:274-332, CDS features with an ID= attribute), the pyfaidx contigs (:262-266, upper case),
+// and iter_gene_clusters (:335-468: per present strain the ';'-separated feature ids of the
+// panaroo cell, the up/downstream window of :413-446, reverse complement on the minus strand).
+// At ~1 us of interpreter time per attribute access that loop cannot feed one GPU at BASELINE
+// configs #4 / #5.  Here the genomes are parsed once into flat arrays and a
+// cluster is cut by one call that appends ASCII sequences + descriptors to buffers the packer
+// (pf_pack_2bit / pf_pack_4bit) reads directly.  Semantics follow panfeed_b200/input.py (the Python
+// mirror of the reference, which the CPU tests compare this file with) line by line, including
+// Python's slice clamping and the tolerance for malformed GFF lines.  No device code in this file.
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/panfeed_b200.h"
+
+namespace {
+
+struct FeatureRec {
+  std::string id, contig;
+  int64_t start = 0, end = 0;
+  int32_t strand = 1;
+};
+
+struct Genome {
+  std::string name;
+  std::vector<FeatureRec> features;
+  std::unordered_map<std::string, uint32_t> feature_of;       // id -> index (the last one wins)
+  std::vector<std::string> contig_name, contig_seq;
+  std::unordered_map<std::string, uint32_t> contig_of;        // name -> index (the last one wins)
+};
+
+inline bool str_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 && c <= 31); }
+
+// Python's int(str): optional whitespace, sign, decimal digits with single underscores between them
+bool py_int(const char* p, const char* e, int64_t* out) {
+  while (p < e && str_space((unsigned char)*p)) ++p;
+  while (e > p && str_space((unsigned char)e[-1])) --e;
+  if (p == e) return false;
+  bool neg = false;
+  if (*p == '+' || *p == '-') { neg = *p == '-'; ++p; }
+  if (p == e || *p < '0' || *p > '9') return false;
+  int64_t v = 0;
+  bool last_us = false;
+  for (; p < e; ++p) {
+    if (*p == '_') { if (last_us) return false; last_us = true; continue; }
+    if (*p < '0' || *p > '9') return false;
+    last_us = false;
+    if (v > (INT64_MAX - 9) / 10) return false;
+    v = v * 10 + (*p - '0');
+  }
+  if (last_us) return false;
+  *out = neg ? -v : v;
+  return true;
+}
+
+// text-mode reading like Python's open(path): "\r\n" and lone "\r" become "\n"
+bool read_text(const char* path, std::string* out) {
+  FILE* f = fopen(path, "rb");
+  if (!f) return false;
+  std::string raw;
+  char buf[1 << 16];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) raw.append(buf, n);
+  fclose(f);
+  out->clear();
+  out->reserve(raw.size());
+  for (size_t i = 0; i < raw.size(); ++i) {
+    if (raw[i] == '\r') {
+      out->push_back('\n');
+      if (i + 1 < raw.size() && raw[i + 1] == '\n') ++i;
+    } else {
+      out->push_back(raw[i]);
+    }
+  }
+  return true;
+}
+
+// input.py parse_gff (reference :274-332): lines up to "##FASTA"; cols[2] == "CDS"; int(cols[3]),
+// int(cols[4]); strand '+' -> 1 else -1; every ';' field of cols[8] that starts with "ID" and holds
+// '=' sets the id to the text between its first and second '='; lines that raise are skipped.
+void parse_gff_text(const char* p, const char* e, Genome* g, uint32_t* skipped) {
+  while (p < e) {
+    const char* nl = (const char*)memchr(p, '\n', e - p);
+    const char* le = nl ? nl + 1 : e;                 // the line, newline included (as Python iterates)
+    const char* h = p;
+    while (h < le && str_space((unsigned char)*h)) ++h;
+    if (le - h >= 7 && memcmp(h, "##FASTA", 7) == 0) break;
+    if (h < le && *h == '#') { p = le; continue; }
+    const char* col[10];
+    int nc = 0;
+    col[nc++] = p;
+    for (const char* q = p; q < le && nc < 10; ++q)
+      if (*q == '\t') col[nc++] = q + 1;
+    // col[i] .. col[i+1]-1 is column i; the last parsed column runs to the end of the line unless more tabs follow
+    auto col_end = [&](int i) -> const char* {
+      if (i + 1 < nc) return col[i + 1] - 1;
+      const char* q = col[i];
+      while (q < le && *q != '\t') ++q;
+      return q;
+    };
+    bool bad = false;
+    do {
+      if (nc < 3) { bad = true; break; }              // cols[2] raises IndexError
+      const char* t0 = col[2];
+      const char* t1 = col_end(2);
+      if (!(t1 - t0 == 3 && memcmp(t0, "CDS", 3) == 0)) break;      // not wanted: skipped silently
+      if (nc < 5) { bad = true; break; }
+      int64_t start, end;
+      if (!py_int(col[3], col_end(3), &start) || !py_int(col[4], col_end(4), &end)) { bad = true; break; }
+      if (nc < 7) { bad = true; break; }
+      const int32_t strand = (col_end(6) - col[6] == 1 && *col[6] == '+') ? 1 : -1;
+      if (nc < 9) { bad = true; break; }
+      const char* a0 = col[8];
+      const char* a1 = col_end(8);
+      bool have = false;
+      std::string ident;
+      for (const char* f0 = a0; f0 <= a1;) {
+        const char* f1 = (const char*)memchr(f0, ';', a1 - f0);
+        if (!f1) f1 = a1;
+        if (f1 - f0 >= 2 && f0[0] == 'I' && f0[1] == 'D') {
+          const char* eq = (const char*)memchr(f0, '=', f1 - f0);
+          if (eq) {
+            const char* eq2 = (const char*)memchr(eq + 1, '=', f1 - (eq + 1));
+            ident.assign(eq + 1, eq2 ? eq2 : f1);
+            have = true;
+          }
+        }
+        f0 = f1 + 1;
+      }
+      if (!have) break;
+      FeatureRec fr;
+      fr.id = ident;
+      fr.contig.assign(col[0], col_end(0));
+      fr.start = start; fr.end = end; fr.strand = strand;
+      auto it = g->feature_of.find(ident);
+      if (it == g->feature_of.end()) {
+        g->feature_of.emplace(ident, (uint32_t)g->features.size());
+        g->features.push_back(std::move(fr));
+      } else {
+        g->features[it->second] = std::move(fr);      // dict assignment: the last line wins
+      }
+    } while (false);
+    if (bad) ++*skipped;
+    p = le;
+  }
+}
+
+// input.py read_fasta_text: '>' lines name a record (first whitespace-separated word, "" if none),
+// other lines are stripped and appended; sequences are upper-cased; a repeated name replaces.
+void parse_fasta_text(const char* p, const char* e, Genome* g) {
+  bool have = false;
+  std::string name, seq;
+  auto close = [&]() {
+    if (!have) return;
+    for (char& c : seq) if (c >= 'a' && c <= 'z') c = (char)(c - 32);
+    auto it = g->contig_of.find(name);
+    if (it == g->contig_of.end()) {
+      g->contig_of.emplace(name, (uint32_t)g->contig_name.size());
+      g->contig_name.push_back(name);
+      g->contig_seq.push_back(std::move(seq));
+    } else {
+      g->contig_seq[it->second] = std::move(seq);
+    }
+    seq.clear();
+  };
+  while (p < e) {
+    const char* nl = (const char*)memchr(p, '\n', e - p);
+    const char* le = nl ? nl : e;
+    const char* l1 = le;
+    while (l1 > p && (l1[-1] == '\r' || l1[-1] == '\n')) --l1;
+    if (l1 > p && *p == '>') {
+      close();
+      const char* q = p + 1;
+      while (q < l1 && str_space((unsigned char)*q)) ++q;
+      const char* w = q;
+      while (w < l1 && !str_space((unsigned char)*w)) ++w;
+      name.assign(q, w);
+      have = true;
+    } else if (have) {
+      const char* a = p;
+      const char* b = l1;
+      while (a < b && str_space((unsigned char)*a)) ++a;
+      while (b > a && str_space((unsigned char)b[-1])) --b;
+      seq.append(a, b);
+    }
+    p = nl ? nl + 1 : e;
+  }
+  close();
+}
+
+// pyfaidx's complement table restricted to upper case (input.py:448-452 uses it on upper-case contigs)
+struct CompLut {
+  unsigned char t[256];
+  CompLut() {
+    for (int i = 0; i < 256; ++i) t[i] = (unsigned char)i;
+    const char* a = "ACTGNactgnYRWSKMDVHBXyrwskmdvhbx";
+    const char* b = "TGACNtgacnRYWSMKHBDVXrywsmkhbdvx";
+    for (int i = 0; a[i]; ++i) t[(unsigned char)a[i]] = (unsigned char)b[i];
+  }
+};
+const CompLut kComp;
+
+}  // namespace
+
+struct pf_feeder {
+  std::vector<Genome> genomes;
+  std::string err;
+  // result of the last pf_feeder_cut
+  std::string ascii;
+  std::vector<uint64_t> seq_off;
+  std::vector<uint32_t> cell, feature;
+  std::vector<int32_t> start, end, offset, strand;
+  std::vector<uint32_t> miss_cell;
+  std::vector<uint8_t> miss_kind;
+  std::string miss_text;
+  std::vector<uint64_t> miss_off;
+};
+
+extern "C" int pf_feeder_create(pf_feeder** out) {
+  if (!out) return PF_ERR_INVALID;
+  *out = new pf_feeder();
+  return PF_OK;
+}
+
+extern "C" void pf_feeder_destroy(pf_feeder* f) { delete f; }
+
+extern "C" const char* pf_feeder_last_error(const pf_feeder* f) { return f ? f->err.c_str() : "null feeder"; }
+
+extern "C" int pf_feeder_add_genome_text(pf_feeder* f, const char* name, const char* gff, uint64_t gff_len,
+                                         const char* fasta, uint64_t fasta_len, uint32_t* skipped_lines) {
+  if (!f || !name || (!gff && gff_len)) return PF_ERR_INVALID;
+  Genome g;
+  g.name = name;
+  uint32_t skipped = 0;
+  parse_gff_text(gff, gff + gff_len, &g, &skipped);
+  if (fasta) {
+    parse_fasta_text(fasta, fasta + fasta_len, &g);
+  } else {
+    // open(gff).read().split("##FASTA")[1]: the text between the first and the second marker
+    const std::string text(gff, gff_len);
+    const size_t a = text.find("##FASTA");
+    if (a == std::string::npos) {
+      f->err = std::string("genome ") + name + ": no FASTA file and no ##FASTA section in the GFF";
+      return PF_ERR_INVALID;
+    }
+    size_t b = text.find("##FASTA", a + 7);
+    if (b == std::string::npos) b = text.size();
+    parse_fasta_text(text.data() + a + 7, text.data() + b, &g);
+  }
+  if (skipped_lines) *skipped_lines = skipped;
+  f->genomes.push_back(std::move(g));
+  return (int)f->genomes.size() - 1;
+}
+
+extern "C" int pf_feeder_add_genome(pf_feeder* f, const char* name, const char* gff_path, const char* fasta_path,
+                                    uint32_t* skipped_lines) {
+  if (!f || !name || !gff_path) return PF_ERR_INVALID;
+  std::string gff, fasta;
+  if (!read_text(gff_path, &gff)) { f->err = std::string("cannot read ") + gff_path; return PF_ERR_INVALID; }
+  if (fasta_path && !read_text(fasta_path, &fasta)) { f->err = std::string("cannot read ") + fasta_path; return PF_ERR_INVALID; }
+  return pf_feeder_add_genome_text(f, name, gff.data(), gff.size(), fasta_path ? fasta.data() : nullptr, fasta.size(),
+                                   skipped_lines);
+}
+
+extern "C" int pf_feeder_genome_info(const pf_feeder* f, uint32_t genome, uint32_t* n_features, uint32_t* n_contigs,
+                                     uint64_t* n_bases) {
+  if (!f || genome >= f->genomes.size()) return PF_ERR_INVALID;
+  const Genome& g = f->genomes[genome];
+  if (n_features) *n_features = (uint32_t)g.features.size();
+  if (n_contigs) *n_contigs = (uint32_t)g.contig_name.size();
+  if (n_bases) { uint64_t n = 0; for (auto& s : g.contig_seq) n += s.size(); *n_bases = n; }
+  return PF_OK;
+}
+
+extern "C" int pf_feeder_feature(const pf_feeder* f, uint32_t genome, uint32_t feature, const char** id,
+                                 const char** contig, int64_t* start, int64_t* end, int32_t* strand) {
+  if (!f || genome >= f->genomes.size() || feature >= f->genomes[genome].features.size()) return PF_ERR_INVALID;
+  const FeatureRec& r = f->genomes[genome].features[feature];
+  if (id) *id = r.id.c_str();
+  if (contig) *contig = r.contig.c_str();
+  if (start) *start = r.start;
+  if (end) *end = r.end;
+  if (strand) *strand = r.strand;
+  return PF_OK;
+}
+
+// One cluster (input.py:335-468 / cut_window): cells_blob holds n_cells panaroo cells separated by
+// '\n'; cell i belongs to genome genome[i].  For every ';'-separated feature id, in order: the
+// feature and its contig are looked up (a miss is recorded, the gene skipped), the window
+// [a, b) is sliced with Python's clamping and, on the minus strand, reverse-complemented.
+extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
+                             uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
+                             pf_cut_result* out) {
+  if (!f || !out || (n_cells && (!genome || !cells_blob))) return PF_ERR_INVALID;
+  f->ascii.clear();
+  f->seq_off.assign(1, 0);
+  f->cell.clear(); f->feature.clear();
+  f->start.clear(); f->end.clear(); f->offset.clear(); f->strand.clear();
+  f->miss_cell.clear(); f->miss_kind.clear(); f->miss_text.clear(); f->miss_off.assign(1, 0);
+  const char* p = cells_blob;
+  const char* e = cells_blob + cells_len;
+  std::string gene;
+  for (uint32_t ci = 0; ci < n_cells; ++ci) {
+    if (genome[ci] >= f->genomes.size()) { f->err = "pf_feeder_cut: genome index out of range"; return PF_ERR_INVALID; }
+    const Genome& g = f->genomes[genome[ci]];
+    const char* ce = (const char*)memchr(p, '\n', e - p);
+    if (!ce) {
+      if (ci + 1 != n_cells) { f->err = "pf_feeder_cut: fewer cells in the blob than n_cells"; return PF_ERR_INVALID; }
+      ce = e;
+    }
+    for (const char* g0 = p; g0 <= ce;) {
+      const char* g1 = (const char*)memchr(g0, ';', ce - g0);
+      if (!g1) g1 = ce;
+      gene.assign(g0, g1);
+      g0 = g1 + 1;
+      auto miss = [&](uint8_t kind, const std::string& what) {
+        f->miss_cell.push_back(ci);
+        f->miss_kind.push_back(kind);
+        f->miss_text += what;
+        f->miss_off.push_back(f->miss_text.size());
+      };
+      auto fi = g.feature_of.find(gene);
+      if (fi == g.feature_of.end()) { miss(0, gene); continue; }
+      const FeatureRec& ft = g.features[fi->second];
+      auto cit = g.contig_of.find(ft.contig);
+      if (cit == g.contig_of.end()) { miss(1, ft.contig); continue; }
+      const std::string& contig = g.contig_seq[cit->second];
+      // cut_window (reference input.py:413-446)
+      const bool over_up = ft.strand > 0 && ft.start - 1 - up < 0;
+      const bool over_down = ft.strand < 0 && ft.start - 1 - down < 0;
+      const int64_t offset = over_up ? ft.start - 1 : up;
+      const int64_t offset_d = over_down ? ft.start - 1 : down;
+      int64_t a, b, seq_start, seq_end;
+      if (ft.strand > 0) {
+        a = ft.start - 1 - offset;
+        seq_start = ft.start - offset;
+        b = seq_end = (down_start_codon ? ft.start : ft.end) + offset_d;
+      } else {
+        b = seq_end = ft.end + offset;
+        if (down_start_codon) { a = ft.end - 1 - offset_d; seq_start = ft.end - offset_d; }
+        else { a = ft.start - 1 - offset_d; seq_start = ft.start - offset_d; }
+      }
+      // contig[a:b] with Python's slice semantics
+      const int64_t n = (int64_t)contig.size();
+      int64_t lo = a < 0 ? std::max<int64_t>(a + n, 0) : std::min(a, n);
+      int64_t hi = b < 0 ? std::max<int64_t>(b + n, 0) : std::min(b, n);
+      if (hi < lo) hi = lo;
+      const size_t at = f->ascii.size();
+      f->ascii.resize(at + (size_t)(hi - lo));
+      char* dst = &f->ascii[0] + at;
+      if (ft.strand < 0) {
+        for (int64_t i = 0; i < hi - lo; ++i) dst[i] = (char)kComp.t[(unsigned char)contig[(size_t)(hi - 1 - i)]];
+      } else if (hi > lo) {
+        memcpy(dst, contig.data() + lo, (size_t)(hi - lo));
+      }
+      f->seq_off.push_back(f->ascii.size());
+      f->cell.push_back(ci);
+      f->feature.push_back(fi->second);
+      f->start.push_back((int32_t)seq_start);
+      f->end.push_back((int32_t)seq_end);
+      f->offset.push_back((int32_t)offset);
+      f->strand.push_back(ft.strand);
+    }
+    p = ce < e ? ce + 1 : e;
+  }
+  memset(out, 0, sizeof *out);
+  out->n_seqs = (uint32_t)f->cell.size();
+  out->ascii = f->ascii.data();
+  out->seq_off = f->seq_off.data();
+  out->cell = f->cell.data();
+  out->feature = f->feature.data();
+  out->start = f->start.data();
+  out->end = f->end.data();
+  out->offset = f->offset.data();
+  out->strand = f->strand.data();
+  out->n_missing = (uint32_t)f->miss_cell.size();
+  out->missing_cell = f->miss_cell.data();
+  out->missing_kind = f->miss_kind.data();
+  out->missing_text = f->miss_text.data();
+  out->missing_off = f->miss_off.data();
+  return PF_OK;
+}

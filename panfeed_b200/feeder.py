@@ -1,0 +1,239 @@
+"""Native feeder: GFF3/FASTA parsing and per-cluster sequence cutting in the library
+(`pf_feeder_*`, csrc/pf_feeder.cu) instead of the Python loops of `input.py`.
+
+`prep_feeder` stands where `input.prep_data_n_fasta` does (reference input.py:68-138) and
+`iter_packed_clusters` where `iter_gene_clusters` + `cluster_cutter` do (input.py:335-468,
+panfeed.py:23-113): it yields the 4-tuples `pattern_hasher` consumes, with a `NativePackedCluster`
+whose sequences are one ASCII blob the native packer reads without a Python object per
+sequence.  The Python path stays the behavioural reference; `tests/test_feeder_native.py`
+checks that both produce identical batches on the fixture genomes.
+"""
+import ctypes as C
+import logging
+import os
+import sys
+
+import numpy as np
+import pandas as pd
+
+from . import capi
+from .input import _genome_name, _listing
+
+logger = logging.getLogger("panfeed.input")
+
+
+class NativeFeeder:
+    """Genomes parsed once by the library; `cut` returns the sequences of one cluster."""
+
+    def __init__(self):
+        self.lib = capi.load()
+        self.h = C.c_void_p()
+        rc = self.lib.pf_feeder_create(C.byref(self.h))
+        if rc != 0:
+            raise capi.PfError(rc, "pf_feeder_create failed")
+        self.names = []
+        self._feature_names = {}
+
+    def close(self):
+        if self.h:
+            self.lib.pf_feeder_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _error(self, rc, what):
+        msg = self.lib.pf_feeder_last_error(self.h)
+        raise capi.PfError(rc, f"{what}: {msg.decode() if msg else ''}")
+
+    def add_genome(self, name, gff_path, fasta_path=None):
+        """-> genome index.  Malformed GFF lines are skipped like the reference does
+        (input.py:326-330), with one warning per file."""
+        skipped = C.c_uint32()
+        rc = self.lib.pf_feeder_add_genome(self.h, name.encode(), os.fsencode(gff_path),
+                                           None if fasta_path is None else os.fsencode(fasta_path),
+                                           C.byref(skipped))
+        if rc < 0:
+            self._error(rc, f"reading {gff_path}")
+        if skipped.value:
+            logger.warning(f"skipped {skipped.value} malformed feature lines of {gff_path}")
+        self.names.append(name)
+        return rc
+
+    def add_genome_text(self, name, gff_text, fasta_text=None):
+        gff = gff_text.encode() if isinstance(gff_text, str) else gff_text
+        fasta = fasta_text.encode() if isinstance(fasta_text, str) else fasta_text
+        skipped = C.c_uint32()
+        rc = self.lib.pf_feeder_add_genome_text(self.h, name.encode(), gff, len(gff), fasta,
+                                                0 if fasta is None else len(fasta), C.byref(skipped))
+        if rc < 0:
+            self._error(rc, f"parsing genome {name}")
+        self.names.append(name)
+        return rc
+
+    def genome_info(self, genome):
+        nf, ncg, nb = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        rc = self.lib.pf_feeder_genome_info(self.h, genome, C.byref(nf), C.byref(ncg), C.byref(nb))
+        if rc != 0:
+            self._error(rc, "pf_feeder_genome_info")
+        return {"features": nf.value, "contigs": ncg.value, "bases": nb.value}
+
+    def feature(self, genome, feature):
+        """-> (id, contig, start, end, strand) of a parsed feature."""
+        ident, contig = C.c_char_p(), C.c_char_p()
+        start, end, strand = C.c_int64(), C.c_int64(), C.c_int32()
+        rc = self.lib.pf_feeder_feature(self.h, genome, feature, C.byref(ident), C.byref(contig),
+                                        C.byref(start), C.byref(end), C.byref(strand))
+        if rc != 0:
+            self._error(rc, "pf_feeder_feature")
+        return ident.value.decode(), contig.value.decode(), start.value, end.value, strand.value
+
+    def feature_names(self, genome, feature):
+        key = (genome, feature)
+        got = self._feature_names.get(key)
+        if got is None:
+            got = self._feature_names[key] = self.feature(genome, feature)[:2]
+        return got
+
+    def cut(self, genomes, cells_blob, up, down, down_start_codon):
+        """genomes: uint32 array (genome index per cell); cells_blob: the cells joined with
+        newlines (bytes).  -> dict of copies of the pf_cut_result arrays."""
+        genomes = np.ascontiguousarray(genomes, dtype=np.uint32)
+        res = capi.CutResult()
+        rc = self.lib.pf_feeder_cut(self.h, len(genomes), genomes.ctypes.data, cells_blob, len(cells_blob),
+                                    int(up), int(down), int(bool(down_start_codon)), C.byref(res))
+        if rc != 0:
+            self._error(rc, "pf_feeder_cut")
+        n = res.n_seqs
+
+        def arr(ptr, count, dtype):
+            if count == 0:
+                return np.zeros(0, dtype)
+            return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
+
+        seq_off = arr(res.seq_off, n + 1, np.uint64)
+        out = {"n_seqs": n, "seq_off": seq_off,
+               "ascii": C.string_at(res.ascii, int(seq_off[-1])) if n else b"",
+               "cell": arr(res.cell, n, np.uint32), "feature": arr(res.feature, n, np.uint32),
+               "start": arr(res.start, n, np.int32), "end": arr(res.end, n, np.int32),
+               "offset": arr(res.offset, n, np.int32), "strand": arr(res.strand, n, np.int32),
+               "missing": []}
+        if res.n_missing:
+            moff = arr(res.missing_off, res.n_missing + 1, np.uint64)
+            text = C.string_at(res.missing_text, int(moff[-1]))
+            mcell = arr(res.missing_cell, res.n_missing, np.uint32)
+            mkind = arr(res.missing_kind, res.n_missing, np.uint8)
+            out["missing"] = [(int(mcell[i]), int(mkind[i]), text[int(moff[i]):int(moff[i + 1])].decode())
+                              for i in range(res.n_missing)]
+        return out
+
+
+class NativePackedCluster:
+    """The attributes of `packer.PackedCluster`, filled from a native cut: sequences as one
+    ASCII blob + lengths (`seq_bytes` and `meta` are built only if somebody asks)."""
+    __slots__ = ("idx", "clusterpresab", "ascii_blob", "seq_len", "sample", "target", "start", "end",
+                 "offset", "strand", "k", "canonical", "consider_missing", "_feeder", "_genome",
+                 "_feature", "_strain", "_meta")
+
+    def __init__(self, idx, clusterpresab, cut, sample, target, genome, strains, feeder):
+        self.idx = idx
+        self.clusterpresab = clusterpresab
+        self.ascii_blob = cut["ascii"]
+        self.seq_len = np.diff(cut["seq_off"]).astype(np.int64)
+        self.sample = sample
+        self.target = target
+        self.start, self.end = cut["start"], cut["end"]
+        self.offset, self.strand = cut["offset"], cut["strand"]
+        self._feeder, self._genome, self._feature, self._strain = feeder, genome, cut["feature"], strains
+        self._meta = None
+
+    @property
+    def seq_bytes(self):
+        off = np.concatenate([[0], np.cumsum(self.seq_len)])
+        return [self.ascii_blob[int(off[i]):int(off[i + 1])] for i in range(len(self.seq_len))]
+
+    @property
+    def meta(self):
+        """[(strain, feature id, contig)] per sequence (for the kmers.tsv rows)."""
+        if self._meta is None:
+            self._meta = [(self._strain[i],) + self._feeder.feature_names(int(self._genome[i]), int(self._feature[i]))
+                          for i in range(len(self._feature))]
+        return self._meta
+
+    def n_records(self, k, canonical):
+        n = int(np.maximum(self.seq_len - k + 1, 0).sum())
+        return n if canonical else 2 * n
+
+
+def prep_feeder(filelist, fastalist, gffdir, fastadir, output=None):
+    """-> (NativeFeeder, {genome name: genome index}).  Same file discovery as
+    `input.prep_data_n_fasta` (reference input.py:68-138); the nucleotides stay in the library."""
+    gff_files, gff_is_list = _listing(gffdir)
+    if gff_is_list:
+        gff_path = {_genome_name(f): f for f in gff_files if f.endswith(".gff")}
+    else:
+        gff_path = {g: os.path.join(gffdir, f"{g}.gff") for g in filelist}
+    fasta_path = {}
+    if fastadir is not None:
+        files, is_list = _listing(fastadir)
+        for f in files:
+            if f.endswith(".fna") or f.endswith(".fasta"):
+                fasta_path[_genome_name(f)] = f if is_list else os.path.join(fastadir, f)
+    feeder = NativeFeeder()
+    index = {}
+    for genome in filelist:
+        logger.debug(f"Handling {genome}")
+        fasta = None
+        if genome in fastalist:
+            if genome not in fasta_path:
+                logger.error(f"Neither {genome}.fna not {genome}.fasta found in {fastadir}")
+                sys.exit(1)
+            fasta = fasta_path[genome]
+        index[genome] = feeder.add_genome(genome, gff_path[genome], fasta)
+    return feeder, index
+
+
+def iter_packed_clusters(panaroo, feeder, genome_index, up, down, down_start_codon, stroi, klength,
+                         canon, consider_missing_cluster, gene_list=None, raise_missing=False):
+    """Yields what `cluster_cutter(iter_gene_clusters(...))` yields — (idx, packed cluster,
+    int presence vector, None) per panaroo row — with the cutting done by the library."""
+    cols = [str(c) for c in panaroo.columns]
+    missing = set(cols).difference(genome_index.keys())
+    if missing:
+        raise KeyError(f"{len(missing)} strains of the pangenome table have no GFF "
+                       f"(e.g. {sorted(missing)[0]}); the reference would emit misaligned "
+                       "presence vectors here, this build refuses")
+    order = sorted(cols)
+    rank = {s: i for i, s in enumerate(order)}
+    perm = np.argsort(np.array([rank[c] for c in cols]), kind="stable")        # table columns in rank order
+    genome_of_rank = np.array([genome_index[s] for s in order], np.uint32)
+    target_of_rank = np.array([s in stroi for s in order], bool)
+    values = panaroo.to_numpy(dtype=object)[:, perm]
+    present_all = pd.notna(values)
+    n_rows, S = values.shape
+    for i, idx in enumerate(panaroo.index):
+        if gene_list is not None and idx not in gene_list:
+            logger.debug(f"Skipping {idx} ({i + 1}/{n_rows})")
+            continue
+        logger.debug(f"Extracting sequences from {idx} ({i + 1}/{n_rows})")
+        ranks = np.flatnonzero(present_all[i])
+        clusterpresab = np.zeros(S, dtype=int)
+        clusterpresab[ranks] = 1
+        cells = values[i, ranks]
+        blob = "\n".join(cells).encode() if len(ranks) else b""
+        cut = feeder.cut(genome_of_rank[ranks], blob, up, down, down_start_codon)
+        for cell, kind, name in cut["missing"]:
+            strain = order[ranks[cell]]
+            msg = (f"Could not find gene {name} from {idx} in {strain}" if kind == 0
+                   else f"Could not find chromosome {name} in {strain}")
+            logger.warning(msg)
+            if raise_missing:
+                raise KeyError(msg)
+        sample = ranks[cut["cell"]].astype(np.uint32)
+        pc = NativePackedCluster(idx, clusterpresab, cut, sample, target_of_rank[sample],
+                                 genome_of_rank[sample], [order[r] for r in sample], feeder)
+        pc.k, pc.canonical, pc.consider_missing = klength, bool(canon), bool(consider_missing_cluster)
+        yield idx, pc, clusterpresab, None

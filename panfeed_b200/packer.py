@@ -103,24 +103,55 @@ def pack_planes_numpy(seq_bytes):
     return packed, offs[:-1].astype(np.uint64), amb_seq, amb_plane, amb_off
 
 
+class SeqMeta:
+    """(strain, feature id, contig) of every sequence of a batch, cluster after cluster; the
+    per-cluster lists are only built when an entry is read (clusters cut by the native feeder
+    make theirs on demand, and only the positional rows of a second pass need them)."""
+
+    def __init__(self, clusters, counts):
+        self.clusters = clusters
+        self.first = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+
+    def __len__(self):
+        return int(self.first[-1])
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += len(self)
+        c = int(np.searchsorted(self.first, i, side="right")) - 1
+        return self.clusters[c].meta[i - int(self.first[c])]
+
+    def __iter__(self):
+        for pc in self.clusters:
+            yield from pc.meta
+
+
 def pack_batch(packed_clusters, cluster_ids=None):
-    """-> (capi.HostBatch, seq_meta list, cluster idx list)."""
-    seq_bytes = []
+    """-> (capi.HostBatch, seq_meta (SeqMeta), cluster idx list).  Clusters are
+    `PackedCluster`s (Python cutting) or `feeder.NativePackedCluster`s (one ASCII blob each)."""
+    blobs, lens = [], []
     for pc in packed_clusters:
-        seq_bytes.extend(pc.seq_bytes)
-    n_seqs = len(seq_bytes)
-    lens = np.fromiter((len(b) for b in seq_bytes), np.int64, n_seqs)
-    packed, base_off, amb_seq, amb_plane, amb_off = capi.pack_sequences(seq_bytes)
+        if hasattr(pc, "ascii_blob"):
+            blobs.append(pc.ascii_blob)
+            lens.append(pc.seq_len)
+        else:
+            blobs.extend(pc.seq_bytes)
+            lens.append(np.fromiter((len(b) for b in pc.seq_bytes), np.int64, len(pc.seq_bytes)))
+    lens = np.concatenate(lens).astype(np.int64) if lens else np.zeros(0, np.int64)
+    n_seqs = len(lens)
+    seq_off = np.zeros(n_seqs + 1, np.uint64)
+    np.cumsum(lens, out=seq_off[1:])
+    packed, base_off, amb_seq, amb_plane, amb_off = capi.pack_blob(b"".join(blobs), seq_off)
 
     seqs = np.zeros(n_seqs, capi.SEQ_DTYPE)
     clusters = np.zeros(len(packed_clusters), capi.CLUSTER_DTYPE)
     S = len(packed_clusters[0].clusterpresab) if packed_clusters else 0
     W = (S + 31) // 32
     presence = np.zeros((len(packed_clusters), W), np.uint32)
-    meta, ids = [], []
+    ids, counts = [], []
     i = 0
     for ci, pc in enumerate(packed_clusters):
-        n = len(pc.seq_bytes)
+        n = len(pc.sample)
         sl = slice(i, i + n)
         seqs["cluster"][sl] = ci
         seqs["sample"][sl] = pc.sample
@@ -131,14 +162,14 @@ def pack_batch(packed_clusters, cluster_ids=None):
         seqs["strand"][sl] = pc.strand
         clusters["id"][ci] = ci if cluster_ids is None else cluster_ids[ci]
         presence[ci] = presence_words(pc.clusterpresab)
-        meta.extend(pc.meta)
+        counts.append(n)
         ids.append(pc.idx)
         i += n
     seqs["base_off"] = base_off
     seqs["len"] = lens.astype(np.uint32)
     seqs["flags"] |= amb_seq.astype(np.uint32) * capi.PF_SEQ_AMBIGUOUS
     seqs["amb_off"] = amb_off
-    return capi.HostBatch(packed, seqs, clusters, presence, amb_plane), meta, ids
+    return capi.HostBatch(packed, seqs, clusters, presence, amb_plane), SeqMeta(list(packed_clusters), counts), ids
 
 
 _ACGT = np.frombuffer(b"ACGT", np.uint8)

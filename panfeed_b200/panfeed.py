@@ -154,8 +154,8 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
     #      threads (pf_format_positions), 1e8 rows are too many for Python ----------------
     pos_text = ""
     if len(r["pos_seq"]):
-        leads = [f"{idxs[hb.seqs['cluster'][i]]}\t{meta[i][0]}\t{meta[i][1]}\t{meta[i][2]}\t"
-                 f"{hb.seqs['strand'][i]}\t".encode() for i in range(len(hb.seqs))]
+        leads = [f"{idxs[c]}\t{m[0]}\t{m[1]}\t{m[2]}\t{st}\t".encode()
+                 for c, st, m in zip(hb.seqs["cluster"].tolist(), hb.seqs["strand"].tolist(), meta)]
         pos_text = capi.format_positions(r, k, canonical, leads, hb.seqs["strand"]).decode()
     return pos_text, "".join(pat_text), hash_texts
 

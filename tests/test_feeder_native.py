@@ -1,0 +1,148 @@
+"""The native feeder (pf_feeder_*: GFF3 / FASTA parsing and cluster cutting in the library) against
+the Python feeder of panfeed_b200/input.py, which mirrors the reference's input.py:274-468 and is
+what the golden files were checked with.  Both must hand the packer identical batches.
+Pure host code: runs without a GPU."""
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from panfeed_b200 import feeder as nf
+from panfeed_b200 import input as pyin
+from panfeed_b200 import packer, panfeed
+
+import helpers
+
+FIX = os.path.join(helpers.GOLDEN, "fixture")
+
+
+def _table():
+    return pd.read_csv(os.path.join(FIX, "gene_presence_absence.csv"), sep=",", index_col=0,
+                       low_memory=False).drop(columns=["Non-unique Gene name", "Annotation"])
+
+
+def _both(up, down, dsc, stroi, fastadir, gene_list=None, canon=True):
+    gffdir = os.path.join(FIX, "gffs")
+    filelist, fastalist = pyin.what_are_my_inputfiles(gffdir, fastadir)
+    table = _table()
+    data = pyin.prep_data_n_fasta(filelist, fastalist, gffdir, fastadir, None)
+    py = [panfeed.cluster_cutter(x, 31, stroi, False, canon, False, None)
+          for x in pyin.iter_gene_clusters(table, data, up, down, dsc, True, gene_list)]
+    native, index = nf.prep_feeder(filelist, fastalist, gffdir, fastadir)
+    nat = list(nf.iter_packed_clusters(table, native, index, up, down, dsc, stroi, 31, canon, False,
+                                       gene_list))
+    return py, nat, native
+
+
+@pytest.mark.parametrize("up,down,dsc", [(0, 0, False), (100, 50, False), (40, 40, True), (5000, 7000, False),
+                                          (3, 0, True)])
+@pytest.mark.parametrize("fasta", [False, True])
+def test_native_feeder_batches_equal_python_feeder(up, down, dsc, fasta):
+    stroi = {"s00", "s05"}
+    fastadir = os.path.join(FIX, "fastas") if fasta else None
+    py, nat, native = _both(up, down, dsc, stroi, fastadir)
+    assert [p[0] for p in py] == [n[0] for n in nat]
+    for (idx, a, presab_a, _), (_, b, presab_b, _) in zip(py, nat):
+        assert (presab_a == presab_b).all(), idx
+        assert a.seq_bytes == b.seq_bytes, idx
+        for f in ("sample", "target", "start", "end", "offset", "strand"):
+            assert (np.asarray(getattr(a, f)) == np.asarray(getattr(b, f))).all(), (idx, f)
+        assert a.meta == b.meta, idx
+        assert a.n_records(31, True) == b.n_records(31, True)
+        assert (b.k, b.canonical, b.consider_missing) == (31, True, False)
+    hb_a, meta_a, ids_a = packer.pack_batch([p[1] for p in py])
+    hb_b, meta_b, ids_b = packer.pack_batch([n[1] for n in nat])
+    assert ids_a == ids_b
+    assert list(meta_a) == list(meta_b) and len(meta_a) == len(hb_a.seqs)
+    assert meta_b[0] == meta_a[0] and meta_b[len(meta_b) - 1] == meta_a[-1]
+    assert (hb_a.packed == hb_b.packed).all()
+    assert hb_a.seqs.tobytes() == hb_b.seqs.tobytes()
+    assert (hb_a.presence == hb_b.presence).all()
+    assert hb_a.clusters.tobytes() == hb_b.clusters.tobytes()
+    assert (hb_a.amb is None) == (hb_b.amb is None)
+    if hb_a.amb is not None:
+        assert (hb_a.amb == hb_b.amb).all()
+    native.close()
+
+
+def test_native_feeder_gene_list_and_missing_genes(caplog):
+    """--genes keeps the listed clusters; a feature id that is not in the GFF is skipped with the
+    reference's warning (the fixture's group_acc1 names s07_refound_1, which no GFF has)."""
+    genes = {line.rstrip("\n") for line in open(os.path.join(FIX, "genes.txt"))}
+    py, nat, native = _both(10, 10, False, "", None, genes)
+    assert [p[0] for p in py] == [n[0] for n in nat] and len(nat) == len(genes & set(_table().index))
+    import logging
+    caplog.clear()
+    with caplog.at_level(logging.WARNING, logger="panfeed.input"):
+        py, nat, native = _both(0, 0, False, "", None, {"group_acc1"})
+    msgs = [r.getMessage() for r in caplog.records]
+    assert msgs.count("Could not find gene s07_refound_1 from group_acc1 in s07") == 2     # both feeders
+    assert py[0][1].seq_bytes == nat[0][1].seq_bytes
+    filelist, fastalist = pyin.what_are_my_inputfiles(os.path.join(FIX, "gffs"), None)
+    with pytest.raises(KeyError):
+        list(nf.iter_packed_clusters(_table(), native, {g: i for i, g in enumerate(filelist)}, 0, 0, False, "",
+                                     31, True, False, {"group_acc1"}, raise_missing=True))
+
+
+GFF = """##gff-version 3
+##sequence-region ctg1 1 60
+ctg1\tprodigal\tCDS\t5\t16\t.\t+\t0\tID=g1;Name=x
+ctg1\tprodigal\tgene\t5\t16\t.\t+\t0\tID=skipped_type
+  # an indented comment
+ctg1\tprodigal\tCDS\tabc\t16\t.\t+\t0\tID=bad_int
+ctg1\tprodigal\tCDS\t20\t31\t.\t-\t0\tName=y;ID=g2=tail;IDX=overrides;z=1
+ctg1\tprodigal\tCDS\t 40 \t50_0\t.\t?\t0\tlocus=1;ID=g3;
+ctg2\tprodigal\tCDS\t1\t9\t.\t+\t0\tID=g4;z
+short\tline\tCDS
+ctgX\tprodigal\tCDS\t1\t9\t.\t+\t0\tID=no_contig;z=2
+ctg1\tprodigal\tCDS\t1\t6\t.\t+\t0\tID=g1;again=1
+ctg1\tprodigal\tCDS\t2\t7\t.\t+\t0\tID=trail
+##FASTA
+>ctg1 some description
+acgtacgtacGTACGTNNRYacgtacgtac
+  ACGTACGTACGTACGTACGTACGTACGTAC\r
+>ctg2
+ACGTAC
+>ctg2 again
+TTTTTTTTTTTT
+"""
+
+
+def test_native_feeder_parsing_quirks_match_python(tmp_path):
+    """Hand-written GFF with the reference parser's quirks: non-CDS rows, malformed rows, the last
+    ID-like attribute winning ("IDX=overrides"), ids cut at a second '=', int() tolerance
+    (" 40 ", "50_0"), any strand but '+' read as minus, repeated ids / contig names replacing the
+    earlier ones, lower case and padded sequence lines, windows running off both contig ends."""
+    path = tmp_path / "q.gff"
+    path.write_text(GFF)
+    feats = pyin.parse_gff(str(path))
+    contigs = pyin.read_fasta_text(open(path).read().split("##FASTA")[1].split("\n"))
+    native = nf.NativeFeeder()
+    g = native.add_genome("q", str(path))
+    info = native.genome_info(g)
+    assert info["features"] == len(feats) and info["contigs"] == len(contigs)
+    assert info["bases"] == sum(len(v) for v in contigs.values())
+    got = {}
+    for i in range(info["features"]):
+        ident, contig, start, end, strand = native.feature(g, i)
+        got[ident] = (contig, start, end, strand)
+    assert got == {k: (v.chromosome, v.start, v.end, v.strand) for k, v in feats.items()}
+    # an ID that ends the line keeps its newline (the reference splits the unstripped line)
+    assert set(got) == {"g1", "overrides", "g3", "g4", "no_contig", "trail\n"}
+    assert got["g1"][1:3] == (1, 6)
+    table = pd.DataFrame({"q": ["g1;overrides;g3;nope;g4;no_contig;"]}, index=["cl"])
+    for up, down, dsc in [(0, 0, False), (3, 4, False), (100, 100, False), (2, 2, True), (30, 0, True)]:
+        py = list(pyin.iter_gene_clusters(table, {"q": (contigs, feats)}, up, down, dsc, True))
+        a = packer.PackedCluster(py[0][0], "cl", py[0][2], {"q"})
+        (_, b, presab, _), = nf.iter_packed_clusters(table, native, {"q": g}, up, down, dsc, {"q"}, 5, True, False)
+        assert a.seq_bytes == b.seq_bytes, (up, down, dsc)
+        assert a.meta == b.meta
+        for f in ("sample", "target", "start", "end", "offset", "strand"):
+            assert (np.asarray(getattr(a, f)) == np.asarray(getattr(b, f))).all(), (up, down, dsc, f)
+    # the same genome from memory, with the FASTA given separately
+    g2 = native.add_genome_text("q2", GFF, ">ctg1\nACGT\n")
+    assert native.genome_info(g2) == {"features": len(feats), "contigs": 1, "bases": 4}
+    with pytest.raises(Exception):
+        native.add_genome_text("q3", GFF.split("##FASTA")[0])       # no sequences at all
+    native.close()

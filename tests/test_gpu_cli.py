@@ -17,10 +17,12 @@ def _read(path):
     return open(path).read()
 
 
+@pytest.mark.parametrize("feeder", ["python", "native"])
 @pytest.mark.parametrize("mode", sorted(helpers.modes()))
-def test_cli_outputs_match_reference(mode, tmp_path):
+def test_cli_outputs_match_reference(mode, feeder, tmp_path):
+    """feeder = native: GFF/FASTA parsing and cluster cutting by the library (--native-feeder)."""
     from panfeed_b200.__main__ import main
-    args = [a for a in helpers.modes()[mode]]
+    args = [a for a in helpers.modes()[mode]] + (["--native-feeder"] if feeder == "native" else [])
     out = str(tmp_path / "out")
     cwd = os.getcwd()
     os.chdir(helpers.GOLDEN)
