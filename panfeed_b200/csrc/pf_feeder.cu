@@ -14,7 +14,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -213,7 +215,8 @@ struct pf_feeder {
   std::vector<Genome> genomes;
   std::string err;
   // result of the last pf_feeder_cut
-  std::string ascii;
+  std::unique_ptr<char[]> ascii;
+  size_t ascii_cap = 0;
   std::vector<uint64_t> seq_off;
   std::vector<uint32_t> cell, feature;
   std::vector<int32_t> start, end, offset, strand;
@@ -299,14 +302,16 @@ extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* gen
                              uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
                              pf_cut_result* out) {
   if (!f || !out || (n_cells && (!genome || !cells_blob))) return PF_ERR_INVALID;
-  f->ascii.clear();
   f->seq_off.assign(1, 0);
   f->cell.clear(); f->feature.clear();
   f->start.clear(); f->end.clear(); f->offset.clear(); f->strand.clear();
   f->miss_cell.clear(); f->miss_kind.clear(); f->miss_text.clear(); f->miss_off.assign(1, 0);
+  struct Piece { const std::string* contig; int64_t lo, hi; bool minus; };
+  std::vector<Piece> pieces;
   const char* p = cells_blob;
   const char* e = cells_blob + cells_len;
   std::string gene;
+  // pass 1 (serial): look the genes up, place the windows
   for (uint32_t ci = 0; ci < n_cells; ++ci) {
     if (genome[ci] >= f->genomes.size()) { f->err = "pf_feeder_cut: genome index out of range"; return PF_ERR_INVALID; }
     const Genome& g = f->genomes[genome[ci]];
@@ -349,18 +354,11 @@ extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* gen
       }
       // contig[a:b] with Python's slice semantics
       const int64_t n = (int64_t)contig.size();
-      int64_t lo = a < 0 ? std::max<int64_t>(a + n, 0) : std::min(a, n);
+      const int64_t lo = a < 0 ? std::max<int64_t>(a + n, 0) : std::min(a, n);
       int64_t hi = b < 0 ? std::max<int64_t>(b + n, 0) : std::min(b, n);
       if (hi < lo) hi = lo;
-      const size_t at = f->ascii.size();
-      f->ascii.resize(at + (size_t)(hi - lo));
-      char* dst = &f->ascii[0] + at;
-      if (ft.strand < 0) {
-        for (int64_t i = 0; i < hi - lo; ++i) dst[i] = (char)kComp.t[(unsigned char)contig[(size_t)(hi - 1 - i)]];
-      } else if (hi > lo) {
-        memcpy(dst, contig.data() + lo, (size_t)(hi - lo));
-      }
-      f->seq_off.push_back(f->ascii.size());
+      pieces.push_back(Piece{&contig, lo, hi, ft.strand < 0});
+      f->seq_off.push_back(f->seq_off.back() + (uint64_t)(hi - lo));
       f->cell.push_back(ci);
       f->feature.push_back(fi->second);
       f->start.push_back((int32_t)seq_start);
@@ -370,9 +368,49 @@ extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* gen
     }
     p = ce < e ? ce + 1 : e;
   }
+  // pass 2 (host threads): copy / reverse-complement the windows into place
+  const size_t total = (size_t)f->seq_off.back();
+  if (total > f->ascii_cap) {
+    f->ascii.reset(new char[total + total / 4 + 64]);
+    f->ascii_cap = total + total / 4 + 64;
+  }
+  {
+    char* base = f->ascii.get();
+    const size_t n_seq = pieces.size();
+    auto fill = [&](size_t s0, size_t s1) {
+      for (size_t s = s0; s < s1; ++s) {
+        const Piece& pc = pieces[s];
+        char* dst = base + f->seq_off[s];
+        const int64_t len = pc.hi - pc.lo;
+        if (pc.minus) {
+          const char* src = pc.contig->data();
+          for (int64_t i = 0; i < len; ++i) dst[i] = (char)kComp.t[(unsigned char)src[pc.hi - 1 - i]];
+        } else if (len > 0) {
+          memcpy(dst, pc.contig->data() + pc.lo, (size_t)len);
+        }
+      }
+    };
+    uint32_t nt = std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    nt = (uint32_t)std::min<size_t>(nt, std::max<size_t>(1, total >> 20));       // >= 1 MiB per thread
+    if (nt <= 1 || n_seq < 2 * nt) fill(0, n_seq);
+    else {
+      // split by bytes, not by sequences
+      std::vector<std::thread> th;
+      size_t s0 = 0;
+      for (uint32_t t = 0; t < nt; ++t) {
+        const uint64_t want = (uint64_t)total * (t + 1) / nt;
+        size_t s1 = t + 1 == nt ? n_seq
+                                : (size_t)(std::upper_bound(f->seq_off.begin(), f->seq_off.end(), want) - f->seq_off.begin() - 1);
+        s1 = std::max(s1, s0);
+        th.emplace_back(fill, s0, s1);
+        s0 = s1;
+      }
+      for (auto& x : th) x.join();
+    }
+  }
   memset(out, 0, sizeof *out);
   out->n_seqs = (uint32_t)f->cell.size();
-  out->ascii = f->ascii.data();
+  out->ascii = f->ascii.get();
   out->seq_off = f->seq_off.data();
   out->cell = f->cell.data();
   out->feature = f->feature.data();

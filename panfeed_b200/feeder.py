@@ -136,18 +136,18 @@ class NativePackedCluster:
     ASCII blob + lengths (`seq_bytes` and `meta` are built only if somebody asks)."""
     __slots__ = ("idx", "clusterpresab", "ascii_blob", "seq_len", "sample", "target", "start", "end",
                  "offset", "strand", "k", "canonical", "consider_missing", "_feeder", "_genome",
-                 "_feature", "_strain", "_meta")
+                 "_feature", "_order", "_meta")
 
-    def __init__(self, idx, clusterpresab, cut, sample, target, genome, strains, feeder):
+    def __init__(self, idx, clusterpresab, ascii_blob, seq_len, sample, target, start, end, offset, strand,
+                 genome, feature, order, feeder):
         self.idx = idx
         self.clusterpresab = clusterpresab
-        self.ascii_blob = cut["ascii"]
-        self.seq_len = np.diff(cut["seq_off"]).astype(np.int64)
+        self.ascii_blob = ascii_blob
+        self.seq_len = seq_len
         self.sample = sample
         self.target = target
-        self.start, self.end = cut["start"], cut["end"]
-        self.offset, self.strand = cut["offset"], cut["strand"]
-        self._feeder, self._genome, self._feature, self._strain = feeder, genome, cut["feature"], strains
+        self.start, self.end, self.offset, self.strand = start, end, offset, strand
+        self._feeder, self._genome, self._feature, self._order = feeder, genome, feature, order
         self._meta = None
 
     @property
@@ -159,7 +159,8 @@ class NativePackedCluster:
     def meta(self):
         """[(strain, feature id, contig)] per sequence (for the kmers.tsv rows)."""
         if self._meta is None:
-            self._meta = [(self._strain[i],) + self._feeder.feature_names(int(self._genome[i]), int(self._feature[i]))
+            self._meta = [(self._order[int(self.sample[i])],) +
+                          self._feeder.feature_names(int(self._genome[i]), int(self._feature[i]))
                           for i in range(len(self._feature))]
         return self._meta
 
@@ -197,9 +198,12 @@ def prep_feeder(filelist, fastalist, gffdir, fastadir, output=None):
 
 
 def iter_packed_clusters(panaroo, feeder, genome_index, up, down, down_start_codon, stroi, klength,
-                         canon, consider_missing_cluster, gene_list=None, raise_missing=False):
+                         canon, consider_missing_cluster, gene_list=None, raise_missing=False,
+                         cells_per_call=16384):
     """Yields what `cluster_cutter(iter_gene_clusters(...))` yields — (idx, packed cluster,
-    int presence vector, None) per panaroo row — with the cutting done by the library."""
+    int presence vector, None) per panaroo row — with the cutting done by the library, several
+    clusters (about `cells_per_call` table cells) per call: the Python work per cluster is a
+    handful of array slices."""
     cols = [str(c) for c in panaroo.columns]
     missing = set(cols).difference(genome_index.keys())
     if missing:
@@ -214,26 +218,51 @@ def iter_packed_clusters(panaroo, feeder, genome_index, up, down, down_start_cod
     values = panaroo.to_numpy(dtype=object)[:, perm]
     present_all = pd.notna(values)
     n_rows, S = values.shape
-    for i, idx in enumerate(panaroo.index):
+    index = list(panaroo.index)
+    rows = []
+    for i, idx in enumerate(index):
         if gene_list is not None and idx not in gene_list:
             logger.debug(f"Skipping {idx} ({i + 1}/{n_rows})")
             continue
-        logger.debug(f"Extracting sequences from {idx} ({i + 1}/{n_rows})")
-        ranks = np.flatnonzero(present_all[i])
-        clusterpresab = np.zeros(S, dtype=int)
-        clusterpresab[ranks] = 1
-        cells = values[i, ranks]
-        blob = "\n".join(cells).encode() if len(ranks) else b""
-        cut = feeder.cut(genome_of_rank[ranks], blob, up, down, down_start_codon)
+        rows.append(i)
+    rows = np.array(rows, np.int64)
+    n_cells = present_all[rows].sum(axis=1) if len(rows) else np.zeros(0, np.int64)
+    at = 0
+    while at < len(rows):
+        # rows at .. to: at least one cluster, then as many as fit the cell budget
+        to, budget = at + 1, cells_per_call - int(n_cells[at])
+        while to < len(rows) and budget - int(n_cells[to]) >= 0:
+            budget -= int(n_cells[to])
+            to += 1
+        sel = rows[at:to]
+        pres = present_all[sel]
+        rr, cc = np.nonzero(pres)                    # row-major: cluster by cluster, ranks ascending
+        cells = values[sel][pres]
+        blob = "\n".join(cells).encode() if len(cells) else b""
+        cut = feeder.cut(genome_of_rank[cc], blob, up, down, down_start_codon)
         for cell, kind, name in cut["missing"]:
-            strain = order[ranks[cell]]
+            idx, strain = index[sel[rr[cell]]], order[cc[cell]]
             msg = (f"Could not find gene {name} from {idx} in {strain}" if kind == 0
                    else f"Could not find chromosome {name} in {strain}")
             logger.warning(msg)
             if raise_missing:
                 raise KeyError(msg)
-        sample = ranks[cut["cell"]].astype(np.uint32)
-        pc = NativePackedCluster(idx, clusterpresab, cut, sample, target_of_rank[sample],
-                                 genome_of_rank[sample], [order[r] for r in sample], feeder)
-        pc.k, pc.canonical, pc.consider_missing = klength, bool(canon), bool(consider_missing_cluster)
-        yield idx, pc, clusterpresab, None
+        seq_cluster = rr[cut["cell"]]
+        sample = cc[cut["cell"]].astype(np.uint32)
+        target = target_of_rank[sample]
+        genome = genome_of_rank[sample]
+        seq_len = np.diff(cut["seq_off"]).astype(np.int64)
+        first = np.searchsorted(seq_cluster, np.arange(len(sel) + 1))
+        byte_at = cut["seq_off"]
+        for j, i in enumerate(sel):
+            idx = index[i]
+            logger.debug(f"Extracting sequences from {idx} ({i + 1}/{n_rows})")
+            a, b = int(first[j]), int(first[j + 1])
+            clusterpresab = pres[j].astype(int)
+            pc = NativePackedCluster(idx, clusterpresab, cut["ascii"][int(byte_at[a]):int(byte_at[b])],
+                                     seq_len[a:b], sample[a:b], target[a:b], cut["start"][a:b], cut["end"][a:b],
+                                     cut["offset"][a:b], cut["strand"][a:b], genome[a:b], cut["feature"][a:b],
+                                     order, feeder)
+            pc.k, pc.canonical, pc.consider_missing = klength, bool(canon), bool(consider_missing_cluster)
+            yield idx, pc, clusterpresab, None
+        at = to
