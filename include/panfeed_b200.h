@@ -383,6 +383,18 @@ int  pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const
                    uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
                    pf_cut_result* out);
 
+/* ---- row filter over the TSV outputs (host threads): the scans of the post-GWAS joins ----
+ * panfeed-get-clusters / panfeed-get-kmers (get_clusters.py:90-101, get_kmers.py:108-145) keep the
+ * rows of kmers_to_hashes.tsv whose hashed_pattern, and of kmers.tsv whose cluster, is in a set
+ * (pandas, 100,000 rows at a time).  pf_tsv_filter maps the file, scans pieces of it on host
+ * threads and returns the matching lines in file order ('\n'-terminated, header excluded when
+ * skip_header) in a buffer the caller releases with pf_free.  column: 0-based, tab-separated,
+ * no quoting.  keys: n_keys strings back to back (keys_blob, key_off[n_keys + 1]). */
+int  pf_tsv_filter(const char* path, uint32_t column, const char* keys_blob, const uint64_t* key_off,
+                   uint64_t n_keys, int skip_header, char** out, uint64_t* out_len, uint64_t* n_rows,
+                   uint32_t n_threads);
+void pf_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

@@ -130,6 +130,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns", "pf_format_kmer_rows", "pf_gzip_members",
            "pf_feeder_create", "pf_feeder_destroy", "pf_feeder_last_error", "pf_feeder_add_genome",
            "pf_feeder_add_genome_text", "pf_feeder_genome_info", "pf_feeder_feature", "pf_feeder_cut",
+           "pf_tsv_filter", "pf_free",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_export",
            "pf_exchange_unpack"]
@@ -180,6 +181,10 @@ def load():
                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     lib.pf_feeder_cut.argtypes = [vp, u32, vp, C.c_char_p, u64, C.c_int32, C.c_int32, C.c_int32,
                                   C.POINTER(CutResult)]
+    lib.pf_tsv_filter.argtypes = [C.c_char_p, u32, C.c_char_p, vp, u64, C.c_int, C.POINTER(vp), C.POINTER(u64),
+                                  C.POINTER(u64), u32]
+    lib.pf_free.argtypes = [vp]
+    lib.pf_free.restype = None
     lib.pf_pack_plan.argtypes = [vp, u32, vp, C.POINTER(u64)]
     lib.pf_pack_2bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, u32]
     lib.pf_pack_4bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, C.POINTER(u64), C.POINTER(C.c_int)]
@@ -279,6 +284,29 @@ def format_patterns(words, n_samples, ids, present=None, n_threads=0):
     if rc != 0:
         raise PfError(rc, "pf_format_patterns failed")
     return out.tobytes()
+
+
+def tsv_filter(path, column, keys, skip_header=True, n_threads=0):
+    """Lines of the TSV file `path` (header excluded) whose tab-separated field `column` is one of
+    `keys` (iterable of str / bytes), in file order: (bytes, number of rows).  pf_tsv_filter,
+    library host threads."""
+    lib = load()
+    kb = [k if isinstance(k, bytes) else str(k).encode() for k in keys]
+    blob = b"".join(kb)
+    off = np.zeros(len(kb) + 1, np.uint64)
+    if kb:
+        np.cumsum(np.fromiter((len(k) for k in kb), np.uint64, len(kb)), out=off[1:])
+    out, n, rows = C.c_void_p(), C.c_uint64(), C.c_uint64()
+    rc = lib.pf_tsv_filter(os.fsencode(path), int(column), blob, off.ctypes.data, len(kb), int(bool(skip_header)),
+                           C.byref(out), C.byref(n), C.byref(rows), int(n_threads))
+    if rc != 0:
+        raise PfError(rc, f"pf_tsv_filter failed on {path}")
+    try:
+        data = C.string_at(out, n.value) if n.value else b""
+    finally:
+        if out:
+            lib.pf_free(out)
+    return data, int(rows.value)
 
 
 def gzip_members(data, level=9, member_bytes=0, n_threads=0):
