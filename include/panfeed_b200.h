@@ -372,6 +372,10 @@ int  pf_feeder_add_genome(pf_feeder* f, const char* name, const char* gff_path, 
 int  pf_feeder_add_genome_text(pf_feeder* f, const char* name, const char* gff, uint64_t gff_len,
                                const char* fasta /* NULL: ##FASTA section of gff */, uint64_t fasta_len,
                                uint32_t* skipped_lines);
+/* n genomes, read and parsed on host threads, appended in the order given; returns the index of
+ * the first (the others follow).  fasta_paths NULL, or NULL entries: the GFF's ##FASTA section. */
+int  pf_feeder_add_genomes(pf_feeder* f, uint32_t n, const char* const* names, const char* const* gff_paths,
+                           const char* const* fasta_paths, uint32_t* skipped_lines, uint32_t n_threads);
 int  pf_feeder_genome_info(const pf_feeder* f, uint32_t genome, uint32_t* n_features, uint32_t* n_contigs,
                            uint64_t* n_bases);
 int  pf_feeder_feature(const pf_feeder* f, uint32_t genome, uint32_t feature, const char** id,

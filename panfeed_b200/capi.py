@@ -128,7 +128,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
            "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream", "pf_format_positions",
            "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns", "pf_format_kmer_rows", "pf_gzip_members",
-           "pf_feeder_create", "pf_feeder_destroy", "pf_feeder_last_error", "pf_feeder_add_genome",
+           "pf_feeder_create", "pf_feeder_destroy", "pf_feeder_last_error", "pf_feeder_add_genome", "pf_feeder_add_genomes",
            "pf_feeder_add_genome_text", "pf_feeder_genome_info", "pf_feeder_feature", "pf_feeder_cut",
            "pf_tsv_filter", "pf_free",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
@@ -175,6 +175,7 @@ def load():
     lib.pf_feeder_last_error.argtypes = [vp]
     lib.pf_feeder_last_error.restype = C.c_char_p
     lib.pf_feeder_add_genome.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(u32)]
+    lib.pf_feeder_add_genomes.argtypes = [vp, u32, vp, vp, vp, vp, u32]
     lib.pf_feeder_add_genome_text.argtypes = [vp, C.c_char_p, C.c_char_p, u64, C.c_char_p, u64, C.POINTER(u32)]
     lib.pf_feeder_genome_info.argtypes = [vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
     lib.pf_feeder_feature.argtypes = [vp, u32, u32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),

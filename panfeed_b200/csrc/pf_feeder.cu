@@ -272,6 +272,35 @@ extern "C" int pf_feeder_add_genome(pf_feeder* f, const char* name, const char* 
                                    skipped_lines);
 }
 
+// Many genomes at once: the files are read and parsed on host threads (a genome is a few MB of
+// text; 500 of them are seconds of single-threaded parsing), then appended in the order given.
+// Returns the index of the first one; the others follow consecutively.
+extern "C" int pf_feeder_add_genomes(pf_feeder* f, uint32_t n, const char* const* names, const char* const* gff_paths,
+                                     const char* const* fasta_paths /* NULL, or NULL entries: ##FASTA section */,
+                                     uint32_t* skipped_lines /* [n] or NULL */, uint32_t n_threads) {
+  if (!f || (n && (!names || !gff_paths))) return PF_ERR_INVALID;
+  const int first = (int)f->genomes.size();
+  if (n == 0) return first;
+  std::vector<pf_feeder> local(n);                       // one scratch feeder per genome: no shared state
+  std::vector<int> rc(n, PF_OK);
+  uint32_t nt = n_threads ? n_threads : std::max(1u, std::thread::hardware_concurrency());
+  nt = std::min(nt, n);
+  std::vector<std::thread> th;
+  for (uint32_t t = 0; t < nt; ++t)
+    th.emplace_back([&, t]() {
+      for (uint32_t i = t; i < n; i += nt) {
+        uint32_t sk = 0;
+        rc[i] = pf_feeder_add_genome(&local[i], names[i], gff_paths[i], fasta_paths ? fasta_paths[i] : nullptr, &sk);
+        if (skipped_lines) skipped_lines[i] = sk;
+      }
+    });
+  for (auto& x : th) x.join();
+  for (uint32_t i = 0; i < n; ++i)
+    if (rc[i] < 0) { f->err = local[i].err; return rc[i]; }
+  for (uint32_t i = 0; i < n; ++i) f->genomes.push_back(std::move(local[i].genomes[0]));
+  return first;
+}
+
 extern "C" int pf_feeder_genome_info(const pf_feeder* f, uint32_t genome, uint32_t* n_features, uint32_t* n_contigs,
                                      uint64_t* n_bases) {
   if (!f || genome >= f->genomes.size()) return PF_ERR_INVALID;

@@ -63,6 +63,24 @@ class NativeFeeder:
         self.names.append(name)
         return rc
 
+    def add_genomes(self, names, gff_paths, fasta_paths=None, n_threads=0):
+        """Several genomes, read and parsed by the library's host threads -> index of the first."""
+        n = len(names)
+        arr = C.c_char_p * n
+        c_names = arr(*[x.encode() for x in names])
+        c_gff = arr(*[os.fsencode(x) for x in gff_paths])
+        c_fa = None
+        if fasta_paths is not None and any(x is not None for x in fasta_paths):
+            c_fa = arr(*[None if x is None else os.fsencode(x) for x in fasta_paths])
+        skipped = np.zeros(max(n, 1), np.uint32)
+        rc = self.lib.pf_feeder_add_genomes(self.h, n, c_names, c_gff, c_fa, skipped.ctypes.data, int(n_threads))
+        if rc < 0:
+            self._error(rc, "reading the genomes")
+        for i in np.flatnonzero(skipped[:n]):
+            logger.warning(f"skipped {skipped[i]} malformed feature lines of {gff_paths[i]}")
+        self.names.extend(names)
+        return rc
+
     def add_genome_text(self, name, gff_text, fasta_text=None):
         gff = gff_text.encode() if isinstance(gff_text, str) else gff_text
         fasta = fasta_text.encode() if isinstance(fasta_text, str) else fasta_text
@@ -184,7 +202,7 @@ def prep_feeder(filelist, fastalist, gffdir, fastadir, output=None):
             if f.endswith(".fna") or f.endswith(".fasta"):
                 fasta_path[_genome_name(f)] = f if is_list else os.path.join(fastadir, f)
     feeder = NativeFeeder()
-    index = {}
+    gffs, fastas = [], []
     for genome in filelist:
         logger.debug(f"Handling {genome}")
         fasta = None
@@ -193,7 +211,10 @@ def prep_feeder(filelist, fastalist, gffdir, fastadir, output=None):
                 logger.error(f"Neither {genome}.fna not {genome}.fasta found in {fastadir}")
                 sys.exit(1)
             fasta = fasta_path[genome]
-        index[genome] = feeder.add_genome(genome, gff_path[genome], fasta)
+        gffs.append(gff_path[genome])
+        fastas.append(fasta)
+    first = feeder.add_genomes(list(filelist), gffs, fastas)
+    index = {genome: first + i for i, genome in enumerate(filelist)}
     return feeder, index
 
 
