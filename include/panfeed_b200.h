@@ -227,8 +227,8 @@ int pf_pattern_ids(pf_ctx* ctx, int cluster_namespace, uint64_t first, uint64_t 
                    uint8_t* host_digests);
 int pf_stats_get(pf_ctx* ctx, pf_stats* out);
 /* sizeof of the ABI structs as the library was built: 0 pf_params, 1 pf_seq_desc,
- * 2 pf_cluster_desc, 3 pf_batch, 4 pf_batch_result, 5 pf_stats, 6 pf_synth_params; 0 for an
- * unknown id.  Lets a binding check its own struct mirrors. */
+ * 2 pf_cluster_desc, 3 pf_batch, 4 pf_batch_result, 5 pf_stats, 6 pf_synth_params,
+ * 7 pf_cut_result; 0 for an unknown id.  Lets a binding check its own struct mirrors. */
 uint32_t pf_struct_size(int which);
 /* CUDA stream the context launches on, as an opaque handle (cudaStream_t). */
 void* pf_stream(pf_ctx* ctx);

@@ -31,6 +31,7 @@ extern "C" uint32_t pf_struct_size(int which) {
     case 4: return (uint32_t)sizeof(pf_batch_result);
     case 5: return (uint32_t)sizeof(pf_stats);
     case 6: return (uint32_t)sizeof(pf_synth_params);
+    case 7: return (uint32_t)sizeof(pf_cut_result);
     default: return 0;
   }
 }
