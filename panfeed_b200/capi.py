@@ -187,8 +187,8 @@ def load():
     lib.pf_free.argtypes = [vp]
     lib.pf_free.restype = None
     lib.pf_pack_plan.argtypes = [vp, u32, vp, C.POINTER(u64)]
-    lib.pf_pack_2bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, u32]
-    lib.pf_pack_4bit.argtypes = [C.c_char_p, vp, u32, vp, vp, vp, C.POINTER(u64), C.POINTER(C.c_int)]
+    lib.pf_pack_2bit.argtypes = [vp, vp, u32, vp, vp, vp, u32]          # ascii: bytes or a raw address
+    lib.pf_pack_4bit.argtypes = [vp, vp, u32, vp, vp, vp, C.POINTER(u64), C.POINTER(C.c_int)]
     lib.pf_format_positions.argtypes = [C.POINTER(BatchResult), u32, C.c_int, u64, u64, C.c_char_p,
                                         C.POINTER(u64), C.POINTER(C.c_int32), C.c_char_p, u64,
                                         C.POINTER(u64), u32]
@@ -227,8 +227,9 @@ def pack_sequences(seq_bytes, n_threads=0):
 
 
 def pack_blob(blob, seq_off, n_threads=0):
-    """The same from the sequences back to back (`blob`, bytes) and their offsets
-    (`seq_off`, uint64 [n + 1]): what the native feeder hands over."""
+    """The same from the sequences back to back (`blob`: bytes, or the address of a buffer that
+    stays valid during the call, e.g. pf_cut_result.ascii) and their offsets (`seq_off`, uint64
+    [n + 1]): what the native feeder hands over."""
     lib = load()
     seq_off = np.ascontiguousarray(seq_off, dtype=np.uint64)
     n = len(seq_off) - 1

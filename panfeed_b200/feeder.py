@@ -116,9 +116,12 @@ class NativeFeeder:
             got = self._feature_names[key] = self.feature(genome, feature)[:2]
         return got
 
-    def cut(self, genomes, cells_blob, up, down, down_start_codon):
+    def cut(self, genomes, cells_blob, up, down, down_start_codon, prepack=False):
         """genomes: uint32 array (genome index per cell); cells_blob: the cells joined with
-        newlines (bytes).  -> dict of copies of the pf_cut_result arrays."""
+        newlines (bytes).  -> dict of copies of the pf_cut_result arrays.  prepack: the sequences
+        are packed into the 2-bit / 4-bit planes straight from the library's buffer ("packed",
+        "base_off", "is_amb", "amb_plane", "amb_off" as capi.pack_blob returns them) and the ASCII
+        text is not copied out ("ascii" is None)."""
         genomes = np.ascontiguousarray(genomes, dtype=np.uint32)
         res = capi.CutResult()
         rc = self.lib.pf_feeder_cut(self.h, len(genomes), genomes.ctypes.data, cells_blob, len(cells_blob),
@@ -132,13 +135,18 @@ class NativeFeeder:
                 return np.zeros(0, dtype)
             return np.ctypeslib.as_array(ptr, shape=(count,)).astype(dtype, copy=True)
 
-        seq_off = arr(res.seq_off, n + 1, np.uint64)
+        seq_off = arr(res.seq_off, n + 1, np.uint64) if n else np.zeros(1, np.uint64)
         out = {"n_seqs": n, "seq_off": seq_off,
-               "ascii": C.string_at(res.ascii, int(seq_off[-1])) if n else b"",
                "cell": arr(res.cell, n, np.uint32), "feature": arr(res.feature, n, np.uint32),
                "start": arr(res.start, n, np.int32), "end": arr(res.end, n, np.int32),
                "offset": arr(res.offset, n, np.int32), "strand": arr(res.strand, n, np.int32),
                "missing": []}
+        if prepack:
+            out["ascii"] = None
+            (out["packed"], out["base_off"], out["is_amb"], out["amb_plane"],
+             out["amb_off"]) = capi.pack_blob(res.ascii if n else b"", seq_off)
+        else:
+            out["ascii"] = C.string_at(res.ascii, int(seq_off[-1])) if n else b""
         if res.n_missing:
             moff = arr(res.missing_off, res.n_missing + 1, np.uint64)
             text = C.string_at(res.missing_text, int(moff[-1]))
@@ -150,17 +158,21 @@ class NativeFeeder:
 
 
 class NativePackedCluster:
-    """The attributes of `packer.PackedCluster`, filled from a native cut: sequences as one
-    ASCII blob + lengths (`seq_bytes` and `meta` are built only if somebody asks)."""
-    __slots__ = ("idx", "clusterpresab", "ascii_blob", "seq_len", "sample", "target", "start", "end",
-                 "offset", "strand", "k", "canonical", "consider_missing", "_feeder", "_genome",
-                 "_feature", "_order", "_meta")
+    """The attributes of `packer.PackedCluster`, filled from a native cut whose sequences were
+    packed on the spot: `packed_words` / `amb_words` are this cluster's slices of the 2-bit / 4-bit
+    planes (every sequence starts on a 64-base boundary, so a cluster is a whole number of words),
+    `base_rel` / `amb_rel` the offsets inside them.  `seq_bytes` (decoded from the planes) and
+    `meta` are built only if somebody asks."""
+    __slots__ = ("idx", "clusterpresab", "packed_words", "base_rel", "is_amb", "amb_words", "amb_rel",
+                 "seq_len", "sample", "target", "start", "end", "offset", "strand", "k", "canonical",
+                 "consider_missing", "_feeder", "_genome", "_feature", "_order", "_meta")
 
-    def __init__(self, idx, clusterpresab, ascii_blob, seq_len, sample, target, start, end, offset, strand,
-                 genome, feature, order, feeder):
+    def __init__(self, idx, clusterpresab, packed_words, base_rel, is_amb, amb_words, amb_rel, seq_len,
+                 sample, target, start, end, offset, strand, genome, feature, order, feeder):
         self.idx = idx
         self.clusterpresab = clusterpresab
-        self.ascii_blob = ascii_blob
+        self.packed_words, self.base_rel = packed_words, base_rel
+        self.is_amb, self.amb_words, self.amb_rel = is_amb, amb_words, amb_rel
         self.seq_len = seq_len
         self.sample = sample
         self.target = target
@@ -170,8 +182,24 @@ class NativePackedCluster:
 
     @property
     def seq_bytes(self):
-        off = np.concatenate([[0], np.cumsum(self.seq_len)])
-        return [self.ascii_blob[int(off[i]):int(off[i + 1])] for i in range(len(self.seq_len))]
+        """The sequences as ASCII, decoded from the planes (tests, debugging)."""
+        acgt = np.frombuffer(b"ACGT", np.uint8)
+        amb = np.frombuffer(capi.AMB_ALPHABET.encode(), np.uint8)
+        sh2 = (62 - 2 * np.arange(32)).astype(np.uint64)
+        sh4 = (60 - 4 * np.arange(16)).astype(np.uint64)
+        out = []
+        for i, n in enumerate(self.seq_len.tolist()):
+            if self.is_amb[i]:
+                w0 = int(self.amb_rel[i]) // 16
+                words = self.amb_words[w0:w0 + (n + 15) // 16]
+                codes = ((words[:, None] >> sh4[None, :]) & np.uint64(15)).astype(np.uint8).ravel()[:n]
+                out.append(amb[codes].tobytes())
+            else:
+                w0 = int(self.base_rel[i]) // 32
+                words = self.packed_words[w0:w0 + (n + 31) // 32]
+                codes = ((words[:, None] >> sh2[None, :]) & np.uint64(3)).astype(np.uint8).ravel()[:n]
+                out.append(acgt[codes].tobytes())
+        return out
 
     @property
     def meta(self):
@@ -260,7 +288,7 @@ def iter_packed_clusters(panaroo, feeder, genome_index, up, down, down_start_cod
         rr, cc = np.nonzero(pres)                    # row-major: cluster by cluster, ranks ascending
         cells = values[sel][pres]
         blob = "\n".join(cells).encode() if len(cells) else b""
-        cut = feeder.cut(genome_of_rank[cc], blob, up, down, down_start_codon)
+        cut = feeder.cut(genome_of_rank[cc], blob, up, down, down_start_codon, prepack=True)
         for cell, kind, name in cut["missing"]:
             idx, strain = index[sel[rr[cell]]], order[cc[cell]]
             msg = (f"Could not find gene {name} from {idx} in {strain}" if kind == 0
@@ -274,16 +302,25 @@ def iter_packed_clusters(panaroo, feeder, genome_index, up, down, down_start_cod
         genome = genome_of_rank[sample]
         seq_len = np.diff(cut["seq_off"]).astype(np.int64)
         first = np.searchsorted(seq_cluster, np.arange(len(sel) + 1))
-        byte_at = cut["seq_off"]
+        # word ranges of the clusters in the planes of this cut
+        packed, base_off, is_amb = cut["packed"], cut["base_off"].astype(np.int64), cut["is_amb"]
+        word_at = np.concatenate([base_off // 32, [len(packed)]]).astype(np.int64)
+        amb_plane = cut["amb_plane"] if cut["amb_plane"] is not None else np.zeros(0, np.uint64)
+        padded = (seq_len + 63) // 64 * 64
+        amb_sym_at = np.concatenate([[0], np.cumsum(np.where(is_amb, padded, 0))]).astype(np.int64)
+        amb_off = cut["amb_off"].astype(np.int64)
         for j, i in enumerate(sel):
             idx = index[i]
             logger.debug(f"Extracting sequences from {idx} ({i + 1}/{n_rows})")
             a, b = int(first[j]), int(first[j + 1])
             clusterpresab = pres[j].astype(int)
-            pc = NativePackedCluster(idx, clusterpresab, cut["ascii"][int(byte_at[a]):int(byte_at[b])],
-                                     seq_len[a:b], sample[a:b], target[a:b], cut["start"][a:b], cut["end"][a:b],
-                                     cut["offset"][a:b], cut["strand"][a:b], genome[a:b], cut["feature"][a:b],
-                                     order, feeder)
+            amb_c = is_amb[a:b]
+            pc = NativePackedCluster(
+                idx, clusterpresab, packed[int(word_at[a]):int(word_at[b])], base_off[a:b] - (base_off[a] if b > a else 0),
+                amb_c, amb_plane[int(amb_sym_at[a]) // 16:int(amb_sym_at[b]) // 16],
+                np.where(amb_c, amb_off[a:b] - amb_sym_at[a], 0), seq_len[a:b], sample[a:b], target[a:b],
+                cut["start"][a:b], cut["end"][a:b], cut["offset"][a:b], cut["strand"][a:b], genome[a:b],
+                cut["feature"][a:b], order, feeder)
             pc.k, pc.canonical, pc.consider_missing = klength, bool(canon), bool(consider_missing_cluster)
             yield idx, pc, clusterpresab, None
         at = to

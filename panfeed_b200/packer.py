@@ -129,19 +129,47 @@ class SeqMeta:
 def pack_batch(packed_clusters, cluster_ids=None):
     """-> (capi.HostBatch, seq_meta (SeqMeta), cluster idx list).  Clusters are
     `PackedCluster`s (Python cutting) or `feeder.NativePackedCluster`s (one ASCII blob each)."""
-    blobs, lens = [], []
+    # planes: clusters the native feeder packed at cutting time bring their word ranges; runs of
+    # clusters that still hold ASCII sequences are packed here; the pieces are then laid end to end
+    # (every sequence starts on a 64-base boundary, so that equals packing everything at once)
+    parts, lens, run = [], [], []
+
+    def flush_run():
+        if run:
+            n = len(run)
+            off = np.zeros(n + 1, np.uint64)
+            np.cumsum(np.fromiter((len(b) for b in run), np.uint64, n), out=off[1:])
+            parts.append(capi.pack_blob(b"".join(run), off))
+            run.clear()
+
     for pc in packed_clusters:
-        if hasattr(pc, "ascii_blob"):
-            blobs.append(pc.ascii_blob)
+        if hasattr(pc, "packed_words"):
+            flush_run()
+            parts.append((pc.packed_words, pc.base_rel, pc.is_amb, pc.amb_words if pc.is_amb.any() else None,
+                          pc.amb_rel))
             lens.append(pc.seq_len)
         else:
-            blobs.extend(pc.seq_bytes)
+            run.extend(pc.seq_bytes)
             lens.append(np.fromiter((len(b) for b in pc.seq_bytes), np.int64, len(pc.seq_bytes)))
+    flush_run()
     lens = np.concatenate(lens).astype(np.int64) if lens else np.zeros(0, np.int64)
     n_seqs = len(lens)
-    seq_off = np.zeros(n_seqs + 1, np.uint64)
-    np.cumsum(lens, out=seq_off[1:])
-    packed, base_off, amb_seq, amb_plane, amb_off = capi.pack_blob(b"".join(blobs), seq_off)
+    words, amb_words = 0, 0
+    base_off, amb_seq, amb_off, amb_planes = [], [], [], []
+    for pk, bo, ia, ap, ao in parts:
+        ia = np.asarray(ia, bool)
+        base_off.append(np.asarray(bo, np.uint64) + np.uint64(words * 32))
+        amb_seq.append(ia)
+        amb_off.append(np.where(ia, np.asarray(ao, np.uint64) + np.uint64(amb_words * 16), np.uint64(0)).astype(np.uint64))
+        words += len(pk)
+        if ap is not None and len(ap):
+            amb_planes.append(ap)
+            amb_words += len(ap)
+    packed = np.concatenate([p[0] for p in parts]) if parts else np.zeros(0, np.uint64)
+    base_off = np.concatenate(base_off) if base_off else np.zeros(0, np.uint64)
+    amb_seq = np.concatenate(amb_seq) if amb_seq else np.zeros(0, bool)
+    amb_off = np.concatenate(amb_off) if amb_off else np.zeros(0, np.uint64)
+    amb_plane = np.concatenate(amb_planes) if amb_planes else None
 
     seqs = np.zeros(n_seqs, capi.SEQ_DTYPE)
     clusters = np.zeros(len(packed_clusters), capi.CLUSTER_DTYPE)

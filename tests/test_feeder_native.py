@@ -132,6 +132,7 @@ def test_native_feeder_parsing_quirks_match_python(tmp_path):
     assert set(got) == {"g1", "overrides", "g3", "g4", "no_contig", "trail\n"}
     assert got["g1"][1:3] == (1, 6)
     table = pd.DataFrame({"q": ["g1;overrides;g3;nope;g4;no_contig;"]}, index=["cl"])
+    saw_amb = False
     for up, down, dsc in [(0, 0, False), (3, 4, False), (100, 100, False), (2, 2, True), (30, 0, True)]:
         py = list(pyin.iter_gene_clusters(table, {"q": (contigs, feats)}, up, down, dsc, True))
         a = packer.PackedCluster(py[0][0], "cl", py[0][2], {"q"})
@@ -140,6 +141,19 @@ def test_native_feeder_parsing_quirks_match_python(tmp_path):
         assert a.meta == b.meta
         for f in ("sample", "target", "start", "end", "offset", "strand"):
             assert (np.asarray(getattr(a, f)) == np.asarray(getattr(b, f))).all(), (up, down, dsc, f)
+        # batches mixing clusters packed at cutting time (N / IUPAC sequences included) with clusters
+        # that still hold ASCII: the planes must be those of packing everything at once
+        want, _, _ = packer.pack_batch([a, a, a, a])
+        for mix in ([b, b, b, b], [a, b, a, b], [b, a, a, b], [a, a, b, b]):
+            got, meta, _ = packer.pack_batch(mix)
+            assert (got.packed == want.packed).all(), (up, down, dsc)
+            assert got.seqs.tobytes() == want.seqs.tobytes(), (up, down, dsc)
+            assert (got.amb is None) == (want.amb is None)
+            if want.amb is not None:
+                assert (got.amb == want.amb).all()
+            assert list(meta) == a.meta * 4
+        saw_amb |= want.amb is not None
+    assert saw_amb                                               # the quirk contig holds N / R / Y
     # the same genome from memory, with the FASTA given separately
     g2 = native.add_genome_text("q2", GFF, ">ctg1\nACGT\n")
     assert native.genome_info(g2) == {"features": len(feats), "contigs": 1, "bases": 4}
