@@ -582,12 +582,39 @@ class Context:
         return self.lib.pf_stream(self.h)
 
 
+class SynthArena:
+    """Reusable pinned host buffers for synth_batch (streamed benchmarks generate one batch
+    after the other; allocating and pinning ~300 MB per batch would dominate)."""
+
+    def __init__(self):
+        self.packed = self.seqs = self.clusters = self.presence = None
+
+    @staticmethod
+    def _pinned(nbytes):
+        import torch
+        return torch.empty(max(8, int(nbytes)), dtype=torch.uint8, pin_memory=True).numpy()
+
+    def take(self, n_words, n_seqs, n_clusters, W):
+        def grow(cur, nbytes):
+            if cur is None or cur.nbytes < nbytes:
+                return self._pinned(nbytes + nbytes // 8)
+            return cur
+        self.packed = grow(self.packed, n_words * 8)
+        self.seqs = grow(self.seqs, n_seqs * SEQ_DTYPE.itemsize)
+        self.clusters = grow(self.clusters, n_clusters * CLUSTER_DTYPE.itemsize)
+        self.presence = grow(self.presence, n_clusters * W * 4)
+        return (self.packed[:n_words * 8].view(np.uint64),
+                self.seqs[:n_seqs * SEQ_DTYPE.itemsize].view(SEQ_DTYPE),
+                self.clusters[:n_clusters * CLUSTER_DTYPE.itemsize].view(CLUSTER_DTYPE),
+                self.presence[:n_clusters * W * 4].view(np.uint32).reshape(n_clusters, W))
+
+
 def synth_batch(device, seed, n_samples, n_clusters, first_cluster=0,
                 total_clusters=None, gene_len=1200, n_founders=8,
                 founder_div=0.01, private_div=0.001, core_fraction=0.6,
-                paralog_rate=0.01, all_targets=False, pinned=False):
+                paralog_rate=0.01, all_targets=False, pinned=False, arena=None):
     """Deterministic synthetic batch, bases generated on the
-    device and returned in host arrays."""
+    device and returned in host arrays (pinned, reused, when `arena` is given)."""
     lib = load()
     p = SynthParams(seed, n_samples, n_clusters, first_cluster, gene_len,
                     n_founders, founder_div, private_div, core_fraction,
@@ -598,15 +625,18 @@ def synth_batch(device, seed, n_samples, n_clusters, first_cluster=0,
     if rc != 0:
         raise PfError(rc, "pf_synth_plan failed")
     W = lib.pf_pattern_words(n_samples)
-    seqs = np.zeros(n_seqs.value, SEQ_DTYPE)
-    clusters = np.zeros(n_clusters, CLUSTER_DTYPE)
-    presence = np.zeros((n_clusters, W), np.uint32)
-    if pinned:
-        import torch
-        packed = torch.empty(max(1, n_words.value), dtype=torch.int64,
-                             pin_memory=True).numpy().view(np.uint64)[:n_words.value]
+    if arena is not None:
+        packed, seqs, clusters, presence = arena.take(n_words.value, n_seqs.value, n_clusters, W)
     else:
-        packed = np.zeros(n_words.value, np.uint64)
+        seqs = np.zeros(n_seqs.value, SEQ_DTYPE)
+        clusters = np.zeros(n_clusters, CLUSTER_DTYPE)
+        presence = np.zeros((n_clusters, W), np.uint32)
+        if pinned:
+            import torch
+            packed = torch.empty(max(1, n_words.value), dtype=torch.int64,
+                                 pin_memory=True).numpy().view(np.uint64)[:n_words.value]
+        else:
+            packed = np.zeros(n_words.value, np.uint64)
     rc = lib.pf_synth_fill(device, C.byref(p), seqs.ctypes.data,
                            clusters.ctypes.data, presence.ctypes.data,
                            packed.ctypes.data)

@@ -2,7 +2,7 @@
 # per-launch device times of one full config-2 step (cold cache, serialised: compare SHARES)
 TAG=${1:-ll}
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${TAG}.csv \
-  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e ${@:2} > gpurun_out/ll_${TAG}.log 2>&1
+  python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-extra ${@:2} > gpurun_out/ll_${TAG}.log 2>&1
 python - <<PY
 import csv, collections
 rows = [r for r in csv.reader(open("gpurun_out/launches_${TAG}.csv")) if len(r) > 10 and r[0].isdigit()]

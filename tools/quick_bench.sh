@@ -1,6 +1,6 @@
 #!/bin/bash
 # quick resident-only bench of config 2 (no e2e, no cpu baseline) + stage split
-timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/qb.json 2> gpurun_out/qb.err || tail -5 gpurun_out/qb.err
+timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e --no-extra > gpurun_out/qb.json 2> gpurun_out/qb.err || tail -5 gpurun_out/qb.err
 python - <<PY
 import json
 d = json.load(open("gpurun_out/qb.json"))
