@@ -319,20 +319,35 @@ int pf_synth_fill(int device, const pf_synth_params* p, pf_seq_desc* seqs,
 /* ---- multi-GPU global pattern dedup ----
  * Clusters are sharded over ranks; the only global state is the reference's
  * `patterns` set (__main__.py:70).  Owner of a pattern = hash(bitset) % world.
- * The caller moves the buffers between ranks (NCCL all-to-all); all pointers
- * in this group are DEVICE pointers owned by the caller. */
+ * The caller moves the buffers between ranks (NCCL all-to-all on the context's
+ * stream, see pf_stream); all pointers in this group are DEVICE pointers owned
+ * by the caller unless named *_host.  Order of one namespace:
+ *   pf_exchange_pack      local patterns bucketed by owner -> send buffer; bucket sizes on the host
+ *                         (the one host sync: they are the split sizes of the all-to-all)
+ *   [all-to-all of the keys]
+ *   pf_exchange_dedup     owner side: unique index of every received key (bit 31 set on the first
+ *                         copy of a pattern: its sender is the one that writes the pattern row),
+ *                         the number of unique keys to a device word (asynchronous) and/or the host
+ *   [all-gather of the unique counts -> exclusive scan = owner_base; reverse all-to-all of the indices]
+ *   pf_exchange_unpack    local_to_global[i] = owner_base[owner(i)] + unique index; writer[i] = bit 31
+ *                         (asynchronous on the context's stream) */
 int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t world,
                      const uint32_t* mask_remap_dev, /* local->global cluster-pattern ids, or NULL */
                      uint32_t* send_words_dev, uint64_t capacity_patterns,
                      uint64_t* counts_host /* [world] */);
 int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace,
                       const uint32_t* recv_words_dev, uint64_t n_recv,
-                      uint32_t* recv_unique_index_dev, uint64_t* n_unique_host);
+                      uint32_t* recv_unique_index_dev,
+                      uint32_t* n_unique_dev /* one word, may be NULL */,
+                      uint64_t* n_unique_host /* may be NULL: then the call does not synchronise */);
+int pf_exchange_unique_count(pf_ctx* ctx, int cluster_namespace, uint64_t* n_unique_host);
 int pf_exchange_unique_export(pf_ctx* ctx, int cluster_namespace,
                               uint32_t* host_out /* n_unique x words */);
 int pf_exchange_unpack(pf_ctx* ctx, int cluster_namespace,
                        const uint32_t* returned_ids_dev, /* in send order */
-                       uint32_t* local_to_global_dev /* [n local patterns] */);
+                       const uint32_t* owner_base_dev /* [world] or NULL (ids already global) */,
+                       uint32_t* local_to_global_dev /* [n local patterns] */,
+                       uint8_t* writer_dev /* [n local patterns] or NULL */);
 
 /* ---- native feeder (host threads of the caller): GFF3 + FASTA -> cut sequences of a cluster ----
  * Replaces, for the feeding side of the path, the reference's parse_gff (input.py:274-332), its

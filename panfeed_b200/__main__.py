@@ -2,15 +2,24 @@
 (`/root/reference/panfeed/__main__.py:84-223`) and wiring (`:226-369`), with the
 two hot callables running on the GPU.  `--cores` and `-ql` are accepted for
 compatibility; clusters are batched to the device instead of forked workers, so
-row order is deterministic and `--compress` output is always valid gzip."""
+row order is deterministic and `--compress` output is always valid gzip.
+
+Several GPUs: `torchrun --nproc-per-node N -m panfeed_b200 <same options>` (one process per
+GPU).  The reference's parallel mode is a reader, N-2 `cluster_cutter` workers and ONE writer
+that owns the `patterns` set (`__main__.py:299-344`, `:70`); here whole clusters are sharded
+over the ranks (greedy by number of genes), every rank writes header-less pieces of
+kmers.tsv / kmers_to_hashes for its clusters, one NCCL exchange (dist.PatternExchange) decides
+which rank writes each pattern's hashes_to_patterns row, and rank 0 joins the pieces into the
+same three files a single process writes."""
 import argparse
 import logging
+import os
 import sys
 from functools import partial
 
 from . import __version__
-from .input import (clean_up_fasta, iter_gene_clusters, prep_data_n_fasta, set_input_output,
-                    what_are_my_inputfiles)
+from .input import (KMERS_TSV_HEADER, clean_up_fasta, create_part_files, iter_gene_clusters,
+                    merge_part_files, prep_data_n_fasta, set_input_output, what_are_my_inputfiles)
 from .panfeed import PatternStore, cluster_cutter, pattern_hasher, write_headers
 
 logger = logging.getLogger("panfeed")
@@ -41,7 +50,9 @@ def get_options(argv=None):
     p.add_argument("-o", "--output", default="panfeed",
                    help="Output directory (must not exist)")
     p.add_argument("-f", "--fasta", help="Directory or file of files with nucleotide fastas")
-    p.add_argument("-k", "--kmer-length", type=int, default=31, help="K-mer length (1..32)")
+    p.add_argument("-k", "--kmer-length", type=int, default=31,
+                   help="K-mer length, 1..32 (this build packs a k-mer into one 64-bit word; the "
+                        "reference accepts longer k-mers, this build exits with an error)")
     p.add_argument("--maf", type=float, default=0.01, help="Minor allele frequency threshold")
     p.add_argument("--upstream", type=int, default=0)
     p.add_argument("--downstream", type=int, default=0)
@@ -79,15 +90,46 @@ def main(argv=None):
         logger.error("this build supports k-mer lengths 1..32 (64-bit 2-bit encoding)")
         sys.exit(1)
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    sharded = world > 1
+    if sharded:
+        import torch
+        import torch.distributed as tdist
+        args.device = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(args.device)
+        os.environ.setdefault("PF_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // world)))
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", args.device))
+        if os.path.exists(args.output):          # every rank sees the same answer: no rank is left waiting
+            logger.error(f"Output directory {args.output} exists! Please remove it and restart")
+            tdist.barrier()
+            sys.exit(1)
+        tdist.barrier()
+
     logger.info("Looking at input GFF files")
     filelist, fastalist = what_are_my_inputfiles(args.gff, args.fasta)
     logger.info(f"Found {len(filelist)} input genomes")
     logger.info("Preparing output files")
     (stroi, genes, kmer_stroi, hash_pat, kmer_hash, genepres) = set_input_output(
         args.targets, args.genes, args.presence_absence, args.output,
-        not args.multiple_files, args.compress)
+        not args.multiple_files, args.compress, make_outputs=not sharded)
+    all_columns = genepres
+    if sharded:
+        if rank == 0:
+            os.mkdir(args.output)
+        tdist.barrier()
+        if not args.multiple_files:
+            kmer_stroi, hash_pat, kmer_hash = create_part_files(args.output, rank, args.compress)
+        # whole clusters to ranks, greedy by the number of genes (cells) of the rows that will be cut
+        from .dist import shard_clusters
+        weights = genepres.notna().sum(axis=1).to_numpy()
+        if genes is not None:
+            weights = weights * genepres.index.isin(list(genes))
+        mine = shard_clusters(weights, world)[rank]
+        genepres = genepres.iloc[mine]
+        logger.info(f"rank {rank}/{world}: {len(mine)} of {len(weights)} clusters")
     logger.info("Preparing inputs")
-    if not args.multiple_files:
+    if not args.multiple_files and not sharded:
         write_headers(hash_pat, kmer_hash, genepres)
     logger.info("Extracting k-mers")
     if args.native_feeder:
@@ -107,18 +149,32 @@ def main(argv=None):
                          consider_missing_cluster=args.consider_missing, output=args.output,
                          compress=args.compress)
         cut_clusters = (iter_o(x) for x in iter_i)
-    patterns = PatternStore()
+    patterns = PatternStore(sharded=sharded and not args.multiple_files)
     func_w = partial(pattern_hasher, kmer_stroi=kmer_stroi, hash_pat=hash_pat,
-                     kmer_hash=kmer_hash, genepres=genepres, patfilt=not args.no_filter,
+                     kmer_hash=kmer_hash, genepres=all_columns, patfilt=not args.no_filter,
                      maf=args.maf, consider_missing_cluster=args.consider_missing,
                      output=args.output, compress=args.compress, device=args.device)
     # one streaming call: the generator packs clusters while the GPU batches them
     patterns = func_w(cut_clusters, patterns=patterns)
+    if patterns.sharded:
+        info = patterns.finish_sharded(hash_pat, klength, len(all_columns.columns), not args.non_canonical,
+                                       args.consider_missing, args.no_filter, args.maf, args.device)
+        logger.info(f"rank {rank}: wrote {info['written_here']} of {info['cluster_patterns_global']} + "
+                    f"{info['kmer_patterns_global']} patterns")
     patterns.close()
 
     for handle in (kmer_stroi, hash_pat, kmer_hash):
         if handle is not None:
             handle.close()
+    if sharded:
+        tdist.barrier()
+        if rank == 0 and not args.multiple_files:
+            import io
+            hp, kh = io.StringIO(), io.StringIO()
+            write_headers(hp, kh, all_columns)
+            merge_part_files(args.output, world, (KMERS_TSV_HEADER, hp.getvalue(), kh.getvalue()), args.compress)
+        tdist.barrier()
+        tdist.destroy_process_group()
     logger.info("Removing temporary fasta files and faidx indices")
     clean_up_fasta(filelist, fastalist, args.output, args.fasta)
 

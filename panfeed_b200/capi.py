@@ -132,7 +132,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_feeder_add_genome_text", "pf_feeder_genome_info", "pf_feeder_feature", "pf_feeder_cut",
            "pf_tsv_filter", "pf_free",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
-           "pf_exchange_dedup", "pf_exchange_unique_export",
+           "pf_exchange_dedup", "pf_exchange_unique_count", "pf_exchange_unique_export",
            "pf_exchange_unpack"]
 
 _lib = None
@@ -199,9 +199,10 @@ def load():
     lib.pf_synth_plan.argtypes = [C.POINTER(SynthParams), C.POINTER(u32), C.POINTER(u64)]
     lib.pf_synth_fill.argtypes = [C.c_int, C.POINTER(SynthParams), vp, vp, vp, vp]
     lib.pf_exchange_pack.argtypes = [vp, C.c_int, u32, vp, vp, u64, C.POINTER(u64)]
-    lib.pf_exchange_dedup.argtypes = [vp, C.c_int, vp, u64, vp, C.POINTER(u64)]
+    lib.pf_exchange_dedup.argtypes = [vp, C.c_int, vp, u64, vp, vp, C.POINTER(u64)]
+    lib.pf_exchange_unique_count.argtypes = [vp, C.c_int, C.POINTER(u64)]
     lib.pf_exchange_unique_export.argtypes = [vp, C.c_int, vp]
-    lib.pf_exchange_unpack.argtypes = [vp, C.c_int, vp, vp]
+    lib.pf_exchange_unpack.argtypes = [vp, C.c_int, vp, vp, vp, vp]
     if lib.pf_abi_version() != PF_ABI_VERSION:
         raise PfError(-1, "ABI version mismatch")
     _lib = lib
@@ -272,7 +273,10 @@ def format_patterns(words, n_samples, ids, present=None, n_threads=0):
     n = len(words)
     if n == 0:
         return b""
-    idb = b"".join(x if isinstance(x, bytes) else x.encode() for x in ids)
+    if isinstance(ids, np.ndarray) and ids.dtype == np.dtype("S24"):
+        idb = np.ascontiguousarray(ids).tobytes()
+    else:
+        idb = b"".join(x if isinstance(x, bytes) else x.encode() for x in ids)
     assert len(idb) == 24 * n
     pres = None if present is None else np.ascontiguousarray(present, dtype=np.uint32)
     need = C.c_uint64()

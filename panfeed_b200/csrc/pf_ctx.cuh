@@ -85,6 +85,8 @@ struct PatternSpace {
   // exchange state
   DevBuf x_owner, x_pos, x_perm, x_counts, x_unique, x_table, x_rep, x_slot, x_winner;
   uint64_t x_n_unique = 0;
+  bool x_unique_pending = false;        // x_n_unique still sits in the pinned mirror below
+  const uint32_t* x_unique_mirror = nullptr;
 };
 
 struct WidthState {       // per key width (narrow u64 / wide Key128)
@@ -388,7 +390,8 @@ constexpr uint32_t kBlkMaxSmem = 220u * 1024u;   // largest kA table we ask for
 enum { C_TICKET_N = 0, C_TICKET_W = 1, C_RUNS_N = 2, C_RUNS_W = 3, C_ERR = 4, C_ROWS_N = 5,
        C_ROWS_W = 6, C_NEW_KP = 7, C_NEW_CP = 8, C_TICKET_MARK_N = 9, C_TICKET_MARK_W = 10,
        C_LOCAL = 11 /* LC_COUNT words: rows, unique, table overflow, row overflow, rescue runs,
-                        partial rows, partial overflow */, C_TICKET_MERGE = 18, C_COUNT = 24 };
+                        partial rows, partial overflow */, C_TICKET_MERGE = 18,
+       C_X_UNIQUE_KP = 19, C_X_UNIQUE_CP = 20 /* owner-side unique counts of the exchange */, C_COUNT = 24 };
 static_assert(C_LOCAL + LC_COUNT <= C_TICKET_MERGE, "counter layout");
 
 bool keep_count(double maf, uint32_t c, uint32_t n) {

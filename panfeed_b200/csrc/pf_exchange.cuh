@@ -92,7 +92,8 @@ x_finish(const uint32_t* __restrict__ recv, uint32_t n, uint32_t key_words,
   for (uint32_t e = blockIdx.x * (blockDim.x / L) + threadIdx.x / L; e < n; e += total) {
     const uint32_t q = rep[e] & ~kTentative;         // every rep is tentative here (empty pool)
     const uint32_t u = winner_rank[q];
-    if (gl == 0) unique_index[e] = u;
+    // bit 31: this copy is the representative of its pattern - its sender writes the pattern row
+    if (gl == 0) unique_index[e] = u | (q == e ? 0x80000000u : 0u);
     if (q == e) {
       const uint32_t* src = recv + (size_t)e * key_words;
       uint32_t* dst = unique_keys + (size_t)u * key_words;
@@ -101,10 +102,16 @@ x_finish(const uint32_t* __restrict__ recv, uint32_t n, uint32_t key_words,
   }
 }
 
+// returned[]: the owner's unique index (bit 31 = writer flag) of every pattern, in send order;
+// owner_base[r] (may be null): global id of rank r's first unique pattern
 __global__ void x_unpack(const uint32_t* __restrict__ returned, const uint32_t* __restrict__ perm,
-                         uint32_t n, uint32_t* __restrict__ local_to_global) {
+                         const uint32_t* __restrict__ owner, const uint32_t* __restrict__ owner_base,
+                         uint32_t n, uint32_t* __restrict__ local_to_global, uint8_t* __restrict__ writer) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) local_to_global[i] = returned[perm[i]];
+  if (i >= n) return;
+  const uint32_t v = returned[perm[i]];
+  local_to_global[i] = (v & 0x7fffffffu) + (owner_base ? owner_base[owner[i]] : 0u);
+  if (writer) writer[i] = (uint8_t)(v >> 31);
 }
 
 }  // namespace pf
@@ -130,7 +137,7 @@ extern "C" int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t wor
   if (n) {
     if (!send_words_dev) return fail(ctx, PF_ERR_INVALID, "null send buffer");
     if (world > 32) return fail(ctx, PF_ERR_UNSUPPORTED, "exchange over more than 32 ranks");
-    TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 32 * 4));
+    TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 64 * 4));
     uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;
     const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
     const uint32_t cgrid = std::min<uint32_t>(cdiv(n, 256), kGridPersist * 2);
@@ -159,14 +166,19 @@ extern "C" int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t wor
 }
 
 extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint32_t* recv_words_dev,
-                                 uint64_t n_recv, uint32_t* recv_unique_index_dev, uint64_t* n_unique_host) {
-  if (!ctx || !n_unique_host) return PF_ERR_INVALID;
+                                 uint64_t n_recv, uint32_t* recv_unique_index_dev, uint32_t* n_unique_dev,
+                                 uint64_t* n_unique_host) {
+  if (!ctx || (!n_unique_host && !n_unique_dev)) return PF_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
   PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
   cudaStream_t st = ctx->stream;
-  *n_unique_host = 0;
+  if (n_unique_host) *n_unique_host = 0;
   s.x_n_unique = 0;
-  if (n_recv == 0) return PF_OK;
+  s.x_unique_pending = false;
+  if (n_recv == 0) {
+    if (n_unique_dev) CU(cudaMemsetAsync(n_unique_dev, 0, 4, st));
+    return PF_OK;
+  }
   if (n_recv >= (1ull << 30)) return fail(ctx, PF_ERR_INVALID, "too many received patterns");
   if (!recv_words_dev || !recv_unique_index_dev) return fail(ctx, PF_ERR_INVALID, "null exchange buffer");
   const uint32_t n = (uint32_t)n_recv;
@@ -183,7 +195,7 @@ extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint3
   TRY(dev_ensure(ctx, s.x_unique, (size_t)n * s.key_words * 4));
   CU(cudaMemsetAsync(table.p, 0xff, (size_t)size * 4, st));
   uint32_t* counters = ctx->d_counters.p ? ctx->d_counters.as<uint32_t>() : nullptr;
-  if (!counters) { TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4)); TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4)); counters = ctx->d_counters.as<uint32_t>(); }
+  if (!counters) { TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4)); TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 64 * 4)); counters = ctx->d_counters.as<uint32_t>(); }
   const uint32_t grid = std::min<uint32_t>(cdiv(n, 8), kGridPersist * 2);
   {
     // lanes per pattern as in K4: short keys would leave most of a warp idle
@@ -195,7 +207,8 @@ extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint3
     if (L == 4) PF_XP(4); else if (L == 8) PF_XP(8); else if (L == 16) PF_XP(16); else PF_XP(32);
 #undef PF_XP
   }
-  TRY(scan_inplace(ctx, winner.as<uint32_t>(), n, counters + C_NEW_KP));
+  uint32_t* total_dev = counters + (cluster_namespace ? C_X_UNIQUE_CP : C_X_UNIQUE_KP);
+  TRY(scan_inplace(ctx, winner.as<uint32_t>(), n, total_dev));
   {
     const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
     const uint32_t fgrid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
@@ -206,38 +219,61 @@ extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint3
 #undef PF_XF
   }
   ctx->launches += 2;
-  TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 32 * 4));
-  uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;
-  mirror_counters<<<1, 32, 0, st>>>(hx, counters + C_NEW_KP, 1);
-  CU(cudaStreamSynchronize(st));
+  TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 64 * 4));
+  // pinned mirror of the unique count, one word per namespace (behind the pack counts)
+  uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT + 32 + (cluster_namespace ? 1 : 0);
+  mirror_counters<<<1, 32, 0, st>>>(hx, total_dev, 1);
+  if (n_unique_dev) CU(cudaMemcpyAsync(n_unique_dev, total_dev, 4, cudaMemcpyDeviceToDevice, st));
+  ctx->launches++;
   CU(cudaGetLastError());
-  const uint32_t total = hx[0];
-  s.x_n_unique = total;
-  *n_unique_host = total;
+  s.x_unique_pending = true;          // x_n_unique is read from the mirror once the stream has passed
+  s.x_unique_mirror = hx;
+  if (n_unique_host) {                // the caller wants the count now: one sync
+    CU(cudaStreamSynchronize(st));
+    s.x_n_unique = hx[0];
+    s.x_unique_pending = false;
+    *n_unique_host = hx[0];
+  }
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_unique_count(pf_ctx* ctx, int cluster_namespace, uint64_t* n_unique_host) {
+  if (!ctx || !n_unique_host) return PF_ERR_INVALID;
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  CU(cudaSetDevice(ctx->device));
+  if (s.x_unique_pending) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    s.x_n_unique = s.x_unique_mirror[0];
+    s.x_unique_pending = false;
+  }
+  *n_unique_host = s.x_n_unique;
   return PF_OK;
 }
 
 extern "C" int pf_exchange_unique_export(pf_ctx* ctx, int cluster_namespace, uint32_t* host_out) {
   if (!ctx) return PF_ERR_INVALID;
+  uint64_t n = 0;
+  TRY(pf_exchange_unique_count(ctx, cluster_namespace, &n));
   PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
-  if (s.x_n_unique == 0) return PF_OK;
+  if (n == 0) return PF_OK;
   if (!host_out) return PF_ERR_INVALID;
-  CU(cudaSetDevice(ctx->device));
-  CU(cudaMemcpy(host_out, s.x_unique.p, s.x_n_unique * s.key_words * 4, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(host_out, s.x_unique.p, n * s.key_words * 4, cudaMemcpyDeviceToHost));
   return PF_OK;
 }
 
 extern "C" int pf_exchange_unpack(pf_ctx* ctx, int cluster_namespace, const uint32_t* returned_ids_dev,
-                                  uint32_t* local_to_global_dev) {
+                                  const uint32_t* owner_base_dev, uint32_t* local_to_global_dev,
+                                  uint8_t* writer_dev) {
   if (!ctx) return PF_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
   PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
   const uint32_t n = (uint32_t)s.n;
   if (n == 0) return PF_OK;
   if (!returned_ids_dev || !local_to_global_dev) return fail(ctx, PF_ERR_INVALID, "null exchange buffer");
-  x_unpack<<<cdiv(n, 256), 256, 0, ctx->stream>>>(returned_ids_dev, s.x_perm.as<uint32_t>(), n, local_to_global_dev);
+  // asynchronous on the context's stream: the caller synchronises when it reads the table
+  x_unpack<<<cdiv(n, 256), 256, 0, ctx->stream>>>(returned_ids_dev, s.x_perm.as<uint32_t>(), s.x_owner.as<uint32_t>(),
+                                                  owner_base_dev, n, local_to_global_dev, writer_dev);
   ctx->launches++;
-  CU(cudaStreamSynchronize(ctx->stream));
   CU(cudaGetLastError());
   return PF_OK;
 }

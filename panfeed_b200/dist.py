@@ -11,8 +11,15 @@ makes the numbering global:
     owner(pattern) = hash(full key) % world                (x_classify kernel)
     all-to-all(v) of the full keys to their owners         (NCCL, torch.distributed)
     owner dedups on the full key, numbers its uniques       (k4_probe + scan + x_finish)
-    all-gather of the unique counts -> global id = base[owner] + unique index
-    reverse all-to-all of the ids, scatter to local order   (x_unpack kernel)
+    all-gather of the unique counts -> base[owner] (exclusive scan, on the device)
+    reverse all-to-all of the unique indices; local order + base[owner]   (x_unpack kernel)
+
+Everything (library kernels and NCCL) is enqueued on the context's own stream, so
+nothing waits on the host but the bucket sizes NCCL needs as split sizes (one small
+all-to-all for both namespaces when the k-mer keys do not depend on the cluster
+ids) and the final counts.  Bit 31 of a returned index marks the ONE sender whose copy
+of the pattern was the first at its owner: that rank writes the pattern's
+hashes_to_patterns row (`writer` table), so every pattern is written exactly once.
 
 With --consider-missing a k-mer pattern key ends with the id of the cluster
 pattern that gives its NaN plane, so cluster patterns are exchanged first and the
@@ -49,6 +56,10 @@ class DeviceBackend:
 
     def __init__(self, ctx, device):
         self.ctx, self.device = ctx, device
+        self.consider_missing = bool(ctx.consider_missing)
+
+    def stream(self):
+        return torch.cuda.ExternalStream(self.ctx.stream_handle(), device=self.device)
 
     def key_words(self, ns):
         return self.ctx.W if ns == CLUSTER else self.ctx.Wk
@@ -64,27 +75,37 @@ class DeviceBackend:
             send.data_ptr() if send.numel() else None, send.shape[0], counts))
         return [int(c) for c in counts]
 
-    def dedup(self, ns, recv, unique_index):
-        n_unique = C.c_uint64()
+    def dedup(self, ns, recv, unique_index, n_unique):
+        """Asynchronous: n_unique is a one-element int32 device tensor."""
         self.ctx._check(self.ctx.lib.pf_exchange_dedup(
             self.ctx.h, ns, recv.data_ptr() if recv.numel() else None, recv.shape[0],
-            unique_index.data_ptr() if unique_index.numel() else None, C.byref(n_unique)))
-        return int(n_unique.value)
+            unique_index.data_ptr() if unique_index.numel() else None, n_unique.data_ptr(), None))
 
-    def unique_keys(self, ns, n_unique):
-        out = np.zeros((n_unique, self.key_words(ns)), np.uint32)
+    def unique_keys(self, ns):
+        n = C.c_uint64()
+        self.ctx._check(self.ctx.lib.pf_exchange_unique_count(self.ctx.h, ns, C.byref(n)))
+        out = np.zeros((n.value, self.key_words(ns)), np.uint32)
         self.ctx._check(self.ctx.lib.pf_exchange_unique_export(self.ctx.h, ns, out.ctypes.data))
         return out
 
-    def unpack(self, ns, returned, local_to_global):
+    def unpack(self, ns, returned, owner_base, local_to_global, writer):
         self.ctx._check(self.ctx.lib.pf_exchange_unpack(
             self.ctx.h, ns, returned.data_ptr() if returned.numel() else None,
-            local_to_global.data_ptr() if local_to_global.numel() else None))
+            owner_base.data_ptr(), local_to_global.data_ptr() if local_to_global.numel() else None,
+            writer.data_ptr() if writer is not None and writer.numel() else None))
+
+
+class _NoStream:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
 
 
 class PatternExchange:
     """Global numbering of the patterns of all ranks.  `run()` returns, per
-    namespace, the local->global id table and this rank's owned unique keys."""
+    namespace, the local->global id table, the writer flags and the counts."""
 
     def __init__(self, ctx, device, backend=None, group=None):
         self.backend = backend if backend is not None else DeviceBackend(ctx, device)
@@ -95,55 +116,84 @@ class PatternExchange:
         self.consider_missing = bool(getattr(ctx, "consider_missing", False)) if ctx is not None \
             else bool(getattr(backend, "consider_missing", False))
 
-    def _exchange(self, ns, mask_remap):
+    # -- collectives (world 1: plain copies, so that a single process runs the same path) --
+    def _a2a(self, out, inp, out_split=None, in_split=None):
+        if self.world == 1:
+            out.copy_(inp)
+        else:
+            dist.all_to_all_single(out, inp, output_split_sizes=out_split, input_split_sizes=in_split,
+                                   group=self.group)
+
+    def _gather(self, out, inp):
+        if self.world == 1:
+            out.copy_(inp)
+        else:
+            dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def _pack(self, ns, mask_remap):
+        be, dev = self.backend, self.device
+        n_local = be.n_local(ns)
+        send = torch.empty((n_local, be.key_words(ns)), dtype=torch.int32, device=dev)
+        return {"ns": ns, "n_local": n_local, "send": send,
+                "send_counts": be.pack(ns, self.world, mask_remap, send)}
+
+    def _counts(self, packs):
+        """Bucket sizes of every packed namespace to their owners: one small all-to-all."""
+        world, dev = self.world, self.device
+        sc = torch.tensor([p["send_counts"] for p in packs], dtype=torch.int64).t().contiguous().to(dev)
+        rc = torch.empty_like(sc)                                    # [world, n_packs]
+        self._a2a(rc, sc)
+        rc = rc.cpu().tolist()
+        for j, p in enumerate(packs):
+            p["recv_counts"] = [int(rc[r][j]) for r in range(world)]
+
+    def _finish(self, p, want_writer):
+        """Keys to the owners, owner-side dedup, ids back: all asynchronous on the stream."""
+        be, world, dev, ns = self.backend, self.world, self.device, p["ns"]
+        n_recv = sum(p["recv_counts"])
+        recv = torch.empty((n_recv, p["send"].shape[1]), dtype=torch.int32, device=dev)
+        self._a2a(recv, p["send"], p["recv_counts"], p["send_counts"])
+        uniq_idx = torch.empty(n_recv, dtype=torch.int32, device=dev)
+        nu = torch.zeros(1, dtype=torch.int32, device=dev)
+        be.dedup(ns, recv, uniq_idx, nu)
+        all_nu = torch.empty(world, dtype=torch.int32, device=dev)
+        self._gather(all_nu, nu)
+        owner_base = (torch.cumsum(all_nu, 0, dtype=torch.int32) - all_nu).contiguous()
+        returned = torch.empty(p["n_local"], dtype=torch.int32, device=dev)
+        self._a2a(returned, uniq_idx, p["send_counts"], p["recv_counts"])
+        l2g = torch.empty(p["n_local"], dtype=torch.int32, device=dev)
+        writer = torch.empty(p["n_local"], dtype=torch.uint8, device=dev) if want_writer else None
+        be.unpack(ns, returned, owner_base, l2g, writer)
+        p.update(local_to_global=l2g, writer=writer, all_nu=all_nu, keep=(recv, uniq_idx, returned, owner_base))
+        return p
+
+    def run(self, want_unique=False, want_writer=False):
         import time
         t0 = time.perf_counter()
-        be, world, dev = self.backend, self.world, self.device
-        kw = be.key_words(ns)
-        n_local = be.n_local(ns)
-        send = torch.empty((n_local, kw), dtype=torch.int32, device=dev)
-        send_counts = be.pack(ns, world, mask_remap, send)
-        t1 = time.perf_counter()
-        sc = torch.tensor(send_counts, dtype=torch.int64, device=dev)
-        rc = torch.empty_like(sc)
-        dist.all_to_all_single(rc, sc, group=self.group)
-        recv_counts = [int(x) for x in rc.tolist()]
-        n_recv = sum(recv_counts)
-        recv = torch.empty((n_recv, kw), dtype=torch.int32, device=dev)
-        dist.all_to_all_single(recv, send, output_split_sizes=recv_counts,
-                               input_split_sizes=send_counts, group=self.group)
-        uniq_idx = torch.empty(n_recv, dtype=torch.int32, device=dev)
-        if dev.type == "cuda":
-            torch.cuda.synchronize(dev)      # NCCL ran on torch's stream; the library uses its own
-        t2 = time.perf_counter()
-        n_unique = be.dedup(ns, recv, uniq_idx)
-        t3 = time.perf_counter()
-        nu = torch.tensor([n_unique], dtype=torch.int64, device=dev)
-        all_nu = [torch.empty_like(nu) for _ in range(world)]
-        dist.all_gather(all_nu, nu, group=self.group)
-        counts = [int(x) for x in torch.cat(all_nu).tolist()]      # one read-back, not one per rank
-        base = sum(counts[:self.rank])
-        uniq_idx += base
-        returned = torch.empty(n_local, dtype=torch.int32, device=dev)
-        dist.all_to_all_single(returned, uniq_idx, output_split_sizes=send_counts,
-                               input_split_sizes=recv_counts, group=self.group)
-        l2g = torch.empty(n_local, dtype=torch.int32, device=dev)
-        if dev.type == "cuda":
-            torch.cuda.synchronize(dev)
-        t4 = time.perf_counter()
-        be.unpack(ns, returned, l2g)
-        t5 = time.perf_counter()
-        return {"local_to_global": l2g, "n_global": sum(counts), "n_owned": n_unique,
-                "owned_base": base, "bytes_sent": int(send.numel() * 4),
-                "ms": {"pack": (t1 - t0) * 1e3, "a2a_keys": (t2 - t1) * 1e3, "dedup": (t3 - t2) * 1e3,
-                       "a2a_ids": (t4 - t3) * 1e3, "unpack": (t5 - t4) * 1e3}}
-
-    def run(self, want_unique=False):
-        cl = self._exchange(CLUSTER, None)
-        remap = cl["local_to_global"] if self.consider_missing else None
-        km = self._exchange(KMER, remap)
-        out = {"cluster": cl, "kmer": km}
-        if want_unique:
-            cl["owned_keys"] = self.backend.unique_keys(CLUSTER, cl["n_owned"])
-            km["owned_keys"] = self.backend.unique_keys(KMER, km["n_owned"])
+        be = self.backend
+        use_stream = self.device.type == "cuda" and hasattr(be, "stream")
+        with (torch.cuda.stream(be.stream()) if use_stream else _NoStream()):
+            cl = self._pack(CLUSTER, None)
+            if self.consider_missing:
+                # k-mer keys end with the GLOBAL id of the cluster pattern giving their NaN plane:
+                # the cluster namespace has to be numbered first
+                self._counts([cl])
+                self._finish(cl, want_writer)
+                km = self._pack(KMER, cl["local_to_global"])
+                self._counts([km])
+            else:
+                km = self._pack(KMER, None)
+                self._counts([cl, km])
+                self._finish(cl, want_writer)
+            self._finish(km, want_writer)
+            counts = torch.stack([cl["all_nu"], km["all_nu"]]).cpu().tolist()     # the final sync
+        ms = (time.perf_counter() - t0) * 1e3
+        out = {}
+        for name, p, c in (("cluster", cl, counts[0]), ("kmer", km, counts[1])):
+            out[name] = {"local_to_global": p["local_to_global"], "writer": p["writer"],
+                         "n_global": int(sum(c)), "n_owned": int(c[self.rank]),
+                         "owned_base": int(sum(c[:self.rank])), "bytes_sent": int(p["send"].numel() * 4),
+                         "ms": {"total_both_namespaces": ms}}
+            if want_unique:
+                out[name]["owned_keys"] = be.unique_keys(p["ns"])
         return out

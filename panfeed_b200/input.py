@@ -190,16 +190,51 @@ class GzipTextWriter:
         self.close()
 
 
+KMERS_TSV_HEADER = ("cluster\tstrain\tfeature_id\tcontig\tfeature_strand\tcontig_start\t"
+                    "contig_end\tgene_start\tgene_end\tstrand\tk-mer\n")
+
+
 def create_kmer_stroi(output, compress=False):
     """kmers.tsv(.gz) with its header.  input.py:235-246."""
     if compress:
         handle = GzipTextWriter(os.path.join(output, "kmers.tsv.gz"))
     else:
         handle = open(os.path.join(output, "kmers.tsv"), "w")
-    handle.write("cluster\tstrain\tfeature_id\tcontig\tfeature_strand\tcontig_start\t"
-                 "contig_end\tgene_start\tgene_end\tstrand\tk-mer\n")
+    handle.write(KMERS_TSV_HEADER)
     handle.flush()
     return handle
+
+
+OUTPUT_NAMES = ("kmers.tsv", "hashes_to_patterns.tsv", "kmers_to_hashes.tsv")
+
+
+def create_part_files(output, rank, compress=False):
+    """Sharded run: this rank's header-less pieces of the three outputs
+    (kmers.tsv, hashes_to_patterns, kmers_to_hashes) under <output>/.parts/.  With --compress
+    every piece is a complete gzip stream, so the merged file is a run of gzip members."""
+    parts = os.path.join(output, ".parts")
+    os.makedirs(parts, exist_ok=True)
+    handles = []
+    for name in OUTPUT_NAMES:
+        path = os.path.join(parts, f"{name}{'.gz' if compress else ''}.{rank}")
+        handles.append(GzipTextWriter(path) if compress else open(path, "w"))
+    return tuple(handles)
+
+
+def merge_part_files(output, world, headers, compress=False):
+    """Rank 0, after every rank closed its pieces: header + the pieces in rank order -> the
+    three output files; the pieces are removed."""
+    import shutil
+    from . import capi
+    parts = os.path.join(output, ".parts")
+    for name, header in zip(OUTPUT_NAMES, headers):
+        final = os.path.join(output, name + (".gz" if compress else ""))
+        with open(final, "wb") as out:
+            out.write(capi.gzip_members(header.encode(), 9) if compress else header.encode())
+            for r in range(world):
+                with open(os.path.join(parts, f"{name}{'.gz' if compress else ''}.{r}"), "rb") as piece:
+                    shutil.copyfileobj(piece, out, 16 << 20)
+    shutil.rmtree(parts)
 
 
 def create_hash_files(output, compress=False):
@@ -212,8 +247,10 @@ def create_hash_files(output, compress=False):
 
 
 def set_input_output(stroi_in, genes_in, presence_absence, output,
-                     single_file=True, compress=False):
-    """-> (stroi, genes, kmer_stroi, hash_pat, kmer_hash, genepres).  input.py:183-232."""
+                     single_file=True, compress=False, make_outputs=True):
+    """-> (stroi, genes, kmer_stroi, hash_pat, kmer_hash, genepres).  input.py:183-232.
+    make_outputs=False (ranks of a sharded run: the output directory and the three files
+    belong to rank 0) only reads the inputs."""
     genepres = pd.read_csv(presence_absence, sep=",", index_col=0, low_memory=False).drop(
         columns=["Non-unique Gene name", "Annotation"])
     if stroi_in is not None:
@@ -224,11 +261,13 @@ def set_input_output(stroi_in, genes_in, presence_absence, output,
     genes = None
     if genes_in is not None:
         genes = {line.rstrip("\n") for line in open(genes_in)}
+    kmer_stroi = hash_pat = kmer_hash = None
+    if not make_outputs:
+        return stroi, genes, kmer_stroi, hash_pat, kmer_hash, genepres
     if os.path.exists(output):
         logger.error(f"Output directory {output} exists! Please remove it and restart")
         sys.exit(1)
     os.mkdir(output)
-    kmer_stroi = hash_pat = kmer_hash = None
     if single_file:
         kmer_stroi = create_kmer_stroi(output, compress)
         hash_pat, kmer_hash = create_hash_files(output, compress)

@@ -65,20 +65,48 @@ def write_headers(hash_pat, kmer_hash, genepres):
     kmer_hash.flush()
 
 
-class PatternStore:
-    """What `patterns` is in this build: the GPU context (pattern tables and
-    pools live in HBM) and the ids of every pattern written so far."""
+class _IdTable:
+    """Growable numpy S24 array: the id strings of one pattern namespace, appended batch by
+    batch (rebuilding an array from a Python list of every id issued so far would make a first
+    pass quadratic in the number of patterns)."""
 
     def __init__(self):
+        self.buf = np.zeros(1024, "S24")
+        self.n = 0
+
+    def append(self, ids):
+        m = len(ids)
+        if self.n + m > len(self.buf):
+            grown = np.zeros(max(2 * len(self.buf), self.n + m), "S24")
+            grown[:self.n] = self.buf[:self.n]
+            self.buf = grown
+        self.buf[self.n:self.n + m] = ids
+        self.n += m
+
+    def view(self):
+        return self.buf[:self.n]
+
+
+class PatternStore:
+    """What `patterns` is in this build: the GPU context (pattern tables and
+    pools live in HBM) and the ids of every pattern numbered so far.
+
+    sharded=True (several ranks, `torchrun -m panfeed_b200`): this rank sees only its shard of
+    the clusters, so whether a pattern is NEW is a global question: hashes_to_patterns rows are
+    not written batch by batch but once, by `finish_sharded`, after the pattern exchange."""
+
+    def __init__(self, sharded=False):
         self.ctx = None
         self.key = None
-        self.kmer_ids = []        # pool index -> id string (float64 namespace)
-        self.cluster_ids = []     # pool index -> id string (int64 namespace)
-        self.cluster_bits = []    # pool index -> presence words (for the NaN plane)
-        self.seen = set()         # the reference's `patterns` set of id strings
+        self.sharded = bool(sharded)
+        self.kmer_ids = _IdTable()       # pool index -> id (float64 namespace)
+        self.cluster_ids = _IdTable()    # pool index -> id (int64 namespace)
+        self.cluster_bits = []           # per batch: presence words of the new cluster patterns (NaN planes)
+        self._cluster_bits_cat = None
+        self.n_patterns = 0              # len() of the reference's `patterns` set
 
     def __len__(self):
-        return len(self.seen)
+        return self.n_patterns
 
     def context(self, k, S, canonical, consider_missing, cluster_equal_filter, maf,
                 device=0, sort_bits=0):
@@ -93,17 +121,56 @@ class PatternStore:
                              "its PatternStore was created with")
         return self.ctx
 
+    def cluster_planes(self):
+        """[n cluster patterns, W] presence words of every cluster pattern numbered so far."""
+        if self.cluster_bits and (self._cluster_bits_cat is None or len(self.cluster_bits) > 1):
+            self._cluster_bits_cat = np.concatenate(self.cluster_bits)
+            self.cluster_bits = [self._cluster_bits_cat]
+        return self._cluster_bits_cat
+
     def reset(self):
         """`patterns = set()` of --multiple-files (panfeed.py:165)."""
         if self.ctx is not None:
             self.ctx.reset_patterns()
-        self.kmer_ids, self.cluster_ids, self.cluster_bits = [], [], []
-        self.seen = set()
+        self.kmer_ids, self.cluster_ids = _IdTable(), _IdTable()
+        self.cluster_bits, self._cluster_bits_cat = [], None
+        self.n_patterns = 0
 
     def close(self):
         if self.ctx is not None:
             self.ctx.close()
             self.ctx = None
+
+    def finish_sharded(self, hash_pat, k, S, canonical, consider_missing, cluster_equal_filter, maf,
+                       device, chunk=1 << 16):
+        """After the last batch of a sharded run: the global pattern exchange
+        (dist.PatternExchange over NCCL), then the hashes_to_patterns rows of the patterns THIS
+        rank is the writer of (the owner of a pattern names the first rank that sent it), so
+        that the ranks together write every pattern once - the job of the reference's single
+        writer process and its `patterns` set (__main__.py:67-81, panfeed.py:210-212)."""
+        import torch
+        from . import dist as pfdist
+        ctx = self.context(k, S, canonical, consider_missing, cluster_equal_filter, maf, device)
+        dev = torch.device("cuda", device)
+        out = pfdist.PatternExchange(ctx, dev).run(want_writer=True)
+        W = (S + 31) // 32
+        written = 0
+        for ns, name, ids in ((True, "cluster", self.cluster_ids.view()), (False, "kmer", self.kmer_ids.view())):
+            wr = out[name]["writer"].cpu().numpy().astype(bool)
+            assert len(wr) == len(ids), "pattern ids out of step with the device pools"
+            for c0 in range(0, len(wr), chunk):
+                sel = wr[c0:c0 + chunk]
+                if not sel.any():
+                    continue
+                bits = ctx.export_patterns(ns, c0, len(sel))[sel]
+                present = None
+                if consider_missing and not ns:
+                    present = self.cluster_planes()[bits[:, W].astype(np.int64)]
+                hash_pat.write(capi.format_patterns(bits, S, ids[c0:c0 + chunk][sel], present).decode())
+                written += int(sel.sum())
+        self.n_patterns = out["cluster"]["n_global"] + out["kmer"]["n_global"]
+        return {"written_here": written, "cluster_patterns_global": out["cluster"]["n_global"],
+                "kmer_patterns_global": out["kmer"]["n_global"]}
 
 
 def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
@@ -113,52 +180,49 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
     ctx.submit(hb)
     r = ctx.collect()
 
-    # ---- new patterns -> ids (MD5 on the device, K5) + hashes_to_patterns rows ----
+    # ---- new patterns -> ids (MD5 on the device, K5) + hashes_to_patterns rows.  The pattern
+    #      tables are keyed on the full vector, so every new pattern is a new id: nothing is
+    #      looked up per pattern on the host. ----
     pat_text = []
     new_cp = r["new_cluster_patterns"]
     if len(new_cp):
-        new_ids = [x.decode() for x in ctx.pattern_ids(True, r["cluster_pattern_base"], len(new_cp))]
-        fresh = []
-        for pid in new_ids:
-            fresh.append(pid not in store.seen)
-            store.seen.add(pid)
-        store.cluster_ids += new_ids
-        store.cluster_bits += [w for w in new_cp]
-        sel = np.array(fresh, bool)
-        pat_text.append(capi.format_patterns(new_cp[sel], S, [p for p, f in zip(new_ids, fresh) if f]).decode())
+        new_ids = ctx.pattern_ids(True, r["cluster_pattern_base"], len(new_cp))
+        store.cluster_ids.append(new_ids)
+        store.cluster_bits.append(new_cp.copy())
+        if not store.sharded:
+            pat_text.append(capi.format_patterns(new_cp, S, new_ids).decode())
+            store.n_patterns += len(new_cp)
     new_kp = r["new_kmer_patterns"]
     if len(new_kp):
         W = (S + 31) // 32
-        present = None
-        if consider_missing:      # NaN cells = samples whose cluster is absent (the key's last word
-            present = np.stack([store.cluster_bits[c] for c in new_kp[:, W]])   # names that cluster pattern)
-        new_ids = [x.decode() for x in ctx.pattern_ids(False, r["kmer_pattern_base"], len(new_kp))]
-        fresh = []
-        for pid in new_ids:
-            fresh.append(pid not in store.seen)
-            store.seen.add(pid)
-        store.kmer_ids += new_ids
-        sel = np.array(fresh, bool)
-        pat_text.append(capi.format_patterns(new_kp[sel], S, [p for p, f in zip(new_ids, fresh) if f],
-                                             None if present is None else present[sel]).decode())
+        new_ids = ctx.pattern_ids(False, r["kmer_pattern_base"], len(new_kp))
+        store.kmer_ids.append(new_ids)
+        if not store.sharded:
+            present = None
+            if consider_missing:      # NaN cells = samples whose cluster is absent (the key's last word
+                present = store.cluster_planes()[new_kp[:, W].astype(np.int64)]   # names that cluster pattern)
+            pat_text.append(capi.format_patterns(new_kp, S, new_ids, present).decode())
+            store.n_patterns += len(new_kp)
 
     # ---- kmers_to_hashes rows, cluster by cluster: formatted by the library's host threads
     #      (pf_format_kmer_rows; inside a cluster the plain k-mers in alphabetical order, then the
     #      rows holding N/IUPAC symbols - the reference's order is arbitrary too) --------------
-    kmer_ids = np.array(store.kmer_ids, dtype="S24") if store.kmer_ids else np.zeros(0, "S24")
-    cluster_ids = np.array(store.cluster_ids, dtype="S24") if store.cluster_ids else np.zeros(0, "S24")
-    text, off = capi.format_kmer_rows(r, k, [str(idx).encode() for idx in idxs], kmer_ids, cluster_ids)
+    text, off = capi.format_kmer_rows(r, k, [str(idx).encode() for idx in idxs], store.kmer_ids.view(),
+                                      store.cluster_ids.view())
     hash_texts = [text[int(off[c]):int(off[c + 1])].decode() for c in range(len(idxs))]
 
     # ---- kmers.tsv rows from the positional records: formatted by the library's host
-    #      threads (pf_format_positions), 1e8 rows are too many for Python ----------------
+    #      threads (pf_format_positions), 1e8 rows are too many for Python.  Only the target
+    #      sequences need their leading fields (and with them their lazily built metadata). ----
     pos_text = ""
     if len(r["pos_seq"]):
-        leads = [f"{idxs[c]}\t{m[0]}\t{m[1]}\t{m[2]}\t{st}\t".encode()
-                 for c, st, m in zip(hb.seqs["cluster"].tolist(), hb.seqs["strand"].tolist(), meta)]
-        pos_text = capi.format_positions(r, k, canonical, leads, hb.seqs["strand"]).decode()
+        leads = [b""] * len(hb.seqs)
+        cl, strand = hb.seqs["cluster"], hb.seqs["strand"]
+        for i in np.unique(r["pos_seq"]).tolist():
+            m = meta[i]
+            leads[i] = f"{idxs[cl[i]]}\t{m[0]}\t{m[1]}\t{m[2]}\t{strand[i]}\t".encode()
+        pos_text = capi.format_positions(r, k, canonical, leads, strand).decode()
     return pos_text, "".join(pat_text), hash_texts
-
 
 def pattern_hasher(cluster_dict_iter, kmer_stroi, hash_pat, kmer_hash, genepres, patfilt, maf,
                    output, patterns=None, consider_missing_cluster=False, compress=False,
@@ -200,7 +264,8 @@ def pattern_hasher(cluster_dict_iter, kmer_stroi, hash_pat, kmer_hash, genepres,
         else:
             if kmer_stroi is not None:
                 kmer_stroi.write(pos_text)
-            hash_pat.write(pat_text)
+            if pat_text:
+                hash_pat.write(pat_text)
             kmer_hash.write("".join(hash_texts))
         pending, pending_records = [], 0
 

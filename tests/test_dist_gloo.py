@@ -48,19 +48,26 @@ class NumpyBackend:
         order = np.argsort(owner, kind="stable")
         perm = np.empty(len(keys), np.int64); perm[order] = np.arange(len(keys))
         self.perm[ns] = perm
+        self.owner = getattr(self, "owner", {}); self.owner[ns] = owner
         send.copy_(torch.from_numpy(keys[order].astype(np.int32).reshape(send.shape)))
         return [int((owner == r).sum()) for r in range(world)]
-    def dedup(self, ns, recv, unique_index):
+    def dedup(self, ns, recv, unique_index, n_unique):
         keys = recv.numpy().astype(np.uint32)
         seen, idx = {}, []
         for k in keys:
-            idx.append(seen.setdefault(k.tobytes(), len(seen)))
+            first = k.tobytes() not in seen
+            u = seen.setdefault(k.tobytes(), len(seen))
+            idx.append(u - (1 << 31) if first else u)        # bit 31 (int32): first copy = writer
         unique_index.copy_(torch.tensor(idx, dtype=torch.int32))
         self.uniq[ns] = np.array([np.frombuffer(b, np.uint32) for b in seen]).reshape(len(seen), keys.shape[1])
-        return len(seen)
-    def unique_keys(self, ns, n): return self.uniq[ns]
-    def unpack(self, ns, returned, l2g):
-        l2g.copy_(returned[torch.from_numpy(self.perm[ns])])
+        n_unique.fill_(len(seen))
+    def unique_keys(self, ns): return self.uniq[ns]
+    def unpack(self, ns, returned, owner_base, l2g, writer):
+        v = returned[torch.from_numpy(self.perm[ns])].numpy().astype(np.int64) & 0xffffffff
+        base = owner_base.numpy().astype(np.int64)[self.owner[ns]]
+        l2g.copy_(torch.from_numpy(((v & 0x7fffffff) + base).astype(np.int32)))
+        if writer is not None:
+            writer.copy_(torch.from_numpy((v >> 31).astype(np.uint8)))
 
 os.environ["PYTHONHASHSEED"] = "0"
 dist.init_process_group("gloo")
@@ -80,7 +87,7 @@ else:
 be = NumpyBackend({pfdist.CLUSTER: cl_local, pfdist.KMER: kp_local}, cm)
 be.consider_missing = cm
 ex = pfdist.PatternExchange(None, torch.device("cpu"), backend=be)
-out = ex.run(want_unique=True)
+out = ex.run(want_unique=True, want_writer=True)
 # gather everything on every rank and check global consistency
 def gather(obj):
     lst = [None] * world
@@ -91,19 +98,22 @@ km_g = out["kmer"]["local_to_global"].numpy()
 true_k = kp_local.copy()
 if cm:
     true_k[:, -1] = cl_g[kp_local[:, -1]]
-all_cl = gather((cl_local, cl_g, out["cluster"]["owned_keys"], out["cluster"]["owned_base"]))
-all_km = gather((true_k, km_g, out["kmer"]["owned_keys"], out["kmer"]["owned_base"]))
+all_cl = gather((cl_local, cl_g, out["cluster"]["owned_keys"], out["cluster"]["owned_base"], out["cluster"]["writer"].numpy()))
+all_km = gather((true_k, km_g, out["kmer"]["owned_keys"], out["kmer"]["owned_base"], out["kmer"]["writer"].numpy()))
 for name, allx, total in (("cluster", all_cl, out["cluster"]["n_global"]), ("kmer", all_km, out["kmer"]["n_global"])):
     key_to_id = {}
-    for keys, ids, _, _ in allx:
+    for keys, ids, _, _, _ in allx:
         for k, i in zip(keys, ids):
             assert key_to_id.setdefault(k.tobytes(), int(i)) == int(i), name + ": same key, two ids"
     assert len(set(key_to_id.values())) == len(key_to_id), name + ": two keys share an id"
     assert sorted(key_to_id.values()) == list(range(total)), name + ": ids not dense"
     # the owner's exported unique keys sit at owned_base + index
-    for _, _, owned, base in allx:
+    for _, _, owned, base, _ in allx:
         for j, k in enumerate(owned):
             assert key_to_id[k.tobytes()] == base + j
+    # every global pattern has exactly one writer over all ranks
+    written = [int(i) for _, ids, _, _, wr in allx for i, w in zip(ids, wr) if w]
+    assert sorted(written) == list(range(total)), name + ": writer flags"
 print(f"rank {rank} ok cm={cm} clusters={out['cluster']['n_global']} kmers={out['kmer']['n_global']}")
 dist.destroy_process_group()
 '''

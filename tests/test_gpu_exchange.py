@@ -52,20 +52,31 @@ def test_exchange_two_contexts_one_gpu(cm):
         uniq, n_unique = [], []
         for o, be in enumerate(bes):
             u = torch.empty(recvs[o].shape[0], dtype=torch.int32, device=dev)
-            n_unique.append(be.dedup(ns, recvs[o], u))
+            nu = torch.zeros(1, dtype=torch.int32, device=dev)
+            be.dedup(ns, recvs[o], u, nu)          # asynchronous on the context's stream
+            torch.cuda.synchronize()
+            n_unique.append(int(nu.cpu().item()))
             uniq.append(u)
-        bases = [0, n_unique[0]]
+        owner_base = torch.tensor([0, n_unique[0]], dtype=torch.int32, device=dev)
+        writers = []
         for r, be in enumerate(bes):
             back = []
             for o in range(world):
                 off = sum(counts[q][o] for q in range(r))
-                back.append(uniq[o][off:off + counts[r][o]] + bases[o])
+                back.append(uniq[o][off:off + counts[r][o]])
             returned = torch.cat(back).contiguous()
             out = torch.empty(be.n_local(ns), dtype=torch.int32, device=dev)
-            be.unpack(ns, returned, out)
+            wr = torch.empty(be.n_local(ns), dtype=torch.uint8, device=dev)
+            torch.cuda.synchronize()
+            be.unpack(ns, returned, owner_base, out, wr)
+            torch.cuda.synchronize()
             l2g[(ns, r)] = out
+            writers.append(wr.cpu().numpy())
         l2g[(ns, "total")] = sum(n_unique)
-        l2g[(ns, "owned")] = [be.unique_keys(ns, n) for be, n in zip(bes, n_unique)]
+        l2g[(ns, "owned")] = [be.unique_keys(ns) for be in bes]
+        # exactly one writer per global pattern
+        written = np.concatenate([l2g[(ns, r)].cpu().numpy()[writers[r] != 0] for r in range(world)])
+        assert sorted(written.tolist()) == list(range(sum(n_unique)))
 
     # reference: one context over all clusters
     one = capi.Context(k, S, True, cm, False, False, 0.02)

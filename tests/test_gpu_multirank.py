@@ -1,0 +1,106 @@
+"""The multi-GPU product path on real hardware, two ranks over NCCL
+(`torchrun --nproc-per-node 2`; skipped on a box with one GPU):
+
+  * `torchrun -m panfeed_b200 ...` shards the clusters, runs the pattern exchange and writes ONE
+    set of three files: they must equal the unmodified reference's goldens after sorting, like
+    the single-process CLI (the reference's own parallel mode, `__main__.py:299-344`, is held to
+    the same sorted comparison: its row order is nondeterministic);
+  * `selfcheck.check_exchange`: local keys == the owners' keys under the returned global ids, no
+    duplicate in the global tables, and the same pattern sets as ONE context over all clusters,
+    with and without the cluster-absent encoding.
+"""
+import gzip
+import os
+import subprocess
+import sys
+
+import pytest
+
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+needs_two = pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+
+
+def _torchrun(args, port, cwd, timeout=900):
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port)] + args,
+                       capture_output=True, text=True, timeout=timeout, env=env, cwd=cwd)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    return r
+
+
+def _read(path):
+    if os.path.exists(path + ".gz"):
+        return gzip.open(path + ".gz", "rt").read()
+    return open(path).read()
+
+
+CASES = [("basic", []), ("considermissing", []), ("cm_nofilter_up", []), ("noncanonical", []),
+         ("compress", []), ("secondpass", ["--native-feeder"])]
+
+
+@needs_two
+@pytest.mark.parametrize("mode,extra", CASES)
+def test_cli_two_ranks_match_reference(mode, extra, tmp_path):
+    out = str(tmp_path / "out")
+    args = ["-m", "panfeed_b200"] + list(helpers.modes()[mode]) + extra + ["--output", out]
+    _torchrun(args, 29610 + [c[0] for c in CASES].index(mode), helpers.GOLDEN)
+    assert not os.path.exists(os.path.join(out, ".parts"))
+    for name in helpers.FILES:
+        got = _read(os.path.join(out, name))
+        want = helpers.golden(mode, name)
+        assert got.split("\n")[0] == [x for x in want.split("\n") if x.startswith(
+            ("cluster\t", "hashed_pattern"))][0]
+        assert helpers.sorted_lines(got) == helpers.sorted_lines(want), (mode, name)
+    if mode == "compress":
+        assert os.path.exists(os.path.join(out, "hashes_to_patterns.tsv.gz"))
+
+
+WORKER = r'''
+import os, sys, json
+import torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from panfeed_b200 import selfcheck
+local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+res = [selfcheck.check_exchange(local, cm, n_samples=int(sys.argv[2]), clusters_per_rank=int(sys.argv[3]),
+                                gene_len=int(sys.argv[4])) for cm in (False, True)]
+if dist.get_rank() == 0:
+    print("SELFCHECK " + json.dumps(res))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+@needs_two
+@pytest.mark.parametrize("samples,clusters,gene_len", [(256, 6, 400), (1500, 3, 300)])
+def test_exchange_two_ranks_nccl(samples, clusters, gene_len, tmp_path):
+    """(1500 samples: sample slices of the block engine, 47-word keys through NCCL.)"""
+    path = tmp_path / "worker.py"
+    path.write_text(WORKER)
+    r = _torchrun([str(path), ROOT, str(samples), str(clusters), str(gene_len)], 29650 + samples % 7, ROOT)
+    assert "SELFCHECK" in r.stdout, r.stdout[-2000:]
+
+
+def test_exchange_selfcheck_single_rank():
+    """World size 1 goes through the same pack / dedup / unpack kernels (plain copies for the
+    collectives): runs on any GPU box."""
+    from panfeed_b200 import selfcheck
+    for cm in (False, True):
+        res = selfcheck.check_exchange(0, cm, n_samples=300, clusters_per_rank=5, gene_len=350)
+        assert res["ok"] and res["kmer_patterns_global"] == res["kmer_patterns_local"] > 0
