@@ -557,7 +557,7 @@ def rank_clusters(cfg, env):
 def make_context(cfg, env, args):
     from panfeed_b200 import capi
     return capi.Context(cfg["k"], cfg["samples"], canonical=True, consider_missing=cfg["cm"],
-                        cluster_equal_filter=False, emit_positions=cfg["targets"], maf=cfg["maf"],
+                        cluster_equal_filter=False, emit_positions=2 if cfg["targets"] else 0, maf=cfg["maf"],
                         sort_bits=args.sort_bits, device=env.local)
 
 

@@ -53,7 +53,14 @@ typedef struct pf_params {
   uint32_t cluster_equal_filter; /* 1 iff --no-filter GIVEN: the reference runs the
                                     "same as cluster" filter only when patfilt is
                                     False (panfeed.py:202-204, __main__.py:292)     */
-  uint32_t emit_positions;       /* 1 if any --targets strain exists (panfeed.py:90)*/
+  uint32_t emit_positions;       /* 0: none.  Non-zero if any --targets strain exists (panfeed.py:90):
+                                    1 = one 21-byte record per k-mer instance of a target sequence
+                                        (pos_* arrays of the result);
+                                    2 = compact: only what the input does not already determine
+                                        leaves the device - the used_strand bit of every window
+                                        (pos_strand_bits); pf_format_positions_compact derives the
+                                        k-mer text and the coordinates from the caller's own packed
+                                        plane and descriptors (panfeed.py:91-102 are affine in pos) */
   uint32_t sort_bits;            /* 0 = auto; else number of leading bits of the
                                     mixed key the radix sort orders (multiple of 8,
                                     8..64); the rest is resolved exactly in K3     */
@@ -155,6 +162,13 @@ typedef struct pf_batch_result {
                                       pos_kmer holds an index into pos_wide_kmer              */
   const uint64_t* pos_wide_kmer;   /* 2 words per ambiguous positional k-mer                  */
   uint64_t        n_pos_wide;
+  /* emit_positions == 2: n_pos still counts the instances, the pos_* arrays above are NULL and
+   * bit (i & 31) of pos_strand_bits[i >> 5], i = pf_seq_desc.base_off + pos, is 1 iff the reverse
+   * complement was the canonical k-mer of the window starting at `pos` of that sequence
+   * (used_strand = -1, panfeed.py:69-75).  Words of sequences without PF_SEQ_TARGET are
+   * undefined; with canonical == 0 nothing is needed and the plane is empty. */
+  const uint32_t* pos_strand_bits;
+  uint64_t        n_pos_bit_words; /* 2 * pf_batch.n_words, or 0                              */
 } pf_batch_result;
 
 typedef struct pf_stats {
@@ -245,6 +259,18 @@ int pf_format_positions(const pf_batch_result* result, uint32_t k, int canonical
                         uint64_t count, const char* lead_blob, const uint64_t* lead_off,
                         const int32_t* seq_strand, char* out, uint64_t out_cap, uint64_t* out_len,
                         uint32_t n_threads);
+
+/* The same rows from the compact form (emit_positions == 2): for sequences [seq_first, seq_first +
+ * seq_count) of `batch` that carry PF_SEQ_TARGET, in array order, every window in ascending
+ * position.  The k-mer text comes from the batch's own planes (the 4-bit plane for sequences
+ * flagged PF_SEQ_AMBIGUOUS), the coordinates from the descriptors:
+ *   contig_start = strand > 0 ? start + pos : end - pos - k,  gene_start = pos - offset,
+ * used_strand from strand_bits (canonical) or +-pf_seq_desc.strand (two rows, canonical == 0;
+ * strand_bits may then be NULL).  lead_blob / lead_off index the sequences of the batch. */
+int pf_format_positions_compact(const pf_batch* batch, const uint32_t* strand_bits, uint32_t k,
+                                int canonical, uint32_t seq_first, uint32_t seq_count,
+                                const char* lead_blob, const uint64_t* lead_off, char* out,
+                                uint64_t out_cap, uint64_t* out_len, uint32_t n_threads);
 
 /* The hashes_to_patterns rows of n patterns (panfeed.py:183-187,217-223): ids (n x 24 chars,
  * e.g. from pf_pattern_ids + base64), then per sample a tab and '0' / '1' — or nothing where

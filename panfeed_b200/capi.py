@@ -77,7 +77,9 @@ class BatchResult(C.Structure):
                 ("pos_gene_start", C.POINTER(C.c_int32)),
                 ("pos_flags", C.POINTER(C.c_uint8)),
                 ("pos_wide_kmer", C.POINTER(C.c_uint64)),
-                ("n_pos_wide", C.c_uint64)]
+                ("n_pos_wide", C.c_uint64),
+                ("pos_strand_bits", C.POINTER(C.c_uint32)),
+                ("n_pos_bit_words", C.c_uint64)]
 
 
 class Stats(C.Structure):
@@ -127,6 +129,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_upload", "pf_execute", "pf_submit", "pf_collect",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
            "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream", "pf_format_positions",
+           "pf_format_positions_compact",
            "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns", "pf_format_kmer_rows", "pf_gzip_members",
            "pf_feeder_create", "pf_feeder_destroy", "pf_feeder_last_error", "pf_feeder_add_genome", "pf_feeder_add_genomes",
            "pf_feeder_add_genome_text", "pf_feeder_genome_info", "pf_feeder_feature", "pf_feeder_cut",
@@ -192,6 +195,8 @@ def load():
     lib.pf_format_positions.argtypes = [C.POINTER(BatchResult), u32, C.c_int, u64, u64, C.c_char_p,
                                         C.POINTER(u64), C.POINTER(C.c_int32), C.c_char_p, u64,
                                         C.POINTER(u64), u32]
+    lib.pf_format_positions_compact.argtypes = [C.POINTER(Batch), vp, u32, C.c_int, u32, u32, C.c_char_p,
+                                                C.POINTER(u64), C.c_char_p, u64, C.POINTER(u64), u32]
     lib.pf_pattern_ids.argtypes = [vp, C.c_int, u64, u64, vp]
     lib.pf_stats_get.argtypes = [vp, C.POINTER(Stats)]
     lib.pf_stream.argtypes = [vp]
@@ -424,6 +429,37 @@ def format_positions(r, k, canonical, leads, seq_strand, n_threads=0):
     return out.tobytes()
 
 
+def format_positions_compact(hb, strand_bits, k, canonical, leads, n_threads=0):
+    """kmers.tsv text (bytes) of the PF_SEQ_TARGET sequences of the HostBatch `hb` from the compact
+    positional form (Context(emit_positions=2)): `strand_bits` = r["pos_strand_bits"] of the
+    batch's collect().  leads[i] as in format_positions (may be b"" for non-target sequences)."""
+    lib = load()
+    n = len(hb.seqs)
+    if n == 0:
+        return b""
+    b = hb.struct()
+    blob = b"".join(leads)
+    off = np.zeros(n + 1, np.uint64)
+    np.cumsum(np.fromiter((len(x) for x in leads), np.uint64, n), out=off[1:])
+    bits = None
+    if canonical:
+        bits = np.ascontiguousarray(strand_bits, dtype=np.uint32)
+        if bits.size < 2 * hb.packed.size:
+            raise ValueError("strand bit plane is shorter than the packed plane")
+    need = C.c_uint64()
+    args = (C.byref(b), bits.ctypes.data if bits is not None else None, int(k), int(bool(canonical)), 0, n, blob,
+            off.ctypes.data_as(C.POINTER(C.c_uint64)))
+    rc = lib.pf_format_positions_compact(*args, None, 0, C.byref(need), int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_format_positions_compact (sizing) failed")
+    out = np.empty(int(need.value), np.uint8)
+    rc = lib.pf_format_positions_compact(*args, out.ctypes.data_as(C.c_char_p), out.size, C.byref(need),
+                                         int(n_threads))
+    if rc != 0:
+        raise PfError(rc, "pf_format_positions_compact failed")
+    return out.tobytes()
+
+
 def _np(ptr, n, dtype, copy=True):
     if n == 0:
         return np.zeros(0, dtype)
@@ -481,6 +517,7 @@ class Context:
                  cluster_equal_filter=False, emit_positions=False, maf=0.01,
                  sort_bits=0, device=0, mode=0, debug_flags=0):
         self.lib = load()
+        # emit_positions: False / True (21-byte records) / 2 (compact: the used_strand bit plane)
         self.params = Params(PF_ABI_VERSION, k, n_samples, int(canonical),
                              int(consider_missing), int(cluster_equal_filter),
                              int(emit_positions), sort_bits, mode, debug_flags, maf)
@@ -526,6 +563,7 @@ class Context:
         r = BatchResult()
         self._check(self.lib.pf_collect(self.h, C.byref(r)))
         nr, nw = int(r.n_rows), int(r.n_wide_rows)
+        n_rec = int(r.n_pos) if r.pos_seq else 0        # compact positional form: no record arrays
         _np = lambda p, n, d: globals()["_np"](p, n, d, copy)  # noqa: E731
         out = {
             "row_cluster": _np(r.row_cluster, nr, np.uint32),
@@ -545,13 +583,15 @@ class Context:
             "new_cluster_patterns": _np(r.new_cluster_patterns,
                                         r.n_new_cluster_patterns * self.W,
                                         np.uint32).reshape(-1, self.W),
-            "pos_kmer": _np(r.pos_kmer, r.n_pos, np.uint64),
-            "pos_seq": _np(r.pos_seq, r.n_pos, np.uint32),
-            "pos_contig_start": _np(r.pos_contig_start, r.n_pos, np.int32),
-            "pos_gene_start": _np(r.pos_gene_start, r.n_pos, np.int32),
-            "pos_flags": _np(r.pos_flags, r.n_pos, np.uint8),
+            "pos_kmer": _np(r.pos_kmer, n_rec, np.uint64),
+            "pos_seq": _np(r.pos_seq, n_rec, np.uint32),
+            "pos_contig_start": _np(r.pos_contig_start, n_rec, np.int32),
+            "pos_gene_start": _np(r.pos_gene_start, n_rec, np.int32),
+            "pos_flags": _np(r.pos_flags, n_rec, np.uint8),
             "pos_wide_kmer": _np(r.pos_wide_kmer, 2 * r.n_pos_wide,
                                  np.uint64).reshape(-1, 2),
+            "n_pos": int(r.n_pos),
+            "pos_strand_bits": _np(r.pos_strand_bits, r.n_pos_bit_words, np.uint32),
         }
         out["d2h_bytes"] = int(sum(v.nbytes for v in out.values()
                                    if isinstance(v, np.ndarray)))

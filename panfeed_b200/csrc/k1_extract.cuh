@@ -52,7 +52,7 @@ k1_extract(const uint64_t* __restrict__ bases, const uint32_t* __restrict__ ambb
     if (d.len < (uint32_t)k) continue;
     const uint32_t nwin = d.len - (uint32_t)k + 1u;
     const uint64_t* w = bases + (d.base_off >> 5);
-    const bool target = (d.flags & 1u) != 0u;
+    const bool target = (d.flags & 1u) != 0u && pos.kmer != nullptr;
     if (!RECORDS && !target) continue;
     const bool amb = (d.flags & 2u) != 0u;
     const uint32_t* ab = amb ? (ambbits + (d.amb_off >> 5)) : nullptr;
@@ -128,6 +128,36 @@ k1_extract(const uint64_t* __restrict__ bases, const uint32_t* __restrict__ ambb
   }
 }
 
+// Compact positional form (pf_params.emit_positions == 2, canonical mode): the only fact about a
+// window of a --targets sequence that its descriptor and position do not already give is which
+// strand was the canonical one (used_strand, panfeed.py:69-75).  One warp per target sequence,
+// lane l owns window 32 * it + l: the 32 verdicts of an iteration are one ballot = one word of
+// the bit plane, which is indexed like the packed plane (bit (i & 31) of word (i >> 5),
+// i = base_off + pos; sequences start on 64-base boundaries, so words are never shared).
+__global__ void __launch_bounds__(kK1Warps * 32)
+k1_strand_bits(const uint64_t* __restrict__ bases, const SeqDev* __restrict__ seqs, uint32_t n_seqs, int k,
+               uint32_t* __restrict__ strand_bits) {
+  const uint32_t lane = lane_id();
+  const uint32_t stride = gridDim.x * kK1Warps;
+  const int kshift = 64 - 2 * k;
+  for (uint32_t s = blockIdx.x * kK1Warps + (threadIdx.x >> 5); s < n_seqs; s += stride) {
+    const SeqDev d = seqs[s];
+    if (!(d.flags & 1u) || d.len < (uint32_t)k) continue;
+    const uint32_t nwin = d.len - (uint32_t)k + 1u;
+    const uint64_t* w = bases + (d.base_off >> 5);
+    uint32_t* out = strand_bits + (d.base_off >> 5);
+    for (uint32_t it = 0; it * 32u < nwin; ++it) {
+      const uint64_t w0 = __ldg(w + it), w1 = __ldg(w + it + 1);       // the same two words for the whole warp
+      const uint32_t sh = 2u * lane;
+      const uint64_t x = (w0 << sh) | ((w1 >> 1) >> (63u - sh));
+      const uint64_t fwd = x >> kshift;
+      const bool use_rc = (it * 32u + lane < nwin) && revcomp2(fwd, k) < fwd;
+      const uint32_t word = __ballot_sync(kFull, use_rc);
+      if (lane == 0) out[it] = word;
+    }
+  }
+}
+
 // ---- 4-bit plane: ambiguity bits and the wide (128-bit) extraction --------
 // One ambiguity bit per symbol, 32 per word, first symbol in the top bit.
 __global__ void k1_amb_bits(const uint64_t* __restrict__ amb_codes, uint64_t n_amb_words,
@@ -162,7 +192,8 @@ __global__ void k1_extract_wide(const uint64_t* __restrict__ amb_codes,
                                 const SeqDev* __restrict__ seqs,
                                 const uint32_t* __restrict__ wide_seqs, uint32_t n_wide_seqs,
                                 int k, Key128* __restrict__ keys, uint32_t* __restrict__ vals,
-                                uint64_t* __restrict__ pos_wide, uint8_t* __restrict__ pos_flags) {
+                                uint64_t* __restrict__ pos_wide, uint8_t* __restrict__ pos_flags,
+                                uint32_t* __restrict__ strand_bits /* compact positional form, else null */) {
   const uint32_t lane = lane_id();
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t stride = gridDim.x * (blockDim.x >> 5);
@@ -194,7 +225,13 @@ __global__ void k1_extract_wide(const uint64_t* __restrict__ amb_codes,
         const size_t rec = (size_t)d.wrec_off + p;
         keys[rec] = is_amb ? mix128(canon) : Key128{0, 0};
         vals[rec] = is_amb ? d.sample : kInvalidSample;
-        if (target && is_amb) {
+        if (target && is_amb && strand_bits) {
+          // runs after k1_strand_bits on the same stream: the strand choice of an ambiguous
+          // window must come from the 4-bit comparison
+          const uint64_t i = d.base_off + p;
+          if (use_rc) atomicOr(&strand_bits[i >> 5], 1u << (i & 31u));
+          else atomicAnd(&strand_bits[i >> 5], ~(1u << (i & 31u)));
+        } else if (target && is_amb) {
           pos_wide[2 * ((size_t)d.pwide_off + p)] = canon.hi;
           pos_wide[2 * ((size_t)d.pwide_off + p) + 1] = canon.lo;
           // runs after the narrow kernel on the same stream: the strand choice of an
@@ -206,7 +243,7 @@ __global__ void k1_extract_wide(const uint64_t* __restrict__ amb_codes,
         keys[rec] = is_amb ? mix128(f) : Key128{0, 0};
         keys[rec + 1] = is_amb ? mix128(r) : Key128{0, 0};
         vals[rec] = vals[rec + 1] = is_amb ? d.sample : kInvalidSample;
-        if (target && is_amb) {
+        if (target && is_amb && pos_wide) {
           pos_wide[2 * ((size_t)d.pwide_off + p)] = f.hi;
           pos_wide[2 * ((size_t)d.pwide_off + p) + 1] = f.lo;
         }

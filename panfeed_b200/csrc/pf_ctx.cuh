@@ -123,6 +123,7 @@ struct BatchState {
   DevBuf d_row_cluster, d_row_kmer, d_wrow_kmer, d_row_count, d_row_pattern;
   DevBuf d_cl_pattern;
   DevBuf d_pos_kmer, d_pos_seq, d_pos_cstart, d_pos_gstart, d_pos_flags, d_pos_wide;
+  DevBuf d_pos_bits;             // compact positional form: used_strand bit plane, indexed like d_bases
   DevBuf d_seq_rec_off, d_tile_first_seq;
   PinBuf h_seq_rec_off, h_tile_first_seq;
   std::vector<std::pair<uint32_t, uint32_t>> nar_ranges;   // narrow record range of every cluster
@@ -270,7 +271,9 @@ struct pf_ctx : BatchState {
   bool fused = false;            // K1 fused into the histogram and the first pass (no record write in K1)
   DevBuf d_digests;
   int extra_bits = 0;      // sort bits added after a table overflow (sticky)
-  double row_ratio = 1.0 / 48;   // surviving rows per record, learned from earlier batches
+  double row_ratio = 1.0 / 48;   // surviving rows per record, learned from earlier batches (pf_create scales
+                                 // the first guess with 1 / n_samples: rows per cluster do not grow with S, records do)
+  bool row_ratio_learned = false;
   uint64_t unique_last = 0;
   uint32_t rescued_last = 0;
   // block aggregation (k3_block.cuh): no records, partial (k-mer, bitset) rows per position block
@@ -294,7 +297,7 @@ struct pf_ctx : BatchState {
   // pinned results
   PinBuf r_row_cluster, r_row_kmer, r_wrow_kmer, r_row_count, r_row_pattern, r_cl_pattern;
   PinBuf r_new_kp, r_new_cp, r_pos_kmer, r_pos_seq, r_pos_cstart, r_pos_gstart, r_pos_flags,
-      r_pos_wide;
+      r_pos_wide, r_pos_bits;
   PinBuf r_wrow_cluster, r_wrow_count, r_wrow_pattern;   // pipelined submit: wide rows apart
   cudaEvent_t ev_d2h[2]{};
   pf_stats stats{};
@@ -311,7 +314,7 @@ struct pf_ctx : BatchState {
   uint32_t pipe_subs = 1;        // sub-batches of the last submit
   bool pipe_mode = false;        // inside submit_pipelined: pf_execute leaves the D2H to it
   double pipe_ms[10] = {0};      // stage times summed over the sub-batches
-  uint64_t pipe_rows = 0, pipe_wide_rows = 0, pipe_pos = 0, pipe_pos_wide = 0;
+  uint64_t pipe_rows = 0, pipe_wide_rows = 0, pipe_pos = 0, pipe_pos_wide = 0, pipe_bit_words = 0;
   uint32_t pipe_clusters = 0;
   uint64_t pipe_kp_base = 0, pipe_cp_base = 0, pipe_kp_copied = 0;
   uint64_t pipe_row_cap = 0, pipe_wide_cap = 0;

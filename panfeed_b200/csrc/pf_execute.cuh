@@ -263,7 +263,16 @@ int launch_k1(pf_ctx* ctx) {
   WidthState& Wd = ctx->wid;
   PosOut po{ctx->d_pos_kmer.as<uint64_t>(), ctx->d_pos_seq.as<uint32_t>(), ctx->d_pos_cstart.as<int32_t>(),
             ctx->d_pos_gstart.as<int32_t>(), ctx->d_pos_flags.as<uint8_t>()};
-  if (ctx->n_seqs && N.n_records && !(ctx->fused && ctx->n_pos == 0)) {
+  const bool compact = ctx->prm.emit_positions == 2u;
+  if (compact && ctx->n_pos && P.canonical && ctx->n_seqs) {
+    // compact positional form: one bit per window of the target sequences, nothing else
+    const uint32_t grid = std::min<uint32_t>(cdiv(ctx->n_seqs, kK1Warps), 148 * 8);
+    k1_strand_bits<<<grid, kK1Warps * 32, 0, st>>>(ctx->d_bases.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(), ctx->n_seqs,
+                                                   (int)P.k, ctx->d_pos_bits.as<uint32_t>());
+    ctx->launches++;
+  }
+  if (compact) po = PosOut{nullptr, nullptr, nullptr, nullptr, nullptr};   // k1_extract: no positional records
+  if (ctx->n_seqs && N.n_records && !(ctx->fused && (ctx->n_pos == 0 || compact))) {
     const uint32_t grid = std::min<uint32_t>(cdiv(ctx->n_seqs, kK1Warps), 148 * 8);
 #define PF_K1(CANON, REC)                                                                              \
     k1_extract<CANON, REC><<<grid, kK1Warps * 32, 0, st>>>(ctx->d_bases.as<uint64_t>(), ctx->d_ambbits.as<uint32_t>(), \
@@ -280,12 +289,14 @@ int launch_k1(pf_ctx* ctx) {
       k1_extract_wide<true><<<grid, 256, 0, st>>>(ctx->d_amb.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(),
                                                  ctx->d_wide_seqs.as<uint32_t>(), ctx->n_wide_seqs, (int)P.k,
                                                  Wd.keys[0].as<Key128>(), Wd.vals[0].as<uint32_t>(),
-                                                 ctx->d_pos_wide.as<uint64_t>(), ctx->d_pos_flags.as<uint8_t>());
+                                                 ctx->d_pos_wide.as<uint64_t>(), ctx->d_pos_flags.as<uint8_t>(),
+                                                 compact && ctx->n_pos ? ctx->d_pos_bits.as<uint32_t>() : nullptr);
     else
       k1_extract_wide<false><<<grid, 256, 0, st>>>(ctx->d_amb.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(),
                                                   ctx->d_wide_seqs.as<uint32_t>(), ctx->n_wide_seqs, (int)P.k,
                                                   Wd.keys[0].as<Key128>(), Wd.vals[0].as<uint32_t>(),
-                                                  ctx->d_pos_wide.as<uint64_t>(), ctx->d_pos_flags.as<uint8_t>());
+                                                  compact ? nullptr : ctx->d_pos_wide.as<uint64_t>(),
+                                                  ctx->d_pos_flags.as<uint8_t>(), nullptr);
     ctx->launches++;
   }
   CU(cudaGetLastError());
@@ -551,18 +562,29 @@ extern "C" int pf_execute(pf_ctx* ctx) {
     TRY(dev_ensure(ctx, Wd.keys[i], ((size_t)Wd.n_records + 2) * 16));
     TRY(dev_ensure(ctx, Wd.vals[i], ((size_t)Wd.n_records + 2) * 4));
   }
-  if (ctx->n_pos) {
+  const bool compact_pos = ctx->prm.emit_positions == 2u;
+  if (ctx->n_pos && compact_pos) {
+    if (ctx->prm.canonical) TRY(dev_ensure(ctx, ctx->d_pos_bits, (size_t)ctx->n_words * 8 + 16));
+  } else if (ctx->n_pos) {
     TRY(dev_ensure(ctx, ctx->d_pos_kmer, (size_t)ctx->n_pos * 8));
     TRY(dev_ensure(ctx, ctx->d_pos_seq, (size_t)ctx->n_pos * 4));
     TRY(dev_ensure(ctx, ctx->d_pos_cstart, (size_t)ctx->n_pos * 4));
     TRY(dev_ensure(ctx, ctx->d_pos_gstart, (size_t)ctx->n_pos * 4));
     TRY(dev_ensure(ctx, ctx->d_pos_flags, (size_t)ctx->n_pos));
   }
-  if (ctx->n_pos_wide) TRY(dev_ensure(ctx, ctx->d_pos_wide, (size_t)ctx->n_pos_wide * 16));
+  if (ctx->n_pos_wide && !compact_pos) TRY(dev_ensure(ctx, ctx->d_pos_wide, (size_t)ctx->n_pos_wide * 16));
   TRY(dev_ensure(ctx, ctx->d_cl_pattern, std::max<size_t>(1, ctx->n_clusters) * 4));
   if (part) {
-    ctx->row_cap = std::max<uint64_t>(ctx->row_cap, std::max<uint64_t>(
-        65536, (uint64_t)(ctx->row_ratio * 1.3 * (double)N.n_records) + 4096));
+    uint64_t want_rows = std::max<uint64_t>(65536, (uint64_t)(ctx->row_ratio * 1.3 * (double)N.n_records) + 4096);
+    if (!ctx->row_ratio_learned) {
+      // the first batch's estimate is a guess: it must not take more than a quarter of the free
+      // memory for the candidate bitsets (50,000 samples: 6 kB per row); a guess that turns out too
+      // small is corrected by the row-overflow retry below
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+        want_rows = std::min<uint64_t>(want_rows, std::max<uint64_t>(65536, free_b / 4 / ((size_t)ctx->Wk * 4 + 24)));
+    }
+    ctx->row_cap = std::max<uint64_t>(ctx->row_cap, want_rows);
     TRY(ensure_rows(ctx, ctx->row_cap, ctx->row_cap, false));
   }
 
@@ -795,7 +817,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
     ctx->unique_last = N.n_records ? hcnt[C_LOCAL + LC_UNIQUE] : 0;
     if (ctx->used_block && ctx->n_slices == 1)   // distinct k-mers = partial rows - rows folded into an earlier one
       ctx->unique_last = (uint64_t)hcnt[C_LOCAL + LC_PARTIALS] - hcnt[C_LOCAL + LC_RESCUE];
-    if (N.n_records) ctx->row_ratio = std::max(1e-4, (double)N.n_rows / (double)N.n_records);
+    if (N.n_records) { ctx->row_ratio = std::max(1e-4, (double)N.n_rows / (double)N.n_records); ctx->row_ratio_learned = true; }
   } else {
     TRY((runs_width<uint64_t, false>(ctx, N, ro)));
   }

@@ -167,6 +167,137 @@ extern "C" int pf_format_positions(const pf_batch_result* r, uint32_t k, int can
 }
 
 // ---------------------------------------------------------------------------
+// Compact positional form (pf_params.emit_positions == 2): the device returns one bit per
+// window (was the reverse complement the canonical k-mer?); everything else of a kmers.tsv
+// row is a function of the caller's own batch.
+// ---------------------------------------------------------------------------
+namespace {
+struct CJob {
+  const pf_batch* b;
+  const uint32_t* bits;
+  uint32_t k;
+  int canonical;
+  const char* lead_blob;
+  const uint64_t* lead_off;
+};
+inline bool strand_bit(const CJob& j, const pf_seq_desc& q, uint32_t p) {
+  const uint64_t i = q.base_off + p;
+  return (j.bits[i >> 5] >> (i & 31u)) & 1u;
+}
+inline uint64_t seq_rows_len(const CJob& j, uint32_t si) {
+  const pf_seq_desc& q = j.b->seqs[si];
+  if (!(q.flags & PF_SEQ_TARGET) || q.len < j.k) return 0;
+  const uint32_t nwin = q.len - j.k + 1;
+  const uint64_t lead = j.lead_off[si + 1] - j.lead_off[si];
+  uint64_t total = 0;
+  for (uint32_t p = 0; p < nwin; ++p) {
+    const int64_t c0 = q.strand > 0 ? (int64_t)q.start + p : (int64_t)q.end - p - j.k, g0 = (int64_t)p - q.offset;
+    const uint64_t coords = (uint64_t)len_int(c0) + len_int(c0 + j.k) + len_int(g0) + len_int(g0 + j.k) + 4;
+    if (j.canonical) total += lead + coords + (strand_bit(j, q, p) ? 2 : 1) + 1 + j.k + 1;
+    else total += 2 * (lead + coords + 1 + j.k + 1) + len_int(q.strand) + len_int(-(int64_t)q.strand);
+  }
+  return total;
+}
+inline char* write_seq_rows(const CJob& j, uint32_t si, char* p) {
+  const pf_seq_desc& q = j.b->seqs[si];
+  if (!(q.flags & PF_SEQ_TARGET) || q.len < j.k) return p;
+  const uint32_t nwin = q.len - j.k + 1, k = j.k;
+  const uint64_t lead = j.lead_off[si + 1] - j.lead_off[si];
+  const char* lead_p = j.lead_blob + j.lead_off[si];
+  // the sequence's symbols once, windows are slices of it
+  std::vector<char> text((size_t)q.len);
+  if (q.flags & PF_SEQ_AMBIGUOUS) {
+    for (uint32_t s = 0; s < q.len; ++s) {
+      const uint64_t i = q.amb_off + s;
+      text[s] = kAmb[(j.b->amb_codes[i >> 4] >> (60 - 4 * (i & 15u))) & 15u];
+    }
+  } else {
+    for (uint32_t s = 0; s < q.len; ++s) {
+      const uint64_t i = q.base_off + s;
+      text[s] = kAcgt[(j.b->packed_bases[i >> 5] >> (62 - 2 * (i & 31u))) & 3u];
+    }
+  }
+  for (uint32_t w = 0; w < nwin; ++w) {
+    const int64_t c0 = q.strand > 0 ? (int64_t)q.start + w : (int64_t)q.end - w - k, g0 = (int64_t)w - q.offset;
+    auto head = [&](char* o) {
+      memcpy(o, lead_p, lead);
+      o += lead;
+      o += put_int(o, c0); *o++ = '\t';
+      o += put_int(o, c0 + k); *o++ = '\t';
+      o += put_int(o, g0); *o++ = '\t';
+      o += put_int(o, g0 + k); *o++ = '\t';
+      return o;
+    };
+    const char* fwd = text.data() + w;
+    if (j.canonical) {
+      const bool rc = strand_bit(j, q, w);
+      p = head(p);
+      if (rc) { *p++ = '-'; *p++ = '1'; } else { *p++ = '1'; }
+      *p++ = '\t';
+      if (rc) for (uint32_t s = 0; s < k; ++s) p[s] = comp_symbol(fwd[k - 1 - s]);
+      else memcpy(p, fwd, k);
+      p += k;
+      *p++ = '\n';
+    } else {
+      p = head(p);
+      p += put_int(p, q.strand); *p++ = '\t';
+      memcpy(p, fwd, k); p += k;
+      *p++ = '\n';
+      p = head(p);
+      p += put_int(p, -(int64_t)q.strand); *p++ = '\t';
+      for (uint32_t s = 0; s < k; ++s) p[s] = comp_symbol(fwd[k - 1 - s]);
+      p += k;
+      *p++ = '\n';
+    }
+  }
+  return p;
+}
+}  // namespace
+
+extern "C" int pf_format_positions_compact(const pf_batch* b, const uint32_t* strand_bits, uint32_t k, int canonical,
+                                           uint32_t seq_first, uint32_t seq_count, const char* lead_blob,
+                                           const uint64_t* lead_off, char* out, uint64_t out_cap, uint64_t* out_len,
+                                           uint32_t n_threads) {
+  if (!b || !out_len || k < 1 || k > 32) return PF_ERR_INVALID;
+  if ((uint64_t)seq_first + seq_count > b->n_seqs) return PF_ERR_INVALID;
+  *out_len = 0;
+  if (seq_count == 0) return PF_OK;
+  if (!b->seqs || !b->packed_bases || !lead_blob || !lead_off || (canonical && !strand_bits)) return PF_ERR_INVALID;
+  for (uint32_t i = seq_first; i < seq_first + seq_count; ++i)
+    if ((b->seqs[i].flags & PF_SEQ_TARGET) && (b->seqs[i].flags & PF_SEQ_AMBIGUOUS) && !b->amb_codes) return PF_ERR_INVALID;
+  CJob j{b, strand_bits, k, canonical, lead_blob, lead_off};
+  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  uint32_t nt = n_threads ? n_threads : hw;
+  nt = std::max(1u, std::min<uint32_t>(nt, (seq_count + 63u) / 64u));
+  const uint32_t per = (seq_count + nt - 1) / nt;
+  std::vector<uint64_t> bytes(nt, 0);
+  auto run = [&](auto&& fn) {
+    if (nt == 1) { fn(0u); return; }
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < nt; ++t) th.emplace_back(fn, t);
+    for (auto& x : th) x.join();
+  };
+  run([&](uint32_t t) {
+    const uint32_t a = seq_first + std::min(seq_count, t * per), e = seq_first + std::min(seq_count, (t + 1) * per);
+    uint64_t s = 0;
+    for (uint32_t i = a; i < e; ++i) s += seq_rows_len(j, i);
+    bytes[t] = s;
+  });
+  uint64_t total = 0;
+  std::vector<uint64_t> start(nt, 0);
+  for (uint32_t t = 0; t < nt; ++t) { start[t] = total; total += bytes[t]; }
+  *out_len = total;
+  if (!out) return PF_OK;                       // sizing call
+  if (out_cap < total) return PF_ERR_NOMEM;
+  run([&](uint32_t t) {
+    const uint32_t a = seq_first + std::min(seq_count, t * per), e = seq_first + std::min(seq_count, (t + 1) * per);
+    char* p = out + start[t];
+    for (uint32_t i = a; i < e; ++i) p = write_seq_rows(j, i, p);
+  });
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------
 // Native packer: ASCII sequences -> the 2-bit / 4-bit planes of a pf_batch (what
 // panfeed_b200/packer.py:pack_batch does with numpy look-up tables), host threads.
 // ---------------------------------------------------------------------------

@@ -89,7 +89,8 @@ int pipe_enqueue_results(pf_ctx* ctx, const SubRange& r) {
   TRY(pin_grow(ctx, ctx->r_wrow_count, std::max<uint64_t>(8, (RW + nw) * 4), RW * 4));
   TRY(pin_grow(ctx, ctx->r_wrow_pattern, std::max<uint64_t>(8, (RW + nw) * 4), RW * 4));
   TRY(pin_grow(ctx, ctx->r_wrow_kmer, std::max<uint64_t>(8, (RW + nw) * 16), RW * 16));
-  if (ctx->n_pos) {
+  const bool compact = ctx->prm.emit_positions == 2u;
+  if (ctx->n_pos && !compact) {
     const uint64_t P0 = ctx->pipe_pos, np = ctx->n_pos;
     TRY(pin_grow(ctx, ctx->r_pos_kmer, (P0 + np) * 8, P0 * 8));
     TRY(pin_grow(ctx, ctx->r_pos_seq, (P0 + np) * 4, P0 * 4));
@@ -118,7 +119,9 @@ int pipe_enqueue_results(pf_ctx* ctx, const SubRange& r) {
   TRY(d2h(ctx->r_wrow_pattern, RW * 4, ctx->d_row_pattern.as<uint32_t>() + nr, nw * 4));
   TRY(d2h(ctx->r_wrow_kmer, RW * 16, ctx->d_wrow_kmer.p, nw * 16));
   TRY(d2h(ctx->r_cl_pattern, (size_t)ctx->pipe_clusters * 4, ctx->d_cl_pattern.p, (size_t)ctx->n_clusters * 4));
-  if (ctx->n_pos) {
+  if (ctx->n_pos && compact && ctx->prm.canonical)      // (r_pos_bits covers the whole batch: sized by the submit)
+    TRY(d2h(ctx->r_pos_bits, (size_t)r.w0 * 8, ctx->d_pos_bits.p, (size_t)(r.w1 - r.w0) * 8));
+  if (ctx->n_pos && !compact) {
     const uint64_t P0 = ctx->pipe_pos, np = ctx->n_pos;
     TRY(d2h(ctx->r_pos_kmer, P0 * 8, ctx->d_pos_kmer.p, np * 8));
     TRY(d2h(ctx->r_pos_seq, P0 * 4, ctx->d_pos_seq.p, np * 4));
@@ -177,6 +180,11 @@ int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>
   ctx->pipe_cp_base = ctx->cp.n;
   for (double& m : ctx->pipe_ms) m = 0;
   TRY(pin_ensure(ctx, ctx->r_cl_pattern, std::max<size_t>(8, (size_t)b->n_clusters * 4)));
+  ctx->pipe_bit_words = 0;
+  if (ctx->prm.emit_positions == 2u && ctx->prm.canonical) {
+    TRY(pin_ensure(ctx, ctx->r_pos_bits, std::max<size_t>(8, (size_t)b->n_words * 8)));
+    ctx->pipe_bit_words = b->n_words * 2;
+  }
   {
     // row arrays: learned rows-per-base ratio, grown on demand
     const uint64_t est = (uint64_t)(ctx->row_ratio * 1.3 * (double)b->n_words * 32.0) + 65536;
@@ -335,6 +343,15 @@ int collect_pipelined(pf_ctx* ctx, pf_batch_result* out) {
     out->pos_flags = ctx->r_pos_flags.as<uint8_t>();
     out->pos_wide_kmer = ctx->r_pos_wide.as<uint64_t>();
     out->n_pos_wide = ctx->pipe_pos_wide;
+    if (ctx->prm.emit_positions == 2u) {
+      out->pos_kmer = nullptr; out->pos_seq = nullptr; out->pos_contig_start = nullptr;
+      out->pos_gene_start = nullptr; out->pos_flags = nullptr; out->pos_wide_kmer = nullptr;
+      out->n_pos_wide = 0;
+      if (ctx->pipe_pos && ctx->pipe_bit_words) {
+        out->pos_strand_bits = ctx->r_pos_bits.as<uint32_t>();
+        out->n_pos_bit_words = ctx->pipe_bit_words;
+      }
+    }
   }
   pf_stats& s = ctx->stats;
   s.batches++;
@@ -385,14 +402,17 @@ extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
   TRY(d2h(ctx->r_cl_pattern, ctx->d_cl_pattern.p, (size_t)ctx->n_clusters * 4));
   TRY(d2h(ctx->r_new_kp, ctx->kp.pool.as<uint32_t>() + ctx->kp_base * ctx->Wk, new_kp * ctx->Wk * 4));
   TRY(d2h(ctx->r_new_cp, ctx->cp.pool.as<uint32_t>() + ctx->cp_base * ctx->W, new_cp * ctx->W * 4));
-  if (ctx->n_pos) {
+  const bool compact = ctx->prm.emit_positions == 2u;
+  if (ctx->n_pos && compact) {
+    if (ctx->prm.canonical) TRY(d2h(ctx->r_pos_bits, ctx->d_pos_bits.p, (size_t)ctx->n_words * 8));
+  } else if (ctx->n_pos) {
     TRY(d2h(ctx->r_pos_kmer, ctx->d_pos_kmer.p, (size_t)ctx->n_pos * 8));
     TRY(d2h(ctx->r_pos_seq, ctx->d_pos_seq.p, (size_t)ctx->n_pos * 4));
     TRY(d2h(ctx->r_pos_cstart, ctx->d_pos_cstart.p, (size_t)ctx->n_pos * 4));
     TRY(d2h(ctx->r_pos_gstart, ctx->d_pos_gstart.p, (size_t)ctx->n_pos * 4));
     TRY(d2h(ctx->r_pos_flags, ctx->d_pos_flags.p, (size_t)ctx->n_pos));
   }
-  if (ctx->n_pos_wide) TRY(d2h(ctx->r_pos_wide, ctx->d_pos_wide.p, (size_t)ctx->n_pos_wide * 16));
+  if (ctx->n_pos_wide && !compact) TRY(d2h(ctx->r_pos_wide, ctx->d_pos_wide.p, (size_t)ctx->n_pos_wide * 16));
   CU(cudaEventRecord(ctx->ev_d2h[1], st));
   CU(cudaStreamSynchronize(st));
   if (ctx->rows_prefetched) CU(cudaStreamSynchronize(ctx->copy_stream));
@@ -426,6 +446,15 @@ extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
     out->pos_flags = ctx->r_pos_flags.as<uint8_t>();
     out->pos_wide_kmer = ctx->r_pos_wide.as<uint64_t>();
     out->n_pos_wide = ctx->n_pos_wide;
+    if (compact) {
+      out->pos_kmer = nullptr; out->pos_seq = nullptr; out->pos_contig_start = nullptr;
+      out->pos_gene_start = nullptr; out->pos_flags = nullptr; out->pos_wide_kmer = nullptr;
+      out->n_pos_wide = 0;
+      if (ctx->n_pos && ctx->prm.canonical) {
+        out->pos_strand_bits = ctx->r_pos_bits.as<uint32_t>();
+        out->n_pos_bit_words = ctx->n_words * 2;
+      }
+    }
   }
   // ---- stats ---------------------------------------------------------------
   pf_stats& s = ctx->stats;

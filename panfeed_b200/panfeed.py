@@ -112,8 +112,9 @@ class PatternStore:
                 device=0, sort_bits=0):
         key = (k, S, canonical, consider_missing, cluster_equal_filter, maf, device)
         if self.ctx is None:
+            # positional rows in the compact form: only the used_strand bits leave the device
             self.ctx = capi.Context(k, S, canonical, consider_missing, cluster_equal_filter,
-                                    emit_positions=True, maf=maf, sort_bits=sort_bits,
+                                    emit_positions=2, maf=maf, sort_bits=sort_bits,
                                     device=device)
             self.key = key
         elif key != self.key:
@@ -212,16 +213,18 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
     hash_texts = [text[int(off[c]):int(off[c + 1])].decode() for c in range(len(idxs))]
 
     # ---- kmers.tsv rows from the positional records: formatted by the library's host
-    #      threads (pf_format_positions), 1e8 rows are too many for Python.  Only the target
-    #      sequences need their leading fields (and with them their lazily built metadata). ----
+    #      threads (pf_format_positions_compact: the device only returns the used_strand bit
+    #      of every window, the rest of a row follows from the batch itself), 1e8 rows are too
+    #      many for Python.  Only the target sequences need their leading fields (and with them
+    #      their lazily built metadata). ----
     pos_text = ""
-    if len(r["pos_seq"]):
+    if r["n_pos"]:
         leads = [b""] * len(hb.seqs)
         cl, strand = hb.seqs["cluster"], hb.seqs["strand"]
-        for i in np.unique(r["pos_seq"]).tolist():
+        for i in np.nonzero(hb.seqs["flags"] & capi.PF_SEQ_TARGET)[0].tolist():
             m = meta[i]
             leads[i] = f"{idxs[cl[i]]}\t{m[0]}\t{m[1]}\t{m[2]}\t{strand[i]}\t".encode()
-        pos_text = capi.format_positions(r, k, canonical, leads, strand).decode()
+        pos_text = capi.format_positions_compact(hb, r["pos_strand_bits"], k, canonical, leads).decode()
     return pos_text, "".join(pat_text), hash_texts
 
 def pattern_hasher(cluster_dict_iter, kmer_stroi, hash_pat, kmer_hash, genepres, patfilt, maf,

@@ -220,3 +220,55 @@ def test_gzip_text_writer_matches_gzip_open(tmp_path):
     empty = str(tmp_path / "empty.tsv.gz")
     GzipTextWriter(empty).close()
     assert gzip.open(empty, "rt").read() == ""
+
+
+@pytest.mark.parametrize("k", [1, 15, 31, 32])
+@pytest.mark.parametrize("canonical", [True, False])
+@pytest.mark.parametrize("threads", [1, 4])
+def test_native_compact_position_rows_match_python(k, canonical, threads):
+    """pf_format_positions_compact (emit_positions = 2: the device only returns the used_strand
+    bit of every window) against a Python rendering of panfeed.py:64-107 on the same batch:
+    k-mer text from the packed planes, coordinates from the descriptors."""
+    from panfeed_b200 import packer
+    rng = np.random.default_rng(7 * k + canonical)
+    n_seqs = 90 if threads > 1 else 12
+    seqs_txt = []
+    for i in range(n_seqs):
+        L = int(rng.integers(0, 140))
+        alphabet = list("ACGTNRYK") if i % 7 == 3 else list("ACGT")
+        seqs_txt.append("".join(rng.choice(alphabet, L)) if L else "")
+    packed, base_off, is_amb, amb_plane, amb_off = capi.pack_sequences([s.encode() for s in seqs_txt])
+    seqs = np.zeros(n_seqs, capi.SEQ_DTYPE)
+    seqs["base_off"], seqs["amb_off"] = base_off, amb_off
+    seqs["len"] = [len(s) for s in seqs_txt]
+    seqs["flags"] = (rng.random(n_seqs) < 0.7) * capi.PF_SEQ_TARGET + is_amb * capi.PF_SEQ_AMBIGUOUS
+    seqs["start"] = rng.integers(1, 4_000_000, n_seqs)
+    seqs["end"] = seqs["start"] + seqs["len"] - 1
+    seqs["offset"] = rng.integers(0, 120, n_seqs)
+    seqs["strand"] = rng.choice([1, -1], n_seqs)
+    hb = capi.HostBatch(packed, seqs, np.zeros(1, capi.CLUSTER_DTYPE), np.zeros((1, 1), np.uint32), amb_plane)
+    leads = [f"cl{i % 4}\tstrain_{i}\tgene{i}\tctg{i % 3}\t{int(seqs['strand'][i])}\t".encode() for i in range(n_seqs)]
+    # the bit plane the device would return: 1 where the reverse complement is the canonical k-mer
+    bits = np.zeros(2 * len(packed) + 2, np.uint32)
+    want = []
+    for i, s in enumerate(seqs_txt):
+        q = seqs[i]
+        for p in range(len(s) - k + 1):
+            fwd = s[p:p + k]
+            rc = fwd.encode().translate(_COMP)[::-1].decode()
+            c0 = int(q["start"]) + p if q["strand"] > 0 else int(q["end"]) - p - k
+            g0 = p - int(q["offset"])
+            use_rc = not fwd <= rc
+            if use_rc:
+                j = int(q["base_off"]) + p
+                bits[j >> 5] |= np.uint32(1 << (j & 31))
+            if not (q["flags"] & capi.PF_SEQ_TARGET):
+                continue
+            head = leads[i].decode() + f"{c0}\t{c0 + k}\t{g0}\t{g0 + k}\t"
+            if canonical:
+                want.append(f"{head}{-1 if use_rc else 1}\t{rc if use_rc else fwd}\n")
+            else:
+                st = int(q["strand"])
+                want.append(f"{head}{st}\t{fwd}\n{head}{-st}\t{rc}\n")
+    got = capi.format_positions_compact(hb, bits if canonical else None, k, canonical, leads, n_threads=threads)
+    assert got.decode() == "".join(want)

@@ -282,6 +282,16 @@ def test_block_engine_sample_slices_10k():
     assert out["stats"]["engine"] == 2
 
 
+def test_block_engine_sample_slices_50k_consider_missing():
+    """BASELINE config #5's sample count with the cluster-absent encoding (NaN plane, MAF over
+    the present samples only) on short clusters (the oracle's limit), against the C oracle."""
+    rng = np.random.default_rng(33)
+    S = 50000
+    items, stroi = _random_items(rng, S, 31, 2, 80)
+    out, want = _compare_with_oracle(items, set(), S, 31, True, True, False, 0.01, batch_clusters=2)
+    assert out["stats"]["engine"] == 2
+
+
 @pytest.mark.parametrize("smem_kb,S", [("0", 90), ("2", 90), ("2", 1300)])
 def test_block_engine_merge_spills_to_global_table(smem_kb, S, monkeypatch):
     """kB1_local merges a cluster's partial rows in shared memory; a cluster with more rows than
