@@ -844,7 +844,9 @@ def main():
         dt_rank = time.perf_counter() - t0
         dt = env.reduce(dt_rank, "max")
         h2d = h2d_bytes(hb)
+        pst = ctx.stats()         # device times of the LAST pipelined submit, summed over its sub-batches
         e2e = {"value": total_bases * args.steps / dt, "unit": "bases/s",
+               "stages_ms_pipelined_last_step": {k_: round(pst[k_], 3) for k_ in STAGE_KEYS + ("ms_h2d", "ms_d2h")},
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * dt / args.steps, "sub_batches": ctx.stats()["sub_batches"],
                "unique_kmers_per_s": U_total * args.steps / dt,

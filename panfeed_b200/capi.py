@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libpanfeed_b200.so")
+# PF_LIB_PATH: a differently built library (kernel A/B experiments); default = the in-tree build
+LIB_PATH = os.environ.get("PF_LIB_PATH") or os.path.join(HERE, "csrc", "libpanfeed_b200.so")
 
 PF_ABI_VERSION = 1
 PF_SEQ_TARGET = 1

@@ -53,7 +53,10 @@ struct ClusterBlk {        // 16 bytes
   uint32_t seq_start, n_seqs, max_nwin, reserved;
 };
 
-constexpr int kBlkThreads = 256;
+#ifndef PF_KA_THREADS
+#define PF_KA_THREADS 256
+#endif
+constexpr int kBlkThreads = PF_KA_THREADS;
 constexpr int kBlkWarps = kBlkThreads / 32;
 constexpr int kBlkRun = 16;                       // windows per task
 constexpr uint32_t kBlkOverflow = 0xffffffffu;    // slab count of a block that did not fit

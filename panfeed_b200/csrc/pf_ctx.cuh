@@ -319,6 +319,7 @@ struct pf_ctx : BatchState {
   uint64_t pipe_kp_base = 0, pipe_cp_base = 0, pipe_kp_copied = 0;
   uint64_t pipe_row_cap = 0, pipe_wide_cap = 0;
   cudaEvent_t ev_pipe[2]{};
+  std::vector<std::array<cudaEvent_t, 5>> dbg_ev;   // PF_DEBUG_PIPE: per sub-batch {upload start, upload end, kernels start, kernels end, D2H end}
   uint32_t pipe_min_seqs = 200000;   // batches with fewer sequences are not split
   uint32_t pipe_target_seqs = 262144;   // sequences per sub-batch
   uint32_t pipe_first_seqs = 98304;     // ... of the first one (its upload is not hidden)
@@ -376,12 +377,24 @@ bool debug_sync(const char* name) {
   static const char* v = getenv("PF_DEBUG_SYNC");
   return v && (v[0] == '1' || strstr(name, v) != nullptr);
 }
+// PF_DEBUG_TIME=1: synchronise after every stage and print the wall-clock time since the previous
+// stage boundary (host work + device work of the stage).
+inline double pf_now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+inline bool debug_time() { static const bool v = getenv("PF_DEBUG_TIME") != nullptr; return v; }
+static thread_local double g_stage_tick = 0;
 #define STAGE(name)                                                                      \
   do {                                                                                   \
-    if (debug_sync(name)) {                                                                  \
+    if (debug_sync(name) || debug_time()) {                                              \
       cudaError_t e_ = cudaStreamSynchronize(ctx->stream);                               \
       if (e_ != cudaSuccess)                                                             \
         return fail(ctx, PF_ERR_CUDA, "stage %s: %s", name, cudaGetErrorString(e_));     \
+      if (debug_time()) {                                                                \
+        const double t_ = pf_now_ms();                                                   \
+        fprintf(stderr, "[pf] stage %-28s %8.3f ms\n", name, t_ - g_stage_tick);         \
+        g_stage_tick = t_;                                                               \
+      }                                                                                  \
     }                                                                                    \
   } while (0)
 

@@ -588,6 +588,8 @@ extern "C" int pf_execute(pf_ctx* ctx) {
     TRY(ensure_rows(ctx, ctx->row_cap, ctx->row_cap, false));
   }
 
+  if (debug_time()) g_stage_tick = pf_now_ms();
+  STAGE("buffers ensured");
   CU(cudaMemsetAsync(counters, 0, C_COUNT * 4, st));
   CU(cudaEventRecord(ctx->ev[EV_START], st));
 
@@ -876,6 +878,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
     ctx->rows_prefetched = true;
   }
 
+  STAGE("rows emitted");
   // ---- K4 ---------------------------------------------------------------
   // the previous batch's K4 is long over by now (this call has synchronised the stream at least
   // once since): fold its pattern count in, then number this batch's patterns behind it
@@ -883,6 +886,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   ctx->kp_base = ctx->kp.n;
   TRY(dedup(ctx, ctx->kp, ctx->d_cand.as<uint32_t>(), (uint32_t)rows, ctx->d_rep, ctx->d_slot_of,
             ctx->d_winner, ctx->d_row_pattern.as<uint32_t>(), C_NEW_KP));
+  STAGE("k4 k-mer rows");
   CU(cudaEventRecord(ctx->ev[EV_DEDUP], st));
   TRY(pin_ensure(ctx, ctx->h_done, 16));
   mirror_counters<<<1, 32, 0, st>>>(hcnt, counters, C_COUNT);

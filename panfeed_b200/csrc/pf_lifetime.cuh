@@ -235,6 +235,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->r_wrow_cluster, &ctx->r_wrow_count, &ctx->r_wrow_pattern, &ctx->r_pos_bits})
     fp(*b);
   for (auto& ev : ctx->ev_d2h) if (ev) cudaEventDestroy(ev);
+  for (auto& e : ctx->dbg_ev) for (auto& x : e) if (x) cudaEventDestroy(x);
   for (int i = 0; i < 2; ++i) if (ctx->ev_pipe[i]) cudaEventDestroy(ctx->ev_pipe[i]);
   if (ctx->ev_rows) cudaEventDestroy(ctx->ev_rows);
   if (ctx->up_stream) cudaStreamDestroy(ctx->up_stream);

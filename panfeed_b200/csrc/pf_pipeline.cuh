@@ -202,12 +202,21 @@ int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>
   const double t_begin = now();
   double t_up = 0, t_ex = 0, t_out = 0, t_fin = 0, t_join = 0;
   CU(cudaEventRecord(ctx->ev_pipe[0], st));
+  if (dbg) {                // GPU-side timeline of the sub-batches, printed by pf_collect
+    while (ctx->dbg_ev.size() < J) {
+      std::array<cudaEvent_t, 5> e{};
+      for (auto& x : e) cudaEventCreate(&x);
+      ctx->dbg_ev.push_back(e);
+    }
+    cudaEventRecord(ctx->dbg_ev[0][0], up);
+  }
   auto add_h2d = [&]() {
     float m = 0;
     if (cudaEventElapsedTime(&m, ctx->ev_h2d[0], ctx->ev_h2d[1]) == cudaSuccess) ctx->pipe_ms[0] += m;
     else cudaGetLastError();
   };
   TRY(upload_async(ctx, *ctx, b, subs[0], up));
+  if (dbg) cudaEventRecord(ctx->dbg_ev[0][1], up);
   TRY(upload_finish_slot(ctx, *ctx, st));
   add_h2d();
 
@@ -229,7 +238,9 @@ int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>
     helper.w.start([&, j, slot]() {
       cudaSetDevice(ctx->device);
       const double t0 = now();
+      if (dbg) cudaEventRecord(ctx->dbg_ev[j][0], up);
       helper.rc = upload_async(ctx, *slot, b, subs[j], up);
+      if (dbg) cudaEventRecord(ctx->dbg_ev[j][1], up);
       t_up += now() - t0;
     });
     return PF_OK;
@@ -246,11 +257,14 @@ int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>
     // this slot's previous rows must have left the device before they are overwritten
     CU(cudaStreamWaitEvent(st, ctx->ev_out_done, 0));
     t0 = now();
+    if (dbg) cudaEventRecord(ctx->dbg_ev[j][2], st);
     TRY(pf_execute(ctx));
     t_ex += now() - t0;
     CU(cudaEventRecord(ctx->ev_exec_end, st));
+    if (dbg) cudaEventRecord(ctx->dbg_ev[j][3], st);
     t0 = now();
     TRY(pipe_enqueue_results(ctx, subs[j]));
+    if (dbg) cudaEventRecord(ctx->dbg_ev[j][4], ctx->copy_stream);
     t_out += now() - t0;
     t0 = now();
     // pf_execute folded sub-batch j-1's pattern count in before its own K4: those patterns are
@@ -315,6 +329,16 @@ int collect_pipelined(pf_ctx* ctx, pf_batch_result* out) {
   CU(cudaEventRecord(ctx->ev_d2h[1], st));
   CU(cudaStreamSynchronize(st));
   CU(cudaStreamSynchronize(ctx->copy_stream));
+  if (getenv("PF_DEBUG_PIPE") && ctx->dbg_ev.size() >= ctx->pipe_subs) {
+    CU(cudaStreamSynchronize(ctx->up_stream));
+    for (uint32_t j = 0; j < ctx->pipe_subs; ++j) {
+      float t[5] = {0, 0, 0, 0, 0};
+      for (int i = 0; i < 5; ++i)
+        if (cudaEventElapsedTime(&t[i], ctx->ev_pipe[0], ctx->dbg_ev[j][i]) != cudaSuccess) { cudaGetLastError(); t[i] = -1; }
+      fprintf(stderr, "[pf] timeline sub %u: upload %.2f..%.2f  kernels %.2f..%.2f  d2h done %.2f ms\n", j, t[0], t[1], t[2],
+              t[3], t[4]);
+    }
+  }
   if (out) {
     memset(out, 0, sizeof *out);
     out->n_rows = ctx->pipe_rows;

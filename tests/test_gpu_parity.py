@@ -53,7 +53,8 @@ def test_fixture_modes_match_reference_goldens(mode, engine):
 
 def _random_items(rng, S, k, n_clusters, L, amb_rate=0.0, div=0.03):
     comp = str.maketrans("ACGTN", "TGCAN")
-    names = [f"g{i:04d}" for i in range(S)]
+    names = [f"g{i:0{max(4, len(str(S - 1)))}d}" for i in range(S)]     # sorted order == rank order
+    rank = {s: i for i, s in enumerate(names)}
     order = list(rng.permutation(names))
     items = []
     for c in range(n_clusters):
@@ -72,7 +73,7 @@ def _random_items(rng, S, k, n_clusters, L, amb_rate=0.0, div=0.03):
             if rng.random() > p_present:
                 absent.append(s)
                 continue
-            presab[names.index(s)] = 1
+            presab[rank[s]] = 1
             lst = []
             for _ in range(2 if rng.random() < 0.1 else 1):
                 q = founders[int(rng.integers(3))].copy()
