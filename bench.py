@@ -111,16 +111,19 @@ def config_of(args, cid):
 # clocks
 # --------------------------------------------------------------------------
 class ClockSampler:
-    """SM clock and clock-event reasons of one GPU, sampled every 2 ms through NVML from a
-    thread of this process while the timed region runs (the timed region is tens of ms: an
+    """SM clock and clock-event reasons of one GPU, sampled every `period` s (default 5 ms; 50 ms
+    for the streamed configs, whose timed regions last seconds: NVML queries take driver locks
+    that CUDA calls of the measured thread also need) through NVML from a thread of this process
+    while the timed region runs (the timed region is tens of ms: an
     `nvidia-smi -lms` child would not have printed its first line by the time it ends).
     Falls back to `nvidia-smi -lms 20` when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
+    def __init__(self, device, period=0.005):
         self.device = device
+        self.period = period
         self.p = None
         self.f = None
         self.thread = None
@@ -162,7 +165,7 @@ class ClockSampler:
                 self.samples.append((float(mhz), int(why)))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         if self.nvml is not None:
@@ -195,7 +198,8 @@ class ClockSampler:
             reasons = sorted({n for _, why in self.samples for n, bit in names if why & bit})
             sm = [m for m, _ in self.samples]
             return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": self.max_mhz,
-                    "reasons": reasons, "samples": len(sm), "source": "nvml, 2 ms period, timed region only"}
+                    "reasons": reasons, "samples": len(sm),
+                    "source": f"nvml, {self.period * 1e3:.0f} ms period, timed region only"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -738,7 +742,7 @@ def main():
 
     if cfg["id"] != 2 or cfg["batch"] < cfg["clusters"]:
         # a streamed config as the headline: K passes over all its batches
-        sampler = ClockSampler(local)
+        sampler = ClockSampler(local, period=0.05)
         sampler.start()
         r = run_streamed(cfg, env, args, passes=max(1, min(args.steps, 3)))
         clocks = sampler.stop()

@@ -5,6 +5,7 @@
 //   host side    pf_ctx.cuh pf_lifetime.cuh pf_upload.cuh pf_execute.cuh pf_pipeline.cuh
 //                pf_synth_api.cuh pf_exchange.cuh
 // (pf_format.cu, the native text formatter, is a second, host-only translation unit.)
+#include <cuda.h>            // driver types for the virtual-memory pool (entry points are fetched at run time)
 #include <cuda_runtime.h>
 
 #include <algorithm>

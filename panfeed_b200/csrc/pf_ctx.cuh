@@ -76,9 +76,22 @@ struct PinBuf {
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// The pattern pools only ever grow, up to tens of GB (50,000 samples: 6 kB per pattern).  Growing a
+// cudaMalloc'ed array means allocate + copy + free of everything numbered so far, and cudaFree
+// stalls the whole device; instead the pool reserves a range of virtual addresses once and maps
+// more physical memory behind what is already there (CUDA virtual memory management, driver entry
+// points fetched through the runtime: no link-time dependency on libcuda).  Pointers into the pool
+// stay valid, nothing is copied.  Falls back to the copying DevBuf if the driver refuses.
+struct PoolBuf : DevBuf {
+  bool vmm = false;
+  CUdeviceptr base = 0;
+  size_t reserved = 0;
+  std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
+};
+
 struct PatternSpace {
   uint32_t key_words = 0;
-  DevBuf pool;            // n x key_words
+  PoolBuf pool;           // n x key_words
   uint64_t n = 0;         // committed patterns
   DevBuf table;           // table_size x u32
   uint32_t table_size = 0;
@@ -345,8 +358,12 @@ int fail(pf_ctx* c, int code, const char* fmt, ...) {
                   __FILE__, __LINE__);                                                 \
   } while (0)
 
+// PF_DEBUG_ALLOC=1: report every (re)allocation - in the steady state there must be none
+inline bool debug_alloc() { static const bool v = getenv("PF_DEBUG_ALLOC") != nullptr; return v; }
+
 int dev_ensure(pf_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false) {
   if (bytes <= b.cap) return PF_OK;
+  if (debug_alloc()) fprintf(stderr, "[pf] alloc: device buffer %zu -> %zu bytes%s\n", b.cap, bytes, keep ? " (copy)" : "");
   size_t want = std::max(bytes, b.cap + b.cap / 2);
   want = (want + 255) & ~size_t(255);
   void* np = nullptr;
@@ -362,6 +379,7 @@ int dev_ensure(pf_ctx* ctx, DevBuf& b, size_t bytes, bool keep = false) {
 }
 int pin_ensure(pf_ctx* ctx, PinBuf& b, size_t bytes) {
   if (bytes <= b.cap) return PF_OK;
+  if (debug_alloc()) fprintf(stderr, "[pf] alloc: pinned buffer %zu -> %zu bytes\n", b.cap, bytes);
   size_t want = std::max(bytes, b.cap + b.cap / 2);
   want = (want + 4095) & ~size_t(4095);
   if (b.p) CU(cudaFreeHost(b.p));
@@ -371,6 +389,103 @@ int pin_ensure(pf_ctx* ctx, PinBuf& b, size_t bytes) {
   return PF_OK;
 }
 #define TRY(x) do { int r_ = (x); if (r_ != PF_OK) return r_; } while (0)
+
+struct VmmApi {
+  CUresult (*reserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*addr_free)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*create)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*set_access)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*granularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  bool ok = false;
+};
+const VmmApi& vmm_api() {
+  static const VmmApi api = []() {
+    VmmApi a;
+    if (getenv("PF_NO_VMM")) return a;
+    auto get = [](const char* name, void** fn) {
+      cudaDriverEntryPointQueryResult st;
+      return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &st) == cudaSuccess &&
+             st == cudaDriverEntryPointSuccess && *fn != nullptr;
+    };
+    a.ok = get("cuMemAddressReserve", (void**)&a.reserve) && get("cuMemAddressFree", (void**)&a.addr_free) &&
+           get("cuMemCreate", (void**)&a.create) && get("cuMemRelease", (void**)&a.release) &&
+           get("cuMemMap", (void**)&a.map) && get("cuMemUnmap", (void**)&a.unmap) &&
+           get("cuMemSetAccess", (void**)&a.set_access) &&
+           get("cuMemGetAllocationGranularity", (void**)&a.granularity);
+    if (!a.ok) cudaGetLastError();
+    return a;
+  }();
+  return api;
+}
+
+void pool_free(PoolBuf& b) {
+  if (b.vmm) {
+    const VmmApi& api = vmm_api();
+    size_t off = 0;
+    for (auto& c : b.chunks) { api.unmap(b.base + off, c.second); api.release(c.first); off += c.second; }
+    if (b.base) api.addr_free(b.base, b.reserved);
+    b.chunks.clear();
+    b.base = 0; b.reserved = 0; b.vmm = false;
+  } else if (b.p) {
+    cudaFree(b.p);
+  }
+  b.p = nullptr; b.cap = 0;
+}
+
+// grow a pattern pool to at least `bytes`, keeping its contents (and, with VMM, its address)
+int pool_ensure(pf_ctx* ctx, PoolBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return PF_OK;
+  const VmmApi& api = vmm_api();
+  if (debug_alloc()) fprintf(stderr, "[pf] alloc: pattern pool %zu -> %zu bytes\n", b.cap, bytes);
+  if (api.ok && (b.vmm || !b.p)) {
+    CUmemAllocationProp prop{};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = ctx->device;
+    size_t gran = 0;
+    bool good = api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && gran > 0;
+    if (good && !b.p) {
+      size_t free_b = 0, total_b = 0;
+      good = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess;
+      if (good) {
+        const size_t want_va = (total_b + gran - 1) / gran * gran;      // a pool cannot outgrow the device
+        CUdeviceptr base = 0;
+        good = api.reserve(&base, want_va, gran, 0, 0) == CUDA_SUCCESS;
+        if (good) { b.base = base; b.reserved = want_va; b.p = reinterpret_cast<void*>(base); b.cap = 0; b.vmm = true; }
+      }
+    }
+    if (good) {
+      size_t want = std::max(bytes, b.cap + std::max<size_t>(b.cap / 4, (size_t)64 << 20));
+      want = (want + gran - 1) / gran * gran;
+      if (want > b.reserved) return fail(ctx, PF_ERR_NOMEM, "pattern pool would exceed the device memory");
+      const size_t add = want - b.cap;
+      CUmemGenericAllocationHandle h = 0;
+      CUresult r = api.create(&h, add, &prop, 0);
+      if (r != CUDA_SUCCESS && want > bytes) {                     // no room for the generous step: the exact one
+        want = (bytes + gran - 1) / gran * gran;
+        r = api.create(&h, want - b.cap, &prop, 0);
+      }
+      if (r != CUDA_SUCCESS) return fail(ctx, PF_ERR_NOMEM, "cuMemCreate of %zu bytes for the pattern pool failed (%d)", want - b.cap, (int)r);
+      const size_t got = want - b.cap;
+      CUmemAccessDesc acc{};
+      acc.location = prop.location;
+      acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+      if (api.map(b.base + b.cap, got, 0, h, 0) != CUDA_SUCCESS ||
+          api.set_access(b.base + b.cap, got, &acc, 1) != CUDA_SUCCESS) {
+        api.release(h);
+        return fail(ctx, PF_ERR_CUDA, "mapping %zu more bytes of the pattern pool failed", got);
+      }
+      b.chunks.emplace_back(h, got);
+      b.cap = want;
+      return PF_OK;
+    }
+    if (b.vmm) return fail(ctx, PF_ERR_CUDA, "pattern pool: virtual memory management failed");
+  }
+  return dev_ensure(ctx, b, bytes, true);       // copying fallback
+}
 
 // PF_DEBUG_SYNC=1: synchronise after every stage so a device fault names its kernel.
 bool debug_sync(const char* name) {

@@ -154,7 +154,7 @@ int table_reserve(pf_ctx* ctx, PatternSpace& s, uint64_t extra) {
   cudaStream_t st = ctx->stream;
   const uint64_t need = (s.n + extra) * 2 + 16;
   if (need >= (1ull << 31)) return fail(ctx, PF_ERR_NOMEM, "pattern table would exceed 2^31 slots");
-  TRY(dev_ensure(ctx, s.pool, std::max<size_t>(1, (s.n + extra)) * s.key_words * 4, true));
+  TRY(pool_ensure(ctx, s.pool, std::max<size_t>(1, (s.n + extra)) * s.key_words * 4));
   if (need <= s.table_size) return PF_OK;
   uint32_t size = std::max<uint32_t>(1024, s.table_size);
   while (size < need) size *= 2;

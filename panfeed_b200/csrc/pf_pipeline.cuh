@@ -6,6 +6,7 @@ namespace {
 // grow a pinned result array, keeping the `used` bytes already copied into it
 int pin_grow(pf_ctx* ctx, PinBuf& b, size_t need, size_t used) {
   if (need <= b.cap) return PF_OK;
+  if (debug_alloc()) fprintf(stderr, "[pf] alloc: pinned result array %zu -> %zu bytes (copy)\n", b.cap, need);
   CU(cudaStreamSynchronize(ctx->copy_stream));     // copies into the old array are in flight
   size_t want = std::max(need, b.cap + b.cap / 2);
   want = (want + 4095) & ~size_t(4095);
@@ -71,6 +72,10 @@ void pipe_add_timings(pf_ctx* ctx, const BatchState* slot = nullptr) {
   const float v[10] = {0.f, t.ms_extract, t.ms_hist, t.ms_sort, t.ms_mark, t.ms_count, t.ms_reduce,
                        t.ms_dedup, 0.f, 0.f};
   for (int i = 0; i < 10; ++i) ctx->pipe_ms[i] += v[i];
+  static const bool dbg = getenv("PF_DEBUG_PIPE") != nullptr;
+  if (dbg)
+    fprintf(stderr, "[pf] sub-batch stages: cluster rows %.3f  kA %.3f  kB %.3f  emit %.3f  k4 %.3f  (hist %.3f mark %.3f) ms\n",
+            t.ms_extract, t.ms_sort, t.ms_count, t.ms_reduce, t.ms_dedup, t.ms_hist, t.ms_mark);
 }
 
 // D2H of the current slot's results behind everything it executed, appended to the pinned
@@ -248,12 +253,20 @@ int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>
   BatchState* nx = &ctx->alt;
   BatchState* nx2 = &ctx->alt2;
   if (J > 1) TRY(start_upload(1, nx));
-  for (size_t j = 0; j < J; ++j) {
-    double t0 = now();
-    helper.join();                       // sub-batch j+1 is enqueued (started one iteration ago)
+  // the upload of sub-batch j+1 has been enqueued (its planning is host work of ~1 ms): wait for
+  // that, then start the one of j+2 in the slot sub-batch j-1 ran in
+  auto next_upload = [&](size_t j) -> int {
+    const double t0 = now();
+    helper.join();
     t_join += now() - t0;
     if (helper.rc != PF_OK) return helper.rc;
     if (j + 2 < J) TRY(start_upload(j + 2, nx2));
+    return PF_OK;
+  };
+  for (size_t j = 0; j < J; ++j) {
+    double t0 = now();
+    // (sub-batch 0 does not wait for the planning of sub-batch 1: its kernels go first)
+    if (j > 0) TRY(next_upload(j));
     // this slot's previous rows must have left the device before they are overwritten
     CU(cudaStreamWaitEvent(st, ctx->ev_out_done, 0));
     t0 = now();
@@ -271,6 +284,7 @@ int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>
     // final, and so are the stage timestamps of the slot it ran in (now *nx2)
     TRY(pipe_copy_new_patterns(ctx));
     if (j > 0) pipe_add_timings(ctx, nx2);
+    if (j == 0) TRY(next_upload(0));
     if (j + 1 < J) {
       ctx->executed = false;
       std::swap(static_cast<BatchState&>(*ctx), *nx);     // *ctx: sub-batch j+1; *nx: free (j's slot)
