@@ -766,8 +766,9 @@ def main():
 
     S, C, L, k = cfg["samples"], cfg["clusters"], cfg["gene_len"], cfg["k"]
     total_clusters = C * world
+    head_arena = capi.SynthArena()       # all four arrays of the batch in pinned host memory
     hb = capi.synth_batch(local, cfg["seed"], S, C, first_cluster=rank * C, total_clusters=total_clusters,
-                          gene_len=L, pinned=True, all_targets=cfg["targets"])
+                          gene_len=L, all_targets=cfg["targets"], arena=head_arena)
     n_bases = hb.n_bases
     ctx = make_context(cfg, env, args)
     stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)

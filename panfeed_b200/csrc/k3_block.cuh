@@ -76,6 +76,83 @@ __global__ void plan_seq_lite(const SeqDev* __restrict__ seqs, uint32_t n, SeqLi
   out[i] = l;
 }
 
+// ---------------------------------------------------------------------------
+// Device-side planning of an upload ("lite" upload): the caller's pf_seq_desc array goes to the
+// device as it is and ONE kernel does what the host planner does per sequence - validation
+// (include/panfeed_b200.h: pf_seq_desc), rebasing to the sub-range, the 64-byte SeqDev and the
+// 16-byte SeqLite - plus the batch totals.  The host then touches no descriptor at all: with
+// several ranks sharing the host's cores the per-sequence planning (~15 ns per sequence and
+// thread) was what bounded the end-to-end rate.  Only the block engine can run from it (no
+// record offsets are computed); a batch that falls back to the record engine is re-planned on
+// the host from the device copy of the descriptors.
+// ---------------------------------------------------------------------------
+struct LiteTotals {          // 64 bytes, zeroed (err = all ones) before the kernel
+  unsigned long long bases, windows, pos_windows;
+  unsigned long long err;    // min over bad sequences of (index << 32 | code); ~0 = none
+  uint32_t pad[8];
+};
+enum : uint32_t { kLiteErrCluster = 1, kLiteErrClusterOrder, kLiteErrSample, kLiteErrSampleOrder, kLiteErrPresence,
+                  kLiteErrAlign, kLiteErrPlane, kLiteErrStrand, kLiteErrAmbiguous, kLiteErrOrder };
+
+__global__ void __launch_bounds__(256)
+plan_from_raw(const pf_seq_desc* __restrict__ raw, uint32_t n, uint32_t cluster_base, uint64_t base_rebase,
+              uint32_t n_clusters, uint32_t S, uint32_t W, const uint32_t* __restrict__ presence,
+              uint64_t plane_bases, int k, uint32_t emit_positions, SeqDev* __restrict__ out,
+              SeqLite* __restrict__ lite, LiteTotals* __restrict__ tot) {
+  __shared__ unsigned long long s_sum[3][8];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long bases = 0, windows = 0, posw = 0;
+  if (i < n) {
+    const pf_seq_desc q = raw[i];
+    uint32_t err = 0;
+    const uint32_t cluster = q.cluster - cluster_base;
+    const uint64_t base_off = q.base_off - base_rebase;
+    if (q.cluster < cluster_base || cluster >= n_clusters) err = kLiteErrCluster;
+    else if (q.sample >= S) err = kLiteErrSample;
+    else if (!((presence[(size_t)cluster * W + (q.sample >> 5)] >> (q.sample & 31u)) & 1u)) err = kLiteErrPresence;
+    else if (q.base_off < base_rebase || (base_off & 63u)) err = kLiteErrAlign;
+    else if (base_off + q.len > plane_bases) err = kLiteErrPlane;
+    else if (q.strand != 1 && q.strand != -1) err = kLiteErrStrand;
+    else if (q.flags & PF_SEQ_AMBIGUOUS) err = kLiteErrAmbiguous;
+    else if (i) {
+      const pf_seq_desc p = raw[i - 1];
+      if (q.cluster < p.cluster) err = kLiteErrClusterOrder;
+      else if (q.cluster == p.cluster && q.sample < p.sample) err = kLiteErrSampleOrder;
+    }
+    if (err) {
+      atomicMin(&tot->err, ((unsigned long long)i << 32) | err);
+    } else {
+      const bool target = emit_positions && (q.flags & PF_SEQ_TARGET);
+      SeqDev d;
+      d.base_off = base_off; d.amb_off = 0; d.len = q.len; d.sample = q.sample; d.cluster = cluster;
+      d.flags = target ? 1u : 0u;
+      d.start = q.start; d.end = q.end; d.offset = q.offset; d.strand = q.strand;
+      d.rec_off = 0; d.pos_off = 0; d.wrec_off = 0; d.pwide_off = 0;
+      out[i] = d;
+      SeqLite l;
+      l.word_off = (uint32_t)(base_off >> 5); l.len = q.len; l.sample_flags = q.sample; l.amb_word_off = 0;
+      lite[i] = l;
+      const uint32_t nwin = q.len >= (uint32_t)k ? q.len - (uint32_t)k + 1u : 0u;
+      bases = q.len; windows = nwin; posw = target ? nwin : 0u;
+    }
+  }
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    bases += __shfl_xor_sync(kFull, bases, m);
+    windows += __shfl_xor_sync(kFull, windows, m);
+    posw += __shfl_xor_sync(kFull, posw, m);
+  }
+  if ((threadIdx.x & 31u) == 0) {
+    s_sum[0][threadIdx.x >> 5] = bases; s_sum[1][threadIdx.x >> 5] = windows; s_sum[2][threadIdx.x >> 5] = posw;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += s_sum[threadIdx.x][w];
+    if (t) atomicAdd(threadIdx.x == 0 ? &tot->bases : threadIdx.x == 1 ? &tot->windows : &tot->pos_windows, t);
+  }
+}
+
 // one warp per cluster: its sequence range (sequences are sorted by cluster), the
 // longest window count and from it the number of position blocks
 __global__ void plan_cluster_blocks(const SeqDev* __restrict__ seqs, uint32_t n_seqs, uint32_t n_clusters,

@@ -152,6 +152,17 @@ struct BatchState {
   // the slot's result arrays have left the device
   cudaEvent_t ev_up_done = nullptr, ev_exec_end = nullptr, ev_out_done = nullptr;
   PinBuf h_done;                 // pinned mirror of the batch's new k-mer pattern count (K4)
+  // device-side planning ("lite" upload, plan_from_raw): the caller's descriptors as uploaded, the
+  // totals the kernel computed, and what a later fall-back to the record engine needs to re-plan
+  // the batch on the host
+  bool lite = false;
+  DevBuf d_raw, d_lite_tot;
+  PinBuf h_raw, h_lite_tot;
+  std::vector<pf_cluster_desc> lite_clusters;
+  std::vector<uint32_t> lite_presence;
+  const pf_seq_desc* lite_src = nullptr;     // caller's descriptors of the sub-range (valid during the call)
+  uint32_t lite_c0 = 0;                      // rebasing of the sub-range (cluster index, first base)
+  uint64_t lite_b0 = 0;
 };
 
 
@@ -336,6 +347,7 @@ struct pf_ctx : BatchState {
   uint32_t pipe_min_seqs = 200000;   // batches with fewer sequences are not split
   uint32_t pipe_target_seqs = 262144;   // sequences per sub-batch
   uint32_t pipe_first_seqs = 98304;     // ... of the first one (its upload is not hidden)
+  bool lite_ok = true;           // device-side planning of uploads (PF_LITE=0 disables; off after a record fall-back)
 };
 
 namespace {

@@ -699,6 +699,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
         } else {
           blk = false;
           if (++ctx->block_fallbacks >= 2) ctx->block_mode = false;
+          TRY(replan_full(ctx));            // (a device-planned upload has no record offsets yet)
           TRY(ensure_records());
         }
         continue;

@@ -89,9 +89,172 @@ namespace {
 // [w0,w1) of the 2-bit plane and [a0,a1) of the 4-bit plane.
 struct SubRange { uint32_t s0, s1, c0, c1; uint64_t w0, w1, a0, a1; };
 
+// The per-sequence checks of an upload for ONE sequence of the (sub-)batch: the message the host
+// planner would give.  The lite upload validates on the device and calls this for the first bad index.
+std::string describe_bad_seq(const pf_ctx* ctx, const pf_batch* b, uint32_t i, uint32_t rc, uint64_t rb, uint64_t ra) {
+  const uint32_t S = ctx->prm.n_samples, W = ctx->W;
+  char buf[256];
+  pf_seq_desc q = b->seqs[i];
+  q.cluster -= rc; q.base_off -= rb; q.amb_off -= (q.flags & PF_SEQ_AMBIGUOUS) ? ra : 0;
+  auto f = [&](const char* fmt, uint32_t a1, uint32_t a2 = 0, uint32_t a3 = 0) { snprintf(buf, sizeof buf, fmt, a1, a2, a3); return std::string(buf); };
+  if (q.cluster >= b->n_clusters) return f("seq %u: cluster %u out of range", i, q.cluster);
+  if (i && q.cluster + rc < b->seqs[i - 1].cluster) return f("seq %u: clusters must be non-decreasing", i);
+  if (q.sample >= S) return f("seq %u: sample rank %u >= n_samples %u", i, q.sample, S);
+  if (i && q.cluster + rc == b->seqs[i - 1].cluster && q.sample < b->seqs[i - 1].sample)
+    return f("seq %u: sample ranks must be non-decreasing inside a cluster", i);
+  if (!((b->cluster_presence[(size_t)q.cluster * W + (q.sample >> 5)] >> (q.sample & 31)) & 1u))
+    return f("seq %u: sample %u is not marked present in cluster %u", i, q.sample, q.cluster);
+  if (q.base_off & 63u) return f("seq %u: base_off must be a multiple of 64", i);
+  if (q.base_off + q.len > b->n_words * 32ull) return f("seq %u: bases run past the packed plane", i);
+  if (q.strand != 1 && q.strand != -1) return f("seq %u: strand must be +1/-1", i);
+  if (q.flags & PF_SEQ_AMBIGUOUS) return f("seq %u is flagged ambiguous but the batch has no 4-bit plane", i);
+  return f("seq %u: malformed descriptor", i);
+}
+
+// ClusterDev of every cluster of the (sub-)batch: presence popcount, MAF window, filters folded in.
+// rec ranges stay zero unless `nr` / `wr` give them (record engines).
+int build_clusters(pf_ctx* ctx, const pf_batch* b, ClusterDev* hc, const std::pair<uint32_t, uint32_t>* nr,
+                   const std::pair<uint32_t, uint32_t>* wr) {
+  const pf_params& P = ctx->prm;
+  const uint32_t S = P.n_samples, W = ctx->W;
+  for (uint32_t c = 0; c < b->n_clusters; ++c) {
+    uint32_t np = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+      uint32_t word = b->cluster_presence[(size_t)c * W + w];
+      if (w == W - 1 && (S & 31u)) {
+        if (word >> (S & 31u)) return fail(ctx, PF_ERR_INVALID, "cluster %u: presence bits beyond n_samples", c);
+      }
+      np += (uint32_t)__builtin_popcount(word);
+    }
+    ClusterDev& d = hc[c];
+    d.rec_start = nr ? nr[c].first : 0; d.rec_end = nr ? nr[c].second : 0;
+    d.wrec_start = wr ? wr[c].first : 0; d.wrec_end = wr ? wr[c].second : 0;
+    d.id = b->clusters[c].id; d.n_present = np;
+    const uint32_t n = P.consider_missing ? np : S;
+    uint32_t lo, hi;
+    {
+      std::lock_guard<std::mutex> lk(ctx->maf_mu);
+      auto it = ctx->maf_cache.find(n);
+      if (it == ctx->maf_cache.end()) {
+        uint32_t wl, wh;
+        pf_maf_window(P.maf, n, &wl, &wh);
+        it = ctx->maf_cache.emplace(n, std::make_pair(wl, wh)).first;
+      }
+      lo = it->second.first; hi = it->second.second;
+    }
+    // "same as cluster" (panfeed.py:202-204): k-mer bits are a subset of the
+    // cluster's, so equality <=> count == n_present; NaN entries never compare equal.
+    if (P.cluster_equal_filter && (!P.consider_missing || np == S)) {
+      if (np == 0) { lo = 1; hi = 0; }
+      else hi = std::min(hi, np - 1);
+    }
+    if (lo == 0) lo = 1;                    // a k-mer row always has >= 1 sample
+    d.lo = lo; d.hi = hi;
+  }
+  return PF_OK;
+}
+
+// Lite upload: no per-sequence host work.  H2D of the packed plane and of the caller's descriptors
+// as they are, one device kernel validates and builds SeqDev / SeqLite and the totals
+// (plan_from_raw), then the block planning kernels.  upload_finish* reads the totals.
+int upload_async_lite(pf_ctx* ctx, BatchState& B, const pf_batch* b, uint32_t rc, uint64_t rb, cudaStream_t st) {
+  const pf_params& P = ctx->prm;
+  const uint32_t W = ctx->W, n = b->n_seqs, nc = b->n_clusters;
+  B.lite = true;
+  B.lite_src = b->seqs; B.lite_c0 = rc; B.lite_b0 = rb;
+  B.lite_clusters.assign(b->clusters, b->clusters + nc);
+  B.lite_presence.assign(b->cluster_presence, b->cluster_presence + (size_t)nc * W);
+  const size_t slack_words = 80;
+  TRY(dev_ensure(ctx, B.d_bases, (b->n_words + slack_words) * 8));
+  CU(cudaEventRecord(B.ev_h2d[0], st));
+  if (b->n_words) CU(cudaMemcpyAsync(B.d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync((char*)B.d_bases.p + b->n_words * 8, 0, slack_words * 8, st));
+  // descriptors: straight from the caller's array if it is pinned, else through the slot's pinned
+  // staging buffer (a plain copy on the planning threads; a pageable cudaMemcpyAsync would block)
+  TRY(dev_ensure(ctx, B.d_raw, (size_t)n * sizeof(pf_seq_desc)));
+  const void* src = b->seqs;
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, b->seqs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!pinned) {
+    cudaGetLastError();
+    TRY(pin_ensure(ctx, B.h_raw, (size_t)n * sizeof(pf_seq_desc)));
+    static const uint32_t host_thr = []() { const char* e = getenv("PF_HOST_THREADS"); const int v = e ? atoi(e) : 0;
+                                            return v > 0 ? (uint32_t)v : 8u; }();
+    const uint32_t n_thr = std::max(1u, std::min<uint32_t>(std::min(host_thr, std::thread::hardware_concurrency()),
+                                                           (n + 65535u) / 65536u));
+    const uint32_t per = (n + n_thr - 1) / n_thr;
+    char* dst = B.h_raw.as<char>();
+    const char* from = reinterpret_cast<const char*>(b->seqs);
+    ctx->pool.parallel(n_thr, [&](uint32_t t) {
+      const size_t i0 = std::min<size_t>(n, (size_t)t * per), i1 = std::min<size_t>(n, i0 + per);
+      memcpy(dst + i0 * sizeof(pf_seq_desc), from + i0 * sizeof(pf_seq_desc), (i1 - i0) * sizeof(pf_seq_desc));
+    });
+    src = dst;
+  }
+  CU(cudaMemcpyAsync(B.d_raw.p, src, (size_t)n * sizeof(pf_seq_desc), cudaMemcpyHostToDevice, st));
+  // clusters
+  TRY(pin_ensure(ctx, B.h_clusters, std::max<size_t>(1, nc) * sizeof(ClusterDev)));
+  TRY(build_clusters(ctx, b, B.h_clusters.as<ClusterDev>(), nullptr, nullptr));
+  TRY(dev_ensure(ctx, B.d_seqs, std::max<size_t>(1, n) * sizeof(SeqDev)));
+  TRY(dev_ensure(ctx, B.d_seq_lite, std::max<size_t>(1, n) * sizeof(SeqLite)));
+  TRY(dev_ensure(ctx, B.d_clusters, std::max<size_t>(1, nc) * sizeof(ClusterDev)));
+  TRY(dev_ensure(ctx, B.d_presence, std::max<size_t>(1, (size_t)nc * W) * 4));
+  TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4));
+  TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 64 * 4));
+  TRY(dev_ensure(ctx, B.d_lite_tot, sizeof(LiteTotals)));
+  TRY(pin_ensure(ctx, B.h_lite_tot, sizeof(LiteTotals)));
+  CU(cudaMemcpyAsync(B.d_clusters.p, B.h_clusters.p, (size_t)nc * sizeof(ClusterDev), cudaMemcpyHostToDevice, st));
+  // (the presence words come from the slot's own copy: the caller's array may be pageable)
+  CU(cudaMemcpyAsync(B.d_presence.p, B.lite_presence.data(), (size_t)nc * W * 4, cudaMemcpyHostToDevice, st));
+  CU(cudaMemsetAsync(B.d_lite_tot.p, 0, 24, st));
+  CU(cudaMemsetAsync((char*)B.d_lite_tot.p + 24, 0xff, 8, st));
+  plan_from_raw<<<cdiv(n, 256), 256, 0, st>>>(B.d_raw.as<pf_seq_desc>(), n, rc, rb, nc, P.n_samples, W,
+                                               B.d_presence.as<uint32_t>(), b->n_words * 32ull, (int)P.k,
+                                               P.emit_positions, B.d_seqs.as<SeqDev>(), B.d_seq_lite.as<SeqLite>(),
+                                               B.d_lite_tot.as<LiteTotals>());
+  ctx->launches++;
+  mirror_counters<<<1, 32, 0, st>>>(B.h_lite_tot.as<uint32_t>(), B.d_lite_tot.as<uint32_t>(), 16);
+  B.n_seqs = n; B.n_clusters = nc; B.n_wide_seqs = 0;
+  B.n_words = b->n_words; B.n_amb_words = 0;
+  B.n_bases = 0; B.n_pos = 0; B.n_pos_wide = 0;         // totals: upload_finish*
+  B.nar.n_records = 0; B.wid.n_records = 0;
+  B.nar.n_tiles = B.wid.n_tiles = 0; B.nar.n_ltiles = 0; B.nar.max_seg = B.wid.max_seg = 0;
+  B.nar.passes = B.wid.passes = 1; B.nar.sort_bits = B.wid.sort_bits = 8;
+  B.nar_ranges.clear();
+  CU(cudaEventRecord(B.ev_h2d[1], st));
+  TRY(plan_blocks(ctx, B, st, false));
+  CU(cudaEventRecord(B.ev_up_done, st));
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+
+// After the stream has passed a lite upload: errors and totals of plan_from_raw
+int lite_finish(pf_ctx* ctx, BatchState& B) {
+  if (!B.lite) return PF_OK;
+  const LiteTotals& t = *B.h_lite_tot.as<LiteTotals>();
+  if (t.err != ~0ull) {
+    const uint32_t i = (uint32_t)(t.err >> 32);
+    if (B.lite_src && i < B.n_seqs) {        // the host planner's message for that sequence
+      pf_batch v{};
+      v.seqs = B.lite_src; v.n_seqs = B.n_seqs; v.n_clusters = B.n_clusters; v.n_words = B.n_words;
+      v.cluster_presence = B.lite_presence.data();
+      return fail(ctx, PF_ERR_INVALID, "%s", describe_bad_seq(ctx, &v, i, B.lite_c0, B.lite_b0, 0).c_str());
+    }
+    return fail(ctx, PF_ERR_INVALID, "seq %u: malformed descriptor (check %u)", i, (uint32_t)t.err);
+  }
+  const uint64_t mult = ctx->prm.canonical ? 1u : 2u;
+  if (t.windows * mult >= (1ull << 32) - kSortTile) return fail(ctx, PF_ERR_INVALID, "batch holds more than 2^32 k-mer records; split it");
+  if (t.pos_windows >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "more than 2^32 positional records; split the batch");
+  B.n_bases = t.bases;
+  B.nar.n_records = (uint32_t)(t.windows * mult);
+  B.n_pos = (uint32_t)t.pos_windows;
+  return PF_OK;
+}
+
 // Validate + plan + H2D of the sub-range into the CURRENT batch slot, all asynchronous on `st`
 // (the caller's buffers must stay valid until `st` has passed).  upload_finish completes it.
-int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRange& r, cudaStream_t st) {
+int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRange& r, cudaStream_t st,
+                 bool force_full = false, bool have_bases = false) {
   const double t_dbg_in = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
   pf_batch view = *full;
   view.seqs = full->seqs ? full->seqs + r.s0 : nullptr;
@@ -110,10 +273,14 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
   B.executed = false;
   const pf_params& P = ctx->prm;
   const uint32_t k = P.k, S = P.n_samples, W = ctx->W;
-  if (b->n_seqs && (!b->seqs || !b->packed_bases)) return fail(ctx, PF_ERR_INVALID, "null seqs/packed_bases");
+  if (b->n_seqs && (!b->seqs || (!b->packed_bases && !have_bases))) return fail(ctx, PF_ERR_INVALID, "null seqs/packed_bases");
   if (b->n_clusters && (!b->clusters || !b->cluster_presence))
     return fail(ctx, PF_ERR_INVALID, "null clusters/cluster_presence");
   if (b->n_clusters == 0 && b->n_seqs) return fail(ctx, PF_ERR_INVALID, "sequences without clusters");
+  B.lite = false;
+  if (!force_full && ctx->lite_ok && ctx->block_mode && P.emit_positions != 1u && b->n_amb_words == 0 && b->n_seqs &&
+      b->n_words < (1ull << 32))
+    return upload_async_lite(ctx, B, b, rc, rb, st);
 
   TRY(pin_ensure(ctx, B.h_seqs, std::max<size_t>(1, b->n_seqs) * sizeof(SeqDev)));
   TRY(pin_ensure(ctx, B.h_clusters, std::max<size_t>(1, b->n_clusters) * sizeof(ClusterDev)));
@@ -127,8 +294,8 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
   const size_t slack_words = 80;
   TRY(dev_ensure(ctx, B.d_bases, (b->n_words + slack_words) * 8));
   CU(cudaEventRecord(B.ev_h2d[0], st));
-  if (b->n_words) CU(cudaMemcpyAsync(B.d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, st));
-  CU(cudaMemsetAsync((char*)B.d_bases.p + b->n_words * 8, 0, slack_words * 8, st));
+  if (b->n_words && !have_bases) CU(cudaMemcpyAsync(B.d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, st));
+  if (!have_bases) CU(cudaMemsetAsync((char*)B.d_bases.p + b->n_words * 8, 0, slack_words * 8, st));
 
   static const bool dbg_up = getenv("PF_DEBUG_PIPE") != nullptr;
   auto now_ms = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -230,40 +397,7 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
     }
   }
   const double t_dbg1 = now_ms();
-  for (uint32_t c = 0; c < b->n_clusters; ++c) {
-    uint32_t np = 0;
-    for (uint32_t w = 0; w < W; ++w) {
-      uint32_t word = b->cluster_presence[(size_t)c * W + w];
-      if (w == W - 1 && (S & 31u)) {
-        if (word >> (S & 31u)) return fail(ctx, PF_ERR_INVALID, "cluster %u: presence bits beyond n_samples", c);
-      }
-      np += (uint32_t)__builtin_popcount(word);
-    }
-    ClusterDev& d = hc[c];
-    d.rec_start = nr[c].first; d.rec_end = nr[c].second;
-    d.wrec_start = wr[c].first; d.wrec_end = wr[c].second;
-    d.id = b->clusters[c].id; d.n_present = np;
-    const uint32_t n = P.consider_missing ? np : S;
-    uint32_t lo, hi;
-    {
-      std::lock_guard<std::mutex> lk(ctx->maf_mu);
-      auto it = ctx->maf_cache.find(n);
-      if (it == ctx->maf_cache.end()) {
-        uint32_t wl, wh;
-        pf_maf_window(P.maf, n, &wl, &wh);
-        it = ctx->maf_cache.emplace(n, std::make_pair(wl, wh)).first;
-      }
-      lo = it->second.first; hi = it->second.second;
-    }
-    // "same as cluster" (panfeed.py:202-204): k-mer bits are a subset of the
-    // cluster's, so equality <=> count == n_present; NaN entries never compare equal.
-    if (P.cluster_equal_filter && (!P.consider_missing || np == S)) {
-      if (np == 0) { lo = 1; hi = 0; }
-      else hi = std::min(hi, np - 1);
-    }
-    if (lo == 0) lo = 1;                    // a k-mer row always has >= 1 sample
-    d.lo = lo; d.hi = hi;
-  }
+  TRY(build_clusters(ctx, b, hc, nr.data(), wr.data()));
 
   const double t_dbg2 = now_ms();
   B.n_seqs = b->n_seqs; B.n_clusters = b->n_clusters; B.n_wide_seqs = n_wide;
@@ -346,6 +480,7 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
 // Second half of an upload: wait for the copies and the planning kernels, read n_items back.
 int upload_finish(pf_ctx* ctx, BatchState& B, cudaStream_t up) {
   CU(cudaStreamSynchronize(up));
+  TRY(lite_finish(ctx, B));
   if (ctx->block_mode) TRY(plan_blocks_finish(ctx, B, up));
   CU(cudaStreamSynchronize(up));
   CU(cudaGetLastError());
@@ -357,10 +492,30 @@ int upload_finish(pf_ctx* ctx, BatchState& B, cudaStream_t up) {
 // stream, which runs the slot's kernels next.
 int upload_finish_slot(pf_ctx* ctx, BatchState& B, cudaStream_t compute) {
   CU(cudaEventSynchronize(B.ev_up_done));
+  TRY(lite_finish(ctx, B));
   if (ctx->block_mode) TRY(plan_blocks_finish(ctx, B, compute, false));
   CU(cudaGetLastError());
   B.have_batch = true;
   return PF_OK;
+}
+// A lite slot has to leave the block engine: plan it again on the host (record offsets, tile
+// lists) from the device copy of the caller's descriptors; the packed plane is already there.
+int replan_full(pf_ctx* ctx) {
+  BatchState& B = *ctx;
+  if (!B.lite) return PF_OK;
+  std::vector<pf_seq_desc> raw(B.n_seqs);
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (B.n_seqs) CU(cudaMemcpy(raw.data(), B.d_raw.p, (size_t)B.n_seqs * sizeof(pf_seq_desc), cudaMemcpyDeviceToHost));
+  for (auto& q : raw) { q.cluster -= B.lite_c0; q.base_off -= B.lite_b0; }
+  pf_batch v{};
+  v.n_words = B.n_words;
+  v.seqs = raw.data(); v.n_seqs = B.n_seqs;
+  v.clusters = B.lite_clusters.data(); v.n_clusters = B.n_clusters;
+  v.cluster_presence = B.lite_presence.data();
+  const SubRange r{0, B.n_seqs, 0, B.n_clusters, 0, B.n_words, 0, 0};
+  ctx->lite_ok = false;                     // this input does not suit the block engine: plan on the host from now on
+  TRY(upload_async(ctx, B, &v, r, ctx->stream, /*force_full=*/true, /*have_bases=*/true));
+  return upload_finish(ctx, B, ctx->stream);
 }
 }  // namespace
 

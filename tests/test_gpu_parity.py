@@ -410,3 +410,44 @@ def test_synthetic_device_batch_matches_oracle():
     assert got_rows == want_rows
     assert len(r["new_kmer_patterns"]) == len(want["kmer_pattern_bits"])
     assert st["unique_kmers"] == want["n_unique"]
+
+
+@pytest.mark.parametrize("lite", ["1", "0"])
+def test_malformed_batches_are_refused_with_the_same_message(lite, monkeypatch):
+    """Descriptor validation runs on the device for the block engine (plan_from_raw) and on the
+    host otherwise (PF_LITE=0): both must refuse a malformed batch, naming the first bad sequence
+    with the same message, and leave the context usable."""
+    from panfeed_b200 import capi
+    monkeypatch.setenv("PF_LITE", lite)
+    S, C, L, k = 40, 3, 200, 31
+    good = capi.synth_batch(0, 5, S, C, total_clusters=C, gene_len=L)
+    ctx = capi.Context(k, S, maf=0.01)
+    try:
+        cases = []
+        bad = capi.HostBatch(good.packed, good.seqs.copy(), good.clusters, good.presence.copy())
+        s = int(bad.seqs["sample"][7])
+        c = int(bad.seqs["cluster"][7])
+        bad.presence[c, s >> 5] &= ~np.uint32(1 << (s & 31))
+        cases.append((bad, f"seq 7: sample {s} is not marked present in cluster {c}"))
+        bad = capi.HostBatch(good.packed, good.seqs.copy(), good.clusters, good.presence)
+        bad.seqs["strand"][11] = 0
+        cases.append((bad, "seq 11: strand must be +1/-1"))
+        bad = capi.HostBatch(good.packed, good.seqs.copy(), good.clusters, good.presence)
+        bad.seqs["base_off"][5] += 32
+        cases.append((bad, "seq 5: base_off must be a multiple of 64"))
+        bad = capi.HostBatch(good.packed, good.seqs.copy(), good.clusters, good.presence)
+        bad.seqs["len"][len(bad.seqs) - 1] += 4096
+        cases.append((bad, f"seq {len(bad.seqs) - 1}: bases run past the packed plane"))
+        bad = capi.HostBatch(good.packed, good.seqs.copy(), good.clusters, good.presence)
+        j = int(np.nonzero(bad.seqs["cluster"] == 1)[0][3])       # a sequence inside cluster 1 claims cluster 0
+        bad.seqs["cluster"][j] = 0
+        cases.append((bad, f"seq {j}: clusters must be non-decreasing"))
+        for hb, msg in cases:
+            with pytest.raises(capi.PfError) as e:
+                ctx.submit(hb)
+            assert msg in str(e.value), (msg, str(e.value))
+        ctx.submit(good)
+        r = ctx.collect()
+        assert len(r["row_cluster"]) > 0
+    finally:
+        ctx.close()
