@@ -255,59 +255,61 @@ struct BlkPlan {
   const uint4* item_desc;        // [n_items * n_slices] {first seq, end seq (absolute), first window, cluster}
 };
 
-// Shared memory of kA.
+// Shared memory of kA.  Both tables hand out DENSE row ids on insertion and the inserting
+// thread clears its row before publishing the id, so nothing but the (small) key / state
+// arrays is initialised per block and the epilogue needs no compaction pass.
 //
 // chunk table: the R = k + 15 bases that the 16 windows of a run cover, as a 128-bit key
-//   (top-aligned; the number of valid windows of a ragged run sits in the 5 low bits, which the
-//   94 base bits never reach).  Sequences of a cluster are copies of a few haplotypes, so the ~500
-//   sequences of a run collapse into a few dozen distinct chunks, each with one sample bitset
-//   (crows).  A slot's state word goes empty -> locked -> (full | chunk id); chunk ids are dense.
-// k-mer rows: NO hash table.  Level 2 takes the distinct chunks 32 at a time, one window offset q
-//   per warp iteration: lane c holds the k-mer of chunk c at offset q, `match.any` groups the
-//   lanes holding the same k-mer, `redux.or` over each group ORs the chunks' bitsets word by
-//   word, and the lowest lane of a group writes the finished row (key, W words) to a dense row
-//   it took from a counter - one shared-memory atomic per warp iteration instead of a
-//   find-or-insert per k-mer, no divergent probing, and no row has to be cleared beforehand.
-//   The same k-mer at two window offsets, or in two 32-chunk tiles, simply gives two partial
-//   rows: kB merges partial rows by key anyway (that is how k-mers that start in two runs meet).
+//   (top-aligned).  Sequences of a cluster are copies of a few haplotypes, so the ~500
+//   sequences of a run collapse into a few dozen distinct chunks; only those are cut into
+//   k-mers.  A slot's state word goes empty -> locked -> (full | chunk id).
+// k-mer table: 64-bit keys claimed with one CAS; rowid[slot] is published afterwards
+//   (0xffff = not yet), readers of a freshly claimed slot spin for those few cycles.
 constexpr uint32_t kChunkEmpty = 0u, kChunkLocked = 1u, kChunkFull = 0x80000000u;
 struct ARunView {
   BlkHead* h;              // n_unique = k-mer rows handed out, work = chunk ids handed out
-  uint64_t* rkey;          // [cap + 1]   key of row id (row `cap`: scratch of an overflowing block)
+  uint64_t* keys;          // [slots]
+  uint64_t* rkey;          // [cap + 1]   key of row id
   uint64_t* ckhi;          // [ccap]
   uint64_t* cklo;          // [ccap]
   uint32_t* cstate;        // [cslots]
-  uint32_t* pool;          // [(cap + 1) * WS]
+  uint32_t* pool;          // [(cap + 1) * WS]   row `cap` takes the ORs of an overflowing block
   uint32_t* crows;         // [ccap * WS]
-  uint32_t cmask, cshift, cap, ccap;
+  uint16_t* rowid;         // [slots]
+  uint16_t* cmeta;         // [ccap]  low byte: bitset word of the chunk's first sample; bit 15: other words too
+  uint32_t mask, shift, cmask, cshift, cap, ccap;
 };
 __host__ __device__ inline uint32_t blkA_ccap(uint32_t cslots) { return cslots * 3u / 4u; }
-// cap: k-mer rows; cslots: chunk slots (power of two).  (`slots` is what the k-mer hash table of
-// earlier versions took; it only scales the row budget now.)
-__host__ __device__ inline uint32_t blkA_smem_bytes(uint32_t /*slots*/, uint32_t cap, uint32_t cslots, uint32_t W) {
+// slots: k-mer key slots (power of two); cap: k-mer rows (<= 13/16 slots); cslots: chunk slots
+__host__ __device__ inline uint32_t blkA_smem_bytes(uint32_t slots, uint32_t cap, uint32_t cslots, uint32_t W) {
   const uint32_t ccap = blkA_ccap(cslots), WS = W | 1u;
-  return (uint32_t)sizeof(BlkHead) + (cap + 1u) * 8u + ccap * 16u + cslots * 4u +
-         (cap + 1u) * WS * 4u + ccap * WS * 4u + 16u;
+  return (uint32_t)sizeof(BlkHead) + slots * 8u + (cap + 1u) * 8u + ccap * 16u + cslots * 4u +
+         (cap + 1u) * WS * 4u + ccap * WS * 4u + slots * 2u + ccap * 2u + 16u;
 }
-__device__ __forceinline__ ARunView arun_view(unsigned char* raw, uint32_t cap, uint32_t cslots, uint32_t W) {
+__device__ __forceinline__ ARunView arun_view(unsigned char* raw, uint32_t slots, uint32_t cap, uint32_t cslots, uint32_t W) {
   ARunView a;
   const uint32_t WS = W | 1u;
   a.cap = cap;
   a.ccap = blkA_ccap(cslots);
   a.h = reinterpret_cast<BlkHead*>(raw);
-  a.rkey = reinterpret_cast<uint64_t*>(raw + sizeof(BlkHead));
+  a.keys = reinterpret_cast<uint64_t*>(raw + sizeof(BlkHead));
+  a.rkey = a.keys + slots;
   a.ckhi = a.rkey + (a.cap + 1u);
   a.cklo = a.ckhi + a.ccap;
   a.cstate = reinterpret_cast<uint32_t*>(a.cklo + a.ccap);
   a.pool = a.cstate + cslots;
   a.crows = a.pool + (a.cap + 1u) * WS;
+  a.rowid = reinterpret_cast<uint16_t*>(a.crows + a.ccap * WS);
+  a.cmeta = a.rowid + slots;
+  a.mask = slots - 1u;
+  a.shift = 32u - (uint32_t)__popc(a.mask);
   a.cmask = cslots - 1u;
   a.cshift = 32u - (uint32_t)__popc(a.cmask);
   return a;
 }
 // chunk id of (hi, lo); 0xffffffff if the chunk table is full (the caller then cuts the run
 // into k-mers itself)
-__device__ __noinline__ uint32_t chunk_find_or_insert(const ARunView a, uint64_t hi, uint64_t lo) {
+__device__ __noinline__ uint32_t chunk_find_or_insert(const ARunView a, uint64_t hi, uint64_t lo, uint32_t wofs) {
   const uint64_t m = (hi ^ (hi >> 29)) * 0x9e3779b97f4a7c15ULL + (lo ^ (lo >> 31)) * 0xc2b2ae3d27d4eb4fULL;
   uint32_t s = (uint32_t)(m >> 32) >> a.cshift;
   uint32_t spins = 0;
@@ -329,6 +331,7 @@ __device__ __noinline__ uint32_t chunk_find_or_insert(const ARunView a, uint64_t
           *reinterpret_cast<volatile uint32_t*>(&a.cstate[s]) = kChunkEmpty;
           return 0xffffffffu;
         }
+        a.cmeta[id] = (uint16_t)wofs;
         *reinterpret_cast<volatile uint64_t*>(&a.ckhi[id]) = hi;
         *reinterpret_cast<volatile uint64_t*>(&a.cklo[id]) = lo;
         __threadfence_block();
@@ -341,6 +344,35 @@ __device__ __noinline__ uint32_t chunk_find_or_insert(const ARunView a, uint64_t
     __nanosleep(20);                          // (lets the owner run if it is a lane of this warp)
   }
   return 0xffffffffu;
+}
+// row id of a k-mer (insert if new); a.cap = the scratch row when the block overflows
+__device__ __noinline__ uint32_t kmer_row_slow(const ARunView a, uint64_t key, uint32_t h, uint32_t WS) {
+  const uint32_t limit = min(a.mask, 96u);
+  bool found = false;
+  for (uint32_t probes = 0; probes < limit; ++probes) {
+    uint64_t cur = *reinterpret_cast<const volatile uint64_t*>(&a.keys[h]);
+    if (cur == ~0ull) {
+      cur = atomicCAS(reinterpret_cast<unsigned long long*>(&a.keys[h]), ~0ull, (unsigned long long)key);
+      if (cur == ~0ull) {                                     // this thread owns the new slot
+        uint32_t id = atomicAdd(&a.h->n_unique, 1u);
+        if (id >= a.cap) { a.h->overflow = 1u; id = a.cap; }
+        a.rkey[id] = key;
+        __threadfence_block();
+        *reinterpret_cast<volatile uint16_t*>(&a.rowid[h]) = (uint16_t)id;
+        return id;
+      }
+    }
+    if (cur == key) { found = true; break; }
+    h = (h + 1u) & a.mask;
+  }
+  if (!found) { a.h->overflow = 1u; return a.cap; }
+  for (uint32_t spins = 0; spins < (1u << 14); ++spins) {
+    const uint32_t id = *reinterpret_cast<const volatile uint16_t*>(&a.rowid[h]);
+    if (id != 0xffffu) return id;
+    __nanosleep(20);                          // (lets the owner run if it is a lane of this warp)
+  }
+  a.h->overflow = 1u;
+  return a.cap;
 }
 
 #ifndef PF_KA_MIN_CTAS
@@ -358,8 +390,8 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
                    uint32_t* __restrict__ rescue_items /* out: items whose table overflowed */) {
   extern __shared__ __align__(16) unsigned char blk_raw[];
   const uint32_t W = plan.W, WS = W | 1u;
-  const ARunView a = arun_view(blk_raw, plan.cap, plan.cslots, W);
-  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const ARunView a = arun_view(blk_raw, plan.slots, plan.cap, plan.cslots, W);
+  const uint32_t tid = threadIdx.x;
   const uint32_t item = item_list ? item_list[blockIdx.x] : blockIdx.x;
 
   const uint4 desc = __ldg(plan.item_desc + item);
@@ -373,8 +405,11 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
   uint4 raw_first = make_uint4(0, 0, 0, 0);
   if (seq_lo + tid < seq_hi) raw_first = __ldg(reinterpret_cast<const uint4*>(seqs + seq_lo + tid));
 
-  // only the chunk table needs initialising: k-mer rows are written in full by whoever takes them
+  for (uint32_t i = tid; i < plan.slots; i += kBlkThreads) { a.keys[i] = ~0ull; a.rowid[i] = 0xffffu; }
   for (uint32_t i = tid; i < plan.cslots; i += kBlkThreads) a.cstate[i] = kChunkEmpty;
+  // all bitset rows are cleared here by the whole CTA: a lone inserting lane clearing its own
+  // row costs a warp instruction per word
+  for (uint32_t i = tid; i < (a.cap + 1u) * WS; i += kBlkThreads) a.pool[i] = 0u;
   for (uint32_t i = tid; i < a.ccap * WS; i += kBlkThreads) a.crows[i] = 0u;
   if (tid == 0) { a.h->n_unique = 0; a.h->overflow = 0; a.h->work = 0; a.h->n_pass = 0; }
   uint64_t wf0 = 0, wf1 = 0, wf2 = 0;
@@ -385,19 +420,32 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
   __syncthreads();
 
   const uint32_t sh64 = 64u - 2u * (uint32_t)k;
+  const uint32_t R = (uint32_t)k + (uint32_t)kBlkRun - 1u;      // bases a full run covers (<= 47)
+  // top-aligned masks of the R bases
+  const uint64_t cm_hi = R >= 32u ? ~0ull : (~0ull << (64u - 2u * R));
+  const uint64_t cm_lo = R > 32u ? (~0ull << (64u - 2u * (R - 32u))) : 0ull;
 
-  // one k-mer instance that goes no chunk's way (N/IUPAC sequences, a full chunk table): a row of
-  // its own with one sample bit (kB merges it with the other rows of its k-mer)
-  auto put_single = [&](uint64_t key, uint32_t wofs, uint32_t bit) {
-    uint32_t id = atomicAdd(&a.h->n_unique, 1u);
-    if (id >= a.cap) { a.h->overflow = 1u; id = a.cap; }
-    a.rkey[id] = key;
-    uint32_t* dst = a.pool + id * WS;
-    for (uint32_t w = 0; w < W; ++w) dst[w] = w == wofs ? bit : 0u;
+  // one k-mer (in the low 2k bits) -> row, OR `nw` words starting at src into it
+  auto put_bits = [&](uint64_t key, const uint32_t* src, uint32_t first_word, uint32_t nw) {
+    const uint32_t h = blk_hash((uint32_t)(key >> 32), (uint32_t)key, a.shift);
+    uint32_t id = 0xffffu;
+    if (*reinterpret_cast<const volatile uint64_t*>(&a.keys[h]) == key)
+      id = *reinterpret_cast<const volatile uint16_t*>(&a.rowid[h]);
+    if (id == 0xffffu) id = kmer_row_slow(a, key, h, WS);
+    uint32_t* dst = a.pool + id * WS + first_word;
+    for (uint32_t w = 0; w < nw; ++w) {
+      const uint32_t x = src[w];
+      if (x) atomicOr(dst + w, x);
+    }
+  };
+  auto put_kmer = [&](uint64_t fwd, const uint32_t* src, uint32_t first_word, uint32_t nw) {
+    const uint64_t rc = revcomp2(fwd, k);
+    if (CANON) put_bits(rc < fwd ? rc : fwd, src, first_word, nw);
+    else { put_bits(fwd, src, first_word, nw); put_bits(rc, src, first_word, nw); }
   };
 
-  // ---- phase 1: every sequence's run -> chunk table (or, for ambiguous runs and a full chunk
-  //      table, straight into rows of their own) ----------------------------------------------
+  // ---- phase 1: every sequence's run -> chunk table (or, for ragged / ambiguous runs and a
+  //      full chunk table, straight into the k-mer table) ------------------------------------
   for (uint32_t si = seq_lo + tid; si < seq_hi; si += kBlkThreads) {
     const bool first = si == seq_lo + tid;
     const uint4 raw = first ? raw_first : __ldg(reinterpret_cast<const uint4*>(seqs + si));
@@ -419,15 +467,11 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
       lo = (w1 << (2u * o0)) | (w2 >> (64u - 2u * o0));
     }
     uint32_t cs = 0xffffffffu;
-    if (!amb) {
-      // the nb = nv + k - 1 bases the run's windows cover, the rest masked off; nv in the low bits
-      const uint32_t nb = nv + (uint32_t)k - 1u;
-      const uint64_t m_hi = nb >= 32u ? ~0ull : (~0ull << (64u - 2u * nb));
-      const uint64_t m_lo = nb > 32u ? (~0ull << (64u - 2u * (nb - 32u))) : 0ull;
-      cs = chunk_find_or_insert(a, hi & m_hi, (lo & m_lo) | (uint64_t)nv);
-    }
+    if (nv == (uint32_t)kBlkRun && !amb) cs = chunk_find_or_insert(a, hi & cm_hi, lo & cm_lo, wofs);
     if (cs != 0xffffffffu) {
       atomicOr(&a.crows[cs * WS + wofs], bit);
+      const uint16_t meta = a.cmeta[cs];            // most chunks are one sample's: remember if not
+      if ((meta & 0xffu) != wofs && !(meta & 0x8000u)) a.cmeta[cs] = meta | 0x8000u;
     } else {
       const uint32_t* ab = amb ? ambbits + raw.w : nullptr;
       for (uint32_t q = 0; q < nv; ++q) {
@@ -440,60 +484,33 @@ kA_block_aggregate(const uint64_t* __restrict__ bases, const uint32_t* __restric
         }
         if (!dead) {
           const uint64_t x = q ? ((hi << (2u * q)) | (lo >> (64u - 2u * q))) : hi;
-          const uint64_t fwd = x >> sh64, rc = revcomp2(fwd, k);
-          if (CANON) put_single(rc < fwd ? rc : fwd, wofs, bit);
-          else { put_single(fwd, wofs, bit); put_single(rc, wofs, bit); }
+          put_kmer(x >> sh64, &bit, wofs, 1u);
         }
       }
     }
   }
   __syncthreads();
 
-  // ---- phase 2: distinct chunks x 16 window offsets -> k-mer rows.  A warp takes one window
-  //      offset q at a time and the chunks 32 at a time: lanes holding the same k-mer form a
-  //      group (match.any), the group ORs its chunks' bitsets (redux.or), its lowest lane
-  //      writes the row. ----------------------------------------------------------------------
+  // ---- phase 2: distinct chunks x 16 windows -> k-mer table, whole sample bitsets at a time ----
   const uint32_t n_chunks = min(a.h->work, a.ccap);
-  constexpr uint32_t kRowsPerKmer = CANON ? 1u : 2u;
-  for (uint32_t q = warp; q < (uint32_t)kBlkRun; q += (uint32_t)kBlkWarps) {
-    for (uint32_t c0 = 0; c0 < n_chunks; c0 += 32u) {
-      const uint32_t c = c0 + lane;
-      const bool in = c < n_chunks;
-      const uint64_t hi = in ? a.ckhi[c] : 0ull, lo = in ? a.cklo[c] : 0ull;
-      const bool valid = in && q < ((uint32_t)lo & 31u);           // (a ragged run has fewer windows)
+  const uint32_t n_pairs = n_chunks * (uint32_t)kBlkRun;
+  // pairs cost very different amounts (a new k-mer is an insertion, a many-sample chunk ORs W
+  // words): the first round is static, after it the warps take 32 pairs at a time from a counter
+  for (uint32_t p0 = (tid & ~31u);;) {
+    const uint32_t p = p0 + (tid & 31u);
+    if (p < n_pairs) {
+      const uint32_t cs = p >> 4, q = p & 15u;
+      const uint64_t hi = a.ckhi[cs], lo = a.cklo[cs];
       const uint64_t x = q ? ((hi << (2u * q)) | (lo >> (64u - 2u * q))) : hi;
-      const uint64_t fwd = x >> sh64, rc = revcomp2(fwd, k);
-      const uint64_t key = (CANON && rc < fwd) ? rc : fwd;
-      const uint32_t vm = __ballot_sync(kFull, valid);
-      if (vm == 0u) continue;
-      uint32_t m = __match_any_sync(kFull, key) & vm;
-      if (!valid) m = 1u << lane;                                    // a group of its own, contributing nothing
-      const bool leader = valid && (uint32_t)(__ffs(m) - 1) == lane;
-      const uint32_t lm = __ballot_sync(kFull, leader);
-      const uint32_t n_rows = (uint32_t)__popc(lm) * kRowsPerKmer;
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&a.h->n_unique, n_rows);
-      base = __shfl_sync(kFull, base, 0);
-      uint32_t row = base + (uint32_t)__popc(lm & lanemask_lt()) * kRowsPerKmer;
-      if (base + n_rows > a.cap) {                                   // does not fit: the block is rerun with more rows
-        if (lane == 0) a.h->overflow = 1u;
-        row = a.cap;                                                 // (scratch row; its content is never read)
-      }
-      const uint32_t row2 = (CANON || row == a.cap) ? row : row + 1u;
-      const uint32_t* src = a.crows + c * WS;
-      for (uint32_t w = 0; w < W; ++w) {
-        const uint32_t v = valid ? src[w] : 0u;
-        const uint32_t r = __reduce_or_sync(m, v);
-        if (leader) {
-          a.pool[row * WS + w] = r;
-          if (!CANON) a.pool[row2 * WS + w] = r;
-        }
-      }
-      if (leader) {
-        a.rkey[row] = key;
-        if (!CANON) a.rkey[row2] = rc;
-      }
+      const uint16_t meta = a.cmeta[cs];
+      if (meta & 0x8000u) put_kmer(x >> sh64, a.crows + cs * WS, 0u, W);
+      else put_kmer(x >> sh64, a.crows + cs * WS + (meta & 0xffu), meta & 0xffu, 1u);
     }
+    __syncwarp();
+    uint32_t nx = 0;
+    if ((tid & 31u) == 0u) nx = atomicAdd(&a.h->n_pass, 32u);
+    p0 = (uint32_t)kBlkThreads + __shfl_sync(kFull, nx, 0);
+    if (p0 >= n_pairs) break;
   }
   __syncthreads();
 

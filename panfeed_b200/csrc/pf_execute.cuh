@@ -649,21 +649,24 @@ extern "C" int pf_execute(pf_ctx* ctx) {
         const uint32_t first_rescue = hcnt[C_LOCAL + LC_RESCUE];
         while (hcnt[C_LOCAL + LC_TABLE_OVERFLOW] == 1u) {
           const uint32_t n_resc = hcnt[C_LOCAL + LC_RESCUE];
-          // twice the rows, and twice the chunk slots so that the chunk level keeps absorbing the
-          // sequences (a run that spills past the chunk table pays one row per window and sequence);
-          // past what shared memory holds: all the rows the current chunk table leaves room for
-          const uint32_t per_row = 8u + (ctx->Ws | 1u) * 4u;
-          auto fit_rows = [&](uint32_t cs) -> uint32_t {
-            const uint32_t fixed = blkA_smem_bytes(0u, 0u, cs, ctx->Ws);
-            return fixed + per_row < kBlkMaxSmem ? (kBlkMaxSmem - fixed) / per_row - 1u : 0u;
-          };
-          uint32_t slots2 = slots * 2u, cslots2 = std::min<uint32_t>(cslots * 2u, 1024u);
-          uint32_t cap2 = std::min<uint32_t>(fit_rows(cslots2), cap * 2u);
-          if (cap2 <= cap) { cslots2 = cslots; slots2 = slots; cap2 = fit_rows(cslots); }
+          // twice the key slots, as many rows as then fit (the chunk table stays: a full one only
+          // sends runs down the direct path)
+          uint32_t slots2 = slots * 2u, cap2 = 0;
+          if (slots2 <= 8192u && blkA_smem_bytes(slots2, 0u, cslots, ctx->Ws) < kBlkMaxSmem) {
+            const uint32_t per_row = 8u + (ctx->Ws | 1u) * 4u;
+            const uint32_t fit = (kBlkMaxSmem - blkA_smem_bytes(slots2, 0u, cslots, ctx->Ws)) / per_row;
+            cap2 = std::min<uint32_t>(std::min<uint32_t>(fit, slots2 * 13u / 16u),
+                                      std::max<uint32_t>(cap * 2u, slots2 * 5u / 8u));
+          }
+          if (cap2 <= cap) {        // no more rows with more slots: try all the rows the current slots allow
+            slots2 = slots;
+            const uint32_t per_row = 8u + (ctx->Ws | 1u) * 4u;
+            const uint32_t fit = (kBlkMaxSmem - blkA_smem_bytes(slots, 0u, cslots, ctx->Ws)) / per_row;
+            cap2 = std::min<uint32_t>(fit, slots * 13u / 16u);
+          }
           if (cap2 <= cap) { too_big = true; break; }
           slots = slots2;
           cap = cap2;
-          cslots = cslots2;
           CU(cudaMemsetAsync(counters + C_LOCAL + LC_TABLE_OVERFLOW, 0, 4, st));
           CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));
           TRY(launch_block_aggregate(ctx, ctx->d_rescue[cur].as<uint32_t>(), n_resc, slots, cap, cslots,
