@@ -654,7 +654,8 @@ def run_streamed(cfg, env, args, passes=1):
         res[mode] = tot
     engine = ctx.stats()["engine"]
     ctx.close()
-    del arena
+    del arena, exch
+    torch.cuda.empty_cache()        # the exchange buffers of this config (torch's caching allocator)
     out = {"workload": workload_config(cfg, env.world), "n_gpus": env.world, "scaling": cfg["scaling"],
            "batches_per_gpu": n_b, "clusters_per_batch": cfg["batch"], "passes": passes,
            "engine": {0: "records (partition mode)", 1: "records (full sort)", 2: "block aggregation"}[engine]}
@@ -721,6 +722,18 @@ def main():
     if args.impl == "reference":
         run_reference(args)
         return
+    # stdout carries ONE JSON line: everything libraries print there (NCCL's version banner comes
+    # from C code, whatever NCCL_DEBUG_FILE says) goes to stderr until the line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     env = Env()
     torch, dist = env.torch, env.dist
     from panfeed_b200 import capi
@@ -758,7 +771,7 @@ def main():
                         "value": e2e["bases_per_s"], "unit": "bases/s", "ms_per_step": e2e["ms"],
                         "h2d_bytes_per_step": e2e["h2d_bytes"], "d2h_bytes_per_step": e2e["d2h_bytes"]},
                     "roofline": None, "exchange_selfcheck": selfcheck, "affinity": env.affinity}
-            print(json.dumps(line))
+            emit(line)
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -888,7 +901,7 @@ def main():
             line["extra_configs"] = extra
         if not args.no_cpu_baseline and world == 1:      # reported at N = 1 only
             line["cpu_baseline"] = cpu_baseline_c(hb, S, k, cfg["maf"], cfg["cm"], args.cpu_seconds)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -365,7 +365,9 @@ int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace,
                       const uint32_t* recv_words_dev, uint64_t n_recv,
                       uint32_t* recv_unique_index_dev,
                       uint32_t* n_unique_dev /* one word, may be NULL */,
-                      uint64_t* n_unique_host /* may be NULL: then the call does not synchronise */);
+                      uint64_t* n_unique_host /* may be NULL: then the call does not synchronise */,
+                      uint32_t keep_unique_keys /* 1: keep the owner-side unique keys (n_unique x words
+                                                   of device memory) for pf_exchange_unique_export */);
 int pf_exchange_unique_count(pf_ctx* ctx, int cluster_namespace, uint64_t* n_unique_host);
 int pf_exchange_unique_export(pf_ctx* ctx, int cluster_namespace,
                               uint32_t* host_out /* n_unique x words */);

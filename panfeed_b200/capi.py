@@ -205,7 +205,7 @@ def load():
     lib.pf_synth_plan.argtypes = [C.POINTER(SynthParams), C.POINTER(u32), C.POINTER(u64)]
     lib.pf_synth_fill.argtypes = [C.c_int, C.POINTER(SynthParams), vp, vp, vp, vp]
     lib.pf_exchange_pack.argtypes = [vp, C.c_int, u32, vp, vp, u64, C.POINTER(u64)]
-    lib.pf_exchange_dedup.argtypes = [vp, C.c_int, vp, u64, vp, vp, C.POINTER(u64)]
+    lib.pf_exchange_dedup.argtypes = [vp, C.c_int, vp, u64, vp, vp, C.POINTER(u64), u32]
     lib.pf_exchange_unique_count.argtypes = [vp, C.c_int, C.POINTER(u64)]
     lib.pf_exchange_unique_export.argtypes = [vp, C.c_int, vp]
     lib.pf_exchange_unpack.argtypes = [vp, C.c_int, vp, vp, vp, vp]

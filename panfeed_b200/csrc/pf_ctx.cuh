@@ -87,6 +87,11 @@ struct PoolBuf : DevBuf {
   CUdeviceptr base = 0;
   size_t reserved = 0;
   std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
+  // growth ahead of need on the context's grower thread (mapping memory costs 10-30 ms in a process
+  // with NCCL peers): `cap` is what the calling thread may use, `growing` marks a mapping in flight
+  // that raises it when joined
+  bool growing = false;
+  size_t grown_cap = 0;
 };
 
 struct PatternSpace {
@@ -98,6 +103,7 @@ struct PatternSpace {
   // exchange state
   DevBuf x_owner, x_pos, x_perm, x_counts, x_unique, x_table, x_rep, x_slot, x_winner;
   uint64_t x_n_unique = 0;
+  bool x_have_unique = false;           // x_unique holds the owner-side unique keys of the last exchange
   bool x_unique_pending = false;        // x_n_unique still sits in the pinned mirror below
   const uint32_t* x_unique_mirror = nullptr;
 };
@@ -280,6 +286,7 @@ struct pf_ctx : BatchState {
   std::mutex maf_mu;       // the upload helper thread of the pipelined submit shares the cache
   WorkerPool pool;         // planning threads
   AsyncWorker uploader;    // enqueues the uploads of the pipelined submit
+  AsyncWorker grower;      // maps more memory behind a pattern pool before it is needed
 
   BatchState alt, alt2;    // the other batch slots (pipelined submit)
   DevBuf d_counters;       // u32[C_COUNT]: tickets, n_runs, errors, totals
@@ -433,7 +440,7 @@ const VmmApi& vmm_api() {
   return api;
 }
 
-void pool_free(PoolBuf& b) {
+void pool_free(PoolBuf& b) {          // (the context's grower thread has been joined)
   if (b.vmm) {
     const VmmApi& api = vmm_api();
     size_t off = 0;
@@ -447,54 +454,97 @@ void pool_free(PoolBuf& b) {
   b.p = nullptr; b.cap = 0;
 }
 
-// grow a pattern pool to at least `bytes`, keeping its contents (and, with VMM, its address)
+// map physical memory behind a VMM pool up to `want` bytes (rounded up); *cap_out = the new size.
+// Touches nothing below the current end, so it may run while kernels use the pool.
+int pool_map_to(pf_ctx* ctx, PoolBuf& b, size_t cur_cap, size_t want, size_t floor_bytes, size_t* cap_out) {
+  const VmmApi& api = vmm_api();
+  CUmemAllocationProp prop{};
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = ctx->device;
+  size_t gran = 0;
+  if (api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || gran == 0) return PF_ERR_CUDA;
+  want = std::min((want + gran - 1) / gran * gran, b.reserved);
+  floor_bytes = (floor_bytes + gran - 1) / gran * gran;
+  if (floor_bytes > b.reserved) return PF_ERR_NOMEM;
+  CUmemGenericAllocationHandle h = 0;
+  CUresult r = want > cur_cap ? api.create(&h, want - cur_cap, &prop, 0) : CUDA_ERROR_INVALID_VALUE;
+  if (r != CUDA_SUCCESS && floor_bytes > cur_cap && floor_bytes < want) {     // no room for the generous step: the exact one
+    want = floor_bytes;
+    r = api.create(&h, want - cur_cap, &prop, 0);
+  }
+  if (r != CUDA_SUCCESS) return PF_ERR_NOMEM;
+  const size_t got = want - cur_cap;
+  CUmemAccessDesc acc{};
+  acc.location = prop.location;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (api.map(b.base + cur_cap, got, 0, h, 0) != CUDA_SUCCESS || api.set_access(b.base + cur_cap, got, &acc, 1) != CUDA_SUCCESS) {
+    api.release(h);
+    return PF_ERR_CUDA;
+  }
+  b.chunks.emplace_back(h, got);
+  *cap_out = want;
+  return PF_OK;
+}
+
+// a growth started ahead of need has to be over before the pool's size is looked at again
+void pool_join(pf_ctx* ctx, PoolBuf& b) {
+  if (!b.growing) return;
+  ctx->grower.join();
+  b.growing = false;
+  if (b.grown_cap > b.cap) b.cap = b.grown_cap;
+}
+
+// grow a pattern pool to at least `bytes`, keeping its contents (and, with VMM, its address).
+// Sizes double (from 256 MB), and once more than half of a pool is in use the next doubling is
+// mapped on the grower thread while the kernels run.
 int pool_ensure(pf_ctx* ctx, PoolBuf& b, size_t bytes) {
-  if (bytes <= b.cap) return PF_OK;
+  constexpr size_t kMinStep = (size_t)256 << 20;
+  // doubling up to 4 GB, then a quarter at a time: the exchange of a sharded run needs room for
+  // two more copies of every pattern next to the pool
+  auto grow_step = [](size_t cap) { return cap < ((size_t)4 << 30) ? cap : std::max<size_t>((size_t)2 << 30, cap / 4); };
+  auto prefetch = [&]() {
+    if (!b.vmm || b.growing || b.cap < kMinStep || bytes <= b.cap / 2 || b.cap >= b.reserved) return;
+    const size_t cur = b.cap, want = cur + grow_step(cur);
+    b.growing = true;
+    b.grown_cap = cur;
+    ctx->grower.start([ctx, &b, cur, want]() {
+      cudaSetDevice(ctx->device);
+      size_t got = cur;
+      if (pool_map_to(ctx, b, cur, want, cur, &got) == PF_OK) b.grown_cap = got;
+    });
+  };
+  if (bytes <= b.cap) { prefetch(); return PF_OK; }
+  pool_join(ctx, b);
+  if (bytes <= b.cap) { prefetch(); return PF_OK; }
   const VmmApi& api = vmm_api();
   if (debug_alloc()) fprintf(stderr, "[pf] alloc: pattern pool %zu -> %zu bytes\n", b.cap, bytes);
   if (api.ok && (b.vmm || !b.p)) {
-    CUmemAllocationProp prop{};
-    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
-    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-    prop.location.id = ctx->device;
-    size_t gran = 0;
-    bool good = api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && gran > 0;
-    if (good && !b.p) {
-      size_t free_b = 0, total_b = 0;
-      good = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess;
-      if (good) {
+    if (!b.p) {
+      CUmemAllocationProp prop{};
+      prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+      prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      prop.location.id = ctx->device;
+      size_t gran = 0, free_b = 0, total_b = 0;
+      if (api.granularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && gran > 0 &&
+          cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
         const size_t want_va = (total_b + gran - 1) / gran * gran;      // a pool cannot outgrow the device
         CUdeviceptr base = 0;
-        good = api.reserve(&base, want_va, gran, 0, 0) == CUDA_SUCCESS;
-        if (good) { b.base = base; b.reserved = want_va; b.p = reinterpret_cast<void*>(base); b.cap = 0; b.vmm = true; }
+        if (api.reserve(&base, want_va, gran, 0, 0) == CUDA_SUCCESS) {
+          b.base = base; b.reserved = want_va; b.p = reinterpret_cast<void*>(base); b.cap = 0; b.vmm = true;
+        }
       }
     }
-    if (good) {
-      size_t want = std::max(bytes, b.cap + std::max<size_t>(b.cap / 4, (size_t)64 << 20));
-      want = (want + gran - 1) / gran * gran;
-      if (want > b.reserved) return fail(ctx, PF_ERR_NOMEM, "pattern pool would exceed the device memory");
-      const size_t add = want - b.cap;
-      CUmemGenericAllocationHandle h = 0;
-      CUresult r = api.create(&h, add, &prop, 0);
-      if (r != CUDA_SUCCESS && want > bytes) {                     // no room for the generous step: the exact one
-        want = (bytes + gran - 1) / gran * gran;
-        r = api.create(&h, want - b.cap, &prop, 0);
-      }
-      if (r != CUDA_SUCCESS) return fail(ctx, PF_ERR_NOMEM, "cuMemCreate of %zu bytes for the pattern pool failed (%d)", want - b.cap, (int)r);
-      const size_t got = want - b.cap;
-      CUmemAccessDesc acc{};
-      acc.location = prop.location;
-      acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-      if (api.map(b.base + b.cap, got, 0, h, 0) != CUDA_SUCCESS ||
-          api.set_access(b.base + b.cap, got, &acc, 1) != CUDA_SUCCESS) {
-        api.release(h);
-        return fail(ctx, PF_ERR_CUDA, "mapping %zu more bytes of the pattern pool failed", got);
-      }
-      b.chunks.emplace_back(h, got);
-      b.cap = want;
+    if (b.vmm) {
+      // small pools (cluster patterns, tests) take what they need; big ones double
+      const size_t step = b.cap < kMinStep ? std::max<size_t>(b.cap, (size_t)8 << 20) : grow_step(b.cap);
+      size_t got = b.cap;
+      const int rc = pool_map_to(ctx, b, b.cap, std::max(bytes, b.cap + step), bytes, &got);
+      if (rc == PF_ERR_NOMEM) return fail(ctx, PF_ERR_NOMEM, "no device memory left for %zu bytes of patterns", bytes);
+      if (rc != PF_OK) return fail(ctx, PF_ERR_CUDA, "mapping more memory behind the pattern pool failed");
+      b.cap = got;
       return PF_OK;
     }
-    if (b.vmm) return fail(ctx, PF_ERR_CUDA, "pattern pool: virtual memory management failed");
   }
   return dev_ensure(ctx, b, bytes, true);       // copying fallback
 }

@@ -94,7 +94,7 @@ x_finish(const uint32_t* __restrict__ recv, uint32_t n, uint32_t key_words,
     const uint32_t u = winner_rank[q];
     // bit 31: this copy is the representative of its pattern - its sender writes the pattern row
     if (gl == 0) unique_index[e] = u | (q == e ? 0x80000000u : 0u);
-    if (q == e) {
+    if (q == e && unique_keys) {
       const uint32_t* src = recv + (size_t)e * key_words;
       uint32_t* dst = unique_keys + (size_t)u * key_words;
       for (uint32_t w = gl; w < key_words; w += L) dst[w] = src[w];
@@ -167,7 +167,7 @@ extern "C" int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t wor
 
 extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint32_t* recv_words_dev,
                                  uint64_t n_recv, uint32_t* recv_unique_index_dev, uint32_t* n_unique_dev,
-                                 uint64_t* n_unique_host) {
+                                 uint64_t* n_unique_host, uint32_t keep_unique_keys) {
   if (!ctx || (!n_unique_host && !n_unique_dev)) return PF_ERR_INVALID;
   CU(cudaSetDevice(ctx->device));
   PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
@@ -192,7 +192,8 @@ extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint3
   TRY(dev_ensure(ctx, rep, (size_t)n * 4));
   TRY(dev_ensure(ctx, slot_of, (size_t)n * 4));
   TRY(dev_ensure(ctx, winner, ((size_t)n + 1) * 4));
-  TRY(dev_ensure(ctx, s.x_unique, (size_t)n * s.key_words * 4));
+  if (keep_unique_keys) TRY(dev_ensure(ctx, s.x_unique, (size_t)n * s.key_words * 4));
+  s.x_have_unique = keep_unique_keys != 0;
   CU(cudaMemsetAsync(table.p, 0xff, (size_t)size * 4, st));
   uint32_t* counters = ctx->d_counters.p ? ctx->d_counters.as<uint32_t>() : nullptr;
   if (!counters) { TRY(dev_ensure(ctx, ctx->d_counters, C_COUNT * 4)); TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 64 * 4)); counters = ctx->d_counters.as<uint32_t>(); }
@@ -214,7 +215,7 @@ extern "C" int pf_exchange_dedup(pf_ctx* ctx, int cluster_namespace, const uint3
     const uint32_t fgrid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
 #define PF_XF(LL)                                                                                          \
     x_finish<LL><<<fgrid, 256, 0, st>>>(recv_words_dev, n, s.key_words, rep.as<uint32_t>(), winner.as<uint32_t>(), \
-                                        recv_unique_index_dev, s.x_unique.as<uint32_t>())
+                                        recv_unique_index_dev, keep_unique_keys ? s.x_unique.as<uint32_t>() : nullptr)
     if (L == 4) PF_XF(4); else if (L == 8) PF_XF(8); else if (L == 16) PF_XF(16); else PF_XF(32);
 #undef PF_XF
   }
@@ -257,6 +258,7 @@ extern "C" int pf_exchange_unique_export(pf_ctx* ctx, int cluster_namespace, uin
   PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
   if (n == 0) return PF_OK;
   if (!host_out) return PF_ERR_INVALID;
+  if (!s.x_have_unique) return fail(ctx, PF_ERR_STATE, "pf_exchange_dedup was not asked to keep the unique keys");
   CU(cudaMemcpy(host_out, s.x_unique.p, n * s.key_words * 4, cudaMemcpyDeviceToHost));
   return PF_OK;
 }

@@ -226,6 +226,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->d_rescue[0], &ctx->d_rescue[1], &ctx->d_table2_base, &ctx->d_table2,
                     &ctx->d_next, &ctx->d_pslice, &ctx->d_cta_cluster, &ctx->d_slab_cnt, &ctx->d_spill})
     fd(*b);
+  ctx->grower.join();
   for (PatternSpace* s : {&ctx->kp, &ctx->cp}) pool_free(s->pool);
   for (PatternSpace* s : {&ctx->kp, &ctx->cp})
     for (DevBuf* b : {&s->table, &s->x_owner, &s->x_pos, &s->x_perm, &s->x_counts, &s->x_unique,

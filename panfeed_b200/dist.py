@@ -75,11 +75,13 @@ class DeviceBackend:
             send.data_ptr() if send.numel() else None, send.shape[0], counts))
         return [int(c) for c in counts]
 
-    def dedup(self, ns, recv, unique_index, n_unique):
-        """Asynchronous: n_unique is a one-element int32 device tensor."""
+    def dedup(self, ns, recv, unique_index, n_unique, keep_unique=False):
+        """Asynchronous: n_unique is a one-element int32 device tensor.  keep_unique: the owner
+        keeps a compact copy of its unique keys for unique_keys() (tests, self-check)."""
         self.ctx._check(self.ctx.lib.pf_exchange_dedup(
             self.ctx.h, ns, recv.data_ptr() if recv.numel() else None, recv.shape[0],
-            unique_index.data_ptr() if unique_index.numel() else None, n_unique.data_ptr(), None))
+            unique_index.data_ptr() if unique_index.numel() else None, n_unique.data_ptr(), None,
+            int(bool(keep_unique))))
 
     def unique_keys(self, ns):
         n = C.c_uint64()
@@ -147,7 +149,7 @@ class PatternExchange:
         for j, p in enumerate(packs):
             p["recv_counts"] = [int(rc[r][j]) for r in range(world)]
 
-    def _finish(self, p, want_writer):
+    def _finish(self, p, want_writer, want_unique=False):
         """Keys to the owners, owner-side dedup, ids back: all asynchronous on the stream."""
         be, world, dev, ns = self.backend, self.world, self.device, p["ns"]
         n_recv = sum(p["recv_counts"])
@@ -155,7 +157,7 @@ class PatternExchange:
         self._a2a(recv, p["send"], p["recv_counts"], p["send_counts"])
         uniq_idx = torch.empty(n_recv, dtype=torch.int32, device=dev)
         nu = torch.zeros(1, dtype=torch.int32, device=dev)
-        be.dedup(ns, recv, uniq_idx, nu)
+        be.dedup(ns, recv, uniq_idx, nu, want_unique)
         all_nu = torch.empty(world, dtype=torch.int32, device=dev)
         self._gather(all_nu, nu)
         owner_base = (torch.cumsum(all_nu, 0, dtype=torch.int32) - all_nu).contiguous()
@@ -178,14 +180,14 @@ class PatternExchange:
                 # k-mer keys end with the GLOBAL id of the cluster pattern giving their NaN plane:
                 # the cluster namespace has to be numbered first
                 self._counts([cl])
-                self._finish(cl, want_writer)
+                self._finish(cl, want_writer, want_unique)
                 km = self._pack(KMER, cl["local_to_global"])
                 self._counts([km])
             else:
                 km = self._pack(KMER, None)
                 self._counts([cl, km])
-                self._finish(cl, want_writer)
-            self._finish(km, want_writer)
+                self._finish(cl, want_writer, want_unique)
+            self._finish(km, want_writer, want_unique)
             counts = torch.stack([cl["all_nu"], km["all_nu"]]).cpu().tolist()     # the final sync
         ms = (time.perf_counter() - t0) * 1e3
         out = {}

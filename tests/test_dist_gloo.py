@@ -51,7 +51,7 @@ class NumpyBackend:
         self.owner = getattr(self, "owner", {}); self.owner[ns] = owner
         send.copy_(torch.from_numpy(keys[order].astype(np.int32).reshape(send.shape)))
         return [int((owner == r).sum()) for r in range(world)]
-    def dedup(self, ns, recv, unique_index, n_unique):
+    def dedup(self, ns, recv, unique_index, n_unique, keep_unique=False):
         keys = recv.numpy().astype(np.uint32)
         seen, idx = {}, []
         for k in keys:

@@ -53,7 +53,7 @@ def test_exchange_two_contexts_one_gpu(cm):
         for o, be in enumerate(bes):
             u = torch.empty(recvs[o].shape[0], dtype=torch.int32, device=dev)
             nu = torch.zeros(1, dtype=torch.int32, device=dev)
-            be.dedup(ns, recvs[o], u, nu)          # asynchronous on the context's stream
+            be.dedup(ns, recvs[o], u, nu, True)    # asynchronous on the context's stream
             torch.cuda.synchronize()
             n_unique.append(int(nu.cpu().item()))
             uniq.append(u)
