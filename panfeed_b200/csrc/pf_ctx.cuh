@@ -92,6 +92,7 @@ struct PoolBuf : DevBuf {
   // that raises it when joined
   bool growing = false;
   size_t grown_cap = 0;
+  bool big_step_done = false;
 };
 
 struct PatternSpace {
@@ -502,7 +503,18 @@ int pool_ensure(pf_ctx* ctx, PoolBuf& b, size_t bytes) {
   constexpr size_t kMinStep = (size_t)256 << 20;
   // doubling up to 4 GB, then a quarter at a time: the exchange of a sharded run needs room for
   // two more copies of every pattern next to the pool
-  auto grow_step = [](size_t cap) { return cap < ((size_t)4 << 30) ? cap : std::max<size_t>((size_t)2 << 30, cap / 4); };
+  // (mapping costs 10-40 ms per call in a process with NCCL peers, whatever the size, and stalls
+  //  the device: a pool that outgrows 256 MB takes a quarter of the free memory, up to 48 GB, in
+  //  ONE call; after that a quarter of its size at a time)
+  auto grow_step = [&](size_t cap) -> size_t {
+    if (!b.big_step_done) {
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+      b.big_step_done = true;
+      return std::max<size_t>(cap, std::min<size_t>(free_b / 4, (size_t)48 << 30));
+    }
+    return std::max<size_t>((size_t)2 << 30, cap / 4);
+  };
   auto prefetch = [&]() {
     if (!b.vmm || b.growing || b.cap < kMinStep || bytes <= b.cap / 2 || b.cap >= b.reserved) return;
     const size_t cur = b.cap, want = cur + grow_step(cur);
@@ -537,7 +549,7 @@ int pool_ensure(pf_ctx* ctx, PoolBuf& b, size_t bytes) {
     }
     if (b.vmm) {
       // small pools (cluster patterns, tests) take what they need; big ones double
-      const size_t step = b.cap < kMinStep ? std::max<size_t>(b.cap, (size_t)8 << 20) : grow_step(b.cap);
+      const size_t step = std::max(bytes, b.cap) < kMinStep ? std::max<size_t>(b.cap, (size_t)8 << 20) : grow_step(b.cap);
       size_t got = b.cap;
       const int rc = pool_map_to(ctx, b, b.cap, std::max(bytes, b.cap + step), bytes, &got);
       if (rc == PF_ERR_NOMEM) return fail(ctx, PF_ERR_NOMEM, "no device memory left for %zu bytes of patterns", bytes);
