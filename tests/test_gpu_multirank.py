@@ -70,6 +70,42 @@ def test_cli_two_ranks_match_reference(mode, extra, tmp_path):
         assert os.path.exists(os.path.join(out, "hashes_to_patterns.tsv.gz"))
 
 
+@needs_two
+def test_cli_two_ranks_multiple_files(tmp_path):
+    """--multiple-files under torchrun: every rank writes the directories of its own clusters (the
+    pattern set is per cluster there, panfeed.py:165: no exchange); checked per cluster against
+    the oracle port like the single-process test."""
+    import pandas as pd
+    from oracle import ref_port
+    out = str(tmp_path / "out")
+    _torchrun(["-m", "panfeed_b200", "--gff", "fixture/gffs/", "--presence-absence",
+               "fixture/gene_presence_absence.csv", "--targets", "fixture/stroi.txt", "--multiple-files",
+               "--output", out], 29640, helpers.GOLDEN)
+    cwd = os.getcwd()
+    os.chdir(helpers.GOLDEN)
+    try:
+        table = pd.read_csv("fixture/gene_presence_absence.csv", sep=",", index_col=0,
+                            low_memory=False).drop(columns=["Non-unique Gene name", "Annotation"])
+        genomes = ref_port.load_inputs("fixture/gffs/")
+        stroi = {x.rstrip("\n") for x in open("fixture/stroi.txt")}
+        h2p_head, k2h_head = ref_port.headers(table.columns)
+        n = 0
+        for item in ref_port.feed_clusters(table, genomes, 0, 0, False):
+            res = ref_port.kmer_stage(item, 31, stroi, True, False)
+            a, b, c = ref_port.pattern_stage((res,), True, 0.01, False, set())
+            d = os.path.join(out, item[1])
+            assert helpers.sorted_lines(open(os.path.join(d, "kmers.tsv")).read()) == \
+                helpers.sorted_lines(ref_port.KMERS_HEADER + a)
+            assert helpers.sorted_lines(open(os.path.join(d, "hashes_to_patterns.tsv")).read()) == \
+                helpers.sorted_lines(h2p_head + b)
+            assert helpers.sorted_lines(open(os.path.join(d, "kmers_to_hashes.tsv")).read()) == \
+                helpers.sorted_lines(k2h_head + c)
+            n += 1
+        assert n >= 5
+    finally:
+        os.chdir(cwd)
+
+
 WORKER = r'''
 import os, sys, json
 import torch, torch.distributed as dist

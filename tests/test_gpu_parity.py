@@ -451,3 +451,35 @@ def test_malformed_batches_are_refused_with_the_same_message(lite, monkeypatch):
         assert len(r["row_cluster"]) > 0
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("canon", [True, False])
+def test_pipelined_submit_compact_positions(canon, monkeypatch):
+    """The compact positional form (emit_positions = 2: one used_strand bit per window) through a
+    pipelined submit (device-planned sub-batches, the bit plane copied slice by slice) against the
+    21-byte record form of the same batch (host-planned, plain): every record's strand bit, and
+    the kmers.tsv text both forms format, must agree."""
+    from panfeed_b200 import capi
+    monkeypatch.setenv("PF_PIPELINE_SEQS", "1500")
+    S, C, L, k = 48, 120, 260, 21
+    hb = capi.synth_batch(0, 77, S, C, total_clusters=C, gene_len=L, all_targets=True)
+    hb.seqs["flags"][::3] = 0                      # a third of the sequences are not targets
+    res = {}
+    for mode in (2, 1):
+        ctx = capi.Context(k, S, canonical=canon, emit_positions=mode, maf=0.02)
+        try:
+            ctx.submit(hb)
+            res[mode] = (ctx.collect(), ctx.stats())
+        finally:
+            ctx.close()
+    (rc, stc), (rr, st) = res[2], res[1]
+    assert stc["sub_batches"] >= 3
+    nwin = np.maximum(hb.seqs["len"].astype(np.int64) - k + 1, 0)
+    n_target = int(nwin[(hb.seqs["flags"] & 1) != 0].sum())
+    assert rc["n_pos"] == rr["n_pos"] == n_target
+    leads = [f"c{int(q['cluster'])}\ts{int(q['sample'])}\tg{i}\tctg\t{int(q['strand'])}\t".encode()
+             for i, q in enumerate(hb.seqs)]
+    a = capi.format_positions_compact(hb, rc["pos_strand_bits"], k, canon, leads)
+    b = capi.format_positions(rr, k, canon, leads, hb.seqs["strand"])
+    assert len(a) > 0 and sorted(a.split(b"\n")) == sorted(b.split(b"\n"))
+    assert np.array_equal(np.sort(rc["row_kmer"]), np.sort(rr["row_kmer"]))
