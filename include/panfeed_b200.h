@@ -168,7 +168,7 @@ typedef struct pf_batch_result {
    * (used_strand = -1, panfeed.py:69-75).  Words of sequences without PF_SEQ_TARGET are
    * undefined; with canonical == 0 nothing is needed and the plane is empty. */
   const uint32_t* pos_strand_bits;
-  uint64_t        n_pos_bit_words; /* 2 * pf_batch.n_words, or 0                              */
+  uint64_t        n_pos_bit_words; /* pf_batch.n_words (one bit per base position), or 0      */
 } pf_batch_result;
 
 typedef struct pf_stats {

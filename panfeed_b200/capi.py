@@ -445,7 +445,7 @@ def format_positions_compact(hb, strand_bits, k, canonical, leads, n_threads=0):
     bits = None
     if canonical:
         bits = np.ascontiguousarray(strand_bits, dtype=np.uint32)
-        if bits.size < 2 * hb.packed.size:
+        if bits.size < hb.packed.size:
             raise ValueError("strand bit plane is shorter than the packed plane")
     need = C.c_uint64()
     args = (C.byref(b), bits.ctypes.data if bits is not None else None, int(k), int(bool(canonical)), 0, n, blob,

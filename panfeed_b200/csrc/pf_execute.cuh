@@ -564,7 +564,7 @@ extern "C" int pf_execute(pf_ctx* ctx) {
   }
   const bool compact_pos = ctx->prm.emit_positions == 2u;
   if (ctx->n_pos && compact_pos) {
-    if (ctx->prm.canonical) TRY(dev_ensure(ctx, ctx->d_pos_bits, (size_t)ctx->n_words * 8 + 16));
+    if (ctx->prm.canonical) TRY(dev_ensure(ctx, ctx->d_pos_bits, (size_t)ctx->n_words * 4 + 16));
   } else if (ctx->n_pos) {
     TRY(dev_ensure(ctx, ctx->d_pos_kmer, (size_t)ctx->n_pos * 8));
     TRY(dev_ensure(ctx, ctx->d_pos_seq, (size_t)ctx->n_pos * 4));

@@ -125,7 +125,7 @@ int pipe_enqueue_results(pf_ctx* ctx, const SubRange& r) {
   TRY(d2h(ctx->r_wrow_kmer, RW * 16, ctx->d_wrow_kmer.p, nw * 16));
   TRY(d2h(ctx->r_cl_pattern, (size_t)ctx->pipe_clusters * 4, ctx->d_cl_pattern.p, (size_t)ctx->n_clusters * 4));
   if (ctx->n_pos && compact && ctx->prm.canonical)      // (r_pos_bits covers the whole batch: sized by the submit)
-    TRY(d2h(ctx->r_pos_bits, (size_t)r.w0 * 8, ctx->d_pos_bits.p, (size_t)(r.w1 - r.w0) * 8));
+    TRY(d2h(ctx->r_pos_bits, (size_t)r.w0 * 4, ctx->d_pos_bits.p, (size_t)(r.w1 - r.w0) * 4));   // one bit per base: a u32 per packed word
   if (ctx->n_pos && !compact) {
     const uint64_t P0 = ctx->pipe_pos, np = ctx->n_pos;
     TRY(d2h(ctx->r_pos_kmer, P0 * 8, ctx->d_pos_kmer.p, np * 8));
@@ -187,8 +187,8 @@ int submit_pipelined(pf_ctx* ctx, const pf_batch* b, const std::vector<SubRange>
   TRY(pin_ensure(ctx, ctx->r_cl_pattern, std::max<size_t>(8, (size_t)b->n_clusters * 4)));
   ctx->pipe_bit_words = 0;
   if (ctx->prm.emit_positions == 2u && ctx->prm.canonical) {
-    TRY(pin_ensure(ctx, ctx->r_pos_bits, std::max<size_t>(8, (size_t)b->n_words * 8)));
-    ctx->pipe_bit_words = b->n_words * 2;
+    TRY(pin_ensure(ctx, ctx->r_pos_bits, std::max<size_t>(8, (size_t)b->n_words * 4)));
+    ctx->pipe_bit_words = b->n_words;
   }
   {
     // row arrays: learned rows-per-base ratio, grown on demand
@@ -442,7 +442,7 @@ extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
   TRY(d2h(ctx->r_new_cp, ctx->cp.pool.as<uint32_t>() + ctx->cp_base * ctx->W, new_cp * ctx->W * 4));
   const bool compact = ctx->prm.emit_positions == 2u;
   if (ctx->n_pos && compact) {
-    if (ctx->prm.canonical) TRY(d2h(ctx->r_pos_bits, ctx->d_pos_bits.p, (size_t)ctx->n_words * 8));
+    if (ctx->prm.canonical) TRY(d2h(ctx->r_pos_bits, ctx->d_pos_bits.p, (size_t)ctx->n_words * 4));
   } else if (ctx->n_pos) {
     TRY(d2h(ctx->r_pos_kmer, ctx->d_pos_kmer.p, (size_t)ctx->n_pos * 8));
     TRY(d2h(ctx->r_pos_seq, ctx->d_pos_seq.p, (size_t)ctx->n_pos * 4));
@@ -490,7 +490,7 @@ extern "C" int pf_collect(pf_ctx* ctx, pf_batch_result* out) {
       out->n_pos_wide = 0;
       if (ctx->n_pos && ctx->prm.canonical) {
         out->pos_strand_bits = ctx->r_pos_bits.as<uint32_t>();
-        out->n_pos_bit_words = ctx->n_words * 2;
+        out->n_pos_bit_words = ctx->n_words;
       }
     }
   }

@@ -249,7 +249,7 @@ def test_native_compact_position_rows_match_python(k, canonical, threads):
     hb = capi.HostBatch(packed, seqs, np.zeros(1, capi.CLUSTER_DTYPE), np.zeros((1, 1), np.uint32), amb_plane)
     leads = [f"cl{i % 4}\tstrain_{i}\tgene{i}\tctg{i % 3}\t{int(seqs['strand'][i])}\t".encode() for i in range(n_seqs)]
     # the bit plane the device would return: 1 where the reverse complement is the canonical k-mer
-    bits = np.zeros(2 * len(packed) + 2, np.uint32)
+    bits = np.zeros(len(packed), np.uint32)
     want = []
     for i, s in enumerate(seqs_txt):
         q = seqs[i]

@@ -209,7 +209,7 @@ def test_config3_second_pass_positions_full_size():
     (rc, stc), (rr, st) = out[2], out[1]
     nwin = np.maximum(hb.seqs["len"].astype(np.int64) - K + 1, 0)
     assert rc["n_pos"] == rr["n_pos"] == int(nwin.sum()) == st["instances"] > 9e7
-    assert len(rc["pos_seq"]) == 0 and len(rc["pos_strand_bits"]) == 2 * len(hb.packed)
+    assert len(rc["pos_seq"]) == 0 and len(rc["pos_strand_bits"]) == len(hb.packed)
     assert stc["rows"] == st["rows"] and np.array_equal(np.sort(rc["row_kmer"]), np.sort(rr["row_kmer"]))
     # every record: sequence, position, coordinates, strand bit
     seq = rr["pos_seq"].astype(np.int64)
