@@ -31,12 +31,15 @@ def _n_gpus():
         return 0
 
 
-needs_two = pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+# ranks of the torchrun launches (PF_TEST_RANKS=8 on an 8-GPU box: some ranks then own no cluster
+# of the five-cluster fixture at all, which the product path must survive)
+RANKS = max(2, int(os.environ.get("PF_TEST_RANKS", "2")))
+needs_two = pytest.mark.skipif(_n_gpus() < RANKS, reason=f"needs {RANKS} GPUs (gpurun --gpus {RANKS})")
 
 
 def _torchrun(args, port, cwd, timeout=900):
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(RANKS),
                         "--master-addr", "127.0.0.1", "--master-port", str(port)] + args,
                        capture_output=True, text=True, timeout=timeout, env=env, cwd=cwd)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
