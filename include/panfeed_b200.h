@@ -36,7 +36,7 @@ typedef enum pf_status {
   PF_ERR_INVALID = -1,      /* bad argument / malformed batch              */
   PF_ERR_CUDA = -2,         /* CUDA runtime error (no device, launch, ...) */
   PF_ERR_NOMEM = -3,        /* host or device allocation failed            */
-  PF_ERR_UNSUPPORTED = -4,  /* e.g. k > 32                                 */
+  PF_ERR_UNSUPPORTED = -4,  /* e.g. k > 64                                 */
   PF_ERR_STATE = -5,        /* call order violated                         */
   PF_ERR_INTERNAL = -6      /* device-side watchdog / invariant violated   */
 } pf_status;
@@ -46,7 +46,9 @@ typedef struct pf_ctx pf_ctx;
 /* Options bound into the two reference callables at __main__.py:277-297. */
 typedef struct pf_params {
   uint32_t abi_version;          /* PF_ABI_VERSION                                  */
-  uint32_t k;                    /* -k/--kmer-length, 1..32 (64-bit 2-bit path)      */
+  uint32_t k;                    /* -k/--kmer-length, 1..64: up to 32 a k-mer is one 64-bit word
+                                    (all engines); 33..64 two words, through the 128-bit record
+                                    engine, rows come back as wide rows (2 bits per base)        */
   uint32_t n_samples;            /* S = number of strain columns of the panaroo CSV */
   uint32_t canonical;            /* 1 unless --non-canonical (panfeed.py:69-88)     */
   uint32_t consider_missing;     /* --consider-missing (panfeed.py:16-20,192-196)   */
@@ -133,7 +135,9 @@ typedef struct pf_batch_result {
   const uint64_t* row_kmer;        /* 2-bit k-mer, first base in the top used bits          */
   const uint32_t* row_count;       /* number of samples carrying it                         */
   const uint32_t* row_pattern;     /* index into the context's k-mer pattern pool           */
-  /* rows whose k-mer holds N/IUPAC symbols (128-bit keys, 4 bits per symbol) */
+  /* rows whose k-mer takes two words: N/IUPAC symbols (k <= 32, 4 bits per symbol, codes of
+     PF_AMB_ALPHABET) or any k-mer of 33..64 bases (2 bits per base); first symbol in the top
+     used bits of [hi, lo] */
   uint64_t        n_wide_rows;
   const uint32_t* wide_row_cluster;
   const uint64_t* wide_row_kmer;   /* 2 words per row: [hi, lo]                             */

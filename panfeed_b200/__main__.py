@@ -51,8 +51,9 @@ def get_options(argv=None):
                    help="Output directory (must not exist)")
     p.add_argument("-f", "--fasta", help="Directory or file of files with nucleotide fastas")
     p.add_argument("-k", "--kmer-length", type=int, default=31,
-                   help="K-mer length, 1..32 (this build packs a k-mer into one 64-bit word; the "
-                        "reference accepts longer k-mers, this build exits with an error)")
+                   help="K-mer length, 1..64 (a k-mer is packed into one or two 64-bit words; the "
+                        "reference accepts longer k-mers, this build exits with an error).  33..64 run on "
+                        "the 128-bit record engine, several times slower than 1..32")
     p.add_argument("--maf", type=float, default=0.01, help="Minor allele frequency threshold")
     p.add_argument("--upstream", type=int, default=0)
     p.add_argument("--downstream", type=int, default=0)
@@ -86,8 +87,8 @@ def main(argv=None):
     if args.maf > 0.5:
         logger.warning("--maf should be below 0.5")
         sys.exit(1)
-    if klength < 1 or klength > 32:
-        logger.error("this build supports k-mer lengths 1..32 (64-bit 2-bit encoding)")
+    if klength < 1 or klength > 64:
+        logger.error("this build supports k-mer lengths 1..64 (2 bits per base in one or two 64-bit words)")
         sys.exit(1)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

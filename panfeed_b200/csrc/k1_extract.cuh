@@ -158,6 +158,84 @@ k1_strand_bits(const uint64_t* __restrict__ bases, const SeqDev* __restrict__ se
   }
 }
 
+// ---- k = 33..64: a k-mer is 2k <= 128 bits ------------------------------------------------
+// The reference takes any -k (its k-mers are Python strings, panfeed.py:59-88).  Up to 32 bases a
+// k-mer is one 64-bit word and goes through the engines above; from 33 to 64 it is a Key128 (2 bits
+// per base, first base in the top USED bits) and every window goes through the 128-bit record
+// pipeline that the N/IUPAC windows use (radix sort of mixed keys + run reduction).  One warp
+// walks one sequence; lane l of iteration `it` owns the window starting at base 32 * it + l: the
+// three words it needs are the same for the whole warp.
+template <bool CANON>
+__global__ void __launch_bounds__(kK1Warps * 32)
+k1_extract_long(const uint64_t* __restrict__ bases, const SeqDev* __restrict__ seqs, uint32_t n_seqs, int k,
+                Key128* __restrict__ keys, uint32_t* __restrict__ vals, PosOut pos,
+                uint64_t* __restrict__ pos_wide, uint32_t* __restrict__ strand_bits) {
+  const uint32_t lane = lane_id();
+  const uint32_t stride = gridDim.x * kK1Warps;
+  const uint32_t drop = 128u - 2u * (uint32_t)k;                  // unused low bits of the 64-base string (0..62)
+  const uint64_t top_mask = (2u * (uint32_t)k - 64u) >= 64u ? ~0ull : ((1ull << (2u * (uint32_t)k - 64u)) - 1ull);
+  for (uint32_t s = blockIdx.x * kK1Warps + (threadIdx.x >> 5); s < n_seqs; s += stride) {
+    const SeqDev d = seqs[s];
+    if (d.len < (uint32_t)k) continue;
+    const uint32_t nwin = d.len - (uint32_t)k + 1u;
+    const uint64_t* w = bases + (d.base_off >> 5);
+    const bool target = (d.flags & 1u) != 0u;
+    for (uint32_t it = 0; it * 32u < nwin; ++it) {
+      const uint32_t p = it * 32u + lane;
+      const bool valid = p < nwin;
+      const uint64_t w0 = __ldg(w + it), w1 = __ldg(w + it + 1), w2 = __ldg(w + it + 2);
+      const uint32_t sh = 2u * lane;
+      // the 64 bases from base p, first base on top
+      uint64_t hi = w0, lo = w1;
+      if (sh) { hi = (w0 << sh) | (w1 >> (64u - sh)); lo = (w1 << sh) | (w2 >> (64u - sh)); }
+      if (drop) lo &= ~0ull << drop;                               // the k-mer's own bases only
+      Key128 f, r;
+      f.hi = drop ? hi >> drop : hi;
+      f.lo = drop ? (lo >> drop) | (hi << (64u - drop)) : lo;
+      // reverse complement of the 64-base string: the k-mer's is its last k bases
+      r.hi = revcomp2(lo, 32) & top_mask;
+      r.lo = revcomp2(hi, 32);
+      const bool use_rc = r < f;                                   // reference: fwd <= rc keeps fwd (+1)
+      if (CANON && strand_bits && target) {
+        const uint32_t word = __ballot_sync(kFull, valid && use_rc);
+        if (lane == 0) strand_bits[(d.base_off >> 5) + it] = word;
+      }
+      if (!valid) continue;
+      if (CANON) {
+        const Key128 canon = use_rc ? r : f;
+        const size_t rec = (size_t)d.wrec_off + p;
+        keys[rec] = mix128(canon);
+        vals[rec] = d.sample;
+        if (target && pos.kmer) {
+          const size_t q = (size_t)d.pos_off + p, wq = (size_t)d.pwide_off + p;
+          pos.kmer[q] = (uint64_t)wq;
+          pos.seq[q] = s;
+          pos.contig_start[q] = d.strand > 0 ? d.start + (int32_t)p : d.end - (int32_t)p - k;
+          pos.gene_start[q] = (int32_t)p - d.offset;
+          pos.flags[q] = (uint8_t)((use_rc ? 1u : 0u) | 2u);
+          pos_wide[2 * wq] = canon.hi;
+          pos_wide[2 * wq + 1] = canon.lo;
+        }
+      } else {
+        const size_t rec = (size_t)d.wrec_off + 2 * (size_t)p;
+        keys[rec] = mix128(f);
+        keys[rec + 1] = mix128(r);
+        vals[rec] = vals[rec + 1] = d.sample;
+        if (target && pos.kmer) {
+          const size_t q = (size_t)d.pos_off + p, wq = (size_t)d.pwide_off + p;
+          pos.kmer[q] = (uint64_t)wq;
+          pos.seq[q] = s;
+          pos.contig_start[q] = d.strand > 0 ? d.start + (int32_t)p : d.end - (int32_t)p - k;
+          pos.gene_start[q] = (int32_t)p - d.offset;
+          pos.flags[q] = 2u;
+          pos_wide[2 * wq] = f.hi;
+          pos_wide[2 * wq + 1] = f.lo;
+        }
+      }
+    }
+  }
+}
+
 // ---- 4-bit plane: ambiguity bits and the wide (128-bit) extraction --------
 // One ambiguity bit per symbol, 32 per word, first symbol in the top bit.
 __global__ void k1_amb_bits(const uint64_t* __restrict__ amb_codes, uint64_t n_amb_words,

@@ -264,7 +264,7 @@ int launch_k1(pf_ctx* ctx) {
   PosOut po{ctx->d_pos_kmer.as<uint64_t>(), ctx->d_pos_seq.as<uint32_t>(), ctx->d_pos_cstart.as<int32_t>(),
             ctx->d_pos_gstart.as<int32_t>(), ctx->d_pos_flags.as<uint8_t>()};
   const bool compact = ctx->prm.emit_positions == 2u;
-  if (compact && ctx->n_pos && P.canonical && ctx->n_seqs) {
+  if (compact && ctx->n_pos && P.canonical && ctx->n_seqs && P.k <= 32) {
     // compact positional form: one bit per window of the target sequences, nothing else
     const uint32_t grid = std::min<uint32_t>(cdiv(ctx->n_seqs, kK1Warps), 148 * 8);
     k1_strand_bits<<<grid, kK1Warps * 32, 0, st>>>(ctx->d_bases.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(), ctx->n_seqs,
@@ -283,7 +283,20 @@ int launch_k1(pf_ctx* ctx) {
 #undef PF_K1
     ctx->launches++;
   }
-  if (ctx->n_wide_seqs && Wd.n_records) {
+  if (P.k > 32 && ctx->n_seqs && Wd.n_records) {
+    // two-word k-mers: records, positional records (or the used_strand plane) of every window
+    const uint32_t grid = std::min<uint32_t>(cdiv(ctx->n_seqs, kK1Warps), 148 * 8);
+    uint32_t* bits = compact && ctx->n_pos && P.canonical ? ctx->d_pos_bits.as<uint32_t>() : nullptr;
+    if (P.canonical)
+      k1_extract_long<true><<<grid, kK1Warps * 32, 0, st>>>(ctx->d_bases.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(), ctx->n_seqs,
+                                                            (int)P.k, Wd.keys[0].as<Key128>(), Wd.vals[0].as<uint32_t>(), po,
+                                                            ctx->d_pos_wide.as<uint64_t>(), bits);
+    else
+      k1_extract_long<false><<<grid, kK1Warps * 32, 0, st>>>(ctx->d_bases.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(), ctx->n_seqs,
+                                                             (int)P.k, Wd.keys[0].as<Key128>(), Wd.vals[0].as<uint32_t>(), po,
+                                                             ctx->d_pos_wide.as<uint64_t>(), nullptr);
+    ctx->launches++;
+  } else if (ctx->n_wide_seqs && Wd.n_records) {
     const uint32_t grid = std::min<uint32_t>(cdiv(ctx->n_wide_seqs, 8), 148 * 8);
     if (P.canonical)
       k1_extract_wide<true><<<grid, 256, 0, st>>>(ctx->d_amb.as<uint64_t>(), ctx->d_seqs.as<SeqDev>(),

@@ -49,6 +49,23 @@ inline int len_int(int64_t v) {
   return len;
 }
 
+// text of a two-word k-mer [hi, lo], first symbol in the top used bits: 4 bits per symbol (N/IUPAC
+// k-mers, k <= 32) or, for k > 32, 2 bits per base
+inline void wide_kmer_text(const uint64_t* w, uint32_t k, char* out) {
+  if (k > 32) {
+    for (uint32_t s = 0; s < k; ++s) {
+      const uint32_t pos = 2 * (k - 1 - s);
+      out[s] = kAcgt[((pos < 64 ? w[1] >> pos : w[0] >> (pos - 64))) & 3u];
+    }
+    return;
+  }
+  for (uint32_t s = 0; s < k; ++s) {
+    const uint32_t nib = k - 1 - s;
+    const uint64_t word = nib < 16 ? w[1] : w[0];
+    out[s] = kAmb[(word >> (4 * (nib % 16))) & 15u];
+  }
+}
+
 struct Job {
   const pf_batch_result* r;
   uint32_t k;
@@ -62,12 +79,7 @@ struct Job {
 inline void kmer_text(const Job& j, uint64_t i, char* out) {
   const uint32_t k = j.k;
   if (j.r->pos_flags[i] & 2u) {
-    const uint64_t* w = j.r->pos_wide_kmer + 2 * j.r->pos_kmer[i];      // [hi, lo], 4 bits per symbol
-    for (uint32_t s = 0; s < k; ++s) {
-      const uint32_t nib = k - 1 - s;
-      const uint64_t word = nib < 16 ? w[1] : w[0];
-      out[s] = kAmb[(word >> (4 * (nib % 16))) & 15u];
-    }
+    wide_kmer_text(j.r->pos_wide_kmer + 2 * j.r->pos_kmer[i], k, out);
   } else {
     const uint64_t v = j.r->pos_kmer[i];
     for (uint32_t s = 0; s < k; ++s) out[s] = kAcgt[(v >> (2 * (k - 1 - s))) & 3u];
@@ -91,7 +103,7 @@ inline char* write_row(const Job& j, uint64_t i, char* p) {
   const uint32_t seq = j.r->pos_seq[i];
   const uint64_t lead = j.lead_off[seq + 1] - j.lead_off[seq];
   const int64_t c0 = j.r->pos_contig_start[i], g0 = j.r->pos_gene_start[i];
-  char km[40];
+  char km[72];
   kmer_text(j, i, km);
   auto head = [&](char* q) {
     memcpy(q, j.lead_blob + j.lead_off[seq], lead);
@@ -129,7 +141,7 @@ extern "C" int pf_format_positions(const pf_batch_result* r, uint32_t k, int can
                                    uint64_t count, const char* lead_blob, const uint64_t* lead_off,
                                    const int32_t* seq_strand, char* out, uint64_t out_cap, uint64_t* out_len,
                                    uint32_t n_threads) {
-  if (!r || !out_len || k < 1 || k > 32) return PF_ERR_INVALID;
+  if (!r || !out_len || k < 1 || k > 64) return PF_ERR_INVALID;
   if (first + count > r->n_pos) return PF_ERR_INVALID;
   *out_len = 0;
   if (count == 0) return PF_OK;
@@ -258,7 +270,7 @@ extern "C" int pf_format_positions_compact(const pf_batch* b, const uint32_t* st
                                            uint32_t seq_first, uint32_t seq_count, const char* lead_blob,
                                            const uint64_t* lead_off, char* out, uint64_t out_cap, uint64_t* out_len,
                                            uint32_t n_threads) {
-  if (!b || !out_len || k < 1 || k > 32) return PF_ERR_INVALID;
+  if (!b || !out_len || k < 1 || k > 64) return PF_ERR_INVALID;
   if ((uint64_t)seq_first + seq_count > b->n_seqs) return PF_ERR_INVALID;
   *out_len = 0;
   if (seq_count == 0) return PF_OK;
@@ -465,7 +477,7 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
                                    const uint64_t* tag_off, const char* kmer_ids, uint64_t n_kmer_ids,
                                    const char* cluster_ids, uint64_t n_cluster_ids, char* out, uint64_t out_cap,
                                    uint64_t* out_len, uint64_t* cluster_off, uint32_t n_threads) {
-  if (!r || !out_len || !tag_off || k == 0 || k > 32) return PF_ERR_INVALID;
+  if (!r || !out_len || !tag_off || k == 0 || k > 64) return PF_ERR_INVALID;
   const uint64_t nc = r->n_clusters, nn = r->n_rows, nw = r->n_wide_rows;
   *out_len = 0;
   if (nc >= (1ull << 32) || nn >= (1ull << 32) || nw >= (1ull << 32)) return PF_ERR_INVALID;
@@ -550,12 +562,7 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
         const uint32_t i = ow[j];
         memcpy(p, tag, tl); p += tl;
         *p++ = '\t';
-        const uint64_t* w = r->wide_row_kmer + 2 * (uint64_t)i;            // [hi, lo], 4 bits per symbol
-        for (uint32_t s = 0; s < k; ++s) {
-          const uint32_t nib = k - 1 - s;
-          const uint64_t word = nib < 16 ? w[1] : w[0];
-          p[s] = kAmb[(word >> (4 * (nib % 16))) & 15u];
-        }
+        wide_kmer_text(r->wide_row_kmer + 2 * (uint64_t)i, k, p);
         p += k;
         *p++ = '\t';
         memcpy(p, kmer_ids + (size_t)r->wide_row_pattern[i] * 24, 24); p += 24;

@@ -47,8 +47,9 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
   *out = nullptr;
   if (p->abi_version != PF_ABI_VERSION)
     return fail(nullptr, PF_ERR_INVALID, "pf_create: ABI version %u != %u", p->abi_version, PF_ABI_VERSION);
-  if (p->k < 1 || p->k > 32)
-    return fail(nullptr, PF_ERR_UNSUPPORTED, "k=%u unsupported: the 64-bit 2-bit path covers 1..32", p->k);
+  if (p->k < 1 || p->k > 64)
+    return fail(nullptr, PF_ERR_UNSUPPORTED, "k=%u unsupported: k-mers of 1..64 bases are packed into one or two 64-bit "
+                                             "words (1..32: all engines; 33..64: the 128-bit record engine)", p->k);
   if (p->n_samples < 1) return fail(nullptr, PF_ERR_INVALID, "n_samples must be >= 1");
   if (p->sort_bits != 0 && (p->sort_bits % 8 != 0 || p->sort_bits < 8 || p->sort_bits > 64))
     return fail(nullptr, PF_ERR_INVALID, "sort_bits must be 0 or a multiple of 8 in 8..64");
@@ -162,6 +163,7 @@ extern "C" int pf_create(pf_ctx** out, int device, const pf_params* p) {
     ctx->blk_cap = cap;
     ctx->blk_cslots = cslots;
     if (p->k == 32 && !p->canonical) ctx->block_mode = false;   // all-T k-mer == the empty-slot mark
+    if (p->k > 32) ctx->block_mode = false;                      // two-word k-mers: the 128-bit record pipeline
     if (const char* e = getenv("PF_MERGE_SMEM_KB")) {       // 0: every cluster through the global table
       const long kb = atol(e);
       if (kb >= 0 && kb <= 216) ctx->merge_slots = (uint32_t)(kb * 256);

@@ -290,6 +290,7 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
   uint32_t* hw = B.h_wide_seqs.as<uint32_t>();
 
   const uint32_t mult = P.canonical ? 1u : 2u;
+  const bool long_k = k > 32;          // two-word k-mers: every window is a record of the 128-bit pipeline
   // the packed plane is the bulk of the transfer: start it before the host-side planning
   const size_t slack_words = 80;
   TRY(dev_ensure(ctx, B.d_bases, (b->n_words + slack_words) * 8));
@@ -339,6 +340,7 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
         if (q.base_off + q.len > b->n_words * 32ull) return errf(p, "seq %u: bases run past the packed plane", i);
         if (q.strand != 1 && q.strand != -1) return errf(p, "seq %u: strand must be +1/-1", i);
         const bool amb = (q.flags & PF_SEQ_AMBIGUOUS) != 0;
+        if (amb && long_k) return errf(p, "seq %u holds N/IUPAC symbols: not supported with k > 32", i);
         if (amb) {
           if (!b->amb_codes) return errf(p, "seq %u is ambiguous but amb_codes is NULL", i);
           if (q.amb_off & 31u) return errf(p, "seq %u: amb_off must be a multiple of 32", i);
@@ -346,9 +348,9 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
         }
         const bool target = P.emit_positions && (q.flags & PF_SEQ_TARGET);
         const uint32_t nwin = q.len >= k ? q.len - k + 1 : 0;
-        p.rec += (uint64_t)nwin * mult;
+        if (!long_k) p.rec += (uint64_t)nwin * mult;
         if (target) p.pos += nwin;
-        if (amb) { p.wrec += (uint64_t)nwin * mult; p.wide++; if (target) p.pwide += nwin; }
+        if (amb || long_k) { p.wrec += (uint64_t)nwin * mult; p.wide++; if (target) p.pwide += nwin; }
         p.bases += q.len;
       }
     });
@@ -383,9 +385,9 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
         d.start = q.start; d.end = q.end; d.offset = q.offset; d.strand = q.strand;
         d.rec_off = (uint32_t)o.rec; d.pos_off = (uint32_t)o.pos; d.wrec_off = (uint32_t)o.wrec;
         d.pwide_off = (uint32_t)o.pwide;
-        o.rec += (uint64_t)nwin * mult;
+        if (!long_k) o.rec += (uint64_t)nwin * mult;
         if (target) o.pos += nwin;
-        if (amb) { o.wrec += (uint64_t)nwin * mult; hw[o.wide++] = i; if (target) o.pwide += nwin; }
+        if (amb || long_k) { o.wrec += (uint64_t)nwin * mult; hw[o.wide++] = i; if (target) o.pwide += nwin; }
       }
     });
     // clusters without sequences are empty ranges at the start of the next non-empty one
@@ -449,7 +451,7 @@ int upload_async(pf_ctx* ctx, BatchState& B, const pf_batch* full, const SubRang
         B.d_tile_first_seq.as<uint32_t>());
     ctx->launches += 2;
   }
-  if (n_wide) {
+  if (n_wide && !long_k) {
     const size_t bit_words = (b->n_amb_words + 1) / 2 + 4;
     TRY(dev_ensure(ctx, B.d_amb, (b->n_amb_words + 8) * 8));
     TRY(dev_ensure(ctx, B.d_ambbits, bit_words * 4));

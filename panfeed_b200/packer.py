@@ -215,11 +215,18 @@ def kmers_to_str(kmers, k):
 
 
 def wide_kmers_to_str(kmers, k):
-    """[n,2] uint64 (hi, lo) 4-bit k-mers -> numpy bytes array S{k}."""
+    """[n,2] uint64 (hi, lo) two-word k-mers -> numpy bytes array S{k}: 4 bits per symbol
+    (N/IUPAC k-mers, k <= 32) or, for k > 32, 2 bits per base."""
     kmers = np.asarray(kmers, np.uint64).reshape(-1, 2)
     if kmers.shape[0] == 0:
         return np.zeros(0, f"S{k}")
     out = np.zeros((kmers.shape[0], k), np.uint8)
+    if k > 32:
+        for i in range(k):
+            pos = 2 * (k - 1 - i)
+            word = kmers[:, 1] >> np.uint64(pos) if pos < 64 else kmers[:, 0] >> np.uint64(pos - 64)
+            out[:, i] = _ACGT[(word & np.uint64(3)).astype(np.uint8)]
+        return np.ascontiguousarray(out).view(f"S{k}").ravel()
     for i in range(k):
         nib = k - 1 - i                    # nibble index from the bottom
         word = kmers[:, 1] if nib < 16 else kmers[:, 0]

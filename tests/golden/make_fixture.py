@@ -10,6 +10,7 @@ the layout `tests/unit_test.sh:18-52` expects:
     fixture/gene_presence_absence.csv    panaroo table
     fixture/stroi.txt                    --targets
     fixture/genes.txt                    --genes (second pass)
+    fixture/genes_acgt.txt               --genes: the clusters without N/IUPAC symbols (k > 32 modes)
     fixture/input_gffs.txt, input_fastas.txt
 
 It deliberately covers: both strands, paralogs (';'), a refound gene whose ID
@@ -158,6 +159,9 @@ def build(outdir, seed=20261018):
         fh.write("s01\ns02\ns05\n")
     with open(os.path.join(outdir, "genes.txt"), "w") as fh:
         fh.write("group_acc1\ngroup_para\ngroup_edge\n")
+    # the clusters without N/IUPAC symbols (k > 32 runs: two-word k-mers take plain bases only)
+    with open(os.path.join(outdir, "genes_acgt.txt"), "w") as fh:
+        fh.write("group_core\ngroup_acc1\ngroup_acc2\ngroup_short\ngroup_single\n")
     with open(os.path.join(outdir, "input_gffs.txt"), "w") as fh:
         for g in genomes:
             fh.write(os.path.join("fixture", "gffs", f"{g}.gff") + "\n")

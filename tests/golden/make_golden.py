@@ -50,6 +50,10 @@ MODES = {
                               "100", "--downstream", "100"],
     "k15": BASE + T + ["-k", "15", "--upstream", "30", "--downstream", "30"],
     "k32": BASE + T + ["-k", "32"],
+    # k > 32 (two-word k-mers here; the clusters without N/IUPAC symbols)
+    "k40": BASE + T + ["-k", "40", "--upstream", "30", "--downstream", "30", "--genes", "fixture/genes_acgt.txt"],
+    "k64_nc": BASE + T + ["-k", "64", "--non-canonical", "--upstream", "60", "--downstream", "60",
+                          "--maf", "0.1", "--genes", "fixture/genes_acgt.txt"],
     "cm_nofilter_up": BASE + T + ["--consider-missing", "--no-filter",
                                   "--upstream", "100", "--downstream", "100",
                                   "--maf", "0.2"],

@@ -119,6 +119,10 @@ CASES = [
     (5,   4,  3, 60,  True,  False, False, 0.0,  0.0,  8, 3),    # tiny even k: palindromes
     (1,   31, 2, 100, True,  False, False, 0.01, 0.0,  0, 2),    # single sample
     (600, 31, 2, 700, True,  False, False, 0.01, 0.0,  0, 1),    # multi-tile segments
+    # k > 32: two-word k-mers through the 128-bit record pipeline
+    (40,  33, 4, 300, True,  False, False, 0.01, 0.0,  0, 2),
+    (70,  48, 3, 250, False, True,  True,  0.05, 0.0,  16, 3),
+    (33,  64, 3, 200, True,  True,  False, 0.02, 0.0,  0, 1),
 ]
 
 
@@ -130,10 +134,12 @@ def test_random_clusters_match_oracle(case, engine):
     items, stroi = _random_items(rng, S, k, nc, L, amb)
     out, _ = _compare_with_oracle(items, stroi, S, k, canon, cm, nf, maf,
                                   batch_clusters=bc, sort_bits=sb, **ENGINES[engine])
-    if engine == "block" and not (k == 32 and not canon):
+    if engine == "block" and k <= 32 and not (k == 32 and not canon):
         assert out["stats"]["engine"] == 2
     else:
         assert out["stats"]["engine"] == (1 if engine == "fullsort" else 0)
+    if k > 32:
+        assert len(out["row_kmer"]) > 0 and all(len(x) == k for x in out["row_kmer"][:50])
 
 
 @pytest.mark.parametrize("case", CASES[:6], ids=[str(i) for i in range(6)])
