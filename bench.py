@@ -566,9 +566,7 @@ def make_context(cfg, env, args):
 
 
 def h2d_bytes(hb):
-    """Bytes pf_submit copies to the device: the packed plane, the 24 bytes of every 48-byte
-    descriptor the device needs (device-side planning), cluster descriptors and presence words."""
-    return int(hb.packed.nbytes + hb.seqs.nbytes // 2 + hb.clusters.nbytes + hb.presence.nbytes)
+    return int(hb.packed.nbytes + hb.seqs.nbytes + hb.clusters.nbytes + hb.presence.nbytes)
 
 
 STAGE_KEYS = ("ms_extract", "ms_hist", "ms_sort", "ms_mark", "ms_count", "ms_reduce", "ms_dedup", "ms_total")

@@ -77,10 +77,8 @@ __global__ void plan_seq_lite(const SeqDev* __restrict__ seqs, uint32_t n, SeqLi
 }
 
 // ---------------------------------------------------------------------------
-// Device-side planning of an upload ("lite" upload): the first 24 bytes of every caller
-// pf_seq_desc (plane offset, length, cluster, sample, flags: the coordinate fields are only needed
-// by the host-side formatter) go to the device and ONE kernel does what the host planner does per
-// sequence - validation
+// Device-side planning of an upload ("lite" upload): the caller's pf_seq_desc array goes to the
+// device as it is and ONE kernel does what the host planner does per sequence - validation
 // (include/panfeed_b200.h: pf_seq_desc), rebasing to the sub-range, the 64-byte SeqDev and the
 // 16-byte SeqLite - plus the batch totals.  The host then touches no descriptor at all: with
 // several ranks sharing the host's cores the per-sequence planning (~15 ns per sequence and
@@ -88,11 +86,6 @@ __global__ void plan_seq_lite(const SeqDev* __restrict__ seqs, uint32_t n, SeqLi
 // record offsets are computed); a batch that falls back to the record engine is re-planned on
 // the host from the device copy of the descriptors.
 // ---------------------------------------------------------------------------
-struct SeqUp {               // the first 24 bytes of a pf_seq_desc: all the device needs of it here
-  uint64_t base_off;
-  uint32_t len, cluster, sample, flags;
-};
-static_assert(sizeof(SeqUp) == 24, "SeqUp");
 struct LiteTotals {          // 64 bytes, zeroed (err = all ones) before the kernel
   unsigned long long bases, windows, pos_windows;
   unsigned long long err;    // min over bad sequences of (index << 32 | code); ~0 = none
@@ -102,7 +95,7 @@ enum : uint32_t { kLiteErrCluster = 1, kLiteErrClusterOrder, kLiteErrSample, kLi
                   kLiteErrAlign, kLiteErrPlane, kLiteErrStrand, kLiteErrAmbiguous, kLiteErrOrder };
 
 __global__ void __launch_bounds__(256)
-plan_from_raw(const SeqUp* __restrict__ raw, uint32_t n, uint32_t cluster_base, uint64_t base_rebase,
+plan_from_raw(const pf_seq_desc* __restrict__ raw, uint32_t n, uint32_t cluster_base, uint64_t base_rebase,
               uint32_t n_clusters, uint32_t S, uint32_t W, const uint32_t* __restrict__ presence,
               uint64_t plane_bases, int k, uint32_t emit_positions, SeqDev* __restrict__ out,
               SeqLite* __restrict__ lite, LiteTotals* __restrict__ tot) {
@@ -110,7 +103,7 @@ plan_from_raw(const SeqUp* __restrict__ raw, uint32_t n, uint32_t cluster_base, 
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long bases = 0, windows = 0, posw = 0;
   if (i < n) {
-    const SeqUp q = raw[i];
+    const pf_seq_desc q = raw[i];
     uint32_t err = 0;
     const uint32_t cluster = q.cluster - cluster_base;
     const uint64_t base_off = q.base_off - base_rebase;
@@ -119,9 +112,10 @@ plan_from_raw(const SeqUp* __restrict__ raw, uint32_t n, uint32_t cluster_base, 
     else if (!((presence[(size_t)cluster * W + (q.sample >> 5)] >> (q.sample & 31u)) & 1u)) err = kLiteErrPresence;
     else if (q.base_off < base_rebase || (base_off & 63u)) err = kLiteErrAlign;
     else if (base_off + q.len > plane_bases) err = kLiteErrPlane;
+    else if (q.strand != 1 && q.strand != -1) err = kLiteErrStrand;
     else if (q.flags & PF_SEQ_AMBIGUOUS) err = kLiteErrAmbiguous;
     else if (i) {
-      const SeqUp p = raw[i - 1];
+      const pf_seq_desc p = raw[i - 1];
       if (q.cluster < p.cluster) err = kLiteErrClusterOrder;
       else if (q.cluster == p.cluster && q.sample < p.sample) err = kLiteErrSampleOrder;
     }
@@ -132,7 +126,7 @@ plan_from_raw(const SeqUp* __restrict__ raw, uint32_t n, uint32_t cluster_base, 
       SeqDev d;
       d.base_off = base_off; d.amb_off = 0; d.len = q.len; d.sample = q.sample; d.cluster = cluster;
       d.flags = target ? 1u : 0u;
-      d.start = 0; d.end = 0; d.offset = 0; d.strand = 1;     // (coordinates stay with the caller: see pf_format_positions_compact)
+      d.start = q.start; d.end = q.end; d.offset = q.offset; d.strand = q.strand;
       d.rec_off = 0; d.pos_off = 0; d.wrec_off = 0; d.pwide_off = 0;
       out[i] = d;
       SeqLite l;

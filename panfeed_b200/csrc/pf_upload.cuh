@@ -169,32 +169,29 @@ int upload_async_lite(pf_ctx* ctx, BatchState& B, const pf_batch* b, uint32_t rc
   CU(cudaEventRecord(B.ev_h2d[0], st));
   if (b->n_words) CU(cudaMemcpyAsync(B.d_bases.p, b->packed_bases, b->n_words * 8, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync((char*)B.d_bases.p + b->n_words * 8, 0, slack_words * 8, st));
-  // descriptors: the 24 bytes the device needs of each, gathered into the slot's pinned staging
-  // buffer by the planning threads (a strided copy; the strand is checked on the way: it is not
-  // among those bytes) - half the bytes of the descriptor array on the PCIe link
-  static_assert(sizeof(pf_seq_desc) == 48 && offsetof(pf_seq_desc, flags) == 20, "pf_seq_desc layout");
-  TRY(dev_ensure(ctx, B.d_raw, (size_t)std::max(1u, n) * sizeof(SeqUp)));
-  TRY(pin_ensure(ctx, B.h_raw, (size_t)std::max(1u, n) * sizeof(SeqUp)));
-  {
+  // descriptors: straight from the caller's array if it is pinned, else through the slot's pinned
+  // staging buffer (a plain copy on the planning threads; a pageable cudaMemcpyAsync would block)
+  TRY(dev_ensure(ctx, B.d_raw, (size_t)n * sizeof(pf_seq_desc)));
+  const void* src = b->seqs;
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, b->seqs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!pinned) {
+    cudaGetLastError();
+    TRY(pin_ensure(ctx, B.h_raw, (size_t)n * sizeof(pf_seq_desc)));
     static const uint32_t host_thr = []() { const char* e = getenv("PF_HOST_THREADS"); const int v = e ? atoi(e) : 0;
                                             return v > 0 ? (uint32_t)v : 8u; }();
     const uint32_t n_thr = std::max(1u, std::min<uint32_t>(std::min(host_thr, std::thread::hardware_concurrency()),
                                                            (n + 65535u) / 65536u));
     const uint32_t per = (n + n_thr - 1) / n_thr;
-    SeqUp* dst = B.h_raw.as<SeqUp>();
-    const pf_seq_desc* from = b->seqs;
-    std::vector<uint32_t> bad_strand(n_thr, 0xffffffffu);
+    char* dst = B.h_raw.as<char>();
+    const char* from = reinterpret_cast<const char*>(b->seqs);
     ctx->pool.parallel(n_thr, [&](uint32_t t) {
-      const uint32_t i0 = std::min(n, t * per), i1 = std::min(n, i0 + per);
-      for (uint32_t i = i0; i < i1; ++i) {
-        memcpy(&dst[i], &from[i], sizeof(SeqUp));
-        if (from[i].strand != 1 && from[i].strand != -1 && bad_strand[t] == 0xffffffffu) bad_strand[t] = i;
-      }
+      const size_t i0 = std::min<size_t>(n, (size_t)t * per), i1 = std::min<size_t>(n, i0 + per);
+      memcpy(dst + i0 * sizeof(pf_seq_desc), from + i0 * sizeof(pf_seq_desc), (i1 - i0) * sizeof(pf_seq_desc));
     });
-    for (uint32_t t = 0; t < n_thr; ++t)
-      if (bad_strand[t] != 0xffffffffu) return fail(ctx, PF_ERR_INVALID, "seq %u: strand must be +1/-1", bad_strand[t]);
+    src = dst;
   }
-  CU(cudaMemcpyAsync(B.d_raw.p, B.h_raw.p, (size_t)n * sizeof(SeqUp), cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(B.d_raw.p, src, (size_t)n * sizeof(pf_seq_desc), cudaMemcpyHostToDevice, st));
   // clusters
   TRY(pin_ensure(ctx, B.h_clusters, std::max<size_t>(1, nc) * sizeof(ClusterDev)));
   TRY(build_clusters(ctx, b, B.h_clusters.as<ClusterDev>(), nullptr, nullptr));
@@ -211,7 +208,7 @@ int upload_async_lite(pf_ctx* ctx, BatchState& B, const pf_batch* b, uint32_t rc
   CU(cudaMemcpyAsync(B.d_presence.p, B.lite_presence.data(), (size_t)nc * W * 4, cudaMemcpyHostToDevice, st));
   CU(cudaMemsetAsync(B.d_lite_tot.p, 0, 24, st));
   CU(cudaMemsetAsync((char*)B.d_lite_tot.p + 24, 0xff, 8, st));
-  plan_from_raw<<<cdiv(n, 256), 256, 0, st>>>(B.d_raw.as<SeqUp>(), n, rc, rb, nc, P.n_samples, W,
+  plan_from_raw<<<cdiv(n, 256), 256, 0, st>>>(B.d_raw.as<pf_seq_desc>(), n, rc, rb, nc, P.n_samples, W,
                                                B.d_presence.as<uint32_t>(), b->n_words * 32ull, (int)P.k,
                                                P.emit_positions, B.d_seqs.as<SeqDev>(), B.d_seq_lite.as<SeqLite>(),
                                                B.d_lite_tot.as<LiteTotals>());
@@ -508,16 +505,10 @@ int upload_finish_slot(pf_ctx* ctx, BatchState& B, cudaStream_t compute) {
 int replan_full(pf_ctx* ctx) {
   BatchState& B = *ctx;
   if (!B.lite) return PF_OK;
-  std::vector<SeqUp> up(B.n_seqs);
-  CU(cudaStreamSynchronize(ctx->stream));
-  if (B.n_seqs) CU(cudaMemcpy(up.data(), B.d_raw.p, (size_t)B.n_seqs * sizeof(SeqUp), cudaMemcpyDeviceToHost));
   std::vector<pf_seq_desc> raw(B.n_seqs);
-  for (uint32_t i = 0; i < B.n_seqs; ++i) {      // (no positional records in a lite slot: the coordinates are not needed)
-    pf_seq_desc q{};
-    q.base_off = up[i].base_off - B.lite_b0; q.len = up[i].len; q.cluster = up[i].cluster - B.lite_c0;
-    q.sample = up[i].sample; q.flags = up[i].flags; q.strand = 1;
-    raw[i] = q;
-  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (B.n_seqs) CU(cudaMemcpy(raw.data(), B.d_raw.p, (size_t)B.n_seqs * sizeof(pf_seq_desc), cudaMemcpyDeviceToHost));
+  for (auto& q : raw) { q.cluster -= B.lite_c0; q.base_off -= B.lite_b0; }
   pf_batch v{};
   v.n_words = B.n_words;
   v.seqs = raw.data(); v.n_seqs = B.n_seqs;
