@@ -49,10 +49,10 @@ CONFIGS = {
     3: dict(samples=500, clusters=200, cm=False, targets=True, batch=200, scaling="strong",
             name="BASELINE.json configs[2]: same pangenome, second pass over 200 clusters, every "
                  "sample a --targets strain (positional kmers.tsv records)"),
-    4: dict(samples=10000, clusters=5000, cm=False, targets=False, batch=96, scaling="strong",
+    4: dict(samples=10000, clusters=5000, cm=False, targets=False, batch=240, scaling="strong",
             name="BASELINE.json configs[3]: synthetic 10,000 genomes x 5,000 clusters "
                  "(10k-bit presence patterns), clusters sharded over the ranks"),
-    5: dict(samples=50000, clusters=1000, cm=True, targets=False, batch=20, scaling="weak",
+    5: dict(samples=50000, clusters=1000, cm=True, targets=False, batch=60, scaling="weak",
             name="BASELINE.json configs[4]: synthetic 50,000 genomes x 8,000 clusters, cluster-absent "
                  "encoding, global pattern dedup over NCCL; 1,000 clusters per rank (= the full "
                  "8,000 at N = 8)"),

@@ -909,6 +909,8 @@ kB3_emit(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ sl
       out.kmer[gi] = slab_keys[base + i];
       out.count[gi] = cnt;
       uint32_t* dst = out.cand + gi * out.key_words;
+      // (one row per half-warp through shuffles, so that loads and stores are coalesced segments,
+      //  was measured and is slower: kB 2.48 against 2.06 ms per config-2 step)
       const uint4* row = row_of(i);
       for (uint32_t q = 0; q < WP / 4; ++q) {
         const uint4 x = row[q];
@@ -935,22 +937,43 @@ kB3_emit(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ sl
 
 // ---------------------------------------------------------------------------
 // sample slices: a k-mer's bitset is spread over up to n_slices partial rows (one per slice,
-// after kB1 merged the rows of the same slice).  kB4 links them per k-mer in a cross-slice
-// table of the cluster and sums the popcounts; kB5 applies the MAF window to the sum and
-// assembles the full-width bitsets of the survivors.
+// after kB1 merged the rows of the same slice).  kB4 sums the popcounts per k-mer in a cross-slice
+// table of the cluster; kB5 applies the MAF window to the sum, hands the survivors (~1 % of the
+// k-mers at 10,000 samples) their output row and clears it; kB6 goes over the partial rows once
+// more and copies those of a surviving k-mer to their place in its row.  (An earlier version
+// chained the rows of a k-mer through a linked list and assembled the row by walking it: a
+// dependent load per slice.  Now every step is parallel over rows or table slots.)
 // ---------------------------------------------------------------------------
-struct LinkEntry {         // 16 bytes, memset to 0xff: key empty, head nil, count = -1
+struct LinkEntry {         // 16 bytes, memset to 0xff: key empty, row nil, count = -1
   unsigned long long key;
-  uint32_t head;           // last linked partial row (chain through `next`)
+  uint32_t row;            // kB5: output row of a surviving k-mer
   uint32_t count;          // (sum of popcounts) - 1
 };
 
+__device__ __forceinline__ uint32_t partial_row_count(const uint32_t* __restrict__ slab_rows,
+                                                      const uint32_t* __restrict__ slab_cnt, uint32_t p, uint32_t WP) {
+  uint32_t cnt = slab_cnt[p];
+  if (cnt == kCntDirty) {                      // another row of the k-mer was folded in: recount
+    const uint4* row = reinterpret_cast<const uint4*>(slab_rows + (size_t)p * WP);
+    cnt = 0;
+    for (uint32_t q = 0; q < WP / 4; ++q) {
+      const uint4 x = row[q];
+      cnt += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
+    }
+  }
+  return cnt;
+}
+
+// one warp per kA work item, one row per lane and turn.  (Four rows per lane in flight measured
+// slower, 0.49 against 0.39 ms on 48 clusters of 10,000 samples: the registers cost occupancy, and
+// visiting the slices of a run far apart in time was slower still, 0.76 ms: the 20 slices of a
+// k-mer hitting its entry together is what keeps the table in L2.)
 __global__ void __launch_bounds__(256)
 kB4_link(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_rows,
          const uint32_t* __restrict__ slab_base, const uint32_t* __restrict__ slab_count,
          const uint32_t* __restrict__ item_cluster, uint32_t n_items, uint32_t n_slices,
          const uint32_t* __restrict__ slab_cnt, const uint32_t* __restrict__ table2_base /* CTAs of 256 slots */,
-         LinkEntry* __restrict__ table2, uint32_t* __restrict__ next, uint32_t WP) {
+         LinkEntry* __restrict__ table2, uint32_t WP) {
   const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (item >= n_items) return;
   const uint32_t n = slab_count[item];
@@ -958,42 +981,33 @@ kB4_link(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ sl
   const uint32_t c = item_cluster[item / n_slices];
   const uint32_t tb = table2_base[c] * 256u, ts = (table2_base[c + 1] - table2_base[c]) * 256u;
   const uint32_t base = slab_base[item];
-  for (uint32_t i = lane_id(); i < n; i += 32) {
-    const uint32_t p = base + i;
-    uint32_t cnt = slab_cnt[p];
-    if (cnt == kCntDead) continue;                          // folded into an earlier row of its slice
-    if (cnt == kCntDirty) {
-      const uint4* row = reinterpret_cast<const uint4*>(slab_rows + (size_t)p * WP);
-      cnt = 0;
-      for (uint32_t q = 0; q < WP / 4; ++q) {
-        const uint4 x = row[q];
-        cnt += __popc(x.x) + __popc(x.y) + __popc(x.z) + __popc(x.w);
-      }
-    }
-    const uint64_t key = slab_keys[p];
+  for (uint32_t i = lane_id(); i < n; i += 32u) {
+    const uint32_t cnt = partial_row_count(slab_rows, slab_cnt, base + i, WP);
+    if (cnt == kCntDead) continue;              // folded into an earlier row of its slice
+    const unsigned long long key = slab_keys[base + i];
     uint32_t s = __umulhi((uint32_t)(mix64(key) >> 32), ts);
-    for (;;) {
-      const unsigned long long old = atomicCAS(&table2[tb + s].key, ~0ull, (unsigned long long)key);
-      if (old == ~0ull || old == key) break;
+    for (;;) {                                  // find or insert, linear probing
+      const unsigned long long o = atomicCAS(&table2[tb + s].key, ~0ull, key);
+      if (o == ~0ull || o == key) break;
       if (++s == ts) s = 0;
     }
     atomicAdd(&table2[tb + s].count, cnt);
-    next[p] = atomicExch(&table2[tb + s].head, p);
   }
 }
 
 // one CTA per 256 slots of a cluster's cross-slice table
 __global__ void __launch_bounds__(256)
-kB5_emit(const LinkEntry* __restrict__ table2, const uint32_t* __restrict__ cta_cluster,
-         const uint32_t* __restrict__ next, const uint16_t* __restrict__ pslice,
-         const uint32_t* __restrict__ slab_rows, const ClusterDev* __restrict__ clusters, RowOut out,
-         uint32_t row_capacity, uint32_t* __restrict__ counters, uint32_t W, uint32_t Ws, uint32_t WP) {
+kB5_emit(LinkEntry* __restrict__ table2, const uint32_t* __restrict__ cta_cluster,
+         const uint32_t* __restrict__ table2_base, uint32_t* __restrict__ home_bits,
+         const ClusterDev* __restrict__ clusters, RowOut out, uint32_t row_capacity,
+         uint32_t* __restrict__ counters, uint32_t W) {
   __shared__ uint32_t w_pass[8], w_used[8];
   __shared__ uint32_t cta_base, cta_ok;
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   const uint32_t c = cta_cluster[blockIdx.x];
   const ClusterDev cl = clusters[c];
-  const LinkEntry e = table2[(size_t)blockIdx.x * 256u + threadIdx.x];
+  const size_t slot = (size_t)blockIdx.x * 256u + threadIdx.x;
+  const LinkEntry e = table2[slot];
   const bool used = e.key != ~0ull;
   const uint32_t total = e.count + 1u;
   const bool pass = used && total >= cl.lo && total <= cl.hi;
@@ -1015,31 +1029,73 @@ kB5_emit(const LinkEntry* __restrict__ table2, const uint32_t* __restrict__ cta_
   __syncthreads();
   if (!cta_ok || mp == 0u) return;
   const uint32_t g0 = cta_base + w_pass[warp];
-  // the warp writes its surviving rows one after the other: clear the row, then copy every
-  // linked slice to its place
-  uint32_t rest = mp, r = 0;
-  while (rest) {
-    const int src_lane = __ffs(rest) - 1;
-    rest &= rest - 1u;
-    const unsigned long long key = __shfl_sync(kFull, e.key, src_lane);
-    const uint32_t tot = __shfl_sync(kFull, total, src_lane);
-    uint32_t p = __shfl_sync(kFull, e.head, src_lane);
-    const size_t gi = (size_t)g0 + r;
-    ++r;
-    uint32_t* dst = out.cand + gi * out.key_words;
+  if (pass) {
+    const size_t gi = (size_t)g0 + __popc(mp & lanemask_lt());
+    out.cluster[gi] = cl.id;
+    out.kmer[gi] = e.key;
+    out.count[gi] = total;
+    table2[slot].row = (uint32_t)gi;             // kB6 copies the k-mer's slices there
+    // ... and finds the few survivors through one bit per table slot, set at the HOME slot of
+    // the key (a few MB, resident in L2), instead of probing the table for every partial row
+    const uint32_t tb = table2_base[c] * 256u, ts = (table2_base[c + 1] - table2_base[c]) * 256u;
+    const uint32_t home = tb + __umulhi((uint32_t)(mix64(e.key) >> 32), ts);
+    atomicOr(&home_bits[home >> 5], 1u << (home & 31));
+  }
+  // the warp clears its surviving rows one after the other, all lanes on one row
+  for (uint32_t r = 0, n = (uint32_t)__popc(mp); r < n; ++r) {
+    uint32_t* dst = out.cand + ((size_t)g0 + r) * out.key_words;
     for (uint32_t w = lane; w < W; w += 32) dst[w] = 0u;
-    if (lane == 0) {
-      out.cluster[gi] = cl.id;
-      out.kmer[gi] = key;
-      out.count[gi] = tot;
-      if (out.key_words > W) dst[W] = out.cluster_pattern[c];
+    if (lane == 0 && out.key_words > W) dst[W] = out.cluster_pattern[c];
+  }
+}
+
+// one warp per kA work item: the partial rows of surviving k-mers go to their slice of the row
+__global__ void __launch_bounds__(256)
+kB6_scatter(const uint64_t* __restrict__ slab_keys, const uint32_t* __restrict__ slab_rows,
+            const uint32_t* __restrict__ slab_base, const uint32_t* __restrict__ slab_count,
+            const uint32_t* __restrict__ item_cluster, uint32_t n_items, uint32_t n_slices,
+            const uint32_t* __restrict__ slab_cnt, const uint32_t* __restrict__ table2_base,
+            const LinkEntry* __restrict__ table2, const uint32_t* __restrict__ home_bits, RowOut out, uint32_t W,
+            uint32_t Ws, uint32_t WP) {
+  const uint32_t item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (item >= n_items) return;
+  const uint32_t n = slab_count[item];
+  if (n == kBlkOverflow || n == 0) return;
+  const uint32_t run_item = item / n_slices, slice = item - run_item * n_slices;
+  const uint32_t c = item_cluster[run_item];
+  const uint32_t tb = table2_base[c] * 256u, ts = (table2_base[c + 1] - table2_base[c]) * 256u;
+  const uint32_t base = slab_base[item];
+  const uint32_t w0 = slice * Ws;
+  const uint32_t lane = lane_id();
+  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+    const uint32_t p = base + i0 + lane;
+    uint32_t g = 0xffffffffu;
+    if (i0 + lane < n && slab_cnt[p] != kCntDead) {      // (dead: folded into an earlier row of its slice)
+      const unsigned long long key = slab_keys[p];
+      uint32_t s = __umulhi((uint32_t)(mix64(key) >> 32), ts);
+      if ((home_bits[(tb + s) >> 5] >> ((tb + s) & 31)) & 1u) {      // a survivor lives at this home slot
+        uint32_t probes = 0;                             // (kB4 put the key there; bounded all the same)
+        while (table2[tb + s].key != key && ++probes <= ts) { if (++s == ts) s = 0; }
+        if (probes <= ts) g = table2[tb + s].row;        // nil: its k-mer did not pass the window
+      }
     }
-    __syncwarp();
-    while (p != 0xffffffffu) {
-      const uint32_t w0 = (uint32_t)pslice[p] * Ws;
-      const uint32_t* src = slab_rows + (size_t)p * WP;
-      for (uint32_t w = lane; w < Ws && w0 + w < W; w += 32) dst[w0 + w] = src[w];
-      p = next[p];
+    // the rows of survivors (a fifth of the partial rows: surviving k-mers sit in most slices) are
+    // copied by half-warps, two rows per instruction, 64 B coalesced: ms_count of config 4 129.0
+    // against 135.7 ms with every lane copying its own row
+    uint32_t m = __ballot_sync(kFull, g != 0xffffffffu);
+    while (m) {
+      const int l0 = __ffs(m) - 1;
+      m &= m - 1;
+      const int l1 = m ? __ffs(m) - 1 : -1;
+      if (m) m &= m - 1;
+      const int from = lane < 16 ? l0 : l1;
+      const uint32_t gg = __shfl_sync(kFull, g, from < 0 ? 0 : from);
+      const uint32_t pp = __shfl_sync(kFull, p, from < 0 ? 0 : from);
+      if (from >= 0) {
+        const uint32_t* src = slab_rows + (size_t)pp * WP;
+        uint32_t* dst = out.cand + (size_t)gg * out.key_words + w0;
+        for (uint32_t w = lane & 15u; w < Ws && w0 + w < W; w += 16u) dst[w] = src[w];
+      }
     }
   }
 }

@@ -321,7 +321,7 @@ struct pf_ctx : BatchState {
   bool used_block = false;       // the last batch went through kA/kB
   DevBuf d_slab_base, d_slab_count, d_slab_keys, d_slab_rows,
       d_group_base /* merge-table offsets per (cluster, slice) */, d_mtable,
-      d_table2_base, d_table2, d_next, d_pslice, d_cta_cluster, d_slab_cnt, d_rescue[2],
+      d_table2_base, d_table2, d_home_bits, d_cta_cluster, d_slab_cnt, d_rescue[2],
       d_spill /* (cluster, slice) merged in the global table */;
   uint32_t merge_fp_mask = 0x7fffu;   // PF_MERGE_FP_BITS (tests: a 1-bit fingerprint exercises the mismatch path)
   uint32_t merge_slots = 49152;  // shared-memory merge table of kB1_local (PF_MERGE_SMEM_KB)
@@ -469,6 +469,7 @@ int pool_map_to(pf_ctx* ctx, PoolBuf& b, size_t cur_cap, size_t want, size_t flo
   floor_bytes = (floor_bytes + gran - 1) / gran * gran;
   if (floor_bytes > b.reserved) return PF_ERR_NOMEM;
   CUmemGenericAllocationHandle h = 0;
+  const auto t0 = std::chrono::steady_clock::now();
   CUresult r = want > cur_cap ? api.create(&h, want - cur_cap, &prop, 0) : CUDA_ERROR_INVALID_VALUE;
   if (r != CUDA_SUCCESS && floor_bytes > cur_cap && floor_bytes < want) {     // no room for the generous step: the exact one
     want = floor_bytes;
@@ -485,6 +486,9 @@ int pool_map_to(pf_ctx* ctx, PoolBuf& b, size_t cur_cap, size_t want, size_t flo
   }
   b.chunks.emplace_back(h, got);
   *cap_out = want;
+  if (debug_alloc())
+    fprintf(stderr, "[pf] alloc: mapped %zu MB behind a pool (now %zu MB) in %.1f ms\n", got >> 20, want >> 20,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   return PF_OK;
 }
 

@@ -471,7 +471,6 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
   const uint64_t n_slots = ((uint64_t)n_partials * eighths + 7) / 8 + 3ull * n_cs + 16;   // >= sum of ceil(p e / 8) + 2
   if (n_slots >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "too many partial rows for one batch; split it");
   TRY(dev_ensure(ctx, ctx->d_mtable, n_slots * sizeof(MergeEntry)));
-  if (ns > 1) TRY(dev_ensure(ctx, ctx->d_pslice, (size_t)n_partials * 2));
   TRY(dev_ensure(ctx, ctx->d_spill, std::max<size_t>(1, n_cs)));
   CU(cudaMemsetAsync(counters + C_LOCAL + LC_RESCUE, 0, 4, st));     // kB1 counts the folded rows there
   // shared-memory merge per (cluster, slice); clusters too large for it clear their region of the
@@ -480,7 +479,7 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
       ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(), ctx->d_slab_cnt.as<uint32_t>(),
       ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(), ctx->d_item_base.as<uint32_t>(), ns,
       ctx->d_group_base.as<uint32_t>(), ctx->d_mtable.as<MergeEntry>(),
-      ns > 1 ? ctx->d_pslice.as<uint16_t>() : nullptr, WP, counters + C_LOCAL, ctx->merge_slots,
+      nullptr, WP, counters + C_LOCAL, ctx->merge_slots,
       ctx->d_spill.as<uint8_t>(), ctx->merge_fp_mask);
   ctx->launches++;
   const uint32_t g0 = cdiv((uint64_t)n_it * 32, 256);
@@ -488,7 +487,7 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
                                  ctx->d_slab_cnt.as<uint32_t>(), ctx->d_slab_base.as<uint32_t>(),
                                  ctx->d_slab_count.as<uint32_t>(), ctx->d_item_cluster.as<uint32_t>(), n_it, ns,
                                  ctx->d_group_base.as<uint32_t>(), ctx->d_mtable.as<MergeEntry>(),
-                                 ns > 1 ? ctx->d_pslice.as<uint16_t>() : nullptr, WP, counters + C_LOCAL,
+                                 nullptr, WP, counters + C_LOCAL,
                                  ctx->d_spill.as<uint8_t>());
   const uint32_t cap = (uint32_t)std::min<uint64_t>(ctx->row_cap, 0x7fffffffu);
   if (ns == 1) {
@@ -500,33 +499,38 @@ int launch_block_merge(pf_ctx* ctx, RowOut ro, uint32_t n_partials) {
     CU(cudaGetLastError());
     return PF_OK;
   }
-  // ---- sample slices: link the per-slice rows of a k-mer, filter on the summed count, assemble ----
+  // ---- sample slices: sum the per-slice counts of a k-mer, filter on the sum, assemble the survivors ----
   plan_table2_ctas<<<cdiv(nc, 256), 256, 0, st>>>(ctx->d_table2_base.as<uint32_t>(), nc);
   TRY(scan_inplace(ctx, ctx->d_table2_base.as<uint32_t>(), nc, ctx->d_plan_total.as<uint32_t>() + 2));
   const uint64_t max_ctas = ((uint64_t)n_partials + n_partials / 2) / 256 + 2ull * nc + 2;
   TRY(dev_ensure(ctx, ctx->d_table2, max_ctas * 256 * sizeof(LinkEntry)));
   TRY(dev_ensure(ctx, ctx->d_cta_cluster, max_ctas * 4));
-  TRY(dev_ensure(ctx, ctx->d_next, (size_t)n_partials * 4));
   CU(cudaMemsetAsync(ctx->d_table2.p, 0xff, max_ctas * 256 * sizeof(LinkEntry), st));
+  TRY(dev_ensure(ctx, ctx->d_home_bits, max_ctas * 32));      // one bit per slot
+  CU(cudaMemsetAsync(ctx->d_home_bits.p, 0, max_ctas * 32, st));
   plan_expand_owner<<<cdiv((uint64_t)nc * 32, 256), 256, 0, st>>>(ctx->d_table2_base.as<uint32_t>(), nc,
                                                                   ctx->d_cta_cluster.as<uint32_t>());
   kB4_link<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
                                ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(),
                                ctx->d_item_cluster.as<uint32_t>(), n_it, ns, ctx->d_slab_cnt.as<uint32_t>(),
-                               ctx->d_table2_base.as<uint32_t>(), ctx->d_table2.as<LinkEntry>(),
-                               ctx->d_next.as<uint32_t>(), WP);
+                               ctx->d_table2_base.as<uint32_t>(), ctx->d_table2.as<LinkEntry>(), WP);
   // grid of kB5 = CTAs of all cross-slice tables: one small read-back
   TRY(pin_ensure(ctx, ctx->h_plan, 16));
   mirror_counters<<<1, 32, 0, st>>>(ctx->h_plan.as<uint32_t>() + 2, ctx->d_plan_total.as<uint32_t>() + 2, 1);
   CU(cudaStreamSynchronize(st));
   const uint32_t n_ctas = ctx->h_plan.as<uint32_t>()[2];
   if (n_ctas > max_ctas) return fail(ctx, PF_ERR_INTERNAL, "cross-slice table larger than planned");
-  if (n_ctas)
+  if (n_ctas) {
     kB5_emit<<<n_ctas, 256, 0, st>>>(ctx->d_table2.as<LinkEntry>(), ctx->d_cta_cluster.as<uint32_t>(),
-                                     ctx->d_next.as<uint32_t>(), ctx->d_pslice.as<uint16_t>(),
-                                     ctx->d_slab_rows.as<uint32_t>(), ctx->d_clusters.as<ClusterDev>(), ro, cap,
-                                     counters + C_LOCAL, ctx->W, ctx->Ws, WP);
-  ctx->launches += 6;
+                                     ctx->d_table2_base.as<uint32_t>(), ctx->d_home_bits.as<uint32_t>(),
+                                     ctx->d_clusters.as<ClusterDev>(), ro, cap, counters + C_LOCAL, ctx->W);
+    kB6_scatter<<<g0, 256, 0, st>>>(ctx->d_slab_keys.as<uint64_t>(), ctx->d_slab_rows.as<uint32_t>(),
+                                    ctx->d_slab_base.as<uint32_t>(), ctx->d_slab_count.as<uint32_t>(),
+                                    ctx->d_item_cluster.as<uint32_t>(), n_it, ns, ctx->d_slab_cnt.as<uint32_t>(),
+                                    ctx->d_table2_base.as<uint32_t>(), ctx->d_table2.as<LinkEntry>(),
+                                    ctx->d_home_bits.as<uint32_t>(), ro, ctx->W, ctx->Ws, WP);
+  }
+  ctx->launches += 8;
   CU(cudaGetLastError());
   return PF_OK;
 }

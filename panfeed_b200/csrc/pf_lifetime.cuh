@@ -226,7 +226,7 @@ extern "C" void pf_destroy(pf_ctx* ctx) {
                     &ctx->d_cl_rep, &ctx->d_cl_slot, &ctx->d_cl_winner, &ctx->d_digests, &ctx->d_slab_base,
                     &ctx->d_slab_count, &ctx->d_slab_keys, &ctx->d_slab_rows, &ctx->d_group_base, &ctx->d_mtable,
                     &ctx->d_rescue[0], &ctx->d_rescue[1], &ctx->d_table2_base, &ctx->d_table2,
-                    &ctx->d_next, &ctx->d_pslice, &ctx->d_cta_cluster, &ctx->d_slab_cnt, &ctx->d_spill})
+                    &ctx->d_home_bits, &ctx->d_cta_cluster, &ctx->d_slab_cnt, &ctx->d_spill})
     fd(*b);
   ctx->grower.join();
   for (PatternSpace* s : {&ctx->kp, &ctx->cp}) pool_free(s->pool);
