@@ -501,8 +501,8 @@ void pool_join(pf_ctx* ctx, PoolBuf& b) {
 }
 
 // grow a pattern pool to at least `bytes`, keeping its contents (and, with VMM, its address).
-// Sizes double (from 256 MB), and once more than half of a pool is in use the next doubling is
-// mapped on the grower thread while the kernels run.
+// Small pools double; a pool that outgrows 256 MB takes one big step, and once 7/8 of that is in
+// use the next quarter is mapped on the grower thread while the kernels run.
 int pool_ensure(pf_ctx* ctx, PoolBuf& b, size_t bytes) {
   constexpr size_t kMinStep = (size_t)256 << 20;
   // doubling up to 4 GB, then a quarter at a time: the exchange of a sharded run needs room for
@@ -520,7 +520,7 @@ int pool_ensure(pf_ctx* ctx, PoolBuf& b, size_t bytes) {
     return std::max<size_t>((size_t)2 << 30, cap / 4);
   };
   auto prefetch = [&]() {
-    if (!b.vmm || b.growing || b.cap < kMinStep || bytes <= b.cap / 2 || b.cap >= b.reserved) return;
+    if (!b.vmm || b.growing || b.cap < kMinStep || bytes <= b.cap / 8 * 7 || b.cap >= b.reserved) return;
     const size_t cur = b.cap, want = cur + grow_step(cur);
     b.growing = true;
     b.grown_cap = cur;
