@@ -663,6 +663,8 @@ def run_streamed(cfg, env, args, passes=1, warm_passes=1):
                 exchange_ms_all.append(round((time.perf_counter() - t0) * 1e3, 2))
                 tot["patterns_global"] = out["kmer"]["n_global"]
                 tot["exchange_bytes_sent"] = out["kmer"]["bytes_sent"] + out["cluster"]["bytes_sent"]
+                if out["kmer"]["ms"].get("stages"):
+                    exchange_ms_all.append(out["kmer"]["ms"]["stages"])
         tot["cold_ms"] = cold_ms
         tot["exchange_ms_all"] = exchange_ms_all
         res[mode] = tot

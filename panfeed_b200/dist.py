@@ -115,6 +115,7 @@ class PatternExchange:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self._marks = None
         self.consider_missing = bool(getattr(ctx, "consider_missing", False)) if ctx is not None \
             else bool(getattr(backend, "consider_missing", False))
 
@@ -155,9 +156,11 @@ class PatternExchange:
         n_recv = sum(p["recv_counts"])
         recv = torch.empty((n_recv, p["send"].shape[1]), dtype=torch.int32, device=dev)
         self._a2a(recv, p["send"], p["recv_counts"], p["send_counts"])
+        self._mark(f"keys all-to-all ns{ns}")
         uniq_idx = torch.empty(n_recv, dtype=torch.int32, device=dev)
         nu = torch.zeros(1, dtype=torch.int32, device=dev)
         be.dedup(ns, recv, uniq_idx, nu, want_unique)
+        self._mark(f"owner dedup ns{ns}")
         all_nu = torch.empty(world, dtype=torch.int32, device=dev)
         self._gather(all_nu, nu)
         owner_base = (torch.cumsum(all_nu, 0, dtype=torch.int32) - all_nu).contiguous()
@@ -166,23 +169,37 @@ class PatternExchange:
         l2g = torch.empty(p["n_local"], dtype=torch.int32, device=dev)
         writer = torch.empty(p["n_local"], dtype=torch.uint8, device=dev) if want_writer else None
         be.unpack(ns, returned, owner_base, l2g, writer)
+        self._mark(f"ids back + unpack ns{ns}")
         p.update(local_to_global=l2g, writer=writer, all_nu=all_nu, keep=(recv, uniq_idx, returned, owner_base))
         return p
 
+    def _mark(self, name):
+        """PF_EXCHANGE_TIMING=1: an event on the exchange's stream at every stage boundary."""
+        if self._marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append((name, e))
+
     def run(self, want_unique=False, want_writer=False):
+        import os
         import time
         t0 = time.perf_counter()
         be = self.backend
         use_stream = self.device.type == "cuda" and hasattr(be, "stream")
+        self._marks = [] if (use_stream and os.environ.get("PF_EXCHANGE_TIMING")) else None
         with (torch.cuda.stream(be.stream()) if use_stream else _NoStream()):
+            self._mark("start")
             cl = self._pack(CLUSTER, None)
             if self.consider_missing:
                 # k-mer keys end with the GLOBAL id of the cluster pattern giving their NaN plane:
                 # the cluster namespace has to be numbered first
                 self._counts([cl])
                 self._finish(cl, want_writer, want_unique)
+                self._mark("cluster namespace")
                 km = self._pack(KMER, cl["local_to_global"])
+                self._mark("pack kmer")
                 self._counts([km])
+                self._mark("counts")
             else:
                 km = self._pack(KMER, None)
                 self._counts([cl, km])
@@ -190,12 +207,15 @@ class PatternExchange:
             self._finish(km, want_writer, want_unique)
             counts = torch.stack([cl["all_nu"], km["all_nu"]]).cpu().tolist()     # the final sync
         ms = (time.perf_counter() - t0) * 1e3
+        stages = None
+        if self._marks:
+            stages = [(b[0], round(a[1].elapsed_time(b[1]), 3)) for a, b in zip(self._marks, self._marks[1:])]
         out = {}
         for name, p, c in (("cluster", cl, counts[0]), ("kmer", km, counts[1])):
             out[name] = {"local_to_global": p["local_to_global"], "writer": p["writer"],
                          "n_global": int(sum(c)), "n_owned": int(c[self.rank]),
                          "owned_base": int(sum(c[:self.rank])), "bytes_sent": int(p["send"].numel() * 4),
-                         "ms": {"total_both_namespaces": ms}}
+                         "ms": {"total_both_namespaces": ms, "stages": stages}}
             if want_unique:
                 out[name]["owned_keys"] = be.unique_keys(p["ns"])
         return out
