@@ -669,6 +669,8 @@ def run_streamed(cfg, env, args, passes=1, warm_passes=1):
         tot["exchange_ms_all"] = exchange_ms_all
         res[mode] = tot
     engine = ctx.stats()["engine"]
+    if exch is not None:
+        exch.close()
     ctx.close()
     del arena, exch
     torch.cuda.empty_cache()        # the exchange buffers of this config (torch's caching allocator)
@@ -893,6 +895,8 @@ def main():
                 round((h2d + d2h) * args.steps / x / 1e9, 1) for x in env.gather(dt_rank)]
             e2e["pcie"] = measure_pcie(env)
             e2e["affinity_per_rank"] = env.gather(env.affinity)
+    if exch is not None:
+        exch.close()
     ctx.close()
     ctx = None
 

@@ -381,6 +381,32 @@ int pf_exchange_unpack(pf_ctx* ctx, int cluster_namespace,
                        uint32_t* local_to_global_dev /* [n local patterns] */,
                        uint8_t* writer_dev /* [n local patterns] or NULL */);
 
+/* The same exchange over peer memory (ranks of one box): the keys go straight from the local
+ * pattern pool into the OWNER's receive buffer with NVLink peer stores - no send buffer, no
+ * all-to-all of the keys.  Order of one namespace:
+ *   pf_exchange_classify     owners and bucket positions of the local patterns; bucket sizes on
+ *                            the host (one sync)
+ *   [all-gather of every rank's bucket sizes: rank r's bucket for owner o starts at row
+ *    sum of counts[r' -> o] over r' < r of o's receive buffer, which holds sum over all r']
+ *   pf_exchange_recv_buffer  this rank's receive buffer (library-owned, grows; a growth
+ *                            invalidates earlier handles: peers close their mappings first) and
+ *                            its CUDA IPC handle, which the caller passes to the peers
+ *   pf_exchange_open_peer    map a peer's receive buffer (cudaIpcOpenMemHandle); cache the result
+ *   pf_exchange_scatter      every local key to owner_buffer[owner] + (row0[owner] + position);
+ *                            asynchronous on the context's stream
+ *   [a barrier of all ranks on that stream: every scatter has completed]
+ *   pf_exchange_dedup on the receive buffer, then as above */
+int pf_exchange_classify(pf_ctx* ctx, int cluster_namespace, uint32_t world,
+                         const uint32_t* mask_remap_dev, uint64_t* counts_host /* [world] */);
+int pf_exchange_recv_buffer(pf_ctx* ctx, int cluster_namespace, uint64_t min_rows, void** dev_ptr,
+                            uint64_t* capacity_rows, unsigned char* ipc_handle_out /* 64 bytes */);
+int pf_exchange_open_peer(pf_ctx* ctx, const unsigned char* ipc_handle /* 64 bytes */, void** mapped);
+int pf_exchange_close_peer(pf_ctx* ctx, void* mapped);
+int pf_exchange_scatter(pf_ctx* ctx, int cluster_namespace, uint32_t world,
+                        const uint32_t* mask_remap_dev, void* const* dest_ptrs /* [world]: device
+                        pointers, the own buffer or pf_exchange_open_peer mappings */,
+                        const uint64_t* dest_row0 /* [world] */);
+
 /* ---- native feeder (host threads of the caller): GFF3 + FASTA -> cut sequences of a cluster ----
  * Replaces, for the feeding side of the path, the reference's parse_gff (input.py:274-332), its
  * pyfaidx contigs (input.py:262-266) and the per-strain loop of iter_gene_clusters

@@ -137,7 +137,8 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_tsv_filter", "pf_free",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_count", "pf_exchange_unique_export",
-           "pf_exchange_unpack"]
+           "pf_exchange_unpack", "pf_exchange_classify", "pf_exchange_recv_buffer", "pf_exchange_open_peer",
+           "pf_exchange_close_peer", "pf_exchange_scatter"]
 
 _lib = None
 
@@ -209,6 +210,11 @@ def load():
     lib.pf_exchange_unique_count.argtypes = [vp, C.c_int, C.POINTER(u64)]
     lib.pf_exchange_unique_export.argtypes = [vp, C.c_int, vp]
     lib.pf_exchange_unpack.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    lib.pf_exchange_classify.argtypes = [vp, C.c_int, u32, vp, C.POINTER(u64)]
+    lib.pf_exchange_recv_buffer.argtypes = [vp, C.c_int, u64, C.POINTER(vp), C.POINTER(u64), C.POINTER(C.c_ubyte)]
+    lib.pf_exchange_open_peer.argtypes = [vp, C.POINTER(C.c_ubyte), C.POINTER(vp)]
+    lib.pf_exchange_close_peer.argtypes = [vp, vp]
+    lib.pf_exchange_scatter.argtypes = [vp, C.c_int, u32, vp, C.POINTER(vp), C.POINTER(u64)]
     if lib.pf_abi_version() != PF_ABI_VERSION:
         raise PfError(-1, "ABI version mismatch")
     _lib = lib

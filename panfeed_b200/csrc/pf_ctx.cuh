@@ -102,7 +102,7 @@ struct PatternSpace {
   DevBuf table;           // table_size x u32
   uint32_t table_size = 0;
   // exchange state
-  DevBuf x_owner, x_pos, x_perm, x_counts, x_unique, x_table, x_rep, x_slot, x_winner;
+  DevBuf x_owner, x_pos, x_perm, x_counts, x_unique, x_table, x_rep, x_slot, x_winner, x_recv;
   uint64_t x_n_unique = 0;
   bool x_have_unique = false;           // x_unique holds the owner-side unique keys of the last exchange
   bool x_unique_pending = false;        // x_n_unique still sits in the pinned mirror below

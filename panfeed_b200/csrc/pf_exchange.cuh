@@ -81,6 +81,39 @@ x_pack(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
   }
 }
 
+// The same move without the send buffer and the all-to-all: every key goes straight to its
+// place in the OWNER's receive buffer, which this rank has mapped (CUDA IPC, NVLink peer
+// stores).  row0[o]: first row of this rank's bucket inside owner o's buffer; send0[o]: the
+// bucket's first position in this rank's send order (what x_pack calls offsets).
+struct XDest {
+  uint32_t* ptr[32];
+  uint32_t row0[32];
+  uint32_t send0[32];
+};
+template <int L>
+__global__ void __launch_bounds__(256)
+x_scatter(const uint32_t* __restrict__ pool, uint32_t n, uint32_t key_words,
+          const uint32_t* __restrict__ mask_remap, const uint32_t* __restrict__ owner,
+          const uint32_t* __restrict__ pos, const XDest d, uint32_t* __restrict__ perm) {
+  __shared__ uint32_t* s_ptr[32];
+  __shared__ uint32_t s_row0[32], s_send0[32];
+  if (threadIdx.x < 32) { s_ptr[threadIdx.x] = d.ptr[threadIdx.x]; s_row0[threadIdx.x] = d.row0[threadIdx.x]; s_send0[threadIdx.x] = d.send0[threadIdx.x]; }
+  __syncthreads();
+  const uint32_t gl = lane_id() & (L - 1);
+  const uint32_t total = gridDim.x * (blockDim.x / L);
+  for (uint32_t e = blockIdx.x * (blockDim.x / L) + threadIdx.x / L; e < n; e += total) {
+    const uint32_t o = owner[e], p = pos[e];
+    const uint32_t* key = pool + (size_t)e * key_words;
+    uint32_t* out = s_ptr[o] + ((size_t)s_row0[o] + p) * key_words;
+    for (uint32_t w = gl; w < key_words; w += L) {
+      uint32_t v = key[w];
+      if (mask_remap && w == key_words - 1) v = mask_remap[v];
+      out[w] = v;
+    }
+    if (gl == 0) perm[e] = s_send0[o] + p;
+  }
+}
+
 // unique index of every received key + compacted unique keys
 template <int L>
 __global__ void __launch_bounds__(256)
@@ -116,6 +149,47 @@ __global__ void x_unpack(const uint32_t* __restrict__ returned, const uint32_t* 
 
 }  // namespace pf
 
+namespace {
+// owners, bucket positions and bucket sizes of the local patterns of one namespace; the sizes
+// come back to the host (one sync: they size the receive side)
+int exchange_classify(pf_ctx* ctx, PatternSpace& s, bool cluster_namespace, uint32_t world,
+                      const uint32_t* mask_remap_dev, std::vector<uint32_t>& counts) {
+  cudaStream_t st = ctx->stream;
+  const uint32_t n = (uint32_t)s.n;
+  if (mask_remap_dev && (cluster_namespace || !ctx->prm.consider_missing))
+    return fail(ctx, PF_ERR_INVALID, "mask_remap only applies to k-mer patterns with consider_missing");
+  if (world > 32) return fail(ctx, PF_ERR_UNSUPPORTED, "exchange over more than 32 ranks");
+  TRY(dev_ensure(ctx, s.x_owner, std::max<size_t>(1, n) * 4));
+  TRY(dev_ensure(ctx, s.x_pos, std::max<size_t>(1, n) * 4));
+  TRY(dev_ensure(ctx, s.x_perm, std::max<size_t>(1, n) * 4));
+  TRY(dev_ensure(ctx, s.x_counts, (size_t)world * 2 * 4));
+  CU(cudaMemsetAsync(s.x_counts.p, 0, (size_t)world * 2 * 4, st));
+  counts.assign(world, 0);
+  if (n == 0) return PF_OK;
+  TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 64 * 4));
+  uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;
+  const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
+  const uint32_t cgrid = std::min<uint32_t>(cdiv(n, 256), kGridPersist * 2);
+#define PF_XC(LL)                                                                                        \
+  x_classify<LL><<<cgrid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev, world,    \
+                                        s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(),                \
+                                        s.x_counts.as<uint32_t>())
+  if (L == 4) PF_XC(4); else if (L == 8) PF_XC(8); else if (L == 16) PF_XC(16); else PF_XC(32);
+#undef PF_XC
+  x_offsets<<<1, 32, 0, st>>>(s.x_counts.as<uint32_t>(), world);
+  mirror_counters<<<1, 32, 0, st>>>(hx, s.x_counts.as<uint32_t>(), world);
+  ctx->launches += 3;
+  CU(cudaGetLastError());
+  return PF_OK;
+}
+int exchange_counts_to_host(pf_ctx* ctx, uint32_t world, std::vector<uint32_t>& counts) {
+  CU(cudaStreamSynchronize(ctx->stream));        // the only sync: bucket sizes for the receive side
+  const uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;
+  for (uint32_t r = 0; r < world; ++r) counts[r] = hx[r];
+  return PF_OK;
+}
+}  // namespace
+
 extern "C" int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t world,
                                 const uint32_t* mask_remap_dev, uint32_t* send_words_dev,
                                 uint64_t capacity_patterns, uint64_t* counts_host) {
@@ -126,42 +200,118 @@ extern "C" int pf_exchange_pack(pf_ctx* ctx, int cluster_namespace, uint32_t wor
   cudaStream_t st = ctx->stream;
   const uint32_t n = (uint32_t)s.n;
   if (n > capacity_patterns) return fail(ctx, PF_ERR_INVALID, "send buffer too small: %u patterns", n);
-  if (mask_remap_dev && (cluster_namespace || !ctx->prm.consider_missing))
-    return fail(ctx, PF_ERR_INVALID, "mask_remap only applies to k-mer patterns with consider_missing");
-  TRY(dev_ensure(ctx, s.x_owner, std::max<size_t>(1, n) * 4));
-  TRY(dev_ensure(ctx, s.x_pos, std::max<size_t>(1, n) * 4));
-  TRY(dev_ensure(ctx, s.x_perm, std::max<size_t>(1, n) * 4));
-  TRY(dev_ensure(ctx, s.x_counts, (size_t)world * 2 * 4));
-  CU(cudaMemsetAsync(s.x_counts.p, 0, (size_t)world * 2 * 4, st));
-  std::vector<uint32_t> counts(world, 0);
+  if (n && !send_words_dev) return fail(ctx, PF_ERR_INVALID, "null send buffer");
+  std::vector<uint32_t> counts;
+  TRY(exchange_classify(ctx, s, cluster_namespace != 0, world, mask_remap_dev, counts));
   if (n) {
-    if (!send_words_dev) return fail(ctx, PF_ERR_INVALID, "null send buffer");
-    if (world > 32) return fail(ctx, PF_ERR_UNSUPPORTED, "exchange over more than 32 ranks");
-    TRY(pin_ensure(ctx, ctx->h_counters, C_COUNT * 4 + 64 * 4));
-    uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;
     const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
-    const uint32_t cgrid = std::min<uint32_t>(cdiv(n, 256), kGridPersist * 2);
     const uint32_t pgrid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
-#define PF_XC(LL)                                                                                          \
-    do {                                                                                                   \
-      x_classify<LL><<<cgrid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev, world,  \
-                                            s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(),              \
-                                            s.x_counts.as<uint32_t>());                                    \
-      x_offsets<<<1, 32, 0, st>>>(s.x_counts.as<uint32_t>(), world);                                       \
-      x_pack<LL><<<pgrid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev,             \
-                                        s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(),                  \
-                                        s.x_counts.as<uint32_t>() + world, send_words_dev,                 \
-                                        s.x_perm.as<uint32_t>());                                          \
-    } while (0)
+#define PF_XC(LL)                                                                                        \
+    x_pack<LL><<<pgrid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev,             \
+                                      s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(),                  \
+                                      s.x_counts.as<uint32_t>() + world, send_words_dev,                 \
+                                      s.x_perm.as<uint32_t>())
     if (L == 4) PF_XC(4); else if (L == 8) PF_XC(8); else if (L == 16) PF_XC(16); else PF_XC(32);
 #undef PF_XC
-    mirror_counters<<<1, 32, 0, st>>>(hx, s.x_counts.as<uint32_t>(), world);
-    ctx->launches += 3;
-    CU(cudaStreamSynchronize(st));           // the only sync: bucket sizes for the caller's all-to-all
+    ctx->launches++;
     CU(cudaGetLastError());
-    for (uint32_t r = 0; r < world; ++r) counts[r] = hx[r];
+    TRY(exchange_counts_to_host(ctx, world, counts));
   }
   for (uint32_t r = 0; r < world; ++r) counts_host[r] = counts[r];
+  return PF_OK;
+}
+
+// ---- the same exchange over peer memory: classify -> [the caller gathers the bucket sizes of
+//      all ranks and maps the owners' receive buffers] -> scatter -> [barrier] -> dedup ----
+extern "C" int pf_exchange_classify(pf_ctx* ctx, int cluster_namespace, uint32_t world,
+                                    const uint32_t* mask_remap_dev, uint64_t* counts_host) {
+  if (!ctx || !counts_host || world == 0) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  TRY(finalize_pending(ctx));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  std::vector<uint32_t> counts;
+  TRY(exchange_classify(ctx, s, cluster_namespace != 0, world, mask_remap_dev, counts));
+  if (s.n) TRY(exchange_counts_to_host(ctx, world, counts));
+  for (uint32_t r = 0; r < world; ++r) counts_host[r] = counts[r];
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_recv_buffer(pf_ctx* ctx, int cluster_namespace, uint64_t min_rows, void** dev_ptr,
+                                       uint64_t* capacity_rows, unsigned char* ipc_handle_out /* 64 bytes */) {
+  if (!ctx || !dev_ptr || !capacity_rows || !ipc_handle_out) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  const size_t row = (size_t)s.key_words * 4;
+  if (!s.x_recv.p || s.x_recv.cap < min_rows * row) {
+    // (peers that mapped the old buffer have closed it: the caller's protocol, see dist.py)
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (s.x_recv.p) { CU(cudaFree(s.x_recv.p)); s.x_recv.p = nullptr; s.x_recv.cap = 0; }      // (contents are scratch)
+    TRY(dev_ensure(ctx, s.x_recv, std::max<size_t>(row, min_rows * row)));
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, s.x_recv.p) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, PF_ERR_CUDA, "cudaIpcGetMemHandle failed on the receive buffer");
+  }
+  memcpy(ipc_handle_out, &h, 64);
+  *dev_ptr = s.x_recv.p;
+  *capacity_rows = s.x_recv.cap / row;
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_open_peer(pf_ctx* ctx, const unsigned char* ipc_handle /* 64 bytes */, void** mapped) {
+  if (!ctx || !ipc_handle || !mapped) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, 64);
+  void* p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    cudaGetLastError();
+    return fail(ctx, PF_ERR_CUDA, "cudaIpcOpenMemHandle failed: no peer access to the owner's receive buffer");
+  }
+  *mapped = p;
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_close_peer(pf_ctx* ctx, void* mapped) {
+  if (!ctx) return PF_ERR_INVALID;
+  if (!mapped) return PF_OK;
+  CU(cudaSetDevice(ctx->device));
+  if (cudaIpcCloseMemHandle(mapped) != cudaSuccess) { cudaGetLastError(); return fail(ctx, PF_ERR_CUDA, "cudaIpcCloseMemHandle failed"); }
+  return PF_OK;
+}
+
+extern "C" int pf_exchange_scatter(pf_ctx* ctx, int cluster_namespace, uint32_t world,
+                                   const uint32_t* mask_remap_dev, void* const* dest_ptrs /* [world] */,
+                                   const uint64_t* dest_row0 /* [world] */) {
+  if (!ctx || !dest_ptrs || !dest_row0 || world == 0 || world > 32) return PF_ERR_INVALID;
+  CU(cudaSetDevice(ctx->device));
+  PatternSpace& s = cluster_namespace ? ctx->cp : ctx->kp;
+  cudaStream_t st = ctx->stream;
+  const uint32_t n = (uint32_t)s.n;
+  if (n == 0) return PF_OK;
+  if (!s.x_owner.p || !s.x_pos.p) return fail(ctx, PF_ERR_STATE, "pf_exchange_scatter before pf_exchange_classify");
+  const uint32_t* hx = ctx->h_counters.as<uint32_t>() + C_COUNT;      // bucket sizes of the classify call
+  XDest d{};
+  uint32_t run = 0;
+  for (uint32_t r = 0; r < world; ++r) {
+    if (hx[r] && !dest_ptrs[r]) return fail(ctx, PF_ERR_INVALID, "no receive buffer of rank %u", r);
+    if (dest_row0[r] + hx[r] >= (1ull << 32)) return fail(ctx, PF_ERR_INVALID, "receive buffer of rank %u too large", r);
+    d.ptr[r] = static_cast<uint32_t*>(dest_ptrs[r]);
+    d.row0[r] = (uint32_t)dest_row0[r];
+    d.send0[r] = run;
+    run += hx[r];
+  }
+  const int L = s.key_words <= 16 ? 4 : s.key_words <= 32 ? 8 : s.key_words <= 64 ? 16 : 32;
+  const uint32_t pgrid = std::min<uint32_t>(cdiv(n, 256 / L), kGridPersist * 4);
+#define PF_XS(LL)                                                                                        \
+  x_scatter<LL><<<pgrid, 256, 0, st>>>(s.pool.as<uint32_t>(), n, s.key_words, mask_remap_dev,            \
+                                       s.x_owner.as<uint32_t>(), s.x_pos.as<uint32_t>(), d, s.x_perm.as<uint32_t>())
+  if (L == 4) PF_XS(4); else if (L == 8) PF_XS(8); else if (L == 16) PF_XS(16); else PF_XS(32);
+#undef PF_XS
+  ctx->launches++;
+  CU(cudaGetLastError());
   return PF_OK;
 }
 

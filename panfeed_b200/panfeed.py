@@ -153,7 +153,9 @@ class PatternStore:
         from . import dist as pfdist
         ctx = self.context(k, S, canonical, consider_missing, cluster_equal_filter, maf, device)
         dev = torch.device("cuda", device)
-        out = pfdist.PatternExchange(ctx, dev).run(want_writer=True)
+        exchange = pfdist.PatternExchange(ctx, dev)
+        out = exchange.run(want_writer=True)
+        exchange.close()
         W = (S + 31) // 32
         written = 0
         for ns, name, ids in ((True, "cluster", self.cluster_ids.view()), (False, "kmer", self.kmer_ids.view())):

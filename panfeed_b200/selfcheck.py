@@ -44,6 +44,7 @@ def check_exchange(local_device, consider_missing, seed=20261018, n_samples=256,
     hb = capi.synth_batch(local_device, seed, S, cpr, first_cluster=rank * cpr,
                           total_clusters=world * cpr, gene_len=gene_len)
     ctx = capi.Context(k, S, consider_missing=consider_missing, maf=maf, device=local_device)
+    ex = None
     try:
         ctx.submit(hb)
         ctx.collect()
@@ -96,6 +97,9 @@ def check_exchange(local_device, consider_missing, seed=20261018, n_samples=256,
                 "the global k-mer pattern set differs from the single-context one"
         return {"world": world, "consider_missing": bool(consider_missing),
                 "cluster_patterns_global": int(len(glob_cl)), "kmer_patterns_global": int(len(glob_km)),
-                "kmer_patterns_local": int(n_km), "ok": True}
+                "kmer_patterns_local": int(n_km), "ok": True,
+                "transport": "peer memory" if ex.peer else ("nccl all-to-all" if world > 1 else "local copy")}
     finally:
+        if ex is not None:
+            ex.close()
         ctx.close()

@@ -37,8 +37,9 @@ RANKS = max(2, int(os.environ.get("PF_TEST_RANKS", "2")))
 needs_two = pytest.mark.skipif(_n_gpus() < RANKS, reason=f"needs {RANKS} GPUs (gpurun --gpus {RANKS})")
 
 
-def _torchrun(args, port, cwd, timeout=900):
+def _torchrun(args, port, cwd, timeout=900, extra_env=None):
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    env.update(extra_env or {})
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(RANKS),
                         "--master-addr", "127.0.0.1", "--master-port", str(port)] + args,
                        capture_output=True, text=True, timeout=timeout, env=env, cwd=cwd)
@@ -127,13 +128,20 @@ dist.destroy_process_group()
 
 
 @needs_two
-@pytest.mark.parametrize("samples,clusters,gene_len", [(256, 6, 400), (1500, 3, 300)])
-def test_exchange_two_ranks_nccl(samples, clusters, gene_len, tmp_path):
-    """(1500 samples: sample slices of the block engine, 47-word keys through NCCL.)"""
+@pytest.mark.parametrize("samples,clusters,gene_len,peer", [(256, 6, 400, "1"), (1500, 3, 300, "1"), (256, 6, 400, "0")])
+def test_exchange_two_ranks_nccl(samples, clusters, gene_len, peer, tmp_path):
+    """(1500 samples: sample slices of the block engine, 47-word keys.)  peer = 1: the keys go
+    straight into the owners' receive buffers (CUDA IPC mappings, NVLink stores); 0: the NCCL
+    all-to-all of the keys, which is also what a box without peer access falls back to."""
     path = tmp_path / "worker.py"
     path.write_text(WORKER)
-    r = _torchrun([str(path), ROOT, str(samples), str(clusters), str(gene_len)], 29650 + samples % 7, ROOT)
+    r = _torchrun([str(path), ROOT, str(samples), str(clusters), str(gene_len)],
+                  29650 + samples % 7 + 3 * int(peer), ROOT, extra_env={"PF_EXCHANGE_PEER": peer})
     assert "SELFCHECK" in r.stdout, r.stdout[-2000:]
+    line = [x for x in r.stdout.splitlines() if x.startswith("SELFCHECK")][0]
+    print(line)
+    if peer == "0":
+        assert "nccl all-to-all" in line
 
 
 def test_exchange_selfcheck_single_rank():
