@@ -9,7 +9,9 @@ single writer owns (`/root/reference/panfeed/__main__.py:70`,
 makes the numbering global:
 
     owner(pattern) = hash(full key) % world                (x_classify kernel)
-    all-to-all(v) of the full keys to their owners         (NCCL, torch.distributed)
+    the full keys to their owners: written straight into the owners' receive buffers, which the
+      ranks of a box map once over CUDA IPC (x_scatter, NVLink peer stores); where a buffer
+      cannot be mapped: x_pack + all-to-all(v)             (NCCL, torch.distributed)
     owner dedups on the full key, numbers its uniques       (k4_probe + scan + x_finish)
     all-gather of the unique counts -> base[owner] (exclusive scan, on the device)
     reverse all-to-all of the unique indices; local order + base[owner]   (x_unpack kernel)
