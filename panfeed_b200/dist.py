@@ -159,10 +159,12 @@ class PatternExchange:
             else bool(getattr(backend, "consider_missing", False))
         # peer memory (ranks of one box, NVLink): the keys are written straight into the owners'
         # receive buffers; falls back to the NCCL all-to-all for good if a buffer cannot be mapped
+        explicit = peer_memory is not None       # (tests drive the protocol with a host model)
         if peer_memory is None:
             peer_memory = os.environ.get("PF_EXCHANGE_PEER", "1") != "0"
-        self.peer = bool(peer_memory) and self.world > 1 and getattr(device, "type", "cpu") == "cuda" \
-            and hasattr(self.backend, "scatter")
+        self.peer = bool(peer_memory) and self.world > 1 and hasattr(self.backend, "scatter") \
+            and (explicit or getattr(device, "type", "cpu") == "cuda")
+        self.recv_slack_rows = 1024                      # a receive buffer grows to need * 5/4 + this
         self._peer_maps = {KMER: {}, CLUSTER: {}}        # ns -> {rank: (handle, mapped pointer)}
         self._peer_seen = {KMER: False, CLUSTER: False}
 
@@ -175,7 +177,8 @@ class PatternExchange:
                 self.backend.close_peer(mapped)
             maps.clear()
         if opened and self.world > 1:
-            torch.cuda.synchronize(self.device)
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
             self._host_all_ok(True)
         self._peer_seen = {KMER: False, CLUSTER: False}
 
@@ -254,9 +257,9 @@ class PatternExchange:
         # every rank's bucket sizes, receive capacity and handle: all ranks then know every
         # rank's row count and which buffers have to grow
         mine = torch.tensor(counts + [cap] + np.frombuffer(handle, np.int64).tolist(), dtype=torch.int64).to(dev)
-        allv = torch.empty((world, world + 9), dtype=torch.int64, device=dev)
+        allv = torch.empty(world * (world + 9), dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(allv, mine, group=self.group)
-        allv = allv.cpu().numpy()                                       # sync
+        allv = allv.cpu().numpy().reshape(world, world + 9)             # sync
         M = allv[:, :world]                                             # M[src][dst]
         need = M.sum(axis=0)
         grow = need > allv[:, world]
@@ -268,14 +271,15 @@ class PatternExchange:
             for r in np.nonzero(grow)[0].tolist():
                 if r in maps:
                     be.close_peer(maps.pop(r)[1])
-            torch.cuda.synchronize(dev)
+            if dev.type == "cuda":
+                torch.cuda.synchronize(dev)
             self._host_all_ok(True)                                     # barrier
             if grow[rank]:
-                ptr, cap, handle = be.recv_buffer(ns, int(need[rank]) + int(need[rank]) // 4 + 1024)
+                ptr, cap, handle = be.recv_buffer(ns, int(need[rank]) + int(need[rank]) // 4 + self.recv_slack_rows)
             mine = torch.from_numpy(np.frombuffer(handle, np.int64).copy()).to(dev)
-            allh = torch.empty((world, 8), dtype=torch.int64, device=dev)
+            allh = torch.empty(world * 8, dtype=torch.int64, device=dev)
             dist.all_gather_into_tensor(allh, mine, group=self.group)
-            allh = allh.cpu().numpy()
+            allh = allh.cpu().numpy().reshape(world, 8)
             handles = [allh[r].tobytes() for r in range(world)]
         ok = True
         ptrs = [0] * world
