@@ -751,7 +751,7 @@ def main():
     def emit(line):
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line, default=str), flush=True)     # (a stray non-JSON value must not cost the line)
         os.dup2(2, 1)
 
     env = Env()
@@ -821,7 +821,10 @@ def main():
             exch_out["last"] = out
             for ns in ("cluster", "kmer"):
                 for k_, v_ in out[ns]["ms"].items():
-                    exch_ms[ns + "_" + k_] = v_
+                    if isinstance(v_, (int, float)):
+                        exch_ms[ns + "_" + k_] = v_
+                    elif v_:
+                        exch_ms[ns + "_" + k_] = v_          # PF_EXCHANGE_TIMING: list of (stage, ms)
 
     # ---- value: batch resident in HBM -------------------------------------
     ctx.upload(hb)
@@ -1041,7 +1044,8 @@ def headline_line(args, cfg, env, hb, st, stage_ms, ms_step, value, U, U_total, 
     if cfg["targets"]:
         line["positional_records_per_s"] = env.world * M / (ms_step * 1e-3)
     if exch_ms:
-        line["exchange_ms_last_step_rank0"] = {k_: round(v_, 3) for k_, v_ in exch_ms.items()}
+        line["exchange_ms_last_step_rank0"] = {k_: round(v_, 3) if isinstance(v_, (int, float)) else v_
+                                               for k_, v_ in exch_ms.items()}
     return line
 
 
