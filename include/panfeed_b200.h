@@ -460,6 +460,26 @@ int  pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const
                    uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
                    pf_cut_result* out);
 
+/* The same cut with the sequences packed on the spot (host threads; n_threads 0 = all cores):
+ * the windows go from the contigs straight into the planes of a pf_batch - the layout of
+ * pf_pack_plan (every sequence on a 64-base boundary), the codes of pf_pack_2bit and, for
+ * sequences holding N / IUPAC symbols, pf_pack_4bit - without the ASCII copy in between.
+ * out->ascii is NULL; out->seq_off still gives the lengths.  A symbol outside the 16 IUPAC codes:
+ * PF_ERR_UNSUPPORTED, planes->bad_symbol names it.  Valid until the next call on this feeder. */
+typedef struct pf_cut_planes {
+  const uint64_t* packed;     /* 2-bit plane, n_words words of 32 bases                              */
+  uint64_t n_words;
+  const uint64_t* base_off;   /* [n_seqs] first base of a sequence in the plane                      */
+  const uint8_t*  is_amb;     /* [n_seqs] 1: the sequence holds a symbol outside ACGT                 */
+  const uint64_t* amb_plane;  /* 4-bit plane of the flagged sequences, or NULL                       */
+  uint64_t n_amb_words;
+  const uint64_t* amb_off;    /* [n_seqs] first symbol in the 4-bit plane (0 when not flagged)       */
+  int32_t bad_symbol;
+} pf_cut_planes;
+int  pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
+                          uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
+                          uint32_t n_threads, pf_cut_result* out, pf_cut_planes* planes);
+
 /* ---- row filter over the TSV outputs (host threads): the scans of the post-GWAS joins ----
  * panfeed-get-clusters / panfeed-get-kmers (get_clusters.py:90-101, get_kmers.py:108-145) keep the
  * rows of kmers_to_hashes.tsv whose hashed_pattern, and of kmers.tsv whose cluster, is in a set

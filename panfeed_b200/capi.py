@@ -126,6 +126,14 @@ class CutResult(C.Structure):
                 ("missing_off", C.POINTER(C.c_uint64))]
 
 
+class CutPlanes(C.Structure):
+    """pf_cut_planes (include/panfeed_b200.h)."""
+    _fields_ = [("packed", C.POINTER(C.c_uint64)), ("n_words", C.c_uint64),
+                ("base_off", C.POINTER(C.c_uint64)), ("is_amb", C.POINTER(C.c_uint8)),
+                ("amb_plane", C.POINTER(C.c_uint64)), ("n_amb_words", C.c_uint64),
+                ("amb_off", C.POINTER(C.c_uint64)), ("bad_symbol", C.c_int32)]
+
+
 EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_upload", "pf_execute", "pf_submit", "pf_collect",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
@@ -134,6 +142,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns", "pf_format_kmer_rows", "pf_gzip_members",
            "pf_feeder_create", "pf_feeder_destroy", "pf_feeder_last_error", "pf_feeder_add_genome", "pf_feeder_add_genomes",
            "pf_feeder_add_genome_text", "pf_feeder_genome_info", "pf_feeder_feature", "pf_feeder_cut",
+           "pf_feeder_cut_packed",
            "pf_tsv_filter", "pf_free",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_count", "pf_exchange_unique_export",
@@ -187,6 +196,8 @@ def load():
                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
     lib.pf_feeder_cut.argtypes = [vp, u32, vp, C.c_char_p, u64, C.c_int32, C.c_int32, C.c_int32,
                                   C.POINTER(CutResult)]
+    lib.pf_feeder_cut_packed.argtypes = [vp, u32, vp, C.c_char_p, u64, C.c_int32, C.c_int32, C.c_int32, u32,
+                                         C.POINTER(CutResult), C.POINTER(CutPlanes)]
     lib.pf_tsv_filter.argtypes = [C.c_char_p, u32, C.c_char_p, vp, u64, C.c_int, C.POINTER(vp), C.POINTER(u64),
                                   C.POINTER(u64), u32]
     lib.pf_free.argtypes = [vp]

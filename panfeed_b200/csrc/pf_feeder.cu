@@ -62,24 +62,40 @@ bool py_int(const char* p, const char* e, int64_t* out) {
   return true;
 }
 
-// text-mode reading like Python's open(path): "\r\n" and lone "\r" become "\n"
+// text-mode reading like Python's open(path): "\r\n" and lone "\r" become "\n".  One read of the
+// whole file; the translation (in place) only runs if the text holds a '\r' at all.
 bool read_text(const char* path, std::string* out) {
   FILE* f = fopen(path, "rb");
   if (!f) return false;
-  std::string raw;
-  char buf[1 << 16];
-  size_t n;
-  while ((n = fread(buf, 1, sizeof buf, f)) > 0) raw.append(buf, n);
-  fclose(f);
   out->clear();
-  out->reserve(raw.size());
-  for (size_t i = 0; i < raw.size(); ++i) {
-    if (raw[i] == '\r') {
-      out->push_back('\n');
-      if (i + 1 < raw.size() && raw[i + 1] == '\n') ++i;
-    } else {
-      out->push_back(raw[i]);
+  long size = -1;
+  if (fseek(f, 0, SEEK_END) == 0) { size = ftell(f); if (fseek(f, 0, SEEK_SET) != 0) size = -1; }
+  size_t got = 0;
+  if (size > 0) {
+    out->resize((size_t)size);
+    got = fread(&(*out)[0], 1, (size_t)size, f);
+    out->resize(got);
+  }
+  if (size < 0 || got == (size_t)size) {            // not seekable, or the file grew: take what follows
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out->append(buf, n);
+  }
+  fclose(f);
+  char* b = &(*out)[0];
+  const size_t n = out->size();
+  const char* first = n ? (const char*)memchr(b, '\r', n) : nullptr;
+  if (first) {
+    size_t w = (size_t)(first - b);
+    for (size_t i = w; i < n; ++i) {
+      if (b[i] == '\r') {
+        b[w++] = '\n';
+        if (i + 1 < n && b[i + 1] == '\n') ++i;
+      } else {
+        b[w++] = b[i];
+      }
     }
+    out->resize(w);
   }
   return true;
 }
@@ -161,7 +177,6 @@ void parse_fasta_text(const char* p, const char* e, Genome* g) {
   std::string name, seq;
   auto close = [&]() {
     if (!have) return;
-    for (char& c : seq) if (c >= 'a' && c <= 'z') c = (char)(c - 32);
     auto it = g->contig_of.find(name);
     if (it == g->contig_of.end()) {
       g->contig_of.emplace(name, (uint32_t)g->contig_name.size());
@@ -185,12 +200,23 @@ void parse_fasta_text(const char* p, const char* e, Genome* g) {
       while (w < l1 && !str_space((unsigned char)*w)) ++w;
       name.assign(q, w);
       have = true;
+      // one allocation per contig: its lines end where the next record starts (growing the string
+      // line by line re-allocates and page-faults its way up, which serialises the parsing threads)
+      const char* body = nl ? nl + 1 : e;
+      const char* next = body < e ? (*body == '>' ? body : (const char*)memmem(body, (size_t)(e - body), "\n>", 2)) : e;
+      seq.reserve((size_t)((next ? next : e) - body));
     } else if (have) {
       const char* a = p;
       const char* b = l1;
       while (a < b && str_space((unsigned char)*a)) ++a;
       while (b > a && str_space((unsigned char)b[-1])) --b;
+      const size_t at = seq.size();
       seq.append(a, b);
+      char* q = &seq[at];                               // str.upper() of the reference's contigs (ASCII)
+      for (size_t i = 0, m = (size_t)(b - a); i < m; ++i) {
+        const unsigned char c = (unsigned char)q[i];
+        q[i] = (char)(c - (((unsigned)(c - 'a') < 26u) << 5));
+      }
     }
     p = nl ? nl + 1 : e;
   }
@@ -224,6 +250,11 @@ struct pf_feeder {
   std::vector<uint8_t> miss_kind;
   std::string miss_text;
   std::vector<uint64_t> miss_off;
+  // planes of the last pf_feeder_cut_packed (capacity is kept from call to call)
+  std::unique_ptr<uint64_t[]> packed, amb_plane;
+  size_t packed_cap = 0, amb_cap = 0;
+  std::vector<uint64_t> base_off, amb_off;
+  std::vector<uint8_t> is_amb;
 };
 
 extern "C" int pf_feeder_create(pf_feeder** out) {
@@ -247,29 +278,37 @@ extern "C" int pf_feeder_add_genome_text(pf_feeder* f, const char* name, const c
     parse_fasta_text(fasta, fasta + fasta_len, &g);
   } else {
     // open(gff).read().split("##FASTA")[1]: the text between the first and the second marker
-    const std::string text(gff, gff_len);
-    const size_t a = text.find("##FASTA");
-    if (a == std::string::npos) {
+    const char* a = gff_len ? (const char*)memmem(gff, gff_len, "##FASTA", 7) : nullptr;
+    if (!a) {
       f->err = std::string("genome ") + name + ": no FASTA file and no ##FASTA section in the GFF";
       return PF_ERR_INVALID;
     }
-    size_t b = text.find("##FASTA", a + 7);
-    if (b == std::string::npos) b = text.size();
-    parse_fasta_text(text.data() + a + 7, text.data() + b, &g);
+    const char* end = gff + gff_len;
+    const char* b = (const char*)memmem(a + 7, (size_t)(end - (a + 7)), "##FASTA", 7);
+    if (!b) b = end;
+    parse_fasta_text(a + 7, b, &g);
   }
   if (skipped_lines) *skipped_lines = skipped;
   f->genomes.push_back(std::move(g));
   return (int)f->genomes.size() - 1;
 }
 
-extern "C" int pf_feeder_add_genome(pf_feeder* f, const char* name, const char* gff_path, const char* fasta_path,
-                                    uint32_t* skipped_lines) {
-  if (!f || !name || !gff_path) return PF_ERR_INVALID;
-  std::string gff, fasta;
+namespace {
+// gff / fasta: file buffers the caller keeps from genome to genome (their capacity is reused)
+int add_genome_files(pf_feeder* f, const char* name, const char* gff_path, const char* fasta_path,
+                     uint32_t* skipped_lines, std::string& gff, std::string& fasta) {
   if (!read_text(gff_path, &gff)) { f->err = std::string("cannot read ") + gff_path; return PF_ERR_INVALID; }
   if (fasta_path && !read_text(fasta_path, &fasta)) { f->err = std::string("cannot read ") + fasta_path; return PF_ERR_INVALID; }
   return pf_feeder_add_genome_text(f, name, gff.data(), gff.size(), fasta_path ? fasta.data() : nullptr, fasta.size(),
                                    skipped_lines);
+}
+}  // namespace
+
+extern "C" int pf_feeder_add_genome(pf_feeder* f, const char* name, const char* gff_path, const char* fasta_path,
+                                    uint32_t* skipped_lines) {
+  if (!f || !name || !gff_path) return PF_ERR_INVALID;
+  std::string gff, fasta;
+  return add_genome_files(f, name, gff_path, fasta_path, skipped_lines, gff, fasta);
 }
 
 // Many genomes at once: the files are read and parsed on host threads (a genome is a few MB of
@@ -288,9 +327,11 @@ extern "C" int pf_feeder_add_genomes(pf_feeder* f, uint32_t n, const char* const
   std::vector<std::thread> th;
   for (uint32_t t = 0; t < nt; ++t)
     th.emplace_back([&, t]() {
+      std::string gff, fasta;                             // this thread's file buffers
       for (uint32_t i = t; i < n; i += nt) {
         uint32_t sk = 0;
-        rc[i] = pf_feeder_add_genome(&local[i], names[i], gff_paths[i], fasta_paths ? fasta_paths[i] : nullptr, &sk);
+        if (!names[i] || !gff_paths[i]) { rc[i] = PF_ERR_INVALID; continue; }
+        rc[i] = add_genome_files(&local[i], names[i], gff_paths[i], fasta_paths ? fasta_paths[i] : nullptr, &sk, gff, fasta);
         if (skipped_lines) skipped_lines[i] = sk;
       }
     });
@@ -327,20 +368,20 @@ extern "C" int pf_feeder_feature(const pf_feeder* f, uint32_t genome, uint32_t f
 // '\n'; cell i belongs to genome genome[i].  For every ';'-separated feature id, in order: the
 // feature and its contig are looked up (a miss is recorded, the gene skipped), the window
 // [a, b) is sliced with Python's clamping and, on the minus strand, reverse-complemented.
-extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
-                             uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
-                             pf_cut_result* out) {
-  if (!f || !out || (n_cells && (!genome || !cells_blob))) return PF_ERR_INVALID;
+namespace {
+struct Piece { const std::string* contig; int64_t lo, hi; bool minus; };
+
+// pass 1 (serial): look the genes up, place the windows; fills the descriptor arrays of `f`
+int place_windows(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
+                  uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
+                  std::vector<Piece>& pieces) {
   f->seq_off.assign(1, 0);
   f->cell.clear(); f->feature.clear();
   f->start.clear(); f->end.clear(); f->offset.clear(); f->strand.clear();
   f->miss_cell.clear(); f->miss_kind.clear(); f->miss_text.clear(); f->miss_off.assign(1, 0);
-  struct Piece { const std::string* contig; int64_t lo, hi; bool minus; };
-  std::vector<Piece> pieces;
   const char* p = cells_blob;
   const char* e = cells_blob + cells_len;
   std::string gene;
-  // pass 1 (serial): look the genes up, place the windows
   for (uint32_t ci = 0; ci < n_cells; ++ci) {
     if (genome[ci] >= f->genomes.size()) { f->err = "pf_feeder_cut: genome index out of range"; return PF_ERR_INVALID; }
     const Genome& g = f->genomes[genome[ci]];
@@ -397,6 +438,48 @@ extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* gen
     }
     p = ce < e ? ce + 1 : e;
   }
+  return PF_OK;
+}
+
+void fill_cut_result(const pf_feeder* f, pf_cut_result* out) {
+  memset(out, 0, sizeof *out);
+  out->n_seqs = (uint32_t)f->cell.size();
+  out->seq_off = f->seq_off.data();
+  out->cell = f->cell.data();
+  out->feature = f->feature.data();
+  out->start = f->start.data();
+  out->end = f->end.data();
+  out->offset = f->offset.data();
+  out->strand = f->strand.data();
+  out->n_missing = (uint32_t)f->miss_cell.size();
+  out->missing_cell = f->miss_cell.data();
+  out->missing_kind = f->miss_kind.data();
+  out->missing_text = f->miss_text.data();
+  out->missing_off = f->miss_off.data();
+}
+
+// [0, n_seq) split into nt ranges of about equal bases; range t = [cut[t], cut[t + 1])
+std::vector<size_t> split_by_bases(const std::vector<uint64_t>& seq_off, uint32_t nt) {
+  const size_t n_seq = seq_off.size() - 1;
+  const uint64_t total = seq_off.back();
+  std::vector<size_t> cut(nt + 1, n_seq);
+  cut[0] = 0;
+  for (uint32_t t = 1; t < nt; ++t) {
+    const uint64_t want = total * t / nt;
+    size_t s = (size_t)(std::upper_bound(seq_off.begin(), seq_off.end(), want) - seq_off.begin() - 1);
+    cut[t] = std::max(std::min(s, n_seq), cut[t - 1]);
+  }
+  return cut;
+}
+}  // namespace
+
+extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
+                             uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
+                             pf_cut_result* out) {
+  if (!f || !out || (n_cells && (!genome || !cells_blob))) return PF_ERR_INVALID;
+  std::vector<Piece> pieces;
+  const int rc = place_windows(f, n_cells, genome, cells_blob, cells_len, up, down, down_start_codon, pieces);
+  if (rc != PF_OK) return rc;
   // pass 2 (host threads): copy / reverse-complement the windows into place
   const size_t total = (size_t)f->seq_off.back();
   if (total > f->ascii_cap) {
@@ -423,34 +506,154 @@ extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* gen
     nt = (uint32_t)std::min<size_t>(nt, std::max<size_t>(1, total >> 20));       // >= 1 MiB per thread
     if (nt <= 1 || n_seq < 2 * nt) fill(0, n_seq);
     else {
-      // split by bytes, not by sequences
+      const std::vector<size_t> cut = split_by_bases(f->seq_off, nt);             // by bytes, not by sequences
       std::vector<std::thread> th;
-      size_t s0 = 0;
-      for (uint32_t t = 0; t < nt; ++t) {
-        const uint64_t want = (uint64_t)total * (t + 1) / nt;
-        size_t s1 = t + 1 == nt ? n_seq
-                                : (size_t)(std::upper_bound(f->seq_off.begin(), f->seq_off.end(), want) - f->seq_off.begin() - 1);
-        s1 = std::max(s1, s0);
-        th.emplace_back(fill, s0, s1);
-        s0 = s1;
-      }
+      for (uint32_t t = 0; t < nt; ++t) th.emplace_back(fill, cut[t], cut[t + 1]);
       for (auto& x : th) x.join();
     }
   }
-  memset(out, 0, sizeof *out);
-  out->n_seqs = (uint32_t)f->cell.size();
+  fill_cut_result(f, out);
   out->ascii = f->ascii.get();
-  out->seq_off = f->seq_off.data();
-  out->cell = f->cell.data();
-  out->feature = f->feature.data();
-  out->start = f->start.data();
-  out->end = f->end.data();
-  out->offset = f->offset.data();
-  out->strand = f->strand.data();
-  out->n_missing = (uint32_t)f->miss_cell.size();
-  out->missing_cell = f->miss_cell.data();
-  out->missing_kind = f->miss_kind.data();
-  out->missing_text = f->miss_text.data();
-  out->missing_off = f->miss_off.data();
+  return PF_OK;
+}
+
+// The same cut with the sequences packed on the spot: contig windows go straight into the 2-bit
+// plane of a pf_batch (and, for sequences holding N / IUPAC symbols, the 4-bit plane) on host
+// threads, without the ASCII copy and the second pass of pf_pack_2bit / pf_pack_4bit over it.
+// Layout and codes are exactly those of pf_pack_plan / pf_pack_2bit / pf_pack_4bit on the ASCII
+// result of pf_feeder_cut (tests/test_feeder_native.py compares the two).
+namespace {
+struct PackLut {
+  uint8_t two_fwd[256], two_rc[256], four_fwd[256], four_rc[256];
+  PackLut() {
+    uint8_t two[256], four[256];
+    memset(two, 255, sizeof two);
+    memset(four, 255, sizeof four);
+    two[(unsigned char)'A'] = 0; two[(unsigned char)'C'] = 1; two[(unsigned char)'G'] = 2; two[(unsigned char)'T'] = 3;
+    const char* amb = "ABCDGHKMNRSTVWXY";                       // the 4-bit alphabet of pf_pack_4bit
+    for (int i = 0; i < 16; ++i) four[(unsigned char)amb[i]] = (uint8_t)i;
+    for (int c = 0; c < 256; ++c) {
+      // 2-bit tables: 0x80 marks a symbol outside ACGT (its low bits pack as A, like pf_pack_2bit)
+      two_fwd[c] = two[c] == 255 ? 0x80 : two[c]; four_fwd[c] = four[c];
+      two_rc[c] = two[kComp.t[c]] == 255 ? 0x80 : two[kComp.t[c]]; four_rc[c] = four[kComp.t[c]];
+    }
+  }
+};
+const PackLut kPack;
+}  // namespace
+
+extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
+                                    uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
+                                    uint32_t n_threads, pf_cut_result* out, pf_cut_planes* planes) {
+  if (!f || !out || !planes || (n_cells && (!genome || !cells_blob))) return PF_ERR_INVALID;
+  std::vector<Piece> pieces;
+  const int rc = place_windows(f, n_cells, genome, cells_blob, cells_len, up, down, down_start_codon, pieces);
+  if (rc != PF_OK) return rc;
+  const size_t n_seq = pieces.size();
+  // pf_pack_plan: every sequence starts on a 64-base boundary
+  f->base_off.resize(n_seq);
+  f->amb_off.assign(n_seq, 0);
+  f->is_amb.assign(n_seq, 0);
+  uint64_t pos = 0;
+  for (size_t s = 0; s < n_seq; ++s) {
+    f->base_off[s] = pos;
+    pos += (uint64_t)(pieces[s].hi - pieces[s].lo + 63) / 64 * 64;
+  }
+  const size_t n_words = (size_t)(pos / 32);
+  if (n_words > f->packed_cap) {
+    f->packed_cap = n_words + n_words / 4 + 64;
+    f->packed.reset(new uint64_t[f->packed_cap]);
+  }
+  uint32_t nt = n_threads ? n_threads : std::max(1u, std::thread::hardware_concurrency());
+  nt = (uint32_t)std::min<size_t>(nt, std::max<size_t>(1, (size_t)f->seq_off.back() >> 18));    // >= 256 k bases per thread
+  nt = (uint32_t)std::max<size_t>(1, std::min<size_t>(nt, n_seq));
+  const std::vector<size_t> cut = split_by_bases(f->seq_off, nt);
+  auto run = [&](auto&& fn) {
+    if (nt == 1) { fn(0u); return; }
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < nt; ++t) th.emplace_back(fn, t);
+    for (auto& x : th) x.join();
+  };
+  // pf_pack_2bit: padding and non-ACGT symbols pack as A; a sequence with any of the latter is flagged
+  run([&](uint32_t t) {
+    for (size_t s = cut[t]; s < cut[t + 1]; ++s) {
+      const Piece& pc = pieces[s];
+      const uint64_t len = (uint64_t)(pc.hi - pc.lo);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(pc.contig->data());
+      uint64_t* dst = f->packed.get() + f->base_off[s] / 32;
+      const uint64_t words = (len + 63) / 64 * 2;
+      uint32_t bad = 0;
+      for (uint64_t w = 0; w < words; ++w) {
+        const uint64_t p0 = w * 32;
+        const uint32_t m = (uint32_t)std::min<uint64_t>(32, len > p0 ? len - p0 : 0);
+        uint64_t v = 0;
+        if (pc.minus) {
+          const unsigned char* q = src + pc.hi - 1 - p0;          // symbol j of the word: complement of q[-j]
+          for (uint32_t j = 0; j < m; ++j) { const uint32_t c = kPack.two_rc[*(q - j)]; bad |= c; v = (v << 2) | (c & 3u); }
+        } else {
+          const unsigned char* q = src + pc.lo + p0;
+          for (uint32_t j = 0; j < m; ++j) { const uint32_t c = kPack.two_fwd[q[j]]; bad |= c; v = (v << 2) | (c & 3u); }
+        }
+        dst[w] = m ? v << (2 * (32 - m)) : 0;
+      }
+      f->is_amb[s] = (bad & 0x80u) ? 1 : 0;
+    }
+  });
+  // pf_pack_4bit for the flagged sequences (rare: N / IUPAC symbols)
+  uint64_t apos = 0;
+  std::vector<uint32_t> amb_seqs;
+  for (size_t s = 0; s < n_seq; ++s)
+    if (f->is_amb[s]) {
+      f->amb_off[s] = apos;
+      apos += (uint64_t)(pieces[s].hi - pieces[s].lo + 63) / 64 * 64;
+      amb_seqs.push_back((uint32_t)s);
+    }
+  const size_t n_amb_words = (size_t)(apos / 16);
+  int bad_symbol = 0;
+  if (n_amb_words) {
+    if (n_amb_words > f->amb_cap) {
+      f->amb_cap = n_amb_words + n_amb_words / 4 + 64;
+      f->amb_plane.reset(new uint64_t[f->amb_cap]);
+    }
+    const uint64_t a_code = kPack.four_fwd[(unsigned char)'A'];
+    for (uint32_t s : amb_seqs) {
+      const Piece& pc = pieces[s];
+      const uint64_t len = (uint64_t)(pc.hi - pc.lo), padded = (len + 63) / 64 * 64;
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(pc.contig->data());
+      uint64_t* dst = f->amb_plane.get() + f->amb_off[s] / 16;
+      for (uint64_t w = 0; w < padded / 16; ++w) {
+        uint64_t v = 0;
+        for (uint32_t j = 0; j < 16; ++j) {
+          const uint64_t p = w * 16 + j;
+          uint64_t c = a_code;                                   // padding packs as A
+          if (p < len) {
+            const unsigned char sym = pc.minus ? src[pc.hi - 1 - p] : src[pc.lo + p];
+            c = pc.minus ? kPack.four_rc[sym] : kPack.four_fwd[sym];
+            if (c == 255u) {
+              if (!bad_symbol) bad_symbol = pc.minus ? kComp.t[sym] : sym;
+              c = a_code;
+            }
+          }
+          v = (v << 4) | c;
+        }
+        dst[w] = v;
+      }
+    }
+  }
+  fill_cut_result(f, out);
+  out->ascii = nullptr;
+  memset(planes, 0, sizeof *planes);
+  planes->packed = f->packed.get();
+  planes->n_words = n_words;
+  planes->base_off = f->base_off.data();
+  planes->is_amb = f->is_amb.data();
+  planes->amb_plane = n_amb_words ? f->amb_plane.get() : nullptr;
+  planes->n_amb_words = n_amb_words;
+  planes->amb_off = f->amb_off.data();
+  planes->bad_symbol = bad_symbol;
+  if (bad_symbol) {
+    f->err = std::string("unsupported sequence symbol '") + (char)bad_symbol + "'";
+    return PF_ERR_UNSUPPORTED;
+  }
   return PF_OK;
 }

@@ -32,6 +32,7 @@ extern "C" uint32_t pf_struct_size(int which) {
     case 5: return (uint32_t)sizeof(pf_stats);
     case 6: return (uint32_t)sizeof(pf_synth_params);
     case 7: return (uint32_t)sizeof(pf_cut_result);
+    case 8: return (uint32_t)sizeof(pf_cut_planes);
     default: return 0;
   }
 }

@@ -119,13 +119,22 @@ class NativeFeeder:
     def cut(self, genomes, cells_blob, up, down, down_start_codon, prepack=False):
         """genomes: uint32 array (genome index per cell); cells_blob: the cells joined with
         newlines (bytes).  -> dict of copies of the pf_cut_result arrays.  prepack: the sequences
-        are packed into the 2-bit / 4-bit planes straight from the library's buffer ("packed",
-        "base_off", "is_amb", "amb_plane", "amb_off" as capi.pack_blob returns them) and the ASCII
-        text is not copied out ("ascii" is None)."""
+        go from the contigs straight into the 2-bit / 4-bit planes (pf_feeder_cut_packed, host
+        threads: "packed", "base_off", "is_amb", "amb_plane", "amb_off" as capi.pack_blob would
+        return them for the ASCII cut) and there is no ASCII text ("ascii" is None)."""
         genomes = np.ascontiguousarray(genomes, dtype=np.uint32)
         res = capi.CutResult()
-        rc = self.lib.pf_feeder_cut(self.h, len(genomes), genomes.ctypes.data, cells_blob, len(cells_blob),
-                                    int(up), int(down), int(bool(down_start_codon)), C.byref(res))
+        planes = capi.CutPlanes()
+        if prepack:
+            rc = self.lib.pf_feeder_cut_packed(self.h, len(genomes), genomes.ctypes.data, cells_blob, len(cells_blob),
+                                               int(up), int(down), int(bool(down_start_codon)), 0,
+                                               C.byref(res), C.byref(planes))
+            if rc == -4 and planes.bad_symbol:
+                raise ValueError(f"unsupported sequence symbol {chr(planes.bad_symbol)!r}: only "
+                                 f"{capi.AMB_ALPHABET} (IUPAC, upper case) are accepted")
+        else:
+            rc = self.lib.pf_feeder_cut(self.h, len(genomes), genomes.ctypes.data, cells_blob, len(cells_blob),
+                                        int(up), int(down), int(bool(down_start_codon)), C.byref(res))
         if rc != 0:
             self._error(rc, "pf_feeder_cut")
         n = res.n_seqs
@@ -143,8 +152,11 @@ class NativeFeeder:
                "missing": []}
         if prepack:
             out["ascii"] = None
-            (out["packed"], out["base_off"], out["is_amb"], out["amb_plane"],
-             out["amb_off"]) = capi.pack_blob(res.ascii if n else b"", seq_off)
+            out["packed"] = arr(planes.packed, int(planes.n_words), np.uint64)
+            out["base_off"] = arr(planes.base_off, n, np.uint64)
+            out["is_amb"] = arr(planes.is_amb, n, np.uint8).astype(bool)
+            out["amb_plane"] = arr(planes.amb_plane, int(planes.n_amb_words), np.uint64) if planes.n_amb_words else None
+            out["amb_off"] = arr(planes.amb_off, n, np.uint64)
         else:
             out["ascii"] = C.string_at(res.ascii, int(seq_off[-1])) if n else b""
         if res.n_missing:

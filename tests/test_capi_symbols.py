@@ -38,7 +38,8 @@ def test_ctypes_mirrors_match_the_library():
     mirrors = {0: ctypes.sizeof(capi.Params), 1: capi.SEQ_DTYPE.itemsize,
                2: capi.CLUSTER_DTYPE.itemsize, 3: ctypes.sizeof(capi.Batch),
                4: ctypes.sizeof(capi.BatchResult), 5: ctypes.sizeof(capi.Stats),
-               6: ctypes.sizeof(capi.SynthParams), 7: ctypes.sizeof(capi.CutResult)}
+               6: ctypes.sizeof(capi.SynthParams), 7: ctypes.sizeof(capi.CutResult),
+               8: ctypes.sizeof(capi.CutPlanes)}
     for which, size in mirrors.items():
         assert lib.pf_struct_size(which) == size, which
     assert lib.pf_struct_size(99) == 0

@@ -10,7 +10,7 @@ import pytest
 
 from panfeed_b200 import feeder as nf
 from panfeed_b200 import input as pyin
-from panfeed_b200 import packer, panfeed
+from panfeed_b200 import capi, packer, panfeed
 
 import helpers
 
@@ -159,4 +159,58 @@ def test_native_feeder_parsing_quirks_match_python(tmp_path):
     assert native.genome_info(g2) == {"features": len(feats), "contigs": 1, "bases": 4}
     with pytest.raises(Exception):
         native.add_genome_text("q3", GFF.split("##FASTA")[0])       # no sequences at all
+    native.close()
+
+
+def test_cut_packed_equals_cut_then_pack():
+    """pf_feeder_cut_packed (contig windows straight into the 2-bit / 4-bit planes, host threads)
+    against pf_feeder_cut + pf_pack_2bit / pf_pack_4bit over its ASCII result, on random genomes:
+    both strands, windows clamped at both contig ends, empty windows, N / IUPAC runs, lengths
+    around the 32- and 64-base word boundaries, enough bases for several threads."""
+    rng = np.random.default_rng(7)
+    native = nf.NativeFeeder()
+    cells, genomes = [], []
+    alphabet = np.frombuffer(b"ACGT", np.uint8)
+    for gi in range(6):
+        n_genes = 180
+        lens = rng.integers(1, 2600, n_genes)
+        lens[:12] = [1, 31, 32, 33, 63, 64, 65, 127, 128, 129, 1, 2]
+        contig = alphabet[rng.integers(0, 4, int(lens.sum()) + 50)].copy()
+        for _ in range(25):                                    # N / IUPAC runs and lower case
+            at = int(rng.integers(0, len(contig) - 8))
+            contig[at:at + int(rng.integers(1, 8))] = np.frombuffer(b"NRYKMSWBDHVX", np.uint8)[rng.integers(0, 12)]
+        text = contig.tobytes().decode()
+        text = text[:500].lower() + text[500:]
+        rows, pos, ids = [], 1, []
+        for j, ln in enumerate(lens.tolist()):
+            strand = "+" if rng.random() < 0.5 else "-"
+            rows.append(f"c\tx\tCDS\t{pos}\t{pos + ln - 1}\t.\t{strand}\t0\tID=g{gi}_{j};x=1")
+            ids.append(f"g{gi}_{j}")
+            pos += ln
+        rows.append(f"c\tx\tCDS\t{len(text) + 6000}\t{len(text) + 6010}\t.\t+\t0\tID=g{gi}_off;x=1")     # past the contig end
+        ids.append(f"g{gi}_off")
+        g = native.add_genome_text(f"s{gi}", "\n".join(rows) + "\n##FASTA\n>c\n" +
+                                   "\n".join(text[i:i + 70] for i in range(0, len(text), 70)) + "\n")
+        for j in range(0, len(ids), 3):
+            cells.append(";".join(ids[j:j + 3]))
+            genomes.append(g)
+    blob = "\n".join(cells).encode()
+    genomes = np.array(genomes, np.uint32)
+    for up, down, dsc in [(0, 0, False), (17, 40, False), (5000, 5000, False), (10, 25, True)]:
+        a = native.cut(genomes, blob, up, down, dsc, prepack=False)
+        want = capi.pack_blob(a["ascii"], a["seq_off"])
+        b = native.cut(genomes, blob, up, down, dsc, prepack=True)
+        assert b["ascii"] is None and b["n_seqs"] == a["n_seqs"] > 1000
+        for f in ("seq_off", "cell", "feature", "start", "end", "offset", "strand"):
+            assert (a[f] == b[f]).all(), f
+        assert (np.diff(a["seq_off"].astype(np.int64)) == 0).any()          # empty windows are in
+        assert (want[0] == b["packed"]).all()
+        assert (want[1] == b["base_off"]).all()
+        assert (want[2] == b["is_amb"]).all() and want[2].any() and not want[2].all()
+        assert (want[3] == b["amb_plane"]).all()
+        assert (want[4] == b["amb_off"]).all()
+    # a symbol outside the 16 IUPAC codes is refused and named, like the packer does
+    g = native.add_genome_text("bad", "c\tx\tCDS\t1\t12\t.\t-\t0\tID=z;x=1\n##FASTA\n>c\nACGTAC*TACGT\n")
+    with pytest.raises(ValueError, match=r"\*"):
+        native.cut(np.array([g], np.uint32), b"z", 0, 0, False, prepack=True)
     native.close()
