@@ -134,12 +134,13 @@ def main(argv=None):
         write_headers(hash_pat, kmer_hash, genepres)
     logger.info("Extracting k-mers")
     if args.native_feeder:
-        from .feeder import iter_packed_clusters, prep_feeder
+        from .feeder import iter_packed_batches, iter_packed_clusters, prep_feeder
         native, genome_index = prep_feeder(filelist, fastalist, args.gff, args.fasta, args.output)
-        cut_clusters = iter_packed_clusters(genepres, native, genome_index, args.upstream, args.downstream,
-                                            args.downstream_start_codon, stroi, klength,
-                                            not args.non_canonical, args.consider_missing, genes,
-                                            args.stop_on_missing)
+        # whole GPU batches straight from the library; --multiple-files runs cluster by cluster
+        cut = iter_packed_clusters if args.multiple_files else iter_packed_batches
+        cut_clusters = cut(genepres, native, genome_index, args.upstream, args.downstream,
+                           args.downstream_start_codon, stroi, klength, not args.non_canonical,
+                           args.consider_missing, genes, args.stop_on_missing)
     else:
         data = prep_data_n_fasta(filelist, fastalist, args.gff, args.fasta, args.output)
         iter_i = iter_gene_clusters(genepres, data, args.upstream, args.downstream,

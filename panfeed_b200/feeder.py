@@ -258,6 +258,64 @@ def prep_feeder(filelist, fastalist, gffdir, fastadir, output=None):
     return feeder, index
 
 
+class _CutPlan:
+    """What both iterators share: the panaroo table as arrays in sample-rank order, the rows to cut
+    and the library call that cuts a run of them."""
+
+    def __init__(self, panaroo, feeder, genome_index, up, down, down_start_codon, stroi, gene_list, raise_missing):
+        cols = [str(c) for c in panaroo.columns]
+        missing = set(cols).difference(genome_index.keys())
+        if missing:
+            raise KeyError(f"{len(missing)} strains of the pangenome table have no GFF "
+                           f"(e.g. {sorted(missing)[0]}); the reference would emit misaligned "
+                           "presence vectors here, this build refuses")
+        self.feeder, self.up, self.down, self.dsc = feeder, up, down, down_start_codon
+        self.raise_missing = raise_missing
+        self.order = sorted(cols)
+        rank = {s: i for i, s in enumerate(self.order)}
+        perm = np.argsort(np.array([rank[c] for c in cols]), kind="stable")        # table columns in rank order
+        self.genome_of_rank = np.array([genome_index[s] for s in self.order], np.uint32)
+        self.target_of_rank = np.array([s in stroi for s in self.order], bool)
+        self.values = panaroo.to_numpy(dtype=object)[:, perm]
+        self.present_all = pd.notna(self.values)
+        self.n_rows, self.S = self.values.shape
+        self.index = list(panaroo.index)
+        rows = []
+        for i, idx in enumerate(self.index):
+            if gene_list is not None and idx not in gene_list:
+                logger.debug(f"Skipping {idx} ({i + 1}/{self.n_rows})")
+                continue
+            rows.append(i)
+        self.rows = np.array(rows, np.int64)
+        self.n_cells = self.present_all[self.rows].sum(axis=1) if len(self.rows) else np.zeros(0, np.int64)
+
+    def take(self, at, cell_budget):
+        """-> `to`: rows at .. to hold at least one cluster, then as many as fit the cell budget."""
+        to, budget = at + 1, cell_budget - int(self.n_cells[at])
+        while to < len(self.rows) and budget - int(self.n_cells[to]) >= 0:
+            budget -= int(self.n_cells[to])
+            to += 1
+        return to
+
+    def cut(self, at, to):
+        """Cut rows at .. to -> (sel, pres, rr, cc, cut): the table rows, their presence matrix, the
+        (cluster, rank) of every present cell in row-major order, the library's result."""
+        sel = self.rows[at:to]
+        pres = self.present_all[sel]
+        rr, cc = np.nonzero(pres)                    # row-major: cluster by cluster, ranks ascending
+        cells = self.values[sel][pres]
+        blob = "\n".join(cells).encode() if len(cells) else b""
+        cut = self.feeder.cut(self.genome_of_rank[cc], blob, self.up, self.down, self.dsc, prepack=True)
+        for cell, kind, name in cut["missing"]:
+            idx, strain = self.index[sel[rr[cell]]], self.order[cc[cell]]
+            msg = (f"Could not find gene {name} from {idx} in {strain}" if kind == 0
+                   else f"Could not find chromosome {name} in {strain}")
+            logger.warning(msg)
+            if self.raise_missing:
+                raise KeyError(msg)
+        return sel, pres, rr, cc, cut
+
+
 def iter_packed_clusters(panaroo, feeder, genome_index, up, down, down_start_codon, stroi, klength,
                          canon, consider_missing_cluster, gene_list=None, raise_missing=False,
                          cells_per_call=16384):
@@ -265,53 +323,16 @@ def iter_packed_clusters(panaroo, feeder, genome_index, up, down, down_start_cod
     int presence vector, None) per panaroo row — with the cutting done by the library, several
     clusters (about `cells_per_call` table cells) per call: the Python work per cluster is a
     handful of array slices."""
-    cols = [str(c) for c in panaroo.columns]
-    missing = set(cols).difference(genome_index.keys())
-    if missing:
-        raise KeyError(f"{len(missing)} strains of the pangenome table have no GFF "
-                       f"(e.g. {sorted(missing)[0]}); the reference would emit misaligned "
-                       "presence vectors here, this build refuses")
-    order = sorted(cols)
-    rank = {s: i for i, s in enumerate(order)}
-    perm = np.argsort(np.array([rank[c] for c in cols]), kind="stable")        # table columns in rank order
-    genome_of_rank = np.array([genome_index[s] for s in order], np.uint32)
-    target_of_rank = np.array([s in stroi for s in order], bool)
-    values = panaroo.to_numpy(dtype=object)[:, perm]
-    present_all = pd.notna(values)
-    n_rows, S = values.shape
-    index = list(panaroo.index)
-    rows = []
-    for i, idx in enumerate(index):
-        if gene_list is not None and idx not in gene_list:
-            logger.debug(f"Skipping {idx} ({i + 1}/{n_rows})")
-            continue
-        rows.append(i)
-    rows = np.array(rows, np.int64)
-    n_cells = present_all[rows].sum(axis=1) if len(rows) else np.zeros(0, np.int64)
+    plan = _CutPlan(panaroo, feeder, genome_index, up, down, down_start_codon, stroi, gene_list, raise_missing)
+    index, order, n_rows = plan.index, plan.order, plan.n_rows
     at = 0
-    while at < len(rows):
-        # rows at .. to: at least one cluster, then as many as fit the cell budget
-        to, budget = at + 1, cells_per_call - int(n_cells[at])
-        while to < len(rows) and budget - int(n_cells[to]) >= 0:
-            budget -= int(n_cells[to])
-            to += 1
-        sel = rows[at:to]
-        pres = present_all[sel]
-        rr, cc = np.nonzero(pres)                    # row-major: cluster by cluster, ranks ascending
-        cells = values[sel][pres]
-        blob = "\n".join(cells).encode() if len(cells) else b""
-        cut = feeder.cut(genome_of_rank[cc], blob, up, down, down_start_codon, prepack=True)
-        for cell, kind, name in cut["missing"]:
-            idx, strain = index[sel[rr[cell]]], order[cc[cell]]
-            msg = (f"Could not find gene {name} from {idx} in {strain}" if kind == 0
-                   else f"Could not find chromosome {name} in {strain}")
-            logger.warning(msg)
-            if raise_missing:
-                raise KeyError(msg)
+    while at < len(plan.rows):
+        to = plan.take(at, cells_per_call)
+        sel, pres, rr, cc, cut = plan.cut(at, to)
         seq_cluster = rr[cut["cell"]]
         sample = cc[cut["cell"]].astype(np.uint32)
-        target = target_of_rank[sample]
-        genome = genome_of_rank[sample]
+        target = plan.target_of_rank[sample]
+        genome = plan.genome_of_rank[sample]
         seq_len = np.diff(cut["seq_off"]).astype(np.int64)
         first = np.searchsorted(seq_cluster, np.arange(len(sel) + 1))
         # word ranges of the clusters in the planes of this cut
@@ -335,4 +356,71 @@ def iter_packed_clusters(panaroo, feeder, genome_index, up, down, down_start_cod
                 cut["feature"][a:b], order, feeder)
             pc.k, pc.canonical, pc.consider_missing = klength, bool(canon), bool(consider_missing_cluster)
             yield idx, pc, clusterpresab, None
+        at = to
+
+
+class NativePackedBatch:
+    """A run of clusters cut by the library, already in the form of a pf_batch: `hb` is what
+    `packer.pack_batch` makes of the same clusters (the planes of the cut ARE the planes of the
+    batch), `idxs` their panaroo row names.  `pattern_hasher` submits it as it is: no Python
+    object per cluster, no second copy of the planes.  (strain, feature id, contig) of a sequence
+    are looked up only when a kmers.tsv row needs them (`meta`)."""
+    __slots__ = ("hb", "idxs", "k", "canonical", "consider_missing", "_feeder", "_genome", "_feature", "_order")
+
+    def __init__(self, hb, idxs, genome, feature, order, feeder):
+        self.hb, self.idxs = hb, idxs
+        self._feeder, self._genome, self._feature, self._order = feeder, genome, feature, order
+
+    def meta(self, i):
+        return (self._order[int(self.hb.seqs["sample"][i])],) + \
+            self._feeder.feature_names(int(self._genome[i]), int(self._feature[i]))
+
+    def n_records(self, k, canonical):
+        n = int(np.maximum(self.hb.seqs["len"].astype(np.int64) - k + 1, 0).sum())
+        return n if canonical else 2 * n
+
+
+def iter_packed_batches(panaroo, feeder, genome_index, up, down, down_start_codon, stroi, klength,
+                        canon, consider_missing_cluster, gene_list=None, raise_missing=False,
+                        target_bases=96 * 1024 * 1024, first_cells=16384):
+    """The batch-level form of `iter_packed_clusters`: yields (idxs, NativePackedBatch, None, None),
+    one library call and a few array operations per BATCH of clusters.  The first call cuts about
+    `first_cells` table cells; from its bases per cell the following calls are sized to about
+    `target_bases` bases (whole clusters, at least one)."""
+    plan = _CutPlan(panaroo, feeder, genome_index, up, down, down_start_codon, stroi, gene_list, raise_missing)
+    W = (plan.S + 31) // 32
+    at, cells_per_call = 0, int(first_cells)
+    seen_cells = seen_bases = 0
+    while at < len(plan.rows):
+        to = plan.take(at, cells_per_call)
+        sel, pres, rr, cc, cut = plan.cut(at, to)
+        n = cut["n_seqs"]
+        cell = cut["cell"]
+        seqs = np.zeros(n, capi.SEQ_DTYPE)
+        sample = cc[cell].astype(np.uint32)
+        seq_len = np.diff(cut["seq_off"]).astype(np.uint32) if n else np.zeros(0, np.uint32)
+        seqs["base_off"] = cut["base_off"]
+        seqs["len"] = seq_len
+        seqs["cluster"] = rr[cell]
+        seqs["sample"] = sample
+        seqs["flags"] = (plan.target_of_rank[sample].astype(np.uint32) * capi.PF_SEQ_TARGET |
+                         cut["is_amb"].astype(np.uint32) * capi.PF_SEQ_AMBIGUOUS)
+        for f in ("start", "end", "offset", "strand"):
+            seqs[f] = cut[f]
+        seqs["amb_off"] = cut["amb_off"]
+        clusters = np.zeros(len(sel), capi.CLUSTER_DTYPE)
+        clusters["id"] = np.arange(len(sel), dtype=np.uint32)
+        bits = np.zeros((len(sel), W * 32), np.uint8)
+        bits[:, :plan.S] = pres
+        presence = np.packbits(bits, axis=1, bitorder="little").view(np.uint32).reshape(len(sel), W)
+        hb = capi.HostBatch(cut["packed"], seqs, clusters, presence, cut["amb_plane"])
+        idxs = [plan.index[i] for i in sel]
+        logger.debug(f"Extracted sequences of {len(idxs)} clusters ({idxs[0]} ..; {to}/{len(plan.rows)})")
+        pb = NativePackedBatch(hb, idxs, plan.genome_of_rank[sample], cut["feature"], plan.order, feeder)
+        pb.k, pb.canonical, pb.consider_missing = klength, bool(canon), bool(consider_missing_cluster)
+        yield idxs, pb, None, None
+        seen_cells += int(pres.sum())
+        seen_bases += int(seq_len.sum())
+        if seen_bases:
+            cells_per_call = int(min(max(first_cells, target_bases * seen_cells // seen_bases), 1 << 22))
         at = to

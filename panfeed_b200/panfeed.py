@@ -176,10 +176,10 @@ class PatternStore:
                 "kmer_patterns_global": out["kmer"]["n_global"]}
 
 
-def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
-    """One GPU batch -> (kmers.tsv text, hashes_to_patterns text, per-cluster
-    kmers_to_hashes texts)."""
-    hb, meta, ids = packer.pack_batch(pcs, list(range(len(pcs))))
+def _run_batch(store, ctx, hb, meta, idxs, S, k, canonical, consider_missing):
+    """One GPU batch (`hb`: the capi.HostBatch; meta(i) -> (strain, feature id, contig) of its
+    sequence i; idxs: the names of its clusters) -> (kmers.tsv text, hashes_to_patterns text,
+    per-cluster kmers_to_hashes texts)."""
     ctx.submit(hb)
     r = ctx.collect()
 
@@ -224,7 +224,7 @@ def _run_batch(store, ctx, pcs, idxs, S, k, canonical, consider_missing):
         leads = [b""] * len(hb.seqs)
         cl, strand = hb.seqs["cluster"], hb.seqs["strand"]
         for i in np.nonzero(hb.seqs["flags"] & capi.PF_SEQ_TARGET)[0].tolist():
-            m = meta[i]
+            m = meta(i)
             leads[i] = f"{idxs[cl[i]]}\t{m[0]}\t{m[1]}\t{m[2]}\t{strand[i]}\t".encode()
         pos_text = capi.format_positions_compact(hb, r["pos_strand_bits"], k, canonical, leads).decode()
     return pos_text, "".join(pat_text), hash_texts
@@ -242,16 +242,23 @@ def pattern_hasher(cluster_dict_iter, kmer_stroi, hash_pat, kmer_hash, genepres,
 
     pending, pending_records = [], 0
 
-    def flush():
+    def flush(ready=None):
+        """Runs the pending clusters as one batch, or `ready`: a batch the native feeder cut and
+        packed as a whole (feeder.NativePackedBatch)."""
         nonlocal pending, pending_records, hash_pat, kmer_hash
-        if not pending:
+        if ready is not None:
+            first, hb, meta, idxs = ready, ready.hb, ready.meta, ready.idxs
+        elif pending:
+            pcs = [p[1] for p in pending]
+            idxs = [p[0] for p in pending]
+            first = pcs[0]
+            hb, seq_meta, _ = packer.pack_batch(pcs, list(range(len(pcs))))
+            meta = seq_meta.__getitem__
+        else:
             return
-        pcs = [p[1] for p in pending]
-        idxs = [p[0] for p in pending]
-        first = pcs[0]
         ctx = patterns.context(first.k, S, first.canonical, bool(consider_missing_cluster),
                                patfilt == False, maf, device, sort_bits)  # noqa: E712
-        pos_text, pat_text, hash_texts = _run_batch(patterns, ctx, pcs, idxs, S, first.k,
+        pos_text, pat_text, hash_texts = _run_batch(patterns, ctx, hb, meta, idxs, S, first.k,
                                                     first.canonical, bool(consider_missing_cluster))
         if multiple_files:
             path = os.path.join(output, idxs[0])
@@ -272,9 +279,14 @@ def pattern_hasher(cluster_dict_iter, kmer_stroi, hash_pat, kmer_hash, genepres,
             if pat_text:
                 hash_pat.write(pat_text)
             kmer_hash.write("".join(hash_texts))
-        pending, pending_records = [], 0
+        if ready is None:
+            pending, pending_records = [], 0
 
     for idx, pc, clusterpresab, memchunk in cluster_dict_iter:
+        if hasattr(pc, "hb"):               # a whole batch from the native feeder (never with --multiple-files)
+            flush()
+            flush(pc)
+            continue
         if multiple_files:
             flush()
             patterns.reset()

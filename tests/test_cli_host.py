@@ -94,3 +94,18 @@ def test_cli_host_logic_multiple_files(tmp_path, monkeypatch):
         assert n > 1
     finally:
         os.chdir(cwd)
+
+
+def test_cli_host_logic_native_feeder_many_batches(tmp_path, monkeypatch):
+    """--native-feeder with the library's whole-batch cuts forced down to a few clusters each."""
+    import functools
+    from panfeed_b200 import feeder
+    monkeypatch.setattr(feeder, "iter_packed_batches",
+                        functools.partial(feeder.iter_packed_batches, first_cells=9, target_bases=5000))
+    for mode in ("considermissing", "secondpass", "nc_updown"):
+        out = str(tmp_path / mode)
+        _run_cli(list(helpers.modes()[mode]) + ["--native-feeder"], out, monkeypatch)
+        assert OracleContext.instances[0].n_batches > 2
+        for name in helpers.FILES:
+            assert helpers.sorted_lines(_read(os.path.join(out, name))) == \
+                helpers.sorted_lines(helpers.golden(mode, name)), (mode, name)

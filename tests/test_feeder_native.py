@@ -214,3 +214,40 @@ def test_cut_packed_equals_cut_then_pack():
     with pytest.raises(ValueError, match=r"\*"):
         native.cut(np.array([g], np.uint32), b"z", 0, 0, False, prepack=True)
     native.close()
+
+
+@pytest.mark.parametrize("up,down,dsc,first_cells,target", [(0, 0, False, 16384, 96 << 20), (100, 50, False, 7, 3000),
+                                                            (40, 40, True, 1, 1), (30, 10, False, 25, 40000)])
+def test_packed_batches_equal_packed_clusters(up, down, dsc, first_cells, target):
+    """iter_packed_batches (one library call and a few array operations per GPU batch) hands over
+    exactly the pf_batch that pack_batch builds from the per-cluster objects of
+    iter_packed_clusters, whatever the batch boundaries; sequence metadata on demand."""
+    stroi = {"s00", "s05"}
+    gffdir = os.path.join(FIX, "gffs")
+    filelist, fastalist = pyin.what_are_my_inputfiles(gffdir, None)
+    table = _table()
+    native, index = nf.prep_feeder(filelist, fastalist, gffdir, None)
+    clusters = list(nf.iter_packed_clusters(table, native, index, up, down, dsc, stroi, 31, True, False))
+    batches = list(nf.iter_packed_batches(table, native, index, up, down, dsc, stroi, 31, True, False,
+                                          target_bases=target, first_cells=first_cells))
+    assert sum(len(b[0]) for b in batches) == len(clusters)
+    if first_cells < 100:
+        assert len(batches) > 1
+    at = 0
+    for idxs, pb, _, _ in batches:
+        mine = clusters[at:at + len(idxs)]
+        at += len(idxs)
+        assert idxs == [c[0] for c in mine] == pb.idxs
+        want, meta, _ = packer.pack_batch([c[1] for c in mine])
+        got = pb.hb
+        assert (got.packed == want.packed).all()
+        assert got.seqs.tobytes() == want.seqs.tobytes()
+        assert got.clusters.tobytes() == want.clusters.tobytes()
+        assert (got.presence == want.presence).all() and got.presence.dtype == want.presence.dtype
+        assert (got.amb is None) == (want.amb is None)
+        if want.amb is not None:
+            assert (got.amb == want.amb).all()
+        assert [pb.meta(i) for i in range(len(got.seqs))] == list(meta)
+        assert pb.n_records(31, True) == sum(c[1].n_records(31, True) for c in mine)
+        assert (pb.k, pb.canonical, pb.consider_missing) == (31, True, False)
+    native.close()

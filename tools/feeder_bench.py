@@ -74,5 +74,13 @@ print(f"native feeder: read {t1 - t0:.2f} s, cut {t2 - t1:.2f} s, pack {t3 - t2:
       f"-> {bases / (t3 - t1) / 1e6:.1f} Mbases/s cut+pack")
 assert (hb.packed == hb2.packed).all() and hb.seqs.tobytes() == hb2.seqs.tobytes()
 print("batches identical")
+
+t1 = time.perf_counter()
+got = [x[1] for x in nf.iter_packed_batches(table, native, index, 100, 100, False, stroi, 31, True, False)]
+t2 = time.perf_counter()
+nb = sum(int(b.hb.seqs["len"].sum()) for b in got)
+assert nb == bases
+print(f"native feeder, whole batches (iter_packed_batches, {len(got)} batches): cut + pack {t2 - t1:.2f} s "
+      f"-> {bases / (t2 - t1) / 1e6:.1f} Mbases/s")
 import shutil
 shutil.rmtree(tmp)
