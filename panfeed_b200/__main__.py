@@ -63,9 +63,12 @@ def get_options(argv=None):
     p.add_argument("--consider-missing", action="store_true", default=False)
     p.add_argument("--multiple-files", action="store_true", default=False)
     p.add_argument("--compress", action="store_true", default=False)
+    p.add_argument("--python-feeder", action="store_true", default=False,
+                   help="parse GFF/FASTA and cut the cluster sequences with the Python loops that mirror the "
+                        "reference's input.py instead of the library's native feeder (pf_feeder_*, the "
+                        "default: same outputs, an order of magnitude faster)")
     p.add_argument("--native-feeder", action="store_true", default=False,
-                   help="parse GFF/FASTA and cut the cluster sequences in the library (pf_feeder_*) "
-                        "instead of the Python loops; same outputs")
+                   help="accepted for compatibility: the native feeder is the default")
     p.add_argument("--cores", type=int, default=1, help="accepted for compatibility (GPU build)")
     p.add_argument("-ql", "--queue-limit", type=int, default=3,
                    help="accepted for compatibility (GPU build)")
@@ -133,14 +136,16 @@ def main(argv=None):
     if not args.multiple_files and not sharded:
         write_headers(hash_pat, kmer_hash, genepres)
     logger.info("Extracting k-mers")
-    if args.native_feeder:
-        from .feeder import iter_packed_batches, iter_packed_clusters, prep_feeder
+    if not args.python_feeder:
+        from .feeder import iter_packed_batches, iter_packed_clusters, prefetch, prep_feeder
         native, genome_index = prep_feeder(filelist, fastalist, args.gff, args.fasta, args.output)
         # whole GPU batches straight from the library; --multiple-files runs cluster by cluster
         cut = iter_packed_clusters if args.multiple_files else iter_packed_batches
         cut_clusters = cut(genepres, native, genome_index, args.upstream, args.downstream,
                            args.downstream_start_codon, stroi, klength, not args.non_canonical,
                            args.consider_missing, genes, args.stop_on_missing)
+        if not args.multiple_files:
+            cut_clusters = prefetch(cut_clusters)      # the next batch is cut while this one runs
     else:
         data = prep_data_n_fasta(filelist, fastalist, args.gff, args.fasta, args.output)
         iter_i = iter_gene_clusters(genepres, data, args.upstream, args.downstream,

@@ -258,6 +258,50 @@ def prep_feeder(filelist, fastalist, gffdir, fastadir, output=None):
     return feeder, index
 
 
+def prefetch(iterator, depth=2):
+    """Runs `iterator` on a background thread, `depth` items ahead of the consumer: the library
+    cuts and packs the next GPU batch (GIL released inside the calls) while the current one is on
+    the device and its rows are formatted and written.  Exceptions of the producer are re-raised
+    at the consumer, in order."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=max(1, int(depth)))
+    done = object()
+    stop = threading.Event()
+
+    def put(item):
+        while not stop.is_set():
+            try:
+                q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def work():
+        try:
+            for item in iterator:
+                if not put((item, None)):
+                    return
+            put((done, None))
+        except BaseException as exc:      # noqa: BLE001 - handed to the consumer
+            put((done, exc))
+
+    th = threading.Thread(target=work, name="pf-feeder", daemon=True)
+    th.start()
+    try:
+        while True:
+            item, exc = q.get()
+            if exc is not None:
+                raise exc
+            if item is done:
+                return
+            yield item
+    finally:
+        stop.set()                        # the consumer left early (error downstream): let the producer go
+        th.join(timeout=5)
+
+
 class _CutPlan:
     """What both iterators share: the panaroo table as arrays in sample-rank order, the rows to cut
     and the library call that cuts a run of them."""

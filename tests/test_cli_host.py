@@ -35,7 +35,7 @@ def _run_cli(args, out, monkeypatch):
 @pytest.mark.parametrize("feeder", ["python", "native"])
 @pytest.mark.parametrize("mode", sorted(helpers.modes()))
 def test_cli_host_logic_matches_reference(mode, feeder, tmp_path, monkeypatch):
-    args = list(helpers.modes()[mode]) + (["--native-feeder"] if feeder == "native" else [])
+    args = list(helpers.modes()[mode]) + (["--native-feeder"] if feeder == "native" else ["--python-feeder"])
     out = str(tmp_path / "out")
     _run_cli(args, out, monkeypatch)
     for name in helpers.FILES:
@@ -56,21 +56,22 @@ def test_cli_host_logic_small_batches(tmp_path, monkeypatch):
     monkeypatch.setattr(panfeed, "BATCH_RECORDS", 2000)
     for mode in ("considermissing", "secondpass"):
         out = str(tmp_path / mode)
-        _run_cli(list(helpers.modes()[mode]), out, monkeypatch)
+        _run_cli(list(helpers.modes()[mode]) + ["--python-feeder"], out, monkeypatch)
         assert OracleContext.instances[0].n_batches > 1
         for name in helpers.FILES:
             assert helpers.sorted_lines(_read(os.path.join(out, name))) == \
                 helpers.sorted_lines(helpers.golden(mode, name)), (mode, name)
 
 
-def test_cli_host_logic_multiple_files(tmp_path, monkeypatch):
+@pytest.mark.parametrize("feeder", [[], ["--python-feeder"]])
+def test_cli_host_logic_multiple_files(feeder, tmp_path, monkeypatch):
     """--multiple-files: one directory per cluster, the pattern set reset per cluster
     (panfeed.py:35-43,153-167); against the reference's restatement per cluster."""
     import pandas as pd
     from oracle import ref_port
     out = str(tmp_path / "out")
     _run_cli(["--gff", "fixture/gffs/", "--presence-absence", "fixture/gene_presence_absence.csv",
-              "--targets", "fixture/stroi.txt", "--multiple-files"], out, monkeypatch)
+              "--targets", "fixture/stroi.txt", "--multiple-files"] + feeder, out, monkeypatch)
     cwd = os.getcwd()
     os.chdir(helpers.GOLDEN)
     try:

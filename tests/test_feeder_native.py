@@ -251,3 +251,39 @@ def test_packed_batches_equal_packed_clusters(up, down, dsc, first_cells, target
         assert pb.n_records(31, True) == sum(c[1].n_records(31, True) for c in mine)
         assert (pb.k, pb.canonical, pb.consider_missing) == (31, True, False)
     native.close()
+
+
+def test_prefetch_order_errors_and_early_exit():
+    """feeder.prefetch: same items in the same order; a producer error surfaces at the consumer
+    after the items before it; a consumer that stops early does not leave the producer stuck."""
+    import threading
+    import time
+    assert list(nf.prefetch(iter(range(100)), depth=3)) == list(range(100))
+    assert list(nf.prefetch(iter(()))) == []
+
+    def failing():
+        yield 1
+        yield 2
+        raise KeyError("gene")
+    got = []
+    with pytest.raises(KeyError, match="gene"):
+        for x in nf.prefetch(failing()):
+            got.append(x)
+    assert got == [1, 2]
+
+    produced = []
+
+    def endless():
+        i = 0
+        while True:
+            produced.append(i)
+            yield i
+            i += 1
+    before = threading.active_count()
+    gen = nf.prefetch(endless(), depth=2)
+    assert next(gen) == 0
+    gen.close()
+    time.sleep(0.3)
+    n = len(produced)
+    time.sleep(0.3)
+    assert len(produced) == n and threading.active_count() == before

@@ -20,9 +20,10 @@ def _read(path):
 @pytest.mark.parametrize("feeder", ["python", "native"])
 @pytest.mark.parametrize("mode", sorted(helpers.modes()))
 def test_cli_outputs_match_reference(mode, feeder, tmp_path):
-    """feeder = native: GFF/FASTA parsing and cluster cutting by the library (--native-feeder)."""
+    """feeder = native: GFF/FASTA parsing and cluster cutting by the library (the default);
+    python: the loops that mirror the reference's input.py (--python-feeder)."""
     from panfeed_b200.__main__ import main
-    args = [a for a in helpers.modes()[mode]] + (["--native-feeder"] if feeder == "native" else [])
+    args = [a for a in helpers.modes()[mode]] + (["--native-feeder"] if feeder == "native" else ["--python-feeder"])
     out = str(tmp_path / "out")
     cwd = os.getcwd()
     os.chdir(helpers.GOLDEN)

@@ -53,7 +53,7 @@ def _read(path):
     return open(path).read()
 
 
-CASES = [("basic", []), ("considermissing", []), ("cm_nofilter_up", []), ("noncanonical", []),
+CASES = [("basic", ["--python-feeder"]), ("considermissing", []), ("cm_nofilter_up", []), ("noncanonical", []),
          ("compress", []), ("secondpass", ["--native-feeder"])]
 
 
