@@ -55,9 +55,9 @@ print(f"pangenome: {G} genomes x {N} clusters, {bases / 1e6:.0f} Mbases to cut (
 
 from panfeed_b200.__main__ import main  # noqa: E402
 
-for label, extra in (("first pass, python feeder", []), ("first pass, native feeder", ["--native-feeder"]),
+for label, extra in (("first pass, python feeder", ["--python-feeder"]), ("first pass, native feeder (default)", []),
                      ("second pass (all targets, 1/10 of the clusters), native feeder",
-                      ["--native-feeder", "--targets", os.path.join(tmp, "targets.txt"), "--genes",
+                      ["--targets", os.path.join(tmp, "targets.txt"), "--genes",
                        os.path.join(tmp, "genes.txt")])):
     out = os.path.join(tmp, "out_" + str(abs(hash(label)) % 10000))
     t0 = time.perf_counter()
