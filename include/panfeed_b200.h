@@ -453,6 +453,12 @@ int  pf_feeder_genome_info(const pf_feeder* f, uint32_t genome, uint32_t* n_feat
                            uint64_t* n_bases);
 int  pf_feeder_feature(const pf_feeder* f, uint32_t genome, uint32_t feature, const char** id,
                        const char** contig, int64_t* start, int64_t* end, int32_t* strand);
+/* Contig `contig` of a genome (in order of first appearance): its name, its length and whether it
+ * is used IN PLACE - a FASTA record whose lines all have one width (a shorter last one allowed)
+ * stays where it lies in the mapped file text, case folded when a window is cut; any other record
+ * is copied line by line, stripped and upper-cased as the reference's pyfaidx contigs are. */
+int  pf_feeder_contig(const pf_feeder* f, uint32_t genome, uint32_t contig, const char** name,
+                      uint64_t* n_bases, uint32_t* in_place);
 /* One cluster: cells_blob = the n_cells panaroo cells (';'-separated feature ids) of the strains
  * that have the cluster, joined with '\n'; genome[i] = genome index of cell i.  The result (valid
  * until the next call on this feeder) lists the sequences cell by cell, genes in cell order. */

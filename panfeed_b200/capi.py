@@ -141,7 +141,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_format_positions_compact",
            "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns", "pf_format_kmer_rows", "pf_gzip_members",
            "pf_feeder_create", "pf_feeder_destroy", "pf_feeder_last_error", "pf_feeder_add_genome", "pf_feeder_add_genomes",
-           "pf_feeder_add_genome_text", "pf_feeder_genome_info", "pf_feeder_feature", "pf_feeder_cut",
+           "pf_feeder_add_genome_text", "pf_feeder_genome_info", "pf_feeder_feature", "pf_feeder_contig", "pf_feeder_cut",
            "pf_feeder_cut_packed",
            "pf_tsv_filter", "pf_free",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
@@ -194,6 +194,7 @@ def load():
     lib.pf_feeder_genome_info.argtypes = [vp, u32, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64)]
     lib.pf_feeder_feature.argtypes = [vp, u32, u32, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p),
                                       C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
+    lib.pf_feeder_contig.argtypes = [vp, u32, u32, C.POINTER(C.c_char_p), C.POINTER(u64), C.POINTER(u32)]
     lib.pf_feeder_cut.argtypes = [vp, u32, vp, C.c_char_p, u64, C.c_int32, C.c_int32, C.c_int32,
                                   C.POINTER(CutResult)]
     lib.pf_feeder_cut_packed.argtypes = [vp, u32, vp, C.c_char_p, u64, C.c_int32, C.c_int32, C.c_int32, u32,

@@ -20,6 +20,11 @@
 #include <unordered_map>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "../../include/panfeed_b200.h"
 
 namespace {
@@ -30,12 +35,57 @@ struct FeatureRec {
   int32_t strand = 1;
 };
 
+// The text of one input file: a private mapping of the file (no copy out of the page cache and
+// no first touch of as much fresh memory, which costs more than the parsing itself and does
+// not scale over threads) or, where a file cannot be mapped, a buffer read with fread.
+struct FileText {
+  char* p = nullptr;
+  size_t n = 0, mapped = 0;
+  std::string owned;
+  FileText() = default;
+  FileText(const FileText&) = delete;
+  FileText& operator=(const FileText&) = delete;
+  FileText(FileText&& o) noexcept { *this = std::move(o); }
+  FileText& operator=(FileText&& o) noexcept {
+    if (this != &o) {
+      release();
+      const bool in_owned = !o.mapped && o.p;
+      owned = std::move(o.owned);
+      p = in_owned ? &owned[0] : o.p;
+      n = o.n; mapped = o.mapped;
+      o.p = nullptr; o.n = 0; o.mapped = 0;
+    }
+    return *this;
+  }
+  ~FileText() { release(); }
+  void release() {
+    if (mapped) munmap(p, mapped);
+    p = nullptr; n = 0; mapped = 0;
+    owned = std::string();
+  }
+  const char* data() const { return p; }
+  size_t size() const { return n; }
+};
+
+// A contig is either a string of its own (upper case, the copying parser) or a VIEW of the
+// genome's file text: a FASTA record whose lines all hold `width` symbols (the last one may be
+// shorter) needs no copy - base i sits at lines[i + i / width] - and no second first touch of
+// as much memory again; its case is folded when a window is cut.
+struct Contig {
+  std::string owned;
+  const char* lines = nullptr;
+  uint64_t width = 0, n = 0;
+  uint64_t size() const { return lines ? n : (uint64_t)owned.size(); }
+};
+
 struct Genome {
   std::string name;
   std::vector<FeatureRec> features;
   std::unordered_map<std::string, uint32_t> feature_of;       // id -> index (the last one wins)
-  std::vector<std::string> contig_name, contig_seq;
+  std::vector<std::string> contig_name;
+  std::vector<Contig> contigs;
   std::unordered_map<std::string, uint32_t> contig_of;        // name -> index (the last one wins)
+  FileText text;                                              // the file the views point into
 };
 
 inline bool str_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 && c <= 31); }
@@ -62,28 +112,33 @@ bool py_int(const char* p, const char* e, int64_t* out) {
   return true;
 }
 
-// text-mode reading like Python's open(path): "\r\n" and lone "\r" become "\n".  One read of the
-// whole file; the translation (in place) only runs if the text holds a '\r' at all.
-bool read_text(const char* path, std::string* out) {
-  FILE* f = fopen(path, "rb");
-  if (!f) return false;
-  out->clear();
-  long size = -1;
-  if (fseek(f, 0, SEEK_END) == 0) { size = ftell(f); if (fseek(f, 0, SEEK_SET) != 0) size = -1; }
-  size_t got = 0;
-  if (size > 0) {
-    out->resize((size_t)size);
-    got = fread(&(*out)[0], 1, (size_t)size, f);
-    out->resize(got);
+// text-mode reading like Python's open(path): "\r\n" and lone "\r" become "\n" - in place (the
+// mapping is private: copy on write), and only if the text holds a '\r' at all.
+bool read_text(const char* path, FileText* out) {
+  out->release();
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return false;
+  struct stat st;
+  if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+    void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);
+    if (m != MAP_FAILED) {
+      madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+      out->p = (char*)m;
+      out->n = out->mapped = (size_t)st.st_size;
+    }
   }
-  if (size < 0 || got == (size_t)size) {            // not seekable, or the file grew: take what follows
+  if (!out->mapped) {                                 // a pipe, an empty file, no mmap: read it
+    std::string& b = out->owned;
+    b.reserve(1 << 16);                               // (never the in-object small-string buffer: views point here)
     char buf[1 << 16];
-    size_t n;
-    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out->append(buf, n);
+    ssize_t got;
+    while ((got = read(fd, buf, sizeof buf)) > 0) b.append(buf, (size_t)got);
+    out->p = &b[0];
+    out->n = b.size();
   }
-  fclose(f);
-  char* b = &(*out)[0];
-  const size_t n = out->size();
+  close(fd);
+  char* b = out->p;
+  const size_t n = out->n;
   const char* first = n ? (const char*)memchr(b, '\r', n) : nullptr;
   if (first) {
     size_t w = (size_t)(first - b);
@@ -95,7 +150,7 @@ bool read_text(const char* path, std::string* out) {
         b[w++] = b[i];
       }
     }
-    out->resize(w);
+    out->n = w;
   }
   return true;
 }
@@ -170,22 +225,55 @@ void parse_gff_text(const char* p, const char* e, Genome* g, uint32_t* skipped) 
   }
 }
 
+// A FASTA record as a view (see Contig): body .. the next line that starts with '>' (or e).  Regular
+// means: every line holds the same number of symbols except a shorter last one, no line starts or
+// ends with whitespace (the copying parser would strip it), blank lines only after the last one.
+// Returns the end of the record, or nullptr if the record has to be copied.
+const char* fasta_record_view(const char* body, const char* e, Contig* c) {
+  const char* q = body;
+  uint64_t width = 0, n = 0;
+  bool last_short = false, ended = false;
+  while (q < e && *q != '>') {
+    const char* nl = (const char*)memchr(q, '\n', e - q);
+    const char* le = nl ? nl : e;
+    const uint64_t len = (uint64_t)(le - q);
+    if (len == 0) {
+      ended = true;
+    } else {
+      if (ended || last_short || str_space((unsigned char)q[0]) || str_space((unsigned char)le[-1])) return nullptr;
+      if (width == 0) width = len;
+      else if (len > width) return nullptr;
+      if (len < width) last_short = true;
+      n += len;
+    }
+    q = nl ? nl + 1 : e;
+  }
+  if (n == 0) return nullptr;                       // nothing to point at: an (empty) string of its own
+  c->owned.clear();
+  c->lines = body;
+  c->width = width;
+  c->n = n;
+  return q;
+}
+
 // input.py read_fasta_text: '>' lines name a record (first whitespace-separated word, "" if none),
 // other lines are stripped and appended; sequences are upper-cased; a repeated name replaces.
-void parse_fasta_text(const char* p, const char* e, Genome* g) {
+// views: [p, e) outlives the genome (it is the genome's own `text`): regular records stay where they are.
+void parse_fasta_text(const char* p, const char* e, Genome* g, bool views) {
   bool have = false;
-  std::string name, seq;
+  std::string name;
+  Contig cur;
   auto close = [&]() {
     if (!have) return;
     auto it = g->contig_of.find(name);
     if (it == g->contig_of.end()) {
       g->contig_of.emplace(name, (uint32_t)g->contig_name.size());
       g->contig_name.push_back(name);
-      g->contig_seq.push_back(std::move(seq));
+      g->contigs.push_back(std::move(cur));
     } else {
-      g->contig_seq[it->second] = std::move(seq);
+      g->contigs[it->second] = std::move(cur);
     }
-    seq.clear();
+    cur = Contig();
   };
   while (p < e) {
     const char* nl = (const char*)memchr(p, '\n', e - p);
@@ -200,16 +288,21 @@ void parse_fasta_text(const char* p, const char* e, Genome* g) {
       while (w < l1 && !str_space((unsigned char)*w)) ++w;
       name.assign(q, w);
       have = true;
+      const char* body = nl ? nl + 1 : e;
+      if (views) {
+        const char* end = fasta_record_view(body, e, &cur);
+        if (end) { p = end; continue; }
+      }
       // one allocation per contig: its lines end where the next record starts (growing the string
       // line by line re-allocates and page-faults its way up, which serialises the parsing threads)
-      const char* body = nl ? nl + 1 : e;
       const char* next = body < e ? (*body == '>' ? body : (const char*)memmem(body, (size_t)(e - body), "\n>", 2)) : e;
-      seq.reserve((size_t)((next ? next : e) - body));
+      cur.owned.reserve((size_t)((next ? next : e) - body));
     } else if (have) {
       const char* a = p;
       const char* b = l1;
       while (a < b && str_space((unsigned char)*a)) ++a;
       while (b > a && str_space((unsigned char)b[-1])) --b;
+      std::string& seq = cur.owned;
       const size_t at = seq.size();
       seq.append(a, b);
       char* q = &seq[at];                               // str.upper() of the reference's contigs (ASCII)
@@ -234,6 +327,25 @@ struct CompLut {
   }
 };
 const CompLut kComp;
+
+// bases [lo, hi) of a contig as contiguous upper-case bytes: where they are when the contig owns
+// its text, gathered line by line into `tmp` (case folded) when it is a view of the file
+const unsigned char* contig_window(const Contig& c, int64_t lo, int64_t hi, std::vector<unsigned char>& tmp) {
+  if (!c.lines) return reinterpret_cast<const unsigned char*>(c.owned.data()) + lo;
+  tmp.resize((size_t)(hi - lo));
+  unsigned char* dst = tmp.data();
+  uint64_t pos = (uint64_t)lo;
+  const uint64_t end = (uint64_t)hi;
+  while (pos < end) {
+    const uint64_t col = pos % c.width;
+    const uint64_t take = std::min<uint64_t>(c.width - col, end - pos);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(c.lines) + pos + pos / c.width;
+    for (uint64_t i = 0; i < take; ++i) dst[i] = (unsigned char)(src[i] - (((unsigned)(src[i] - 'a') < 26u) << 5));
+    dst += take;
+    pos += take;
+  }
+  return tmp.data();
+}
 
 }  // namespace
 
@@ -267,15 +379,16 @@ extern "C" void pf_feeder_destroy(pf_feeder* f) { delete f; }
 
 extern "C" const char* pf_feeder_last_error(const pf_feeder* f) { return f ? f->err.c_str() : "null feeder"; }
 
-extern "C" int pf_feeder_add_genome_text(pf_feeder* f, const char* name, const char* gff, uint64_t gff_len,
-                                         const char* fasta, uint64_t fasta_len, uint32_t* skipped_lines) {
-  if (!f || !name || (!gff && gff_len)) return PF_ERR_INVALID;
-  Genome g;
-  g.name = name;
+namespace {
+// views: gff (or fasta, when given) is g.text and stays alive with the genome
+int add_genome_parsed(pf_feeder* f, Genome&& g_in, const char* gff, uint64_t gff_len, const char* fasta,
+                      uint64_t fasta_len, uint32_t* skipped_lines, bool views) {
+  Genome g = std::move(g_in);
+  const char* name = g.name.c_str();
   uint32_t skipped = 0;
   parse_gff_text(gff, gff + gff_len, &g, &skipped);
   if (fasta) {
-    parse_fasta_text(fasta, fasta + fasta_len, &g);
+    parse_fasta_text(fasta, fasta + fasta_len, &g, views);
   } else {
     // open(gff).read().split("##FASTA")[1]: the text between the first and the second marker
     const char* a = gff_len ? (const char*)memmem(gff, gff_len, "##FASTA", 7) : nullptr;
@@ -286,29 +399,49 @@ extern "C" int pf_feeder_add_genome_text(pf_feeder* f, const char* name, const c
     const char* end = gff + gff_len;
     const char* b = (const char*)memmem(a + 7, (size_t)(end - (a + 7)), "##FASTA", 7);
     if (!b) b = end;
-    parse_fasta_text(a + 7, b, &g);
+    parse_fasta_text(a + 7, b, &g, views);
   }
   if (skipped_lines) *skipped_lines = skipped;
   f->genomes.push_back(std::move(g));
   return (int)f->genomes.size() - 1;
 }
+}  // namespace
+
+extern "C" int pf_feeder_add_genome_text(pf_feeder* f, const char* name, const char* gff, uint64_t gff_len,
+                                         const char* fasta, uint64_t fasta_len, uint32_t* skipped_lines) {
+  if (!f || !name || (!gff && gff_len)) return PF_ERR_INVALID;
+  Genome g;
+  g.name = name;
+  return add_genome_parsed(f, std::move(g), gff, gff_len, fasta, fasta_len, skipped_lines, false);   // the caller's memory
+}
 
 namespace {
-// gff / fasta: file buffers the caller keeps from genome to genome (their capacity is reused)
 int add_genome_files(pf_feeder* f, const char* name, const char* gff_path, const char* fasta_path,
-                     uint32_t* skipped_lines, std::string& gff, std::string& fasta) {
+                     uint32_t* skipped_lines) {
+  FileText gff, fasta;
   if (!read_text(gff_path, &gff)) { f->err = std::string("cannot read ") + gff_path; return PF_ERR_INVALID; }
   if (fasta_path && !read_text(fasta_path, &fasta)) { f->err = std::string("cannot read ") + fasta_path; return PF_ERR_INVALID; }
-  return pf_feeder_add_genome_text(f, name, gff.data(), gff.size(), fasta_path ? fasta.data() : nullptr, fasta.size(),
-                                   skipped_lines);
+  // the text that holds the sequences becomes the genome's: regular FASTA records are used in place
+  Genome g;
+  g.name = name;
+  g.text = std::move(fasta_path ? fasta : gff);     // (mapping or heap buffer: the address stays)
+  const char* t = g.text.data();
+  const uint64_t tn = g.text.size();
+  const int rc = fasta_path ? add_genome_parsed(f, std::move(g), gff.data(), gff.size(), t, tn, skipped_lines, true)
+                            : add_genome_parsed(f, std::move(g), t, tn, nullptr, 0, skipped_lines, true);
+  if (rc >= 0) {
+    bool used = false;
+    for (const Contig& c : f->genomes[rc].contigs) used |= c.lines != nullptr;
+    if (!used) f->genomes[rc].text.release();       // nothing points into it
+  }
+  return rc;
 }
 }  // namespace
 
 extern "C" int pf_feeder_add_genome(pf_feeder* f, const char* name, const char* gff_path, const char* fasta_path,
                                     uint32_t* skipped_lines) {
   if (!f || !name || !gff_path) return PF_ERR_INVALID;
-  std::string gff, fasta;
-  return add_genome_files(f, name, gff_path, fasta_path, skipped_lines, gff, fasta);
+  return add_genome_files(f, name, gff_path, fasta_path, skipped_lines);
 }
 
 // Many genomes at once: the files are read and parsed on host threads (a genome is a few MB of
@@ -327,11 +460,10 @@ extern "C" int pf_feeder_add_genomes(pf_feeder* f, uint32_t n, const char* const
   std::vector<std::thread> th;
   for (uint32_t t = 0; t < nt; ++t)
     th.emplace_back([&, t]() {
-      std::string gff, fasta;                             // this thread's file buffers
       for (uint32_t i = t; i < n; i += nt) {
         uint32_t sk = 0;
         if (!names[i] || !gff_paths[i]) { rc[i] = PF_ERR_INVALID; continue; }
-        rc[i] = add_genome_files(&local[i], names[i], gff_paths[i], fasta_paths ? fasta_paths[i] : nullptr, &sk, gff, fasta);
+        rc[i] = add_genome_files(&local[i], names[i], gff_paths[i], fasta_paths ? fasta_paths[i] : nullptr, &sk);
         if (skipped_lines) skipped_lines[i] = sk;
       }
     });
@@ -348,7 +480,17 @@ extern "C" int pf_feeder_genome_info(const pf_feeder* f, uint32_t genome, uint32
   const Genome& g = f->genomes[genome];
   if (n_features) *n_features = (uint32_t)g.features.size();
   if (n_contigs) *n_contigs = (uint32_t)g.contig_name.size();
-  if (n_bases) { uint64_t n = 0; for (auto& s : g.contig_seq) n += s.size(); *n_bases = n; }
+  if (n_bases) { uint64_t n = 0; for (auto& c : g.contigs) n += c.size(); *n_bases = n; }
+  return PF_OK;
+}
+
+extern "C" int pf_feeder_contig(const pf_feeder* f, uint32_t genome, uint32_t contig, const char** name,
+                                uint64_t* n_bases, uint32_t* in_place) {
+  if (!f || genome >= f->genomes.size() || contig >= f->genomes[genome].contigs.size()) return PF_ERR_INVALID;
+  const Genome& g = f->genomes[genome];
+  if (name) *name = g.contig_name[contig].c_str();
+  if (n_bases) *n_bases = g.contigs[contig].size();
+  if (in_place) *in_place = g.contigs[contig].lines ? 1u : 0u;
   return PF_OK;
 }
 
@@ -369,7 +511,7 @@ extern "C" int pf_feeder_feature(const pf_feeder* f, uint32_t genome, uint32_t f
 // feature and its contig are looked up (a miss is recorded, the gene skipped), the window
 // [a, b) is sliced with Python's clamping and, on the minus strand, reverse-complemented.
 namespace {
-struct Piece { const std::string* contig; int64_t lo, hi; bool minus; };
+struct Piece { const Contig* contig; int64_t lo, hi; bool minus; };
 
 // pass 1 (serial): look the genes up, place the windows; fills the descriptor arrays of `f`
 int place_windows(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
@@ -406,7 +548,7 @@ int place_windows(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const 
       const FeatureRec& ft = g.features[fi->second];
       auto cit = g.contig_of.find(ft.contig);
       if (cit == g.contig_of.end()) { miss(1, ft.contig); continue; }
-      const std::string& contig = g.contig_seq[cit->second];
+      const Contig& contig = g.contigs[cit->second];
       // cut_window (reference input.py:413-446)
       const bool over_up = ft.strand > 0 && ft.start - 1 - up < 0;
       const bool over_down = ft.strand < 0 && ft.start - 1 - down < 0;
@@ -490,15 +632,17 @@ extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* gen
     char* base = f->ascii.get();
     const size_t n_seq = pieces.size();
     auto fill = [&](size_t s0, size_t s1) {
+      std::vector<unsigned char> tmp;
       for (size_t s = s0; s < s1; ++s) {
         const Piece& pc = pieces[s];
         char* dst = base + f->seq_off[s];
         const int64_t len = pc.hi - pc.lo;
+        if (len <= 0) continue;
+        const unsigned char* src = contig_window(*pc.contig, pc.lo, pc.hi, tmp);
         if (pc.minus) {
-          const char* src = pc.contig->data();
-          for (int64_t i = 0; i < len; ++i) dst[i] = (char)kComp.t[(unsigned char)src[pc.hi - 1 - i]];
-        } else if (len > 0) {
-          memcpy(dst, pc.contig->data() + pc.lo, (size_t)len);
+          for (int64_t i = 0; i < len; ++i) dst[i] = (char)kComp.t[src[len - 1 - i]];
+        } else {
+          memcpy(dst, src, (size_t)len);
         }
       }
     };
@@ -576,10 +720,11 @@ extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32
   };
   // pf_pack_2bit: padding and non-ACGT symbols pack as A; a sequence with any of the latter is flagged
   run([&](uint32_t t) {
+    std::vector<unsigned char> tmp;
     for (size_t s = cut[t]; s < cut[t + 1]; ++s) {
       const Piece& pc = pieces[s];
       const uint64_t len = (uint64_t)(pc.hi - pc.lo);
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(pc.contig->data());
+      const unsigned char* src = len ? contig_window(*pc.contig, pc.lo, pc.hi, tmp) : nullptr;
       uint64_t* dst = f->packed.get() + f->base_off[s] / 32;
       const uint64_t words = (len + 63) / 64 * 2;
       uint32_t bad = 0;
@@ -588,10 +733,10 @@ extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32
         const uint32_t m = (uint32_t)std::min<uint64_t>(32, len > p0 ? len - p0 : 0);
         uint64_t v = 0;
         if (pc.minus) {
-          const unsigned char* q = src + pc.hi - 1 - p0;          // symbol j of the word: complement of q[-j]
+          const unsigned char* q = src + len - 1 - p0;            // symbol j of the word: complement of q[-j]
           for (uint32_t j = 0; j < m; ++j) { const uint32_t c = kPack.two_rc[*(q - j)]; bad |= c; v = (v << 2) | (c & 3u); }
         } else {
-          const unsigned char* q = src + pc.lo + p0;
+          const unsigned char* q = src + p0;
           for (uint32_t j = 0; j < m; ++j) { const uint32_t c = kPack.two_fwd[q[j]]; bad |= c; v = (v << 2) | (c & 3u); }
         }
         dst[w] = m ? v << (2 * (32 - m)) : 0;
@@ -616,10 +761,11 @@ extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32
       f->amb_plane.reset(new uint64_t[f->amb_cap]);
     }
     const uint64_t a_code = kPack.four_fwd[(unsigned char)'A'];
+    std::vector<unsigned char> tmp;
     for (uint32_t s : amb_seqs) {
       const Piece& pc = pieces[s];
       const uint64_t len = (uint64_t)(pc.hi - pc.lo), padded = (len + 63) / 64 * 64;
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(pc.contig->data());
+      const unsigned char* src = contig_window(*pc.contig, pc.lo, pc.hi, tmp);
       uint64_t* dst = f->amb_plane.get() + f->amb_off[s] / 16;
       for (uint64_t w = 0; w < padded / 16; ++w) {
         uint64_t v = 0;
@@ -627,7 +773,7 @@ extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32
           const uint64_t p = w * 16 + j;
           uint64_t c = a_code;                                   // padding packs as A
           if (p < len) {
-            const unsigned char sym = pc.minus ? src[pc.hi - 1 - p] : src[pc.lo + p];
+            const unsigned char sym = pc.minus ? src[len - 1 - p] : src[p];
             c = pc.minus ? kPack.four_rc[sym] : kPack.four_fwd[sym];
             if (c == 255u) {
               if (!bad_symbol) bad_symbol = pc.minus ? kComp.t[sym] : sym;

@@ -99,6 +99,14 @@ class NativeFeeder:
             self._error(rc, "pf_feeder_genome_info")
         return {"features": nf.value, "contigs": ncg.value, "bases": nb.value}
 
+    def contig(self, genome, contig):
+        """-> (name, number of bases, used in place) of a parsed contig."""
+        name, n, in_place = C.c_char_p(), C.c_uint64(), C.c_uint32()
+        rc = self.lib.pf_feeder_contig(self.h, genome, contig, C.byref(name), C.byref(n), C.byref(in_place))
+        if rc != 0:
+            self._error(rc, "pf_feeder_contig")
+        return name.value.decode(), n.value, bool(in_place.value)
+
     def feature(self, genome, feature):
         """-> (id, contig, start, end, strand) of a parsed feature."""
         ident, contig = C.c_char_p(), C.c_char_p()

@@ -287,3 +287,101 @@ def test_prefetch_order_errors_and_early_exit():
     n = len(produced)
     time.sleep(0.3)
     assert len(produced) == n and threading.active_count() == before
+
+
+@pytest.mark.parametrize("layout", ["regular60", "regular_exact", "one_line", "crlf", "lower", "ragged", "blank_tail",
+                                    "blank_inside", "padded", "separate_fasta", "tiny"])
+def test_contig_views_match_python_feeder(layout, tmp_path):
+    """Regular FASTA records are used where they lie in the (mapped) file text, anything else is
+    copied line by line like the reference does: both must cut the same sequences, whatever the
+    line width, the length of the last line, the line ends, the case, blank or padded lines, a
+    repeated contig name, genes on both strands and windows past both contig ends."""
+    rng = np.random.default_rng(hash(layout) % 1000)
+    n_contigs = 1 if layout == "tiny" else 4
+    lens = [7] if layout == "tiny" else [240, 1200, 61, 3000]
+    if layout == "regular_exact":
+        lens = [240, 1200, 60, 3000]
+    contigs = ["".join(rng.choice(list("ACGT"), n)) for n in lens]
+    contigs[0] = contigs[0][:3] + "N" + contigs[0][4:]
+
+    def lines_of(seq, ci):
+        if layout in ("regular60", "regular_exact", "crlf", "separate_fasta", "tiny", "blank_tail"):
+            out = [seq[i:i + 60] for i in range(0, len(seq), 60)]
+        elif layout == "one_line":
+            out = [seq]
+        elif layout == "lower":
+            out = [seq[i:i + 70].lower() if (i // 70) % 2 else seq[i:i + 70] for i in range(0, len(seq), 70)]
+        elif layout == "ragged":
+            out, i = [], 0
+            while i < len(seq):
+                w = int(rng.integers(1, 90))
+                out.append(seq[i:i + w])
+                i += w
+        elif layout == "blank_inside":
+            out = [seq[i:i + 50] for i in range(0, len(seq), 50)]
+            out.insert(len(out) // 2, "")
+        elif layout == "padded":
+            out = [("  " if i % 120 == 0 else "") + seq[i:i + 60] + (" " if i % 180 == 0 else "")
+                   for i in range(0, len(seq), 60)]
+        if layout == "blank_tail":
+            out += ["", ""]
+        return out
+
+    rows, ids = [], []
+    for ci, seq in enumerate(contigs):
+        pos = 1
+        j = 0
+        while pos + 5 < len(seq):
+            ln = int(rng.integers(3, 200))
+            end = min(len(seq), pos + ln - 1)
+            strand = "+" if rng.random() < 0.5 else "-"
+            rows.append(f"c{ci}\tx\tCDS\t{pos}\t{end}\t.\t{strand}\t0\tID=g{ci}_{j};x=1")
+            ids.append(f"g{ci}_{j}")
+            pos = end + int(rng.integers(1, 40))
+            j += 1
+    fasta = []
+    for ci, seq in enumerate(contigs):
+        fasta.append(f">c{ci} description {ci}")
+        fasta += lines_of(seq, ci)
+    if layout != "tiny":                                      # a repeated name replaces the earlier record
+        fasta.append(">c1 again")
+        contigs[1] = contigs[1][::-1]
+        fasta += lines_of(contigs[1], 1)
+    nl = "\r\n" if layout == "crlf" else "\n"
+    gff_text = nl.join(["##gff-version 3"] + rows) + nl
+    fasta_text = nl.join(fasta) + nl
+    gff_path = tmp_path / "g.gff"
+    fasta_path = None
+    if layout == "separate_fasta":
+        fasta_path = tmp_path / "g.fna"
+        gff_path.write_bytes(gff_text.encode())
+        fasta_path.write_bytes(fasta_text.encode())
+        pcontigs = pyin.read_fasta_text(open(fasta_path).read().split("\n"))
+    else:
+        gff_path.write_bytes((gff_text + "##FASTA" + nl + fasta_text).encode())
+        pcontigs = pyin.read_fasta_text(open(gff_path).read().split("##FASTA")[1].split("\n"))
+    feats = pyin.parse_gff(str(gff_path))
+    assert [len(pcontigs[f"c{ci}"]) for ci in range(n_contigs)] == lens
+    native = nf.NativeFeeder()
+    g = native.add_genome("q", str(gff_path), None if fasta_path is None else str(fasta_path))
+    info = native.genome_info(g)
+    assert info == {"features": len(feats), "contigs": n_contigs, "bases": sum(lens)}
+    listed = [native.contig(g, ci) for ci in range(n_contigs)]
+    assert [(x[0], x[1]) for x in listed] == [(f"c{ci}", lens[ci]) for ci in range(n_contigs)]
+    if layout != "ragged":                      # (a short ragged record can come out regular by chance)
+        assert [x[2] for x in listed] == [layout not in ("blank_inside", "padded")] * n_contigs
+    table = pd.DataFrame({"q": [";".join(ids)]}, index=["cl"])
+    for up, down, dsc in [(0, 0, False), (25, 10, False), (5000, 5000, False), (9, 9, True)]:
+        py = list(pyin.iter_gene_clusters(table, {"q": (pcontigs, feats)}, up, down, dsc, True))
+        want = [q.sequence.encode() for q in py[0][0]["q"]]
+        cut = native.cut(np.zeros(1, np.uint32) + g, ";".join(ids).encode(), up, down, dsc, prepack=False)
+        off = cut["seq_off"].astype(np.int64)
+        got = [cut["ascii"][off[i]:off[i + 1]] for i in range(cut["n_seqs"])]
+        assert got == want, (layout, up, down, dsc)
+        packed = native.cut(np.zeros(1, np.uint32) + g, ";".join(ids).encode(), up, down, dsc, prepack=True)
+        ref = capi.pack_blob(cut["ascii"], cut["seq_off"])
+        assert (packed["packed"] == ref[0]).all() and (packed["is_amb"] == ref[2]).all()
+        assert (packed["amb_plane"] is None) == (ref[3] is None)
+        if ref[3] is not None:
+            assert (packed["amb_plane"] == ref[3]).all() and (packed["amb_off"] == ref[4]).all()
+    native.close()
