@@ -328,8 +328,9 @@ struct CompLut {
 };
 const CompLut kComp;
 
-// bases [lo, hi) of a contig as contiguous upper-case bytes: where they are when the contig owns
-// its text, gathered line by line into `tmp` (case folded) when it is a view of the file
+// bases [lo, hi) of a contig as contiguous bytes: where they are when the contig owns its text
+// (upper case), gathered line by line into `tmp` when it is a view of the file (case as in the
+// file: the consumers fold it)
 const unsigned char* contig_window(const Contig& c, int64_t lo, int64_t hi, std::vector<unsigned char>& tmp) {
   if (!c.lines) return reinterpret_cast<const unsigned char*>(c.owned.data()) + lo;
   tmp.resize((size_t)(hi - lo));
@@ -340,7 +341,7 @@ const unsigned char* contig_window(const Contig& c, int64_t lo, int64_t hi, std:
     const uint64_t col = pos % c.width;
     const uint64_t take = std::min<uint64_t>(c.width - col, end - pos);
     const unsigned char* src = reinterpret_cast<const unsigned char*>(c.lines) + pos + pos / c.width;
-    for (uint64_t i = 0; i < take; ++i) dst[i] = (unsigned char)(src[i] - (((unsigned)(src[i] - 'a') < 26u) << 5));
+    memcpy(dst, src, (size_t)take);
     dst += take;
     pos += take;
   }
@@ -513,35 +514,37 @@ extern "C" int pf_feeder_feature(const pf_feeder* f, uint32_t genome, uint32_t f
 namespace {
 struct Piece { const Contig* contig; int64_t lo, hi; bool minus; };
 
-// pass 1 (serial): look the genes up, place the windows; fills the descriptor arrays of `f`
-int place_windows(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
-                  uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
-                  std::vector<Piece>& pieces) {
-  f->seq_off.assign(1, 0);
-  f->cell.clear(); f->feature.clear();
-  f->start.clear(); f->end.clear(); f->offset.clear(); f->strand.clear();
-  f->miss_cell.clear(); f->miss_kind.clear(); f->miss_text.clear(); f->miss_off.assign(1, 0);
-  const char* p = cells_blob;
-  const char* e = cells_blob + cells_len;
+// pass 1: look the genes up, place the windows.  The cells are independent, so ranges of them go
+// to host threads (a look-up is two hash probes, ~0.5 us: on a many-core host the serial form is
+// what bounds a cut); every range fills its own arrays, which are laid end to end afterwards.
+struct Placed {
+  std::vector<Piece> pieces;
+  std::vector<uint32_t> cell, feature;
+  std::vector<int32_t> start, end, offset, strand;
+  std::vector<uint32_t> miss_cell;
+  std::vector<uint8_t> miss_kind;
+  std::string miss_text;
+  std::vector<uint64_t> miss_off;          // ends of the names inside miss_text
+};
+
+void place_cells(const pf_feeder* f, uint32_t c0, uint32_t c1, const uint32_t* genome,
+                 const std::vector<const char*>& cell_at, int32_t up, int32_t down, int32_t down_start_codon,
+                 Placed& o) {
   std::string gene;
-  for (uint32_t ci = 0; ci < n_cells; ++ci) {
-    if (genome[ci] >= f->genomes.size()) { f->err = "pf_feeder_cut: genome index out of range"; return PF_ERR_INVALID; }
+  for (uint32_t ci = c0; ci < c1; ++ci) {
     const Genome& g = f->genomes[genome[ci]];
-    const char* ce = (const char*)memchr(p, '\n', e - p);
-    if (!ce) {
-      if (ci + 1 != n_cells) { f->err = "pf_feeder_cut: fewer cells in the blob than n_cells"; return PF_ERR_INVALID; }
-      ce = e;
-    }
+    const char* p = cell_at[ci];
+    const char* ce = cell_at[ci + 1] - 1;          // the separator (or the end of the blob) after the cell
     for (const char* g0 = p; g0 <= ce;) {
       const char* g1 = (const char*)memchr(g0, ';', ce - g0);
       if (!g1) g1 = ce;
       gene.assign(g0, g1);
       g0 = g1 + 1;
       auto miss = [&](uint8_t kind, const std::string& what) {
-        f->miss_cell.push_back(ci);
-        f->miss_kind.push_back(kind);
-        f->miss_text += what;
-        f->miss_off.push_back(f->miss_text.size());
+        o.miss_cell.push_back(ci);
+        o.miss_kind.push_back(kind);
+        o.miss_text += what;
+        o.miss_off.push_back(o.miss_text.size());
       };
       auto fi = g.feature_of.find(gene);
       if (fi == g.feature_of.end()) { miss(0, gene); continue; }
@@ -569,17 +572,75 @@ int place_windows(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const 
       const int64_t lo = a < 0 ? std::max<int64_t>(a + n, 0) : std::min(a, n);
       int64_t hi = b < 0 ? std::max<int64_t>(b + n, 0) : std::min(b, n);
       if (hi < lo) hi = lo;
-      pieces.push_back(Piece{&contig, lo, hi, ft.strand < 0});
-      f->seq_off.push_back(f->seq_off.back() + (uint64_t)(hi - lo));
-      f->cell.push_back(ci);
-      f->feature.push_back(fi->second);
-      f->start.push_back((int32_t)seq_start);
-      f->end.push_back((int32_t)seq_end);
-      f->offset.push_back((int32_t)offset);
-      f->strand.push_back(ft.strand);
+      o.pieces.push_back(Piece{&contig, lo, hi, ft.strand < 0});
+      o.cell.push_back(ci);
+      o.feature.push_back(fi->second);
+      o.start.push_back((int32_t)seq_start);
+      o.end.push_back((int32_t)seq_end);
+      o.offset.push_back((int32_t)offset);
+      o.strand.push_back(ft.strand);
     }
-    p = ce < e ? ce + 1 : e;
   }
+}
+
+int place_windows(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
+                  uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
+                  std::vector<Piece>& pieces, uint32_t n_threads = 0) {
+  f->seq_off.assign(1, 0);
+  f->cell.clear(); f->feature.clear();
+  f->start.clear(); f->end.clear(); f->offset.clear(); f->strand.clear();
+  f->miss_cell.clear(); f->miss_kind.clear(); f->miss_text.clear(); f->miss_off.assign(1, 0);
+  pieces.clear();
+  // where the cells start: cell i is [cell_at[i], cell_at[i + 1] - 1)
+  std::vector<const char*> cell_at(n_cells + 1);
+  const char* p = cells_blob;
+  const char* e = cells_blob + cells_len;
+  for (uint32_t ci = 0; ci < n_cells; ++ci) {
+    if (genome[ci] >= f->genomes.size()) { f->err = "pf_feeder_cut: genome index out of range"; return PF_ERR_INVALID; }
+    cell_at[ci] = p;
+    const char* ce = (const char*)memchr(p, '\n', e - p);
+    if (!ce) {
+      if (ci + 1 != n_cells) { f->err = "pf_feeder_cut: fewer cells in the blob than n_cells"; return PF_ERR_INVALID; }
+      ce = e;
+    }
+    p = ce + 1;                                     // (one past the end after the last cell: never read)
+  }
+  cell_at[n_cells] = p;
+  // all cores, >= 2,048 cells (~1 ms) per thread; a caller that names a thread count gets it
+  uint32_t nt = n_threads ? std::min(n_threads, std::max(1u, n_cells / 8u))
+                          : std::min(std::max(1u, std::thread::hardware_concurrency()), n_cells / 2048u);
+  nt = std::max(1u, nt);
+  std::vector<Placed> part(nt);
+  if (nt == 1) {
+    place_cells(f, 0, n_cells, genome, cell_at, up, down, down_start_codon, part[0]);
+  } else {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < nt; ++t)
+      th.emplace_back([&, t]() {
+        place_cells(f, (uint32_t)((uint64_t)n_cells * t / nt), (uint32_t)((uint64_t)n_cells * (t + 1) / nt), genome,
+                    cell_at, up, down, down_start_codon, part[t]);
+      });
+    for (auto& x : th) x.join();
+  }
+  size_t n_seq = 0;
+  for (const Placed& o : part) n_seq += o.pieces.size();
+  pieces.reserve(n_seq);
+  f->seq_off.reserve(n_seq + 1);
+  for (const Placed& o : part) {
+    pieces.insert(pieces.end(), o.pieces.begin(), o.pieces.end());
+    f->cell.insert(f->cell.end(), o.cell.begin(), o.cell.end());
+    f->feature.insert(f->feature.end(), o.feature.begin(), o.feature.end());
+    f->start.insert(f->start.end(), o.start.begin(), o.start.end());
+    f->end.insert(f->end.end(), o.end.begin(), o.end.end());
+    f->offset.insert(f->offset.end(), o.offset.begin(), o.offset.end());
+    f->strand.insert(f->strand.end(), o.strand.begin(), o.strand.end());
+    const uint64_t text0 = f->miss_text.size();
+    f->miss_cell.insert(f->miss_cell.end(), o.miss_cell.begin(), o.miss_cell.end());
+    f->miss_kind.insert(f->miss_kind.end(), o.miss_kind.begin(), o.miss_kind.end());
+    f->miss_text += o.miss_text;
+    for (uint64_t end : o.miss_off) f->miss_off.push_back(text0 + end);
+  }
+  for (const Piece& pc : pieces) f->seq_off.push_back(f->seq_off.back() + (uint64_t)(pc.hi - pc.lo));
   return PF_OK;
 }
 
@@ -639,10 +700,11 @@ extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* gen
         const int64_t len = pc.hi - pc.lo;
         if (len <= 0) continue;
         const unsigned char* src = contig_window(*pc.contig, pc.lo, pc.hi, tmp);
+        auto up = [](unsigned char c) { return (unsigned char)(c - (((unsigned)(c - 'a') < 26u) << 5)); };
         if (pc.minus) {
-          for (int64_t i = 0; i < len; ++i) dst[i] = (char)kComp.t[src[len - 1 - i]];
+          for (int64_t i = 0; i < len; ++i) dst[i] = (char)kComp.t[up(src[len - 1 - i])];
         } else {
-          memcpy(dst, src, (size_t)len);
+          for (int64_t i = 0; i < len; ++i) dst[i] = (char)up(src[i]);
         }
       }
     };
@@ -677,13 +739,34 @@ struct PackLut {
     const char* amb = "ABCDGHKMNRSTVWXY";                       // the 4-bit alphabet of pf_pack_4bit
     for (int i = 0; i < 16; ++i) four[(unsigned char)amb[i]] = (uint8_t)i;
     for (int c = 0; c < 256; ++c) {
-      // 2-bit tables: 0x80 marks a symbol outside ACGT (its low bits pack as A, like pf_pack_2bit)
-      two_fwd[c] = two[c] == 255 ? 0x80 : two[c]; four_fwd[c] = four[c];
-      two_rc[c] = two[kComp.t[c]] == 255 ? 0x80 : two[kComp.t[c]]; four_rc[c] = four[kComp.t[c]];
+      // any case (contigs used in place keep the file's; the reference upper-cases them).  2-bit
+      // tables: 0x80 marks a symbol outside ACGT (its low bits pack as A, like pf_pack_2bit)
+      const int u = (c >= 'a' && c <= 'z') ? c - 32 : c;
+      two_fwd[c] = two[u] == 255 ? 0x80 : two[u]; four_fwd[c] = four[u];
+      two_rc[c] = two[kComp.t[u]] == 255 ? 0x80 : two[kComp.t[u]]; four_rc[c] = four[kComp.t[u]];
     }
   }
 };
 const PackLut kPack;
+
+// 8 symbols at a time (SWAR): x holds them as bytes, the FIRST one in the top byte.  If all are
+// ACGT in either case, *code16 = their 2-bit codes (A 0, C 1, G 2, T 3), first symbol in the top
+// bits, and the result is true; otherwise false (the caller takes the table loop).
+inline bool pack8(uint64_t x, uint32_t* code16) {
+  const uint64_t k01 = 0x0101010101010101ull;
+  x &= ~(0x20 * k01);                                             // fold the case bit
+  const uint64_t code = ((x >> 1) ^ (x >> 2)) & (3 * k01);        // A 0x41, C 0x43, G 0x47, T 0x54 -> 0, 1, 2, 3
+  const uint64_t b0 = code & k01, b1 = (code >> 1) & k01, b01 = b0 & b1;
+  // the letter each code stands for: 0x41 + {0, 2, 6, 0x13}; equal to x iff x was that letter
+  const uint64_t letter = 0x41 * k01 + (b0 << 1) + (b1 << 2) + (b1 << 1) + (b01 << 3) + (b01 << 1) + b01;
+  if (x != letter) return false;
+  uint64_t y = code;
+  y = (y | (y >> 6)) & 0x000F000F000F000Full;
+  y = (y | (y >> 12)) & 0x000000FF000000FFull;
+  y = (y | (y >> 24)) & 0xFFFFull;
+  *code16 = (uint32_t)y;
+  return true;
+}
 }  // namespace
 
 extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const char* cells_blob,
@@ -691,7 +774,7 @@ extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32
                                     uint32_t n_threads, pf_cut_result* out, pf_cut_planes* planes) {
   if (!f || !out || !planes || (n_cells && (!genome || !cells_blob))) return PF_ERR_INVALID;
   std::vector<Piece> pieces;
-  const int rc = place_windows(f, n_cells, genome, cells_blob, cells_len, up, down, down_start_codon, pieces);
+  const int rc = place_windows(f, n_cells, genome, cells_blob, cells_len, up, down, down_start_codon, pieces, n_threads);
   if (rc != PF_OK) return rc;
   const size_t n_seq = pieces.size();
   // pf_pack_plan: every sequence starts on a 64-base boundary
@@ -709,7 +792,7 @@ extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32
     f->packed.reset(new uint64_t[f->packed_cap]);
   }
   uint32_t nt = n_threads ? n_threads : std::max(1u, std::thread::hardware_concurrency());
-  nt = (uint32_t)std::min<size_t>(nt, std::max<size_t>(1, (size_t)f->seq_off.back() >> 18));    // >= 256 k bases per thread
+  if (!n_threads) nt = (uint32_t)std::min<size_t>(nt, std::max<size_t>(1, (size_t)f->seq_off.back() >> 18));    // >= 256 k bases per thread
   nt = (uint32_t)std::max<size_t>(1, std::min<size_t>(nt, n_seq));
   const std::vector<size_t> cut = split_by_bases(f->seq_off, nt);
   auto run = [&](auto&& fn) {
@@ -732,6 +815,24 @@ extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32
         const uint64_t p0 = w * 32;
         const uint32_t m = (uint32_t)std::min<uint64_t>(32, len > p0 ? len - p0 : 0);
         uint64_t v = 0;
+        if (m == 32) {                                            // a full word: four groups of 8 symbols
+          bool ok = true;
+          for (uint32_t gq = 0; gq < 4 && ok; ++gq) {
+            uint64_t x;
+            uint32_t c16;
+            if (pc.minus) {                                       // the 8 symbols END at q: the last byte loaded is the first symbol
+              memcpy(&x, src + len - p0 - 8 * gq - 8, 8);
+              ok = pack8(x, &c16);
+              c16 ^= 0xFFFFu;                                     // complement: A <-> T, C <-> G
+            } else {
+              memcpy(&x, src + p0 + 8 * gq, 8);
+              ok = pack8(__builtin_bswap64(x), &c16);
+            }
+            v = (v << 16) | c16;
+          }
+          if (ok) { dst[w] = v; continue; }
+          v = 0;
+        }
         if (pc.minus) {
           const unsigned char* q = src + len - 1 - p0;            // symbol j of the word: complement of q[-j]
           for (uint32_t j = 0; j < m; ++j) { const uint32_t c = kPack.two_rc[*(q - j)]; bad |= c; v = (v << 2) | (c & 3u); }
@@ -776,7 +877,10 @@ extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32
             const unsigned char sym = pc.minus ? src[len - 1 - p] : src[p];
             c = pc.minus ? kPack.four_rc[sym] : kPack.four_fwd[sym];
             if (c == 255u) {
-              if (!bad_symbol) bad_symbol = pc.minus ? kComp.t[sym] : sym;
+              if (!bad_symbol) {                                 // as the reference would see it: upper case, complemented
+                const unsigned char u = (unsigned char)(sym - (((unsigned)(sym - 'a') < 26u) << 5));
+                bad_symbol = pc.minus ? kComp.t[u] : u;
+              }
               c = a_code;
             }
           }

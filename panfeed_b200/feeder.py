@@ -124,7 +124,7 @@ class NativeFeeder:
             got = self._feature_names[key] = self.feature(genome, feature)[:2]
         return got
 
-    def cut(self, genomes, cells_blob, up, down, down_start_codon, prepack=False):
+    def cut(self, genomes, cells_blob, up, down, down_start_codon, prepack=False, n_threads=0):
         """genomes: uint32 array (genome index per cell); cells_blob: the cells joined with
         newlines (bytes).  -> dict of copies of the pf_cut_result arrays.  prepack: the sequences
         go from the contigs straight into the 2-bit / 4-bit planes (pf_feeder_cut_packed, host
@@ -135,7 +135,7 @@ class NativeFeeder:
         planes = capi.CutPlanes()
         if prepack:
             rc = self.lib.pf_feeder_cut_packed(self.h, len(genomes), genomes.ctypes.data, cells_blob, len(cells_blob),
-                                               int(up), int(down), int(bool(down_start_codon)), 0,
+                                               int(up), int(down), int(bool(down_start_codon)), int(n_threads),
                                                C.byref(res), C.byref(planes))
             if rc == -4 and planes.bad_symbol:
                 raise ValueError(f"unsupported sequence symbol {chr(planes.bad_symbol)!r}: only "

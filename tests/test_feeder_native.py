@@ -192,7 +192,7 @@ def test_cut_packed_equals_cut_then_pack():
         g = native.add_genome_text(f"s{gi}", "\n".join(rows) + "\n##FASTA\n>c\n" +
                                    "\n".join(text[i:i + 70] for i in range(0, len(text), 70)) + "\n")
         for j in range(0, len(ids), 3):
-            cells.append(";".join(ids[j:j + 3]))
+            cells.append(";".join(ids[j:j + 3]) + (";nope_%d" % j if j % 30 == 0 else ""))     # misses in every thread's range
             genomes.append(g)
     blob = "\n".join(cells).encode()
     genomes = np.array(genomes, np.uint32)
@@ -200,6 +200,11 @@ def test_cut_packed_equals_cut_then_pack():
         a = native.cut(genomes, blob, up, down, dsc, prepack=False)
         want = capi.pack_blob(a["ascii"], a["seq_off"])
         b = native.cut(genomes, blob, up, down, dsc, prepack=True)
+        for nt in (1, 3, 7):                                  # the look-ups and the packing on that many threads
+            c = native.cut(genomes, blob, up, down, dsc, prepack=True, n_threads=nt)
+            assert all((b[f] == c[f]).all() for f in ("seq_off", "cell", "feature", "start", "end", "offset",
+                                                      "strand", "packed", "base_off", "is_amb", "amb_off"))
+            assert b["missing"] == c["missing"] and len(b["missing"]) > 3
         assert b["ascii"] is None and b["n_seqs"] == a["n_seqs"] > 1000
         for f in ("seq_off", "cell", "feature", "start", "end", "offset", "strand"):
             assert (a[f] == b[f]).all(), f
