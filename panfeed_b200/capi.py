@@ -289,9 +289,23 @@ def pack_blob(blob, seq_off, n_threads=0):
     return packed, base_off, is_amb.astype(bool), amb_plane, amb_off
 
 
-def format_patterns(words, n_samples, ids, present=None, n_threads=0):
+_scratch_bufs = {}
+
+
+def _scratch(name, nbytes):
+    """A grow-only uint8 buffer per formatter: the text of one batch is hundreds of MB, and fresh
+    memory for every batch costs more (first touch) than formatting into it."""
+    buf = _scratch_bufs.get(name)
+    if buf is None or buf.size < nbytes:
+        buf = _scratch_bufs[name] = np.empty(int(nbytes) + int(nbytes) // 4 + 4096, np.uint8)
+    return buf
+
+
+def format_patterns(words, n_samples, ids, present=None, n_threads=0, raw=False):
     """hashes_to_patterns text (bytes) of the patterns `words` ([n, >= W] uint32) with their
-    24-character ids; `present` ([n, >= W] uint32) marks the samples whose cell is not NaN."""
+    24-character ids; `present` ([n, >= W] uint32) marks the samples whose cell is not NaN.
+    raw=True (all three formatters): a uint8 view of a buffer that the next call of the same
+    formatter reuses, for callers that write the text out at once."""
     lib = load()
     words = np.ascontiguousarray(words, dtype=np.uint32)
     n = len(words)
@@ -309,11 +323,11 @@ def format_patterns(words, n_samples, ids, present=None, n_threads=0):
     rc = lib.pf_format_patterns(*args, None, 0, C.byref(need), int(n_threads))
     if rc != 0:
         raise PfError(rc, "pf_format_patterns (sizing) failed")
-    out = np.empty(int(need.value), np.uint8)
+    out = _scratch("patterns", need.value)
     rc = lib.pf_format_patterns(*args, out.ctypes.data_as(C.c_char_p), out.size, C.byref(need), int(n_threads))
     if rc != 0:
         raise PfError(rc, "pf_format_patterns failed")
-    return out.tobytes()
+    return out[:int(need.value)] if raw else out[:int(need.value)].tobytes()
 
 
 def tsv_filter(path, column, keys, skip_header=True, n_threads=0):
@@ -355,7 +369,7 @@ def gzip_members(data, level=9, member_bytes=0, n_threads=0):
     return out[:int(need.value)].tobytes()
 
 
-def format_kmer_rows(r, k, tags, kmer_ids, cluster_ids, n_threads=0):
+def format_kmer_rows(r, k, tags, kmer_ids, cluster_ids, n_threads=0, raw=False):
     """kmers_to_hashes text of the batch result `r` (a dict as returned by Context.collect(), or
     any dict with row_*, wide_row_* and cluster_pattern), formatted by the library's host threads
     (pf_format_kmer_rows).  tags[c] = first column of cluster c (bytes); kmer_ids / cluster_ids:
@@ -396,11 +410,11 @@ def format_kmer_rows(r, k, tags, kmer_ids, cluster_ids, n_threads=0):
     rc = lib.pf_format_kmer_rows(*args, None, 0, C.byref(need), cl_off.ctypes.data, int(n_threads))
     if rc != 0:
         raise PfError(rc, "pf_format_kmer_rows (sizing) failed")
-    out = np.empty(int(need.value), np.uint8)
+    out = _scratch("kmer_rows", need.value)
     rc = lib.pf_format_kmer_rows(*args, out.ctypes.data, out.size, C.byref(need), cl_off.ctypes.data, int(n_threads))
     if rc != 0:
         raise PfError(rc, "pf_format_kmer_rows failed")
-    return out.tobytes(), cl_off
+    return (out[:int(need.value)] if raw else out[:int(need.value)].tobytes()), cl_off
 
 
 def format_positions(r, k, canonical, leads, seq_strand, n_threads=0):
@@ -448,7 +462,7 @@ def format_positions(r, k, canonical, leads, seq_strand, n_threads=0):
     return out.tobytes()
 
 
-def format_positions_compact(hb, strand_bits, k, canonical, leads, n_threads=0):
+def format_positions_compact(hb, strand_bits, k, canonical, leads, n_threads=0, raw=False):
     """kmers.tsv text (bytes) of the PF_SEQ_TARGET sequences of the HostBatch `hb` from the compact
     positional form (Context(emit_positions=2)): `strand_bits` = r["pos_strand_bits"] of the
     batch's collect().  leads[i] as in format_positions (may be b"" for non-target sequences)."""
@@ -471,12 +485,12 @@ def format_positions_compact(hb, strand_bits, k, canonical, leads, n_threads=0):
     rc = lib.pf_format_positions_compact(*args, None, 0, C.byref(need), int(n_threads))
     if rc != 0:
         raise PfError(rc, "pf_format_positions_compact (sizing) failed")
-    out = np.empty(int(need.value), np.uint8)
+    out = _scratch("positions", need.value)
     rc = lib.pf_format_positions_compact(*args, out.ctypes.data_as(C.c_char_p), out.size, C.byref(need),
                                          int(n_threads))
     if rc != 0:
         raise PfError(rc, "pf_format_positions_compact failed")
-    return out.tobytes()
+    return out[:int(need.value)] if raw else out[:int(need.value)].tobytes()
 
 
 def _np(ptr, n, dtype, copy=True):

@@ -473,6 +473,18 @@ extern "C" int pf_format_patterns(const uint32_t* pattern_words, uint64_t n, uin
 // their 4-bit codes.  (The reference's order inside a cluster is that of a Python dict of
 // k-mers filled in window order; consumers key on the k-mer, not on the row order.)
 // ---------------------------------------------------------------------------
+namespace {
+struct KeyedRow { uint64_t kmer; uint32_t row; };
+struct QuadLut {                                   // the four bases of a byte of 2-bit codes, first base in the top bits
+  char t[256][4];
+  QuadLut() {
+    for (int b = 0; b < 256; ++b)
+      for (int j = 0; j < 4; ++j) t[b][j] = "ACGT"[(b >> (6 - 2 * j)) & 3];
+  }
+};
+const QuadLut kQuad;
+}  // namespace
+
 extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const char* tag_blob,
                                    const uint64_t* tag_off, const char* kmer_ids, uint64_t n_kmer_ids,
                                    const char* cluster_ids, uint64_t n_cluster_ids, char* out, uint64_t out_cap,
@@ -485,6 +497,7 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
   if (nn && (!r->row_cluster || !r->row_kmer || !r->row_pattern || !kmer_ids)) return PF_ERR_INVALID;
   if (nw && (!r->wide_row_cluster || !r->wide_row_kmer || !r->wide_row_pattern || !kmer_ids)) return PF_ERR_INVALID;
   if (nc == 0) return (nn || nw) ? PF_ERR_INVALID : PF_OK;
+  if (nn && k > 32) return PF_ERR_INVALID;             // one-word k-mers hold at most 32 bases
   // rows of every cluster: counting sort of the row indices (narrow rows first, then wide)
   std::vector<uint32_t> first(nc + 1, 0), first_w(nc + 1, 0);
   for (uint64_t i = 0; i < nn; ++i) {
@@ -523,13 +536,18 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
   nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nt, (nn + nw + nc + 16383) / 16384));
   std::atomic<uint32_t> next{0};
   auto work = [&]() {
+    std::vector<KeyedRow> keyed;
     for (;;) {
       const uint32_t c = next.fetch_add(1);
       if (c >= nc) return;
-      uint32_t* o = order.data() + first[c];
+      // (k-mer, row) pairs side by side: the sort compares values it already holds instead of
+      // chasing row indices into the result arrays
+      const uint32_t* o = order.data() + first[c];
       const uint32_t n = first[c + 1] - first[c];
-      std::sort(o, o + n, [&](uint32_t a, uint32_t b) {
-        return r->row_kmer[a] != r->row_kmer[b] ? r->row_kmer[a] < r->row_kmer[b] : a < b;
+      keyed.resize(n);
+      for (uint32_t j = 0; j < n; ++j) keyed[j] = KeyedRow{r->row_kmer[o[j]], o[j]};
+      std::sort(keyed.begin(), keyed.end(), [](const KeyedRow& a, const KeyedRow& b) {
+        return a.kmer != b.kmer ? a.kmer < b.kmer : a.row < b.row;
       });
       uint32_t* ow = order_w.data() + first_w[c];
       const uint32_t n_w = first_w[c + 1] - first_w[c];
@@ -548,11 +566,13 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
       memcpy(p, cluster_ids + (size_t)r->cluster_pattern[c] * 24, 24); p += 24;
       *p++ = '\n';
       for (uint32_t j = 0; j < n; ++j) {
-        const uint32_t i = o[j];
+        const uint32_t i = keyed[j].row;
         memcpy(p, tag, tl); p += tl;
         *p++ = '\t';
-        const uint64_t v = r->row_kmer[i];
-        for (uint32_t s = 0; s < k; ++s) p[s] = kAcgt[(v >> (2 * (k - 1 - s))) & 3u];
+        // four bases per table look-up, first base in the top bits; the up to three letters written
+        // past the k-th are overwritten by the rest of the row (a tab and a 24-character id follow)
+        uint64_t u = keyed[j].kmer << (64 - 2 * k);
+        for (uint32_t s4 = 0; s4 < k; s4 += 4, u <<= 8) memcpy(p + s4, kQuad.t[u >> 56], 4);
         p += k;
         *p++ = '\t';
         memcpy(p, kmer_ids + (size_t)r->row_pattern[i] * 24, 24); p += 24;

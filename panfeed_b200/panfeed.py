@@ -169,17 +169,35 @@ class PatternStore:
                 present = None
                 if consider_missing and not ns:
                     present = self.cluster_planes()[bits[:, W].astype(np.int64)]
-                hash_pat.write(capi.format_patterns(bits, S, ids[c0:c0 + chunk][sel], present).decode())
+                write_text(hash_pat, capi.format_patterns(bits, S, ids[c0:c0 + chunk][sel], present))
                 written += int(sel.sum())
         self.n_patterns = out["cluster"]["n_global"] + out["kmer"]["n_global"]
         return {"written_here": written, "cluster_patterns_global": out["cluster"]["n_global"],
                 "kmer_patterns_global": out["kmer"]["n_global"]}
 
 
+def write_text(handle, data):
+    """`data` (bytes or a uint8 array of UTF-8 text) to a handle opened in text mode, without a
+    Python str in between: a batch's rows are hundreds of MB, and decode + join + the text layer's
+    re-encode cost more than formatting them.  Plain files take the bytes through their binary
+    buffer, GzipTextWriter takes bytes as they are, anything else (StringIO) gets a str."""
+    if len(data) == 0:
+        return
+    raw = getattr(handle, "buffer", None)
+    if raw is not None:
+        handle.flush()
+        raw.write(data)
+    elif hasattr(handle, "parts"):                  # input.GzipTextWriter
+        handle.write(bytes(data))
+    else:
+        handle.write(bytes(data).decode())
+
+
 def _run_batch(store, ctx, hb, meta, idxs, S, k, canonical, consider_missing):
     """One GPU batch (`hb`: the capi.HostBatch; meta(i) -> (strain, feature id, contig) of its
-    sequence i; idxs: the names of its clusters) -> (kmers.tsv text, hashes_to_patterns text,
-    per-cluster kmers_to_hashes texts)."""
+    sequence i; idxs: the names of its clusters) -> (kmers.tsv text, list of hashes_to_patterns
+    texts, kmers_to_hashes text) as bytes / uint8 arrays; the arrays are the formatters' reused
+    buffers, to be written out before the next batch."""
     ctx.submit(hb)
     r = ctx.collect()
 
@@ -193,7 +211,7 @@ def _run_batch(store, ctx, hb, meta, idxs, S, k, canonical, consider_missing):
         store.cluster_ids.append(new_ids)
         store.cluster_bits.append(new_cp.copy())
         if not store.sharded:
-            pat_text.append(capi.format_patterns(new_cp, S, new_ids).decode())
+            pat_text.append(capi.format_patterns(new_cp, S, new_ids))
             store.n_patterns += len(new_cp)
     new_kp = r["new_kmer_patterns"]
     if len(new_kp):
@@ -204,30 +222,29 @@ def _run_batch(store, ctx, hb, meta, idxs, S, k, canonical, consider_missing):
             present = None
             if consider_missing:      # NaN cells = samples whose cluster is absent (the key's last word
                 present = store.cluster_planes()[new_kp[:, W].astype(np.int64)]   # names that cluster pattern)
-            pat_text.append(capi.format_patterns(new_kp, S, new_ids, present).decode())
+            pat_text.append(capi.format_patterns(new_kp, S, new_ids, present))
             store.n_patterns += len(new_kp)
 
     # ---- kmers_to_hashes rows, cluster by cluster: formatted by the library's host threads
     #      (pf_format_kmer_rows; inside a cluster the plain k-mers in alphabetical order, then the
     #      rows holding N/IUPAC symbols - the reference's order is arbitrary too) --------------
-    text, off = capi.format_kmer_rows(r, k, [str(idx).encode() for idx in idxs], store.kmer_ids.view(),
-                                      store.cluster_ids.view())
-    hash_texts = [text[int(off[c]):int(off[c + 1])].decode() for c in range(len(idxs))]
+    hash_text, _ = capi.format_kmer_rows(r, k, [str(idx).encode() for idx in idxs], store.kmer_ids.view(),
+                                         store.cluster_ids.view(), raw=True)
 
     # ---- kmers.tsv rows from the positional records: formatted by the library's host
     #      threads (pf_format_positions_compact: the device only returns the used_strand bit
     #      of every window, the rest of a row follows from the batch itself), 1e8 rows are too
     #      many for Python.  Only the target sequences need their leading fields (and with them
     #      their lazily built metadata). ----
-    pos_text = ""
+    pos_text = b""
     if r["n_pos"]:
         leads = [b""] * len(hb.seqs)
         cl, strand = hb.seqs["cluster"], hb.seqs["strand"]
         for i in np.nonzero(hb.seqs["flags"] & capi.PF_SEQ_TARGET)[0].tolist():
             m = meta(i)
             leads[i] = f"{idxs[cl[i]]}\t{m[0]}\t{m[1]}\t{m[2]}\t{strand[i]}\t".encode()
-        pos_text = capi.format_positions_compact(hb, r["pos_strand_bits"], k, canonical, leads).decode()
-    return pos_text, "".join(pat_text), hash_texts
+        pos_text = capi.format_positions_compact(hb, r["pos_strand_bits"], k, canonical, leads, raw=True)
+    return pos_text, pat_text, hash_text
 
 def pattern_hasher(cluster_dict_iter, kmer_stroi, hash_pat, kmer_hash, genepres, patfilt, maf,
                    output, patterns=None, consider_missing_cluster=False, compress=False,
@@ -258,27 +275,28 @@ def pattern_hasher(cluster_dict_iter, kmer_stroi, hash_pat, kmer_hash, genepres,
             return
         ctx = patterns.context(first.k, S, first.canonical, bool(consider_missing_cluster),
                                patfilt == False, maf, device, sort_bits)  # noqa: E712
-        pos_text, pat_text, hash_texts = _run_batch(patterns, ctx, hb, meta, idxs, S, first.k,
+        pos_text, pat_texts, hash_text = _run_batch(patterns, ctx, hb, meta, idxs, S, first.k,
                                                     first.canonical, bool(consider_missing_cluster))
         if multiple_files:
             path = os.path.join(output, idxs[0])
             if not os.path.exists(path):
                 os.mkdir(path)
             ks = create_kmer_stroi(path, compress)
-            ks.write(pos_text)
+            write_text(ks, pos_text)
             ks.close()
             hp, kh = create_hash_files(path, compress)
             write_headers(hp, kh, genepres)
-            hp.write(pat_text)
-            kh.write("".join(hash_texts))
+            for t in pat_texts:
+                write_text(hp, t)
+            write_text(kh, hash_text)
             hp.close()
             kh.close()
         else:
             if kmer_stroi is not None:
-                kmer_stroi.write(pos_text)
-            if pat_text:
-                hash_pat.write(pat_text)
-            kmer_hash.write("".join(hash_texts))
+                write_text(kmer_stroi, pos_text)
+            for t in pat_texts:
+                write_text(hash_pat, t)
+            write_text(kmer_hash, hash_text)
         if ready is None:
             pending, pending_records = [], 0
 
