@@ -455,10 +455,21 @@ extern "C" int pf_format_patterns(const uint32_t* pattern_words, uint64_t n, uin
       p += 24;
       const uint32_t* bits = pattern_words + (size_t)i * stride_words;
       const uint32_t* pw = present_words ? present_words + (size_t)i * present_stride : nullptr;
-      for (uint32_t s = 0; s < n_samples; ++s) {
-        *p++ = '\t';
-        if (pw && !((pw[s >> 5] >> (s & 31u)) & 1u)) continue;          // NaN: empty field
-        *p++ = ((bits[s >> 5] >> (s & 31u)) & 1u) ? '1' : '0';
+      if (pw) {
+        // NaN (cluster absent): an empty field.  Branch-free: the digit is always written and
+        // only kept (p moves past it) where the sample is present; the byte after a dropped
+        // digit is rewritten by the next tab or the closing newline of this same row
+        for (uint32_t s = 0; s < n_samples; ++s) {
+          const uint32_t present = (pw[s >> 5] >> (s & 31u)) & 1u;
+          p[0] = '\t';
+          p[1] = (char)('0' + ((bits[s >> 5] >> (s & 31u)) & 1u));
+          p += 1 + present;
+        }
+      } else {
+        for (uint32_t s = 0; s < n_samples; ++s) {
+          *p++ = '\t';
+          *p++ = (char)('0' + ((bits[s >> 5] >> (s & 31u)) & 1u));
+        }
       }
       *p++ = '\n';
     }
