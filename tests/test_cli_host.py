@@ -110,3 +110,18 @@ def test_cli_host_logic_native_feeder_many_batches(tmp_path, monkeypatch):
         for name in helpers.FILES:
             assert helpers.sorted_lines(_read(os.path.join(out, name))) == \
                 helpers.sorted_lines(helpers.golden(mode, name)), (mode, name)
+
+
+@pytest.mark.parametrize("feeder", [[], ["--python-feeder"]])
+def test_cli_stop_on_missing_raises(feeder, tmp_path, monkeypatch):
+    """--stop-on-missing: a feature id of the table that no GFF holds ends the run with the
+    reference's KeyError (input.py:396-400) - also when the cut runs on the feeder's thread."""
+    genes = tmp_path / "genes.txt"
+    genes.write_text("group_acc1\n")                          # names s07_refound_1, which no GFF has
+    with pytest.raises(KeyError, match="Could not find gene s07_refound_1 from group_acc1 in s07"):
+        _run_cli(["--gff", "fixture/gffs/", "--presence-absence", "fixture/gene_presence_absence.csv",
+                  "--genes", str(genes), "--stop-on-missing"] + feeder, str(tmp_path / "out"), monkeypatch)
+    # without the flag the gene is skipped with a warning and the run completes
+    _run_cli(["--gff", "fixture/gffs/", "--presence-absence", "fixture/gene_presence_absence.csv",
+              "--genes", str(genes)] + feeder, str(tmp_path / "out2"), monkeypatch)
+    assert os.path.getsize(os.path.join(str(tmp_path / "out2"), "kmers_to_hashes.tsv")) > 100
