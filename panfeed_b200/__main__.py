@@ -101,9 +101,12 @@ def main(argv=None):
         import torch
         import torch.distributed as tdist
         args.device = int(os.environ.get("LOCAL_RANK", "0"))
-        torch.cuda.set_device(args.device)
         os.environ.setdefault("PF_HOST_THREADS", str(max(2, (os.cpu_count() or 16) // world)))
-        tdist.init_process_group("nccl", device_id=torch.device("cuda", args.device))
+        if os.environ.get("PF_DIST_BACKEND", "nccl") == "nccl":
+            torch.cuda.set_device(args.device)
+            tdist.init_process_group("nccl", device_id=torch.device("cuda", args.device))
+        else:       # the CPU tests of the sharded wiring rendezvous over gloo (the GPU context is a stand-in there)
+            tdist.init_process_group(os.environ["PF_DIST_BACKEND"])
         if os.path.exists(args.output):          # every rank sees the same answer: no rank is left waiting
             logger.error(f"Output directory {args.output} exists! Please remove it and restart")
             tdist.barrier()

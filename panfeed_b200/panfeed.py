@@ -152,8 +152,10 @@ class PatternStore:
         import torch
         from . import dist as pfdist
         ctx = self.context(k, S, canonical, consider_missing, cluster_equal_filter, maf, device)
-        dev = torch.device("cuda", device)
-        exchange = pfdist.PatternExchange(ctx, dev)
+        # (a context may bring its own exchange primitives and device: the CPU tests' stand-in does)
+        dev = getattr(ctx, "exchange_device", None) or torch.device("cuda", device)
+        backend = ctx.exchange_backend() if hasattr(ctx, "exchange_backend") else None
+        exchange = pfdist.PatternExchange(ctx, dev, backend=backend)
         out = exchange.run(want_writer=True)
         exchange.close()
         W = (S + 31) // 32

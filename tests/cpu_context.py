@@ -198,3 +198,70 @@ class OracleContext:
 
     def close(self):
         pass
+
+    # ---- sharded runs: the pattern exchange over gloo with host primitives ----
+    @property
+    def exchange_device(self):
+        import torch
+        return torch.device("cpu")
+
+    def exchange_backend(self):
+        return HostExchangeBackend(self)
+
+
+class HostExchangeBackend:
+    """pf_exchange_pack / dedup / unpack on host arrays (the all-to-all transport), over the
+    pattern pools of an OracleContext: lets `PatternStore.finish_sharded` and dist.PatternExchange
+    run their real choreography between CPU processes."""
+
+    def __init__(self, ctx):
+        self.ctx, self.consider_missing = ctx, ctx.consider_missing
+        self.perm, self.owner, self.uniq = {}, {}, {}
+
+    def _pool(self, ns):
+        rows = self.ctx._cp_rows if ns == 1 else self.ctx._kp_rows
+        w = self.ctx.W if ns == 1 else self.ctx.Wk
+        return np.stack(rows).astype(np.uint32) if rows else np.zeros((0, w), np.uint32)
+
+    def key_words(self, ns):
+        return self.ctx.W if ns == 1 else self.ctx.Wk
+
+    def n_local(self, ns):
+        return len(self.ctx._cp_rows if ns == 1 else self.ctx._kp_rows)
+
+    def pack(self, ns, world, mask_remap, send):
+        import torch
+        import zlib
+        keys = self._pool(ns)
+        if mask_remap is not None:
+            keys[:, -1] = mask_remap.numpy().astype(np.uint32)[keys[:, -1]]
+        owner = np.array([zlib.crc32(k.tobytes()) % world for k in keys], np.int64)
+        order = np.argsort(owner, kind="stable")
+        perm = np.empty(len(keys), np.int64)
+        perm[order] = np.arange(len(keys))
+        self.perm[ns], self.owner[ns] = perm, owner
+        send.copy_(torch.from_numpy(keys[order].astype(np.int32).reshape(send.shape)))
+        return [int((owner == r).sum()) for r in range(world)]
+
+    def dedup(self, ns, recv, unique_index, n_unique, keep_unique=False):
+        import torch
+        keys = recv.numpy().astype(np.uint32)
+        seen, idx = {}, []
+        for k in keys:
+            first = k.tobytes() not in seen
+            u = seen.setdefault(k.tobytes(), len(seen))
+            idx.append(u - (1 << 31) if first else u)        # bit 31: the first copy names the writer
+        unique_index.copy_(torch.tensor(idx, dtype=torch.int32))
+        self.uniq[ns] = np.array([np.frombuffer(b, np.uint32) for b in seen], np.uint32).reshape(len(seen), keys.shape[1])
+        n_unique.fill_(len(seen))
+
+    def unique_keys(self, ns):
+        return self.uniq[ns]
+
+    def unpack(self, ns, returned, owner_base, l2g, writer):
+        import torch
+        v = returned[torch.from_numpy(self.perm[ns])].numpy().astype(np.int64) & 0xffffffff
+        base = owner_base.numpy().astype(np.int64)[self.owner[ns]]
+        l2g.copy_(torch.from_numpy(((v & 0x7fffffff) + base).astype(np.int32)))
+        if writer is not None:
+            writer.copy_(torch.from_numpy((v >> 31).astype(np.uint8)))
