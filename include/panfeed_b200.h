@@ -486,6 +486,30 @@ int  pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32_t* genome
                           uint64_t cells_len, int32_t up, int32_t down, int32_t down_start_codon,
                           uint32_t n_threads, pf_cut_result* out, pf_cut_planes* planes);
 
+/* ---- the pangenome table (host threads): panaroo's gene_presence_absence.csv ----
+ * What the reference reads with pd.read_csv(path, sep=",", index_col=0, low_memory=False)
+ * .drop(columns=["Non-unique Gene name", "Annotation"]) (input.py:198-201) and walks with
+ * iterrows() (input.py:352).  The file is mapped, a cell is an (offset, length) into it; RFC-4180
+ * quoting, blank lines skipped, short rows padded with missing cells; a cell that is empty or
+ * one of na_values (the caller passes pandas' STR_NA_VALUES) is absent.  Escaped quotes inside a
+ * row label or a kept cell are refused (PF_ERR_INVALID + pf_table_last_error). */
+typedef struct pf_table pf_table;
+int  pf_table_create(pf_table** out);
+void pf_table_destroy(pf_table* t);
+const char* pf_table_last_error(const pf_table* t);
+int  pf_table_load(pf_table* t, const char* path, const char* const* drop_columns, uint32_t n_drop,
+                   const char* const* na_values, uint32_t n_na, uint32_t n_threads);
+int  pf_table_shape(const pf_table* t, uint64_t* n_rows, uint32_t* n_cols);
+/* names back to back with their offsets [n + 1]: the kept columns (row_labels 0) or the row labels */
+int  pf_table_names(const pf_table* t, int row_labels, const char** blob, const uint64_t** off);
+int  pf_table_row_counts(const pf_table* t, uint32_t* n_present /* [n_rows] */);
+/* The cells of rows[0 .. n_sel) with the columns in the order col_order (col_order[j] = table
+ * column at position j, NULL = table order): present[i * n_cols + j] (may be NULL) and the
+ * present cells row by row joined with '\n' - the cells_blob of pf_feeder_cut.  blob and present
+ * NULL: sizing only (blob_len, n_cells). */
+int  pf_table_cells(const pf_table* t, const uint64_t* rows, uint64_t n_sel, const uint32_t* col_order,
+                    uint8_t* present, char* blob, uint64_t blob_cap, uint64_t* blob_len, uint64_t* n_cells);
+
 /* ---- row filter over the TSV outputs (host threads): the scans of the post-GWAS joins ----
  * panfeed-get-clusters / panfeed-get-kmers (get_clusters.py:90-101, get_kmers.py:108-145) keep the
  * rows of kmers_to_hashes.tsv whose hashed_pattern, and of kmers.tsv whose cluster, is in a set

@@ -17,6 +17,8 @@ import os
 import sys
 from functools import partial
 
+import numpy as np
+
 from . import __version__
 from .input import (KMERS_TSV_HEADER, clean_up_fasta, create_part_files, iter_gene_clusters,
                     merge_part_files, prep_data_n_fasta, set_input_output, what_are_my_inputfiles)
@@ -119,7 +121,8 @@ def main(argv=None):
     logger.info("Preparing output files")
     (stroi, genes, kmer_stroi, hash_pat, kmer_hash, genepres) = set_input_output(
         args.targets, args.genes, args.presence_absence, args.output,
-        not args.multiple_files, args.compress, make_outputs=not sharded)
+        not args.multiple_files, args.compress, make_outputs=not sharded,
+        native_table=not args.python_feeder)
     all_columns = genepres
     if sharded:
         if rank == 0:
@@ -129,11 +132,12 @@ def main(argv=None):
             kmer_stroi, hash_pat, kmer_hash = create_part_files(args.output, rank, args.compress)
         # whole clusters to ranks, greedy by the number of genes (cells) of the rows that will be cut
         from .dist import shard_clusters
-        weights = genepres.notna().sum(axis=1).to_numpy()
+        native_table = hasattr(genepres, "n_present")
+        weights = genepres.n_present() if native_table else genepres.notna().sum(axis=1).to_numpy()
         if genes is not None:
-            weights = weights * genepres.index.isin(list(genes))
+            weights = weights * np.isin(np.array(list(genepres.index), dtype=object), list(genes))
         mine = shard_clusters(weights, world)[rank]
-        genepres = genepres.iloc[mine]
+        genepres = genepres.take(mine) if native_table else genepres.iloc[mine]
         logger.info(f"rank {rank}/{world}: {len(mine)} of {len(weights)} clusters")
     logger.info("Preparing inputs")
     if not args.multiple_files and not sharded:

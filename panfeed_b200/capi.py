@@ -143,6 +143,8 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_feeder_create", "pf_feeder_destroy", "pf_feeder_last_error", "pf_feeder_add_genome", "pf_feeder_add_genomes",
            "pf_feeder_add_genome_text", "pf_feeder_genome_info", "pf_feeder_feature", "pf_feeder_contig", "pf_feeder_cut",
            "pf_feeder_cut_packed",
+           "pf_table_create", "pf_table_destroy", "pf_table_last_error", "pf_table_load", "pf_table_shape",
+           "pf_table_names", "pf_table_row_counts", "pf_table_cells",
            "pf_tsv_filter", "pf_free",
            "pf_synth_plan", "pf_synth_fill", "pf_exchange_pack",
            "pf_exchange_dedup", "pf_exchange_unique_count", "pf_exchange_unique_export",
@@ -199,6 +201,16 @@ def load():
                                   C.POINTER(CutResult)]
     lib.pf_feeder_cut_packed.argtypes = [vp, u32, vp, C.c_char_p, u64, C.c_int32, C.c_int32, C.c_int32, u32,
                                          C.POINTER(CutResult), C.POINTER(CutPlanes)]
+    lib.pf_table_create.argtypes = [C.POINTER(vp)]
+    lib.pf_table_destroy.argtypes = [vp]
+    lib.pf_table_destroy.restype = None
+    lib.pf_table_last_error.argtypes = [vp]
+    lib.pf_table_last_error.restype = C.c_char_p
+    lib.pf_table_load.argtypes = [vp, C.c_char_p, C.POINTER(C.c_char_p), u32, C.POINTER(C.c_char_p), u32, u32]
+    lib.pf_table_shape.argtypes = [vp, C.POINTER(u64), C.POINTER(u32)]
+    lib.pf_table_names.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
+    lib.pf_table_row_counts.argtypes = [vp, vp]
+    lib.pf_table_cells.argtypes = [vp, vp, u64, vp, vp, vp, u64, C.POINTER(u64), C.POINTER(u64)]
     lib.pf_tsv_filter.argtypes = [C.c_char_p, u32, C.c_char_p, vp, u64, C.c_int, C.POINTER(vp), C.POINTER(u64),
                                   C.POINTER(u64), u32]
     lib.pf_free.argtypes = [vp]

@@ -907,3 +907,234 @@ extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32
   }
   return PF_OK;
 }
+
+// ---------------------------------------------------------------------------
+// The pangenome table (panaroo's gene_presence_absence.csv): what the reference reads with
+// pd.read_csv(path, sep=",", index_col=0, low_memory=False).drop(columns=[...])
+// (input.py:198-201) and walks with iterrows().  pandas spends ~0.5 us per cell on a wide table
+// and holds every cell as a Python object (BASELINE config #5 is 4e8 cells); here the file is
+// mapped, lines and fields are located on host threads and a cell is an (offset, length) into
+// the mapping.  Semantics kept: RFC-4180 quoting (delimiters and line ends inside quotes),
+// blank lines skipped, short rows padded with missing cells, pandas' strings for a missing
+// value (handed over by the caller) and the empty cell mean "absent".
+// ---------------------------------------------------------------------------
+struct pf_table {
+  std::string err;
+  FileText text;
+  std::vector<std::string> columns, rows;            // kept column names, row labels
+  std::string col_blob, row_blob;                    // the same, back to back
+  std::vector<uint64_t> col_off, row_off;
+  std::vector<uint64_t> cell_off;                    // [n_rows * n_cols] into text
+  std::vector<uint32_t> cell_len;                    // 0: absent
+};
+
+namespace {
+// end of the record that starts at p (the '\n' that ends it, or e); quotes may hold line ends
+const char* csv_record_end(const char* p, const char* e) {
+  const char* nl = (const char*)memchr(p, '\n', e - p);
+  if (!nl) nl = e;
+  if (!memchr(p, '"', nl - p)) return nl;
+  bool in_q = false;
+  for (const char* q = p; q < e; ++q) {
+    if (*q == '"') in_q = !in_q;                     // ("" inside quotes toggles twice)
+    else if (*q == '\n' && !in_q) return q;
+  }
+  return e;
+}
+
+// the fields of one record: fn(index, begin, end, plain) - [begin, end) is the field's text with
+// the enclosing quotes removed; plain = false if it still holds "" escapes or text after the
+// closing quote (the caller decides whether it can live with that)
+template <typename F>
+uint32_t csv_fields(const char* p, const char* e, F&& fn) {
+  uint32_t n = 0;
+  for (;;) {
+    if (p < e && *p == '"') {
+      const char* q = p + 1;
+      bool plain = true;
+      const char* close = nullptr;
+      while (q < e) {
+        const char* c = (const char*)memchr(q, '"', e - q);
+        if (!c) break;
+        if (c + 1 < e && c[1] == '"') { plain = false; q = c + 2; continue; }
+        close = c;
+        break;
+      }
+      const char* fe = close ? close : e;
+      const char* next = close ? close + 1 : e;
+      const char* comma = next < e ? (const char*)memchr(next, ',', e - next) : nullptr;
+      if (close && (comma ? comma : e) != next) plain = false;            // text after the closing quote
+      fn(n++, p + 1, fe, plain);
+      if (!comma) return n;
+      p = comma + 1;
+    } else {
+      const char* comma = (const char*)memchr(p, ',', e - p);
+      fn(n++, p, comma ? comma : e, true);
+      if (!comma) return n;
+      p = comma + 1;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int pf_table_create(pf_table** out) {
+  if (!out) return PF_ERR_INVALID;
+  *out = new pf_table();
+  return PF_OK;
+}
+extern "C" void pf_table_destroy(pf_table* t) { delete t; }
+extern "C" const char* pf_table_last_error(const pf_table* t) { return t ? t->err.c_str() : "null table"; }
+
+extern "C" int pf_table_load(pf_table* t, const char* path, const char* const* drop_columns, uint32_t n_drop,
+                             const char* const* na_values, uint32_t n_na, uint32_t n_threads) {
+  if (!t || !path || (n_drop && !drop_columns) || (n_na && !na_values)) return PF_ERR_INVALID;
+  if (!read_text(path, &t->text)) { t->err = std::string("cannot read ") + path; return PF_ERR_INVALID; }
+  const char* p = t->text.data();
+  const char* e = p + t->text.size();
+  if (p == e) { t->err = "empty table"; return PF_ERR_INVALID; }
+  // header: the first field names the index, the dropped names must exist (pandas raises KeyError)
+  const char* he = csv_record_end(p, e);
+  std::vector<std::string> header;
+  csv_fields(p, he, [&](uint32_t, const char* a, const char* b, bool) { header.emplace_back(a, b); });
+  if (!header.empty() && !header.back().empty() && header.back().back() == '\r') header.back().pop_back();
+  const uint32_t n_fields = (uint32_t)header.size();
+  std::vector<int32_t> kept_of(n_fields, -1);          // field -> kept column, -1 dropped / index
+  std::vector<bool> dropped(n_fields, false);
+  for (uint32_t d = 0; d < n_drop; ++d) {
+    bool found = false;
+    for (uint32_t c = 1; c < n_fields; ++c)
+      if (header[c] == drop_columns[d]) { dropped[c] = true; found = true; }
+    if (!found) { t->err = std::string("column not found: ") + drop_columns[d]; return PF_ERR_INVALID; }
+  }
+  t->columns.clear();
+  for (uint32_t c = 1; c < n_fields; ++c)
+    if (!dropped[c]) { kept_of[c] = (int32_t)t->columns.size(); t->columns.push_back(header[c]); }
+  const uint32_t S = (uint32_t)t->columns.size();
+  // records (blank lines are skipped)
+  std::vector<const char*> rec;                          // starts; rec_end[i] by csv_record_end again in the workers
+  std::vector<const char*> rec_end;
+  for (const char* q = he < e ? he + 1 : e; q < e;) {
+    const char* re = csv_record_end(q, e);
+    if (re > q) { rec.push_back(q); rec_end.push_back(re); }
+    q = re < e ? re + 1 : e;
+  }
+  const uint64_t R = rec.size();
+  std::unordered_map<std::string, int> na;
+  size_t na_max = 0;
+  for (uint32_t i = 0; i < n_na; ++i) { na.emplace(na_values[i], 1); na_max = std::max(na_max, strlen(na_values[i])); }
+  t->cell_off.assign((size_t)R * S, 0);
+  t->cell_len.assign((size_t)R * S, 0);
+  t->rows.assign(R, std::string());
+  uint32_t nt = n_threads ? n_threads : std::max(1u, std::thread::hardware_concurrency());
+  nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nt, R / 64 + 1));
+  std::vector<std::string> errs(nt);
+  const char* base = t->text.data();
+  auto work = [&](uint32_t w) {
+    const uint64_t r0 = R * w / nt, r1 = R * (w + 1) / nt;
+    for (uint64_t r = r0; r < r1 && errs[w].empty(); ++r) {
+      uint64_t* off = t->cell_off.data() + (size_t)r * S;
+      uint32_t* len = t->cell_len.data() + (size_t)r * S;
+      const uint32_t got = csv_fields(rec[r], rec_end[r], [&](uint32_t f, const char* a, const char* b, bool plain) {
+        if (f == 0) {
+          if (!plain) errs[w] = "escaped quotes in a row label (record " + std::to_string(r + 2) + ")";
+          t->rows[r].assign(a, b);
+          return;
+        }
+        if (f >= n_fields || kept_of[f] < 0) return;
+        if (!plain) { errs[w] = "escaped quotes in a cell of record " + std::to_string(r + 2); return; }
+        const size_t n = (size_t)(b - a);
+        if (n == 0 || (n <= na_max && na.count(std::string(a, b)))) return;          // absent
+        if (n >= (1ull << 32)) { errs[w] = "cell too long"; return; }
+        off[kept_of[f]] = (uint64_t)(a - base);
+        len[kept_of[f]] = (uint32_t)n;
+      });
+      if (got > n_fields)
+        errs[w] = "Expected " + std::to_string(n_fields) + " fields in record " + std::to_string(r + 2) + ", saw " +
+                  std::to_string(got);
+    }
+  };
+  if (nt == 1) work(0);
+  else {
+    std::vector<std::thread> th;
+    for (uint32_t w = 0; w < nt; ++w) th.emplace_back(work, w);
+    for (auto& x : th) x.join();
+  }
+  for (const std::string& m : errs)
+    if (!m.empty()) { t->err = m; return PF_ERR_INVALID; }
+  auto blob = [](const std::vector<std::string>& v, std::string* b, std::vector<uint64_t>* off) {
+    b->clear();
+    off->assign(1, 0);
+    for (const std::string& s : v) { *b += s; off->push_back(b->size()); }
+  };
+  blob(t->columns, &t->col_blob, &t->col_off);
+  blob(t->rows, &t->row_blob, &t->row_off);
+  return PF_OK;
+}
+
+extern "C" int pf_table_shape(const pf_table* t, uint64_t* n_rows, uint32_t* n_cols) {
+  if (!t) return PF_ERR_INVALID;
+  if (n_rows) *n_rows = t->rows.size();
+  if (n_cols) *n_cols = (uint32_t)t->columns.size();
+  return PF_OK;
+}
+
+extern "C" int pf_table_names(const pf_table* t, int row_labels, const char** blob, const uint64_t** off) {
+  if (!t || !blob || !off) return PF_ERR_INVALID;
+  *blob = row_labels ? t->row_blob.data() : t->col_blob.data();
+  *off = row_labels ? t->row_off.data() : t->col_off.data();
+  return PF_OK;
+}
+
+extern "C" int pf_table_row_counts(const pf_table* t, uint32_t* n_present) {
+  if (!t || !n_present) return PF_ERR_INVALID;
+  const size_t S = t->columns.size();
+  for (size_t r = 0; r < t->rows.size(); ++r) {
+    uint32_t n = 0;
+    const uint32_t* len = t->cell_len.data() + r * S;
+    for (size_t c = 0; c < S; ++c) n += len[c] != 0;
+    n_present[r] = n;
+  }
+  return PF_OK;
+}
+
+// The cells of rows[0 .. n_sel) with the columns in the order col_order (col_order[j] = table
+// column shown at position j; NULL = table order): present[i * n_cols + j] = 1 where row i has a
+// cell there, and those cells, row by row in that order, joined with '\n' - the cells_blob of
+// pf_feeder_cut.  blob NULL: sizing (blob_len, n_cells).
+extern "C" int pf_table_cells(const pf_table* t, const uint64_t* rows, uint64_t n_sel, const uint32_t* col_order,
+                              uint8_t* present, char* blob, uint64_t blob_cap, uint64_t* blob_len, uint64_t* n_cells) {
+  if (!t || (n_sel && !rows) || !blob_len) return PF_ERR_INVALID;
+  const size_t S = t->columns.size();
+  const char* base = t->text.data();
+  uint64_t bytes = 0, cells = 0;
+  for (uint64_t i = 0; i < n_sel; ++i) {
+    if (rows[i] >= t->rows.size()) return PF_ERR_INVALID;
+    const uint32_t* len = t->cell_len.data() + (size_t)rows[i] * S;
+    for (size_t j = 0; j < S; ++j) {
+      const uint32_t l = len[col_order ? col_order[j] : j];
+      if (l) { bytes += l; ++cells; }
+    }
+  }
+  *blob_len = bytes + (cells ? cells - 1 : 0);
+  if (n_cells) *n_cells = cells;
+  if (!blob && !present) return PF_OK;
+  if (blob && blob_cap < *blob_len) return PF_ERR_NOMEM;
+  char* p = blob;
+  bool first = true;
+  for (uint64_t i = 0; i < n_sel; ++i) {
+    const uint64_t* off = t->cell_off.data() + (size_t)rows[i] * S;
+    const uint32_t* len = t->cell_len.data() + (size_t)rows[i] * S;
+    for (size_t j = 0; j < S; ++j) {
+      const size_t c = col_order ? col_order[j] : j;
+      if (col_order && c >= S) return PF_ERR_INVALID;
+      if (present) present[i * S + j] = len[c] != 0;
+      if (len[c] && blob) {
+        if (!first) *p++ = '\n';
+        first = false;
+        memcpy(p, base + off[c], len[c]);
+        p += len[c];
+      }
+    }
+  }
+  return PF_OK;
+}

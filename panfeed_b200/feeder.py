@@ -266,6 +266,106 @@ def prep_feeder(filelist, fastalist, gffdir, fastadir, output=None):
     return feeder, index
 
 
+def _na_values():
+    """The strings pandas reads as a missing value (read_csv's default na_values)."""
+    try:
+        from pandas._libs.parsers import STR_NA_VALUES
+        return sorted(STR_NA_VALUES)
+    except Exception:      # noqa: BLE001 - a pandas without that private name: its documented defaults
+        return ["", "#N/A", "#N/A N/A", "#NA", "-1.#IND", "-1.#QNAN", "-NaN", "-nan", "1.#IND", "1.#QNAN", "<NA>",
+                "N/A", "NA", "NULL", "NaN", "None", "n/a", "nan", "null"]
+
+
+class PanarooTable:
+    """panaroo's gene_presence_absence.csv read by the library (pf_table_*): stands where the
+    reference's `genepres` DataFrame does (pd.read_csv(..., index_col=0).drop(columns=[...]),
+    input.py:198-201) for the native feeder - `columns`, `index`, a row subset (`take`), the
+    cells of a run of rows - without a Python object per cell (pandas needs ~0.5 us and ~60 bytes
+    for each; BASELINE configs #4 / #5 hold 5e7 / 4e8 of them)."""
+
+    DROP = ("Non-unique Gene name", "Annotation")
+
+    def __init__(self, path=None, _parent=None, _rows=None):
+        if _parent is not None:
+            self._owner, self.lib, self.h = _parent._owner, _parent.lib, _parent.h
+            self.columns, self._labels = _parent.columns, _parent._labels
+            self._rows = np.asarray(_rows, np.uint64)
+            return
+        self._owner = self
+        self.lib = capi.load()
+        self.h = C.c_void_p()
+        if self.lib.pf_table_create(C.byref(self.h)) != 0:
+            raise capi.PfError(-1, "pf_table_create failed")
+        drop = (C.c_char_p * len(self.DROP))(*[d.encode() for d in self.DROP])
+        na = [x.encode() for x in _na_values()]
+        rc = self.lib.pf_table_load(self.h, os.fsencode(path), drop, len(self.DROP), (C.c_char_p * len(na))(*na),
+                                    len(na), 0)
+        if rc != 0:
+            msg = self.lib.pf_table_last_error(self.h).decode()
+            if msg.startswith("column not found"):
+                raise KeyError(msg)                  # what DataFrame.drop raises
+            raise capi.PfError(rc, f"reading {path}: {msg}")
+        n_rows, n_cols = C.c_uint64(), C.c_uint32()
+        self.lib.pf_table_shape(self.h, C.byref(n_rows), C.byref(n_cols))
+        self.columns = self._names(0, n_cols.value)
+        self._labels = self._names(1, n_rows.value)
+        self._rows = np.arange(n_rows.value, dtype=np.uint64)
+
+    def _names(self, row_labels, n):
+        blob, off = C.c_void_p(), C.c_void_p()
+        self.lib.pf_table_names(self.h, row_labels, C.byref(blob), C.byref(off))
+        if n == 0:
+            return []
+        o = np.ctypeslib.as_array(C.cast(off, C.POINTER(C.c_uint64)), shape=(n + 1,))
+        text = C.string_at(blob, int(o[-1]))
+        return [text[int(o[i]):int(o[i + 1])].decode() for i in range(n)]
+
+    def __del__(self):
+        try:
+            if self._owner is self and self.h:
+                self.lib.pf_table_destroy(self.h)
+                self.h = C.c_void_p()
+        except Exception:      # noqa: BLE001
+            pass
+
+    @property
+    def index(self):
+        return [self._labels[int(r)] for r in self._rows]
+
+    @property
+    def shape(self):
+        return (len(self._rows), len(self.columns))
+
+    def take(self, positions):
+        """The rows at `positions` (of this view), like DataFrame.iloc[positions]."""
+        return PanarooTable(_parent=self, _rows=self._rows[np.asarray(positions, np.int64)])
+
+    def n_present(self):
+        """Number of present cells of every row (DataFrame.notna().sum(axis=1))."""
+        n_all = np.zeros(len(self._labels), np.uint32)
+        if len(n_all):
+            self.lib.pf_table_row_counts(self.h, n_all.ctypes.data)
+        return n_all[self._rows.astype(np.int64)].astype(np.int64)
+
+    def cells(self, positions, col_order=None):
+        """(present [n, n_cols] bool, the present cells row by row joined with newlines) of the
+        rows at `positions`, columns in the order `col_order`."""
+        rows = np.ascontiguousarray(self._rows[np.asarray(positions, np.int64)], dtype=np.uint64)
+        order = None if col_order is None else np.ascontiguousarray(col_order, dtype=np.uint32)
+        S = len(self.columns)
+        need, n_cells = C.c_uint64(), C.c_uint64()
+        args = (self.h, rows.ctypes.data, len(rows), None if order is None else order.ctypes.data)
+        rc = self.lib.pf_table_cells(*args, None, None, 0, C.byref(need), C.byref(n_cells))
+        if rc != 0:
+            raise capi.PfError(rc, "pf_table_cells (sizing) failed")
+        present = np.zeros((len(rows), S), np.uint8)
+        blob = C.create_string_buffer(max(1, int(need.value)))
+        rc = self.lib.pf_table_cells(*args, present.ctypes.data, blob, int(need.value), C.byref(need), C.byref(n_cells))
+        if rc != 0:
+            raise capi.PfError(rc, "pf_table_cells failed")
+        return present.astype(bool), blob.raw[:int(need.value)]
+
+
 def prefetch(iterator, depth=2):
     """Runs `iterator` on a background thread, `depth` items ahead of the consumer: the library
     cuts and packs the next GPU batch (GIL released inside the calls) while the current one is on
@@ -328,9 +428,16 @@ class _CutPlan:
         perm = np.argsort(np.array([rank[c] for c in cols]), kind="stable")        # table columns in rank order
         self.genome_of_rank = np.array([genome_index[s] for s in self.order], np.uint32)
         self.target_of_rank = np.array([s in stroi for s in self.order], bool)
-        self.values = panaroo.to_numpy(dtype=object)[:, perm]
-        self.present_all = pd.notna(self.values)
-        self.n_rows, self.S = self.values.shape
+        self.perm = perm
+        self.table = panaroo if isinstance(panaroo, PanarooTable) else None
+        if self.table is not None:
+            self.n_rows, self.S = panaroo.shape
+            all_cells = panaroo.n_present()
+        else:
+            self.values = panaroo.to_numpy(dtype=object)[:, perm]
+            self.present_all = pd.notna(self.values)
+            self.n_rows, self.S = self.values.shape
+            all_cells = self.present_all.sum(axis=1)
         self.index = list(panaroo.index)
         rows = []
         for i, idx in enumerate(self.index):
@@ -339,7 +446,7 @@ class _CutPlan:
                 continue
             rows.append(i)
         self.rows = np.array(rows, np.int64)
-        self.n_cells = self.present_all[self.rows].sum(axis=1) if len(self.rows) else np.zeros(0, np.int64)
+        self.n_cells = all_cells[self.rows] if len(self.rows) else np.zeros(0, np.int64)
 
     def take(self, at, cell_budget):
         """-> `to`: rows at .. to hold at least one cluster, then as many as fit the cell budget."""
@@ -353,10 +460,14 @@ class _CutPlan:
         """Cut rows at .. to -> (sel, pres, rr, cc, cut): the table rows, their presence matrix, the
         (cluster, rank) of every present cell in row-major order, the library's result."""
         sel = self.rows[at:to]
-        pres = self.present_all[sel]
-        rr, cc = np.nonzero(pres)                    # row-major: cluster by cluster, ranks ascending
-        cells = self.values[sel][pres]
-        blob = "\n".join(cells).encode() if len(cells) else b""
+        if self.table is not None:
+            pres, blob = self.table.cells(sel, self.perm)
+            rr, cc = np.nonzero(pres)                # row-major: cluster by cluster, ranks ascending
+        else:
+            pres = self.present_all[sel]
+            rr, cc = np.nonzero(pres)
+            cells = self.values[sel][pres]
+            blob = "\n".join(cells).encode() if len(cells) else b""
         cut = self.feeder.cut(self.genome_of_rank[cc], blob, self.up, self.down, self.dsc, prepack=True)
         for cell, kind, name in cut["missing"]:
             idx, strain = self.index[sel[rr[cell]]], self.order[cc[cell]]

@@ -247,12 +247,17 @@ def create_hash_files(output, compress=False):
 
 
 def set_input_output(stroi_in, genes_in, presence_absence, output,
-                     single_file=True, compress=False, make_outputs=True):
+                     single_file=True, compress=False, make_outputs=True, native_table=False):
     """-> (stroi, genes, kmer_stroi, hash_pat, kmer_hash, genepres).  input.py:183-232.
     make_outputs=False (ranks of a sharded run: the output directory and the three files
-    belong to rank 0) only reads the inputs."""
-    genepres = pd.read_csv(presence_absence, sep=",", index_col=0, low_memory=False).drop(
-        columns=["Non-unique Gene name", "Annotation"])
+    belong to rank 0) only reads the inputs.  native_table: `genepres` is a feeder.PanarooTable
+    (same columns / index / rows, read by the library) instead of a DataFrame."""
+    if native_table:        # the library's reader (feeder.PanarooTable): no Python object per cell
+        from .feeder import PanarooTable
+        genepres = PanarooTable(presence_absence)
+    else:
+        genepres = pd.read_csv(presence_absence, sep=",", index_col=0, low_memory=False).drop(
+            columns=["Non-unique Gene name", "Annotation"])
     if stroi_in is not None:
         stroi = {line.rstrip("\n") for line in open(stroi_in)}
     else:

@@ -390,3 +390,71 @@ def test_contig_views_match_python_feeder(layout, tmp_path):
         if ref[3] is not None:
             assert (packed["amb_plane"] == ref[3]).all() and (packed["amb_off"] == ref[4]).all()
     native.close()
+
+
+TABLE = '''Gene,Non-unique Gene name,Annotation,s02,s00,s01,"s 03"
+cl1,,"hypothetical protein, putative",g2_1,g0_1;g0_2,,g3_1
+cl2,x,"two
+lines, with a comma",,g0_3,g1_3,NA
+
+"cl3",y,plain,g2_4,"g0_4",nan,g3_4
+cl4,,,g2_5
+cl5,,"a ""quoted"" word",#N/A,None,g1_6,n/a
+cl6,,,-,0,1.5,g3_7
+'''
+
+
+@pytest.mark.parametrize("crlf", [False, True])
+def test_panaroo_table_equals_pandas(crlf, tmp_path):
+    """feeder.PanarooTable (pf_table_*: the mapped file, cells as offsets) against what the
+    reference does - pd.read_csv(..., index_col=0, low_memory=False).drop(columns=[...]) - on a
+    table with quoted fields (commas, line ends, escaped quotes in a dropped column), a blank
+    line, a short row, pandas' missing-value strings, unsorted columns, both line ends."""
+    path = tmp_path / "t.csv"
+    path.write_bytes((TABLE.replace("\n", "\r\n") if crlf else TABLE).encode())
+    want = pd.read_csv(path, sep=",", index_col=0, low_memory=False, dtype=str).drop(
+        columns=["Non-unique Gene name", "Annotation"])
+    got = nf.PanarooTable(str(path))
+    assert got.columns == [str(c) for c in want.columns] == ["s02", "s00", "s01", "s 03"]
+    assert got.index == [str(i) for i in want.index] and got.shape == want.shape
+    assert (got.n_present() == want.notna().sum(axis=1).to_numpy()).all()
+    vals = want.to_numpy(dtype=object)
+    for order in (None, [1, 2, 0, 3], [3, 2, 1, 0]):
+        for rows in ([0, 1, 2, 3, 4, 5], [4, 0], [3], []):
+            pres, blob = got.cells(rows, order)
+            v = vals[rows][:, order] if order is not None else vals[rows]
+            assert (pres == pd.notna(v)).all() and pres.shape == (len(rows), 4)
+            assert blob == "\n".join(v[pd.notna(v)]).encode()
+    sub = got.take([5, 1, 2])
+    assert sub.index == ["cl6", "cl2", "cl3"] and sub.shape == (3, 4)
+    assert (sub.n_present() == want.iloc[[5, 1, 2]].notna().sum(axis=1).to_numpy()).all()
+    assert sub.cells([1], None)[1] == b"g0_3\ng1_3"
+    assert sub.take([2, 0]).index == ["cl3", "cl6"]
+    (tmp_path / "bad.csv").write_text("Gene,Annotation,s0\ncl1,,g\n")
+    with pytest.raises(KeyError):
+        nf.PanarooTable(str(tmp_path / "bad.csv"))
+    (tmp_path / "long.csv").write_text("Gene,Non-unique Gene name,Annotation,s0\ncl1,,,g,extra,more\n")
+    with pytest.raises(capi.PfError, match="Expected 4 fields"):
+        nf.PanarooTable(str(tmp_path / "long.csv"))
+
+
+def test_batches_from_native_table_equal_batches_from_dataframe():
+    stroi = {"s00", "s05"}
+    gffdir = os.path.join(FIX, "gffs")
+    filelist, fastalist = pyin.what_are_my_inputfiles(gffdir, None)
+    native, index = nf.prep_feeder(filelist, fastalist, gffdir, None)
+    table = nf.PanarooTable(os.path.join(FIX, "gene_presence_absence.csv"))
+    a = list(nf.iter_packed_batches(_table(), native, index, 30, 10, False, stroi, 31, True, False, first_cells=20,
+                                    target_bases=20000))
+    b = list(nf.iter_packed_batches(table, native, index, 30, 10, False, stroi, 31, True, False, first_cells=20,
+                                    target_bases=20000))
+    assert len(a) == len(b) > 1
+    for (ia, pa, _, _), (ib, pb, _, _) in zip(a, b):
+        assert ia == ib
+        assert (pa.hb.packed == pb.hb.packed).all() and pa.hb.seqs.tobytes() == pb.hb.seqs.tobytes()
+        assert (pa.hb.presence == pb.hb.presence).all()
+    genes = {"group_acc1", "group_core0"} & set(table.index) or set(table.index[:2])
+    c = list(nf.iter_packed_clusters(table.take([0, 2, 3]), native, index, 0, 0, False, stroi, 31, True, False, genes))
+    d = list(nf.iter_packed_clusters(_table().iloc[[0, 2, 3]], native, index, 0, 0, False, stroi, 31, True, False, genes))
+    assert [x[0] for x in c] == [x[0] for x in d]
+    native.close()
