@@ -26,6 +26,7 @@
 #include <unistd.h>
 
 #include "../../include/panfeed_b200.h"
+#include "pf_host.h"
 
 namespace {
 
@@ -456,7 +457,7 @@ extern "C" int pf_feeder_add_genomes(pf_feeder* f, uint32_t n, const char* const
   if (n == 0) return first;
   std::vector<pf_feeder> local(n);                       // one scratch feeder per genome: no shared state
   std::vector<int> rc(n, PF_OK);
-  uint32_t nt = n_threads ? n_threads : std::max(1u, std::thread::hardware_concurrency());
+  uint32_t nt = n_threads ? n_threads : pf_host_threads();
   nt = std::min(nt, n);
   std::vector<std::thread> th;
   for (uint32_t t = 0; t < nt; ++t)
@@ -608,7 +609,7 @@ int place_windows(pf_feeder* f, uint32_t n_cells, const uint32_t* genome, const 
   cell_at[n_cells] = p;
   // all cores, >= 2,048 cells (~1 ms) per thread; a caller that names a thread count gets it
   uint32_t nt = n_threads ? std::min(n_threads, std::max(1u, n_cells / 8u))
-                          : std::min(std::max(1u, std::thread::hardware_concurrency()), n_cells / 2048u);
+                          : std::min(pf_host_threads(), n_cells / 2048u);
   nt = std::max(1u, nt);
   std::vector<Placed> part(nt);
   if (nt == 1) {
@@ -708,7 +709,7 @@ extern "C" int pf_feeder_cut(pf_feeder* f, uint32_t n_cells, const uint32_t* gen
         }
       }
     };
-    uint32_t nt = std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    uint32_t nt = std::min<uint32_t>(pf_host_threads(), 8u);
     nt = (uint32_t)std::min<size_t>(nt, std::max<size_t>(1, total >> 20));       // >= 1 MiB per thread
     if (nt <= 1 || n_seq < 2 * nt) fill(0, n_seq);
     else {
@@ -791,7 +792,7 @@ extern "C" int pf_feeder_cut_packed(pf_feeder* f, uint32_t n_cells, const uint32
     f->packed_cap = n_words + n_words / 4 + 64;
     f->packed.reset(new uint64_t[f->packed_cap]);
   }
-  uint32_t nt = n_threads ? n_threads : std::max(1u, std::thread::hardware_concurrency());
+  uint32_t nt = n_threads ? n_threads : pf_host_threads();
   if (!n_threads) nt = (uint32_t)std::min<size_t>(nt, std::max<size_t>(1, (size_t)f->seq_off.back() >> 18));    // >= 256 k bases per thread
   nt = (uint32_t)std::max<size_t>(1, std::min<size_t>(nt, n_seq));
   const std::vector<size_t> cut = split_by_bases(f->seq_off, nt);
@@ -1025,7 +1026,7 @@ extern "C" int pf_table_load(pf_table* t, const char* path, const char* const* d
   t->cell_off.assign((size_t)R * S, 0);
   t->cell_len.assign((size_t)R * S, 0);
   t->rows.assign(R, std::string());
-  uint32_t nt = n_threads ? n_threads : std::max(1u, std::thread::hardware_concurrency());
+  uint32_t nt = n_threads ? n_threads : pf_host_threads();
   nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nt, R / 64 + 1));
   std::vector<std::string> errs(nt);
   const char* base = t->text.data();

@@ -16,6 +16,7 @@
 #include <zlib.h>
 
 #include "../../include/panfeed_b200.h"
+#include "pf_host.h"
 
 namespace {
 
@@ -147,7 +148,7 @@ extern "C" int pf_format_positions(const pf_batch_result* r, uint32_t k, int can
   if (count == 0) return PF_OK;
   if (!lead_blob || !lead_off || (!canonical && !seq_strand)) return PF_ERR_INVALID;
   Job j{r, k, canonical, lead_blob, lead_off, seq_strand};
-  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  const uint32_t hw = pf_host_threads();
   uint32_t nt = n_threads ? n_threads : hw;
   nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nt, (count + 65535) / 65536));
   const uint64_t per = (count + nt - 1) / nt;
@@ -278,7 +279,7 @@ extern "C" int pf_format_positions_compact(const pf_batch* b, const uint32_t* st
   for (uint32_t i = seq_first; i < seq_first + seq_count; ++i)
     if ((b->seqs[i].flags & PF_SEQ_TARGET) && (b->seqs[i].flags & PF_SEQ_AMBIGUOUS) && !b->amb_codes) return PF_ERR_INVALID;
   CJob j{b, strand_bits, k, canonical, lead_blob, lead_off};
-  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  const uint32_t hw = pf_host_threads();
   uint32_t nt = n_threads ? n_threads : hw;
   nt = std::max(1u, std::min<uint32_t>(nt, (seq_count + 63u) / 64u));
   const uint32_t per = (seq_count + nt - 1) / nt;
@@ -327,7 +328,7 @@ const Lut kLut;
 
 template <typename F>
 void parallel_for(uint32_t n, uint32_t n_threads, F&& fn) {
-  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  const uint32_t hw = pf_host_threads();
   uint32_t nt = n_threads ? n_threads : hw;
   nt = std::max(1u, std::min<uint32_t>(nt, (n + 4095u) / 4096u));
   if (nt == 1) { fn(0u, n); return; }
@@ -542,7 +543,7 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
   if (!out) return PF_OK;
   if (out_cap < off[nc]) return PF_ERR_NOMEM;
   // clusters are taken one at a time by the threads (they differ in rows): sort, then write
-  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  const uint32_t hw = pf_host_threads();
   uint32_t nt = n_threads ? n_threads : hw;
   nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nt, (nn + nw + nc + 16383) / 16384));
   std::atomic<uint32_t> next{0};
@@ -635,7 +636,7 @@ extern "C" int pf_gzip_members(const char* text, uint64_t len, int level, uint64
   if (!out) return PF_OK;
   std::vector<std::vector<unsigned char>> parts(n_members);
   std::vector<int> rc(n_members, Z_OK);
-  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  const uint32_t hw = pf_host_threads();
   uint32_t nt = n_threads ? n_threads : hw;
   nt = (uint32_t)std::min<uint64_t>(nt, n_members);
   std::atomic<uint32_t> next{0};

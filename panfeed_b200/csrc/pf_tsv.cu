@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/panfeed_b200.h"
+#include "pf_host.h"
 
 extern "C" void pf_free(void* p) { free(p); }
 
@@ -56,7 +57,7 @@ extern "C" int pf_tsv_filter(const char* path, uint32_t column, const char* keys
     body = nl ? nl + 1 : end;
   }
   const size_t body_size = (size_t)(end - body);
-  const uint32_t hw = std::max(1u, std::thread::hardware_concurrency());
+  const uint32_t hw = pf_host_threads();
   uint32_t nt = n_threads ? n_threads : hw;
   nt = (uint32_t)std::max<size_t>(1, std::min<size_t>(nt, body_size >> 22));      // >= 4 MiB per thread
   // piece boundaries on line starts
