@@ -406,8 +406,8 @@ def prefetch(iterator, depth=2):
                 return
             yield item
     finally:
-        stop.set()                        # the consumer left early (error downstream): let the producer go
-        th.join(timeout=5)
+        stop.set()                        # the consumer left early (error downstream): the producer finishes
+        th.join()                         # the cut it is in, sees the flag and goes; the feeder outlives it
 
 
 class _CutPlan:
