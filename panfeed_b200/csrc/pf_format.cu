@@ -510,11 +510,36 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
   if (nw && (!r->wide_row_cluster || !r->wide_row_kmer || !r->wide_row_pattern || !kmer_ids)) return PF_ERR_INVALID;
   if (nc == 0) return (nn || nw) ? PF_ERR_INVALID : PF_OK;
   if (nn && k > 32) return PF_ERR_INVALID;             // one-word k-mers hold at most 32 bases
-  // rows of every cluster: counting sort of the row indices (narrow rows first, then wide)
+  // rows of every cluster (narrow rows; the wide ones, few, below).  The block engine writes the
+  // rows of a cluster as ONE run (a CTA per cluster reserves them with one atomic), clusters in any
+  // order: then a scan for the run boundaries is all it takes - no counting pass, no scatter of
+  // row indices, which were the serial part of this function.  Anything else (a cluster in
+  // several runs: the record engines, sample slices) goes through a counting sort.
   std::vector<uint32_t> first(nc + 1, 0), first_w(nc + 1, 0);
-  for (uint64_t i = 0; i < nn; ++i) {
-    if (r->row_cluster[i] >= nc || r->row_pattern[i] >= n_kmer_ids) return PF_ERR_INVALID;
-    ++first[r->row_cluster[i] + 1];
+  std::vector<uint32_t> run_at(nc, 0);                  // direct: first row of cluster c's run
+  std::vector<uint32_t> order;
+  bool direct = true;
+  {
+    std::vector<uint8_t> seen(nc, 0);
+    uint64_t i = 0;
+    while (i < nn) {
+      const uint32_t c = r->row_cluster[i];
+      if (c >= nc) return PF_ERR_INVALID;
+      uint64_t j = i + 1;
+      while (j < nn && r->row_cluster[j] == c) ++j;
+      if (seen[c]) { direct = false; break; }
+      seen[c] = 1;
+      run_at[c] = (uint32_t)i;
+      first[c + 1] = (uint32_t)(j - i);
+      i = j;
+    }
+  }
+  if (!direct) {
+    std::fill(first.begin(), first.end(), 0u);
+    for (uint64_t i = 0; i < nn; ++i) {
+      if (r->row_cluster[i] >= nc) return PF_ERR_INVALID;
+      ++first[r->row_cluster[i] + 1];
+    }
   }
   for (uint64_t i = 0; i < nw; ++i) {
     if (r->wide_row_cluster[i] >= nc || r->wide_row_pattern[i] >= n_kmer_ids) return PF_ERR_INVALID;
@@ -525,11 +550,15 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
     first[c + 1] += first[c];
     first_w[c + 1] += first_w[c];
   }
-  std::vector<uint32_t> order(nn), order_w(nw);
+  std::vector<uint32_t> order_w(nw);
   {
-    std::vector<uint32_t> at(first.begin(), first.end() - 1), at_w(first_w.begin(), first_w.end() - 1);
-    for (uint64_t i = 0; i < nn; ++i) order[at[r->row_cluster[i]]++] = (uint32_t)i;
+    std::vector<uint32_t> at_w(first_w.begin(), first_w.end() - 1);
     for (uint64_t i = 0; i < nw; ++i) order_w[at_w[r->wide_row_cluster[i]]++] = (uint32_t)i;
+    if (!direct) {
+      order.resize(nn);
+      std::vector<uint32_t> at(first.begin(), first.end() - 1);
+      for (uint64_t i = 0; i < nn; ++i) order[at[r->row_cluster[i]]++] = (uint32_t)i;
+    }
   }
   // byte offsets of the clusters' texts
   std::vector<uint64_t> off(nc + 1, 0);
@@ -547,6 +576,7 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
   uint32_t nt = n_threads ? n_threads : hw;
   nt = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(nt, (nn + nw + nc + 16383) / 16384));
   std::atomic<uint32_t> next{0};
+  std::atomic<uint32_t> bad_pattern{0};
   auto work = [&]() {
     std::vector<KeyedRow> keyed;
     for (;;) {
@@ -554,10 +584,18 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
       if (c >= nc) return;
       // (k-mer, row) pairs side by side: the sort compares values it already holds instead of
       // chasing row indices into the result arrays
-      const uint32_t* o = order.data() + first[c];
       const uint32_t n = first[c + 1] - first[c];
       keyed.resize(n);
-      for (uint32_t j = 0; j < n; ++j) keyed[j] = KeyedRow{r->row_kmer[o[j]], o[j]};
+      if (direct) {
+        const uint32_t a = run_at[c];
+        for (uint32_t j = 0; j < n; ++j) keyed[j] = KeyedRow{r->row_kmer[a + j], a + j};
+      } else {
+        const uint32_t* o = order.data() + first[c];
+        for (uint32_t j = 0; j < n; ++j) keyed[j] = KeyedRow{r->row_kmer[o[j]], o[j]};
+      }
+      bool ok = true;
+      for (uint32_t j = 0; j < n; ++j) ok &= r->row_pattern[keyed[j].row] < n_kmer_ids;
+      if (!ok) { bad_pattern.store(1); continue; }
       std::sort(keyed.begin(), keyed.end(), [](const KeyedRow& a, const KeyedRow& b) {
         return a.kmer != b.kmer ? a.kmer < b.kmer : a.row < b.row;
       });
@@ -608,7 +646,7 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
     for (uint32_t t = 0; t < nt; ++t) th.emplace_back(work);
     for (auto& x : th) x.join();
   }
-  return PF_OK;
+  return bad_pattern.load() ? PF_ERR_INVALID : PF_OK;          // a row_pattern past the id table
 }
 
 // ---------------------------------------------------------------------------

@@ -126,9 +126,12 @@ def _kmer_rows_python(r, k, tags, kmer_ids, cluster_ids):
 
 @pytest.mark.parametrize("k", [1, 17, 31, 32])
 @pytest.mark.parametrize("threads", [1, 4])
-def test_native_kmer_rows_match_python(k, threads):
+@pytest.mark.parametrize("layout", ["interleaved", "runs"])
+def test_native_kmer_rows_match_python(k, threads, layout):
     """pf_format_kmer_rows against the reference's f-strings (panfeed.py:177, :208): header row
-    per cluster (also for clusters without rows), k-mer rows sorted inside the cluster."""
+    per cluster (also for clusters without rows), k-mer rows sorted inside the cluster.
+    layout: the rows of the clusters interleaved (record engines: counting sort inside), or one
+    run per cluster with the clusters in any order (the block engine: run boundaries only)."""
     rng = np.random.default_rng(7 * k + threads)
     nc = 23
     n = 40_000 if threads > 1 else 2_000
@@ -138,6 +141,11 @@ def test_native_kmer_rows_match_python(k, threads):
     tags = [str(int(x)).encode() for x in rng.integers(0, 100000, nc)]
     row_cluster = rng.integers(0, nc, n).astype(np.uint32)
     row_cluster[row_cluster == 5] = 6                      # cluster 5 has no narrow rows
+    if layout == "runs":
+        rank = rng.permutation(nc)                         # clusters in shuffled order, each one run
+        row_cluster = row_cluster[np.argsort(rank[row_cluster], kind="stable")]
+        assert len(np.flatnonzero(np.diff(row_cluster.astype(np.int64)))) == len(np.unique(row_cluster)) - 1
+        assert (np.diff(row_cluster.astype(np.int64)) < 0).any()
     # distinct k-mers per cluster are what the library returns; duplicates across clusters are fine
     row_kmer = rng.integers(0, 1 << min(62, 2 * k), n, dtype=np.uint64) if k < 32 else \
         rng.integers(0, 1 << 63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
