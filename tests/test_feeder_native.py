@@ -458,3 +458,46 @@ def test_batches_from_native_table_equal_batches_from_dataframe():
     d = list(nf.iter_packed_clusters(_table().iloc[[0, 2, 3]], native, index, 0, 0, False, stroi, 31, True, False, genes))
     assert [x[0] for x in c] == [x[0] for x in d]
     native.close()
+
+
+def test_panaroo_table_fuzz_against_pandas(tmp_path):
+    """Random small tables - quoted fields with commas / line ends / escaped quotes (in the dropped
+    columns), pandas' missing-value strings, padded cells, short rows, blank lines, both line
+    ends, shuffled columns: PanarooTable must see the table pandas sees."""
+    import random
+    rnd = random.Random(11)
+    atoms = ["g1", "g_2;g_3", "", "NA", "nan", "x y", " lead", "trail ", "a,b", 'q"q', "line\nbreak", "N/A", "None",
+             "0", "-", "#NA", "null", "é", "\t"]
+
+    def field(a):
+        if any(ch in a for ch in ',"\n') or rnd.random() < 0.15:
+            return '"' + a.replace('"', '""') + '"'
+        return a
+    path = str(tmp_path / "t.csv")
+    compared = 0
+    for _ in range(150):
+        ncol, nrow = rnd.randint(1, 6), rnd.randint(0, 8)
+        cols = [f"s{j}" for j in range(ncol)]
+        rnd.shuffle(cols)
+        lines = ["Gene,Non-unique Gene name,Annotation," + ",".join(cols)]
+        for r in range(nrow):
+            cells = [rnd.choice([a for a in atoms if '"' not in a]) for _ in range(ncol)]
+            keep = ncol if rnd.random() < 0.8 else rnd.randint(0, ncol)
+            lines.append(",".join([f"cl{r}", field(rnd.choice(["", "x"])), field(rnd.choice(atoms))] +
+                                  [field(c) for c in cells[:keep]]))
+            if rnd.random() < 0.1:
+                lines.append("")
+        nl = rnd.choice(["\n", "\r\n"])
+        with open(path, "wb") as fh:
+            fh.write((nl.join(lines) + (nl if rnd.random() < 0.8 else "")).encode())
+        want = pd.read_csv(path, sep=",", index_col=0, low_memory=False, dtype=str).drop(
+            columns=["Non-unique Gene name", "Annotation"])
+        got = nf.PanarooTable(path)
+        vals = want.to_numpy(dtype=object)
+        pres, blob = got.cells(np.arange(got.shape[0]), None)
+        assert got.columns == [str(c) for c in want.columns] and got.shape == want.shape
+        assert got.index == [str(i) for i in want.index]
+        assert (pres == pd.notna(vals)).all()
+        assert blob == b"\n".join(x.encode() for x in vals[pd.notna(vals)])
+        compared += 1
+    assert compared == 150
