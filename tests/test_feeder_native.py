@@ -501,3 +501,83 @@ def test_panaroo_table_fuzz_against_pandas(tmp_path):
         assert blob == b"\n".join(x.encode() for x in vals[pd.notna(vals)])
         compared += 1
     assert compared == 150
+
+
+def test_native_feeder_fuzz_against_python_feeder(tmp_path):
+    """Random GFF3 + FASTA text built from the quirks both parsers tolerate (short / long rows,
+    int() oddities, any strand symbol, ID attributes in every form, comments, repeated and
+    unnamed contigs, ragged / padded / blank sequence lines, both line ends): features, contigs
+    and the cut sequences with their Seqinfo fields must be the Python feeder's."""
+    import logging
+    import random
+    rnd = random.Random(5)
+    ints = ["1", "12", "40", "99", "150"] * 3 + [" 7", "7 ", "1_0", "+5", "-3", "0", "abc", "", "1.0", "1__0", "_1", "99999"]
+    strands = ["+", "-", "+", "-", ".", "?", "", "+ "]
+    attrs = ["ID=g{}", "ID=g{};Name=x", "ID=g{};x=1", "ID=g{};x=2", "Name=y;ID=g{}", "ID=g{}=tail", "locus=1;ID=g{};", "IDX=o{}", "ID", "Name=z",
+             "ID=g{};ID=h{}", "ID=", "id=g{}"]
+    path = str(tmp_path / "g.gff")
+    cuts = 0
+    logging.disable(logging.WARNING)
+    try:
+        for _ in range(120):
+            fasta_lines = []
+            for c in range(rnd.randint(1, 3)):
+                name = rnd.choice([f"c{c}", f"c{c} desc", f" c{c}", "c0", ""])
+                seq = "".join(rnd.choice("ACGTacgtNnRY") for _ in range(rnd.randint(0, 300)))
+                fasta_lines.append(">" + name)
+                w, style, i = rnd.choice([10, 60, 70, 1000]), rnd.random(), 0
+                while i < len(seq):
+                    ww = w if style < 0.7 else rnd.randint(1, 80)
+                    piece = seq[i:i + ww]
+                    if rnd.random() < 0.05:
+                        piece = " " + piece
+                    if rnd.random() < 0.05:
+                        piece = piece + " "
+                    fasta_lines.append(piece)
+                    if rnd.random() < 0.03:
+                        fasta_lines.append("")
+                    i += ww
+            gff_lines = ["##gff-version 3"]
+            for g in range(rnd.randint(0, 12)):
+                cols = [rnd.choice(["c0", "c1", "c2", "cX"]), "src", rnd.choice(["CDS", "CDS", "gene", "cds"]),
+                        rnd.choice(ints), rnd.choice(ints), ".", rnd.choice(strands), "0",
+                        rnd.choice(attrs).format(g, g)]
+                line = "\t".join((cols + ["extra"])[:rnd.choice([9, 9, 9, 9, 8, 5, 3, 2, 10])])
+                if rnd.random() < 0.05:
+                    line = "  # comment"
+                if rnd.random() < 0.05:
+                    line = "#" + line
+                gff_lines.append(line)
+            nl = rnd.choice(["\n", "\n", "\r\n"])
+            text = nl.join(gff_lines) + nl + "##FASTA" + nl + nl.join(fasta_lines) + (nl if rnd.random() < 0.9 else "")
+            with open(path, "wb") as fh:
+                fh.write(text.encode())
+            feats = pyin.parse_gff(path)
+            pcont = pyin.read_fasta_text(open(path).read().split("##FASTA")[1].split("\n"))
+            native = nf.NativeFeeder()
+            g = native.add_genome("q", path)
+            info = native.genome_info(g)
+            got = {}
+            for i in range(info["features"]):
+                ident, contig, start, end, strand = native.feature(g, i)
+                got[ident] = (contig, start, end, strand)
+            assert got == {k: (v.chromosome, v.start, v.end, v.strand) for k, v in feats.items()}, text
+            listed = [native.contig(g, i) for i in range(info["contigs"])]
+            assert {x[0]: x[1] for x in listed} == {k: len(v) for k, v in pcont.items()}, text
+            ids = [i for i in feats if "\n" not in i and ";" not in i]      # (what a table cell can name)
+            if ids:
+                table = pd.DataFrame({"q": [";".join(ids)]}, index=["cl"])
+                for up, down, dsc in [(0, 0, False), (rnd.randint(0, 50), rnd.randint(0, 50), rnd.random() < 0.5)]:
+                    py = list(pyin.iter_gene_clusters(table, {"q": (pcont, feats)}, up, down, dsc, True))
+                    cut = native.cut(np.zeros(1, np.uint32) + g, ";".join(ids).encode(), up, down, dsc)
+                    off = cut["seq_off"].astype(np.int64)
+                    assert [cut["ascii"][off[i]:off[i + 1]] for i in range(cut["n_seqs"])] == \
+                        [q.sequence.encode() for q in py[0][0]["q"]], text
+                    assert [(q.start, q.end, q.offset, q.strand) for q in py[0][0]["q"]] == \
+                        list(zip(cut["start"].tolist(), cut["end"].tolist(), cut["offset"].tolist(),
+                                 cut["strand"].tolist())), text
+                    cuts += cut["n_seqs"]
+            native.close()
+    finally:
+        logging.disable(logging.NOTSET)
+    assert cuts > 20
