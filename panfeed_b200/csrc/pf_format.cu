@@ -419,6 +419,17 @@ extern "C" int pf_pack_4bit(const char* ascii, const uint64_t* seq_off, uint32_t
 // hashes_to_patterns rows (panfeed.py:183-187,217-223): id, then one field per sample:
 // '0' / '1', or empty where the vector holds NaN (cluster absent, --consider-missing).
 // ---------------------------------------------------------------------------
+namespace {
+struct OctetLut {                                  // the fields of eight samples: tab + '0' / '1', bit 0 first
+  char t[256][16];
+  OctetLut() {
+    for (int b = 0; b < 256; ++b)
+      for (int j = 0; j < 8; ++j) { t[b][2 * j] = '\t'; t[b][2 * j + 1] = (char)('0' + ((b >> j) & 1)); }
+  }
+};
+const OctetLut kOctet;
+}  // namespace
+
 extern "C" int pf_format_patterns(const uint32_t* pattern_words, uint64_t n, uint32_t stride_words,
                                   uint32_t n_samples, const char* ids, const uint32_t* present_words,
                                   uint32_t present_stride, char* out, uint64_t out_cap, uint64_t* out_len,
@@ -467,7 +478,11 @@ extern "C" int pf_format_patterns(const uint32_t* pattern_words, uint64_t n, uin
           p += 1 + present;
         }
       } else {
-        for (uint32_t s = 0; s < n_samples; ++s) {
+        // eight samples per table look-up: "\t0\t1..." of a byte of presence bits (bit 0 first)
+        uint32_t s = 0;
+        for (; s + 8 <= n_samples; s += 8, p += 16)
+          memcpy(p, kOctet.t[(bits[s >> 5] >> (s & 31u)) & 255u], 16);
+        for (; s < n_samples; ++s) {
           *p++ = '\t';
           *p++ = (char)('0' + ((bits[s >> 5] >> (s & 31u)) & 1u));
         }
