@@ -193,6 +193,30 @@ struct CJob {
   const char* lead_blob;
   const uint64_t* lead_off;
 };
+// A coordinate that moves by one from row to row, kept as its decimal text: a step touches the
+// last digit (and the carry's) instead of dividing the number down again.  Anything unusual - a
+// negative value, a change of the number of digits - goes through put_int.
+struct DecCounter {
+  char text[24];
+  int len = 0;
+  int64_t v = 0;
+  void set(int64_t x) { v = x; len = put_int(text, x); }
+  void step(int d) {                                 // d = +1 or -1
+    const int64_t nv = v + d;
+    if (v > 0 && nv > 0) {
+      int i = len - 1;
+      if (d > 0) {
+        while (i >= 0 && text[i] == '9') text[i--] = '0';
+        if (i >= 0) { ++text[i]; v = nv; return; }
+      } else {
+        while (i >= 0 && text[i] == '0') text[i--] = '9';
+        if (i > 0 || (i == 0 && text[0] > '1') || len == 1) { --text[i]; v = nv; return; }
+      }
+    }
+    set(nv);                                         // (the digits touched above are rewritten in full)
+  }
+  char* put(char* o) const { for (int i = 0; i < len; ++i) o[i] = text[i]; return o + len; }
+};
 inline bool strand_bit(const CJob& j, const pf_seq_desc& q, uint32_t p) {
   const uint64_t i = q.base_off + p;
   return (j.bits[i >> 5] >> (i & 31u)) & 1u;
@@ -217,8 +241,8 @@ inline char* write_seq_rows(const CJob& j, uint32_t si, char* p) {
   const uint32_t nwin = q.len - j.k + 1, k = j.k;
   const uint64_t lead = j.lead_off[si + 1] - j.lead_off[si];
   const char* lead_p = j.lead_blob + j.lead_off[si];
-  // the sequence's symbols once, windows are slices of it
-  std::vector<char> text((size_t)q.len);
+  // the sequence's symbols once, and their reverse complement once: windows are slices of both
+  std::vector<char> text((size_t)q.len), rc_text((size_t)q.len);
   if (q.flags & PF_SEQ_AMBIGUOUS) {
     for (uint32_t s = 0; s < q.len; ++s) {
       const uint64_t i = q.amb_off + s;
@@ -230,38 +254,47 @@ inline char* write_seq_rows(const CJob& j, uint32_t si, char* p) {
       text[s] = kAcgt[(j.b->packed_bases[i >> 5] >> (62 - 2 * (i & 31u))) & 3u];
     }
   }
+  for (uint32_t s = 0; s < q.len; ++s) rc_text[s] = comp_symbol(text[q.len - 1 - s]);
+  // the four coordinates of a row move by one from window to window
+  const int dir = q.strand > 0 ? 1 : -1;
+  DecCounter c_lo, c_hi, g_lo, g_hi;
+  {
+    const int64_t c0 = q.strand > 0 ? (int64_t)q.start : (int64_t)q.end - k, g0 = -(int64_t)q.offset;
+    c_lo.set(c0); c_hi.set(c0 + k); g_lo.set(g0); g_hi.set(g0 + k);
+  }
+  char strand_fwd[24], strand_rev[24];
+  const int sf = put_int(strand_fwd, q.strand), sr = put_int(strand_rev, -(int64_t)q.strand);
   for (uint32_t w = 0; w < nwin; ++w) {
-    const int64_t c0 = q.strand > 0 ? (int64_t)q.start + w : (int64_t)q.end - w - k, g0 = (int64_t)w - q.offset;
     auto head = [&](char* o) {
       memcpy(o, lead_p, lead);
       o += lead;
-      o += put_int(o, c0); *o++ = '\t';
-      o += put_int(o, c0 + k); *o++ = '\t';
-      o += put_int(o, g0); *o++ = '\t';
-      o += put_int(o, g0 + k); *o++ = '\t';
+      o = c_lo.put(o); *o++ = '\t';
+      o = c_hi.put(o); *o++ = '\t';
+      o = g_lo.put(o); *o++ = '\t';
+      o = g_hi.put(o); *o++ = '\t';
       return o;
     };
     const char* fwd = text.data() + w;
+    const char* rev = rc_text.data() + (q.len - w - k);        // reverse complement of window w
     if (j.canonical) {
       const bool rc = strand_bit(j, q, w);
       p = head(p);
       if (rc) { *p++ = '-'; *p++ = '1'; } else { *p++ = '1'; }
       *p++ = '\t';
-      if (rc) for (uint32_t s = 0; s < k; ++s) p[s] = comp_symbol(fwd[k - 1 - s]);
-      else memcpy(p, fwd, k);
+      memcpy(p, rc ? rev : fwd, k);
       p += k;
       *p++ = '\n';
     } else {
       p = head(p);
-      p += put_int(p, q.strand); *p++ = '\t';
+      memcpy(p, strand_fwd, sf); p += sf; *p++ = '\t';
       memcpy(p, fwd, k); p += k;
       *p++ = '\n';
       p = head(p);
-      p += put_int(p, -(int64_t)q.strand); *p++ = '\t';
-      for (uint32_t s = 0; s < k; ++s) p[s] = comp_symbol(fwd[k - 1 - s]);
-      p += k;
+      memcpy(p, strand_rev, sr); p += sr; *p++ = '\t';
+      memcpy(p, rev, k); p += k;
       *p++ = '\n';
     }
+    c_lo.step(dir); c_hi.step(dir); g_lo.step(1); g_hi.step(1);
   }
   return p;
 }

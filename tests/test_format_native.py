@@ -251,9 +251,16 @@ def test_native_compact_position_rows_match_python(k, canonical, threads):
     seqs["len"] = [len(s) for s in seqs_txt]
     seqs["flags"] = (rng.random(n_seqs) < 0.7) * capi.PF_SEQ_TARGET + is_amb * capi.PF_SEQ_AMBIGUOUS
     seqs["start"] = rng.integers(1, 4_000_000, n_seqs)
-    seqs["end"] = seqs["start"] + seqs["len"] - 1
     seqs["offset"] = rng.integers(0, 120, n_seqs)
     seqs["strand"] = rng.choice([1, -1], n_seqs)
+    # coordinates that run through a change of their number of digits, upwards and downwards
+    # (the formatter steps decimal texts from row to row), and through zero
+    edge = [1, 5, 9, 95, 995, 9_990, 99_995, 999_990, 1, 8, 99, 950, 9_900, 99_900]
+    ne = min(len(edge), n_seqs)
+    seqs["start"][:ne] = edge[:ne]
+    seqs["strand"][:ne] = ([1, -1] * len(edge))[:ne]
+    seqs["offset"][:ne] = ([0, 3, 10, 99, 100, 101, 7] * 2)[:ne]
+    seqs["end"] = seqs["start"] + seqs["len"] - 1
     hb = capi.HostBatch(packed, seqs, np.zeros(1, capi.CLUSTER_DTYPE), np.zeros((1, 1), np.uint32), amb_plane)
     leads = [f"cl{i % 4}\tstrain_{i}\tgene{i}\tctg{i % 3}\t{int(seqs['strand'][i])}\t".encode() for i in range(n_seqs)]
     # the bit plane the device would return: 1 where the reverse complement is the canonical k-mer
