@@ -407,6 +407,11 @@ int pf_exchange_scatter(pf_ctx* ctx, int cluster_namespace, uint32_t world,
                         pointers, the own buffer or pf_exchange_open_peer mappings */,
                         const uint64_t* dest_row0 /* [world] */);
 
+/* Pattern ids as text (host threads): out[24 * i ..] = base64 of the 16-byte digest i, as
+ * binascii.b2a_base64(md5(...).digest())[:24] gives them (panfeed.py:175-176, 206-207). */
+int pf_base64_ids(const uint8_t* digests /* [n][16], pf_pattern_ids */, uint64_t n, char* out /* [n][24] */,
+                  uint32_t n_threads);
+
 /* ---- native feeder (host threads of the caller): GFF3 + FASTA -> cut sequences of a cluster ----
  * Replaces, for the feeding side of the path, the reference's parse_gff (input.py:274-332), its
  * pyfaidx contigs (input.py:262-266) and the per-strain loop of iter_gene_clusters

@@ -139,7 +139,7 @@ EXPORTS = ["pf_create", "pf_destroy", "pf_last_error", "pf_abi_version",
            "pf_reset_patterns", "pf_pattern_words", "pf_kmer_pattern_words",
            "pf_maf_window", "pf_patterns_export", "pf_pattern_ids", "pf_stats_get", "pf_struct_size", "pf_stream", "pf_format_positions",
            "pf_format_positions_compact",
-           "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_format_patterns", "pf_format_kmer_rows", "pf_gzip_members",
+           "pf_pack_plan", "pf_pack_2bit", "pf_pack_4bit", "pf_base64_ids", "pf_format_patterns", "pf_format_kmer_rows", "pf_gzip_members",
            "pf_feeder_create", "pf_feeder_destroy", "pf_feeder_last_error", "pf_feeder_add_genome", "pf_feeder_add_genomes",
            "pf_feeder_add_genome_text", "pf_feeder_genome_info", "pf_feeder_feature", "pf_feeder_contig", "pf_feeder_cut",
            "pf_feeder_cut_packed",
@@ -215,6 +215,7 @@ def load():
                                   C.POINTER(u64), u32]
     lib.pf_free.argtypes = [vp]
     lib.pf_free.restype = None
+    lib.pf_base64_ids.argtypes = [vp, u64, vp, u32]
     lib.pf_pack_plan.argtypes = [vp, u32, vp, C.POINTER(u64)]
     lib.pf_pack_2bit.argtypes = [vp, vp, u32, vp, vp, vp, u32]          # ascii: bytes or a raw address
     lib.pf_pack_4bit.argtypes = [vp, vp, u32, vp, vp, vp, C.POINTER(u64), C.POINTER(C.c_int)]
@@ -515,8 +516,20 @@ def _np(ptr, n, dtype, copy=True):
 _B64 = np.frombuffer(b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/", np.uint8)
 
 
-def base64_ids(digests):
-    """[n,16] uint8 MD5 digests -> numpy S24 array of base64 strings (with '==')."""
+def base64_ids(digests, n_threads=0):
+    """[n,16] uint8 MD5 digests -> numpy S24 array of base64 strings (with '=='): pf_base64_ids,
+    library host threads (millions of ids per batch)."""
+    digests = np.ascontiguousarray(digests, dtype=np.uint8).reshape(-1, 16)
+    out = np.empty(len(digests), "S24")
+    if len(digests):
+        rc = load().pf_base64_ids(digests.ctypes.data, len(digests), out.ctypes.data, int(n_threads))
+        if rc != 0:
+            raise PfError(rc, "pf_base64_ids failed")
+    return out
+
+
+def base64_ids_numpy(digests):
+    """The same with numpy (the tests compare the two)."""
     d = np.zeros((len(digests), 18), np.uint32)
     d[:, :16] = digests
     t = (d[:, 0::3] << 16) | (d[:, 1::3] << 8) | d[:, 2::3]            # [n, 6] 24-bit groups

@@ -722,6 +722,30 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
 }
 
 // ---------------------------------------------------------------------------
+// Pattern ids: base64 of the 16-byte MD5 digests K5 computed (panfeed.py:175-176, 206-207:
+// binascii.b2a_base64(md5(vector bytes).digest())[:24]) - 24 characters, the last two '='.
+// ---------------------------------------------------------------------------
+extern "C" int pf_base64_ids(const uint8_t* digests, uint64_t n, char* out, uint32_t n_threads) {
+  if (n && (!digests || !out)) return PF_ERR_INVALID;
+  if (n >= (1ull << 32)) return PF_ERR_INVALID;
+  static const char* kB64 = "ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789+/";
+  parallel_for((uint32_t)n, n_threads, [&](uint32_t a, uint32_t b) {
+    for (uint32_t i = a; i < b; ++i) {
+      const uint8_t* d = digests + (size_t)i * 16;
+      char* o = out + (size_t)i * 24;
+      for (int g = 0; g < 5; ++g) {
+        const uint32_t t = ((uint32_t)d[3 * g] << 16) | ((uint32_t)d[3 * g + 1] << 8) | d[3 * g + 2];
+        o[4 * g] = kB64[t >> 18]; o[4 * g + 1] = kB64[(t >> 12) & 63]; o[4 * g + 2] = kB64[(t >> 6) & 63];
+        o[4 * g + 3] = kB64[t & 63];
+      }
+      const uint32_t t = (uint32_t)d[15] << 16;               // the 16th byte and two bytes of padding
+      o[20] = kB64[t >> 18]; o[21] = kB64[(t >> 12) & 63]; o[22] = '='; o[23] = '=';
+    }
+  });
+  return PF_OK;
+}
+
+// ---------------------------------------------------------------------------
 // --compress: the reference opens its three outputs with gzip.open(..., "wt", compresslevel=9)
 // (input.py:235-259) and deflates every row on the one writer process; with --cores > 2 its
 // writers interleave and the file is corrupt.  Here a text buffer is cut into

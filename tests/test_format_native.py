@@ -287,3 +287,17 @@ def test_native_compact_position_rows_match_python(k, canonical, threads):
                 want.append(f"{head}{st}\t{fwd}\n{head}{-st}\t{rc}\n")
     got = capi.format_positions_compact(hb, bits if canonical else None, k, canonical, leads, n_threads=threads)
     assert got.decode() == "".join(want)
+
+
+def test_native_base64_ids_match_python():
+    """pf_base64_ids (the text of the pattern ids, panfeed.py:175-176: b2a_base64(md5)[:24])
+    against Python's base64 and the numpy rendering."""
+    import base64
+    rng = np.random.default_rng(3)
+    d = rng.integers(0, 256, (70_000, 16)).astype(np.uint8)
+    d[0], d[1] = 0, 255
+    for threads in (1, 0):
+        ids = capi.base64_ids(d, threads)
+        assert ids.dtype == np.dtype("S24") and (ids == capi.base64_ids_numpy(d)).all()
+        assert [bytes(x) for x in ids[:50]] == [base64.b64encode(x.tobytes()) for x in d[:50]]
+    assert capi.base64_ids(d[:0]).shape == (0,)
