@@ -201,7 +201,9 @@ def _run_batch(store, ctx, hb, meta, idxs, S, k, canonical, consider_missing):
     texts, kmers_to_hashes text) as bytes / uint8 arrays; the arrays are the formatters' reused
     buffers, to be written out before the next batch."""
     ctx.submit(hb)
-    r = ctx.collect()
+    # views of the context's pinned result buffers (valid until the next collect): everything below
+    # reads them before this function returns; what outlives the batch is copied explicitly
+    r = ctx.collect(copy=False)
 
     # ---- new patterns -> ids (MD5 on the device, K5) + hashes_to_patterns rows.  The pattern
     #      tables are keyed on the full vector, so every new pattern is a new id: nothing is
