@@ -567,6 +567,33 @@ struct QuadLut {                                   // the four bases of a byte o
   }
 };
 const QuadLut kQuad;
+
+// (k-mer, row) pairs in k-mer order, ties by row.  Rows enter in ascending row order, so a STABLE
+// sort on the k-mer alone keeps the ties right: least-significant-digit radix passes of 11 bits
+// over the `bits` the k-mers use (6 passes for k = 31; a comparison sort of a few thousand random
+// keys mispredicts every other branch).  Small inputs go to std::sort.
+inline void sort_keyed(std::vector<KeyedRow>& v, std::vector<KeyedRow>& tmp, uint32_t bits) {
+  const size_t n = v.size();
+  if (n < 256) {
+    std::sort(v.begin(), v.end(), [](const KeyedRow& a, const KeyedRow& b) {
+      return a.kmer != b.kmer ? a.kmer < b.kmer : a.row < b.row;
+    });
+    return;
+  }
+  tmp.resize(n);
+  KeyedRow* src = v.data();
+  KeyedRow* dst = tmp.data();
+  uint32_t count[2048];
+  for (uint32_t shift = 0; shift < bits; shift += 11) {
+    memset(count, 0, sizeof count);
+    for (size_t i = 0; i < n; ++i) ++count[(src[i].kmer >> shift) & 2047u];
+    uint32_t at = 0;
+    for (uint32_t d = 0; d < 2048; ++d) { const uint32_t c = count[d]; count[d] = at; at += c; }
+    for (size_t i = 0; i < n; ++i) dst[count[(src[i].kmer >> shift) & 2047u]++] = src[i];
+    std::swap(src, dst);
+  }
+  if (src != v.data()) memcpy(v.data(), src, n * sizeof(KeyedRow));
+}
 }  // namespace
 
 extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const char* tag_blob,
@@ -650,7 +677,7 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
   std::atomic<uint32_t> next{0};
   std::atomic<uint32_t> bad_pattern{0};
   auto work = [&]() {
-    std::vector<KeyedRow> keyed;
+    std::vector<KeyedRow> keyed, scratch;
     for (;;) {
       const uint32_t c = next.fetch_add(1);
       if (c >= nc) return;
@@ -668,9 +695,7 @@ extern "C" int pf_format_kmer_rows(const pf_batch_result* r, uint32_t k, const c
       bool ok = true;
       for (uint32_t j = 0; j < n; ++j) ok &= r->row_pattern[keyed[j].row] < n_kmer_ids;
       if (!ok) { bad_pattern.store(1); continue; }
-      std::sort(keyed.begin(), keyed.end(), [](const KeyedRow& a, const KeyedRow& b) {
-        return a.kmer != b.kmer ? a.kmer < b.kmer : a.row < b.row;
-      });
+      sort_keyed(keyed, scratch, 2 * k);
       uint32_t* ow = order_w.data() + first_w[c];
       const uint32_t n_w = first_w[c + 1] - first_w[c];
       std::sort(ow, ow + n_w, [&](uint32_t a, uint32_t b) {
