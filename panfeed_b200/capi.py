@@ -314,11 +314,12 @@ def _scratch(name, nbytes):
     return buf
 
 
-def format_patterns(words, n_samples, ids, present=None, n_threads=0, raw=False):
+def format_patterns(words, n_samples, ids, present=None, n_threads=0, raw=False, scratch="patterns"):
     """hashes_to_patterns text (bytes) of the patterns `words` ([n, >= W] uint32) with their
     24-character ids; `present` ([n, >= W] uint32) marks the samples whose cell is not NaN.
     raw=True (all three formatters): a uint8 view of a buffer that the next call of the same
-    formatter reuses, for callers that write the text out at once."""
+    formatter (here: with the same `scratch` name) reuses, for callers that write the text out
+    at once."""
     lib = load()
     words = np.ascontiguousarray(words, dtype=np.uint32)
     n = len(words)
@@ -336,7 +337,7 @@ def format_patterns(words, n_samples, ids, present=None, n_threads=0, raw=False)
     rc = lib.pf_format_patterns(*args, None, 0, C.byref(need), int(n_threads))
     if rc != 0:
         raise PfError(rc, "pf_format_patterns (sizing) failed")
-    out = _scratch("patterns", need.value)
+    out = _scratch(scratch, need.value)
     rc = lib.pf_format_patterns(*args, out.ctypes.data_as(C.c_char_p), out.size, C.byref(need), int(n_threads))
     if rc != 0:
         raise PfError(rc, "pf_format_patterns failed")

@@ -215,7 +215,7 @@ def _run_batch(store, ctx, hb, meta, idxs, S, k, canonical, consider_missing):
         store.cluster_ids.append(new_ids)
         store.cluster_bits.append(new_cp.copy())
         if not store.sharded:
-            pat_text.append(capi.format_patterns(new_cp, S, new_ids))
+            pat_text.append(capi.format_patterns(new_cp, S, new_ids, raw=True, scratch="cluster_patterns"))
             store.n_patterns += len(new_cp)
     new_kp = r["new_kmer_patterns"]
     if len(new_kp):
@@ -226,7 +226,7 @@ def _run_batch(store, ctx, hb, meta, idxs, S, k, canonical, consider_missing):
             present = None
             if consider_missing:      # NaN cells = samples whose cluster is absent (the key's last word
                 present = store.cluster_planes()[new_kp[:, W].astype(np.int64)]   # names that cluster pattern)
-            pat_text.append(capi.format_patterns(new_kp, S, new_ids, present))
+            pat_text.append(capi.format_patterns(new_kp, S, new_ids, present, raw=True, scratch="kmer_patterns"))
             store.n_patterns += len(new_kp)
 
     # ---- kmers_to_hashes rows, cluster by cluster: formatted by the library's host threads
