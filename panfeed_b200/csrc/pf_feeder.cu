@@ -123,7 +123,7 @@ bool read_text(const char* path, FileText* out) {
   if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
     void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);
     if (m != MAP_FAILED) {
-      madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+      // (no MADV_SEQUENTIAL: the pages are read again, at random, when windows are cut)
       out->p = (char*)m;
       out->n = out->mapped = (size_t)st.st_size;
     }
