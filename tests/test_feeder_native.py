@@ -577,6 +577,15 @@ def test_native_feeder_fuzz_against_python_feeder(tmp_path):
                         list(zip(cut["start"].tolist(), cut["end"].tolist(), cut["offset"].tolist(),
                                  cut["strand"].tolist())), text
                     cuts += cut["n_seqs"]
+                    # the same windows packed on the spot (contigs in place or copied, two threads)
+                    pk = native.cut(np.zeros(1, np.uint32) + g, ";".join(ids).encode(), up, down, dsc, prepack=True,
+                                    n_threads=2)
+                    ref = capi.pack_blob(cut["ascii"], cut["seq_off"])
+                    assert (pk["packed"] == ref[0]).all() and (pk["base_off"] == ref[1]).all(), text
+                    assert (pk["is_amb"] == ref[2]).all() and (pk["amb_off"] == ref[4]).all(), text
+                    assert (pk["amb_plane"] is None) == (ref[3] is None), text
+                    if ref[3] is not None:
+                        assert (pk["amb_plane"] == ref[3]).all(), text
             native.close()
     finally:
         logging.disable(logging.NOTSET)
