@@ -1,12 +1,15 @@
 """Native feeder: GFF3/FASTA parsing and per-cluster sequence cutting in the library
 (`pf_feeder_*`, csrc/pf_feeder.cu) instead of the Python loops of `input.py`.
 
-`prep_feeder` stands where `input.prep_data_n_fasta` does (reference input.py:68-138) and
+`PanarooTable` stands where the `genepres` DataFrame does (reference input.py:198-201),
+`prep_feeder` where `input.prep_data_n_fasta` does (input.py:68-138) and `iter_packed_batches` /
 `iter_packed_clusters` where `iter_gene_clusters` + `cluster_cutter` do (input.py:335-468,
-panfeed.py:23-113): it yields the 4-tuples `pattern_hasher` consumes, with a `NativePackedCluster`
-whose sequences are one ASCII blob the native packer reads without a Python object per
-sequence.  The Python path stays the behavioural reference; `tests/test_feeder_native.py`
-checks that both produce identical batches on the fixture genomes.
+panfeed.py:23-113): they yield the 4-tuples `pattern_hasher` consumes - whole GPU batches cut and
+packed by one library call (`NativePackedBatch`, the CLI's default), or one `NativePackedCluster`
+per panaroo row (`--multiple-files`).  `prefetch` runs either on a background thread.  The
+Python path (`--python-feeder`) stays the behavioural reference; `tests/test_feeder_native.py`
+checks that both produce identical batches on the fixture genomes, on hand-written quirks and
+on random GFF3 / FASTA / table text.
 """
 import ctypes as C
 import logging

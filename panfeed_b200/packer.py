@@ -128,7 +128,8 @@ class SeqMeta:
 
 def pack_batch(packed_clusters, cluster_ids=None):
     """-> (capi.HostBatch, seq_meta (SeqMeta), cluster idx list).  Clusters are
-    `PackedCluster`s (Python cutting) or `feeder.NativePackedCluster`s (one ASCII blob each)."""
+    `PackedCluster`s (Python cutting) or `feeder.NativePackedCluster`s (slices of the planes the
+    library packed when it cut them)."""
     # planes: clusters the native feeder packed at cutting time bring their word ranges; runs of
     # clusters that still hold ASCII sequences are packed here; the pieces are then laid end to end
     # (every sequence starts on a 64-base boundary, so that equals packing everything at once)
