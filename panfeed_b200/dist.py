@@ -372,5 +372,7 @@ class PatternExchange:
                          "owned_base": int(sum(c[:self.rank])), "bytes_sent": p["bytes_sent"],
                          "ms": {"total_both_namespaces": ms, "stages": stages}}
             if want_unique:
+                # (each namespace keeps its owner-side unique keys in its OWN scratch - PatternSpace::x_unique
+                #  of ctx->cp / ctx->kp - so the k-mer exchange has not overwritten the cluster namespace's)
                 out[name]["owned_keys"] = be.unique_keys(p["ns"])
         return out
